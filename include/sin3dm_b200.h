@@ -1,0 +1,150 @@
+/*
+ * sin3dm_b200 — C ABI of the B200-native triplane denoising path.
+ *
+ * The reference (Sin3DM) has no FFI layer: its boundary for this path is two Python classes,
+ *   TriplaneUNetModelSmall / ...SmallRaw   (reference src/diffusion/unet_triplane.py:315-510, 513-702)
+ *   GaussianDiffusion / SpacedDiffusion     (reference src/diffusion/gaussian_diffusion.py:102-947,
+ *                                            src/diffusion/respace.py:63-128)
+ * The entry points below are what a ctypes binding of those classes needs (INTEGRATION.md shows the stub);
+ * `sin3dm_b200/` is that binding.  Plain pointers and sizes only — no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; s3d_last_error() gives the message
+ *     (thread-local).  No call synchronises the host with the device unless stated.
+ *   - `*_dev` pointers are device pointers BORROWED from the caller (contiguous fp32, NCHW at the
+ *     boundary: [B, C, H+D, W+D] "composed" triplane, reference src/utils/triplane_util.py:7-25).
+ *     Weights are copied / re-packed into memory owned by the handle.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef SIN3DM_B200_H
+#define SIN3DM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3D_MAX_LEVELS 8
+#define S3D_NCOEF 12
+
+typedef struct s3d_unet s3d_unet;
+
+/* Constructor arguments of the reference UNet (unet_triplane.py:346-357) + implementation knobs. */
+typedef struct {
+    int in_channels;
+    int model_channels;            /* must be a multiple of 64 for the tcgen05 path */
+    int out_channels;
+    int num_res_blocks;            /* the reference only runs with 1 */
+    int n_levels;
+    int channel_mult[S3D_MAX_LEVELS];
+    int use_scale_shift_norm;      /* FiLM (unet_triplane.py:285-297) vs additive embedding */
+    int rollout;                   /* 1: TriplaneUNetModelSmall, 0: ...SmallRaw */
+    int precision;                 /* 3: fp16 hi/lo split, 3 MMAs (fp32-grade, default); 1: single fp16 MMA */
+    int conv_impl;                 /* 0: tcgen05 implicit GEMM; 1: CUDA-core debug kernel */
+} s3d_unet_config;
+
+int s3d_abi_version(void);
+const char* s3d_last_error(void);
+
+/* ---- UNet (replaces TriplaneUNetModelSmall[Raw].__init__/load_state_dict/forward) ---- */
+int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out);
+int s3d_unet_destroy(s3d_unet* u);
+/* Expected checkpoint tensors, in reference state_dict() order. */
+int s3d_unet_num_tensors(const s3d_unet* u);
+int s3d_unet_tensor_info(const s3d_unet* u, int index, const char** name, int* ndim, int64_t shape[4]);
+/* Copy one fp32 tensor (host memory, contiguous, reference layout) by its state_dict key. */
+int s3d_unet_load_tensor(s3d_unet* u, const char* name, const float* host_data, const int64_t* shape, int ndim);
+/* Re-pack everything loaded so far for the kernels (fp16 hi/lo K-major conv operands, folded rollout
+ * weights, concatenated FiLM projection).  Fails if a tensor is missing.  Synchronises the device. */
+int s3d_unet_finalize(s3d_unet* u);
+/* Row width of the per-timestep conditioning vector produced by the embedding MLPs
+ * (time_embed + every block's emb_layers, unet_triplane.py:232-238, 371-375). */
+int s3d_unet_film_dim(const s3d_unet* u);
+/* film[n][film_dim] for n timesteps (fp32 values, already mapped through timestep_map / rescaled). */
+int s3d_unet_film(s3d_unet* u, const float* t_dev, int n, float* film_dev, void* stream);
+/* forward(x, timesteps, H, W, D) -> out (same shape as x with out_channels). */
+int s3d_unet_forward(s3d_unet* u, const float* x_dev, const float* t_dev, float* out_dev, int B, int H, int W, int D,
+                     void* stream);
+/* Same, with the conditioning rows precomputed: sample b uses film_dev[row_dev ? row_dev[b] : b]. */
+int s3d_unet_forward_film(s3d_unet* u, const float* x_dev, const float* film_dev, const int* row_dev, float* out_dev,
+                          int B, int H, int W, int D, void* stream);
+/* Kernel launches issued by the last forward (for bench accounting). */
+int s3d_unet_last_launches(const s3d_unet* u);
+
+/* ---- scheduler step (replaces p_sample / ddim_sample / ddim_reverse_sample element-wise math) ----
+ * coef_dev is [T][S3D_NCOEF] fp32, built by the host mirror from the fp64 tables exactly as
+ * _extract_into_tensor rounds them (gaussian_diffusion.py:934-947):
+ *   0 sqrt_recip_alphas_cumprod   1 sqrt_recipm1_alphas_cumprod   2 posterior_mean_coef1
+ *   3 posterior_mean_coef2        4 exp(0.5*model_log_variance)    5 sqrt(alpha_bar_prev)
+ *   6 sqrt(1-alpha_bar_prev-sigma^2)  7 ddim sigma (eta folded)   8 sqrt(alpha_bar_next)
+ *   9 sqrt(1-alpha_bar_next)     10 sqrt_alphas_cumprod           11 sqrt_one_minus_alphas_cumprod */
+enum { S3D_DDPM = 0, S3D_DDIM = 1, S3D_DDIM_REVERSE = 2 };
+enum { S3D_START_X = 0, S3D_EPSILON = 1 };
+
+typedef struct {
+    int kind;               /* S3D_DDPM / S3D_DDIM / S3D_DDIM_REVERSE */
+    int mean_type;          /* S3D_START_X / S3D_EPSILON */
+    int clip_denoised;
+    int is_mask_t0;
+    int B;
+    int64_t n_per_sample;   /* C*(H+D)*(W+D) */
+    const float* model_out; /* [B, n] */
+    const float* x;         /* [B, n] x_t */
+    const float* noise;     /* [B, n] or NULL -> Philox4x32-10 keyed (seed, sample_base+b, t_idx[b]) */
+    const float* y0;        /* optional inpainting target (ddim_sample y0/mask), NULL if unused */
+    const float* mask;
+    float* sample;          /* [B, n] may alias x */
+    float* pred_xstart;     /* [B, n] or NULL */
+    const float* coef_dev;  /* [T][S3D_NCOEF] */
+    const int* t_idx_dev;   /* [B] step index into coef_dev */
+    uint64_t seed;
+    uint32_t sample_base;
+} s3d_sched_args;
+
+int s3d_sched_step(const s3d_sched_args* a, void* stream);
+/* q_sample: x_t = coef[t][10]*x0 + coef[t][11]*noise (gaussian_diffusion.py:189-207). */
+int s3d_q_sample(const float* x0_dev, const float* noise_dev, float* out_dev, const float* coef_dev, const int* t_idx_dev,
+                 int B, int64_t n_per_sample, void* stream);
+/* N(0,1) fill with the same counter-based generator the sampler uses (noise of sample s at step i). */
+int s3d_philox_normal(float* out_dev, int B, int64_t n_per_sample, uint64_t seed, uint32_t sample_base, uint32_t step,
+                      void* stream);
+
+/* ---- whole sampling loop (replaces p_sample_loop / ddim_sample_loop, gaussian_diffusion.py:442-536, 640-734) ----
+ * Runs i = n_steps-1 .. 0 on the device: UNet forward + scheduler step per iteration, captured once as a
+ * CUDA graph and replayed; the step index lives in device memory, so there is no per-step host work. */
+typedef struct {
+    int kind;               /* S3D_DDPM / S3D_DDIM */
+    int mean_type;
+    int clip_denoised;
+    int is_mask_t0;
+    int n_steps;
+    int B, H, W, D;
+    float* x_dev;           /* in: x_T, out: final sample (in place) [B, C, H+D, W+D] */
+    float* pred_xstart_dev; /* optional */
+    const float* coef_dev;  /* [n_steps][S3D_NCOEF] */
+    const float* film_dev;  /* [n_steps][film_dim] conditioning of step index i (already timestep_map'ed) */
+    const float* step_noise_dev; /* NULL -> Philox; else [n_steps][B][n] with row i used at step index i */
+    const float* y0_dev;
+    const float* mask_dev;
+    uint64_t seed;
+    uint32_t sample_base;   /* global index of sample 0 of this batch (multi-GPU sharding) */
+    int use_graph;          /* 1: CUDA graph replay, 0: plain launches */
+} s3d_loop_args;
+
+int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream);
+
+/* ---- test / bring-up hooks (not part of the drop-in surface) ----
+ * After a forward, intermediate fp32 activations of the last plan can be read back by name
+ * ("in_conv", "<block>.h1", "<block>.out", "down.<l>", "upcat.<j>"); plane 0/1/2 = xy/xz/yz, layout
+ * [B][rows][cols][C].  Synchronises the device.  tests/ use it to localise a failing kernel. */
+int s3d_unet_debug_count(const s3d_unet* u);
+int s3d_unet_debug_info(const s3d_unet* u, int index, const char** name, int* channels, int rows[3], int cols[3],
+                        int* batch);
+int s3d_unet_debug_read(s3d_unet* u, int index, int plane, float* host_out, int64_t n_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIN3DM_B200_H */

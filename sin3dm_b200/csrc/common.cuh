@@ -1,0 +1,89 @@
+// Shared device-side types and helpers for the triplane denoising kernels.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace s3d {
+
+// Planes: 0 = xy [H,W], 1 = xz [H,D], 2 = yz [W,D]  (reference src/utils/triplane_util.py:20-25).
+struct TriDims {
+    int rows[3];
+    int cols[3];
+};
+struct TriF {
+    float* p[3];
+};
+struct TriCF {
+    const float* p[3];
+};
+struct TriH {
+    __half* p[3];
+};
+struct TriCH {
+    const __half* p[3];
+};
+
+constexpr int kGroups = 32;        // GroupNorm32(32, C), reference src/diffusion/nn.py:93-100
+constexpr float kGnEps = 1e-5f;    // torch.nn.GroupNorm default
+constexpr float kLoScale = 2048.f; // lo = (v - fp16(v)) * 2^11 keeps the residual in fp16 normal range
+
+__device__ __forceinline__ float silu_f(float v) {
+    // x * sigmoid(x), reference src/diffusion/nn.py:12-14.  ex2.approx + rcp: ~1e-6 relative.
+    return __fdividef(v, 1.f + __expf(-v));
+}
+
+// fp32 -> (hi, lo) fp16 pair with v ~= hi + lo / 2048, |err| <= 2^-22 |v| (saturating)
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
+}
+
+__device__ __forceinline__ void store_split4(__half* hi_ptr, __half* lo_ptr, float4 v) {
+    __half h[4], l[4];
+    split_f16(v.x, h[0], l[0]);
+    split_f16(v.y, h[1], l[1]);
+    split_f16(v.z, h[2], l[2]);
+    split_f16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi_ptr) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo_ptr) = *reinterpret_cast<uint2*>(l);
+}
+
+// Composed-layout address of plane pixel (r, c): [H+D, W+D] with yz stored transposed.
+__device__ __forceinline__ int composed_offset(int plane, int r, int c, int H, int W, int Wc) {
+    if (plane == 0) return r * Wc + c;
+    if (plane == 1) return r * Wc + W + c;
+    return (H + c) * Wc + r;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 (oracle/philox_ref.py)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// 4 standard normals for counter (idx4, step, sample, stream)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t sample, uint32_t step, uint32_t idx4) {
+    uint4 r = philox4x32_10(make_uint4(idx4, step, sample, 0u),
+                            make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    const float s = 2.3283064365386963e-10f;   // 2^-32
+    float u0 = fminf(__fmul_rn(__fadd_rn(__uint2float_rn(r.x), 1.f), s), 1.f);
+    float u1 = fminf(__fmul_rn(__fadd_rn(__uint2float_rn(r.y), 1.f), s), 1.f);
+    float u2 = fminf(__fmul_rn(__fadd_rn(__uint2float_rn(r.z), 1.f), s), 1.f);
+    float u3 = fminf(__fmul_rn(__fadd_rn(__uint2float_rn(r.w), 1.f), s), 1.f);
+    float rad0 = sqrtf(-2.f * logf(u0)), rad1 = sqrtf(-2.f * logf(u2));
+    const float two_pi = 6.283185307179586f;
+    float s0, c0, s1, c1;
+    sincosf(two_pi * u1, &s0, &c0);
+    sincosf(two_pi * u3, &s1, &c1);
+    return make_float4(rad0 * c0, rad0 * s0, rad1 * c1, rad1 * s1);
+}
+
+}  // namespace s3d

@@ -1,0 +1,230 @@
+// 3x3 (+ fused 1x1 skip) triplane convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+//   reference: TriplaneConv.forward, src/diffusion/unet_triplane.py:31-60 (the per-plane nn.Conv2d 3x3, pad 1)
+//              + TriplaneResBlock skip_connection 1x1 (unet_triplane.py:255, 308-311)
+//
+// GEMM view (per plane, per sample):  D[pixel, co] = sum_{tap, c} A[pixel + tap, c] * W[co, tap*C + c]
+//   M tile  = 128 pixels = an 8 x 16 image patch; the A operand of tap (kh, kw) is the same patch shifted by
+//             (kh-1, kw-1), fetched by ONE 5-D TMA box {64 ch, 16, 8, 1, 1} whose out-of-bounds elements
+//             (negative / >= size coordinates) are zero-filled by the TMA unit == the conv's zero padding.
+//   N tile  = 64 output channels, K chunk = 64 input channels of one tap (128 B rows, SWIZZLE_128B).
+//   The rollout's broadcast channels never enter this GEMM (folded into the 1-D terms added in the epilogue).
+//
+// Precision: operands are fp16 (hi, lo) pairs, v = hi + lo/2048.  NSPLIT == 3 issues
+//   D1 += Ah*Bh ; D2 += Al*Bh ; D2 += Ah*Bl      (tcgen05.mma kind::f16, fp32 accumulate in TMEM)
+// and the epilogue forms D1 + D2/2048 (error ~2^-22, i.e. fp32-grade).  NSPLIT == 1 issues only Ah*Bh.
+//
+// Warp roles (192 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> +bias +rollout 1-D terms +residual -> fp32 NHWC).
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace s3d {
+
+constexpr int kTileH = 8, kTileW = 16;
+constexpr int kBM = 128, kBN = 64, kBK = 64;
+constexpr int kABytes = kBM * kBK * 2;   // 16 KiB
+constexpr int kBBytes = kBN * kBK * 2;   //  8 KiB
+constexpr int kConvThreads = 192;
+
+struct ConvTcMaps {
+    CUtensorMap a[3];   // activations  (C, cols, rows, B, 2) fp16
+    CUtensorMap x[3];   // skip input   (Cs, cols, rows, B, 2) fp16 (unused when Cs == 0)
+    CUtensorMap w[3];   // weights      (Ktot, Cout, 2) fp16, K = tap*C + c, then the Cs skip channels
+};
+
+struct ConvTcArgs {
+    TriDims d;
+    int C, Cout, Cs;
+    int tiles_x[3];
+    int tile_start[4];   // prefix sum of tiles per plane
+    ConvEpi e;
+};
+
+template <int NSPLIT>
+struct ConvTcCfg {
+    static constexpr int kStageBytes = (NSPLIT == 3 ? 2 : 1) * (kABytes + kBBytes);
+    static constexpr int kStages = NSPLIT == 3 ? 4 : 8;
+    static constexpr int kTmemCols = NSPLIT == 3 ? 128 : 64;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_constant__ ConvTcMaps M, const ConvTcArgs A) {
+    using Cfg = ConvTcCfg<NSPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- tile decode (warp-uniform)
+    int plane = 0;
+    if (static_cast<int>(blockIdx.x) >= A.tile_start[1]) plane = 1;
+    if (static_cast<int>(blockIdx.x) >= A.tile_start[2]) plane = 2;
+    const int t_in_plane = blockIdx.x - A.tile_start[plane];
+    const int ty = t_in_plane / A.tiles_x[plane], tx = t_in_plane - ty * A.tiles_x[plane];
+    const int h0 = ty * kTileH, w0 = tx * kTileW;
+    const int n0 = blockIdx.y * kBN;
+    const int b = blockIdx.z;
+    const int cblks = A.C / kBK;
+    const int nk_main = 9 * cblks;
+    const int nk = nk_main + A.Cs / kBK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&M.a[plane]);
+        ptx::prefetch_tmap(&M.w[plane]);
+        if (A.Cs) ptx::prefetch_tmap(&M.x[plane]);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < Cfg::kStages; ++s) {
+                ptx::mbar_init(&full_bar[s], 1);
+                ptx::mbar_init(&empty_bar[s], 1);
+            }
+            ptx::mbar_init(tmem_full_bar, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::kStages;
+                const uint32_t ph = (i / Cfg::kStages) & 1;
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* st = smem + s * Cfg::kStageBytes;
+                ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                const CUtensorMap* amap;
+                int c0, wc, hc;
+                if (i < nk_main) {
+                    const int tap = i / cblks, cb = i - tap * cblks;
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    amap = &M.a[plane];
+                    c0 = cb * kBK; wc = w0 + kw - 1; hc = h0 + kh - 1;
+                } else {
+                    amap = &M.x[plane];
+                    c0 = (i - nk_main) * kBK; wc = w0; hc = h0;
+                }
+                ptx::tma_load_5d(st, amap, &full_bar[s], c0, wc, hc, b, 0);
+                ptx::tma_load_3d(st + kABytes, &M.w[plane], &full_bar[s], i * kBK, n0, 0);
+                if (NSPLIT == 3) {
+                    ptx::tma_load_5d(st + kABytes + kBBytes, amap, &full_bar[s], c0, wc, hc, b, 1);
+                    ptx::tma_load_3d(st + 2 * kABytes + kBBytes, &M.w[plane], &full_bar[s], i * kBK, n0, 1);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, kBN);
+            const uint32_t d1 = tmem_base, d2 = tmem_base + kBN;
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::kStages;
+                const uint32_t ph = (i / Cfg::kStages) & 1;
+                ptx::mbar_wait(&full_bar[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t st = ptx::smem_u32(smem + s * Cfg::kStageBytes);
+                const uint64_t a_hi = ptx::make_sw128_kmajor_desc(st);
+                const uint64_t b_hi = ptx::make_sw128_kmajor_desc(st + kABytes);
+                const uint64_t a_lo = ptx::make_sw128_kmajor_desc(st + kABytes + kBBytes);
+                const uint64_t b_lo = ptx::make_sw128_kmajor_desc(st + 2 * kABytes + kBBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);   // +32 B along K inside the swizzle atom
+                    const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+                    ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
+                    if (NSPLIT == 3) {
+                        ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, acc);
+                        ptx::umma_f16(d2, a_hi + ko, b_lo + ko, idesc, 1u);
+                    }
+                }
+                ptx::umma_commit(&empty_bar[s]);      // frees this smem stage once the MMAs above retire
+            }
+            ptx::umma_commit(tmem_full_bar);          // accumulators complete
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int m = quarter * 32 + lane;
+        const int r = h0 + (m >> 4), c = w0 + (m & 15);
+        const int rows = A.d.rows[plane], cols = A.d.cols[plane];
+        const bool valid = r < rows && c < cols;
+        ptx::mbar_wait(tmem_full_bar, 0);
+        __syncwarp();
+        ptx::tc_fence_after();
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const size_t px = static_cast<size_t>(b) * rows * cols + static_cast<size_t>(r) * cols + c;
+        const float* bias = A.e.bias.p[plane] + n0;
+        const float* trow = nullptr;
+        const float* tcol = nullptr;
+        if (A.e.Trow.p[plane] && valid) {
+            const size_t bo = static_cast<size_t>(b) * 4;
+            trow = A.e.Trow.p[plane] + ((bo + edge_class(c, cols)) * rows + r) * A.Cout + n0;
+            tcol = A.e.Tcol.p[plane] + ((bo + edge_class(r, rows)) * cols + c) * A.Cout + n0;
+        }
+        const float* resid = (A.e.resid.p[plane] && valid) ? A.e.resid.p[plane] + px * A.Cout + n0 : nullptr;
+        const float* emb = A.e.embadd ? A.e.embadd + static_cast<size_t>(A.e.film_row ? A.e.film_row[b] : b) * A.e.film_dim +
+                                            A.e.film_off + n0
+                                      : nullptr;
+        float* outp = A.e.out.p[plane] + px * A.Cout + n0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v1[32], v2[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
+            if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
+            ptx::tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float acc = __uint_as_float(v1[j + q]);
+                        if (NSPLIT == 3) acc = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, acc);
+                        o[q] = acc;
+                    }
+                    const int cc = half * 32 + j;
+                    float4 t = __ldg(reinterpret_cast<const float4*>(bias + cc));
+                    o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+                    if (trow) {
+                        t = __ldg(reinterpret_cast<const float4*>(trow + cc));
+                        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+                        t = __ldg(reinterpret_cast<const float4*>(tcol + cc));
+                        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+                    }
+                    if (emb) {
+                        t = __ldg(reinterpret_cast<const float4*>(emb + cc));
+                        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+                    }
+                    if (resid) {
+                        t = __ldg(reinterpret_cast<const float4*>(resid + cc));
+                        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+                    }
+                    *reinterpret_cast<float4*>(outp + cc) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+}  // namespace s3d

@@ -1,0 +1,695 @@
+// Bandwidth-bound / small kernels of the triplane UNet and the scheduler.
+// Activations: per-plane NHWC fp32 residual stream [B][rows][cols][C]; conv operands are fp16
+// (hi, lo) pairs laid out [2][B][rows][cols][C] so one 5-D TMA map serves both halves.
+#pragma once
+#include "common.cuh"
+
+namespace s3d {
+
+// =====================================================================================
+// in_conv: per-plane 1x1 conv straight off the composed NCHW boundary tensor.
+// reference src/diffusion/unet_triplane.py:378 (TriplaneConv k=1, no rollout) + triplane_util.py:20-25
+// grid (ceil(max_px/32), 3, B), block 256
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, TriDims d, int H, int W, int Dd, int Cin,
+                                                 int Cout, TriCF w, TriCF bias, TriF out) {
+    extern __shared__ float xs[];   // [Cin][32]
+    const int plane = blockIdx.y, b = blockIdx.z;
+    const int npx = d.rows[plane] * d.cols[plane];
+    const int px0 = blockIdx.x * 32;
+    if (px0 >= npx) return;
+    const int Hc = H + Dd, Wc = W + Dd;
+    const float* xb = x + static_cast<size_t>(b) * Cin * Hc * Wc;
+    for (int i = threadIdx.x; i < Cin * 32; i += blockDim.x) {
+        int c = i >> 5, p = i & 31, px = px0 + p;
+        float v = 0.f;
+        if (px < npx) {
+            int r = px / d.cols[plane], cc = px - r * d.cols[plane];
+            v = xb[static_cast<size_t>(c) * Hc * Wc + composed_offset(plane, r, cc, H, W, Wc)];
+        }
+        xs[i] = v;
+    }
+    __syncthreads();
+    const float* wp = w.p[plane];
+    const float* bp = bias.p[plane];
+    float* op = out.p[plane] + static_cast<size_t>(b) * npx * Cout;
+    for (int i = threadIdx.x; i < 32 * Cout; i += blockDim.x) {
+        int p = i / Cout, co = i - p * Cout, px = px0 + p;
+        if (px >= npx) continue;
+        float acc = bp[co];
+        for (int c = 0; c < Cin; ++c) acc = fmaf(wp[co * Cin + c], xs[c * 32 + p], acc);
+        op[static_cast<size_t>(px) * Cout + co] = acc;
+    }
+}
+
+// =====================================================================================
+// GroupNorm statistics (deterministic two-level reduction, fp64 combine).
+// reference src/diffusion/nn.py:17-19 (GroupNorm32 computes in fp32), unet_triplane.py:63-84
+// grid (chunks, 3, B), block (C/4, NY); partial [B][3][chunks][32][2] double; ticket [B][3]
+// stats out [B][3][32][2] = (mean, rstd)
+// =====================================================================================
+template <int NY>
+__global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, int chunks, double* __restrict__ partial,
+                           unsigned int* __restrict__ ticket, float* __restrict__ stats) {
+    extern __shared__ float red[];   // [NY][2][C]
+    __shared__ bool is_last;
+    const int plane = blockIdx.y, b = blockIdx.z, chunk = blockIdx.x;
+    const int npx = d.rows[plane] * d.cols[plane];
+    const int ppc = (npx + chunks - 1) / chunks;
+    const int p0 = chunk * ppc, p1 = min(npx, p0 + ppc);
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const float* xp = x.p[plane] + static_cast<size_t>(b) * npx * C;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (int px = p0 + ty; px < p1; px += NY) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(xp + static_cast<size_t>(px) * C) + tx);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+    float* rs = red + (ty * 2 + 0) * C + tx * 4;
+    float* rq = red + (ty * 2 + 1) * C + tx * 4;
+    rs[0] = s.x; rs[1] = s.y; rs[2] = s.z; rs[3] = s.w;
+    rq[0] = q.x; rq[1] = q.y; rq[2] = q.z; rq[3] = q.w;
+    __syncthreads();
+    const int tid = ty * blockDim.x + tx;
+    const int cpg = C / kGroups;
+    double* part = partial + ((static_cast<size_t>(b) * 3 + plane) * chunks + chunk) * kGroups * 2;
+    if (tid < kGroups) {
+        double ds = 0.0, dq = 0.0;
+        for (int y = 0; y < NY; ++y)
+            for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+                ds += static_cast<double>(red[(y * 2 + 0) * C + c]);
+                dq += static_cast<double>(red[(y * 2 + 1) * C + c]);
+            }
+        part[tid * 2 + 0] = ds;
+        part[tid * 2 + 1] = dq;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int prev = atomicAdd(&ticket[b * 3 + plane], 1u);
+        is_last = (prev == static_cast<unsigned int>(chunks - 1));
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid < kGroups) {
+        const volatile double* pp = partial + (static_cast<size_t>(b) * 3 + plane) * chunks * kGroups * 2;
+        double ds = 0.0, dq = 0.0;
+        for (int ch = 0; ch < chunks; ++ch) {
+            ds += pp[(ch * kGroups + tid) * 2 + 0];
+            dq += pp[(ch * kGroups + tid) * 2 + 1];
+        }
+        const double n = static_cast<double>(npx) * cpg;
+        const double mean = ds / n;
+        double var = dq / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float* st = stats + ((static_cast<size_t>(b) * 3 + plane) * kGroups + tid) * 2;
+        st[0] = static_cast<float>(mean);
+        st[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
+    }
+    if (tid == 0) ticket[b * 3 + plane] = 0u;   // re-arm for the next launch
+}
+
+// =====================================================================================
+// Fused GroupNorm-apply (+FiLM) + SiLU -> fp16 (hi, lo) conv operand, plus the rollout axis sums.
+// reference unet_triplane.py:63-95 (norm, SiLU), :285-297 (FiLM), :37-46 (axis means)
+// One CTA = TH full rows of one plane of one sample.  grid (max_strips, 3, B), block (C/4, NY).
+//   rowsum  [B][rows][C]           complete (sum over cols of the activation)
+//   colpart [B][strips][cols][C]   partial over this strip's rows (summed by k_roll1d, fixed order)
+// =====================================================================================
+struct GnSiluArgs {
+    TriCF x;          // fp32 [B][rows][cols][C]
+    TriDims d;
+    int C, TH;
+    const float* stats;       // [B][3][32][2]
+    TriCF gamma, beta;        // [C]
+    const float* film;        // [rows][film_dim] or nullptr
+    const int* film_row;      // [B] or nullptr (row = b)
+    int film_dim, film_off;   // scale at film_off, shift at film_off + C
+    TriH a;                   // out [2][B][rows][cols][C]
+    TriH x16;                 // optional raw copy of x as (hi, lo) for the 1x1 skip GEMM
+    TriF rowsum, colpart;     // nullptr when rollout is off
+};
+
+template <int NY, int TH_MAX>
+__global__ void __launch_bounds__(1024) k_gn_silu(GnSiluArgs A, int B) {
+    extern __shared__ float sm[];   // coefA[C], coefB[C], red[NY][TH_MAX][C]
+    const int plane = blockIdx.y, b = blockIdx.z;
+    const int rows = A.d.rows[plane], cols = A.d.cols[plane], C = A.C;
+    const int r0 = blockIdx.x * A.TH;
+    if (r0 >= rows) return;
+    const int nr = min(A.TH, rows - r0);
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
+    float* coefA = sm;
+    float* coefB = sm + C;
+    float* red = sm + 2 * C;
+    const int cpg = C / kGroups;
+    const float* st = A.stats + (static_cast<size_t>(b) * 3 + plane) * kGroups * 2;
+    const float* film = nullptr;
+    if (A.film) film = A.film + static_cast<size_t>(A.film_row ? A.film_row[b] : b) * A.film_dim + A.film_off;
+    for (int c = tid; c < C; c += nthr) {
+        float mean = st[(c / cpg) * 2], rstd = st[(c / cpg) * 2 + 1];
+        float g = A.gamma.p[plane][c] * rstd;
+        float o = A.beta.p[plane][c] - mean * g;
+        if (film) {
+            float sc = 1.f + film[c], sh = film[C + c];
+            g *= sc;
+            o = fmaf(o, sc, sh);
+        }
+        coefA[c] = g;
+        coefB[c] = o;
+    }
+    __syncthreads();
+    const float4 ca = *reinterpret_cast<const float4*>(coefA + tx * 4);
+    const float4 cb = *reinterpret_cast<const float4*>(coefB + tx * 4);
+    const size_t plane_elems = static_cast<size_t>(rows) * cols * C;
+    const size_t sample_off = static_cast<size_t>(b) * plane_elems;
+    const size_t lo_off = static_cast<size_t>(B) * plane_elems;
+    const float* xp = A.x.p[plane] + sample_off;
+    __half* ap = A.a.p[plane] + sample_off;
+    __half* xq = A.x16.p[plane] ? A.x16.p[plane] + sample_off : nullptr;
+    const bool sums = A.rowsum.p[plane] != nullptr;
+    float4 racc[TH_MAX];
+#pragma unroll
+    for (int r = 0; r < TH_MAX; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = ty; c < cols; c += NY) {
+        float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < TH_MAX; ++r) {
+            if (r < nr) {
+                const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
+                float4 v = __ldg(reinterpret_cast<const float4*>(xp + off));
+                if (xq) store_split4(xq + off, xq + lo_off + off, v);
+                float4 y;
+                y.x = silu_f(fmaf(v.x, ca.x, cb.x));
+                y.y = silu_f(fmaf(v.y, ca.y, cb.y));
+                y.z = silu_f(fmaf(v.z, ca.z, cb.z));
+                y.w = silu_f(fmaf(v.w, ca.w, cb.w));
+                store_split4(ap + off, ap + lo_off + off, y);
+                cacc.x += y.x; cacc.y += y.y; cacc.z += y.z; cacc.w += y.w;
+                racc[r].x += y.x; racc[r].y += y.y; racc[r].z += y.z; racc[r].w += y.w;
+            }
+        }
+        if (sums) {
+            float* cp = A.colpart.p[plane] +
+                        ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * cols + c) * C + tx * 4;
+            *reinterpret_cast<float4*>(cp) = cacc;
+        }
+    }
+    if (!sums) return;
+#pragma unroll
+    for (int r = 0; r < TH_MAX; ++r)
+        *reinterpret_cast<float4*>(red + (static_cast<size_t>(ty) * TH_MAX + r) * C + tx * 4) = racc[r];
+    __syncthreads();
+    for (int i = tid; i < nr * C; i += nthr) {
+        int r = i / C, c = i - r * C;
+        float acc = 0.f;
+        for (int y = 0; y < NY; ++y) acc += red[(static_cast<size_t>(y) * TH_MAX + r) * C + c];
+        A.rowsum.p[plane][(static_cast<size_t>(b) * rows + r0 + r) * C + c] = acc;
+    }
+}
+
+// =====================================================================================
+// Rollout 1-D terms.  Two thirds of a rollout conv's input channels are constant along one image
+// axis (unet_triplane.py:37-46), so their 3x3 conv collapses exactly to a 1-D conv along the other
+// axis, with the zero padding only distinguishing first / interior / last position across.
+//   T[b][cls][pos][co] = sum_{across in cls} sum_{along, c} mean[pos+along-1][c] * wr[along*C+c][across*Cout+co]
+//   cls: 0 interior {0,1,2}, 1 first {1,2}, 2 last {0,1}, 3 single {1}
+// grid (ceil(Lmax/8), 6, B): blockIdx.y = plane*2 + group.  block 256.
+// =====================================================================================
+struct Roll1dSrc {
+    const float* sum;   // rowsum [B][L][C] or colpart [B][nparts][L][C]
+    int nparts;         // 1 for rowsum
+    float inv_count;    // 1 / (length of the averaged axis)
+    int L;
+    const float* wr;    // [3*C][3*Cout]
+    float* T;           // [B][4][L][Cout]
+};
+struct Roll1dArgs {
+    Roll1dSrc s[6];
+    int C, Cout;
+};
+
+__global__ void __launch_bounds__(256) k_roll1d(Roll1dArgs A) {
+    constexpr int POS = 8;
+    extern __shared__ float sm[];     // src[(POS+2)][C], acc[POS][3*Cout]
+    const Roll1dSrc S = A.s[blockIdx.y];
+    const int b = blockIdx.z, C = A.C, Cout = A.Cout, N = 3 * Cout;
+    const int p0 = blockIdx.x * POS;
+    if (S.T == nullptr || p0 >= S.L) return;
+    float* src = sm;
+    float* accs = sm + (POS + 2) * C;
+    for (int i = threadIdx.x; i < (POS + 2) * C; i += blockDim.x) {
+        int j = i / C, c = i - j * C, pos = p0 + j - 1;
+        float v = 0.f;
+        if (pos >= 0 && pos < S.L) {
+            const float* base = S.sum + (static_cast<size_t>(b) * S.nparts * S.L + pos) * C + c;
+            for (int k = 0; k < S.nparts; ++k) v += base[static_cast<size_t>(k) * S.L * C];
+            v *= S.inv_count;
+        }
+        src[i] = v;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float acc[POS];
+#pragma unroll
+        for (int p = 0; p < POS; ++p) acc[p] = 0.f;
+        for (int al = 0; al < 3; ++al) {
+            const float* wcol = S.wr + static_cast<size_t>(al) * C * N + n;
+            const float* sp = src + al * C;      // src row (p + al) == position p + al - 1
+            for (int c = 0; c < C; ++c) {
+                float wv = __ldg(wcol + static_cast<size_t>(c) * N);
+#pragma unroll
+                for (int p = 0; p < POS; ++p) acc[p] = fmaf(sp[p * C + c], wv, acc[p]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < POS; ++p) accs[p * N + n] = acc[p];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < POS * Cout; i += blockDim.x) {
+        int p = i / Cout, co = i - p * Cout, pos = p0 + p;
+        if (pos >= S.L) continue;
+        float a0 = accs[p * N + co], a1 = accs[p * N + Cout + co], a2 = accs[p * N + 2 * Cout + co];
+        float* T = S.T + static_cast<size_t>(b) * 4 * S.L * Cout + static_cast<size_t>(pos) * Cout + co;
+        const size_t cs = static_cast<size_t>(S.L) * Cout;
+        T[0] = a0 + a1 + a2;
+        T[cs] = a1 + a2;
+        T[2 * cs] = a0 + a1;
+        T[3 * cs] = a1;
+    }
+}
+
+__device__ __forceinline__ int edge_class(int i, int n) {
+    return n == 1 ? 3 : (i == 0 ? 1 : (i == n - 1 ? 2 : 0));
+}
+
+// =====================================================================================
+// CUDA-core 3x3 conv on the same operands as the tcgen05 kernel (bring-up / cross-check path,
+// selected with conv_impl=1).  Uses the ORIGINAL fp32 weights, so it also checks the operand packing.
+// grid (ceil(max_px/4), 3, B), block (64, 4)
+// =====================================================================================
+struct ConvEpi {
+    TriCF bias;        // [Cout] (conv bias + skip-conv bias)
+    TriCF Trow, Tcol;  // [B][4][rows|cols][Cout] or nullptr
+    TriCF resid;       // fp32 [B][rows][cols][Cout] identity skip, or nullptr
+    const float* embadd;   // additive embedding (use_scale_shift_norm = False): film base, or nullptr
+    const int* film_row;
+    int film_dim, film_off;
+    TriF out;          // fp32 [B][rows][cols][Cout]
+};
+
+struct ConvFfmaArgs {
+    TriCH a;       // [2][B][rows][cols][C]
+    TriCH x16;     // [2][B][rows][cols][Cs] or nullptr
+    TriDims d;
+    int C, Cout, Cw, Cs;   // Cw = in-channels of the stored weight (3C with rollout, else C)
+    TriCF w;       // original [Cout][Cw][3][3]
+    TriCF wskip;   // original [Cout][Cs]
+    ConvEpi e;
+    int single;    // 1: ignore the lo halves (precision=1 emulation)
+};
+
+__global__ void __launch_bounds__(256) k_conv_ffma(ConvFfmaArgs A, int B) {
+    const int plane = blockIdx.y, b = blockIdx.z;
+    const int rows = A.d.rows[plane], cols = A.d.cols[plane];
+    const int npx = rows * cols;
+    const int px = blockIdx.x * 4 + threadIdx.y;
+    if (px >= npx) return;
+    const int r = px / cols, c = px - r * cols;
+    const size_t plane_elems = static_cast<size_t>(npx) * A.C;
+    const __half* ah = A.a.p[plane] + static_cast<size_t>(b) * plane_elems;
+    const __half* al = ah + static_cast<size_t>(B) * plane_elems;
+    const float inv = A.single ? 0.f : 1.f / kLoScale;
+    for (int co = threadIdx.x; co < A.Cout; co += 64) {
+        float acc = A.e.bias.p[plane][co];
+        const float* wp = A.w.p[plane] + static_cast<size_t>(co) * A.Cw * 9;
+        for (int kh = 0; kh < 3; ++kh) {
+            int rr = r + kh - 1;
+            if (rr < 0 || rr >= rows) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                int cc = c + kw - 1;
+                if (cc < 0 || cc >= cols) continue;
+                const size_t off = (static_cast<size_t>(rr) * cols + cc) * A.C;
+                for (int ci = 0; ci < A.C; ++ci) {
+                    float av = __half2float(ah[off + ci]) + __half2float(al[off + ci]) * inv;
+                    acc = fmaf(av, wp[(ci * 3 + kh) * 3 + kw], acc);
+                }
+            }
+        }
+        if (A.x16.p[plane]) {
+            const size_t pe = static_cast<size_t>(npx) * A.Cs;
+            const __half* xh = A.x16.p[plane] + static_cast<size_t>(b) * pe + static_cast<size_t>(px) * A.Cs;
+            const __half* xl = xh + static_cast<size_t>(B) * pe;
+            const float* ws = A.wskip.p[plane] + static_cast<size_t>(co) * A.Cs;
+            for (int ci = 0; ci < A.Cs; ++ci)
+                acc = fmaf(__half2float(xh[ci]) + __half2float(xl[ci]) * inv, ws[ci], acc);
+        }
+        if (A.e.Trow.p[plane]) {
+            const size_t bo = static_cast<size_t>(b) * 4;
+            acc += A.e.Trow.p[plane][((bo + edge_class(c, cols)) * rows + r) * A.Cout + co];
+            acc += A.e.Tcol.p[plane][((bo + edge_class(r, rows)) * cols + c) * A.Cout + co];
+        }
+        if (A.e.embadd)
+            acc += A.e.embadd[static_cast<size_t>(A.e.film_row ? A.e.film_row[b] : b) * A.e.film_dim + A.e.film_off + co];
+        const size_t oo = (static_cast<size_t>(b) * npx + px) * A.Cout + co;
+        if (A.e.resid.p[plane]) acc += A.e.resid.p[plane][oo];
+        A.e.out.p[plane][oo] = acc;
+    }
+}
+
+// =====================================================================================
+// 2x2 average pool, stride 2, floor on odd sizes.  reference unet_triplane.py:127-145
+// grid (ceil(max_out_px*C/4 / 256), 3, B)
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_avgpool2(TriCF x, TriDims din, TriDims dout, int C, TriF out) {
+    const int plane = blockIdx.y, b = blockIdx.z;
+    const int orows = dout.rows[plane], ocols = dout.cols[plane], icols = din.cols[plane];
+    const int c4 = C / 4;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= orows * ocols * c4) return;
+    const int v = i % c4, px = i / c4, r = px / ocols, c = px - r * ocols;
+    const float4* ip = reinterpret_cast<const float4*>(x.p[plane] + static_cast<size_t>(b) * din.rows[plane] * icols * C);
+    auto at = [&](int rr, int cc) { return __ldg(ip + (static_cast<size_t>(rr) * icols + cc) * c4 + v); };
+    float4 a = at(2 * r, 2 * c), b4 = at(2 * r, 2 * c + 1), c0 = at(2 * r + 1, 2 * c), d4 = at(2 * r + 1, 2 * c + 1);
+    float4 o;
+    o.x = (a.x + b4.x + c0.x + d4.x) * 0.25f;
+    o.y = (a.y + b4.y + c0.y + d4.y) * 0.25f;
+    o.z = (a.z + b4.z + c0.z + d4.z) * 0.25f;
+    o.w = (a.w + b4.w + c0.w + d4.w) * 0.25f;
+    reinterpret_cast<float4*>(out.p[plane] + static_cast<size_t>(b) * orows * ocols * C)[static_cast<size_t>(px) * c4 + v] = o;
+}
+
+// =====================================================================================
+// Bilinear x2 upsample (align_corners=False) [+ bilinear resize to the skip's size when they differ]
+// + channel concat with the skip.  reference unet_triplane.py:106-124, 494-503
+// out [B][rows][cols][Cu+Cs];  grid (ceil(max_px*(Cu+Cs)/4 / 256), 3, B)
+// =====================================================================================
+__device__ __forceinline__ void bilin_src(int dst, int in_size, float scale, int& i0, int& i1, float& l1) {
+    // ATen area_pixel_compute_source_index(align_corners=false): scale*(dst+0.5)-0.5 clamped at 0
+    float s = fmaxf(scale * (static_cast<float>(dst) + 0.5f) - 0.5f, 0.f);
+    i0 = min(static_cast<int>(s), in_size - 1);
+    i1 = min(i0 + 1, in_size - 1);
+    l1 = s - static_cast<float>(i0);
+}
+
+__global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, TriCF skip, int Cs, TriDims dout,
+                                               TriF out, int do_up) {
+    const int plane = blockIdx.y, b = blockIdx.z;
+    const int orows = dout.rows[plane], ocols = dout.cols[plane];
+    const int lrows = dlow.rows[plane], lcols = dlow.cols[plane];
+    const int Ct = Cu + Cs, c4 = Ct / 4;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= orows * ocols * c4) return;
+    const int v = i % c4, px = i / c4, r = px / ocols, c = px - r * ocols;
+    float4 o;
+    if (v * 4 >= Cu) {
+        const float4* sp = reinterpret_cast<const float4*>(skip.p[plane] + static_cast<size_t>(b) * orows * ocols * Cs);
+        o = __ldg(sp + static_cast<size_t>(px) * (Cs / 4) + (v - Cu / 4));
+    } else {
+        const float4* lp = reinterpret_cast<const float4*>(low.p[plane] + static_cast<size_t>(b) * lrows * lcols * Cu);
+        const int u4 = Cu / 4;
+        auto at = [&](int rr, int cc) { return __ldg(lp + (static_cast<size_t>(rr) * lcols + cc) * u4 + v); };
+        const int urows = do_up ? 2 * lrows : lrows, ucols = do_up ? 2 * lcols : lcols;
+        // value of the (virtual) x2-upsampled map at (ur, uc)
+        auto up_at = [&](int ur, int uc) {
+            if (!do_up) return at(ur, uc);
+            int r0, r1, c0, c1;
+            float lr, lc;
+            bilin_src(ur, lrows, 0.5f, r0, r1, lr);
+            bilin_src(uc, lcols, 0.5f, c0, c1, lc);
+            float4 a = at(r0, c0), bb = at(r0, c1), cc2 = at(r1, c0), dd = at(r1, c1);
+            float w00 = (1.f - lr) * (1.f - lc), w01 = (1.f - lr) * lc, w10 = lr * (1.f - lc), w11 = lr * lc;
+            float4 t;
+            t.x = w00 * a.x + w01 * bb.x + w10 * cc2.x + w11 * dd.x;
+            t.y = w00 * a.y + w01 * bb.y + w10 * cc2.y + w11 * dd.y;
+            t.z = w00 * a.z + w01 * bb.z + w10 * cc2.z + w11 * dd.z;
+            t.w = w00 * a.w + w01 * bb.w + w10 * cc2.w + w11 * dd.w;
+            return t;
+        };
+        if (urows == orows && ucols == ocols) {
+            o = up_at(r, c);
+        } else {
+            int r0, r1, c0, c1;
+            float lr, lc;
+            bilin_src(r, urows, static_cast<float>(urows) / static_cast<float>(orows), r0, r1, lr);
+            bilin_src(c, ucols, static_cast<float>(ucols) / static_cast<float>(ocols), c0, c1, lc);
+            float4 a = up_at(r0, c0), bb = up_at(r0, c1), cc2 = up_at(r1, c0), dd = up_at(r1, c1);
+            float w00 = (1.f - lr) * (1.f - lc), w01 = (1.f - lr) * lc, w10 = lr * (1.f - lc), w11 = lr * lc;
+            o.x = w00 * a.x + w01 * bb.x + w10 * cc2.x + w11 * dd.x;
+            o.y = w00 * a.y + w01 * bb.y + w10 * cc2.y + w11 * dd.y;
+            o.z = w00 * a.z + w01 * bb.z + w10 * cc2.z + w11 * dd.z;
+            o.w = w00 * a.w + w01 * bb.w + w10 * cc2.w + w11 * dd.w;
+        }
+    }
+    reinterpret_cast<float4*>(out.p[plane] + static_cast<size_t>(b) * orows * ocols * Ct)[static_cast<size_t>(px) * c4 + v] = o;
+}
+
+// =====================================================================================
+// out head: GroupNorm + SiLU + 1x1 conv (C -> Cout), written into the composed NCHW boundary tensor,
+// blockIdx.y == 3 zero-fills the D x D corner.  reference unet_triplane.py:441-445, triplane_util.py:7-17
+// grid (ceil(max(max_px, D*D)/128), 4, B), block 128 (one thread per pixel)
+// =====================================================================================
+__global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int Cout, const float* __restrict__ stats,
+                                                  TriCF gamma, TriCF beta, TriCF w, TriCF bias, float* __restrict__ out,
+                                                  int H, int W, int Dd) {
+    extern __shared__ float sm[];   // coefA[C], coefB[C], ws[Cout][C], bs[Cout]
+    const int plane = blockIdx.y, b = blockIdx.z;
+    const int Hc = H + Dd, Wc = W + Dd;
+    float* ob = out + static_cast<size_t>(b) * Cout * Hc * Wc;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (plane == 3) {
+        if (i < Dd * Dd) {
+            int r = i / Dd, c = i - r * Dd;
+            for (int co = 0; co < Cout; ++co) ob[(static_cast<size_t>(co) * Hc + H + r) * Wc + W + c] = 0.f;
+        }
+        return;
+    }
+    const int rows = d.rows[plane], cols = d.cols[plane], npx = rows * cols;
+    if (blockIdx.x * blockDim.x >= npx) return;
+    float* coefA = sm;
+    float* coefB = sm + C;
+    float* ws = sm + 2 * C;
+    float* bs = ws + Cout * C;
+    const int cpg = C / kGroups;
+    const float* st = stats + (static_cast<size_t>(b) * 3 + plane) * kGroups * 2;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float g = gamma.p[plane][c] * st[(c / cpg) * 2 + 1];
+        coefA[c] = g;
+        coefB[c] = beta.p[plane][c] - st[(c / cpg) * 2] * g;
+    }
+    for (int k = threadIdx.x; k < Cout * C; k += blockDim.x) ws[k] = w.p[plane][k];
+    for (int k = threadIdx.x; k < Cout; k += blockDim.x) bs[k] = bias.p[plane][k];
+    __syncthreads();
+    if (i >= npx) return;
+    const int r = i / cols, c = i - r * cols;
+    const float4* xp = reinterpret_cast<const float4*>(x.p[plane] + (static_cast<size_t>(b) * npx + i) * C);
+    float acc[16];
+    float* op = ob + composed_offset(plane, r, c, H, W, Wc);
+    for (int co0 = 0; co0 < Cout; co0 += 16) {
+        const int nco = min(16, Cout - co0);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = k < nco ? bs[co0 + k] : 0.f;
+        for (int v = 0; v < C / 4; ++v) {
+            float4 t = __ldg(xp + v);
+            float y0 = silu_f(fmaf(t.x, coefA[4 * v], coefB[4 * v]));
+            float y1 = silu_f(fmaf(t.y, coefA[4 * v + 1], coefB[4 * v + 1]));
+            float y2 = silu_f(fmaf(t.z, coefA[4 * v + 2], coefB[4 * v + 2]));
+            float y3 = silu_f(fmaf(t.w, coefA[4 * v + 3], coefB[4 * v + 3]));
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < nco) {
+                    const float* wk = ws + (co0 + k) * C + 4 * v;
+                    acc[k] = fmaf(y0, wk[0], fmaf(y1, wk[1], fmaf(y2, wk[2], fmaf(y3, wk[3], acc[k]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < nco) op[static_cast<size_t>(co0 + k) * Hc * Wc] = acc[k];
+    }
+}
+
+// =====================================================================================
+// Timestep conditioning: sinusoid -> Linear -> SiLU -> Linear -> (SiLU -> every block's Linear).
+// reference nn.py:103-121, unet_triplane.py:371-375, 232-238.   One warp per output scalar.
+// =====================================================================================
+__global__ void k_sinusoid(const float* __restrict__ t, const float* __restrict__ freqs, int half, float* __restrict__ out,
+                           int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * half) return;
+    const int r = i / half, k = i - r * half;
+    const float ang = __fmul_rn(t[r], freqs[k]);
+    out[static_cast<size_t>(r) * 2 * half + k] = cosf(ang);
+    out[static_cast<size_t>(r) * 2 * half + half + k] = sinf(ang);
+}
+
+// y[r][n] = bias[n] + sum_k W[n][k] * f(x[r][k]),  f = SiLU if silu_in.  grid (ceil(N/8), rows), block 256
+__global__ void __launch_bounds__(256) k_linear(const float* __restrict__ x, const float* __restrict__ W,
+                                                const float* __restrict__ bias, float* __restrict__ y, int K, int N,
+                                                int silu_in) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + warp, r = blockIdx.y;
+    if (n >= N) return;
+    const float* xr = x + static_cast<size_t>(r) * K;
+    const float* wr = W + static_cast<size_t>(n) * K;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        float v = xr[k];
+        if (silu_in) v = v / (1.f + expf(-v));
+        acc = fmaf(v, wr[k], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[static_cast<size_t>(r) * N + n] = acc + bias[n];
+}
+
+// =====================================================================================
+// Scheduler step: one vectorised pass over [B, n].  Op order and roundings mirror the reference's
+// fp32 tensor expressions (no FMA contraction), so with equal inputs the result is bit-identical.
+// reference gaussian_diffusion.py:294-315 (x0), :209-220 (posterior mean), :431-439 (DDPM sample),
+// :567-599 (DDIM), :626-636 (DDIM reverse).  Last CTA decrements t_idx when `advance` is set.
+// =====================================================================================
+struct SchedArgs {
+    int kind, mean_type, clip, is_mask_t0;
+    int B;
+    long long n;            // per sample, multiple of 4 not required
+    const float* model_out;
+    const float* x;
+    const float* noise;     // nullptr -> philox
+    const float* y0;
+    const float* mask;
+    float* sample;
+    float* x0_out;
+    const float* coef;      // [T][12]
+    int* t_idx;             // [B]
+    unsigned long long seed;
+    unsigned int sample_base;
+    int advance;            // loop mode: t_idx[b] -= 1 after the step (by the last CTA)
+    unsigned int* ticket;
+    long long noise_step_stride;   // loop mode with a noise buffer: noise + t*stride
+};
+
+__device__ __forceinline__ float sched_one(const SchedArgs& A, const float* cf, float nz, float out, float x, float nzv,
+                                           float y0, float mk, float& x0r) {
+    float x0;
+    if (A.mean_type == 0) {
+        x0 = out;
+    } else {
+        x0 = __fsub_rn(__fmul_rn(cf[0], x), __fmul_rn(cf[1], out));
+    }
+    if (A.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    float res;
+    if (A.kind == 0) {
+        float mean = __fadd_rn(__fmul_rn(cf[2], x0), __fmul_rn(cf[3], x));
+        res = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, cf[4]), nzv));
+    } else {
+        if (A.y0) {
+            float mix = __fadd_rn(__fmul_rn(mk, y0), __fmul_rn(__fsub_rn(1.f, mk), x0));
+            if (A.is_mask_t0) x0 = mix;
+            else x0 = __fadd_rn(__fmul_rn(mix, nz), __fmul_rn(x0, __fsub_rn(1.f, nz)));
+        }
+        float eps = __fdiv_rn(__fsub_rn(__fmul_rn(cf[0], x), x0), cf[1]);
+        if (A.kind == 1) {
+            float mean = __fadd_rn(__fmul_rn(x0, cf[5]), __fmul_rn(cf[6], eps));
+            res = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, cf[7]), nzv));
+        } else {
+            res = __fadd_rn(__fmul_rn(x0, cf[8]), __fmul_rn(cf[9], eps));
+        }
+    }
+    x0r = x0;
+    return res;
+}
+
+__global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
+    __shared__ bool is_last;
+    const int b = blockIdx.y;
+    const int t = A.t_idx[b];
+    float cf[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) cf[k] = __ldg(A.coef + static_cast<size_t>(t) * 12 + k);
+    const float nz = t != 0 ? 1.f : 0.f;
+    const size_t base = static_cast<size_t>(b) * A.n;
+    const float* noise = A.noise ? A.noise + static_cast<size_t>(t) * A.noise_step_stride + base : nullptr;
+    const long long n4 = (A.n + 3) / 4;
+    const bool vec = (A.n % 4) == 0;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float o[4], xv[4], nv[4], yv[4] = {0, 0, 0, 0}, mv[4] = {0, 0, 0, 0}, rs[4], x0[4];
+        const long long e0 = i * 4;
+        const int cnt = static_cast<int>(min(4LL, A.n - e0));
+        if (vec) {
+            float4 t4 = *reinterpret_cast<const float4*>(A.model_out + base + e0);
+            o[0] = t4.x; o[1] = t4.y; o[2] = t4.z; o[3] = t4.w;
+            t4 = *reinterpret_cast<const float4*>(A.x + base + e0);
+            xv[0] = t4.x; xv[1] = t4.y; xv[2] = t4.z; xv[3] = t4.w;
+        } else {
+            for (int k = 0; k < 4; ++k) {
+                o[k] = k < cnt ? A.model_out[base + e0 + k] : 0.f;
+                xv[k] = k < cnt ? A.x[base + e0 + k] : 0.f;
+            }
+        }
+        if (noise) {
+            for (int k = 0; k < 4; ++k) nv[k] = k < cnt ? noise[e0 + k] : 0.f;
+        } else if (A.kind != 2) {
+            float4 z = philox_normal4(A.seed, A.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(i));
+            nv[0] = z.x; nv[1] = z.y; nv[2] = z.z; nv[3] = z.w;
+        } else {
+            nv[0] = nv[1] = nv[2] = nv[3] = 0.f;
+        }
+        if (A.y0) {
+            for (int k = 0; k < 4; ++k) {
+                yv[k] = k < cnt ? A.y0[base + e0 + k] : 0.f;
+                mv[k] = k < cnt ? A.mask[base + e0 + k] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rs[k] = sched_one(A, cf, nz, o[k], xv[k], nv[k], yv[k], mv[k], x0[k]);
+        if (vec) {
+            *reinterpret_cast<float4*>(A.sample + base + e0) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+            if (A.x0_out) *reinterpret_cast<float4*>(A.x0_out + base + e0) = make_float4(x0[0], x0[1], x0[2], x0[3]);
+        } else {
+            for (int k = 0; k < cnt; ++k) {
+                A.sample[base + e0 + k] = rs[k];
+                if (A.x0_out) A.x0_out[base + e0 + k] = x0[k];
+            }
+        }
+    }
+    if (!A.advance) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(A.ticket, 1u);
+        is_last = prev == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        for (int k = 0; k < A.B; ++k) A.t_idx[k] -= 1;
+        *A.ticket = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_q_sample(const float* __restrict__ x0, const float* __restrict__ noise,
+                                                  float* __restrict__ out, const float* __restrict__ coef,
+                                                  const int* __restrict__ t_idx, long long n) {
+    const int b = blockIdx.y, t = t_idx[b];
+    const float a = coef[static_cast<size_t>(t) * 12 + 10], s = coef[static_cast<size_t>(t) * 12 + 11];
+    const size_t base = static_cast<size_t>(b) * n;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[base + i] = __fadd_rn(__fmul_rn(a, x0[base + i]), __fmul_rn(s, noise[base + i]));
+}
+
+__global__ void __launch_bounds__(256) k_philox_normal(float* __restrict__ out, long long n, unsigned long long seed,
+                                                       unsigned int sample_base, unsigned int step) {
+    const int b = blockIdx.y;
+    const long long n4 = (n + 3) / 4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float4 z = philox_normal4(seed, sample_base + b, step, static_cast<uint32_t>(i));
+        float zz[4] = {z.x, z.y, z.z, z.w};
+        for (int k = 0; k < 4 && i * 4 + k < n; ++k) out[static_cast<size_t>(b) * n + i * 4 + k] = zz[k];
+    }
+}
+
+}  // namespace s3d

@@ -1,0 +1,1181 @@
+// Host side of libsin3dm_b200: handle, checkpoint ingestion / operand packing, launch plan, C ABI.
+// See include/sin3dm_b200.h for the contract and the reference file:line each entry point replaces.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/sin3dm_b200.h"
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+using namespace s3d;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+    g_err = m;
+    return 1;
+}
+struct S3dError {
+    std::string msg;
+};
+#define S3D_CHECK(cond, msg)                                                      \
+    do {                                                                          \
+        if (!(cond)) throw S3dError{std::string(msg) + " (" #cond ")"};          \
+    } while (0)
+#define CUDA_TRY(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            throw S3dError{std::string(#expr) + ": " + cudaGetErrorName(_e) + ": " + cudaGetErrorString(_e)}; \
+    } while (0)
+#define LAUNCH_CHECK(name)                                                                 \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) throw S3dError{std::string("launch ") + name + ": " + cudaGetErrorString(_e)}; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ driver entry (TMA descriptors)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        S3D_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+// fp16 tensor, dims innermost-first, SWIZZLE_128B, zero OOB fill
+static void make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t bx[5], es[5];
+    uint64_t stride = 2;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstride[i] = stride;
+    }
+    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstride, bx, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw S3dError{"cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))};
+}
+
+// ------------------------------------------------------------------------------------ model description
+static const char* kPlane[3] = {"xy", "xz", "yz"};
+
+struct TensorSpec {
+    std::string name;
+    std::vector<int64_t> shape;
+    std::vector<float> host;
+    bool loaded = false;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+struct BlockSpec {       // one TriplaneResBlock (unet_triplane.py:175-311)
+    std::string name;
+    int cin, cout, level;
+    bool has_skip;
+    int film_off;        // offset of this block's emb_layers output inside a film row
+};
+struct OpSpec {
+    int kind;            // 0 res, 1 down, 2 up
+    int block;           // index into blocks for kind 0
+};
+
+struct DevConv3 {        // one 3x3 TriplaneConv (+ optional fused 1x1 skip)
+    int C = 0, Cout = 0, Cw = 0, Cs = 0, Ktot = 0;
+    float* w_orig[3] = {};      // [Cout][Cw][3][3]
+    float* wskip_orig[3] = {};  // [Cout][Cs]
+    __half* w_pack[3] = {};     // [2][Cout][Ktot]
+    float* wr[3][2] = {};       // rollout 1-D weights [3C][3Cout] per (plane, group)
+    float* bias[3] = {};        // conv bias (+ skip bias)
+};
+struct DevNorm {
+    float* gamma[3] = {};
+    float* beta[3] = {};
+};
+struct DevBlock {
+    DevNorm n1, n2;
+    DevConv3 c1, c2;
+};
+
+struct NamedBuf {
+    std::string name;
+    TriF p;
+    int C;
+    TriDims d;
+};
+
+struct Plan {
+    int B = 0, H = 0, W = 0, D = 0;
+    std::vector<std::function<void(cudaStream_t)>> ops;
+    std::vector<void*> allocs;
+    std::vector<NamedBuf> named;
+    float* film_own = nullptr;      // [B][film_dim] used by s3d_unet_forward
+    float* emb_tmp[3] = {};         // scratch for the embedding MLP (grown on demand)
+    int emb_rows = 0;
+    // per-call bindings read by the op lambdas at launch time
+    const float* x = nullptr;
+    float* out = nullptr;
+    const float* film = nullptr;
+    const int* film_row = nullptr;
+    // sampler-loop state
+    int* t_idx = nullptr;           // [B]
+    unsigned int* ticket = nullptr;
+    float* model_out = nullptr;     // [B][Cout][Hc][Wc]
+    cudaGraphExec_t graph_exec = nullptr;
+    std::string graph_key;
+};
+
+struct s3d_unet {
+    s3d_unet_config cfg;
+    int device = 0;
+    int emb_dim = 0, film_dim = 0;
+    std::vector<TensorSpec> tensors;
+    std::map<std::string, int> index;
+    std::vector<BlockSpec> blocks;
+    std::vector<std::vector<OpSpec>> downs, ups;
+    std::vector<int> level_ch;      // channels of the stream leaving each level (skip widths)
+    bool finalized = false;
+    // device weights
+    std::vector<void*> wallocs;
+    float *te_w0 = nullptr, *te_b0 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr, *film_w = nullptr, *film_b = nullptr;
+    float* freqs = nullptr;
+    float *in_w[3] = {}, *in_b[3] = {}, *out_w[3] = {}, *out_b[3] = {};
+    DevNorm out_norm;
+    std::vector<DevBlock> dblocks;
+    std::unique_ptr<Plan> plan;
+    int last_launches = 0;
+};
+
+static int ch_of(const s3d_unet_config& c, int level) { return c.channel_mult[level] * c.model_channels; }
+
+static void add_tensor(s3d_unet* u, const std::string& name, std::vector<int64_t> shape) {
+    u->index[name] = static_cast<int>(u->tensors.size());
+    TensorSpec t;
+    t.name = name;
+    t.shape = std::move(shape);
+    u->tensors.push_back(std::move(t));
+}
+static void add_linear(s3d_unet* u, const std::string& n, int i, int o) {
+    add_tensor(u, n + ".weight", {o, i});
+    add_tensor(u, n + ".bias", {o});
+}
+static void add_conv(s3d_unet* u, const std::string& n, int i, int o, int k) {
+    for (int p = 0; p < 3; ++p) {
+        add_tensor(u, n + ".conv_" + kPlane[p] + ".weight", {o, i, k, k});
+        add_tensor(u, n + ".conv_" + kPlane[p] + ".bias", {o});
+    }
+}
+static void add_norm(s3d_unet* u, const std::string& n, int c) {
+    for (int p = 0; p < 3; ++p) {
+        add_tensor(u, n + ".norm_" + kPlane[p] + ".weight", {c});
+        add_tensor(u, n + ".norm_" + kPlane[p] + ".bias", {c});
+    }
+}
+
+// Mirrors the constructor loops of the reference (unet_triplane.py:377-445) for num_res_blocks == 1.
+static void build_structure(s3d_unet* u) {
+    const auto& c = u->cfg;
+    const int L = c.n_levels, mc = c.model_channels, r = c.rollout ? 3 : 1;
+    u->emb_dim = 4 * mc;
+    add_linear(u, "time_embed.0", mc, u->emb_dim);
+    add_linear(u, "time_embed.2", u->emb_dim, u->emb_dim);
+    int ch = ch_of(c, 0);
+    add_conv(u, "in_conv.0", c.in_channels, ch, 1);
+    std::vector<int> chans{ch};
+    int film_off = 0;
+    auto add_block = [&](const std::string& name, int cin, int cout, int level) {
+        BlockSpec b{name, cin, cout, level, cin != cout, film_off};
+        film_off += c.use_scale_shift_norm ? 2 * cout : cout;
+        add_norm(u, name + ".in_layers.0", cin);
+        add_conv(u, name + ".in_layers.2", cin * r, cout, 3);
+        add_linear(u, name + ".emb_layers.1", u->emb_dim, c.use_scale_shift_norm ? 2 * cout : cout);
+        add_norm(u, name + ".out_layers.0", cout);
+        add_conv(u, name + ".out_layers.2", cout * r, cout, 3);
+        if (cin != cout) add_conv(u, name + ".skip_connection", cin, cout, 1);
+        u->blocks.push_back(b);
+        return static_cast<int>(u->blocks.size()) - 1;
+    };
+    for (int level = 0; level < L; ++level) {
+        std::vector<OpSpec> ops;
+        int idx = 0;
+        if (level != 0) {
+            ops.push_back({1, -1});
+            idx = 1;
+        }
+        const int cout = ch_of(c, level);
+        ops.push_back({0, add_block("input_blocks." + std::to_string(level) + "." + std::to_string(idx), ch, cout, level)});
+        ch = cout;
+        chans.push_back(ch);
+        u->downs.push_back(ops);
+    }
+    for (int j = 0; j < L; ++j) {
+        const int level = L - 1 - j;
+        std::vector<OpSpec> ops;
+        int ich = chans.back();
+        chans.pop_back();
+        if (level == L - 1) ich = 0;
+        const int cout = ch_of(c, level);
+        ops.push_back({0, add_block("output_blocks." + std::to_string(j) + ".0", ch + ich, cout, level)});
+        ch = cout;
+        if (level > 0) ops.push_back({2, -1});
+        u->ups.push_back(ops);
+    }
+    u->film_dim = film_off;
+    const int c0 = ch_of(c, 0);
+    add_norm(u, "out.0", c0);
+    add_conv(u, "out.2", c0, c.out_channels, 1);
+}
+
+// ------------------------------------------------------------------------------------ device memory helpers
+template <typename T>
+static T* dev_alloc(std::vector<void*>& owner, size_t n) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    owner.push_back(p);
+    return static_cast<T*>(p);
+}
+template <typename T>
+static T* dev_upload(std::vector<void*>& owner, const std::vector<T>& h) {
+    T* p = dev_alloc<T>(owner, h.size());
+    CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+static const TensorSpec& T_(const s3d_unet* u, const std::string& n) {
+    auto it = u->index.find(n);
+    if (it == u->index.end()) throw S3dError{"internal: unknown tensor " + n};
+    const TensorSpec& t = u->tensors[it->second];
+    if (!t.loaded) throw S3dError{"checkpoint tensor not loaded: " + n};
+    return t;
+}
+
+static uint16_t f2h_bits(float f) {
+    __half h = __float2half_rn(f);   // host-callable
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+static float h2f(uint16_t b) {
+    __half h;
+    memcpy(&h, &b, 2);
+    return __half2float(h);
+}
+
+// Pack one plane of a 3x3 conv (+ optional 1x1 skip) into [2][Cout][Ktot] fp16 (hi, lo*2048), K = tap*C + c.
+static std::vector<uint16_t> pack_conv(const std::vector<float>& w, int Cout, int Cw, int C, const std::vector<float>* wskip,
+                                       int Cs) {
+    const int Ktot = 9 * C + Cs;
+    std::vector<uint16_t> out(static_cast<size_t>(2) * Cout * Ktot);
+    auto put = [&](int co, int k, float v) {
+        float vc = std::min(std::max(v, -65504.f), 65504.f);
+        uint16_t hi = f2h_bits(vc);
+        uint16_t lo = f2h_bits((vc - h2f(hi)) * 2048.f);
+        out[static_cast<size_t>(co) * Ktot + k] = hi;
+        out[(static_cast<size_t>(Cout) + co) * Ktot + k] = lo;
+    };
+    for (int co = 0; co < Cout; ++co) {
+        for (int tap = 0; tap < 9; ++tap)
+            for (int c = 0; c < C; ++c) put(co, tap * C + c, w[(static_cast<size_t>(co) * Cw + c) * 9 + tap]);
+        for (int c = 0; c < Cs; ++c) put(co, 9 * C + c, (*wskip)[static_cast<size_t>(co) * Cs + c]);
+    }
+    return out;
+}
+// Rollout 1-D weights of group g (1 or 2) of one plane: wr[(along*C + c)][(across*Cout + co)].
+// row_varying: along = kh, across = kw;  col_varying: along = kw, across = kh.
+static std::vector<float> pack_roll(const std::vector<float>& w, int Cout, int C, int g, bool row_varying) {
+    const int Cw = 3 * C, N = 3 * Cout;
+    std::vector<float> out(static_cast<size_t>(3) * C * N);
+    for (int co = 0; co < Cout; ++co)
+        for (int c = 0; c < C; ++c)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float v = w[((static_cast<size_t>(co) * Cw + g * C + c) * 3 + kh) * 3 + kw];
+                    const int along = row_varying ? kh : kw, across = row_varying ? kw : kh;
+                    out[(static_cast<size_t>(along) * C + c) * N + across * Cout + co] = v;
+                }
+    return out;
+}
+// Which rollout group of which plane varies along rows (see kernels.cuh k_roll1d and unet_triplane.py:37-46):
+//   xy: g1 = mean_D(yz)^T  -> varies with column (W);  g2 = mean_D(xz) -> varies with row (H)
+//   xz: g1 = mean_W(xy)    -> row (H);                 g2 = mean_W(yz) -> column (D)
+//   yz: g1 = mean_H(xy)^T  -> row (W);                 g2 = mean_H(xz) -> column (D)
+static bool roll_row_varying(int plane, int g) { return plane == 0 ? g == 2 : g == 1; }
+
+static void upload_conv3(s3d_unet* u, DevConv3& d, const std::string& name, int C, int Cout, const std::string& skip_name,
+                         int Cs) {
+    const bool ro = u->cfg.rollout;
+    d.C = C;
+    d.Cout = Cout;
+    d.Cw = ro ? 3 * C : C;
+    d.Cs = Cs;
+    d.Ktot = 9 * C + Cs;
+    for (int p = 0; p < 3; ++p) {
+        const auto& w = T_(u, name + ".conv_" + kPlane[p] + ".weight").host;
+        std::vector<float> bias = T_(u, name + ".conv_" + kPlane[p] + ".bias").host;
+        const std::vector<float>* ws = nullptr;
+        if (Cs) {
+            ws = &T_(u, skip_name + ".conv_" + kPlane[p] + ".weight").host;
+            const auto& bs = T_(u, skip_name + ".conv_" + kPlane[p] + ".bias").host;
+            for (int i = 0; i < Cout; ++i) bias[i] += bs[i];
+            d.wskip_orig[p] = dev_upload(u->wallocs, *ws);
+        }
+        d.w_orig[p] = dev_upload(u->wallocs, w);
+        d.bias[p] = dev_upload(u->wallocs, bias);
+        auto packed = pack_conv(w, Cout, d.Cw, C, ws, Cs);
+        d.w_pack[p] = reinterpret_cast<__half*>(dev_upload(u->wallocs, packed));
+        if (ro)
+            for (int g = 1; g <= 2; ++g)
+                d.wr[p][g - 1] = dev_upload(u->wallocs, pack_roll(w, Cout, C, g, roll_row_varying(p, g)));
+    }
+}
+static void upload_norm(s3d_unet* u, DevNorm& n, const std::string& name) {
+    for (int p = 0; p < 3; ++p) {
+        n.gamma[p] = dev_upload(u->wallocs, T_(u, name + ".norm_" + kPlane[p] + ".weight").host);
+        n.beta[p] = dev_upload(u->wallocs, T_(u, name + ".norm_" + kPlane[p] + ".bias").host);
+    }
+}
+
+static void free_all(std::vector<void*>& v) {
+    for (void* p : v) cudaFree(p);
+    v.clear();
+}
+static void destroy_plan(s3d_unet* u) {
+    if (!u->plan) return;
+    if (u->plan->graph_exec) cudaGraphExecDestroy(u->plan->graph_exec);
+    free_all(u->plan->allocs);
+    u->plan.reset();
+}
+
+static void finalize(s3d_unet* u) {
+    CUDA_TRY(cudaSetDevice(u->device));
+    destroy_plan(u);
+    free_all(u->wallocs);
+    const auto& c = u->cfg;
+    u->te_w0 = dev_upload(u->wallocs, T_(u, "time_embed.0.weight").host);
+    u->te_b0 = dev_upload(u->wallocs, T_(u, "time_embed.0.bias").host);
+    u->te_w2 = dev_upload(u->wallocs, T_(u, "time_embed.2.weight").host);
+    u->te_b2 = dev_upload(u->wallocs, T_(u, "time_embed.2.bias").host);
+    // sinusoid frequencies (nn.py:113-116); the host mirror may override them through the "__freqs" pseudo tensor
+    const int half = c.model_channels / 2;
+    std::vector<float> fr(half);
+    auto it = u->index.find("__freqs");
+    if (it != u->index.end() && u->tensors[it->second].loaded) fr = u->tensors[it->second].host;
+    else
+        for (int i = 0; i < half; ++i) fr[i] = expf(static_cast<float>(-std::log(10000.0)) * static_cast<float>(i) / half);
+    u->freqs = dev_upload(u->wallocs, fr);
+    // concatenated emb_layers projection: film[n] = b[n] + W[n][:] . silu(emb)
+    std::vector<float> fw(static_cast<size_t>(u->film_dim) * u->emb_dim), fb(u->film_dim);
+    for (const auto& b : u->blocks) {
+        const auto& w = T_(u, b.name + ".emb_layers.1.weight").host;
+        const auto& bb = T_(u, b.name + ".emb_layers.1.bias").host;
+        std::copy(w.begin(), w.end(), fw.begin() + static_cast<size_t>(b.film_off) * u->emb_dim);
+        std::copy(bb.begin(), bb.end(), fb.begin() + b.film_off);
+    }
+    u->film_w = dev_upload(u->wallocs, fw);
+    u->film_b = dev_upload(u->wallocs, fb);
+    for (int p = 0; p < 3; ++p) {
+        u->in_w[p] = dev_upload(u->wallocs, T_(u, std::string("in_conv.0.conv_") + kPlane[p] + ".weight").host);
+        u->in_b[p] = dev_upload(u->wallocs, T_(u, std::string("in_conv.0.conv_") + kPlane[p] + ".bias").host);
+        u->out_w[p] = dev_upload(u->wallocs, T_(u, std::string("out.2.conv_") + kPlane[p] + ".weight").host);
+        u->out_b[p] = dev_upload(u->wallocs, T_(u, std::string("out.2.conv_") + kPlane[p] + ".bias").host);
+    }
+    upload_norm(u, u->out_norm, "out.0");
+    u->dblocks.assign(u->blocks.size(), DevBlock{});
+    for (size_t i = 0; i < u->blocks.size(); ++i) {
+        const auto& b = u->blocks[i];
+        DevBlock& d = u->dblocks[i];
+        upload_norm(u, d.n1, b.name + ".in_layers.0");
+        upload_norm(u, d.n2, b.name + ".out_layers.0");
+        upload_conv3(u, d.c1, b.name + ".in_layers.2", b.cin, b.cout, "", 0);
+        upload_conv3(u, d.c2, b.name + ".out_layers.2", b.cout, b.cout, b.name + ".skip_connection", b.has_skip ? b.cin : 0);
+    }
+    CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_gn_silu<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_gn_silu<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_gn_silu<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_out_head, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaDeviceSynchronize());
+    u->finalized = true;
+}
+
+// ------------------------------------------------------------------------------------ launch plan
+struct ActF {
+    TriF p;
+    int C = 0;
+    int level = 0;
+};
+struct Act16 {
+    TriH p;
+    int C = 0;
+};
+
+struct PlanBuilder {
+    s3d_unet* u;
+    Plan* P;
+    std::vector<TriDims> dims;   // per level
+    int B;
+
+    size_t px(int level, int plane) const { return static_cast<size_t>(dims[level].rows[plane]) * dims[level].cols[plane]; }
+    int max_px(int level) const { return static_cast<int>(std::max({px(level, 0), px(level, 1), px(level, 2)})); }
+
+    ActF allocF(int level, int C, const std::string& name) {
+        ActF a;
+        a.C = C;
+        a.level = level;
+        for (int p = 0; p < 3; ++p) a.p.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * px(level, p) * C);
+        if (!name.empty()) P->named.push_back({name, a.p, C, dims[level]});
+        return a;
+    }
+    Act16 alloc16(int level, int C) {
+        Act16 a;
+        a.C = C;
+        for (int p = 0; p < 3; ++p) a.p.p[p] = dev_alloc<__half>(P->allocs, static_cast<size_t>(2) * B * px(level, p) * C);
+        return a;
+    }
+    static TriCF cf(const TriF& t) { return TriCF{{t.p[0], t.p[1], t.p[2]}}; }
+    static TriCF cf3(float* const* t) { return TriCF{{t[0], t[1], t[2]}}; }
+
+    // ---- GroupNorm statistics
+    float* stats(const ActF& x) {
+        const int level = x.level, C = x.C;
+        S3D_CHECK(C % kGroups == 0 && C % 4 == 0 && C / 4 <= 128, "unsupported channel count for GroupNorm32");
+        const int chunks = std::max(1, std::min(64, max_px(level) / 64));
+        double* partial = dev_alloc<double>(P->allocs, static_cast<size_t>(B) * 3 * chunks * kGroups * 2);
+        unsigned int* ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3);
+        CUDA_TRY(cudaMemset(ticket, 0, sizeof(unsigned int) * B * 3));
+        float* st = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 3 * kGroups * 2);
+        TriCF xc = cf(x.p);
+        TriDims d = dims[level];
+        const int Bv = B;
+        P->ops.push_back([=](cudaStream_t s) {
+            dim3 grid(chunks, 3, Bv), block(C / 4, 8);
+            k_gn_stats<8><<<grid, block, sizeof(float) * 8 * 2 * C, s>>>(xc, d, C, chunks, partial, ticket, st);
+            LAUNCH_CHECK("k_gn_stats");
+        });
+        return st;
+    }
+
+    struct Sums {
+        TriF rowsum, colpart;
+        int strips[3];
+    };
+
+    // ---- GN apply + SiLU (+FiLM) -> fp16 operands (+ raw x16) (+ axis sums)
+    Sums gn_silu(const ActF& x, const float* st, const DevNorm& n, int film_off, const Act16& a, const Act16* x16) {
+        const int level = x.level, C = x.C;
+        const TriDims d = dims[level];
+        int ny = 16;
+        while ((C / 4) * ny > 1024) ny /= 2;
+        S3D_CHECK(ny >= 4, "channel count too large for k_gn_silu");
+        // rows per strip: aim for >= ~148 CTAs
+        const int total_rows = d.rows[0] + d.rows[1] + d.rows[2];
+        int TH = 4;
+        while (TH > 1 && (total_rows / TH) * B < 148) TH /= 2;
+        GnSiluArgs A{};
+        A.x = cf(x.p);
+        A.d = d;
+        A.C = C;
+        A.TH = TH;
+        A.stats = st;
+        A.gamma = cf3(n.gamma);
+        A.beta = cf3(n.beta);
+        A.film_dim = u->film_dim;
+        A.film_off = film_off;
+        A.a = a.p;
+        if (x16) A.x16 = x16->p;
+        Sums S{};
+        int max_strips = 0;
+        for (int p = 0; p < 3; ++p) {
+            S.strips[p] = (d.rows[p] + TH - 1) / TH;
+            max_strips = std::max(max_strips, S.strips[p]);
+        }
+        if (u->cfg.rollout) {
+            for (int p = 0; p < 3; ++p) {
+                S.rowsum.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * d.rows[p] * C);
+                // colpart is indexed with gridDim.x (= max_strips) strips for every plane
+                S.colpart.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * max_strips * d.cols[p] * C);
+                S.strips[p] = max_strips;
+            }
+            // strips beyond a plane's row count are never written: clear once so the fixed-order sum stays exact
+            for (int p = 0; p < 3; ++p)
+                CUDA_TRY(cudaMemset(S.colpart.p[p], 0, sizeof(float) * static_cast<size_t>(B) * max_strips * d.cols[p] * C));
+            A.rowsum = S.rowsum;
+            A.colpart = S.colpart;
+        }
+        const bool use_film = film_off >= 0;
+        const size_t smem = sizeof(float) * (2 + static_cast<size_t>(ny) * 4) * C;
+        Plan* Pp = P;
+        const int Bv = B;
+        P->ops.push_back([=](cudaStream_t s) {
+            GnSiluArgs Al = A;
+            if (use_film) {
+                Al.film = Pp->film;
+                Al.film_row = Pp->film_row;
+            }
+            dim3 grid(max_strips, 3, Bv), block(C / 4, ny);
+            if (ny == 16) k_gn_silu<16, 4><<<grid, block, smem, s>>>(Al, Bv);
+            else if (ny == 8) k_gn_silu<8, 4><<<grid, block, smem, s>>>(Al, Bv);
+            else k_gn_silu<4, 4><<<grid, block, smem, s>>>(Al, Bv);
+            LAUNCH_CHECK("k_gn_silu");
+        });
+        return S;
+    }
+
+    struct TBuf {
+        TriF Trow, Tcol;
+    };
+    // ---- rollout 1-D terms
+    TBuf roll1d(const Sums& S, int level, const DevConv3& cv) {
+        const TriDims d = dims[level];
+        const int C = cv.C, Cout = cv.Cout;
+        TBuf T{};
+        for (int p = 0; p < 3; ++p) {
+            T.Trow.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 4 * d.rows[p] * Cout);
+            T.Tcol.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 4 * d.cols[p] * Cout);
+        }
+        Roll1dArgs A{};
+        A.C = C;
+        A.Cout = Cout;
+        // (plane, group) -> source plane / kind; see roll_row_varying() and unet_triplane.py:37-46
+        struct SrcDef {
+            int sp;
+            bool colsum;
+        };
+        const SrcDef def[3][2] = {{{2, false}, {1, false}}, {{0, false}, {2, true}}, {{0, true}, {1, true}}};
+        int Lmax = 0;
+        for (int p = 0; p < 3; ++p)
+            for (int g = 0; g < 2; ++g) {
+                const SrcDef sd = def[p][g];
+                const bool rowv = roll_row_varying(p, g + 1);
+                Roll1dSrc& s = A.s[p * 2 + g];
+                s.L = rowv ? d.rows[p] : d.cols[p];
+                if (sd.colsum) {
+                    s.sum = S.colpart.p[sd.sp];
+                    s.nparts = S.strips[sd.sp];
+                    s.inv_count = 1.f / static_cast<float>(d.rows[sd.sp]);
+                    S3D_CHECK(d.cols[sd.sp] == s.L, "rollout geometry");
+                } else {
+                    s.sum = S.rowsum.p[sd.sp];
+                    s.nparts = 1;
+                    s.inv_count = 1.f / static_cast<float>(d.cols[sd.sp]);
+                    S3D_CHECK(d.rows[sd.sp] == s.L, "rollout geometry");
+                }
+                s.wr = cv.wr[p][g];
+                s.T = rowv ? T.Trow.p[p] : T.Tcol.p[p];
+                Lmax = std::max(Lmax, s.L);
+            }
+        const size_t smem = sizeof(float) * (static_cast<size_t>(10) * C + static_cast<size_t>(8) * 3 * Cout);
+        S3D_CHECK(smem <= 48 * 1024, "k_roll1d shared memory");
+        const int Bv = B;
+        P->ops.push_back([=](cudaStream_t s) {
+            dim3 grid((Lmax + 7) / 8, 6, Bv);
+            k_roll1d<<<grid, 256, smem, s>>>(A);
+            LAUNCH_CHECK("k_roll1d");
+        });
+        return T;
+    }
+
+    // ---- 3x3 conv (+ fused 1x1 skip)
+    void conv(const Act16& a, int level, const DevConv3& cv, const TBuf* T, const Act16* x16, const ActF* resid, int emb_off,
+              const ActF& out) {
+        const TriDims d = dims[level];
+        ConvEpi e{};
+        e.bias = cf3(cv.bias);
+        if (T) {
+            e.Trow = cf(T->Trow);
+            e.Tcol = cf(T->Tcol);
+        }
+        if (resid) e.resid = cf(resid->p);
+        e.film_dim = u->film_dim;
+        e.film_off = emb_off;
+        e.out = out.p;
+        const bool use_emb = emb_off >= 0;
+        Plan* Pp = P;
+        const int Bv = B;
+        if (u->cfg.conv_impl == 1) {
+            ConvFfmaArgs A{};
+            A.a = TriCH{{a.p.p[0], a.p.p[1], a.p.p[2]}};
+            if (x16) A.x16 = TriCH{{x16->p.p[0], x16->p.p[1], x16->p.p[2]}};
+            A.d = d;
+            A.C = cv.C;
+            A.Cout = cv.Cout;
+            A.Cw = cv.Cw;
+            A.Cs = cv.Cs;
+            A.w = cf3(cv.w_orig);
+            A.wskip = cf3(cv.wskip_orig);
+            A.e = e;
+            A.single = u->cfg.precision == 1;
+            const int mp = max_px(level);
+            P->ops.push_back([=](cudaStream_t s) {
+                ConvFfmaArgs Al = A;
+                if (use_emb) {
+                    Al.e.embadd = Pp->film;
+                    Al.e.film_row = Pp->film_row;
+                }
+                dim3 grid((mp + 3) / 4, 3, Bv), block(64, 4);
+                k_conv_ffma<<<grid, block, 0, s>>>(Al, Bv);
+                LAUNCH_CHECK("k_conv_ffma");
+            });
+            return;
+        }
+        S3D_CHECK(cv.C % kBK == 0 && cv.Cout % kBN == 0 && cv.Cs % kBK == 0, "tcgen05 conv needs channel counts % 64 == 0");
+        auto maps = std::make_shared<ConvTcMaps>();
+        memset(maps.get(), 0, sizeof(ConvTcMaps));
+        ConvTcArgs A{};
+        A.d = d;
+        A.C = cv.C;
+        A.Cout = cv.Cout;
+        A.Cs = cv.Cs;
+        A.e = e;
+        int total = 0;
+        for (int p = 0; p < 3; ++p) {
+            const uint64_t adims[5] = {static_cast<uint64_t>(cv.C), static_cast<uint64_t>(d.cols[p]),
+                                       static_cast<uint64_t>(d.rows[p]), static_cast<uint64_t>(B), 2};
+            const uint32_t abox[5] = {kBK, kTileW, kTileH, 1, 1};
+            make_tmap(&maps->a[p], a.p.p[p], 5, adims, abox);
+            if (cv.Cs) {
+                const uint64_t xdims[5] = {static_cast<uint64_t>(cv.Cs), static_cast<uint64_t>(d.cols[p]),
+                                           static_cast<uint64_t>(d.rows[p]), static_cast<uint64_t>(B), 2};
+                make_tmap(&maps->x[p], x16->p.p[p], 5, xdims, abox);
+            } else {
+                maps->x[p] = maps->a[p];
+            }
+            const uint64_t wdims[3] = {static_cast<uint64_t>(cv.Ktot), static_cast<uint64_t>(cv.Cout), 2};
+            const uint32_t wbox[3] = {kBK, kBN, 1};
+            make_tmap(&maps->w[p], cv.w_pack[p], 3, wdims, wbox);
+            A.tiles_x[p] = (d.cols[p] + kTileW - 1) / kTileW;
+            const int tiles_y = (d.rows[p] + kTileH - 1) / kTileH;
+            A.tile_start[p] = total;
+            total += A.tiles_x[p] * tiles_y;
+        }
+        A.tile_start[3] = total;
+        const int nsplit = u->cfg.precision == 1 ? 1 : 3;
+        const int ntile_n = cv.Cout / kBN;
+        P->ops.push_back([=](cudaStream_t s) {
+            ConvTcArgs Al = A;
+            if (use_emb) {
+                Al.e.embadd = Pp->film;
+                Al.e.film_row = Pp->film_row;
+            }
+            dim3 grid(total, ntile_n, Bv);
+            if (nsplit == 3) k_conv_tc<3><<<grid, kConvThreads, ConvTcCfg<3>::kSmemBytes, s>>>(*maps, Al);
+            else k_conv_tc<1><<<grid, kConvThreads, ConvTcCfg<1>::kSmemBytes, s>>>(*maps, Al);
+            LAUNCH_CHECK("k_conv_tc");
+        });
+    }
+
+    ActF res_block(int bi, const ActF& x) {
+        const BlockSpec& b = u->blocks[bi];
+        const DevBlock& w = u->dblocks[bi];
+        const int level = x.level;
+        const bool ro = u->cfg.rollout, ssn = u->cfg.use_scale_shift_norm;
+        S3D_CHECK(x.C == b.cin, "res block input width");
+        float* st1 = stats(x);
+        Act16 a1 = alloc16(level, b.cin);
+        Act16 x16{};
+        if (b.has_skip) x16 = alloc16(level, b.cin);
+        Sums s1 = gn_silu(x, st1, w.n1, -1, a1, b.has_skip ? &x16 : nullptr);
+        TBuf t1{};
+        if (ro) t1 = roll1d(s1, level, w.c1);
+        ActF h1 = allocF(level, b.cout, b.name + ".h1");
+        conv(a1, level, w.c1, ro ? &t1 : nullptr, nullptr, nullptr, ssn ? -1 : b.film_off, h1);
+        float* st2 = stats(h1);
+        Act16 a2 = alloc16(level, b.cout);
+        Sums s2 = gn_silu(h1, st2, w.n2, ssn ? b.film_off : -1, a2, nullptr);
+        TBuf t2{};
+        if (ro) t2 = roll1d(s2, level, w.c2);
+        ActF out = allocF(level, b.cout, b.name + ".out");
+        conv(a2, level, w.c2, ro ? &t2 : nullptr, b.has_skip ? &x16 : nullptr, b.has_skip ? nullptr : &x, -1, out);
+        return out;
+    }
+
+    ActF down(const ActF& x, int li) {
+        ActF o = allocF(x.level + 1, x.C, "down." + std::to_string(li));
+        const TriDims di = dims[x.level], dd = dims[x.level + 1];
+        const int C = x.C, Bv = B;
+        TriCF xc = cf(x.p);
+        TriF op = o.p;
+        const int n = max_px(x.level + 1) * (C / 4);
+        P->ops.push_back([=](cudaStream_t s) {
+            dim3 grid((n + 255) / 256, 3, Bv);
+            k_avgpool2<<<grid, 256, 0, s>>>(xc, di, dd, C, op);
+            LAUNCH_CHECK("k_avgpool2");
+        });
+        return o;
+    }
+
+    // x2 bilinear of `low` (+ resize to the skip's size) and concat with `skip` (may be null: plain upsample)
+    ActF upcat(const ActF& low, const ActF* skip, int out_level, bool do_up, const std::string& name) {
+        const int Cs = skip ? skip->C : 0;
+        ActF o = allocF(out_level, low.C + Cs, name);
+        const TriDims dl = dims[low.level], dout = dims[out_level];
+        TriCF lc = cf(low.p), sc{};
+        if (skip) sc = cf(skip->p);
+        TriF op = o.p;
+        const int Cu = low.C, Bv = B;
+        const int n = max_px(out_level) * ((Cu + Cs) / 4);
+        P->ops.push_back([=](cudaStream_t s) {
+            dim3 grid((n + 255) / 256, 3, Bv);
+            k_upcat<<<grid, 256, 0, s>>>(lc, dl, Cu, sc, Cs, dout, op, do_up ? 1 : 0);
+            LAUNCH_CHECK("k_upcat");
+        });
+        return o;
+    }
+};
+
+static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
+    CUDA_TRY(cudaSetDevice(u->device));
+    destroy_plan(u);
+    u->plan.reset(new Plan());
+    Plan* P = u->plan.get();
+    P->B = B; P->H = H; P->W = W; P->D = D;
+    const auto& c = u->cfg;
+    PlanBuilder pb{u, P, {}, B};
+    TriDims d{{H, H, W}, {W, D, D}};
+    for (int l = 0; l < c.n_levels; ++l) {
+        S3D_CHECK(d.rows[0] >= 1 && d.rows[2] >= 1 && d.cols[1] >= 1, "triplane too small for the number of levels");
+        pb.dims.push_back(d);
+        for (int p = 0; p < 3; ++p) {
+            d.rows[p] /= 2;
+            d.cols[p] /= 2;
+        }
+    }
+    P->film_own = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * u->film_dim);
+    // ---- in_conv
+    const int c0 = ch_of(c, 0);
+    ActF h = pb.allocF(0, c0, "in_conv");
+    {
+        const TriDims d0 = pb.dims[0];
+        const int Cin = c.in_channels, mp = pb.max_px(0);
+        TriCF w = PlanBuilder::cf3(u->in_w), bb = PlanBuilder::cf3(u->in_b);
+        TriF op = h.p;
+        P->ops.push_back([=](cudaStream_t s) {
+            dim3 grid((mp + 31) / 32, 3, B);
+            k_in_conv<<<grid, 256, sizeof(float) * Cin * 32, s>>>(P->x, d0, H, W, D, Cin, c0, w, bb, op);
+            LAUNCH_CHECK("k_in_conv");
+        });
+    }
+    // ---- encoder
+    std::vector<ActF> stack;
+    for (int l = 0; l < c.n_levels; ++l) {
+        for (const auto& op : u->downs[l]) {
+            if (op.kind == 1) h = pb.down(h, l);
+            else h = pb.res_block(op.block, h);
+        }
+        stack.push_back(h);
+    }
+    // ---- decoder (unet_triplane.py:488-505)
+    bool pending_up = false;    // an Upsample2x closed the previous output block
+    for (int j = 0; j < c.n_levels; ++j) {
+        const int level = c.n_levels - 1 - j;
+        if (j == 0) {
+            h = stack.back();
+            stack.pop_back();
+        } else {
+            ActF skip = stack.back();
+            stack.pop_back();
+            if (!c.rollout) {
+                // ...SmallRaw concatenates without resizing; mismatched (odd) sizes fail in the reference too
+                for (int p = 0; p < 3; ++p)
+                    S3D_CHECK(2 * pb.dims[level + 1].rows[p] == pb.dims[level].rows[p] &&
+                                  2 * pb.dims[level + 1].cols[p] == pb.dims[level].cols[p],
+                              "TriplaneUNetModelSmallRaw needs even plane sizes at every level (torch.cat would fail)");
+            }
+            h = pb.upcat(h, &skip, level, pending_up, "upcat." + std::to_string(j));
+            pending_up = false;
+        }
+        for (const auto& op : u->ups[j]) {
+            if (op.kind == 2) pending_up = true;     // fused into the next level's upcat
+            else h = pb.res_block(op.block, h);
+        }
+    }
+    S3D_CHECK(!pending_up && h.level == 0, "decoder structure");
+    // ---- out head
+    float* st = pb.stats(h);
+    {
+        const TriDims d0 = pb.dims[0];
+        const int C = h.C, Cout = c.out_channels;
+        TriCF xc = PlanBuilder::cf(h.p), g = PlanBuilder::cf3(u->out_norm.gamma), be = PlanBuilder::cf3(u->out_norm.beta);
+        TriCF w = PlanBuilder::cf3(u->out_w), bb = PlanBuilder::cf3(u->out_b);
+        const int mp = std::max(pb.max_px(0), D * D);
+        const size_t smem = sizeof(float) * (2 * C + static_cast<size_t>(Cout) * C + Cout);
+        S3D_CHECK(smem <= 100 * 1024, "k_out_head shared memory");
+        P->ops.push_back([=](cudaStream_t s) {
+            dim3 grid((mp + 127) / 128, 4, B);
+            k_out_head<<<grid, 128, smem, s>>>(xc, d0, C, Cout, st, g, be, w, bb, P->out, H, W, D);
+            LAUNCH_CHECK("k_out_head");
+        });
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+}
+
+static Plan* get_plan(s3d_unet* u, int B, int H, int W, int D) {
+    if (!u->finalized) throw S3dError{"s3d_unet_finalize() has not been called"};
+    S3D_CHECK(B >= 1 && H >= 1 && W >= 1 && D >= 1, "bad shape");
+    if (!u->plan || u->plan->B != B || u->plan->H != H || u->plan->W != W || u->plan->D != D) build_plan(u, B, H, W, D);
+    return u->plan.get();
+}
+
+// film rows for n timesteps: sinusoid -> Linear -> SiLU -> Linear -> SiLU -> concatenated emb_layers
+static void run_film(s3d_unet* u, Plan* P, const float* t_dev, int n, float* film_dev, cudaStream_t s) {
+    if (P->emb_rows < n) {
+        for (int i = 0; i < 3; ++i) P->emb_tmp[i] = dev_alloc<float>(P->allocs, static_cast<size_t>(n) * u->emb_dim);
+        P->emb_rows = n;
+    }
+    const int mc = u->cfg.model_channels, half = mc / 2, E = u->emb_dim;
+    S3D_CHECK(mc % 2 == 0, "odd model_channels");
+    k_sinusoid<<<(n * half + 255) / 256, 256, 0, s>>>(t_dev, u->freqs, half, P->emb_tmp[0], n);
+    LAUNCH_CHECK("k_sinusoid");
+    k_linear<<<dim3((E + 7) / 8, n), 256, 0, s>>>(P->emb_tmp[0], u->te_w0, u->te_b0, P->emb_tmp[1], mc, E, 0);
+    LAUNCH_CHECK("k_linear");
+    k_linear<<<dim3((E + 7) / 8, n), 256, 0, s>>>(P->emb_tmp[1], u->te_w2, u->te_b2, P->emb_tmp[2], E, E, 1);
+    LAUNCH_CHECK("k_linear");
+    k_linear<<<dim3((u->film_dim + 7) / 8, n), 256, 0, s>>>(P->emb_tmp[2], u->film_w, u->film_b, film_dev, E, u->film_dim, 1);
+    LAUNCH_CHECK("k_linear");
+}
+
+static void run_ops(s3d_unet* u, Plan* P, cudaStream_t s) {
+    for (auto& op : P->ops) op(s);
+    u->last_launches = static_cast<int>(P->ops.size());
+}
+
+static void launch_sched(const SchedArgs& A, cudaStream_t s) {
+    const long long n4 = (A.n + 3) / 4;
+    int gx = static_cast<int>(std::min<long long>((n4 + 255) / 256, 148LL * 8));
+    gx = std::max(gx, 1);
+    k_sched_step<<<dim3(gx, A.B), 256, 0, s>>>(A);
+    LAUNCH_CHECK("k_sched_step");
+}
+
+// ------------------------------------------------------------------------------------ C ABI
+#define API_BEGIN try {
+#define API_END                                   \
+    }                                             \
+    catch (const S3dError& e) { return fail(e.msg); } \
+    catch (const std::exception& e) { return fail(e.what()); } \
+    return 0;
+
+extern "C" {
+
+int s3d_abi_version(void) { return 1; }
+const char* s3d_last_error(void) { return g_err.c_str(); }
+
+int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
+    API_BEGIN
+    S3D_CHECK(cfg && out, "null argument");
+    S3D_CHECK(cfg->num_res_blocks == 1,
+              "num_res_blocks must be 1: the reference constructor (unet_triplane.py:389-405) cannot build a runnable "
+              "model otherwise");
+    S3D_CHECK(cfg->n_levels >= 1 && cfg->n_levels <= S3D_MAX_LEVELS, "n_levels out of range");
+    S3D_CHECK(cfg->model_channels > 0 && cfg->model_channels % 64 == 0, "model_channels must be a multiple of 64");
+    S3D_CHECK(cfg->in_channels >= 1 && cfg->out_channels >= 1 && cfg->out_channels <= 64, "channel counts out of range");
+    for (int l = 0; l < cfg->n_levels; ++l) S3D_CHECK(cfg->channel_mult[l] >= 1, "channel_mult must be >= 1");
+    S3D_CHECK(cfg->precision == 1 || cfg->precision == 3, "precision must be 1 or 3");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    S3D_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    S3D_CHECK(prop.major == 10, "sin3dm_b200 kernels are built for sm_100a (B200) only");
+    std::unique_ptr<s3d_unet> u(new s3d_unet());
+    u->cfg = *cfg;
+    u->device = device;
+    build_structure(u.get());
+    *out = u.release();
+    API_END
+}
+
+int s3d_unet_destroy(s3d_unet* u) {
+    if (!u) return 0;
+    cudaSetDevice(u->device);
+    destroy_plan(u);
+    free_all(u->wallocs);
+    delete u;
+    return 0;
+}
+
+int s3d_unet_num_tensors(const s3d_unet* u) { return u ? static_cast<int>(u->tensors.size()) : 0; }
+
+int s3d_unet_tensor_info(const s3d_unet* u, int index, const char** name, int* ndim, int64_t shape[4]) {
+    API_BEGIN
+    S3D_CHECK(u && index >= 0 && index < static_cast<int>(u->tensors.size()), "bad index");
+    const TensorSpec& t = u->tensors[index];
+    if (name) *name = t.name.c_str();
+    if (ndim) *ndim = static_cast<int>(t.shape.size());
+    if (shape)
+        for (size_t i = 0; i < 4; ++i) shape[i] = i < t.shape.size() ? t.shape[i] : 1;
+    API_END
+}
+
+int s3d_unet_load_tensor(s3d_unet* u, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+    API_BEGIN
+    S3D_CHECK(u && name && host_data && shape, "null argument");
+    std::string n(name);
+    if (n == "__freqs") {
+        S3D_CHECK(ndim == 1 && shape[0] == u->cfg.model_channels / 2, "__freqs shape");
+        if (!u->index.count(n)) add_tensor(u, n, {shape[0]});
+    }
+    auto it = u->index.find(n);
+    if (it == u->index.end()) throw S3dError{"unexpected key in state_dict: " + n};
+    TensorSpec& t = u->tensors[it->second];
+    bool same = static_cast<int>(t.shape.size()) == ndim;
+    for (int i = 0; same && i < ndim; ++i) same = t.shape[i] == shape[i];
+    if (!same) throw S3dError{"size mismatch for " + n};
+    t.host.assign(host_data, host_data + t.numel());
+    t.loaded = true;
+    u->finalized = false;
+    API_END
+}
+
+int s3d_unet_finalize(s3d_unet* u) {
+    API_BEGIN
+    S3D_CHECK(u, "null handle");
+    finalize(u);
+    API_END
+}
+
+int s3d_unet_film_dim(const s3d_unet* u) { return u ? u->film_dim : 0; }
+int s3d_unet_last_launches(const s3d_unet* u) { return u ? u->last_launches : 0; }
+
+int s3d_unet_film(s3d_unet* u, const float* t_dev, int n, float* film_dev, void* stream) {
+    API_BEGIN
+    S3D_CHECK(u && t_dev && film_dev && n >= 1, "bad argument");
+    if (!u->finalized) throw S3dError{"s3d_unet_finalize() has not been called"};
+    CUDA_TRY(cudaSetDevice(u->device));
+    if (!u->plan) build_plan(u, 1, 8, 8, 8);   // scratch owner
+    run_film(u, u->plan.get(), t_dev, n, film_dev, static_cast<cudaStream_t>(stream));
+    API_END
+}
+
+int s3d_unet_forward_film(s3d_unet* u, const float* x_dev, const float* film_dev, const int* row_dev, float* out_dev, int B,
+                          int H, int W, int D, void* stream) {
+    API_BEGIN
+    S3D_CHECK(u && x_dev && film_dev && out_dev, "null argument");
+    CUDA_TRY(cudaSetDevice(u->device));
+    Plan* P = get_plan(u, B, H, W, D);
+    P->x = x_dev;
+    P->out = out_dev;
+    P->film = film_dev;
+    P->film_row = row_dev;
+    run_ops(u, P, static_cast<cudaStream_t>(stream));
+    API_END
+}
+
+int s3d_unet_forward(s3d_unet* u, const float* x_dev, const float* t_dev, float* out_dev, int B, int H, int W, int D,
+                     void* stream) {
+    API_BEGIN
+    S3D_CHECK(u && x_dev && t_dev && out_dev, "null argument");
+    CUDA_TRY(cudaSetDevice(u->device));
+    Plan* P = get_plan(u, B, H, W, D);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    run_film(u, P, t_dev, B, P->film_own, s);
+    P->x = x_dev;
+    P->out = out_dev;
+    P->film = P->film_own;
+    P->film_row = nullptr;
+    run_ops(u, P, s);
+    u->last_launches += 4;
+    API_END
+}
+
+static SchedArgs to_sched(const s3d_sched_args* a) {
+    SchedArgs A{};
+    A.kind = a->kind;
+    A.mean_type = a->mean_type;
+    A.clip = a->clip_denoised;
+    A.is_mask_t0 = a->is_mask_t0;
+    A.B = a->B;
+    A.n = a->n_per_sample;
+    A.model_out = a->model_out;
+    A.x = a->x;
+    A.noise = a->noise;
+    A.y0 = a->y0;
+    A.mask = a->mask;
+    A.sample = a->sample;
+    A.x0_out = a->pred_xstart;
+    A.coef = a->coef_dev;
+    A.t_idx = const_cast<int*>(a->t_idx_dev);
+    A.seed = a->seed;
+    A.sample_base = a->sample_base;
+    return A;
+}
+
+int s3d_sched_step(const s3d_sched_args* a, void* stream) {
+    API_BEGIN
+    S3D_CHECK(a && a->model_out && a->x && a->sample && a->coef_dev && a->t_idx_dev, "null argument");
+    S3D_CHECK(a->kind >= 0 && a->kind <= 2 && (a->mean_type == 0 || a->mean_type == 1), "bad kind / mean_type");
+    S3D_CHECK((a->y0 == nullptr) == (a->mask == nullptr), "y0 and mask go together");
+    S3D_CHECK(a->B >= 1 && a->n_per_sample >= 1, "bad shape");
+    launch_sched(to_sched(a), static_cast<cudaStream_t>(stream));
+    API_END
+}
+
+int s3d_q_sample(const float* x0_dev, const float* noise_dev, float* out_dev, const float* coef_dev, const int* t_idx_dev, int B,
+                 int64_t n, void* stream) {
+    API_BEGIN
+    S3D_CHECK(x0_dev && noise_dev && out_dev && coef_dev && t_idx_dev && B >= 1 && n >= 1, "bad argument");
+    int gx = static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 8));
+    k_q_sample<<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(x0_dev, noise_dev, out_dev, coef_dev, t_idx_dev, n);
+    LAUNCH_CHECK("k_q_sample");
+    API_END
+}
+
+int s3d_philox_normal(float* out_dev, int B, int64_t n, uint64_t seed, uint32_t sample_base, uint32_t step, void* stream) {
+    API_BEGIN
+    S3D_CHECK(out_dev && B >= 1 && n >= 1, "bad argument");
+    int gx = static_cast<int>(std::min<long long>(((n + 3) / 4 + 255) / 256, 148LL * 8));
+    k_philox_normal<<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, n, seed, sample_base, step);
+    LAUNCH_CHECK("k_philox_normal");
+    API_END
+}
+
+__global__ void k_fill_int(int* p, int n, int v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
+    API_BEGIN
+    S3D_CHECK(u && a && a->x_dev && a->coef_dev && a->film_dev, "null argument");
+    S3D_CHECK((a->kind == S3D_DDPM || a->kind == S3D_DDIM) && (a->mean_type == 0 || a->mean_type == 1), "bad kind / mean_type");
+    S3D_CHECK((a->y0_dev == nullptr) == (a->mask_dev == nullptr), "y0 and mask go together");
+    S3D_CHECK(a->n_steps >= 1, "n_steps");
+    CUDA_TRY(cudaSetDevice(u->device));
+    Plan* P = get_plan(u, a->B, a->H, a->W, a->D);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int Hc = a->H + a->D, Wc = a->W + a->D;
+    S3D_CHECK(u->cfg.in_channels == u->cfg.out_channels, "sampling needs in_channels == out_channels");
+    const long long n = static_cast<long long>(u->cfg.out_channels) * Hc * Wc;
+    if (!P->t_idx) {
+        P->t_idx = dev_alloc<int>(P->allocs, a->B);
+        P->ticket = dev_alloc<unsigned int>(P->allocs, 1);
+        CUDA_TRY(cudaMemset(P->ticket, 0, sizeof(unsigned int)));
+        P->model_out = dev_alloc<float>(P->allocs, static_cast<size_t>(a->B) * n);
+    }
+    k_fill_int<<<(a->B + 255) / 256, 256, 0, s>>>(P->t_idx, a->B, a->n_steps - 1);
+    LAUNCH_CHECK("k_fill_int");
+    P->x = a->x_dev;
+    P->out = P->model_out;
+    P->film = a->film_dev;
+    P->film_row = P->t_idx;
+    SchedArgs A{};
+    A.kind = a->kind;
+    A.mean_type = a->mean_type;
+    A.clip = a->clip_denoised;
+    A.is_mask_t0 = a->is_mask_t0;
+    A.B = a->B;
+    A.n = n;
+    A.model_out = P->model_out;
+    A.x = a->x_dev;
+    A.noise = a->step_noise_dev;
+    A.noise_step_stride = a->step_noise_dev ? static_cast<long long>(a->B) * n : 0;
+    A.y0 = a->y0_dev;
+    A.mask = a->mask_dev;
+    A.sample = a->x_dev;
+    A.x0_out = a->pred_xstart_dev;
+    A.coef = a->coef_dev;
+    A.t_idx = P->t_idx;
+    A.seed = a->seed;
+    A.sample_base = a->sample_base;
+    A.advance = 1;
+    A.ticket = P->ticket;
+    auto one_step = [&](cudaStream_t st) {
+        run_ops(u, P, st);
+        launch_sched(A, st);
+    };
+    if (!a->use_graph) {
+        for (int i = 0; i < a->n_steps; ++i) one_step(s);
+    } else {
+        // The graph bakes every pointer and scalar of one step; only the step index (device memory) changes.
+        char key[512];
+        snprintf(key, sizeof(key), "%d|%d|%d|%d|%p|%p|%p|%p|%p|%p|%p|%llu|%u", a->kind, a->mean_type, a->clip_denoised,
+                 a->is_mask_t0, (void*)a->x_dev, (void*)a->pred_xstart_dev, (void*)a->coef_dev, (void*)a->film_dev,
+                 (void*)a->step_noise_dev, (void*)a->y0_dev, (void*)a->mask_dev, (unsigned long long)a->seed, a->sample_base);
+        if (!P->graph_exec || P->graph_key != key) {
+            if (P->graph_exec) {
+                cudaGraphExecDestroy(P->graph_exec);
+                P->graph_exec = nullptr;
+            }
+            cudaStream_t cs;
+            CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                try {
+                    one_step(cs);
+                } catch (...) {
+                    cudaStreamEndCapture(cs, &g);
+                    if (g) cudaGraphDestroy(g);
+                    cudaStreamDestroy(cs);
+                    throw;
+                }
+                e = cudaStreamEndCapture(cs, &g);
+            }
+            cudaStreamDestroy(cs);
+            if (e != cudaSuccess) throw S3dError{std::string("graph capture: ") + cudaGetErrorString(e)};
+            e = cudaGraphInstantiate(&P->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) throw S3dError{std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)};
+            P->graph_key = key;
+        }
+        for (int i = 0; i < a->n_steps; ++i) CUDA_TRY(cudaGraphLaunch(P->graph_exec, s));
+        u->last_launches = static_cast<int>(P->ops.size());
+    }
+    u->last_launches += 1;   // scheduler kernel
+    API_END
+}
+
+int s3d_unet_debug_count(const s3d_unet* u) { return (u && u->plan) ? static_cast<int>(u->plan->named.size()) : 0; }
+
+int s3d_unet_debug_info(const s3d_unet* u, int index, const char** name, int* channels, int rows[3], int cols[3],
+                        int* batch) {
+    API_BEGIN
+    S3D_CHECK(u && u->plan && index >= 0 && index < static_cast<int>(u->plan->named.size()), "bad index");
+    const NamedBuf& nb = u->plan->named[index];
+    if (name) *name = nb.name.c_str();
+    if (channels) *channels = nb.C;
+    if (batch) *batch = u->plan->B;
+    for (int p = 0; p < 3; ++p) {
+        if (rows) rows[p] = nb.d.rows[p];
+        if (cols) cols[p] = nb.d.cols[p];
+    }
+    API_END
+}
+
+int s3d_unet_debug_read(s3d_unet* u, int index, int plane, float* host_out, int64_t n_floats) {
+    API_BEGIN
+    S3D_CHECK(u && u->plan && index >= 0 && index < static_cast<int>(u->plan->named.size()) && plane >= 0 && plane < 3,
+              "bad index");
+    const NamedBuf& nb = u->plan->named[index];
+    const int64_t want = static_cast<int64_t>(u->plan->B) * nb.d.rows[plane] * nb.d.cols[plane] * nb.C;
+    S3D_CHECK(n_floats == want, "buffer size mismatch");
+    CUDA_TRY(cudaSetDevice(u->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(host_out, nb.p.p[plane], sizeof(float) * want, cudaMemcpyDeviceToHost));
+    API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+"""CPU-only checks of the host mirror: respacing index path, fp64 tables, fp32 coefficient table,
+state_dict layout, and that the C-ABI library loads and exports every declared symbol."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import sin3dm_b200 as s3
+from oracle import diffusion_ref as dr
+from oracle import unet_ref as ur
+from oracle.cases import RESPACE_CASES, TABLE_CASES
+from sin3dm_b200 import _lib
+from sin3dm_b200.script_util import create_gaussian_diffusion
+
+
+def test_space_timesteps_bit_exact(golden_dir):
+    want = json.load(open(os.path.join(golden_dir, "respace.json")))
+    for T, spec in RESPACE_CASES:
+        key = f"{T}|{spec if isinstance(spec, str) else ','.join(map(str, spec))}"
+        try:
+            got = sorted(s3.space_timesteps(T, spec))
+        except ValueError:
+            got = "ValueError"
+        assert got == want[key], key
+
+
+def test_tables_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tables.npz"))
+    for name, case in TABLE_CASES.items():
+        d = create_gaussian_diffusion(steps=case["T"], noise_schedule=case.get("schedule", "linear"),
+                                      predict_xstart=True, timestep_respacing=case["respacing"])
+        assert np.array_equal(np.array(d.timestep_map), g[f"{name}/timestep_map"])
+        for k in dr.tables(np.ones(2) * 0.5):
+            assert np.array_equal(getattr(d, k), g[f"{name}/{k}"]), (name, k)
+
+
+@pytest.mark.parametrize("eta", [0.0, 0.7])
+def test_coef_table_matches_reference_expressions(eta):
+    d = create_gaussian_diffusion(predict_xstart=True, timestep_respacing="25")
+    o = dr.RefDiffusion(1000, "25")
+    cf = d.coef_table("cpu", eta)
+    assert cf.shape == (25, _lib.S3D_NCOEF) and cf.dtype == torch.float32
+    t = torch.arange(25)
+    one = torch.zeros(25, 1)
+    f = lambda a: o._x(a, t, one)[:, 0]
+    ab, abp = f(o.tab["alphas_cumprod"]), f(o.tab["alphas_cumprod_prev"])
+    sigma = eta * torch.sqrt((1 - abp) / (1 - ab)) * torch.sqrt(1 - ab / abp)
+    assert torch.equal(cf[:, 0], f(o.tab["sqrt_recip_alphas_cumprod"]))
+    assert torch.equal(cf[:, 2], f(o.tab["posterior_mean_coef1"]))
+    assert torch.equal(cf[:, 4], torch.exp(0.5 * f(o.logvar)))
+    assert torch.equal(cf[:, 5], torch.sqrt(abp))
+    assert torch.equal(cf[:, 6], torch.sqrt(1 - abp - sigma ** 2))
+    assert torch.equal(cf[:, 7], sigma)
+
+
+def test_model_timesteps_map_and_rescale():
+    d = create_gaussian_diffusion(predict_xstart=True, timestep_respacing="10", rescale_timesteps=True)
+    o = dr.RefDiffusion(1000, "10", rescale_timesteps=True)
+    t = torch.tensor([0, 3, 9])
+    assert torch.equal(d._model_timesteps(t), o.model_t(t))
+    d2 = create_gaussian_diffusion(predict_xstart=True, timestep_respacing="ddim50")
+    assert d2._model_timesteps(t).dtype == torch.long
+    assert d2._model_timesteps(t).tolist() == [0, 60, 180]
+
+
+@pytest.mark.parametrize("rollout", [True, False])
+@pytest.mark.parametrize("mult", [(1, 2), (1, 2, 2), (1,)])
+def test_state_dict_layout(rollout, mult):
+    cls = s3.TriplaneUNetModelSmall if rollout else s3.TriplaneUNetModelSmallRaw
+    m = cls(12, 64, 12, 1, 0, mult, use_scale_shift_norm=True)
+    spec = ur.UNetSpec(12, 64, 12, 1, mult, True, rollout)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s in ur.param_shapes(spec)]
+    # zero-init trap: second conv of every block and the out conv start at zero
+    zeros = [k for k, v in m.state_dict().items() if (v == 0).all()]
+    assert any("out_layers.2" in k for k in zeros) and any(k.startswith("out.2") for k in zeros)
+
+
+def test_unsupported_configs_raise():
+    with pytest.raises(NotImplementedError):
+        s3.TriplaneUNetModelSmall(8, 64, 8, num_res_blocks=2)
+    from sin3dm_b200 import gaussian_diffusion as gd
+    with pytest.raises(NotImplementedError):
+        create_gaussian_diffusion(learn_sigma=True)
+    with pytest.raises(ValueError):
+        s3.space_timesteps(50, "60")
+
+
+def test_cpu_tensors_fail_loudly():
+    m = s3.TriplaneUNetModelSmall(8, 64, 8, use_scale_shift_norm=True)
+    with pytest.raises(_lib.S3DError), torch.no_grad():
+        m(torch.zeros(1, 8, 16, 16), torch.zeros(1), H=8, W=8, D=8)
+
+
+def test_abi_exports_every_declared_symbol():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "sin3dm_b200.h")).read()
+    declared = set(re.findall(r"\b(s3d_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib._SIGNATURES), declared ^ set(_lib._SIGNATURES)
+    L = _lib.lib()            # raises if the .so is missing or a symbol cannot be bound
+    assert L.s3d_abi_version() == 1
+    for name in declared:
+        assert hasattr(L, name)
+    # struct sizes agree with the header layout (no compute call: there is no GPU here)
+    import ctypes as C
+    assert C.sizeof(_lib.UNetConfig) == 4 * (5 + 8 + 4)
