@@ -72,6 +72,14 @@ int s3d_unet_forward_film(s3d_unet* u, const float* x_dev, const float* film_dev
                           int B, int H, int W, int D, void* stream);
 /* Kernel launches issued by the last forward (for bench accounting). */
 int s3d_unet_last_launches(const s3d_unet* u);
+/* Bytes of device workspace (activations, operands, statistics) owned by the current launch plan. */
+int64_t s3d_unet_workspace_bytes(const s3d_unet* u);
+/* Launch list of the current plan: kernel name and the dense algorithmic FLOPs the op stands for (convs). */
+int s3d_unet_op_count(const s3d_unet* u);
+int s3d_unet_op_info(const s3d_unet* u, int index, const char** kernel, double* dense_flops);
+/* Mean device time (ms) of every op of the plan, CUDA events around each launch on `stream`; synchronises.
+ * Uses the tensors bound by the last forward / sampling loop (bench.py's roofline leg). */
+int s3d_unet_profile_ops(s3d_unet* u, int iters, float* ms_out, void* stream);
 
 /* ---- scheduler step (replaces p_sample / ddim_sample / ddim_reverse_sample element-wise math) ----
  * coef_dev is [T][S3D_NCOEF] fp32, built by the host mirror from the fp64 tables exactly as

@@ -130,6 +130,9 @@ struct NamedBuf {
 struct Plan {
     int B = 0, H = 0, W = 0, D = 0;
     std::vector<std::function<void(cudaStream_t)>> ops;
+    std::vector<std::string> op_names;   // kernel:layer, parallel to ops
+    std::vector<double> op_flops;        // dense algorithmic FLOPs of the op as the reference executes it (convs only)
+    size_t alloc_bytes = 0;
     std::vector<void*> allocs;
     std::vector<NamedBuf> named;
     float* film_own = nullptr;      // [B][film_dim] used by s3d_unet_forward
@@ -250,11 +253,13 @@ static void build_structure(s3d_unet* u) {
 }
 
 // ------------------------------------------------------------------------------------ device memory helpers
+static size_t* g_alloc_counter = nullptr;   // set while a plan is being built
 template <typename T>
 static T* dev_alloc(std::vector<void*>& owner, size_t n) {
     void* p = nullptr;
     CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
     owner.push_back(p);
+    if (g_alloc_counter) *g_alloc_counter += n * sizeof(T);
     return static_cast<T*>(p);
 }
 template <typename T>
@@ -438,6 +443,16 @@ struct PlanBuilder {
     std::vector<TriDims> dims;   // per level
     int B;
 
+    void add_op(const char* name, double flops, std::function<void(cudaStream_t)> fn) {
+        P->ops.push_back(std::move(fn));
+        P->op_names.push_back(name);
+        P->op_flops.push_back(flops);
+    }
+    // dense FLOPs of one TriplaneConv 3x3 (+ its 1x1 skip) as the reference executes it: rollout channels counted
+    double conv_flops(int level, const DevConv3& cv) const {
+        double pxs = static_cast<double>(px(level, 0) + px(level, 1) + px(level, 2));
+        return 2.0 * B * pxs * cv.Cout * (9.0 * cv.Cw + cv.Cs);
+    }
     size_t px(int level, int plane) const { return static_cast<size_t>(dims[level].rows[plane]) * dims[level].cols[plane]; }
     int max_px(int level) const { return static_cast<int>(std::max({px(level, 0), px(level, 1), px(level, 2)})); }
 
@@ -470,7 +485,7 @@ struct PlanBuilder {
         TriCF xc = cf(x.p);
         TriDims d = dims[level];
         const int Bv = B;
-        P->ops.push_back([=](cudaStream_t s) {
+        add_op("k_gn_stats", 0.0, [=](cudaStream_t s) {
             dim3 grid(chunks, 3, Bv), block(C / 4, 8);
             k_gn_stats<8><<<grid, block, sizeof(float) * 8 * 2 * C, s>>>(xc, d, C, chunks, partial, ticket, st);
             LAUNCH_CHECK("k_gn_stats");
@@ -529,7 +544,7 @@ struct PlanBuilder {
         const size_t smem = sizeof(float) * (2 + static_cast<size_t>(ny) * 4) * C;
         Plan* Pp = P;
         const int Bv = B;
-        P->ops.push_back([=](cudaStream_t s) {
+        add_op("k_gn_silu", 0.0, [=](cudaStream_t s) {
             GnSiluArgs Al = A;
             if (use_film) {
                 Al.film = Pp->film;
@@ -590,7 +605,7 @@ struct PlanBuilder {
         const size_t smem = sizeof(float) * (static_cast<size_t>(10) * C + static_cast<size_t>(8) * 3 * Cout);
         S3D_CHECK(smem <= 48 * 1024, "k_roll1d shared memory");
         const int Bv = B;
-        P->ops.push_back([=](cudaStream_t s) {
+        add_op("k_roll1d", 0.0, [=](cudaStream_t s) {
             dim3 grid((Lmax + 7) / 8, 6, Bv);
             k_roll1d<<<grid, 256, smem, s>>>(A);
             LAUNCH_CHECK("k_roll1d");
@@ -629,7 +644,7 @@ struct PlanBuilder {
             A.e = e;
             A.single = u->cfg.precision == 1;
             const int mp = max_px(level);
-            P->ops.push_back([=](cudaStream_t s) {
+            add_op("k_conv_ffma", conv_flops(level, cv), [=](cudaStream_t s) {
                 ConvFfmaArgs Al = A;
                 if (use_emb) {
                     Al.e.embadd = Pp->film;
@@ -674,7 +689,7 @@ struct PlanBuilder {
         A.tile_start[3] = total;
         const int nsplit = u->cfg.precision == 1 ? 1 : 3;
         const int ntile_n = cv.Cout / kBN;
-        P->ops.push_back([=](cudaStream_t s) {
+        add_op("k_conv_tc", conv_flops(level, cv), [=](cudaStream_t s) {
             ConvTcArgs Al = A;
             if (use_emb) {
                 Al.e.embadd = Pp->film;
@@ -719,7 +734,7 @@ struct PlanBuilder {
         TriCF xc = cf(x.p);
         TriF op = o.p;
         const int n = max_px(x.level + 1) * (C / 4);
-        P->ops.push_back([=](cudaStream_t s) {
+        add_op("k_avgpool2", 0.0, [=](cudaStream_t s) {
             dim3 grid((n + 255) / 256, 3, Bv);
             k_avgpool2<<<grid, 256, 0, s>>>(xc, di, dd, C, op);
             LAUNCH_CHECK("k_avgpool2");
@@ -737,7 +752,7 @@ struct PlanBuilder {
         TriF op = o.p;
         const int Cu = low.C, Bv = B;
         const int n = max_px(out_level) * ((Cu + Cs) / 4);
-        P->ops.push_back([=](cudaStream_t s) {
+        add_op("k_upcat", 0.0, [=](cudaStream_t s) {
             dim3 grid((n + 255) / 256, 3, Bv);
             k_upcat<<<grid, 256, 0, s>>>(lc, dl, Cu, sc, Cs, dout, op, do_up ? 1 : 0);
             LAUNCH_CHECK("k_upcat");
@@ -752,6 +767,10 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     u->plan.reset(new Plan());
     Plan* P = u->plan.get();
     P->B = B; P->H = H; P->W = W; P->D = D;
+    struct CounterGuard {
+        CounterGuard(size_t* c) { g_alloc_counter = c; }
+        ~CounterGuard() { g_alloc_counter = nullptr; }
+    } guard(&P->alloc_bytes);
     const auto& c = u->cfg;
     PlanBuilder pb{u, P, {}, B};
     TriDims d{{H, H, W}, {W, D, D}};
@@ -772,7 +791,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         const int Cin = c.in_channels, mp = pb.max_px(0);
         TriCF w = PlanBuilder::cf3(u->in_w), bb = PlanBuilder::cf3(u->in_b);
         TriF op = h.p;
-        P->ops.push_back([=](cudaStream_t s) {
+        pb.add_op("k_in_conv", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * Cin * c0, [=](cudaStream_t s) {
             dim3 grid((mp + 31) / 32, 3, B);
             k_in_conv<<<grid, 256, sizeof(float) * Cin * 32, s>>>(P->x, d0, H, W, D, Cin, c0, w, bb, op);
             LAUNCH_CHECK("k_in_conv");
@@ -823,7 +842,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         const int mp = std::max(pb.max_px(0), D * D);
         const size_t smem = sizeof(float) * (2 * C + static_cast<size_t>(Cout) * C + Cout);
         S3D_CHECK(smem <= 100 * 1024, "k_out_head shared memory");
-        P->ops.push_back([=](cudaStream_t s) {
+        pb.add_op("k_out_head", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * C * Cout, [=](cudaStream_t s) {
             dim3 grid((mp + 127) / 128, 4, B);
             k_out_head<<<grid, 128, smem, s>>>(xc, d0, C, Cout, st, g, be, w, bb, P->out, H, W, D);
             LAUNCH_CHECK("k_out_head");
@@ -1145,6 +1164,50 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
         u->last_launches = static_cast<int>(P->ops.size());
     }
     u->last_launches += 1;   // scheduler kernel
+    API_END
+}
+
+int64_t s3d_unet_workspace_bytes(const s3d_unet* u) { return (u && u->plan) ? static_cast<int64_t>(u->plan->alloc_bytes) : 0; }
+
+int s3d_unet_op_count(const s3d_unet* u) { return (u && u->plan) ? static_cast<int>(u->plan->ops.size()) : 0; }
+
+int s3d_unet_op_info(const s3d_unet* u, int index, const char** kernel, double* dense_flops) {
+    API_BEGIN
+    S3D_CHECK(u && u->plan && index >= 0 && index < static_cast<int>(u->plan->ops.size()), "bad index");
+    if (kernel) *kernel = u->plan->op_names[index].c_str();
+    if (dense_flops) *dense_flops = u->plan->op_flops[index];
+    API_END
+}
+
+// Re-runs the UNet ops of the current plan `iters` times with a CUDA-event pair around every launch (on `stream`)
+// and returns the mean device time per op in milliseconds.  Synchronises.  Uses the bindings of the last forward / loop.
+int s3d_unet_profile_ops(s3d_unet* u, int iters, float* ms_out, void* stream) {
+    API_BEGIN
+    S3D_CHECK(u && u->plan && ms_out && iters >= 1, "bad argument");
+    Plan* P = u->plan.get();
+    S3D_CHECK(P->x && P->out && P->film, "run a forward or a sampling loop first");
+    CUDA_TRY(cudaSetDevice(u->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n = P->ops.size();
+    std::vector<cudaEvent_t> ev(2 * n);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    std::vector<double> acc(n, 0.0);
+    for (int it = 0; it < iters + 1; ++it) {          // first pass is a warm-up
+        for (size_t i = 0; i < n; ++i) {
+            CUDA_TRY(cudaEventRecord(ev[2 * i], s));
+            P->ops[i](s);
+            CUDA_TRY(cudaEventRecord(ev[2 * i + 1], s));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (it == 0) continue;
+        for (size_t i = 0; i < n; ++i) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+            acc[i] += ms;
+        }
+    }
+    for (size_t i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
+    for (auto& e : ev) cudaEventDestroy(e);
     API_END
 }
 
