@@ -43,21 +43,32 @@ __global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, Tr
 }
 
 // =====================================================================================
-// GroupNorm statistics (deterministic two-level reduction, fp64 combine).
+// GroupNorm statistics (deterministic two-level reduction, fp64 combine) + zero-fill of the rollout
+// axis-sum accumulators that the following k_gn_silu launch adds into.
 // reference src/diffusion/nn.py:17-19 (GroupNorm32 computes in fp32), unet_triplane.py:63-84
 // grid (chunks, 3, B), block (C/4, NY); partial [B][3][chunks][32][2] double; ticket [B][3]
 // stats out [B][3][32][2] = (mean, rstd)
 // =====================================================================================
 template <int NY>
 __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, int chunks, double* __restrict__ partial,
-                           unsigned int* __restrict__ ticket, float* __restrict__ stats) {
+                                                   unsigned int* __restrict__ ticket, float* __restrict__ stats,
+                                                   unsigned long long* __restrict__ zero_buf, long long zero_n) {
     extern __shared__ float red[];   // [NY][2][C]
     __shared__ bool is_last;
+    __shared__ double fin[2][8][kGroups];
     const int plane = blockIdx.y, b = blockIdx.z, chunk = blockIdx.x;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
+    if (zero_buf) {
+        const long long ncta = static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z;
+        const long long cta = (static_cast<long long>(b) * 3 + plane) * gridDim.x + chunk;
+        const long long per = (zero_n + ncta - 1) / ncta;
+        const long long z0 = cta * per, z1 = min(zero_n, z0 + per);
+        for (long long i = z0 + tid; i < z1; i += nthr) zero_buf[i] = 0ull;
+    }
     const int npx = d.rows[plane] * d.cols[plane];
     const int ppc = (npx + chunks - 1) / chunks;
     const int p0 = chunk * ppc, p1 = min(npx, p0 + ppc);
-    const int tx = threadIdx.x, ty = threadIdx.y;
     const float* xp = x.p[plane] + static_cast<size_t>(b) * npx * C;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
     for (int px = p0 + ty; px < p1; px += NY) {
@@ -70,18 +81,14 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
     rs[0] = s.x; rs[1] = s.y; rs[2] = s.z; rs[3] = s.w;
     rq[0] = q.x; rq[1] = q.y; rq[2] = q.z; rq[3] = q.w;
     __syncthreads();
-    const int tid = ty * blockDim.x + tx;
     const int cpg = C / kGroups;
     double* part = partial + ((static_cast<size_t>(b) * 3 + plane) * chunks + chunk) * kGroups * 2;
-    if (tid < kGroups) {
-        double ds = 0.0, dq = 0.0;
+    if (tid < 2 * kGroups) {
+        const int g = tid >> 1, which = tid & 1;
+        double acc = 0.0;
         for (int y = 0; y < NY; ++y)
-            for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
-                ds += static_cast<double>(red[(y * 2 + 0) * C + c]);
-                dq += static_cast<double>(red[(y * 2 + 1) * C + c]);
-            }
-        part[tid * 2 + 0] = ds;
-        part[tid * 2 + 1] = dq;
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(red[(y * 2 + which) * C + c]);
+        part[g * 2 + which] = acc;
     }
     __threadfence();
     __syncthreads();
@@ -92,12 +99,20 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // last CTA of this (sample, plane): 8 lanes per (group, sum|sumsq) walk the chunks in a fixed order
+    const double* pp = partial + (static_cast<size_t>(b) * 3 + plane) * chunks * kGroups * 2;
+    if (tid < 2 * kGroups * 8) {
+        const int slot = tid >> 6, gw = tid & 63;      // gw = g*2 + which
+        double acc = 0.0;
+        for (int ch = slot; ch < chunks; ch += 8) acc += __ldcg(pp + ch * kGroups * 2 + gw);
+        fin[gw & 1][slot][gw >> 1] = acc;
+    }
+    __syncthreads();
     if (tid < kGroups) {
-        const volatile double* pp = partial + (static_cast<size_t>(b) * 3 + plane) * chunks * kGroups * 2;
         double ds = 0.0, dq = 0.0;
-        for (int ch = 0; ch < chunks; ++ch) {
-            ds += pp[(ch * kGroups + tid) * 2 + 0];
-            dq += pp[(ch * kGroups + tid) * 2 + 1];
+        for (int k = 0; k < 8; ++k) {
+            ds += fin[0][k][tid];
+            dq += fin[1][k][tid];
         }
         const double n = static_cast<double>(npx) * cpg;
         const double mean = ds / n;
@@ -113,14 +128,19 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
 // =====================================================================================
 // Fused GroupNorm-apply (+FiLM) + SiLU -> fp16 (hi, lo) conv operand, plus the rollout axis sums.
 // reference unet_triplane.py:63-95 (norm, SiLU), :285-297 (FiLM), :37-46 (axis means)
-// One CTA = TH full rows of one plane of one sample.  grid (max_strips, 3, B), block (C/4, NY).
-//   rowsum  [B][rows][C]           complete (sum over cols of the activation)
-//   colpart [B][strips][cols][C]   partial over this strip's rows (summed by k_roll1d, fixed order)
+// One CTA = an 8-row x TC-column tile of one plane of one sample.  grid (max tiles, 3, B), block (C/4, ny).
+// Axis sums are accumulated as 64-bit fixed point (value * 2^24) with integer atomics: exact, hence
+// independent of tile order / batch composition / GPU count.  sums[b][seg_off[plane*2+kind] + pos][C],
+// kind 0 = sum over columns (indexed by row), kind 1 = sum over rows (indexed by column).
 // =====================================================================================
+constexpr int kGsRows = 8;
+constexpr float kFixScale = 16777216.f;          // 2^24
+constexpr double kFixInv = 1.0 / 16777216.0;
+
 struct GnSiluArgs {
     TriCF x;          // fp32 [B][rows][cols][C]
     TriDims d;
-    int C, TH;
+    int C, csplit;    // tiles = 8-row strips x csplit column segments
     const float* stats;       // [B][3][32][2]
     TriCF gamma, beta;        // [C]
     const float* film;        // [rows][film_dim] or nullptr
@@ -128,19 +148,28 @@ struct GnSiluArgs {
     int film_dim, film_off;   // scale at film_off, shift at film_off + C
     TriH a;                   // out [2][B][rows][cols][C]
     TriH x16;                 // optional raw copy of x as (hi, lo) for the 1x1 skip GEMM
-    TriF rowsum, colpart;     // nullptr when rollout is off
+    unsigned long long* sums; // nullptr when rollout is off
+    int seg_off[6];
+    int total_len;
 };
 
-template <int NY, int TH_MAX>
-__global__ void __launch_bounds__(1024) k_gn_silu(GnSiluArgs A, int B) {
-    extern __shared__ float sm[];   // coefA[C], coefB[C], red[NY][TH_MAX][C]
+__device__ __forceinline__ void fix_add(unsigned long long* p, float v) {
+    atomicAdd(p, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
+}
+
+__global__ void __launch_bounds__(256) k_gn_silu(GnSiluArgs A, int B) {
+    extern __shared__ float sm[];   // coefA[C], coefB[C], red[ny][8][C]
     const int plane = blockIdx.y, b = blockIdx.z;
     const int rows = A.d.rows[plane], cols = A.d.cols[plane], C = A.C;
-    const int r0 = blockIdx.x * A.TH;
+    const int TC = (cols + A.csplit - 1) / A.csplit;
+    const int ctiles = (cols + TC - 1) / TC;
+    const int strip = blockIdx.x / ctiles, ct = blockIdx.x - strip * ctiles;
+    const int r0 = strip * kGsRows;
     if (r0 >= rows) return;
-    const int nr = min(A.TH, rows - r0);
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
+    const int nr = min(kGsRows, rows - r0);
+    const int c0 = ct * TC, c1 = min(cols, c0 + TC);
+    const int tx = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
+    const int tid = ty * blockDim.x + tx, nthr = blockDim.x * ny;
     float* coefA = sm;
     float* coefB = sm + C;
     float* red = sm + 2 * C;
@@ -169,115 +198,153 @@ __global__ void __launch_bounds__(1024) k_gn_silu(GnSiluArgs A, int B) {
     const float* xp = A.x.p[plane] + sample_off;
     __half* ap = A.a.p[plane] + sample_off;
     __half* xq = A.x16.p[plane] ? A.x16.p[plane] + sample_off : nullptr;
-    const bool sums = A.rowsum.p[plane] != nullptr;
-    float4 racc[TH_MAX];
+    unsigned long long* srow = nullptr;
+    unsigned long long* scol = nullptr;
+    if (A.sums) {
+        unsigned long long* sb = A.sums + static_cast<size_t>(b) * A.total_len * C;
+        srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
+        scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
+    }
+    float4 racc[kGsRows];
 #pragma unroll
-    for (int r = 0; r < TH_MAX; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = ty; c < cols; c += NY) {
+    for (int r = 0; r < kGsRows; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = c0 + ty; c < c1; c += ny) {
+        float4 v[kGsRows];
+#pragma unroll
+        for (int r = 0; r < kGsRows; ++r)
+            if (r < nr) v[r] = __ldg(reinterpret_cast<const float4*>(xp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4));
         float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < TH_MAX; ++r) {
+        for (int r = 0; r < kGsRows; ++r) {
             if (r < nr) {
                 const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
-                float4 v = __ldg(reinterpret_cast<const float4*>(xp + off));
-                if (xq) store_split4(xq + off, xq + lo_off + off, v);
+                if (xq) store_split4(xq + off, xq + lo_off + off, v[r]);
                 float4 y;
-                y.x = silu_f(fmaf(v.x, ca.x, cb.x));
-                y.y = silu_f(fmaf(v.y, ca.y, cb.y));
-                y.z = silu_f(fmaf(v.z, ca.z, cb.z));
-                y.w = silu_f(fmaf(v.w, ca.w, cb.w));
+                y.x = silu_f(fmaf(v[r].x, ca.x, cb.x));
+                y.y = silu_f(fmaf(v[r].y, ca.y, cb.y));
+                y.z = silu_f(fmaf(v[r].z, ca.z, cb.z));
+                y.w = silu_f(fmaf(v[r].w, ca.w, cb.w));
                 store_split4(ap + off, ap + lo_off + off, y);
                 cacc.x += y.x; cacc.y += y.y; cacc.z += y.z; cacc.w += y.w;
                 racc[r].x += y.x; racc[r].y += y.y; racc[r].z += y.z; racc[r].w += y.w;
             }
         }
-        if (sums) {
-            float* cp = A.colpart.p[plane] +
-                        ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * cols + c) * C + tx * 4;
-            *reinterpret_cast<float4*>(cp) = cacc;
+        if (scol) {
+            unsigned long long* p = scol + static_cast<size_t>(c) * C + tx * 4;
+            fix_add(p, cacc.x); fix_add(p + 1, cacc.y); fix_add(p + 2, cacc.z); fix_add(p + 3, cacc.w);
         }
     }
-    if (!sums) return;
+    if (!srow) return;
 #pragma unroll
-    for (int r = 0; r < TH_MAX; ++r)
-        *reinterpret_cast<float4*>(red + (static_cast<size_t>(ty) * TH_MAX + r) * C + tx * 4) = racc[r];
+    for (int r = 0; r < kGsRows; ++r)
+        *reinterpret_cast<float4*>(red + (static_cast<size_t>(ty) * kGsRows + r) * C + tx * 4) = racc[r];
     __syncthreads();
     for (int i = tid; i < nr * C; i += nthr) {
         int r = i / C, c = i - r * C;
         float acc = 0.f;
-        for (int y = 0; y < NY; ++y) acc += red[(static_cast<size_t>(y) * TH_MAX + r) * C + c];
-        A.rowsum.p[plane][(static_cast<size_t>(b) * rows + r0 + r) * C + c] = acc;
+        for (int y = 0; y < ny; ++y) acc += red[(static_cast<size_t>(y) * kGsRows + r) * C + c];
+        fix_add(srow + static_cast<size_t>(r0 + r) * C + c, acc);
     }
 }
 
 // =====================================================================================
 // Rollout 1-D terms.  Two thirds of a rollout conv's input channels are constant along one image
 // axis (unet_triplane.py:37-46), so their 3x3 conv collapses exactly to a 1-D conv along the other
-// axis, with the zero padding only distinguishing first / interior / last position across.
-//   T[b][cls][pos][co] = sum_{across in cls} sum_{along, c} mean[pos+along-1][c] * wr[along*C+c][across*Cout+co]
-//   cls: 0 interior {0,1,2}, 1 first {1,2}, 2 last {0,1}, 3 single {1}
-// grid (ceil(Lmax/8), 6, B): blockIdx.y = plane*2 + group.  block 256.
+// axis, with the zero padding only distinguishing first / interior / last position across:
+//   T[b][cls][pos][co] = sum_{along, c} mean[pos+along-1][c] * wc[along*C + c][cls*Cout + co]
+//   wc[..][cls] = sum of the taps `across` that class keeps: 0 interior {0,1,2}, 1 first {1,2}, 2 last {0,1}, 3 single {1}
+// A small fp32 GEMM (M = positions, K = 3C, N = ncls*Cout) on CUDA cores: 16 positions x 64 outputs per CTA,
+// weights streamed through shared memory with cp.async double buffering.
+// grid (ceil(Lmax/16), 6 * ntn, B): blockIdx.y = (plane*2 + group) * ntn + n_tile.  block 128.
 // =====================================================================================
 struct Roll1dSrc {
-    const float* sum;   // rowsum [B][L][C] or colpart [B][nparts][L][C]
-    int nparts;         // 1 for rowsum
+    int sum_off;        // segment offset (positions) of the source sums inside a sample's block
     float inv_count;    // 1 / (length of the averaged axis)
     int L;
-    const float* wr;    // [3*C][3*Cout]
+    int ncls;           // 3, or 4 when the axis across has length 1
+    const float* wc;    // [3*C][4*Cout]
     float* T;           // [B][4][L][Cout]
 };
 struct Roll1dArgs {
     Roll1dSrc s[6];
-    int C, Cout;
+    const unsigned long long* sums;   // [B][total_len][C] fixed point
+    int total_len;
+    int C, Cout, ntn;
 };
 
-__global__ void __launch_bounds__(256) k_roll1d(Roll1dArgs A) {
-    constexpr int POS = 8;
-    extern __shared__ float sm[];     // src[(POS+2)][C], acc[POS][3*Cout]
-    const Roll1dSrc S = A.s[blockIdx.y];
-    const int b = blockIdx.z, C = A.C, Cout = A.Cout, N = 3 * Cout;
-    const int p0 = blockIdx.x * POS;
-    if (S.T == nullptr || p0 >= S.L) return;
-    float* src = sm;
-    float* accs = sm + (POS + 2) * C;
-    for (int i = threadIdx.x; i < (POS + 2) * C; i += blockDim.x) {
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__global__ void __launch_bounds__(128) k_roll1d(Roll1dArgs A) {
+    constexpr int POS = 16, NT = 64, KC = 32;
+    extern __shared__ __align__(16) float sm1[];     // means[(POS+2)][C+4], wbuf[2][KC][NT]
+    const int src_id = blockIdx.y / A.ntn, nt = blockIdx.y - src_id * A.ntn;
+    const Roll1dSrc S = A.s[src_id];
+    const int b = blockIdx.z, C = A.C, Cout = A.Cout, N4 = 4 * Cout;
+    const int p0 = blockIdx.x * POS, n0 = nt * NT;
+    if (S.T == nullptr || p0 >= S.L || n0 >= S.ncls * Cout) return;
+    const int CP = C + 4;
+    float* means = sm1;
+    float* wbuf = sm1 + (POS + 2) * CP;
+    const int tid = threadIdx.x;
+    const int K = 3 * C, nchunks = K / KC;
+    auto load_w = [&](int chunk, int buf) {
+        // KC rows x 64 floats = KC x 16 x 16 B
+        for (int i = tid; i < KC * (NT / 4); i += 128) {
+            int k = i / (NT / 4), v = i - k * (NT / 4);
+            cp_async16(wbuf + (buf * KC + k) * NT + v * 4, S.wc + static_cast<size_t>(chunk * KC + k) * N4 + n0 + v * 4);
+        }
+        cp_async_commit();
+    };
+    load_w(0, 0);
+    const unsigned long long* sb = A.sums + (static_cast<size_t>(b) * A.total_len + S.sum_off) * C;
+    const double scale = kFixInv * static_cast<double>(S.inv_count);
+    for (int i = tid; i < (POS + 2) * C; i += 128) {
         int j = i / C, c = i - j * C, pos = p0 + j - 1;
         float v = 0.f;
-        if (pos >= 0 && pos < S.L) {
-            const float* base = S.sum + (static_cast<size_t>(b) * S.nparts * S.L + pos) * C + c;
-            for (int k = 0; k < S.nparts; ++k) v += base[static_cast<size_t>(k) * S.L * C];
-            v *= S.inv_count;
-        }
-        src[i] = v;
+        if (pos >= 0 && pos < S.L)
+            v = static_cast<float>(static_cast<double>(static_cast<long long>(sb[static_cast<size_t>(pos) * C + c])) * scale);
+        means[j * CP + c] = v;
     }
-    __syncthreads();
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        float acc[POS];
+    const int tn = tid & 15, tp = tid >> 4;          // 4 outputs x 2 positions per thread
+    float acc[2][4];
 #pragma unroll
-        for (int p = 0; p < POS; ++p) acc[p] = 0.f;
-        for (int al = 0; al < 3; ++al) {
-            const float* wcol = S.wr + static_cast<size_t>(al) * C * N + n;
-            const float* sp = src + al * C;      // src row (p + al) == position p + al - 1
-            for (int c = 0; c < C; ++c) {
-                float wv = __ldg(wcol + static_cast<size_t>(c) * N);
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int p = 0; p < POS; ++p) acc[p] = fmaf(sp[p * C + c], wv, acc[p]);
-            }
+        for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (ch + 1 < nchunks) {
+            load_w(ch + 1, (ch + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-#pragma unroll
-        for (int p = 0; p < POS; ++p) accs[p * N + n] = acc[p];
+        __syncthreads();
+        const int kk = ch * KC, al = kk / C, cb = kk - al * C;      // a chunk never straddles a tap (C % 32 == 0)
+        const float* wb = wbuf + (ch & 1) * KC * NT + tn * 4;
+        const float* m0 = means + (tp * 2 + al) * CP + cb;
+#pragma unroll 8
+        for (int k = 0; k < KC; ++k) {
+            const float4 w = *reinterpret_cast<const float4*>(wb + k * NT);
+            const float s0 = m0[k], s1 = m0[CP + k];
+            acc[0][0] = fmaf(s0, w.x, acc[0][0]); acc[0][1] = fmaf(s0, w.y, acc[0][1]);
+            acc[0][2] = fmaf(s0, w.z, acc[0][2]); acc[0][3] = fmaf(s0, w.w, acc[0][3]);
+            acc[1][0] = fmaf(s1, w.x, acc[1][0]); acc[1][1] = fmaf(s1, w.y, acc[1][1]);
+            acc[1][2] = fmaf(s1, w.z, acc[1][2]); acc[1][3] = fmaf(s1, w.w, acc[1][3]);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < POS * Cout; i += blockDim.x) {
-        int p = i / Cout, co = i - p * Cout, pos = p0 + p;
-        if (pos >= S.L) continue;
-        float a0 = accs[p * N + co], a1 = accs[p * N + Cout + co], a2 = accs[p * N + 2 * Cout + co];
-        float* T = S.T + static_cast<size_t>(b) * 4 * S.L * Cout + static_cast<size_t>(pos) * Cout + co;
-        const size_t cs = static_cast<size_t>(S.L) * Cout;
-        T[0] = a0 + a1 + a2;
-        T[cs] = a1 + a2;
-        T[2 * cs] = a0 + a1;
-        T[3 * cs] = a1;
+    const int n = n0 + tn * 4, cls = n / Cout, co = n - cls * Cout;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int pos = p0 + tp * 2 + j;
+        if (pos < S.L)
+            *reinterpret_cast<float4*>(S.T + ((static_cast<size_t>(b) * 4 + cls) * S.L + pos) * Cout + co) =
+                make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
     }
 }
 

@@ -108,7 +108,7 @@ struct DevConv3 {        // one 3x3 TriplaneConv (+ optional fused 1x1 skip)
     float* w_orig[3] = {};      // [Cout][Cw][3][3]
     float* wskip_orig[3] = {};  // [Cout][Cs]
     __half* w_pack[3] = {};     // [2][Cout][Ktot]
-    float* wr[3][2] = {};       // rollout 1-D weights [3C][3Cout] per (plane, group)
+    float* wr[3][2] = {};       // rollout 1-D weights [3C][4Cout] (border classes pre-summed) per (plane, group)
     float* bias[3] = {};        // conv bias (+ skip bias)
 };
 struct DevNorm {
@@ -307,18 +307,22 @@ static std::vector<uint16_t> pack_conv(const std::vector<float>& w, int Cout, in
     }
     return out;
 }
-// Rollout 1-D weights of group g (1 or 2) of one plane: wr[(along*C + c)][(across*Cout + co)].
+// Rollout 1-D weights of group g (1 or 2) of one plane, pre-summed per border class:
+//   wc[(along*C + c)][(cls*Cout + co)] = sum_{across kept by cls} W[co][g*C + c][kh][kw]
 // row_varying: along = kh, across = kw;  col_varying: along = kw, across = kh.
+// cls: 0 interior keeps {0,1,2}, 1 first keeps {1,2}, 2 last keeps {0,1}, 3 single keeps {1}  (zero padding)
 static std::vector<float> pack_roll(const std::vector<float>& w, int Cout, int C, int g, bool row_varying) {
-    const int Cw = 3 * C, N = 3 * Cout;
-    std::vector<float> out(static_cast<size_t>(3) * C * N);
+    const int Cw = 3 * C, N = 4 * Cout;
+    static const bool keep[4][3] = {{true, true, true}, {false, true, true}, {true, true, false}, {false, true, false}};
+    std::vector<float> out(static_cast<size_t>(3) * C * N, 0.f);
     for (int co = 0; co < Cout; ++co)
         for (int c = 0; c < C; ++c)
             for (int kh = 0; kh < 3; ++kh)
                 for (int kw = 0; kw < 3; ++kw) {
                     const float v = w[((static_cast<size_t>(co) * Cw + g * C + c) * 3 + kh) * 3 + kw];
                     const int along = row_varying ? kh : kw, across = row_varying ? kw : kh;
-                    out[(static_cast<size_t>(along) * C + c) * N + across * Cout + co] = v;
+                    for (int cls = 0; cls < 4; ++cls)
+                        if (keep[cls][across]) out[(static_cast<size_t>(along) * C + c) * N + cls * Cout + co] += v;
                 }
     return out;
 }
@@ -418,9 +422,8 @@ static void finalize(s3d_unet* u) {
     }
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_gn_silu<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_gn_silu<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_gn_silu<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_gn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_roll1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_out_head, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaDeviceSynchronize());
     u->finalized = true;
@@ -473,8 +476,32 @@ struct PlanBuilder {
     static TriCF cf(const TriF& t) { return TriCF{{t.p[0], t.p[1], t.p[2]}}; }
     static TriCF cf3(float* const* t) { return TriCF{{t[0], t[1], t[2]}}; }
 
-    // ---- GroupNorm statistics
-    float* stats(const ActF& x) {
+    // ---- rollout axis-sum accumulators of one GN+SiLU site (64-bit fixed point, see k_gn_silu)
+    struct Sums {
+        unsigned long long* buf = nullptr;   // [B][total_len][C]
+        int seg_off[6] = {};                 // plane*2 + kind (0: indexed by row, 1: indexed by column)
+        int total_len = 0;
+        long long count = 0;
+    };
+    Sums alloc_sums(int level, int C) {
+        Sums S;
+        const TriDims d = dims[level];
+        int off = 0;
+        for (int p = 0; p < 3; ++p) {
+            S.seg_off[p * 2 + 0] = off;
+            off += d.rows[p];
+            S.seg_off[p * 2 + 1] = off;
+            off += d.cols[p];
+        }
+        S.total_len = off;
+        S.count = static_cast<long long>(B) * off * C;
+        S.buf = dev_alloc<unsigned long long>(P->allocs, static_cast<size_t>(S.count));
+        CUDA_TRY(cudaMemset(S.buf, 0, sizeof(unsigned long long) * S.count));
+        return S;
+    }
+
+    // ---- GroupNorm statistics (+ zero-fill of the sums the following gn_silu accumulates into)
+    float* stats(const ActF& x, const Sums* zero = nullptr) {
         const int level = x.level, C = x.C;
         S3D_CHECK(C % kGroups == 0 && C % 4 == 0 && C / 4 <= 128, "unsupported channel count for GroupNorm32");
         const int chunks = std::max(1, std::min(64, max_px(level) / 64));
@@ -485,35 +512,41 @@ struct PlanBuilder {
         TriCF xc = cf(x.p);
         TriDims d = dims[level];
         const int Bv = B;
+        unsigned long long* zb = zero ? zero->buf : nullptr;
+        const long long zn = zero ? zero->count : 0;
         add_op("k_gn_stats", 0.0, [=](cudaStream_t s) {
             dim3 grid(chunks, 3, Bv), block(C / 4, 8);
-            k_gn_stats<8><<<grid, block, sizeof(float) * 8 * 2 * C, s>>>(xc, d, C, chunks, partial, ticket, st);
+            k_gn_stats<8><<<grid, block, sizeof(float) * 8 * 2 * C, s>>>(xc, d, C, chunks, partial, ticket, st, zb, zn);
             LAUNCH_CHECK("k_gn_stats");
         });
         return st;
     }
 
-    struct Sums {
-        TriF rowsum, colpart;
-        int strips[3];
-    };
-
     // ---- GN apply + SiLU (+FiLM) -> fp16 operands (+ raw x16) (+ axis sums)
-    Sums gn_silu(const ActF& x, const float* st, const DevNorm& n, int film_off, const Act16& a, const Act16* x16) {
+    void gn_silu(const ActF& x, const float* st, const DevNorm& n, int film_off, const Act16& a, const Act16* x16,
+                 const Sums* S) {
         const int level = x.level, C = x.C;
         const TriDims d = dims[level];
-        int ny = 16;
-        while ((C / 4) * ny > 1024) ny /= 2;
-        S3D_CHECK(ny >= 4, "channel count too large for k_gn_silu");
-        // rows per strip: aim for >= ~148 CTAs
-        const int total_rows = d.rows[0] + d.rows[1] + d.rows[2];
-        int TH = 4;
-        while (TH > 1 && (total_rows / TH) * B < 148) TH /= 2;
+        const int bx = C / 4;
+        S3D_CHECK(bx <= 256, "channel count too large for k_gn_silu");
+        const int ny = std::max(1, 256 / bx);
+        // tiles = 8-row strips x csplit column segments; csplit depends on the geometry only (never on B), so the
+        // result is independent of the batch composition.  Aim for >= 148 CTAs at B = 1.
+        int strips_total = 0, max_strips = 0, min_cols = 1 << 30;
+        for (int p = 0; p < 3; ++p) {
+            const int sp = (d.rows[p] + kGsRows - 1) / kGsRows;
+            strips_total += sp;
+            max_strips = std::max(max_strips, sp);
+            min_cols = std::min(min_cols, d.cols[p]);
+        }
+        int csplit = std::max(1, (148 + strips_total - 1) / strips_total);
+        csplit = std::min(csplit, std::max(1, min_cols / ny));
+        csplit = std::max(csplit, 1);
         GnSiluArgs A{};
         A.x = cf(x.p);
         A.d = d;
         A.C = C;
-        A.TH = TH;
+        A.csplit = csplit;
         A.stats = st;
         A.gamma = cf3(n.gamma);
         A.beta = cf3(n.beta);
@@ -521,42 +554,27 @@ struct PlanBuilder {
         A.film_off = film_off;
         A.a = a.p;
         if (x16) A.x16 = x16->p;
-        Sums S{};
-        int max_strips = 0;
-        for (int p = 0; p < 3; ++p) {
-            S.strips[p] = (d.rows[p] + TH - 1) / TH;
-            max_strips = std::max(max_strips, S.strips[p]);
-        }
-        if (u->cfg.rollout) {
-            for (int p = 0; p < 3; ++p) {
-                S.rowsum.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * d.rows[p] * C);
-                // colpart is indexed with gridDim.x (= max_strips) strips for every plane
-                S.colpart.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * max_strips * d.cols[p] * C);
-                S.strips[p] = max_strips;
-            }
-            // strips beyond a plane's row count are never written: clear once so the fixed-order sum stays exact
-            for (int p = 0; p < 3; ++p)
-                CUDA_TRY(cudaMemset(S.colpart.p[p], 0, sizeof(float) * static_cast<size_t>(B) * max_strips * d.cols[p] * C));
-            A.rowsum = S.rowsum;
-            A.colpart = S.colpart;
+        if (S) {
+            A.sums = S->buf;
+            for (int i = 0; i < 6; ++i) A.seg_off[i] = S->seg_off[i];
+            A.total_len = S->total_len;
         }
         const bool use_film = film_off >= 0;
-        const size_t smem = sizeof(float) * (2 + static_cast<size_t>(ny) * 4) * C;
+        const size_t smem = sizeof(float) * (2 + static_cast<size_t>(ny) * kGsRows) * C;
+        S3D_CHECK(smem <= 100 * 1024, "k_gn_silu shared memory");
         Plan* Pp = P;
         const int Bv = B;
+        const int gx = max_strips * csplit;
         add_op("k_gn_silu", 0.0, [=](cudaStream_t s) {
             GnSiluArgs Al = A;
             if (use_film) {
                 Al.film = Pp->film;
                 Al.film_row = Pp->film_row;
             }
-            dim3 grid(max_strips, 3, Bv), block(C / 4, ny);
-            if (ny == 16) k_gn_silu<16, 4><<<grid, block, smem, s>>>(Al, Bv);
-            else if (ny == 8) k_gn_silu<8, 4><<<grid, block, smem, s>>>(Al, Bv);
-            else k_gn_silu<4, 4><<<grid, block, smem, s>>>(Al, Bv);
+            dim3 grid(gx, 3, Bv), block(bx, ny);
+            k_gn_silu<<<grid, block, smem, s>>>(Al, Bv);
             LAUNCH_CHECK("k_gn_silu");
         });
-        return S;
     }
 
     struct TBuf {
@@ -574,40 +592,41 @@ struct PlanBuilder {
         Roll1dArgs A{};
         A.C = C;
         A.Cout = Cout;
-        // (plane, group) -> source plane / kind; see roll_row_varying() and unet_triplane.py:37-46
+        A.sums = S.buf;
+        A.total_len = S.total_len;
+        // (plane, group) -> source plane / which of its sums; see roll_row_varying() and unet_triplane.py:37-46
+        //   kind 0 = the source plane's sum over its columns (indexed by its row), kind 1 = sum over rows (by column)
         struct SrcDef {
-            int sp;
-            bool colsum;
+            int sp, kind;
         };
-        const SrcDef def[3][2] = {{{2, false}, {1, false}}, {{0, false}, {2, true}}, {{0, true}, {1, true}}};
-        int Lmax = 0;
+        const SrcDef def[3][2] = {{{2, 0}, {1, 0}}, {{0, 0}, {2, 1}}, {{0, 1}, {1, 1}}};
+        int Lmax = 0, ncls_max = 3;
         for (int p = 0; p < 3; ++p)
             for (int g = 0; g < 2; ++g) {
                 const SrcDef sd = def[p][g];
                 const bool rowv = roll_row_varying(p, g + 1);
                 Roll1dSrc& s = A.s[p * 2 + g];
                 s.L = rowv ? d.rows[p] : d.cols[p];
-                if (sd.colsum) {
-                    s.sum = S.colpart.p[sd.sp];
-                    s.nparts = S.strips[sd.sp];
-                    s.inv_count = 1.f / static_cast<float>(d.rows[sd.sp]);
-                    S3D_CHECK(d.cols[sd.sp] == s.L, "rollout geometry");
-                } else {
-                    s.sum = S.rowsum.p[sd.sp];
-                    s.nparts = 1;
-                    s.inv_count = 1.f / static_cast<float>(d.cols[sd.sp]);
-                    S3D_CHECK(d.rows[sd.sp] == s.L, "rollout geometry");
-                }
-                s.wr = cv.wr[p][g];
+                const int across = rowv ? d.cols[p] : d.rows[p];
+                s.ncls = across == 1 ? 4 : 3;
+                ncls_max = std::max(ncls_max, s.ncls);
+                s.sum_off = S.seg_off[sd.sp * 2 + sd.kind];
+                const int src_len = sd.kind == 0 ? d.rows[sd.sp] : d.cols[sd.sp];
+                const int avg_len = sd.kind == 0 ? d.cols[sd.sp] : d.rows[sd.sp];
+                S3D_CHECK(src_len == s.L, "rollout geometry");
+                s.inv_count = 1.f / static_cast<float>(avg_len);
+                s.wc = cv.wr[p][g];
                 s.T = rowv ? T.Trow.p[p] : T.Tcol.p[p];
                 Lmax = std::max(Lmax, s.L);
             }
-        const size_t smem = sizeof(float) * (static_cast<size_t>(10) * C + static_cast<size_t>(8) * 3 * Cout);
-        S3D_CHECK(smem <= 48 * 1024, "k_roll1d shared memory");
+        A.ntn = ncls_max * Cout / 64;
+        S3D_CHECK(C % 32 == 0 && Cout % 64 == 0, "k_roll1d tiling");
+        const size_t smem = sizeof(float) * (static_cast<size_t>(18) * (C + 4) + 2 * 32 * 64);
+        S3D_CHECK(smem <= 100 * 1024, "k_roll1d shared memory");
         const int Bv = B;
         add_op("k_roll1d", 0.0, [=](cudaStream_t s) {
-            dim3 grid((Lmax + 7) / 8, 6, Bv);
-            k_roll1d<<<grid, 256, smem, s>>>(A);
+            dim3 grid((Lmax + 15) / 16, 6 * A.ntn, Bv);
+            k_roll1d<<<grid, 128, smem, s>>>(A);
             LAUNCH_CHECK("k_roll1d");
         });
         return T;
@@ -708,18 +727,23 @@ struct PlanBuilder {
         const int level = x.level;
         const bool ro = u->cfg.rollout, ssn = u->cfg.use_scale_shift_norm;
         S3D_CHECK(x.C == b.cin, "res block input width");
-        float* st1 = stats(x);
+        Sums s1{}, s2{};
+        if (ro) {
+            s1 = alloc_sums(level, b.cin);
+            s2 = alloc_sums(level, b.cout);
+        }
+        float* st1 = stats(x, ro ? &s1 : nullptr);
         Act16 a1 = alloc16(level, b.cin);
         Act16 x16{};
         if (b.has_skip) x16 = alloc16(level, b.cin);
-        Sums s1 = gn_silu(x, st1, w.n1, -1, a1, b.has_skip ? &x16 : nullptr);
+        gn_silu(x, st1, w.n1, -1, a1, b.has_skip ? &x16 : nullptr, ro ? &s1 : nullptr);
         TBuf t1{};
         if (ro) t1 = roll1d(s1, level, w.c1);
         ActF h1 = allocF(level, b.cout, b.name + ".h1");
         conv(a1, level, w.c1, ro ? &t1 : nullptr, nullptr, nullptr, ssn ? -1 : b.film_off, h1);
-        float* st2 = stats(h1);
+        float* st2 = stats(h1, ro ? &s2 : nullptr);
         Act16 a2 = alloc16(level, b.cout);
-        Sums s2 = gn_silu(h1, st2, w.n2, ssn ? b.film_off : -1, a2, nullptr);
+        gn_silu(h1, st2, w.n2, ssn ? b.film_off : -1, a2, nullptr, ro ? &s2 : nullptr);
         TBuf t2{};
         if (ro) t2 = roll1d(s2, level, w.c2);
         ActF out = allocF(level, b.cout, b.name + ".out");
