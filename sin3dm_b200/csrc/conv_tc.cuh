@@ -163,24 +163,54 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         const int r = h0 + (m >> 4), c = w0 + (m & 15);
         const int rows = A.d.rows[plane], cols = A.d.cols[plane];
         const bool valid = r < rows && c < cols;
+        const size_t px = static_cast<size_t>(b) * rows * cols + static_cast<size_t>(r) * cols + c;
+        // Everything the epilogue adds to the accumulator (bias + rollout 1-D terms + additive embedding + identity
+        // residual) is gathered into registers NOW, while the MMA pipeline is still running, so no global-load
+        // latency is left on the critical path after the accumulators land.
+        float pre[kBN];
+        {
+            const float4* bias4 = reinterpret_cast<const float4*>(A.e.bias.p[plane] + n0);
+#pragma unroll
+            for (int j = 0; j < kBN / 4; ++j) {
+                const float4 t = __ldg(bias4 + j);
+                pre[4 * j] = t.x; pre[4 * j + 1] = t.y; pre[4 * j + 2] = t.z; pre[4 * j + 3] = t.w;
+            }
+            if (A.e.embadd) {
+                const float4* e4 = reinterpret_cast<const float4*>(
+                    A.e.embadd + static_cast<size_t>(A.e.film_row ? A.e.film_row[b] : b) * A.e.film_dim + A.e.film_off + n0);
+#pragma unroll
+                for (int j = 0; j < kBN / 4; ++j) {
+                    const float4 t = __ldg(e4 + j);
+                    pre[4 * j] += t.x; pre[4 * j + 1] += t.y; pre[4 * j + 2] += t.z; pre[4 * j + 3] += t.w;
+                }
+            }
+            if (valid && A.e.Trow.p[plane]) {
+                const size_t bo = static_cast<size_t>(b) * 4;
+                const float4* tr = reinterpret_cast<const float4*>(
+                    A.e.Trow.p[plane] + ((bo + edge_class(c, cols)) * rows + r) * A.Cout + n0);
+                const float4* tc = reinterpret_cast<const float4*>(
+                    A.e.Tcol.p[plane] + ((bo + edge_class(r, rows)) * cols + c) * A.Cout + n0);
+#pragma unroll
+                for (int j = 0; j < kBN / 4; ++j) {
+                    const float4 t = __ldg(tr + j), u = __ldg(tc + j);
+                    pre[4 * j] += t.x + u.x; pre[4 * j + 1] += t.y + u.y; pre[4 * j + 2] += t.z + u.z;
+                    pre[4 * j + 3] += t.w + u.w;
+                }
+            }
+            if (valid && A.e.resid.p[plane]) {
+                const float4* rs = reinterpret_cast<const float4*>(A.e.resid.p[plane] + px * A.Cout + n0);
+#pragma unroll
+                for (int j = 0; j < kBN / 4; ++j) {
+                    const float4 t = __ldg(rs + j);
+                    pre[4 * j] += t.x; pre[4 * j + 1] += t.y; pre[4 * j + 2] += t.z; pre[4 * j + 3] += t.w;
+                }
+            }
+        }
+        float* __restrict__ outp = A.e.out.p[plane] + px * A.Cout + n0;
         ptx::mbar_wait(tmem_full_bar, 0);
         __syncwarp();
         ptx::tc_fence_after();
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        const size_t px = static_cast<size_t>(b) * rows * cols + static_cast<size_t>(r) * cols + c;
-        const float* bias = A.e.bias.p[plane] + n0;
-        const float* trow = nullptr;
-        const float* tcol = nullptr;
-        if (A.e.Trow.p[plane] && valid) {
-            const size_t bo = static_cast<size_t>(b) * 4;
-            trow = A.e.Trow.p[plane] + ((bo + edge_class(c, cols)) * rows + r) * A.Cout + n0;
-            tcol = A.e.Tcol.p[plane] + ((bo + edge_class(r, rows)) * cols + c) * A.Cout + n0;
-        }
-        const float* resid = (A.e.resid.p[plane] && valid) ? A.e.resid.p[plane] + px * A.Cout + n0 : nullptr;
-        const float* emb = A.e.embadd ? A.e.embadd + static_cast<size_t>(A.e.film_row ? A.e.film_row[b] : b) * A.e.film_dim +
-                                            A.e.film_off + n0
-                                      : nullptr;
-        float* outp = A.e.out.p[plane] + px * A.Cout + n0;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             uint32_t v1[32], v2[32];
@@ -195,26 +225,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     for (int q = 0; q < 4; ++q) {
                         float acc = __uint_as_float(v1[j + q]);
                         if (NSPLIT == 3) acc = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, acc);
-                        o[q] = acc;
+                        o[q] = acc + pre[half * 32 + j + q];
                     }
-                    const int cc = half * 32 + j;
-                    float4 t = __ldg(reinterpret_cast<const float4*>(bias + cc));
-                    o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-                    if (trow) {
-                        t = __ldg(reinterpret_cast<const float4*>(trow + cc));
-                        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-                        t = __ldg(reinterpret_cast<const float4*>(tcol + cc));
-                        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-                    }
-                    if (emb) {
-                        t = __ldg(reinterpret_cast<const float4*>(emb + cc));
-                        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-                    }
-                    if (resid) {
-                        t = __ldg(reinterpret_cast<const float4*>(resid + cc));
-                        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
-                    }
-                    *reinterpret_cast<float4*>(outp + cc) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(outp + half * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
         }

@@ -49,7 +49,6 @@ __global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, Tr
 // grid (chunks, 3, B), block (C/4, NY); partial [B][3][chunks][32][2] double; ticket [B][3]
 // stats out [B][3][32][2] = (mean, rstd)
 // =====================================================================================
-template <int NY>
 __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, int chunks, double* __restrict__ partial,
                                                    unsigned int* __restrict__ ticket, float* __restrict__ stats,
                                                    unsigned long long* __restrict__ zero_buf, long long zero_n) {
@@ -57,7 +56,7 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
     __shared__ bool is_last;
     __shared__ double fin[2][8][kGroups];
     const int plane = blockIdx.y, b = blockIdx.z, chunk = blockIdx.x;
-    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
     const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
     if (zero_buf) {
         const long long ncta = static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z;
@@ -71,10 +70,18 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
     const int p0 = chunk * ppc, p1 = min(npx, p0 + ppc);
     const float* xp = x.p[plane] + static_cast<size_t>(b) * npx * C;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-    for (int px = p0 + ty; px < p1; px += NY) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(xp + static_cast<size_t>(px) * C) + tx);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    for (int px = p0 + ty; px < p1; px += 4 * NY) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            v[k] = px + k * NY < p1 ? __ldg(reinterpret_cast<const float4*>(xp + static_cast<size_t>(px + k * NY) * C) + tx)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w;
+            q.x = fmaf(v[k].x, v[k].x, q.x); q.y = fmaf(v[k].y, v[k].y, q.y);
+            q.z = fmaf(v[k].z, v[k].z, q.z); q.w = fmaf(v[k].w, v[k].w, q.w);
+        }
     }
     float* rs = red + (ty * 2 + 0) * C + tx * 4;
     float* rq = red + (ty * 2 + 1) * C + tx * 4;
@@ -101,8 +108,8 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
     __threadfence();
     // last CTA of this (sample, plane): 8 lanes per (group, sum|sumsq) walk the chunks in a fixed order
     const double* pp = partial + (static_cast<size_t>(b) * 3 + plane) * chunks * kGroups * 2;
-    if (tid < 2 * kGroups * 8) {
-        const int slot = tid >> 6, gw = tid & 63;      // gw = g*2 + which
+    for (int i = tid; i < 2 * kGroups * 8; i += nthr) {
+        const int slot = i >> 6, gw = i & 63;          // gw = g*2 + which
         double acc = 0.0;
         for (int ch = slot; ch < chunks; ch += 8) acc += __ldcg(pp + ch * kGroups * 2 + gw);
         fin[gw & 1][slot][gw >> 1] = acc;
@@ -280,8 +287,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 __global__ void __launch_bounds__(128) k_roll1d(Roll1dArgs A) {
-    constexpr int POS = 16, NT = 64, KC = 32;
-    extern __shared__ __align__(16) float sm1[];     // means[(POS+2)][C+4], wbuf[2][KC][NT]
+    constexpr int POS = 16, NT = 64, KC = 32, ST = 6;     // 6-deep cp.async ring of 32 x 64 weight chunks (48 KiB)
+    extern __shared__ __align__(16) float sm1[];     // means[(POS+2)][C+4], wbuf[ST][KC][NT]
     const int src_id = blockIdx.y / A.ntn, nt = blockIdx.y - src_id * A.ntn;
     const Roll1dSrc S = A.s[src_id];
     const int b = blockIdx.z, C = A.C, Cout = A.Cout, N4 = 4 * Cout;
@@ -292,22 +299,25 @@ __global__ void __launch_bounds__(128) k_roll1d(Roll1dArgs A) {
     float* wbuf = sm1 + (POS + 2) * CP;
     const int tid = threadIdx.x;
     const int K = 3 * C, nchunks = K / KC;
-    auto load_w = [&](int chunk, int buf) {
-        // KC rows x 64 floats = KC x 16 x 16 B
-        for (int i = tid; i < KC * (NT / 4); i += 128) {
-            int k = i / (NT / 4), v = i - k * (NT / 4);
-            cp_async16(wbuf + (buf * KC + k) * NT + v * 4, S.wc + static_cast<size_t>(chunk * KC + k) * N4 + n0 + v * 4);
+    auto load_w = [&](int chunk) {
+        if (chunk < nchunks) {
+            const int buf = chunk % ST;
+            for (int i = tid; i < KC * (NT / 4); i += 128) {      // KC rows x 64 floats = KC x 16 x 16 B
+                int k = i / (NT / 4), v = i - k * (NT / 4);
+                cp_async16(wbuf + (buf * KC + k) * NT + v * 4, S.wc + static_cast<size_t>(chunk * KC + k) * N4 + n0 + v * 4);
+            }
         }
-        cp_async_commit();
+        cp_async_commit();      // always commit (possibly empty) so the group count stays uniform
     };
-    load_w(0, 0);
+#pragma unroll
+    for (int c = 0; c < ST - 1; ++c) load_w(c);
     const unsigned long long* sb = A.sums + (static_cast<size_t>(b) * A.total_len + S.sum_off) * C;
     const double scale = kFixInv * static_cast<double>(S.inv_count);
     for (int i = tid; i < (POS + 2) * C; i += 128) {
         int j = i / C, c = i - j * C, pos = p0 + j - 1;
         float v = 0.f;
         if (pos >= 0 && pos < S.L)
-            v = static_cast<float>(static_cast<double>(static_cast<long long>(sb[static_cast<size_t>(pos) * C + c])) * scale);
+            v = static_cast<float>(static_cast<double>(static_cast<long long>(__ldcg(sb + static_cast<size_t>(pos) * C + c))) * scale);
         means[j * CP + c] = v;
     }
     const int tn = tid & 15, tp = tid >> 4;          // 4 outputs x 2 positions per thread
@@ -317,15 +327,11 @@ __global__ void __launch_bounds__(128) k_roll1d(Roll1dArgs A) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
     for (int ch = 0; ch < nchunks; ++ch) {
-        if (ch + 1 < nchunks) {
-            load_w(ch + 1, (ch + 1) & 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
+        cp_async_wait<ST - 2>();                     // chunk ch has landed (ST-1 groups were in flight)
+        __syncthreads();                             // ... for every thread; also: everyone is done with chunk ch-1
+        load_w(ch + ST - 1);                         // refill the slot chunk ch-1 used
         const int kk = ch * KC, al = kk / C, cb = kk - al * C;      // a chunk never straddles a tap (C % 32 == 0)
-        const float* wb = wbuf + (ch & 1) * KC * NT + tn * 4;
+        const float* wb = wbuf + (ch % ST) * KC * NT + tn * 4;
         const float* m0 = means + (tp * 2 + al) * CP + cb;
 #pragma unroll 8
         for (int k = 0; k < KC; ++k) {
@@ -336,7 +342,6 @@ __global__ void __launch_bounds__(128) k_roll1d(Roll1dArgs A) {
             acc[1][0] = fmaf(s1, w.x, acc[1][0]); acc[1][1] = fmaf(s1, w.y, acc[1][1]);
             acc[1][2] = fmaf(s1, w.z, acc[1][2]); acc[1][3] = fmaf(s1, w.w, acc[1][3]);
         }
-        __syncthreads();
     }
     const int n = n0 + tn * 4, cls = n / Cout, co = n - cls * Cout;
 #pragma unroll

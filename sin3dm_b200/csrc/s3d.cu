@@ -515,8 +515,9 @@ struct PlanBuilder {
         unsigned long long* zb = zero ? zero->buf : nullptr;
         const long long zn = zero ? zero->count : 0;
         add_op("k_gn_stats", 0.0, [=](cudaStream_t s) {
-            dim3 grid(chunks, 3, Bv), block(C / 4, 8);
-            k_gn_stats<8><<<grid, block, sizeof(float) * 8 * 2 * C, s>>>(xc, d, C, chunks, partial, ticket, st, zb, zn);
+            const int ny = std::max(1, std::min(32, 1024 / (C / 4)));
+            dim3 grid(chunks, 3, Bv), block(C / 4, ny);
+            k_gn_stats<<<grid, block, sizeof(float) * ny * 2 * C, s>>>(xc, d, C, chunks, partial, ticket, st, zb, zn);
             LAUNCH_CHECK("k_gn_stats");
         });
         return st;
@@ -621,7 +622,7 @@ struct PlanBuilder {
             }
         A.ntn = ncls_max * Cout / 64;
         S3D_CHECK(C % 32 == 0 && Cout % 64 == 0, "k_roll1d tiling");
-        const size_t smem = sizeof(float) * (static_cast<size_t>(18) * (C + 4) + 2 * 32 * 64);
+        const size_t smem = sizeof(float) * (static_cast<size_t>(18) * (C + 4) + 6 * 32 * 64);
         S3D_CHECK(smem <= 100 * 1024, "k_roll1d shared memory");
         const int Bv = B;
         add_op("k_roll1d", 0.0, [=](cudaStream_t s) {
