@@ -240,4 +240,152 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     }
 }
 
+
+// =====================================================================================
+// Rollout 1-D terms on the tensor cores (replaces the SIMT k_roll1d on the product path).
+//   T[b][cls][pos][co] = sum_{along, c} mean[pos+along-1][c] * wc[cls*Cout + co][along*C + c]
+// Same pipeline as k_conv_tc with a 1 x 128 "patch": M tile = 128 consecutive positions of one source's mean
+// vector (5-D TMA box {64 ch, 128, 1, 1, 1}; the +-1 tap shift and both ends are the TMA zero fill), 3 taps,
+// N tile = 64 of the 4*Cout class-summed output columns.  fp16 (hi, lo) means come from k_gn_silu's tail.
+// grid (sum over the 6 sources of ceil(L/128), 4*Cout/64, B)
+// =====================================================================================
+struct RollTcMaps {
+    CUtensorMap a[6];   // means of source s: (C, L, 1, B, 2) fp16
+    CUtensorMap w[6];   // class-summed 1-D weights: (3C, 4*Cout, 2) fp16, K = along*C + c
+};
+struct RollTcArgs {
+    int L[6], ncls[6];
+    float* T[6];        // [B][4][L][Cout]
+    int tile_start[7];
+    int C, Cout;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kConvThreads, 1) k_roll_tc(const __grid_constant__ RollTcMaps M, const RollTcArgs A) {
+    using Cfg = ConvTcCfg<NSPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int src = 0;
+#pragma unroll
+    for (int k = 1; k < 6; ++k)
+        if (static_cast<int>(blockIdx.x) >= A.tile_start[k]) src = k;
+    const int p0 = (blockIdx.x - A.tile_start[src]) * kBM;
+    const int n0 = blockIdx.y * kBN;
+    const int b = blockIdx.z;
+    if (A.T[src] == nullptr || n0 >= A.ncls[src] * A.Cout) return;      // uniform for the whole CTA
+    const int cblks = A.C / kBK;
+    const int nk = 3 * cblks;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&M.a[src]);
+        ptx::prefetch_tmap(&M.w[src]);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < Cfg::kStages; ++s) {
+                ptx::mbar_init(&full_bar[s], 1);
+                ptx::mbar_init(&empty_bar[s], 1);
+            }
+            ptx::mbar_init(tmem_full_bar, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::kStages;
+                const uint32_t ph = (i / Cfg::kStages) & 1;
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* st = smem + s * Cfg::kStageBytes;
+                ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                const int al = i / cblks, cb = i - al * cblks;
+                ptx::tma_load_5d(st, &M.a[src], &full_bar[s], cb * kBK, p0 + al - 1, 0, b, 0);
+                ptx::tma_load_3d(st + kABytes, &M.w[src], &full_bar[s], i * kBK, n0, 0);
+                if (NSPLIT == 3) {
+                    ptx::tma_load_5d(st + kABytes + kBBytes, &M.a[src], &full_bar[s], cb * kBK, p0 + al - 1, 0, b, 1);
+                    ptx::tma_load_3d(st + 2 * kABytes + kBBytes, &M.w[src], &full_bar[s], i * kBK, n0, 1);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, kBN);
+            const uint32_t d1 = tmem_base, d2 = tmem_base + kBN;
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % Cfg::kStages;
+                const uint32_t ph = (i / Cfg::kStages) & 1;
+                ptx::mbar_wait(&full_bar[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t st = ptx::smem_u32(smem + s * Cfg::kStageBytes);
+                const uint64_t a_hi = ptx::make_sw128_kmajor_desc(st);
+                const uint64_t b_hi = ptx::make_sw128_kmajor_desc(st + kABytes);
+                const uint64_t a_lo = ptx::make_sw128_kmajor_desc(st + kABytes + kBBytes);
+                const uint64_t b_lo = ptx::make_sw128_kmajor_desc(st + 2 * kABytes + kBBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);
+                    const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+                    ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
+                    if (NSPLIT == 3) {
+                        ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, acc);
+                        ptx::umma_f16(d2, a_hi + ko, b_lo + ko, idesc, 1u);
+                    }
+                }
+                ptx::umma_commit(&empty_bar[s]);
+            }
+            ptx::umma_commit(tmem_full_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const int pos = p0 + m, L = A.L[src];
+        const bool valid = pos < L;
+        const int cls = n0 / A.Cout, co0 = n0 - cls * A.Cout;
+        float* __restrict__ outp = A.T[src] + ((static_cast<size_t>(b) * 4 + cls) * L + pos) * A.Cout + co0;
+        ptx::mbar_wait(tmem_full_bar, 0);
+        __syncwarp();
+        ptx::tc_fence_after();
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v1[32], v2[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
+            if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
+            ptx::tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float acc = __uint_as_float(v1[j + q]);
+                        if (NSPLIT == 3) acc = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, acc);
+                        o[q] = acc;
+                    }
+                    *reinterpret_cast<float4*>(outp + half * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
 }  // namespace s3d

@@ -43,28 +43,19 @@ __global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, Tr
 }
 
 // =====================================================================================
-// GroupNorm statistics (deterministic two-level reduction, fp64 combine) + zero-fill of the rollout
-// axis-sum accumulators that the following k_gn_silu launch adds into.
+// GroupNorm statistics (deterministic two-level reduction, fp64 combine).
 // reference src/diffusion/nn.py:17-19 (GroupNorm32 computes in fp32), unet_triplane.py:63-84
 // grid (chunks, 3, B), block (C/4, NY); partial [B][3][chunks][32][2] double; ticket [B][3]
 // stats out [B][3][32][2] = (mean, rstd)
 // =====================================================================================
 __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, int chunks, double* __restrict__ partial,
-                                                   unsigned int* __restrict__ ticket, float* __restrict__ stats,
-                                                   unsigned long long* __restrict__ zero_buf, long long zero_n) {
-    extern __shared__ float red[];   // [NY][2][C]
+                                                   unsigned int* __restrict__ ticket, float* __restrict__ stats) {
+    extern __shared__ float red[];   // [NY][2][C] then [2][C] channel totals
     __shared__ bool is_last;
     __shared__ double fin[2][8][kGroups];
     const int plane = blockIdx.y, b = blockIdx.z, chunk = blockIdx.x;
     const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
     const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
-    if (zero_buf) {
-        const long long ncta = static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z;
-        const long long cta = (static_cast<long long>(b) * 3 + plane) * gridDim.x + chunk;
-        const long long per = (zero_n + ncta - 1) / ncta;
-        const long long z0 = cta * per, z1 = min(zero_n, z0 + per);
-        for (long long i = z0 + tid; i < z1; i += nthr) zero_buf[i] = 0ull;
-    }
     const int npx = d.rows[plane] * d.cols[plane];
     const int ppc = (npx + chunks - 1) / chunks;
     const int p0 = chunk * ppc, p1 = min(npx, p0 + ppc);
@@ -88,13 +79,21 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
     rs[0] = s.x; rs[1] = s.y; rs[2] = s.z; rs[3] = s.w;
     rq[0] = q.x; rq[1] = q.y; rq[2] = q.z; rq[3] = q.w;
     __syncthreads();
+    // per-channel totals over the NY pixel lanes (2C threads, fixed order), kept behind the lane buffers
+    float* tot = red + NY * 2 * C;
+    for (int i = tid; i < 2 * C; i += nthr) {
+        const int which = i / C, c = i - which * C;
+        float acc = 0.f;
+        for (int y = 0; y < NY; ++y) acc += red[(y * 2 + which) * C + c];
+        tot[i] = acc;
+    }
+    __syncthreads();
     const int cpg = C / kGroups;
     double* part = partial + ((static_cast<size_t>(b) * 3 + plane) * chunks + chunk) * kGroups * 2;
     if (tid < 2 * kGroups) {
         const int g = tid >> 1, which = tid & 1;
         double acc = 0.0;
-        for (int y = 0; y < NY; ++y)
-            for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(red[(y * 2 + which) * C + c]);
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(tot[which * C + c]);
         part[g * 2 + which] = acc;
     }
     __threadfence();
@@ -133,21 +132,23 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
 }
 
 // =====================================================================================
-// Fused GroupNorm-apply (+FiLM) + SiLU -> fp16 (hi, lo) conv operand, plus the rollout axis sums.
+// Fused GroupNorm-apply (+FiLM) + SiLU -> fp16 (hi, lo) conv operand, plus the rollout axis means.
 // reference unet_triplane.py:63-95 (norm, SiLU), :285-297 (FiLM), :37-46 (axis means)
-// One CTA = an 8-row x TC-column tile of one plane of one sample.  grid (max tiles, 3, B), block (C/4, ny).
-// Axis sums are accumulated as 64-bit fixed point (value * 2^24) with integer atomics: exact, hence
-// independent of tile order / batch composition / GPU count.  sums[b][seg_off[plane*2+kind] + pos][C],
-// kind 0 = sum over columns (indexed by row), kind 1 = sum over rows (indexed by column).
+// One CTA = a 4-row x ny-column tile of one plane of one sample (one column per thread: many small CTAs keep
+// enough loads in flight at batch 1).  grid (max tiles, 3, B), block (C/4, ny).
+// Axis sums are accumulated as 64-bit fixed point (value * 2^24) with integer atomics: exact, hence independent of
+// tile order / batch composition / GPU count.  sums[b][seg_off[plane*2+kind] + pos][C], kind 0 = sum over columns
+// (indexed by row), kind 1 = sum over rows (indexed by column).  The last CTA of each (sample, plane) turns that
+// plane's sums into fp16 (hi, lo) means [2][B][total_len][C] (the A operand of the rollout 1-D GEMM) and re-zeroes them.
 // =====================================================================================
-constexpr int kGsRows = 8;
+constexpr int kGsRows = 4;
 constexpr float kFixScale = 16777216.f;          // 2^24
 constexpr double kFixInv = 1.0 / 16777216.0;
 
 struct GnSiluArgs {
     TriCF x;          // fp32 [B][rows][cols][C]
     TriDims d;
-    int C, csplit;    // tiles = 8-row strips x csplit column segments
+    int C;
     const float* stats;       // [B][3][32][2]
     TriCF gamma, beta;        // [C]
     const float* film;        // [rows][film_dim] or nullptr
@@ -155,7 +156,9 @@ struct GnSiluArgs {
     int film_dim, film_off;   // scale at film_off, shift at film_off + C
     TriH a;                   // out [2][B][rows][cols][C]
     TriH x16;                 // optional raw copy of x as (hi, lo) for the 1x1 skip GEMM
-    unsigned long long* sums; // nullptr when rollout is off
+    unsigned long long* sums; // [B][total_len][C] fixed point, zero between launches; nullptr when rollout is off
+    __half* means16;          // [2][B][total_len][C]
+    unsigned int* ticket;     // [B][3]
     int seg_off[6];
     int total_len;
 };
@@ -164,19 +167,21 @@ __device__ __forceinline__ void fix_add(unsigned long long* p, float v) {
     atomicAdd(p, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
 }
 
-__global__ void __launch_bounds__(256) k_gn_silu(GnSiluArgs A, int B) {
-    extern __shared__ float sm[];   // coefA[C], coefB[C], red[ny][8][C]
+__global__ void __launch_bounds__(256, 3) k_gn_silu(GnSiluArgs A, int B) {
+    extern __shared__ float sm[];   // coefA[C], coefB[C], red[ny][4][C]
+    __shared__ bool is_last;
     const int plane = blockIdx.y, b = blockIdx.z;
     const int rows = A.d.rows[plane], cols = A.d.cols[plane], C = A.C;
-    const int TC = (cols + A.csplit - 1) / A.csplit;
-    const int ctiles = (cols + TC - 1) / TC;
-    const int strip = blockIdx.x / ctiles, ct = blockIdx.x - strip * ctiles;
-    const int r0 = strip * kGsRows;
-    if (r0 >= rows) return;
-    const int nr = min(kGsRows, rows - r0);
-    const int c0 = ct * TC, c1 = min(cols, c0 + TC);
     const int tx = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
     const int tid = ty * blockDim.x + tx, nthr = blockDim.x * ny;
+    const int ctiles = (cols + ny - 1) / ny, strips = (rows + kGsRows - 1) / kGsRows;
+    const int ntiles = ctiles * strips;
+    if (static_cast<int>(blockIdx.x) >= ntiles) return;
+    const int strip = blockIdx.x / ctiles, ct = blockIdx.x - strip * ctiles;
+    const int r0 = strip * kGsRows;
+    const int nr = min(kGsRows, rows - r0);
+    const int c = ct * ny + ty;
+    const bool cvalid = c < cols;
     float* coefA = sm;
     float* coefB = sm + C;
     float* red = sm + 2 * C;
@@ -184,17 +189,17 @@ __global__ void __launch_bounds__(256) k_gn_silu(GnSiluArgs A, int B) {
     const float* st = A.stats + (static_cast<size_t>(b) * 3 + plane) * kGroups * 2;
     const float* film = nullptr;
     if (A.film) film = A.film + static_cast<size_t>(A.film_row ? A.film_row[b] : b) * A.film_dim + A.film_off;
-    for (int c = tid; c < C; c += nthr) {
-        float mean = st[(c / cpg) * 2], rstd = st[(c / cpg) * 2 + 1];
-        float g = A.gamma.p[plane][c] * rstd;
-        float o = A.beta.p[plane][c] - mean * g;
+    for (int ch = tid; ch < C; ch += nthr) {
+        float mean = st[(ch / cpg) * 2], rstd = st[(ch / cpg) * 2 + 1];
+        float g = A.gamma.p[plane][ch] * rstd;
+        float o = A.beta.p[plane][ch] - mean * g;
         if (film) {
-            float sc = 1.f + film[c], sh = film[C + c];
+            float sc = 1.f + film[ch], sh = film[C + ch];
             g *= sc;
             o = fmaf(o, sc, sh);
         }
-        coefA[c] = g;
-        coefB[c] = o;
+        coefA[ch] = g;
+        coefB[ch] = o;
     }
     __syncthreads();
     const float4 ca = *reinterpret_cast<const float4*>(coefA + tx * 4);
@@ -205,68 +210,91 @@ __global__ void __launch_bounds__(256) k_gn_silu(GnSiluArgs A, int B) {
     const float* xp = A.x.p[plane] + sample_off;
     __half* ap = A.a.p[plane] + sample_off;
     __half* xq = A.x16.p[plane] ? A.x16.p[plane] + sample_off : nullptr;
-    unsigned long long* srow = nullptr;
-    unsigned long long* scol = nullptr;
-    if (A.sums) {
-        unsigned long long* sb = A.sums + static_cast<size_t>(b) * A.total_len * C;
-        srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
-        scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
-    }
-    float4 racc[kGsRows];
+    float4 y[kGsRows];
 #pragma unroll
-    for (int r = 0; r < kGsRows; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = c0 + ty; c < c1; c += ny) {
+    for (int r = 0; r < kGsRows; ++r) y[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cvalid) {
         float4 v[kGsRows];
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r)
             if (r < nr) v[r] = __ldg(reinterpret_cast<const float4*>(xp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4));
-        float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r) {
             if (r < nr) {
                 const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
                 if (xq) store_split4(xq + off, xq + lo_off + off, v[r]);
-                float4 y;
-                y.x = silu_f(fmaf(v[r].x, ca.x, cb.x));
-                y.y = silu_f(fmaf(v[r].y, ca.y, cb.y));
-                y.z = silu_f(fmaf(v[r].z, ca.z, cb.z));
-                y.w = silu_f(fmaf(v[r].w, ca.w, cb.w));
-                store_split4(ap + off, ap + lo_off + off, y);
-                cacc.x += y.x; cacc.y += y.y; cacc.z += y.z; cacc.w += y.w;
-                racc[r].x += y.x; racc[r].y += y.y; racc[r].z += y.z; racc[r].w += y.w;
+                y[r].x = silu_f(fmaf(v[r].x, ca.x, cb.x));
+                y[r].y = silu_f(fmaf(v[r].y, ca.y, cb.y));
+                y[r].z = silu_f(fmaf(v[r].z, ca.z, cb.z));
+                y[r].w = silu_f(fmaf(v[r].w, ca.w, cb.w));
+                store_split4(ap + off, ap + lo_off + off, y[r]);
             }
         }
-        if (scol) {
-            unsigned long long* p = scol + static_cast<size_t>(c) * C + tx * 4;
-            fix_add(p, cacc.x); fix_add(p + 1, cacc.y); fix_add(p + 2, cacc.z); fix_add(p + 3, cacc.w);
-        }
     }
-    if (!srow) return;
+    if (!A.sums) return;
+    unsigned long long* sb = A.sums + static_cast<size_t>(b) * A.total_len * C;
+    unsigned long long* srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
+    unsigned long long* scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
+    if (cvalid) {
+        float4 cacc;
+        cacc.x = (y[0].x + y[1].x) + (y[2].x + y[3].x);
+        cacc.y = (y[0].y + y[1].y) + (y[2].y + y[3].y);
+        cacc.z = (y[0].z + y[1].z) + (y[2].z + y[3].z);
+        cacc.w = (y[0].w + y[1].w) + (y[2].w + y[3].w);
+        unsigned long long* p = scol + static_cast<size_t>(c) * C + tx * 4;
+        fix_add(p, cacc.x); fix_add(p + 1, cacc.y); fix_add(p + 2, cacc.z); fix_add(p + 3, cacc.w);
+    }
 #pragma unroll
     for (int r = 0; r < kGsRows; ++r)
-        *reinterpret_cast<float4*>(red + (static_cast<size_t>(ty) * kGsRows + r) * C + tx * 4) = racc[r];
+        *reinterpret_cast<float4*>(red + (static_cast<size_t>(ty) * kGsRows + r) * C + tx * 4) = y[r];
     __syncthreads();
     for (int i = tid; i < nr * C; i += nthr) {
-        int r = i / C, c = i - r * C;
+        int r = i / C, ch = i - r * C;
         float acc = 0.f;
-        for (int y = 0; y < ny; ++y) acc += red[(static_cast<size_t>(y) * kGsRows + r) * C + c];
-        fix_add(srow + static_cast<size_t>(r0 + r) * C + c, acc);
+        for (int yy = 0; yy < ny; ++yy) acc += red[(static_cast<size_t>(yy) * kGsRows + r) * C + ch];
+        fix_add(srow + static_cast<size_t>(r0 + r) * C + ch, acc);
     }
+    // ---- last CTA of this (sample, plane): sums -> fp16 (hi, lo) means, and re-zero the accumulators
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int prev = atomicAdd(&A.ticket[b * 3 + plane], 1u);
+        is_last = (prev == static_cast<unsigned int>(ntiles - 1));
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const size_t mlo = static_cast<size_t>(B) * A.total_len * C;
+    __half* mb = A.means16 + static_cast<size_t>(b) * A.total_len * C;
+    for (int kind = 0; kind < 2; ++kind) {
+        const int len = kind == 0 ? rows : cols;
+        const double scale = kFixInv / static_cast<double>(kind == 0 ? cols : rows);
+        const size_t seg = static_cast<size_t>(A.seg_off[plane * 2 + kind]) * C;
+        unsigned long long* sp = sb + seg;
+        for (int i = tid; i < len * C; i += nthr) {
+            const long long sv = static_cast<long long>(__ldcg(sp + i));
+            sp[i] = 0ull;
+            const float m = static_cast<float>(static_cast<double>(sv) * scale);
+            __half hi, lo;
+            split_f16(m, hi, lo);
+            mb[seg + i] = hi;
+            mb[mlo + seg + i] = lo;
+        }
+    }
+    if (tid == 0) A.ticket[b * 3 + plane] = 0u;
 }
 
 // =====================================================================================
-// Rollout 1-D terms.  Two thirds of a rollout conv's input channels are constant along one image
+// Rollout 1-D terms, CUDA-core cross-check kernel (conv_impl = 1).  The tensor-core version is k_roll_tc.
+// Two thirds of a rollout conv's input channels are constant along one image
 // axis (unet_triplane.py:37-46), so their 3x3 conv collapses exactly to a 1-D conv along the other
 // axis, with the zero padding only distinguishing first / interior / last position across:
 //   T[b][cls][pos][co] = sum_{along, c} mean[pos+along-1][c] * wc[along*C + c][cls*Cout + co]
 //   wc[..][cls] = sum of the taps `across` that class keeps: 0 interior {0,1,2}, 1 first {1,2}, 2 last {0,1}, 3 single {1}
-// A small fp32 GEMM (M = positions, K = 3C, N = ncls*Cout) on CUDA cores: 16 positions x 64 outputs per CTA,
-// weights streamed through shared memory with cp.async double buffering.
 // grid (ceil(Lmax/16), 6 * ntn, B): blockIdx.y = (plane*2 + group) * ntn + n_tile.  block 128.
 // =====================================================================================
 struct Roll1dSrc {
-    int sum_off;        // segment offset (positions) of the source sums inside a sample's block
-    float inv_count;    // 1 / (length of the averaged axis)
+    int sum_off;        // segment offset (positions) of the source means inside a sample's block
     int L;
     int ncls;           // 3, or 4 when the axis across has length 1
     const float* wc;    // [3*C][4*Cout]
@@ -274,21 +302,14 @@ struct Roll1dSrc {
 };
 struct Roll1dArgs {
     Roll1dSrc s[6];
-    const unsigned long long* sums;   // [B][total_len][C] fixed point
-    int total_len;
+    const __half* means16;   // [2][B][total_len][C]
+    int total_len, B;
     int C, Cout, ntn;
 };
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
 __global__ void __launch_bounds__(128) k_roll1d(Roll1dArgs A) {
-    constexpr int POS = 16, NT = 64, KC = 32, ST = 6;     // 6-deep cp.async ring of 32 x 64 weight chunks (48 KiB)
-    extern __shared__ __align__(16) float sm1[];     // means[(POS+2)][C+4], wbuf[ST][KC][NT]
+    constexpr int POS = 16, NT = 64;
+    extern __shared__ __align__(16) float sm1[];     // means[(POS+2)][C+4]
     const int src_id = blockIdx.y / A.ntn, nt = blockIdx.y - src_id * A.ntn;
     const Roll1dSrc S = A.s[src_id];
     const int b = blockIdx.z, C = A.C, Cout = A.Cout, N4 = 4 * Cout;
@@ -296,52 +317,27 @@ __global__ void __launch_bounds__(128) k_roll1d(Roll1dArgs A) {
     if (S.T == nullptr || p0 >= S.L || n0 >= S.ncls * Cout) return;
     const int CP = C + 4;
     float* means = sm1;
-    float* wbuf = sm1 + (POS + 2) * CP;
     const int tid = threadIdx.x;
-    const int K = 3 * C, nchunks = K / KC;
-    auto load_w = [&](int chunk) {
-        if (chunk < nchunks) {
-            const int buf = chunk % ST;
-            for (int i = tid; i < KC * (NT / 4); i += 128) {      // KC rows x 64 floats = KC x 16 x 16 B
-                int k = i / (NT / 4), v = i - k * (NT / 4);
-                cp_async16(wbuf + (buf * KC + k) * NT + v * 4, S.wc + static_cast<size_t>(chunk * KC + k) * N4 + n0 + v * 4);
-            }
-        }
-        cp_async_commit();      // always commit (possibly empty) so the group count stays uniform
-    };
-#pragma unroll
-    for (int c = 0; c < ST - 1; ++c) load_w(c);
-    const unsigned long long* sb = A.sums + (static_cast<size_t>(b) * A.total_len + S.sum_off) * C;
-    const double scale = kFixInv * static_cast<double>(S.inv_count);
+    const __half* mh = A.means16 + (static_cast<size_t>(b) * A.total_len + S.sum_off) * C;
+    const __half* ml = mh + static_cast<size_t>(A.B) * A.total_len * C;
     for (int i = tid; i < (POS + 2) * C; i += 128) {
         int j = i / C, c = i - j * C, pos = p0 + j - 1;
         float v = 0.f;
         if (pos >= 0 && pos < S.L)
-            v = static_cast<float>(static_cast<double>(static_cast<long long>(__ldcg(sb + static_cast<size_t>(pos) * C + c))) * scale);
+            v = __half2float(mh[static_cast<size_t>(pos) * C + c]) + __half2float(ml[static_cast<size_t>(pos) * C + c]) * (1.f / kLoScale);
         means[j * CP + c] = v;
     }
+    __syncthreads();
     const int tn = tid & 15, tp = tid >> 4;          // 4 outputs x 2 positions per thread
-    float acc[2][4];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
-    for (int ch = 0; ch < nchunks; ++ch) {
-        cp_async_wait<ST - 2>();                     // chunk ch has landed (ST-1 groups were in flight)
-        __syncthreads();                             // ... for every thread; also: everyone is done with chunk ch-1
-        load_w(ch + ST - 1);                         // refill the slot chunk ch-1 used
-        const int kk = ch * KC, al = kk / C, cb = kk - al * C;      // a chunk never straddles a tap (C % 32 == 0)
-        const float* wb = wbuf + (ch % ST) * KC * NT + tn * 4;
-        const float* m0 = means + (tp * 2 + al) * CP + cb;
-#pragma unroll 8
-        for (int k = 0; k < KC; ++k) {
-            const float4 w = *reinterpret_cast<const float4*>(wb + k * NT);
-            const float s0 = m0[k], s1 = m0[CP + k];
-            acc[0][0] = fmaf(s0, w.x, acc[0][0]); acc[0][1] = fmaf(s0, w.y, acc[0][1]);
-            acc[0][2] = fmaf(s0, w.z, acc[0][2]); acc[0][3] = fmaf(s0, w.w, acc[0][3]);
-            acc[1][0] = fmaf(s1, w.x, acc[1][0]); acc[1][1] = fmaf(s1, w.y, acc[1][1]);
-            acc[1][2] = fmaf(s1, w.z, acc[1][2]); acc[1][3] = fmaf(s1, w.w, acc[1][3]);
-        }
+    float acc[2][4] = {};
+    for (int kk = 0; kk < 3 * C; ++kk) {
+        const int al = kk / C, cb = kk - al * C;
+        const float4 w = __ldg(reinterpret_cast<const float4*>(S.wc + static_cast<size_t>(kk) * N4 + n0 + tn * 4));
+        const float s0 = means[(tp * 2 + al) * CP + cb], s1 = means[(tp * 2 + al + 1) * CP + cb];
+        acc[0][0] = fmaf(s0, w.x, acc[0][0]); acc[0][1] = fmaf(s0, w.y, acc[0][1]);
+        acc[0][2] = fmaf(s0, w.z, acc[0][2]); acc[0][3] = fmaf(s0, w.w, acc[0][3]);
+        acc[1][0] = fmaf(s1, w.x, acc[1][0]); acc[1][1] = fmaf(s1, w.y, acc[1][1]);
+        acc[1][2] = fmaf(s1, w.z, acc[1][2]); acc[1][3] = fmaf(s1, w.w, acc[1][3]);
     }
     const int n = n0 + tn * 4, cls = n / Cout, co = n - cls * Cout;
 #pragma unroll

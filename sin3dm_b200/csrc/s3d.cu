@@ -77,6 +77,23 @@ static void make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t
     if (r != CUDA_SUCCESS) throw S3dError{"cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))};
 }
 
+// same, with explicit byte strides for dims 1..rank-1
+static void make_tmap_strided(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                              const uint32_t* box) {
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i < rank - 1) gstride[i] = strides_bytes[i];
+    }
+    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstride, bx, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw S3dError{"cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))};
+}
+
 // ------------------------------------------------------------------------------------ model description
 static const char* kPlane[3] = {"xy", "xz", "yz"};
 
@@ -109,6 +126,7 @@ struct DevConv3 {        // one 3x3 TriplaneConv (+ optional fused 1x1 skip)
     float* wskip_orig[3] = {};  // [Cout][Cs]
     __half* w_pack[3] = {};     // [2][Cout][Ktot]
     float* wr[3][2] = {};       // rollout 1-D weights [3C][4Cout] (border classes pre-summed) per (plane, group)
+    __half* wr16[3][2] = {};    // same as fp16 (hi, lo) [2][4Cout][3C] (K-major B operand of k_roll_tc)
     float* bias[3] = {};        // conv bias (+ skip bias)
 };
 struct DevNorm {
@@ -355,8 +373,20 @@ static void upload_conv3(s3d_unet* u, DevConv3& d, const std::string& name, int 
         auto packed = pack_conv(w, Cout, d.Cw, C, ws, Cs);
         d.w_pack[p] = reinterpret_cast<__half*>(dev_upload(u->wallocs, packed));
         if (ro)
-            for (int g = 1; g <= 2; ++g)
-                d.wr[p][g - 1] = dev_upload(u->wallocs, pack_roll(w, Cout, C, g, roll_row_varying(p, g)));
+            for (int g = 1; g <= 2; ++g) {
+                const std::vector<float> wc = pack_roll(w, Cout, C, g, roll_row_varying(p, g));
+                d.wr[p][g - 1] = dev_upload(u->wallocs, wc);
+                const int K = 3 * C, N = 4 * Cout;
+                std::vector<uint16_t> w16(static_cast<size_t>(2) * N * K);
+                for (int k = 0; k < K; ++k)
+                    for (int n = 0; n < N; ++n) {
+                        const float v = std::min(std::max(wc[static_cast<size_t>(k) * N + n], -65504.f), 65504.f);
+                        const uint16_t hi = f2h_bits(v);
+                        w16[static_cast<size_t>(n) * K + k] = hi;
+                        w16[(static_cast<size_t>(N) + n) * K + k] = f2h_bits((v - h2f(hi)) * 2048.f);
+                    }
+                d.wr16[p][g - 1] = reinterpret_cast<__half*>(dev_upload(u->wallocs, w16));
+            }
     }
 }
 static void upload_norm(s3d_unet* u, DevNorm& n, const std::string& name) {
@@ -424,6 +454,8 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_gn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_out_head, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaDeviceSynchronize());
     u->finalized = true;
@@ -476,12 +508,13 @@ struct PlanBuilder {
     static TriCF cf(const TriF& t) { return TriCF{{t.p[0], t.p[1], t.p[2]}}; }
     static TriCF cf3(float* const* t) { return TriCF{{t[0], t[1], t[2]}}; }
 
-    // ---- rollout axis-sum accumulators of one GN+SiLU site (64-bit fixed point, see k_gn_silu)
+    // ---- rollout axis-sum accumulators / means of one GN+SiLU site (see k_gn_silu)
     struct Sums {
-        unsigned long long* buf = nullptr;   // [B][total_len][C]
+        unsigned long long* buf = nullptr;   // [B][total_len][C] 64-bit fixed point, zero between launches
+        __half* means16 = nullptr;           // [2][B][total_len][C]
+        unsigned int* ticket = nullptr;      // [B][3]
         int seg_off[6] = {};                 // plane*2 + kind (0: indexed by row, 1: indexed by column)
         int total_len = 0;
-        long long count = 0;
     };
     Sums alloc_sums(int level, int C) {
         Sums S;
@@ -494,17 +527,20 @@ struct PlanBuilder {
             off += d.cols[p];
         }
         S.total_len = off;
-        S.count = static_cast<long long>(B) * off * C;
-        S.buf = dev_alloc<unsigned long long>(P->allocs, static_cast<size_t>(S.count));
-        CUDA_TRY(cudaMemset(S.buf, 0, sizeof(unsigned long long) * S.count));
+        const size_t n = static_cast<size_t>(B) * off * C;
+        S.buf = dev_alloc<unsigned long long>(P->allocs, n);
+        CUDA_TRY(cudaMemset(S.buf, 0, sizeof(unsigned long long) * n));
+        S.means16 = dev_alloc<__half>(P->allocs, 2 * n);
+        S.ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3);
+        CUDA_TRY(cudaMemset(S.ticket, 0, sizeof(unsigned int) * B * 3));
         return S;
     }
 
-    // ---- GroupNorm statistics (+ zero-fill of the sums the following gn_silu accumulates into)
-    float* stats(const ActF& x, const Sums* zero = nullptr) {
+    // ---- GroupNorm statistics
+    float* stats(const ActF& x) {
         const int level = x.level, C = x.C;
         S3D_CHECK(C % kGroups == 0 && C % 4 == 0 && C / 4 <= 128, "unsupported channel count for GroupNorm32");
-        const int chunks = std::max(1, std::min(64, max_px(level) / 64));
+        const int chunks = std::max(1, std::min(128, max_px(level) / 48));
         double* partial = dev_alloc<double>(P->allocs, static_cast<size_t>(B) * 3 * chunks * kGroups * 2);
         unsigned int* ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3);
         CUDA_TRY(cudaMemset(ticket, 0, sizeof(unsigned int) * B * 3));
@@ -512,18 +548,16 @@ struct PlanBuilder {
         TriCF xc = cf(x.p);
         TriDims d = dims[level];
         const int Bv = B;
-        unsigned long long* zb = zero ? zero->buf : nullptr;
-        const long long zn = zero ? zero->count : 0;
         add_op("k_gn_stats", 0.0, [=](cudaStream_t s) {
-            const int ny = std::max(1, std::min(32, 1024 / (C / 4)));
+            const int ny = std::max(1, std::min(16, 1024 / (C / 4)));
             dim3 grid(chunks, 3, Bv), block(C / 4, ny);
-            k_gn_stats<<<grid, block, sizeof(float) * ny * 2 * C, s>>>(xc, d, C, chunks, partial, ticket, st, zb, zn);
+            k_gn_stats<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, d, C, chunks, partial, ticket, st);
             LAUNCH_CHECK("k_gn_stats");
         });
         return st;
     }
 
-    // ---- GN apply + SiLU (+FiLM) -> fp16 operands (+ raw x16) (+ axis sums)
+    // ---- GN apply + SiLU (+FiLM) -> fp16 operands (+ raw x16) (+ axis means)
     void gn_silu(const ActF& x, const float* st, const DevNorm& n, int film_off, const Act16& a, const Act16* x16,
                  const Sums* S) {
         const int level = x.level, C = x.C;
@@ -531,23 +565,13 @@ struct PlanBuilder {
         const int bx = C / 4;
         S3D_CHECK(bx <= 256, "channel count too large for k_gn_silu");
         const int ny = std::max(1, 256 / bx);
-        // tiles = 8-row strips x csplit column segments; csplit depends on the geometry only (never on B), so the
-        // result is independent of the batch composition.  Aim for >= 148 CTAs at B = 1.
-        int strips_total = 0, max_strips = 0, min_cols = 1 << 30;
-        for (int p = 0; p < 3; ++p) {
-            const int sp = (d.rows[p] + kGsRows - 1) / kGsRows;
-            strips_total += sp;
-            max_strips = std::max(max_strips, sp);
-            min_cols = std::min(min_cols, d.cols[p]);
-        }
-        int csplit = std::max(1, (148 + strips_total - 1) / strips_total);
-        csplit = std::min(csplit, std::max(1, min_cols / ny));
-        csplit = std::max(csplit, 1);
+        int gx = 0;
+        for (int p = 0; p < 3; ++p)
+            gx = std::max(gx, ((d.rows[p] + kGsRows - 1) / kGsRows) * ((d.cols[p] + ny - 1) / ny));
         GnSiluArgs A{};
         A.x = cf(x.p);
         A.d = d;
         A.C = C;
-        A.csplit = csplit;
         A.stats = st;
         A.gamma = cf3(n.gamma);
         A.beta = cf3(n.beta);
@@ -557,6 +581,8 @@ struct PlanBuilder {
         if (x16) A.x16 = x16->p;
         if (S) {
             A.sums = S->buf;
+            A.means16 = S->means16;
+            A.ticket = S->ticket;
             for (int i = 0; i < 6; ++i) A.seg_off[i] = S->seg_off[i];
             A.total_len = S->total_len;
         }
@@ -565,7 +591,6 @@ struct PlanBuilder {
         S3D_CHECK(smem <= 100 * 1024, "k_gn_silu shared memory");
         Plan* Pp = P;
         const int Bv = B;
-        const int gx = max_strips * csplit;
         add_op("k_gn_silu", 0.0, [=](cudaStream_t s) {
             GnSiluArgs Al = A;
             if (use_film) {
@@ -581,7 +606,7 @@ struct PlanBuilder {
     struct TBuf {
         TriF Trow, Tcol;
     };
-    // ---- rollout 1-D terms
+    // ---- rollout 1-D terms (tensor-core GEMM; SIMT cross-check kernel when conv_impl == 1)
     TBuf roll1d(const Sums& S, int level, const DevConv3& cv) {
         const TriDims d = dims[level];
         const int C = cv.C, Cout = cv.Cout;
@@ -590,45 +615,83 @@ struct PlanBuilder {
             T.Trow.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 4 * d.rows[p] * Cout);
             T.Tcol.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 4 * d.cols[p] * Cout);
         }
-        Roll1dArgs A{};
-        A.C = C;
-        A.Cout = Cout;
-        A.sums = S.buf;
-        A.total_len = S.total_len;
-        // (plane, group) -> source plane / which of its sums; see roll_row_varying() and unet_triplane.py:37-46
-        //   kind 0 = the source plane's sum over its columns (indexed by its row), kind 1 = sum over rows (by column)
+        // (plane, group) -> source plane / which of its means; see roll_row_varying() and unet_triplane.py:37-46
+        //   kind 0 = the source plane's mean over its columns (indexed by its row), kind 1 = mean over rows (by column)
         struct SrcDef {
             int sp, kind;
         };
         const SrcDef def[3][2] = {{{2, 0}, {1, 0}}, {{0, 0}, {2, 1}}, {{0, 1}, {1, 1}}};
-        int Lmax = 0, ncls_max = 3;
+        int L[6], ncls[6], soff[6], Lmax = 0, ncls_max = 3;
+        float* Tp[6];
         for (int p = 0; p < 3; ++p)
             for (int g = 0; g < 2; ++g) {
                 const SrcDef sd = def[p][g];
                 const bool rowv = roll_row_varying(p, g + 1);
-                Roll1dSrc& s = A.s[p * 2 + g];
-                s.L = rowv ? d.rows[p] : d.cols[p];
+                const int i = p * 2 + g;
+                L[i] = rowv ? d.rows[p] : d.cols[p];
                 const int across = rowv ? d.cols[p] : d.rows[p];
-                s.ncls = across == 1 ? 4 : 3;
-                ncls_max = std::max(ncls_max, s.ncls);
-                s.sum_off = S.seg_off[sd.sp * 2 + sd.kind];
+                ncls[i] = across == 1 ? 4 : 3;
+                ncls_max = std::max(ncls_max, ncls[i]);
+                soff[i] = S.seg_off[sd.sp * 2 + sd.kind];
                 const int src_len = sd.kind == 0 ? d.rows[sd.sp] : d.cols[sd.sp];
-                const int avg_len = sd.kind == 0 ? d.cols[sd.sp] : d.rows[sd.sp];
-                S3D_CHECK(src_len == s.L, "rollout geometry");
-                s.inv_count = 1.f / static_cast<float>(avg_len);
-                s.wc = cv.wr[p][g];
-                s.T = rowv ? T.Trow.p[p] : T.Tcol.p[p];
-                Lmax = std::max(Lmax, s.L);
+                S3D_CHECK(src_len == L[i], "rollout geometry");
+                Tp[i] = rowv ? T.Trow.p[p] : T.Tcol.p[p];
+                Lmax = std::max(Lmax, L[i]);
             }
-        A.ntn = ncls_max * Cout / 64;
-        S3D_CHECK(C % 32 == 0 && Cout % 64 == 0, "k_roll1d tiling");
-        const size_t smem = sizeof(float) * (static_cast<size_t>(18) * (C + 4) + 6 * 32 * 64);
-        S3D_CHECK(smem <= 100 * 1024, "k_roll1d shared memory");
         const int Bv = B;
-        add_op("k_roll1d", 0.0, [=](cudaStream_t s) {
-            dim3 grid((Lmax + 15) / 16, 6 * A.ntn, Bv);
-            k_roll1d<<<grid, 128, smem, s>>>(A);
-            LAUNCH_CHECK("k_roll1d");
+        const int ntn = ncls_max * Cout / 64;
+        S3D_CHECK(C % 64 == 0 && Cout % 64 == 0, "rollout tiling");
+        if (u->cfg.conv_impl == 1) {
+            Roll1dArgs A{};
+            A.C = C;
+            A.Cout = Cout;
+            A.means16 = S.means16;
+            A.total_len = S.total_len;
+            A.B = B;
+            A.ntn = ntn;
+            for (int i = 0; i < 6; ++i) {
+                A.s[i].sum_off = soff[i];
+                A.s[i].L = L[i];
+                A.s[i].ncls = ncls[i];
+                A.s[i].wc = cv.wr[i / 2][i % 2];
+                A.s[i].T = Tp[i];
+            }
+            const size_t smem = sizeof(float) * static_cast<size_t>(18) * (C + 4);
+            add_op("k_roll1d", 0.0, [=](cudaStream_t s) {
+                dim3 grid((Lmax + 15) / 16, 6 * ntn, Bv);
+                k_roll1d<<<grid, 128, smem, s>>>(A);
+                LAUNCH_CHECK("k_roll1d");
+            });
+            return T;
+        }
+        auto maps = std::make_shared<RollTcMaps>();
+        memset(maps.get(), 0, sizeof(RollTcMaps));
+        RollTcArgs A{};
+        A.C = C;
+        A.Cout = Cout;
+        int total = 0;
+        const uint64_t seg_bytes = static_cast<uint64_t>(S.total_len) * C * 2;
+        for (int i = 0; i < 6; ++i) {
+            A.L[i] = L[i];
+            A.ncls[i] = ncls[i];
+            A.T[i] = Tp[i];
+            A.tile_start[i] = total;
+            total += (L[i] + kBM - 1) / kBM;
+            const uint64_t adims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L[i]), 1, static_cast<uint64_t>(B), 2};
+            const uint64_t astr[4] = {static_cast<uint64_t>(C) * 2, seg_bytes, seg_bytes, seg_bytes * B};
+            const uint32_t abox[5] = {kBK, kBM, 1, 1, 1};
+            make_tmap_strided(&maps->a[i], S.means16 + static_cast<size_t>(soff[i]) * C, 5, adims, astr, abox);
+            const uint64_t wdims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(4 * Cout), 2};
+            const uint32_t wbox[3] = {kBK, kBN, 1};
+            make_tmap(&maps->w[i], cv.wr16[i / 2][i % 2], 3, wdims, wbox);
+        }
+        A.tile_start[6] = total;
+        const int nsplit = u->cfg.precision == 1 ? 1 : 3;
+        add_op("k_roll_tc", 0.0, [=](cudaStream_t s) {
+            dim3 grid(total, ntn, Bv);
+            if (nsplit == 3) k_roll_tc<3><<<grid, kConvThreads, ConvTcCfg<3>::kSmemBytes, s>>>(*maps, A);
+            else k_roll_tc<1><<<grid, kConvThreads, ConvTcCfg<1>::kSmemBytes, s>>>(*maps, A);
+            LAUNCH_CHECK("k_roll_tc");
         });
         return T;
     }
@@ -733,7 +796,7 @@ struct PlanBuilder {
             s1 = alloc_sums(level, b.cin);
             s2 = alloc_sums(level, b.cout);
         }
-        float* st1 = stats(x, ro ? &s1 : nullptr);
+        float* st1 = stats(x);
         Act16 a1 = alloc16(level, b.cin);
         Act16 x16{};
         if (b.has_skip) x16 = alloc16(level, b.cin);
@@ -742,7 +805,7 @@ struct PlanBuilder {
         if (ro) t1 = roll1d(s1, level, w.c1);
         ActF h1 = allocF(level, b.cout, b.name + ".h1");
         conv(a1, level, w.c1, ro ? &t1 : nullptr, nullptr, nullptr, ssn ? -1 : b.film_off, h1);
-        float* st2 = stats(h1, ro ? &s2 : nullptr);
+        float* st2 = stats(h1);
         Act16 a2 = alloc16(level, b.cout);
         gn_silu(h1, st2, w.n2, ssn ? b.film_off : -1, a2, nullptr, ro ? &s2 : nullptr);
         TBuf t2{};
