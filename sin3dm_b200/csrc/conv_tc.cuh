@@ -47,40 +47,59 @@ template <int NSPLIT>
 struct ConvTcCfg {
     static constexpr int kStageBytes = (NSPLIT == 3 ? 2 : 1) * (kABytes + kBBytes);
     static constexpr int kStages = NSPLIT == 3 ? 4 : 8;
-    static constexpr int kTmemCols = NSPLIT == 3 ? 128 : 64;
+    static constexpr int kAccCols = NSPLIT == 3 ? 128 : 64;     // TMEM columns of one accumulator stage
+    static constexpr int kTmemCols = 2 * kAccCols;              // double-buffered accumulators
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+struct ConvTile {
+    int plane, h0, w0, n0, b;
+};
+__device__ __forceinline__ ConvTile conv_tile_decode(const ConvTcArgs& A, int t) {
+    const int ts = A.tile_start[3];
+    const int nt_n = A.Cout / kBN;
+    ConvTile T;
+    T.b = t / (ts * nt_n);
+    int rem = t - T.b * ts * nt_n;
+    const int nt = rem / ts;
+    rem -= nt * ts;
+    T.n0 = nt * kBN;
+    T.plane = rem >= A.tile_start[2] ? 2 : (rem >= A.tile_start[1] ? 1 : 0);
+    const int ip = rem - A.tile_start[T.plane];
+    const int ty = ip / A.tiles_x[T.plane];
+    T.h0 = ty * kTileH;
+    T.w0 = (ip - ty * A.tiles_x[T.plane]) * kTileW;
+    return T;
+}
+
+// Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer and the MMA
+// issuer run ahead across tile boundaries (shared-memory ring) and the accumulators are double-buffered in TMEM, so the
+// epilogue of tile i overlaps the main loop of tile i+1.
 template <int NSPLIT>
-__global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_constant__ ConvTcMaps M, const ConvTcArgs A) {
+__global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_constant__ ConvTcMaps M, const ConvTcArgs A,
+                                                             const int total_tiles) {
     using Cfg = ConvTcCfg<NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
-    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // ---- tile decode (warp-uniform)
-    int plane = 0;
-    if (static_cast<int>(blockIdx.x) >= A.tile_start[1]) plane = 1;
-    if (static_cast<int>(blockIdx.x) >= A.tile_start[2]) plane = 2;
-    const int t_in_plane = blockIdx.x - A.tile_start[plane];
-    const int ty = t_in_plane / A.tiles_x[plane], tx = t_in_plane - ty * A.tiles_x[plane];
-    const int h0 = ty * kTileH, w0 = tx * kTileW;
-    const int n0 = blockIdx.y * kBN;
-    const int b = blockIdx.z;
     const int cblks = A.C / kBK;
     const int nk_main = 9 * cblks;
     const int nk = nk_main + A.Cs / kBK;
 
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&M.a[plane]);
-        ptx::prefetch_tmap(&M.w[plane]);
-        if (A.Cs) ptx::prefetch_tmap(&M.x[plane]);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            ptx::prefetch_tmap(&M.a[p]);
+            ptx::prefetch_tmap(&M.w[p]);
+            if (A.Cs) ptx::prefetch_tmap(&M.x[p]);
+        }
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -88,7 +107,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 ptx::mbar_init(&full_bar[s], 1);
                 ptx::mbar_init(&empty_bar[s], 1);
             }
-            ptx::mbar_init(tmem_full_bar, 1);
+            for (int s = 0; s < 2; ++s) {
+                ptx::mbar_init(&tmem_full_bar[s], 1);
+                ptx::mbar_init(&tmem_empty_bar[s], 4);       // one arrive per epilogue warp
+            }
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -102,28 +124,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % Cfg::kStages;
-                const uint32_t ph = (i / Cfg::kStages) & 1;
-                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* st = smem + s * Cfg::kStageBytes;
-                ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                const CUtensorMap* amap;
-                int c0, wc, hc;
-                if (i < nk_main) {
-                    const int tap = i / cblks, cb = i - tap * cblks;
-                    const int kh = tap / 3, kw = tap - kh * 3;
-                    amap = &M.a[plane];
-                    c0 = cb * kBK; wc = w0 + kw - 1; hc = h0 + kh - 1;
-                } else {
-                    amap = &M.x[plane];
-                    c0 = (i - nk_main) * kBK; wc = w0; hc = h0;
-                }
-                ptx::tma_load_5d(st, amap, &full_bar[s], c0, wc, hc, b, 0);
-                ptx::tma_load_3d(st + kABytes, &M.w[plane], &full_bar[s], i * kBK, n0, 0);
-                if (NSPLIT == 3) {
-                    ptx::tma_load_5d(st + kABytes + kBBytes, amap, &full_bar[s], c0, wc, hc, b, 1);
-                    ptx::tma_load_3d(st + 2 * kABytes + kBBytes, &M.w[plane], &full_bar[s], i * kBK, n0, 1);
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const ConvTile T = conv_tile_decode(A, t);
+                for (int i = 0; i < nk; ++i, ++it) {
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (it / Cfg::kStages) & 1;
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * Cfg::kStageBytes;
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                    const CUtensorMap* amap;
+                    int c0, wc, hc;
+                    if (i < nk_main) {
+                        const int tap = i / cblks, cb = i - tap * cblks;
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        amap = &M.a[T.plane];
+                        c0 = cb * kBK; wc = T.w0 + kw - 1; hc = T.h0 + kh - 1;
+                    } else {
+                        amap = &M.x[T.plane];
+                        c0 = (i - nk_main) * kBK; wc = T.w0; hc = T.h0;
+                    }
+                    ptx::tma_load_5d(st, amap, &full_bar[s], c0, wc, hc, T.b, 0);
+                    ptx::tma_load_3d(st + kABytes, &M.w[T.plane], &full_bar[s], i * kBK, T.n0, 0);
+                    if (NSPLIT == 3) {
+                        ptx::tma_load_5d(st + kABytes + kBBytes, amap, &full_bar[s], c0, wc, hc, T.b, 1);
+                        ptx::tma_load_3d(st + 2 * kABytes + kBBytes, &M.w[T.plane], &full_bar[s], i * kBK, T.n0, 1);
+                    }
                 }
             }
         }
@@ -131,105 +157,122 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, kBN);
-            const uint32_t d1 = tmem_base, d2 = tmem_base + kBN;
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % Cfg::kStages;
-                const uint32_t ph = (i / Cfg::kStages) & 1;
-                ptx::mbar_wait(&full_bar[s], ph);
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+                const int as = lt & 1;
+                const uint32_t aph = (lt >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1);        // epilogue has drained this accumulator stage
                 ptx::tc_fence_after();
-                const uint32_t st = ptx::smem_u32(smem + s * Cfg::kStageBytes);
-                const uint64_t a_hi = ptx::make_sw128_kmajor_desc(st);
-                const uint64_t b_hi = ptx::make_sw128_kmajor_desc(st + kABytes);
-                const uint64_t a_lo = ptx::make_sw128_kmajor_desc(st + kABytes + kBBytes);
-                const uint64_t b_lo = ptx::make_sw128_kmajor_desc(st + 2 * kABytes + kBBytes);
+                const uint32_t d1 = tmem_base + as * Cfg::kAccCols, d2 = d1 + kBN;
+                for (int i = 0; i < nk; ++i, ++it) {
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (it / Cfg::kStages) & 1;
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t st = ptx::smem_u32(smem + s * Cfg::kStageBytes);
+                    const uint64_t a_hi = ptx::make_sw128_kmajor_desc(st);
+                    const uint64_t b_hi = ptx::make_sw128_kmajor_desc(st + kABytes);
+                    const uint64_t a_lo = ptx::make_sw128_kmajor_desc(st + kABytes + kBBytes);
+                    const uint64_t b_lo = ptx::make_sw128_kmajor_desc(st + 2 * kABytes + kBBytes);
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                    const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);   // +32 B along K inside the swizzle atom
-                    const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-                    ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
-                    if (NSPLIT == 3) {
-                        ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, acc);
-                        ptx::umma_f16(d2, a_hi + ko, b_lo + ko, idesc, 1u);
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);   // +32 B along K inside the swizzle atom
+                        const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+                        ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
+                        if (NSPLIT == 3) {
+                            ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, acc);
+                            ptx::umma_f16(d2, a_hi + ko, b_lo + ko, idesc, 1u);
+                        }
                     }
+                    ptx::umma_commit(&empty_bar[s]);      // frees this smem stage once the MMAs above retire
                 }
-                ptx::umma_commit(&empty_bar[s]);      // frees this smem stage once the MMAs above retire
+                ptx::umma_commit(&tmem_full_bar[as]);     // this tile's accumulators are complete
             }
-            ptx::umma_commit(tmem_full_bar);          // accumulators complete
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int m = quarter * 32 + lane;
-        const int r = h0 + (m >> 4), c = w0 + (m & 15);
-        const int rows = A.d.rows[plane], cols = A.d.cols[plane];
-        const bool valid = r < rows && c < cols;
-        const size_t px = static_cast<size_t>(b) * rows * cols + static_cast<size_t>(r) * cols + c;
-        // Everything the epilogue adds to the accumulator (bias + rollout 1-D terms + additive embedding + identity
-        // residual) is gathered into registers NOW, while the MMA pipeline is still running, so no global-load
-        // latency is left on the critical path after the accumulators land.
-        float pre[kBN];
-        {
-            const float4* bias4 = reinterpret_cast<const float4*>(A.e.bias.p[plane] + n0);
-#pragma unroll
-            for (int j = 0; j < kBN / 4; ++j) {
-                const float4 t = __ldg(bias4 + j);
-                pre[4 * j] = t.x; pre[4 * j + 1] = t.y; pre[4 * j + 2] = t.z; pre[4 * j + 3] = t.w;
-            }
-            if (A.e.embadd) {
-                const float4* e4 = reinterpret_cast<const float4*>(
-                    A.e.embadd + static_cast<size_t>(A.e.film_row ? A.e.film_row[b] : b) * A.e.film_dim + A.e.film_off + n0);
+        int lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const ConvTile T = conv_tile_decode(A, t);
+            const int plane = T.plane, n0 = T.n0, b = T.b;
+            const int r = T.h0 + (m >> 4), c = T.w0 + (m & 15);
+            const int rows = A.d.rows[plane], cols = A.d.cols[plane];
+            const bool valid = r < rows && c < cols;
+            const size_t px = static_cast<size_t>(b) * rows * cols + static_cast<size_t>(r) * cols + c;
+            // Everything the epilogue adds to the accumulator (bias + rollout 1-D terms + additive embedding + identity
+            // residual) is gathered into registers while the MMA pipeline of this tile is still running.
+            float pre[kBN];
+            {
+                const float4* bias4 = reinterpret_cast<const float4*>(A.e.bias.p[plane] + n0);
 #pragma unroll
                 for (int j = 0; j < kBN / 4; ++j) {
-                    const float4 t = __ldg(e4 + j);
-                    pre[4 * j] += t.x; pre[4 * j + 1] += t.y; pre[4 * j + 2] += t.z; pre[4 * j + 3] += t.w;
+                    const float4 v = __ldg(bias4 + j);
+                    pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
                 }
-            }
-            if (valid && A.e.Trow.p[plane]) {
-                const size_t bo = static_cast<size_t>(b) * 4;
-                const float4* tr = reinterpret_cast<const float4*>(
-                    A.e.Trow.p[plane] + ((bo + edge_class(c, cols)) * rows + r) * A.Cout + n0);
-                const float4* tc = reinterpret_cast<const float4*>(
-                    A.e.Tcol.p[plane] + ((bo + edge_class(r, rows)) * cols + c) * A.Cout + n0);
+                if (A.e.embadd) {
+                    const float4* e4 = reinterpret_cast<const float4*>(
+                        A.e.embadd + static_cast<size_t>(A.e.film_row ? A.e.film_row[b] : b) * A.e.film_dim + A.e.film_off + n0);
 #pragma unroll
-                for (int j = 0; j < kBN / 4; ++j) {
-                    const float4 t = __ldg(tr + j), u = __ldg(tc + j);
-                    pre[4 * j] += t.x + u.x; pre[4 * j + 1] += t.y + u.y; pre[4 * j + 2] += t.z + u.z;
-                    pre[4 * j + 3] += t.w + u.w;
-                }
-            }
-            if (valid && A.e.resid.p[plane]) {
-                const float4* rs = reinterpret_cast<const float4*>(A.e.resid.p[plane] + px * A.Cout + n0);
-#pragma unroll
-                for (int j = 0; j < kBN / 4; ++j) {
-                    const float4 t = __ldg(rs + j);
-                    pre[4 * j] += t.x; pre[4 * j + 1] += t.y; pre[4 * j + 2] += t.z; pre[4 * j + 3] += t.w;
-                }
-            }
-        }
-        float* __restrict__ outp = A.e.out.p[plane] + px * A.Cout + n0;
-        ptx::mbar_wait(tmem_full_bar, 0);
-        __syncwarp();
-        ptx::tc_fence_after();
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t v1[32], v2[32];
-            ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
-            if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
-            ptx::tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float o[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float acc = __uint_as_float(v1[j + q]);
-                        if (NSPLIT == 3) acc = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, acc);
-                        o[q] = acc + pre[half * 32 + j + q];
+                    for (int j = 0; j < kBN / 4; ++j) {
+                        const float4 v = __ldg(e4 + j);
+                        pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w;
                     }
-                    *reinterpret_cast<float4*>(outp + half * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                if (valid && A.e.Trow.p[plane]) {
+                    const size_t bo = static_cast<size_t>(b) * 4;
+                    const float4* tr = reinterpret_cast<const float4*>(
+                        A.e.Trow.p[plane] + ((bo + edge_class(c, cols)) * rows + r) * A.Cout + n0);
+                    const float4* tc = reinterpret_cast<const float4*>(
+                        A.e.Tcol.p[plane] + ((bo + edge_class(r, rows)) * cols + c) * A.Cout + n0);
+#pragma unroll
+                    for (int j = 0; j < kBN / 4; ++j) {
+                        const float4 v = __ldg(tr + j), u = __ldg(tc + j);
+                        pre[4 * j] += v.x + u.x; pre[4 * j + 1] += v.y + u.y; pre[4 * j + 2] += v.z + u.z;
+                        pre[4 * j + 3] += v.w + u.w;
+                    }
+                }
+                if (valid && A.e.resid.p[plane]) {
+                    const float4* rs = reinterpret_cast<const float4*>(A.e.resid.p[plane] + px * A.Cout + n0);
+#pragma unroll
+                    for (int j = 0; j < kBN / 4; ++j) {
+                        const float4 v = __ldg(rs + j);
+                        pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w;
+                    }
                 }
             }
+            float* __restrict__ outp = A.e.out.p[plane] + px * A.Cout + n0;
+            const int as = lt & 1;
+            const uint32_t aph = (lt >> 1) & 1;
+            ptx::mbar_wait(&tmem_full_bar[as], aph);
+            __syncwarp();
+            ptx::tc_fence_after();
+            const uint32_t lane_addr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v1[32], v2[32];
+                ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
+                if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
+                ptx::tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float o[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float acc = __uint_as_float(v1[j + q]);
+                            if (NSPLIT == 3) acc = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, acc);
+                            o[q] = acc + pre[half * 32 + j + q];
+                        }
+                        *reinterpret_cast<float4*>(outp + half * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+            // hand the accumulator stage back to the MMA issuer
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
         }
     }
     ptx::tc_fence_before();
@@ -239,7 +282,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
-
 
 // =====================================================================================
 // Rollout 1-D terms on the tensor cores (replaces the SIMT k_roll1d on the product path).
@@ -296,7 +338,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_roll_tc(const __grid_consta
             ptx::fence_barrier_init();
         }
         __syncwarp();
-        ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+        ptx::tmem_alloc<Cfg::kAccCols>(tmem_ptr_smem);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -384,7 +426,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_roll_tc(const __grid_consta
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+        ptx::tmem_dealloc<Cfg::kAccCols>(tmem_base);
     }
 }
 

@@ -43,22 +43,126 @@ __global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, Tr
 }
 
 // =====================================================================================
-// GroupNorm statistics (deterministic two-level reduction, fp64 combine).
-// reference src/diffusion/nn.py:17-19 (GroupNorm32 computes in fp32), unet_triplane.py:63-84
-// grid (chunks, 3, B), block (C/4, NY); partial [B][3][chunks][32][2] double; ticket [B][3]
-// stats out [B][3][32][2] = (mean, rstd)
+// GroupNorm statistics -> per-channel affine coefficients.
+// reference src/diffusion/nn.py:17-19 (GroupNorm32 computes in fp32), unet_triplane.py:63-84, FiLM :285-297
+// Producers write one (sum, sum-sq) pair per group per CTA ("slot") in fp64; the LAST CTA of a (sample, plane)
+// (atomic ticket) reduces the slots in a fixed order and emits, for the consumer's norm layer,
+//     y = x * coef[c][0] + coef[c][1]   ==  GroupNorm(x) * gamma + beta   (optionally * (1 + scale) + shift)
+// so consumers need no statistics pass, no shared memory and no barrier before their first load.
 // =====================================================================================
-__global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, int chunks, double* __restrict__ partial,
-                                                   unsigned int* __restrict__ ticket, float* __restrict__ stats) {
-    extern __shared__ float red[];   // [NY][2][C] then [2][C] channel totals
-    __shared__ bool is_last;
-    __shared__ double fin[2][8][kGroups];
-    const int plane = blockIdx.y, b = blockIdx.z, chunk = blockIdx.x;
-    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
+struct StatsSink {
+    double* partial;          // [B][3][nslots][32][2]
+    unsigned int* ticket;     // [B][3]
+    float* coef;              // [B][3][C][2]
+    TriCF gamma, beta;        // consumer norm parameters [C]
+    const float* film;        // [rows][film_dim] or nullptr
+    const int* film_row;
+    int film_dim, film_off;   // scale at film_off, shift at film_off + C
+    int C;
+};
+
+// Called by all `nthr` threads (tid = 0..nthr-1, nthr >= 64) of a CTA after it has written its slot(s).
+// `expected` = number of CTAs contributing to this (sample, plane); `sync()` is a barrier over those nthr threads.
+template <class Sync>
+__device__ __forceinline__ void stats_finalize_tail(const StatsSink& S, int b, int plane, int nslots, unsigned int expected,
+                                                    double n_per_group, int tid, int nthr, Sync sync, double* fin /*smem [64*8]*/,
+                                                    int* flag /*smem*/) {
+    __threadfence();
+    sync();
+    if (tid == 0) {
+        unsigned int prev = atomicAdd(&S.ticket[b * 3 + plane], 1u);
+        *flag = (prev == expected - 1u) ? 1 : 0;
+    }
+    sync();
+    if (!*flag) return;
+    __threadfence();
+    const double* pp = S.partial + (static_cast<size_t>(b) * 3 + plane) * nslots * kGroups * 2;
+    // 8 slices x 64 (group, sum|sumsq) entries; every entry walks its slots in a fixed order, 8 loads in flight
+    for (int i = tid; i < 64 * 8; i += nthr) {
+        const int slice = i >> 6, gw = i & 63;
+        double acc = 0.0;
+        int sl = slice;
+        for (; sl + 56 < nslots; sl += 64) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldcg(pp + static_cast<size_t>(sl + 8 * k) * 64 + gw);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc += v[k];
+        }
+        for (; sl < nslots; sl += 8) acc += __ldcg(pp + static_cast<size_t>(sl) * 64 + gw);
+        fin[slice * 64 + gw] = acc;
+    }
+    sync();
+    if (tid < 64) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += fin[k * 64 + tid];
+        fin[tid] = acc;          // slice 0 now holds the totals (tid < 64 only touches column tid)
+    }
+    sync();
+    const int C = S.C, cpg = C / kGroups;
+    const float* film = nullptr;
+    if (S.film) film = S.film + static_cast<size_t>(S.film_row ? S.film_row[b] : b) * S.film_dim + S.film_off;
+    float* co = S.coef + (static_cast<size_t>(b) * 3 + plane) * C * 2;
+    for (int c = tid; c < C; c += nthr) {
+        const int g = c / cpg;
+        const double mean = fin[g * 2] / n_per_group;
+        double var = fin[g * 2 + 1] / n_per_group - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
+        float ga = S.gamma.p[plane][c] * rstd;
+        float be = S.beta.p[plane][c] - static_cast<float>(mean) * ga;
+        if (film) {
+            const float sc = 1.f + film[c], sh = film[C + c];
+            ga *= sc;
+            be = fmaf(be, sc, sh);
+        }
+        co[c * 2] = ga;
+        co[c * 2 + 1] = be;
+    }
+    if (tid == 0) S.ticket[b * 3 + plane] = 0u;   // re-arm for the next launch
+}
+
+// Block-wide reduction of per-thread (sum, sum-sq) float4 pairs laid out as block (C/4, NY) into this CTA's slot.
+// red: smem [(NY*2 + 2) * C] floats.
+__device__ __forceinline__ void stats_block_partial(const StatsSink& S, float4 s, float4 q, int b, int plane, int slot, int nslots,
+                                                    float* red) {
+    const int C = S.C, tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
     const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
+    float* rs = red + (ty * 2 + 0) * C + tx * 4;
+    float* rq = red + (ty * 2 + 1) * C + tx * 4;
+    rs[0] = s.x; rs[1] = s.y; rs[2] = s.z; rs[3] = s.w;
+    rq[0] = q.x; rq[1] = q.y; rq[2] = q.z; rq[3] = q.w;
+    __syncthreads();
+    float* tot = red + NY * 2 * C;
+    for (int i = tid; i < 2 * C; i += nthr) {
+        const int which = i / C, c = i - which * C;
+        float acc = 0.f;
+        for (int y = 0; y < NY; ++y) acc += red[(y * 2 + which) * C + c];
+        tot[i] = acc;
+    }
+    __syncthreads();
+    const int cpg = C / kGroups;
+    double* part = S.partial + ((static_cast<size_t>(b) * 3 + plane) * nslots + slot) * kGroups * 2;
+    if (tid < 2 * kGroups) {
+        const int g = tid >> 1, which = tid & 1;
+        double acc = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(tot[which * C + c]);
+        part[g * 2 + which] = acc;
+    }
+}
+
+// Stand-alone statistics pass (used where the producer kernel does not emit partials itself).
+// grid (nslots, 3, B), block (C/4, NY)
+__global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink S, int nslots) {
+    extern __shared__ float red[];   // [(NY*2 + 2) * C]
+    __shared__ double fin[64 * 8];
+    __shared__ int flag;
+    const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
+    const int C = S.C, tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
     const int npx = d.rows[plane] * d.cols[plane];
-    const int ppc = (npx + chunks - 1) / chunks;
-    const int p0 = chunk * ppc, p1 = min(npx, p0 + ppc);
+    const int ppc = (npx + nslots - 1) / nslots;
+    const int p0 = slot * ppc, p1 = min(npx, p0 + ppc);
     const float* xp = x.p[plane] + static_cast<size_t>(b) * npx * C;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
     for (int px = p0 + ty; px < p1; px += 4 * NY) {
@@ -74,61 +178,10 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
             q.z = fmaf(v[k].z, v[k].z, q.z); q.w = fmaf(v[k].w, v[k].w, q.w);
         }
     }
-    float* rs = red + (ty * 2 + 0) * C + tx * 4;
-    float* rq = red + (ty * 2 + 1) * C + tx * 4;
-    rs[0] = s.x; rs[1] = s.y; rs[2] = s.z; rs[3] = s.w;
-    rq[0] = q.x; rq[1] = q.y; rq[2] = q.z; rq[3] = q.w;
-    __syncthreads();
-    // per-channel totals over the NY pixel lanes (2C threads, fixed order), kept behind the lane buffers
-    float* tot = red + NY * 2 * C;
-    for (int i = tid; i < 2 * C; i += nthr) {
-        const int which = i / C, c = i - which * C;
-        float acc = 0.f;
-        for (int y = 0; y < NY; ++y) acc += red[(y * 2 + which) * C + c];
-        tot[i] = acc;
-    }
-    __syncthreads();
-    const int cpg = C / kGroups;
-    double* part = partial + ((static_cast<size_t>(b) * 3 + plane) * chunks + chunk) * kGroups * 2;
-    if (tid < 2 * kGroups) {
-        const int g = tid >> 1, which = tid & 1;
-        double acc = 0.0;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(tot[which * C + c]);
-        part[g * 2 + which] = acc;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int prev = atomicAdd(&ticket[b * 3 + plane], 1u);
-        is_last = (prev == static_cast<unsigned int>(chunks - 1));
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // last CTA of this (sample, plane): 8 lanes per (group, sum|sumsq) walk the chunks in a fixed order
-    const double* pp = partial + (static_cast<size_t>(b) * 3 + plane) * chunks * kGroups * 2;
-    for (int i = tid; i < 2 * kGroups * 8; i += nthr) {
-        const int slot = i >> 6, gw = i & 63;          // gw = g*2 + which
-        double acc = 0.0;
-        for (int ch = slot; ch < chunks; ch += 8) acc += __ldcg(pp + ch * kGroups * 2 + gw);
-        fin[gw & 1][slot][gw >> 1] = acc;
-    }
-    __syncthreads();
-    if (tid < kGroups) {
-        double ds = 0.0, dq = 0.0;
-        for (int k = 0; k < 8; ++k) {
-            ds += fin[0][k][tid];
-            dq += fin[1][k][tid];
-        }
-        const double n = static_cast<double>(npx) * cpg;
-        const double mean = ds / n;
-        double var = dq / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        float* st = stats + ((static_cast<size_t>(b) * 3 + plane) * kGroups + tid) * 2;
-        st[0] = static_cast<float>(mean);
-        st[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
-    }
-    if (tid == 0) ticket[b * 3 + plane] = 0u;   // re-arm for the next launch
+    stats_block_partial(S, s, q, b, plane, slot, nslots, red);
+    const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
+    stats_finalize_tail(S, b, plane, nslots, static_cast<unsigned int>(nslots), static_cast<double>(npx) * (C / kGroups), tid, nthr,
+                        [] { __syncthreads(); }, fin, &flag);
 }
 
 // =====================================================================================
@@ -138,8 +191,9 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, int C, in
 // enough loads in flight at batch 1).  grid (max tiles, 3, B), block (C/4, ny).
 // Axis sums are accumulated as 64-bit fixed point (value * 2^24) with integer atomics: exact, hence independent of
 // tile order / batch composition / GPU count.  sums[b][seg_off[plane*2+kind] + pos][C], kind 0 = sum over columns
-// (indexed by row), kind 1 = sum over rows (indexed by column).  The last CTA of each (sample, plane) turns that
-// plane's sums into fp16 (hi, lo) means [2][B][total_len][C] (the A operand of the rollout 1-D GEMM) and re-zeroes them.
+// (indexed by row), kind 1 = sum over rows (indexed by column).  The CTA that completes a row strip / a column tile
+// (per-strip and per-column-tile tickets) turns those sums into fp16 (hi, lo) means [2][B][total_len][C] — the A operand
+// of the rollout 1-D GEMM — and re-zeroes them, so no separate finalize / memset pass exists.
 // =====================================================================================
 constexpr int kGsRows = 4;
 constexpr float kFixScale = 16777216.f;          // 2^24
@@ -149,16 +203,14 @@ struct GnSiluArgs {
     TriCF x;          // fp32 [B][rows][cols][C]
     TriDims d;
     int C;
-    const float* stats;       // [B][3][32][2]
-    TriCF gamma, beta;        // [C]
-    const float* film;        // [rows][film_dim] or nullptr
-    const int* film_row;      // [B] or nullptr (row = b)
-    int film_dim, film_off;   // scale at film_off, shift at film_off + C
+    const float* coef;        // [B][3][C][2] from the statistics tail
     TriH a;                   // out [2][B][rows][cols][C]
     TriH x16;                 // optional raw copy of x as (hi, lo) for the 1x1 skip GEMM
     unsigned long long* sums; // [B][total_len][C] fixed point, zero between launches; nullptr when rollout is off
     __half* means16;          // [2][B][total_len][C]
-    unsigned int* ticket;     // [B][3]
+    unsigned int* ticket;     // [B][total_tickets]: per plane, `strips` row-strip tickets then `ctiles` column-tile tickets
+    int tick_off[3];          // offset of plane p's tickets
+    int total_tickets;
     int seg_off[6];
     int total_len;
 };
@@ -167,43 +219,35 @@ __device__ __forceinline__ void fix_add(unsigned long long* p, float v) {
     atomicAdd(p, static_cast<unsigned long long>(__float2ll_rn(v * kFixScale)));
 }
 
+// sums -> fp16 (hi, lo) means for `n` consecutive elements, re-zeroing the accumulators
+__device__ __forceinline__ void means_finalize(unsigned long long* sp, __half* mh, __half* ml, int n, double scale, int tid, int nthr) {
+    for (int i = tid; i < n; i += nthr) {
+        const long long sv = static_cast<long long>(__ldcg(sp + i));
+        sp[i] = 0ull;
+        const float m = static_cast<float>(static_cast<double>(sv) * scale);
+        __half hi, lo;
+        split_f16(m, hi, lo);
+        mh[i] = hi;
+        ml[i] = lo;
+    }
+}
+
 __global__ void __launch_bounds__(256, 3) k_gn_silu(GnSiluArgs A, int B) {
-    extern __shared__ float sm[];   // coefA[C], coefB[C], red[ny][4][C]
-    __shared__ bool is_last;
+    extern __shared__ float red[];   // [ny][4][C]
+    __shared__ int last_row, last_col;
     const int plane = blockIdx.y, b = blockIdx.z;
     const int rows = A.d.rows[plane], cols = A.d.cols[plane], C = A.C;
     const int tx = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
     const int tid = ty * blockDim.x + tx, nthr = blockDim.x * ny;
     const int ctiles = (cols + ny - 1) / ny, strips = (rows + kGsRows - 1) / kGsRows;
-    const int ntiles = ctiles * strips;
-    if (static_cast<int>(blockIdx.x) >= ntiles) return;
+    if (static_cast<int>(blockIdx.x) >= ctiles * strips) return;
     const int strip = blockIdx.x / ctiles, ct = blockIdx.x - strip * ctiles;
     const int r0 = strip * kGsRows;
     const int nr = min(kGsRows, rows - r0);
     const int c = ct * ny + ty;
     const bool cvalid = c < cols;
-    float* coefA = sm;
-    float* coefB = sm + C;
-    float* red = sm + 2 * C;
-    const int cpg = C / kGroups;
-    const float* st = A.stats + (static_cast<size_t>(b) * 3 + plane) * kGroups * 2;
-    const float* film = nullptr;
-    if (A.film) film = A.film + static_cast<size_t>(A.film_row ? A.film_row[b] : b) * A.film_dim + A.film_off;
-    for (int ch = tid; ch < C; ch += nthr) {
-        float mean = st[(ch / cpg) * 2], rstd = st[(ch / cpg) * 2 + 1];
-        float g = A.gamma.p[plane][ch] * rstd;
-        float o = A.beta.p[plane][ch] - mean * g;
-        if (film) {
-            float sc = 1.f + film[ch], sh = film[C + ch];
-            g *= sc;
-            o = fmaf(o, sc, sh);
-        }
-        coefA[ch] = g;
-        coefB[ch] = o;
-    }
-    __syncthreads();
-    const float4 ca = *reinterpret_cast<const float4*>(coefA + tx * 4);
-    const float4 cb = *reinterpret_cast<const float4*>(coefB + tx * 4);
+    const float4* cf4 = reinterpret_cast<const float4*>(A.coef + (static_cast<size_t>(b) * 3 + plane) * C * 2) + tx * 2;
+    const float4 k0 = __ldg(cf4), k1 = __ldg(cf4 + 1);       // (A0,B0,A1,B1), (A2,B2,A3,B3)
     const size_t plane_elems = static_cast<size_t>(rows) * cols * C;
     const size_t sample_off = static_cast<size_t>(b) * plane_elems;
     const size_t lo_off = static_cast<size_t>(B) * plane_elems;
@@ -223,10 +267,10 @@ __global__ void __launch_bounds__(256, 3) k_gn_silu(GnSiluArgs A, int B) {
             if (r < nr) {
                 const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
                 if (xq) store_split4(xq + off, xq + lo_off + off, v[r]);
-                y[r].x = silu_f(fmaf(v[r].x, ca.x, cb.x));
-                y[r].y = silu_f(fmaf(v[r].y, ca.y, cb.y));
-                y[r].z = silu_f(fmaf(v[r].z, ca.z, cb.z));
-                y[r].w = silu_f(fmaf(v[r].w, ca.w, cb.w));
+                y[r].x = silu_f(fmaf(v[r].x, k0.x, k0.y));
+                y[r].y = silu_f(fmaf(v[r].y, k0.z, k0.w));
+                y[r].z = silu_f(fmaf(v[r].z, k1.x, k1.y));
+                y[r].w = silu_f(fmaf(v[r].w, k1.z, k1.w));
                 store_split4(ap + off, ap + lo_off + off, y[r]);
             }
         }
@@ -254,34 +298,32 @@ __global__ void __launch_bounds__(256, 3) k_gn_silu(GnSiluArgs A, int B) {
         for (int yy = 0; yy < ny; ++yy) acc += red[(static_cast<size_t>(yy) * kGsRows + r) * C + ch];
         fix_add(srow + static_cast<size_t>(r0 + r) * C + ch, acc);
     }
-    // ---- last CTA of this (sample, plane): sums -> fp16 (hi, lo) means, and re-zero the accumulators
+    // ---- whoever completes this row strip / this column tile converts it to fp16 means and re-zeroes it
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        unsigned int prev = atomicAdd(&A.ticket[b * 3 + plane], 1u);
-        is_last = (prev == static_cast<unsigned int>(ntiles - 1));
+        unsigned int* tk = A.ticket + static_cast<size_t>(b) * A.total_tickets + A.tick_off[plane];
+        const unsigned int pr = atomicAdd(tk + strip, 1u);
+        const unsigned int pc = atomicAdd(tk + strips + ct, 1u);
+        last_row = pr == static_cast<unsigned int>(ctiles - 1);
+        last_col = pc == static_cast<unsigned int>(strips - 1);
+        if (last_row) tk[strip] = 0u;
+        if (last_col) tk[strips + ct] = 0u;
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!last_row && !last_col) return;
     __threadfence();
     const size_t mlo = static_cast<size_t>(B) * A.total_len * C;
     __half* mb = A.means16 + static_cast<size_t>(b) * A.total_len * C;
-    for (int kind = 0; kind < 2; ++kind) {
-        const int len = kind == 0 ? rows : cols;
-        const double scale = kFixInv / static_cast<double>(kind == 0 ? cols : rows);
-        const size_t seg = static_cast<size_t>(A.seg_off[plane * 2 + kind]) * C;
-        unsigned long long* sp = sb + seg;
-        for (int i = tid; i < len * C; i += nthr) {
-            const long long sv = static_cast<long long>(__ldcg(sp + i));
-            sp[i] = 0ull;
-            const float m = static_cast<float>(static_cast<double>(sv) * scale);
-            __half hi, lo;
-            split_f16(m, hi, lo);
-            mb[seg + i] = hi;
-            mb[mlo + seg + i] = lo;
-        }
+    if (last_row) {
+        const size_t o = (static_cast<size_t>(A.seg_off[plane * 2 + 0]) + r0) * C;
+        means_finalize(sb + o, mb + o, mb + mlo + o, nr * C, kFixInv / static_cast<double>(cols), tid, nthr);
     }
-    if (tid == 0) A.ticket[b * 3 + plane] = 0u;
+    if (last_col) {
+        const int c0 = ct * ny, nc = min(ny, cols - c0);
+        const size_t o = (static_cast<size_t>(A.seg_off[plane * 2 + 1]) + c0) * C;
+        means_finalize(sb + o, mb + o, mb + mlo + o, nc * C, kFixInv / static_cast<double>(rows), tid, nthr);
+    }
 }
 
 // =====================================================================================
@@ -519,9 +561,8 @@ __global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, 
 // blockIdx.y == 3 zero-fills the D x D corner.  reference unet_triplane.py:441-445, triplane_util.py:7-17
 // grid (ceil(max(max_px, D*D)/128), 4, B), block 128 (one thread per pixel)
 // =====================================================================================
-__global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int Cout, const float* __restrict__ stats,
-                                                  TriCF gamma, TriCF beta, TriCF w, TriCF bias, float* __restrict__ out,
-                                                  int H, int W, int Dd) {
+__global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int Cout, const float* __restrict__ coef,
+                                                  TriCF w, TriCF bias, float* __restrict__ out, int H, int W, int Dd) {
     extern __shared__ float sm[];   // coefA[C], coefB[C], ws[Cout][C], bs[Cout]
     const int plane = blockIdx.y, b = blockIdx.z;
     const int Hc = H + Dd, Wc = W + Dd;
@@ -540,12 +581,10 @@ __global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int
     float* coefB = sm + C;
     float* ws = sm + 2 * C;
     float* bs = ws + Cout * C;
-    const int cpg = C / kGroups;
-    const float* st = stats + (static_cast<size_t>(b) * 3 + plane) * kGroups * 2;
+    const float* cf = coef + (static_cast<size_t>(b) * 3 + plane) * C * 2;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float g = gamma.p[plane][c] * st[(c / cpg) * 2 + 1];
-        coefA[c] = g;
-        coefB[c] = beta.p[plane][c] - st[(c / cpg) * 2] * g;
+        coefA[c] = cf[c * 2];
+        coefB[c] = cf[c * 2 + 1];
     }
     for (int k = threadIdx.x; k < Cout * C; k += blockDim.x) ws[k] = w.p[plane][k];
     for (int k = threadIdx.x; k < Cout; k += blockDim.x) bs[k] = bias.p[plane][k];

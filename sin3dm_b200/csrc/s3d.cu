@@ -188,6 +188,7 @@ struct s3d_unet {
     std::vector<DevBlock> dblocks;
     std::unique_ptr<Plan> plan;
     int last_launches = 0;
+    int num_sms = 148;
 };
 
 static int ch_of(const s3d_unet_config& c, int level) { return c.channel_mult[level] * c.model_channels; }
@@ -512,7 +513,9 @@ struct PlanBuilder {
     struct Sums {
         unsigned long long* buf = nullptr;   // [B][total_len][C] 64-bit fixed point, zero between launches
         __half* means16 = nullptr;           // [2][B][total_len][C]
-        unsigned int* ticket = nullptr;      // [B][3]
+        unsigned int* ticket = nullptr;      // [B][total_tickets]
+        int tick_off[3] = {};
+        int total_tickets = 0;
         int seg_off[6] = {};                 // plane*2 + kind (0: indexed by row, 1: indexed by column)
         int total_len = 0;
     };
@@ -531,35 +534,58 @@ struct PlanBuilder {
         S.buf = dev_alloc<unsigned long long>(P->allocs, n);
         CUDA_TRY(cudaMemset(S.buf, 0, sizeof(unsigned long long) * n));
         S.means16 = dev_alloc<__half>(P->allocs, 2 * n);
-        S.ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3);
-        CUDA_TRY(cudaMemset(S.ticket, 0, sizeof(unsigned int) * B * 3));
+        const int ny = std::max(1, 256 / (C / 4));
+        int tk = 0;
+        for (int p = 0; p < 3; ++p) {
+            S.tick_off[p] = tk;
+            tk += (d.rows[p] + kGsRows - 1) / kGsRows + (d.cols[p] + ny - 1) / ny;
+        }
+        S.total_tickets = tk;
+        S.ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * tk);
+        CUDA_TRY(cudaMemset(S.ticket, 0, sizeof(unsigned int) * B * tk));
         return S;
     }
 
-    // ---- GroupNorm statistics
-    float* stats(const ActF& x) {
+    // ---- GroupNorm statistics -> per-channel affine coefficients of the consuming norm layer
+    StatsSink make_sink(int C, int nslots, const DevNorm& n, int film_off) {
+        StatsSink S{};
+        S.partial = dev_alloc<double>(P->allocs, static_cast<size_t>(B) * 3 * nslots * kGroups * 2);
+        S.ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3);
+        CUDA_TRY(cudaMemset(S.ticket, 0, sizeof(unsigned int) * B * 3));
+        S.coef = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 3 * C * 2);
+        S.gamma = cf3(n.gamma);
+        S.beta = cf3(n.beta);
+        S.film_dim = u->film_dim;
+        S.film_off = film_off;
+        S.C = C;
+        return S;
+    }
+    float* stats(const ActF& x, const DevNorm& n, int film_off) {
         const int level = x.level, C = x.C;
         S3D_CHECK(C % kGroups == 0 && C % 4 == 0 && C / 4 <= 128, "unsupported channel count for GroupNorm32");
-        const int chunks = std::max(1, std::min(128, max_px(level) / 48));
-        double* partial = dev_alloc<double>(P->allocs, static_cast<size_t>(B) * 3 * chunks * kGroups * 2);
-        unsigned int* ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3);
-        CUDA_TRY(cudaMemset(ticket, 0, sizeof(unsigned int) * B * 3));
-        float* st = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 3 * kGroups * 2);
+        const int nslots = std::max(1, std::min(128, max_px(level) / 48));
+        StatsSink S = make_sink(C, nslots, n, film_off);
         TriCF xc = cf(x.p);
         TriDims d = dims[level];
         const int Bv = B;
+        const bool use_film = film_off >= 0;
+        Plan* Pp = P;
         add_op("k_gn_stats", 0.0, [=](cudaStream_t s) {
+            StatsSink Sl = S;
+            if (use_film) {
+                Sl.film = Pp->film;
+                Sl.film_row = Pp->film_row;
+            }
             const int ny = std::max(1, std::min(16, 1024 / (C / 4)));
-            dim3 grid(chunks, 3, Bv), block(C / 4, ny);
-            k_gn_stats<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, d, C, chunks, partial, ticket, st);
+            dim3 grid(nslots, 3, Bv), block(C / 4, ny);
+            k_gn_stats<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, d, Sl, nslots);
             LAUNCH_CHECK("k_gn_stats");
         });
-        return st;
+        return S.coef;
     }
 
     // ---- GN apply + SiLU (+FiLM) -> fp16 operands (+ raw x16) (+ axis means)
-    void gn_silu(const ActF& x, const float* st, const DevNorm& n, int film_off, const Act16& a, const Act16* x16,
-                 const Sums* S) {
+    void gn_silu(const ActF& x, const float* coef, const Act16& a, const Act16* x16, const Sums* S) {
         const int level = x.level, C = x.C;
         const TriDims d = dims[level];
         const int bx = C / 4;
@@ -572,33 +598,24 @@ struct PlanBuilder {
         A.x = cf(x.p);
         A.d = d;
         A.C = C;
-        A.stats = st;
-        A.gamma = cf3(n.gamma);
-        A.beta = cf3(n.beta);
-        A.film_dim = u->film_dim;
-        A.film_off = film_off;
+        A.coef = coef;
         A.a = a.p;
         if (x16) A.x16 = x16->p;
         if (S) {
             A.sums = S->buf;
             A.means16 = S->means16;
             A.ticket = S->ticket;
+            A.total_tickets = S->total_tickets;
+            for (int i = 0; i < 3; ++i) A.tick_off[i] = S->tick_off[i];
             for (int i = 0; i < 6; ++i) A.seg_off[i] = S->seg_off[i];
             A.total_len = S->total_len;
         }
-        const bool use_film = film_off >= 0;
-        const size_t smem = sizeof(float) * (2 + static_cast<size_t>(ny) * kGsRows) * C;
+        const size_t smem = sizeof(float) * static_cast<size_t>(ny) * kGsRows * C;
         S3D_CHECK(smem <= 100 * 1024, "k_gn_silu shared memory");
-        Plan* Pp = P;
         const int Bv = B;
         add_op("k_gn_silu", 0.0, [=](cudaStream_t s) {
-            GnSiluArgs Al = A;
-            if (use_film) {
-                Al.film = Pp->film;
-                Al.film_row = Pp->film_row;
-            }
             dim3 grid(gx, 3, Bv), block(bx, ny);
-            k_gn_silu<<<grid, block, smem, s>>>(Al, Bv);
+            k_gn_silu<<<grid, block, smem, s>>>(A, Bv);
             LAUNCH_CHECK("k_gn_silu");
         });
     }
@@ -772,15 +789,17 @@ struct PlanBuilder {
         A.tile_start[3] = total;
         const int nsplit = u->cfg.precision == 1 ? 1 : 3;
         const int ntile_n = cv.Cout / kBN;
+        const int num_sms = u->num_sms;
         add_op("k_conv_tc", conv_flops(level, cv), [=](cudaStream_t s) {
             ConvTcArgs Al = A;
             if (use_emb) {
                 Al.e.embadd = Pp->film;
                 Al.e.film_row = Pp->film_row;
             }
-            dim3 grid(total, ntile_n, Bv);
-            if (nsplit == 3) k_conv_tc<3><<<grid, kConvThreads, ConvTcCfg<3>::kSmemBytes, s>>>(*maps, Al);
-            else k_conv_tc<1><<<grid, kConvThreads, ConvTcCfg<1>::kSmemBytes, s>>>(*maps, Al);
+            const int total_tiles = total * ntile_n * Bv;
+            dim3 grid(std::min(total_tiles, num_sms));
+            if (nsplit == 3) k_conv_tc<3><<<grid, kConvThreads, ConvTcCfg<3>::kSmemBytes, s>>>(*maps, Al, total_tiles);
+            else k_conv_tc<1><<<grid, kConvThreads, ConvTcCfg<1>::kSmemBytes, s>>>(*maps, Al, total_tiles);
             LAUNCH_CHECK("k_conv_tc");
         });
     }
@@ -796,18 +815,18 @@ struct PlanBuilder {
             s1 = alloc_sums(level, b.cin);
             s2 = alloc_sums(level, b.cout);
         }
-        float* st1 = stats(x);
+        float* st1 = stats(x, w.n1, -1);
         Act16 a1 = alloc16(level, b.cin);
         Act16 x16{};
         if (b.has_skip) x16 = alloc16(level, b.cin);
-        gn_silu(x, st1, w.n1, -1, a1, b.has_skip ? &x16 : nullptr, ro ? &s1 : nullptr);
+        gn_silu(x, st1, a1, b.has_skip ? &x16 : nullptr, ro ? &s1 : nullptr);
         TBuf t1{};
         if (ro) t1 = roll1d(s1, level, w.c1);
         ActF h1 = allocF(level, b.cout, b.name + ".h1");
         conv(a1, level, w.c1, ro ? &t1 : nullptr, nullptr, nullptr, ssn ? -1 : b.film_off, h1);
-        float* st2 = stats(h1);
+        float* st2 = stats(h1, w.n2, ssn ? b.film_off : -1);
         Act16 a2 = alloc16(level, b.cout);
-        gn_silu(h1, st2, w.n2, ssn ? b.film_off : -1, a2, nullptr, ro ? &s2 : nullptr);
+        gn_silu(h1, st2, a2, nullptr, ro ? &s2 : nullptr);
         TBuf t2{};
         if (ro) t2 = roll1d(s2, level, w.c2);
         ActF out = allocF(level, b.cout, b.name + ".out");
@@ -921,18 +940,18 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     }
     S3D_CHECK(!pending_up && h.level == 0, "decoder structure");
     // ---- out head
-    float* st = pb.stats(h);
+    float* st = pb.stats(h, u->out_norm, -1);
     {
         const TriDims d0 = pb.dims[0];
         const int C = h.C, Cout = c.out_channels;
-        TriCF xc = PlanBuilder::cf(h.p), g = PlanBuilder::cf3(u->out_norm.gamma), be = PlanBuilder::cf3(u->out_norm.beta);
+        TriCF xc = PlanBuilder::cf(h.p);
         TriCF w = PlanBuilder::cf3(u->out_w), bb = PlanBuilder::cf3(u->out_b);
         const int mp = std::max(pb.max_px(0), D * D);
         const size_t smem = sizeof(float) * (2 * C + static_cast<size_t>(Cout) * C + Cout);
         S3D_CHECK(smem <= 100 * 1024, "k_out_head shared memory");
         pb.add_op("k_out_head", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * C * Cout, [=](cudaStream_t s) {
             dim3 grid((mp + 127) / 128, 4, B);
-            k_out_head<<<grid, 128, smem, s>>>(xc, d0, C, Cout, st, g, be, w, bb, P->out, H, W, D);
+            k_out_head<<<grid, 128, smem, s>>>(xc, d0, C, Cout, st, w, bb, P->out, H, W, D);
             LAUNCH_CHECK("k_out_head");
         });
     }
@@ -1010,6 +1029,7 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     std::unique_ptr<s3d_unet> u(new s3d_unet());
     u->cfg = *cfg;
     u->device = device;
+    u->num_sms = prop.multiProcessorCount;
     build_structure(u.get());
     *out = u.release();
     API_END
