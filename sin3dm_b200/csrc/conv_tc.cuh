@@ -41,6 +41,29 @@ struct ConvTcArgs {
     int tiles_x[3];
     int tile_start[4];   // prefix sum of tiles per plane
     ConvEpi e;
+    StatsSink sink;      // GroupNorm partials of the output (sink.partial == nullptr: none); needs 64 % (Cout/32) == 0
+    int sink_slots;      // slot stride of sink.partial (>= tiles of the largest plane)
+};
+
+struct RollTcMaps {
+    CUtensorMap a[6];   // means of source s: (C, L, 1, B, 2) fp16
+    CUtensorMap w[6];   // class-summed 1-D weights: (3C, 4*Cout, 2) fp16, K = along*C + c
+};
+struct RollTcArgs {
+    int L[6], ncls[6];
+    float* T[6];        // [B][4][L][Cout]
+    int tile_start[7];
+    int C, Cout;
+};
+
+// Fused launch: the rollout 1-D GEMM tiles ("roll tiles") are the first tile indices of the persistent conv kernel; the
+// conv tiles' epilogues wait on a device counter until every roll tile has been written (roll tiles never wait on
+// anything and are the first tile of the lowest-numbered CTAs, so the wait cannot deadlock).
+struct FusedRoll {
+    RollTcArgs R;
+    int n_roll;              // number of roll tiles (0: none; Trow/Tcol come from a separate launch or are absent)
+    int ntn;                 // N tiles per roll M tile
+    unsigned int* counters;  // [2]: roll tiles done, CTAs exited (both return to 0 when the kernel ends)
 };
 
 template <int NSPLIT>
@@ -49,10 +72,12 @@ struct ConvTcCfg {
     static constexpr int kStages = NSPLIT == 3 ? 4 : 8;
     static constexpr int kAccCols = NSPLIT == 3 ? 128 : 64;     // TMEM columns of one accumulator stage
     static constexpr int kTmemCols = 2 * kAccCols;              // double-buffered accumulators
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kStatBytes = kBM * 33 * 4 + 4 * 2 * 32 * 4 + 2 * kBN * 4 + 64 * 8 * 8 + 16;   // epilogue statistics scratch
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStatBytes;
 };
 
 struct ConvTile {
+    int ip;    // tile index inside its plane (statistics slot)
     int plane, h0, w0, n0, b;
 };
 __device__ __forceinline__ ConvTile conv_tile_decode(const ConvTcArgs& A, int t) {
@@ -66,6 +91,7 @@ __device__ __forceinline__ ConvTile conv_tile_decode(const ConvTcArgs& A, int t)
     T.n0 = nt * kBN;
     T.plane = rem >= A.tile_start[2] ? 2 : (rem >= A.tile_start[1] ? 1 : 0);
     const int ip = rem - A.tile_start[T.plane];
+    T.ip = ip;
     const int ty = ip / A.tiles_x[T.plane];
     T.h0 = ty * kTileH;
     T.w0 = (ip - ty * A.tiles_x[T.plane]) * kTileW;
@@ -76,8 +102,9 @@ __device__ __forceinline__ ConvTile conv_tile_decode(const ConvTcArgs& A, int t)
 // issuer run ahead across tile boundaries (shared-memory ring) and the accumulators are double-buffered in TMEM, so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 template <int NSPLIT>
-__global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_constant__ ConvTcMaps M, const ConvTcArgs A,
-                                                             const int total_tiles) {
+__global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_constant__ ConvTcMaps M,
+                                                             const __grid_constant__ RollTcMaps RM, const ConvTcArgs A,
+                                                             const FusedRoll F, const int total_tiles) {
     using Cfg = ConvTcCfg<NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
@@ -87,6 +114,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    // epilogue statistics scratch (behind the 256-byte barrier block)
+    double* stat_fin = reinterpret_cast<double*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // [64*8]
+    float* stat_stage = reinterpret_cast<float*>(stat_fin + 64 * 8);                               // [128][33]
+    float* stat_colp = stat_stage + kBM * 33;                                                      // [4][2][32]
+    float* stat_tot = stat_colp + 4 * 2 * 32;                                                      // [2][64]
+    int* stat_flag = reinterpret_cast<int*>(stat_tot + 2 * kBN);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cblks = A.C / kBK;
@@ -249,30 +282,72 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             __syncwarp();
             ptx::tc_fence_after();
             const uint32_t lane_addr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(quarter * 32) << 16);
+            const bool do_stats = A.sink.partial != nullptr;
+            const int et = threadIdx.x - 64;              // 0..127 among the epilogue threads
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t v1[32], v2[32];
                 ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
                 if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
                 ptx::tmem_ld_wait();
-                if (valid) {
+                if (half == 1) {
+                    // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA issuer
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+                }
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float o[4];
+                for (int j = 0; j < 32; j += 4) {
+                    float o[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float acc = __uint_as_float(v1[j + q]);
-                            if (NSPLIT == 3) acc = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, acc);
-                            o[q] = acc + pre[half * 32 + j + q];
-                        }
-                        *reinterpret_cast<float4*>(outp + half * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    for (int q = 0; q < 4; ++q) {
+                        float acc = __uint_as_float(v1[j + q]);
+                        if (NSPLIT == 3) acc = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, acc);
+                        o[q] = acc + pre[half * 32 + j + q];
+                    }
+                    if (valid) *reinterpret_cast<float4*>(outp + half * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (do_stats) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) stat_stage[m * 33 + j + q] = valid ? o[q] : 0.f;
                     }
                 }
+                if (do_stats) {
+                    // per-channel (sum, sum-sq) of this tile's 128 pixels, fixed summation order
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    {
+                        const int cc = et & 31, qq = et >> 5;
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                        for (int p = 0; p < 32; ++p) {
+                            const float v = stat_stage[(qq * 32 + p) * 33 + cc];
+                            s1 += v;
+                            s2 = fmaf(v, v, s2);
+                        }
+                        stat_colp[(qq * 2 + 0) * 32 + cc] = s1;
+                        stat_colp[(qq * 2 + 1) * 32 + cc] = s2;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et < 64) {
+                        const int which = et >> 5, cc = et & 31;
+                        stat_tot[which * kBN + half * 32 + cc] = (stat_colp[(0 * 2 + which) * 32 + cc] + stat_colp[(1 * 2 + which) * 32 + cc]) +
+                                                                 (stat_colp[(2 * 2 + which) * 32 + cc] + stat_colp[(3 * 2 + which) * 32 + cc]);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
             }
-            // hand the accumulator stage back to the MMA issuer
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+            if (do_stats) {
+                const int cpg = A.Cout / kGroups, gpt = kBN / cpg, g0 = n0 / cpg;
+                if (et < 2 * gpt) {
+                    const int gl = et >> 1, which = et & 1;
+                    double acc = 0.0;
+                    for (int cc = gl * cpg; cc < (gl + 1) * cpg; ++cc) acc += static_cast<double>(stat_tot[which * kBN + cc]);
+                    A.sink.partial[((static_cast<size_t>(b) * 3 + plane) * A.sink_slots + T.ip) * (kGroups * 2) + (g0 + gl) * 2 + which] = acc;
+                }
+                const int tiles_p = A.tile_start[plane + 1] - A.tile_start[plane];
+                stats_finalize_tail(A.sink, b, plane, A.sink_slots, static_cast<unsigned int>(tiles_p * (A.Cout / kBN)),
+                                    static_cast<double>(rows) * cols * cpg, et, 128,
+                                    [] { asm volatile("bar.sync 1, 128;" ::: "memory"); }, stat_fin, stat_flag);
+            }
         }
     }
     ptx::tc_fence_before();
@@ -291,17 +366,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
 // N tile = 64 of the 4*Cout class-summed output columns.  fp16 (hi, lo) means come from k_gn_silu's tail.
 // grid (sum over the 6 sources of ceil(L/128), 4*Cout/64, B)
 // =====================================================================================
-struct RollTcMaps {
-    CUtensorMap a[6];   // means of source s: (C, L, 1, B, 2) fp16
-    CUtensorMap w[6];   // class-summed 1-D weights: (3C, 4*Cout, 2) fp16, K = along*C + c
-};
-struct RollTcArgs {
-    int L[6], ncls[6];
-    float* T[6];        // [B][4][L][Cout]
-    int tile_start[7];
-    int C, Cout;
-};
-
 template <int NSPLIT>
 __global__ void __launch_bounds__(kConvThreads, 1) k_roll_tc(const __grid_constant__ RollTcMaps M, const RollTcArgs A) {
     using Cfg = ConvTcCfg<NSPLIT>;

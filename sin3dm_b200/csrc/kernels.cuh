@@ -7,42 +7,6 @@
 namespace s3d {
 
 // =====================================================================================
-// in_conv: per-plane 1x1 conv straight off the composed NCHW boundary tensor.
-// reference src/diffusion/unet_triplane.py:378 (TriplaneConv k=1, no rollout) + triplane_util.py:20-25
-// grid (ceil(max_px/32), 3, B), block 256
-// =====================================================================================
-__global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, TriDims d, int H, int W, int Dd, int Cin,
-                                                 int Cout, TriCF w, TriCF bias, TriF out) {
-    extern __shared__ float xs[];   // [Cin][32]
-    const int plane = blockIdx.y, b = blockIdx.z;
-    const int npx = d.rows[plane] * d.cols[plane];
-    const int px0 = blockIdx.x * 32;
-    if (px0 >= npx) return;
-    const int Hc = H + Dd, Wc = W + Dd;
-    const float* xb = x + static_cast<size_t>(b) * Cin * Hc * Wc;
-    for (int i = threadIdx.x; i < Cin * 32; i += blockDim.x) {
-        int c = i >> 5, p = i & 31, px = px0 + p;
-        float v = 0.f;
-        if (px < npx) {
-            int r = px / d.cols[plane], cc = px - r * d.cols[plane];
-            v = xb[static_cast<size_t>(c) * Hc * Wc + composed_offset(plane, r, cc, H, W, Wc)];
-        }
-        xs[i] = v;
-    }
-    __syncthreads();
-    const float* wp = w.p[plane];
-    const float* bp = bias.p[plane];
-    float* op = out.p[plane] + static_cast<size_t>(b) * npx * Cout;
-    for (int i = threadIdx.x; i < 32 * Cout; i += blockDim.x) {
-        int p = i / Cout, co = i - p * Cout, px = px0 + p;
-        if (px >= npx) continue;
-        float acc = bp[co];
-        for (int c = 0; c < Cin; ++c) acc = fmaf(wp[co * Cin + c], xs[c * 32 + p], acc);
-        op[static_cast<size_t>(px) * Cout + co] = acc;
-    }
-}
-
-// =====================================================================================
 // GroupNorm statistics -> per-channel affine coefficients.
 // reference src/diffusion/nn.py:17-19 (GroupNorm32 computes in fp32), unet_triplane.py:63-84, FiLM :285-297
 // Producers write one (sum, sum-sq) pair per group per CTA ("slot") in fp64; the LAST CTA of a (sample, plane)
@@ -184,6 +148,176 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink
                         [] { __syncthreads(); }, fin, &flag);
 }
 
+// -------------------------------------------------------------------------------------
+// Element-wise producers.  All of them use block (C/4, NY), give each CTA ("slot") a contiguous pixel range of one
+// plane of one sample, write the fp32 NHWC result and — when `S.partial` is set — also emit the GroupNorm partial sums
+// of what they wrote, so the consumer's statistics need no extra pass over the tensor.
+// grid (nslots, 3, B)
+// -------------------------------------------------------------------------------------
+#define S3D_PRODUCER_TAIL(S, s, q, npx, red)                                                                              \
+    if ((S).partial) {                                                                                                    \
+        __shared__ double fin_[64 * 8];                                                                                   \
+        __shared__ int flag_;                                                                                             \
+        stats_block_partial(S, s, q, b, plane, slot, nslots, red);                                                        \
+        stats_finalize_tail(S, b, plane, nslots, static_cast<unsigned int>(nslots),                                      \
+                            static_cast<double>(npx) * ((S).C / kGroups), static_cast<int>(threadIdx.y * blockDim.x + threadIdx.x), \
+                            static_cast<int>(blockDim.x * blockDim.y), [] { __syncthreads(); }, fin_, &flag_);            \
+    }
+
+__device__ __forceinline__ void acc_sq(float4& s, float4& q, const float4& v) {
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+}
+
+// in_conv: per-plane 1x1 conv straight off the composed NCHW boundary tensor.
+// reference src/diffusion/unet_triplane.py:378 (TriplaneConv k=1, no rollout) + triplane_util.py:20-25
+// smem: xs[Cin][64], wT[Cin][Cout], bias[Cout], red[(NY*2+2)*Cout]
+__global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, TriDims d, int H, int W, int Dd, int Cin,
+                                                 int Cout, TriCF w, TriCF bias, TriF out, StatsSink S, int nslots) {
+    extern __shared__ float smi[];
+    constexpr int PB = 64;
+    const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
+    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
+    const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
+    float* xs = smi;
+    float* wT = xs + Cin * PB;
+    float* bs = wT + Cin * Cout;
+    float* red = bs + Cout;
+    const int npx = d.rows[plane] * d.cols[plane];
+    const int ppc = (npx + nslots - 1) / nslots;
+    const int p0 = slot * ppc, p1 = min(npx, p0 + ppc);
+    const int Hc = H + Dd, Wc = W + Dd;
+    const float* xb = x + static_cast<size_t>(b) * Cin * Hc * Wc;
+    for (int i = tid; i < Cin * Cout; i += nthr) {
+        const int c = i / Cout, co = i - c * Cout;
+        wT[i] = w.p[plane][co * Cin + c];
+    }
+    for (int i = tid; i < Cout; i += nthr) bs[i] = bias.p[plane][i];
+    float* op = out.p[plane] + static_cast<size_t>(b) * npx * Cout;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (int pb = p0; pb < p1; pb += PB) {
+        const int nb = min(PB, p1 - pb);
+        __syncthreads();
+        for (int i = tid; i < Cin * PB; i += nthr) {
+            const int c = i / PB, p = i - c * PB;
+            float v = 0.f;
+            if (p < nb) {
+                const int px = pb + p, r = px / d.cols[plane], cc = px - r * d.cols[plane];
+                v = __ldg(xb + static_cast<size_t>(c) * Hc * Wc + composed_offset(plane, r, cc, H, W, Wc));
+            }
+            xs[i] = v;
+        }
+        __syncthreads();
+        const float4 b4 = *reinterpret_cast<const float4*>(bs + tx * 4);
+        for (int p = ty; p < nb; p += NY) {
+            float4 a = b4;
+            for (int c = 0; c < Cin; ++c) {
+                const float xv = xs[c * PB + p];
+                const float4 w4 = *reinterpret_cast<const float4*>(wT + c * Cout + tx * 4);
+                a.x = fmaf(xv, w4.x, a.x); a.y = fmaf(xv, w4.y, a.y); a.z = fmaf(xv, w4.z, a.z); a.w = fmaf(xv, w4.w, a.w);
+            }
+            *reinterpret_cast<float4*>(op + static_cast<size_t>(pb + p) * Cout + tx * 4) = a;
+            acc_sq(s, q, a);
+        }
+    }
+    __syncthreads();
+    S3D_PRODUCER_TAIL(S, s, q, npx, red)
+}
+
+// 2x2 average pool, stride 2, floor on odd sizes.  reference unet_triplane.py:127-145.  smem: red[(NY*2+2)*C]
+__global__ void __launch_bounds__(256) k_avgpool2(TriCF x, TriDims din, TriDims dout, int C, TriF out, StatsSink S, int nslots) {
+    extern __shared__ float smi[];
+    const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
+    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
+    const int orows = dout.rows[plane], ocols = dout.cols[plane], icols = din.cols[plane];
+    const int npx = orows * ocols, c4 = C / 4;
+    const int ppc = (npx + nslots - 1) / nslots;
+    const int p0 = slot * ppc, p1 = min(npx, p0 + ppc);
+    const float4* ip = reinterpret_cast<const float4*>(x.p[plane] + static_cast<size_t>(b) * din.rows[plane] * icols * C);
+    float4* op = reinterpret_cast<float4*>(out.p[plane] + static_cast<size_t>(b) * npx * C);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (int px = p0 + ty; px < p1; px += NY) {
+        const int r = px / ocols, c = px - r * ocols;
+        const float4* base = ip + (static_cast<size_t>(2 * r) * icols + 2 * c) * c4 + tx;
+        const float4 a = __ldg(base), b4 = __ldg(base + c4), c0 = __ldg(base + static_cast<size_t>(icols) * c4),
+                     d4 = __ldg(base + static_cast<size_t>(icols + 1) * c4);
+        float4 o;
+        o.x = (a.x + b4.x + c0.x + d4.x) * 0.25f;
+        o.y = (a.y + b4.y + c0.y + d4.y) * 0.25f;
+        o.z = (a.z + b4.z + c0.z + d4.z) * 0.25f;
+        o.w = (a.w + b4.w + c0.w + d4.w) * 0.25f;
+        op[static_cast<size_t>(px) * c4 + tx] = o;
+        acc_sq(s, q, o);
+    }
+    S3D_PRODUCER_TAIL(S, s, q, npx, smi)
+}
+
+// Bilinear x2 upsample (align_corners=False) [+ bilinear resize to the skip's size when they differ]
+// + channel concat with the skip.  reference unet_triplane.py:106-124, 494-503.  out [B][rows][cols][Cu+Cs]
+__device__ __forceinline__ void bilin_src(int dst, int in_size, float scale, int& i0, int& i1, float& l1) {
+    // ATen area_pixel_compute_source_index(align_corners=false): scale*(dst+0.5)-0.5 clamped at 0
+    float s = fmaxf(scale * (static_cast<float>(dst) + 0.5f) - 0.5f, 0.f);
+    i0 = min(static_cast<int>(s), in_size - 1);
+    i1 = min(i0 + 1, in_size - 1);
+    l1 = s - static_cast<float>(i0);
+}
+
+__global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, TriCF skip, int Cs, TriDims dout, TriF out,
+                                               int do_up, StatsSink S, int nslots) {
+    extern __shared__ float smi[];
+    const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
+    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
+    const int orows = dout.rows[plane], ocols = dout.cols[plane];
+    const int lrows = dlow.rows[plane], lcols = dlow.cols[plane];
+    const int Ct = Cu + Cs, c4 = Ct / 4, u4 = Cu / 4;
+    const int npx = orows * ocols;
+    const int ppc = (npx + nslots - 1) / nslots;
+    const int p0 = slot * ppc, p1 = min(npx, p0 + ppc);
+    const float4* sp = Cs ? reinterpret_cast<const float4*>(skip.p[plane] + static_cast<size_t>(b) * npx * Cs) : nullptr;
+    const float4* lp = reinterpret_cast<const float4*>(low.p[plane] + static_cast<size_t>(b) * lrows * lcols * Cu);
+    float4* op = reinterpret_cast<float4*>(out.p[plane] + static_cast<size_t>(b) * npx * Ct);
+    const int urows = do_up ? 2 * lrows : lrows, ucols = do_up ? 2 * lcols : lcols;
+    const bool resize = urows != orows || ucols != ocols;
+    auto at = [&](int rr, int cc) { return __ldg(lp + (static_cast<size_t>(rr) * lcols + cc) * u4 + tx); };
+    auto lerp4 = [](const float4& a, const float4& bb, const float4& cc2, const float4& dd, float lr, float lc) {
+        const float w00 = (1.f - lr) * (1.f - lc), w01 = (1.f - lr) * lc, w10 = lr * (1.f - lc), w11 = lr * lc;
+        float4 t;
+        t.x = w00 * a.x + w01 * bb.x + w10 * cc2.x + w11 * dd.x;
+        t.y = w00 * a.y + w01 * bb.y + w10 * cc2.y + w11 * dd.y;
+        t.z = w00 * a.z + w01 * bb.z + w10 * cc2.z + w11 * dd.z;
+        t.w = w00 * a.w + w01 * bb.w + w10 * cc2.w + w11 * dd.w;
+        return t;
+    };
+    // value of the (virtual) x2-upsampled map at (ur, uc)
+    auto up_at = [&](int ur, int uc) {
+        if (!do_up) return at(ur, uc);
+        int r0, r1, c0, c1;
+        float lr, lc;
+        bilin_src(ur, lrows, 0.5f, r0, r1, lr);
+        bilin_src(uc, lcols, 0.5f, c0, c1, lc);
+        return lerp4(at(r0, c0), at(r0, c1), at(r1, c0), at(r1, c1), lr, lc);
+    };
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (int px = p0 + ty; px < p1; px += NY) {
+        const int r = px / ocols, c = px - r * ocols;
+        float4 o;
+        if (tx >= u4) {
+            o = __ldg(sp + static_cast<size_t>(px) * (Cs / 4) + (tx - u4));
+        } else if (!resize) {
+            o = up_at(r, c);
+        } else {
+            int r0, r1, c0, c1;
+            float lr, lc;
+            bilin_src(r, urows, static_cast<float>(urows) / static_cast<float>(orows), r0, r1, lr);
+            bilin_src(c, ucols, static_cast<float>(ucols) / static_cast<float>(ocols), c0, c1, lc);
+            o = lerp4(up_at(r0, c0), up_at(r0, c1), up_at(r1, c0), up_at(r1, c1), lr, lc);
+        }
+        op[static_cast<size_t>(px) * c4 + tx] = o;
+        acc_sq(s, q, o);
+    }
+    S3D_PRODUCER_TAIL(S, s, q, npx, smi)
+}
+
 // =====================================================================================
 // Fused GroupNorm-apply (+FiLM) + SiLU -> fp16 (hi, lo) conv operand, plus the rollout axis means.
 // reference unet_triplane.py:63-95 (norm, SiLU), :285-297 (FiLM), :37-46 (axis means)
@@ -232,7 +366,7 @@ __device__ __forceinline__ void means_finalize(unsigned long long* sp, __half* m
     }
 }
 
-__global__ void __launch_bounds__(256, 3) k_gn_silu(GnSiluArgs A, int B) {
+__global__ void __launch_bounds__(256, 4) k_gn_silu(GnSiluArgs A, int B) {
     extern __shared__ float red[];   // [ny][4][C]
     __shared__ int last_row, last_col;
     const int plane = blockIdx.y, b = blockIdx.z;
@@ -301,14 +435,17 @@ __global__ void __launch_bounds__(256, 3) k_gn_silu(GnSiluArgs A, int B) {
     // ---- whoever completes this row strip / this column tile converts it to fp16 means and re-zeroes it
     __threadfence();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 || tid == 32) {        // two lanes of different warps: the two round trips overlap
         unsigned int* tk = A.ticket + static_cast<size_t>(b) * A.total_tickets + A.tick_off[plane];
-        const unsigned int pr = atomicAdd(tk + strip, 1u);
-        const unsigned int pc = atomicAdd(tk + strips + ct, 1u);
-        last_row = pr == static_cast<unsigned int>(ctiles - 1);
-        last_col = pc == static_cast<unsigned int>(strips - 1);
-        if (last_row) tk[strip] = 0u;
-        if (last_col) tk[strips + ct] = 0u;
+        if (tid == 0) {
+            const unsigned int pr = atomicAdd(tk + strip, 1u);
+            last_row = pr == static_cast<unsigned int>(ctiles - 1);
+            if (last_row) tk[strip] = 0u;
+        } else {
+            const unsigned int pc = atomicAdd(tk + strips + ct, 1u);
+            last_col = pc == static_cast<unsigned int>(strips - 1);
+            if (last_col) tk[strips + ct] = 0u;
+        }
     }
     __syncthreads();
     if (!last_row && !last_col) return;
@@ -467,93 +604,6 @@ __global__ void __launch_bounds__(256) k_conv_ffma(ConvFfmaArgs A, int B) {
         if (A.e.resid.p[plane]) acc += A.e.resid.p[plane][oo];
         A.e.out.p[plane][oo] = acc;
     }
-}
-
-// =====================================================================================
-// 2x2 average pool, stride 2, floor on odd sizes.  reference unet_triplane.py:127-145
-// grid (ceil(max_out_px*C/4 / 256), 3, B)
-// =====================================================================================
-__global__ void __launch_bounds__(256) k_avgpool2(TriCF x, TriDims din, TriDims dout, int C, TriF out) {
-    const int plane = blockIdx.y, b = blockIdx.z;
-    const int orows = dout.rows[plane], ocols = dout.cols[plane], icols = din.cols[plane];
-    const int c4 = C / 4;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= orows * ocols * c4) return;
-    const int v = i % c4, px = i / c4, r = px / ocols, c = px - r * ocols;
-    const float4* ip = reinterpret_cast<const float4*>(x.p[plane] + static_cast<size_t>(b) * din.rows[plane] * icols * C);
-    auto at = [&](int rr, int cc) { return __ldg(ip + (static_cast<size_t>(rr) * icols + cc) * c4 + v); };
-    float4 a = at(2 * r, 2 * c), b4 = at(2 * r, 2 * c + 1), c0 = at(2 * r + 1, 2 * c), d4 = at(2 * r + 1, 2 * c + 1);
-    float4 o;
-    o.x = (a.x + b4.x + c0.x + d4.x) * 0.25f;
-    o.y = (a.y + b4.y + c0.y + d4.y) * 0.25f;
-    o.z = (a.z + b4.z + c0.z + d4.z) * 0.25f;
-    o.w = (a.w + b4.w + c0.w + d4.w) * 0.25f;
-    reinterpret_cast<float4*>(out.p[plane] + static_cast<size_t>(b) * orows * ocols * C)[static_cast<size_t>(px) * c4 + v] = o;
-}
-
-// =====================================================================================
-// Bilinear x2 upsample (align_corners=False) [+ bilinear resize to the skip's size when they differ]
-// + channel concat with the skip.  reference unet_triplane.py:106-124, 494-503
-// out [B][rows][cols][Cu+Cs];  grid (ceil(max_px*(Cu+Cs)/4 / 256), 3, B)
-// =====================================================================================
-__device__ __forceinline__ void bilin_src(int dst, int in_size, float scale, int& i0, int& i1, float& l1) {
-    // ATen area_pixel_compute_source_index(align_corners=false): scale*(dst+0.5)-0.5 clamped at 0
-    float s = fmaxf(scale * (static_cast<float>(dst) + 0.5f) - 0.5f, 0.f);
-    i0 = min(static_cast<int>(s), in_size - 1);
-    i1 = min(i0 + 1, in_size - 1);
-    l1 = s - static_cast<float>(i0);
-}
-
-__global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, TriCF skip, int Cs, TriDims dout,
-                                               TriF out, int do_up) {
-    const int plane = blockIdx.y, b = blockIdx.z;
-    const int orows = dout.rows[plane], ocols = dout.cols[plane];
-    const int lrows = dlow.rows[plane], lcols = dlow.cols[plane];
-    const int Ct = Cu + Cs, c4 = Ct / 4;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= orows * ocols * c4) return;
-    const int v = i % c4, px = i / c4, r = px / ocols, c = px - r * ocols;
-    float4 o;
-    if (v * 4 >= Cu) {
-        const float4* sp = reinterpret_cast<const float4*>(skip.p[plane] + static_cast<size_t>(b) * orows * ocols * Cs);
-        o = __ldg(sp + static_cast<size_t>(px) * (Cs / 4) + (v - Cu / 4));
-    } else {
-        const float4* lp = reinterpret_cast<const float4*>(low.p[plane] + static_cast<size_t>(b) * lrows * lcols * Cu);
-        const int u4 = Cu / 4;
-        auto at = [&](int rr, int cc) { return __ldg(lp + (static_cast<size_t>(rr) * lcols + cc) * u4 + v); };
-        const int urows = do_up ? 2 * lrows : lrows, ucols = do_up ? 2 * lcols : lcols;
-        // value of the (virtual) x2-upsampled map at (ur, uc)
-        auto up_at = [&](int ur, int uc) {
-            if (!do_up) return at(ur, uc);
-            int r0, r1, c0, c1;
-            float lr, lc;
-            bilin_src(ur, lrows, 0.5f, r0, r1, lr);
-            bilin_src(uc, lcols, 0.5f, c0, c1, lc);
-            float4 a = at(r0, c0), bb = at(r0, c1), cc2 = at(r1, c0), dd = at(r1, c1);
-            float w00 = (1.f - lr) * (1.f - lc), w01 = (1.f - lr) * lc, w10 = lr * (1.f - lc), w11 = lr * lc;
-            float4 t;
-            t.x = w00 * a.x + w01 * bb.x + w10 * cc2.x + w11 * dd.x;
-            t.y = w00 * a.y + w01 * bb.y + w10 * cc2.y + w11 * dd.y;
-            t.z = w00 * a.z + w01 * bb.z + w10 * cc2.z + w11 * dd.z;
-            t.w = w00 * a.w + w01 * bb.w + w10 * cc2.w + w11 * dd.w;
-            return t;
-        };
-        if (urows == orows && ucols == ocols) {
-            o = up_at(r, c);
-        } else {
-            int r0, r1, c0, c1;
-            float lr, lc;
-            bilin_src(r, urows, static_cast<float>(urows) / static_cast<float>(orows), r0, r1, lr);
-            bilin_src(c, ucols, static_cast<float>(ucols) / static_cast<float>(ocols), c0, c1, lc);
-            float4 a = up_at(r0, c0), bb = up_at(r0, c1), cc2 = up_at(r1, c0), dd = up_at(r1, c1);
-            float w00 = (1.f - lr) * (1.f - lc), w01 = (1.f - lr) * lc, w10 = lr * (1.f - lc), w11 = lr * lc;
-            o.x = w00 * a.x + w01 * bb.x + w10 * cc2.x + w11 * dd.x;
-            o.y = w00 * a.y + w01 * bb.y + w10 * cc2.y + w11 * dd.y;
-            o.z = w00 * a.z + w01 * bb.z + w10 * cc2.z + w11 * dd.z;
-            o.w = w00 * a.w + w01 * bb.w + w10 * cc2.w + w11 * dd.w;
-        }
-    }
-    reinterpret_cast<float4*>(out.p[plane] + static_cast<size_t>(b) * orows * ocols * Ct)[static_cast<size_t>(px) * c4 + v] = o;
 }
 
 // =====================================================================================

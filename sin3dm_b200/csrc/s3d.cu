@@ -458,15 +458,25 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_out_head, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_in_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaDeviceSynchronize());
     u->finalized = true;
 }
 
 // ------------------------------------------------------------------------------------ launch plan
+// GroupNorm statistics attached to a tensor by its producer kernel.  The buffers exist from the start; the consumer
+// arms the box with its norm parameters (attach_norm) before the plan runs, and an un-armed box is skipped at launch.
+struct SinkBox {
+    StatsSink s{};
+    int nslots = 0;
+    bool armed = false;
+    bool use_film = false;
+};
 struct ActF {
     TriF p;
     int C = 0;
     int level = 0;
+    std::shared_ptr<SinkBox> sink;   // null: producer cannot emit statistics -> stand-alone k_gn_stats
 };
 struct Act16 {
     TriH p;
@@ -560,7 +570,44 @@ struct PlanBuilder {
         S.C = C;
         return S;
     }
+    std::shared_ptr<SinkBox> make_box(int C, int nslots) {
+        auto bx = std::make_shared<SinkBox>();
+        bx->nslots = nslots;
+        StatsSink& S = bx->s;
+        S.partial = dev_alloc<double>(P->allocs, static_cast<size_t>(B) * 3 * nslots * kGroups * 2);
+        CUDA_TRY(cudaMemset(S.partial, 0, sizeof(double) * static_cast<size_t>(B) * 3 * nslots * kGroups * 2));
+        S.ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3);
+        CUDA_TRY(cudaMemset(S.ticket, 0, sizeof(unsigned int) * B * 3));
+        S.coef = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 3 * C * 2);
+        S.film_dim = u->film_dim;
+        S.film_off = -1;
+        S.C = C;
+        return bx;
+    }
+    // sink as seen by a producer launch: disabled unless a consumer armed it
+    static StatsSink live_sink(const std::shared_ptr<SinkBox>& bx, const Plan* Pp) {
+        StatsSink S{};
+        if (bx && bx->armed) {
+            S = bx->s;
+            if (bx->use_film) {
+                S.film = Pp->film;
+                S.film_row = Pp->film_row;
+            }
+        }
+        return S;
+    }
+    // coefficients of `n` (+FiLM at film_off) applied to x: fused into x's producer when it supports it
     float* stats(const ActF& x, const DevNorm& n, int film_off) {
+        if (x.sink) {
+            SinkBox& bx = *x.sink;
+            S3D_CHECK(!bx.armed, "tensor normalised twice");
+            bx.s.gamma = cf3(n.gamma);
+            bx.s.beta = cf3(n.beta);
+            bx.s.film_off = film_off;
+            bx.use_film = film_off >= 0;
+            bx.armed = true;
+            return bx.s.coef;
+        }
         const int level = x.level, C = x.C;
         S3D_CHECK(C % kGroups == 0 && C % 4 == 0 && C / 4 <= 128, "unsupported channel count for GroupNorm32");
         const int nslots = std::max(1, std::min(128, max_px(level) / 48));
@@ -715,7 +762,7 @@ struct PlanBuilder {
 
     // ---- 3x3 conv (+ fused 1x1 skip)
     void conv(const Act16& a, int level, const DevConv3& cv, const TBuf* T, const Act16* x16, const ActF* resid, int emb_off,
-              const ActF& out) {
+              ActF& out) {
         const TriDims d = dims[level];
         ConvEpi e{};
         e.bias = cf3(cv.bias);
@@ -790,8 +837,18 @@ struct PlanBuilder {
         const int nsplit = u->cfg.precision == 1 ? 1 : 3;
         const int ntile_n = cv.Cout / kBN;
         const int num_sms = u->num_sms;
+        // the epilogue can emit the output's GroupNorm partials when a 64-channel N tile holds whole groups
+        std::shared_ptr<SinkBox> box;
+        if (cv.Cout % kGroups == 0 && kBN % (cv.Cout / kGroups) == 0) {
+            int max_tiles = 0;
+            for (int p = 0; p < 3; ++p) max_tiles = std::max(max_tiles, A.tile_start[p + 1] - A.tile_start[p]);
+            box = make_box(cv.Cout, max_tiles);
+            out.sink = box;
+            A.sink_slots = max_tiles;
+        }
         add_op("k_conv_tc", conv_flops(level, cv), [=](cudaStream_t s) {
             ConvTcArgs Al = A;
+            Al.sink = live_sink(box, Pp);
             if (use_emb) {
                 Al.e.embadd = Pp->film;
                 Al.e.film_row = Pp->film_row;
@@ -840,10 +897,15 @@ struct PlanBuilder {
         const int C = x.C, Bv = B;
         TriCF xc = cf(x.p);
         TriF op = o.p;
-        const int n = max_px(x.level + 1) * (C / 4);
+        const int nslots = std::max(1, std::min(128, max_px(x.level + 1) / 16));
+        auto box = make_box(C, nslots);
+        o.sink = box;
+        Plan* Pp = P;
+        S3D_CHECK(C / 4 <= 256, "channel count too large for k_avgpool2");
         add_op("k_avgpool2", 0.0, [=](cudaStream_t s) {
-            dim3 grid((n + 255) / 256, 3, Bv);
-            k_avgpool2<<<grid, 256, 0, s>>>(xc, di, dd, C, op);
+            const int ny = std::max(1, 256 / (C / 4));
+            dim3 grid(nslots, 3, Bv), block(C / 4, ny);
+            k_avgpool2<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, di, dd, C, op, live_sink(box, Pp), nslots);
             LAUNCH_CHECK("k_avgpool2");
         });
         return o;
@@ -857,11 +919,17 @@ struct PlanBuilder {
         TriCF lc = cf(low.p), sc{};
         if (skip) sc = cf(skip->p);
         TriF op = o.p;
-        const int Cu = low.C, Bv = B;
-        const int n = max_px(out_level) * ((Cu + Cs) / 4);
+        const int Cu = low.C, Bv = B, Ct = Cu + Cs;
+        S3D_CHECK(Ct / 4 <= 256 && Cu % 4 == 0 && Cs % 4 == 0, "channel counts unsupported by k_upcat");
+        const int nslots = std::max(1, std::min(128, max_px(out_level) / 32));
+        auto box = make_box(Ct, nslots);
+        o.sink = box;
+        Plan* Pp = P;
         add_op("k_upcat", 0.0, [=](cudaStream_t s) {
-            dim3 grid((n + 255) / 256, 3, Bv);
-            k_upcat<<<grid, 256, 0, s>>>(lc, dl, Cu, sc, Cs, dout, op, do_up ? 1 : 0);
+            const int ny = std::max(1, 256 / (Ct / 4));
+            dim3 grid(nslots, 3, Bv), block(Ct / 4, ny);
+            k_upcat<<<grid, block, sizeof(float) * (ny * 2 + 2) * Ct, s>>>(lc, dl, Cu, sc, Cs, dout, op, do_up ? 1 : 0,
+                                                                           live_sink(box, Pp), nslots);
             LAUNCH_CHECK("k_upcat");
         });
         return o;
@@ -895,12 +963,20 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     ActF h = pb.allocF(0, c0, "in_conv");
     {
         const TriDims d0 = pb.dims[0];
-        const int Cin = c.in_channels, mp = pb.max_px(0);
+        const int Cin = c.in_channels;
         TriCF w = PlanBuilder::cf3(u->in_w), bb = PlanBuilder::cf3(u->in_b);
         TriF op = h.p;
+        const int nslots = std::max(1, std::min(128, pb.max_px(0) / 64));
+        auto box = pb.make_box(c0, nslots);
+        h.sink = box;
+        S3D_CHECK(c0 / 4 <= 256, "channel count too large for k_in_conv");
+        const int ny = std::max(1, 256 / (c0 / 4));
+        const size_t smem = sizeof(float) * (static_cast<size_t>(Cin) * 64 + static_cast<size_t>(Cin) * c0 + c0 +
+                                             static_cast<size_t>(ny * 2 + 2) * c0);
+        S3D_CHECK(smem <= 100 * 1024, "k_in_conv shared memory");
         pb.add_op("k_in_conv", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * Cin * c0, [=](cudaStream_t s) {
-            dim3 grid((mp + 31) / 32, 3, B);
-            k_in_conv<<<grid, 256, sizeof(float) * Cin * 32, s>>>(P->x, d0, H, W, D, Cin, c0, w, bb, op);
+            dim3 grid(nslots, 3, B), block(c0 / 4, ny);
+            k_in_conv<<<grid, block, smem, s>>>(P->x, d0, H, W, D, Cin, c0, w, bb, op, PlanBuilder::live_sink(box, P), nslots);
             LAUNCH_CHECK("k_in_conv");
         });
     }
