@@ -98,6 +98,26 @@ __device__ __forceinline__ ConvTile conv_tile_decode(const ConvTcArgs& A, int t)
     return T;
 }
 
+struct RollTile {
+    int src, p0, n0, b;
+};
+__device__ __forceinline__ RollTile roll_tile_decode(const FusedRoll& F, int t) {
+    const int mt_total = F.R.tile_start[6];
+    RollTile T;
+    T.b = t / (mt_total * F.ntn);
+    int rem = t - T.b * mt_total * F.ntn;
+    const int nt = rem / mt_total;
+    rem -= nt * mt_total;
+    T.n0 = nt * kBN;
+    int src = 0;
+#pragma unroll
+    for (int k = 1; k < 6; ++k)
+        if (rem >= F.R.tile_start[k]) src = k;
+    T.src = src;
+    T.p0 = (rem - F.R.tile_start[src]) * kBM;
+    return T;
+}
+
 // Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer and the MMA
 // issuer run ahead across tile boundaries (shared-memory ring) and the accumulators are double-buffered in TMEM, so the
 // epilogue of tile i overlaps the main loop of tile i+1.
@@ -133,6 +153,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             ptx::prefetch_tmap(&M.w[p]);
             if (A.Cs) ptx::prefetch_tmap(&M.x[p]);
         }
+        if (F.n_roll) {
+#pragma unroll
+            for (int p = 0; p < 6; ++p) {
+                ptx::prefetch_tmap(&RM.a[p]);
+                ptx::prefetch_tmap(&RM.w[p]);
+            }
+        }
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -159,7 +186,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         if (lane == 0) {
             int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const ConvTile T = conv_tile_decode(A, t);
+                if (t < F.n_roll) {
+                    const RollTile T = roll_tile_decode(F, t);
+                    for (int i = 0; i < 3 * cblks; ++i, ++it) {
+                        const int s = it % Cfg::kStages;
+                        const uint32_t ph = (it / Cfg::kStages) & 1;
+                        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                        uint8_t* st = smem + s * Cfg::kStageBytes;
+                        ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                        const int al = i / cblks, cb = i - al * cblks;
+                        ptx::tma_load_5d(st, &RM.a[T.src], &full_bar[s], cb * kBK, T.p0 + al - 1, 0, T.b, 0);
+                        ptx::tma_load_3d(st + kABytes, &RM.w[T.src], &full_bar[s], i * kBK, T.n0, 0);
+                        if (NSPLIT == 3) {
+                            ptx::tma_load_5d(st + kABytes + kBBytes, &RM.a[T.src], &full_bar[s], cb * kBK, T.p0 + al - 1, 0, T.b, 1);
+                            ptx::tma_load_3d(st + 2 * kABytes + kBBytes, &RM.w[T.src], &full_bar[s], i * kBK, T.n0, 1);
+                        }
+                    }
+                    continue;
+                }
+                const ConvTile T = conv_tile_decode(A, t - F.n_roll);
                 for (int i = 0; i < nk; ++i, ++it) {
                     const int s = it % Cfg::kStages;
                     const uint32_t ph = (it / Cfg::kStages) & 1;
@@ -197,7 +242,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1);        // epilogue has drained this accumulator stage
                 ptx::tc_fence_after();
                 const uint32_t d1 = tmem_base + as * Cfg::kAccCols, d2 = d1 + kBN;
-                for (int i = 0; i < nk; ++i, ++it) {
+                const int nk_t = t < F.n_roll ? 3 * cblks : nk;
+                for (int i = 0; i < nk_t; ++i, ++it) {
                     const int s = it % Cfg::kStages;
                     const uint32_t ph = (it / Cfg::kStages) & 1;
                     ptx::mbar_wait(&full_bar[s], ph);
@@ -227,8 +273,50 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int m = quarter * 32 + lane;
         int lt = 0;
+        const int et = threadIdx.x - 64;                  // 0..127 among the epilogue threads
+        bool roll_ready = F.n_roll == 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-            const ConvTile T = conv_tile_decode(A, t);
+            if (t < F.n_roll) {
+                // ---------- rollout 1-D GEMM tile: T[b][cls][pos][co] = accumulator ----------
+                const RollTile T = roll_tile_decode(F, t);
+                const int pos = T.p0 + m, L = F.R.L[T.src];
+                const int cls = T.n0 / A.Cout, co0 = T.n0 - cls * A.Cout;
+                float* __restrict__ outp = F.R.T[T.src] + ((static_cast<size_t>(T.b) * 4 + cls) * L + pos) * A.Cout + co0;
+                const int as = lt & 1;
+                ptx::mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
+                __syncwarp();
+                ptx::tc_fence_after();
+                const uint32_t lane_addr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v1[32], v2[32];
+                    ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
+                    if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
+                    ptx::tmem_ld_wait();
+                    if (half == 1) {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+                    }
+                    if (pos < L) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float o[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                o[q] = __uint_as_float(v1[j + q]);
+                                if (NSPLIT == 3) o[q] = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, o[q]);
+                            }
+                            __stcg(reinterpret_cast<float4*>(outp + half * 32 + j), make_float4(o[0], o[1], o[2], o[3]));
+                        }
+                    }
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) atomicAdd(&F.counters[0], 1u);
+                continue;
+            }
+            const ConvTile T = conv_tile_decode(A, t - F.n_roll);
             const int plane = T.plane, n0 = T.n0, b = T.b;
             const int r = T.h0 + (m >> 4), c = T.w0 + (m & 15);
             const int rows = A.d.rows[plane], cols = A.d.cols[plane];
@@ -253,6 +341,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w;
                     }
                 }
+                if (A.e.Trow.p[plane] && !roll_ready) {
+                    // the rollout terms are produced by this very launch (roll tiles): wait until all of them are written
+                    if (lane == 0) {
+                        const volatile unsigned int* cnt = F.counters;
+                        while (*cnt < static_cast<unsigned int>(F.n_roll)) {
+                        }
+                    }
+                    __syncwarp();
+                    __threadfence();
+                    roll_ready = true;
+                }
                 if (valid && A.e.Trow.p[plane]) {
                     const size_t bo = static_cast<size_t>(b) * 4;
                     const float4* tr = reinterpret_cast<const float4*>(
@@ -261,7 +360,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         A.e.Tcol.p[plane] + ((bo + edge_class(r, rows)) * cols + c) * A.Cout + n0);
 #pragma unroll
                     for (int j = 0; j < kBN / 4; ++j) {
-                        const float4 v = __ldg(tr + j), u = __ldg(tc + j);
+                        const float4 v = __ldcg(tr + j), u = __ldcg(tc + j);      // written by this launch: L2-coherent loads
                         pre[4 * j] += v.x + u.x; pre[4 * j + 1] += v.y + u.y; pre[4 * j + 2] += v.z + u.z;
                         pre[4 * j + 3] += v.w + u.w;
                     }
@@ -283,7 +382,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             ptx::tc_fence_after();
             const uint32_t lane_addr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(quarter * 32) << 16);
             const bool do_stats = A.sink.partial != nullptr;
-            const int et = threadIdx.x - 64;              // 0..127 among the epilogue threads
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t v1[32], v2[32];
@@ -356,10 +454,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         __syncwarp();
         ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
+    if (F.n_roll && threadIdx.x == 0) {
+        // the last CTA to leave re-arms the counters for the next launch
+        const unsigned int prev = atomicAdd(&F.counters[1], 1u);
+        if (prev == gridDim.x - 1) {
+            F.counters[0] = 0u;
+            F.counters[1] = 0u;
+        }
+    }
 }
 
 // =====================================================================================
-// Rollout 1-D terms on the tensor cores (replaces the SIMT k_roll1d on the product path).
+// Rollout 1-D terms on the tensor cores, stand-alone launch (S3D_FUSE_ROLL=0; the default fuses these tiles into k_conv_tc).
 //   T[b][cls][pos][co] = sum_{along, c} mean[pos+along-1][c] * wc[cls*Cout + co][along*C + c]
 // Same pipeline as k_conv_tc with a 1 x 128 "patch": M tile = 128 consecutive positions of one source's mean
 // vector (5-D TMA box {64 ch, 128, 1, 1, 1}; the +-1 tap shift and both ends are the TMA zero fill), 3 taps,

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -189,6 +190,7 @@ struct s3d_unet {
     std::unique_ptr<Plan> plan;
     int last_launches = 0;
     int num_sms = 148;
+    bool fuse_roll = true;   // S3D_FUSE_ROLL=0 launches the rollout 1-D GEMM separately
 };
 
 static int ch_of(const s3d_unet_config& c, int level) { return c.channel_mult[level] * c.model_channels; }
@@ -669,6 +671,9 @@ struct PlanBuilder {
 
     struct TBuf {
         TriF Trow, Tcol;
+        std::shared_ptr<RollTcMaps> roll_maps;   // set when the 1-D GEMM tiles are to be fused into the conv launch
+        RollTcArgs roll_args{};
+        int roll_mtiles = 0, roll_ntn = 0;
     };
     // ---- rollout 1-D terms (tensor-core GEMM; SIMT cross-check kernel when conv_impl == 1)
     TBuf roll1d(const Sums& S, int level, const DevConv3& cv) {
@@ -751,6 +756,13 @@ struct PlanBuilder {
         }
         A.tile_start[6] = total;
         const int nsplit = u->cfg.precision == 1 ? 1 : 3;
+        if (u->fuse_roll) {
+            T.roll_maps = maps;
+            T.roll_args = A;
+            T.roll_mtiles = total;
+            T.roll_ntn = ntn;
+            return T;
+        }
         add_op("k_roll_tc", 0.0, [=](cudaStream_t s) {
             dim3 grid(total, ntn, Bv);
             if (nsplit == 3) k_roll_tc<3><<<grid, kConvThreads, ConvTcCfg<3>::kSmemBytes, s>>>(*maps, A);
@@ -846,6 +858,17 @@ struct PlanBuilder {
             out.sink = box;
             A.sink_slots = max_tiles;
         }
+        FusedRoll F{};
+        auto rmaps = std::make_shared<RollTcMaps>();
+        memset(rmaps.get(), 0, sizeof(RollTcMaps));
+        if (T && T->roll_maps) {
+            rmaps = T->roll_maps;
+            F.R = T->roll_args;
+            F.ntn = T->roll_ntn;
+            F.n_roll = T->roll_mtiles * T->roll_ntn * B;
+            F.counters = dev_alloc<unsigned int>(P->allocs, 2);
+            CUDA_TRY(cudaMemset(F.counters, 0, 2 * sizeof(unsigned int)));
+        }
         add_op("k_conv_tc", conv_flops(level, cv), [=](cudaStream_t s) {
             ConvTcArgs Al = A;
             Al.sink = live_sink(box, Pp);
@@ -853,10 +876,10 @@ struct PlanBuilder {
                 Al.e.embadd = Pp->film;
                 Al.e.film_row = Pp->film_row;
             }
-            const int total_tiles = total * ntile_n * Bv;
+            const int total_tiles = total * ntile_n * Bv + F.n_roll;
             dim3 grid(std::min(total_tiles, num_sms));
-            if (nsplit == 3) k_conv_tc<3><<<grid, kConvThreads, ConvTcCfg<3>::kSmemBytes, s>>>(*maps, Al, total_tiles);
-            else k_conv_tc<1><<<grid, kConvThreads, ConvTcCfg<1>::kSmemBytes, s>>>(*maps, Al, total_tiles);
+            if (nsplit == 3) k_conv_tc<3><<<grid, kConvThreads, ConvTcCfg<3>::kSmemBytes, s>>>(*maps, *rmaps, Al, F, total_tiles);
+            else k_conv_tc<1><<<grid, kConvThreads, ConvTcCfg<1>::kSmemBytes, s>>>(*maps, *rmaps, Al, F, total_tiles);
             LAUNCH_CHECK("k_conv_tc");
         });
     }
@@ -1106,6 +1129,7 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     u->cfg = *cfg;
     u->device = device;
     u->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("S3D_FUSE_ROLL")) u->fuse_roll = atoi(e) != 0;
     build_structure(u.get());
     *out = u.release();
     API_END
