@@ -42,7 +42,6 @@ struct ConvTcArgs {
     int tile_start[4];   // prefix sum of tiles per plane
     ConvEpi e;
     StatsSink sink;      // GroupNorm partials of the output (sink.partial == nullptr: none); needs 64 % (Cout/32) == 0
-    int sink_slots;      // slot stride of sink.partial (>= tiles of the largest plane)
 };
 
 struct RollTcMaps {
@@ -439,12 +438,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     const int gl = et >> 1, which = et & 1;
                     double acc = 0.0;
                     for (int cc = gl * cpg; cc < (gl + 1) * cpg; ++cc) acc += static_cast<double>(stat_tot[which * kBN + cc]);
-                    A.sink.partial[((static_cast<size_t>(b) * 3 + plane) * A.sink_slots + T.ip) * (kGroups * 2) + (g0 + gl) * 2 + which] = acc;
+                    A.sink.partial[((static_cast<size_t>(b) * 3 + plane) * A.sink.nslots + T.ip) * (kGroups * 2) + (g0 + gl) * 2 + which] = acc;
                 }
                 const int tiles_p = A.tile_start[plane + 1] - A.tile_start[plane];
-                stats_finalize_tail(A.sink, b, plane, A.sink_slots, static_cast<unsigned int>(tiles_p * (A.Cout / kBN)),
-                                    static_cast<double>(rows) * cols * cpg, et, 128,
-                                    [] { asm volatile("bar.sync 1, 128;" ::: "memory"); }, stat_fin, stat_flag);
+                stats_group_tail(A.sink, b, plane, T.ip, tiles_p, A.Cout / kBN, et,
+                                 [] { asm volatile("bar.sync 1, 128;" ::: "memory"); }, stat_flag);
             }
         }
     }

@@ -14,60 +14,80 @@ namespace s3d {
 //     y = x * coef[c][0] + coef[c][1]   ==  GroupNorm(x) * gamma + beta   (optionally * (1 + scale) + shift)
 // so consumers need no statistics pass, no shared memory and no barrier before their first load.
 // =====================================================================================
-struct StatsSink {
-    double* partial;          // [B][3][nslots][32][2]
-    unsigned int* ticket;     // [B][3]
-    float* coef;              // [B][3][C][2]
+constexpr int kStatGroup = 8;      // slots per first-level group
+
+struct StatsSink {                 // producer side
+    double* partial;          // [B][3][nslots][64]   per-slot (sum, sum-sq) of the 32 groups
+    unsigned int* ticket;     // [B][3][nsg]          first-level tickets, nsg = ceil(nslots / 8)
+    double* part2;            // [B][3][nsg][64]      per-slot-group sums (what consumers read)
+    int nslots;               // slot stride of `partial`
+    int C;
+};
+struct StatsSrc {                  // consumer side
+    const double* part2;      // [B][3][nsg][64]
+    int nsg;
     TriCF gamma, beta;        // consumer norm parameters [C]
     const float* film;        // [rows][film_dim] or nullptr
     const int* film_row;
     int film_dim, film_off;   // scale at film_off, shift at film_off + C
-    int C;
 };
 
-// Called by all `nthr` threads (tid = 0..nthr-1, nthr >= 64) of a CTA after it has written its slot(s).
-// `expected` = number of CTAs contributing to this (sample, plane); `sync()` is a barrier over those nthr threads.
+// Two-level deterministic reduction.  A producer CTA calls this (all `nthr` >= 64 threads, after writing its slot):
+// the last contributor of a group of 8 slots adds them in slot order into part2.  `plane_slots` = slots this plane
+// really has, `per_slot` = CTAs contributing to one slot.  Consumers add the <= 16 group sums themselves
+// (stats_coef_prologue), so no single CTA ever walks the whole partial list.
 template <class Sync>
-__device__ __forceinline__ void stats_finalize_tail(const StatsSink& S, int b, int plane, int nslots, unsigned int expected,
-                                                    double n_per_group, int tid, int nthr, Sync sync, double* fin /*smem [64*8]*/,
-                                                    int* flag /*smem*/) {
+__device__ __forceinline__ void stats_group_tail(const StatsSink& S, int b, int plane, int slot, int plane_slots, int per_slot, int tid,
+                                                 Sync sync, int* flag /*smem*/) {
+    const int nsg = (S.nslots + kStatGroup - 1) / kStatGroup;
+    const int g1 = slot / kStatGroup;
+    const int in_group = min(kStatGroup, plane_slots - g1 * kStatGroup);
     __threadfence();
     sync();
     if (tid == 0) {
-        unsigned int prev = atomicAdd(&S.ticket[b * 3 + plane], 1u);
-        *flag = (prev == expected - 1u) ? 1 : 0;
+        unsigned int* tk = S.ticket + (static_cast<size_t>(b) * 3 + plane) * nsg + g1;
+        const unsigned int prev = atomicAdd(tk, 1u);
+        const int last = prev == static_cast<unsigned int>(in_group * per_slot - 1);
+        if (last) *tk = 0u;          // re-arm for the next launch
+        *flag = last;
     }
     sync();
     if (!*flag) return;
     __threadfence();
-    const double* pp = S.partial + (static_cast<size_t>(b) * 3 + plane) * nslots * kGroups * 2;
-    // 8 slices x 64 (group, sum|sumsq) entries; every entry walks its slots in a fixed order, 8 loads in flight
-    for (int i = tid; i < 64 * 8; i += nthr) {
-        const int slice = i >> 6, gw = i & 63;
+    if (tid < 64) {
+        const double* pp = S.partial + ((static_cast<size_t>(b) * 3 + plane) * S.nslots + g1 * kStatGroup) * 64 + tid;
+        double v[kStatGroup];
+#pragma unroll
+        for (int k = 0; k < kStatGroup; ++k) v[k] = k < in_group ? __ldcg(pp + k * 64) : 0.0;
         double acc = 0.0;
-        int sl = slice;
-        for (; sl + 56 < nslots; sl += 64) {
+#pragma unroll
+        for (int k = 0; k < kStatGroup; ++k) acc += v[k];
+        S.part2[((static_cast<size_t>(b) * 3 + plane) * nsg + g1) * 64 + tid] = acc;
+    }
+}
+
+// Consumer prologue: per-channel affine coefficients  y = x * coefA[c] + coefB[c]  ==  GroupNorm(x)*gamma+beta (optionally
+// FiLM'ed) from the group sums.  All threads of the CTA call it; fin: smem double[64]; coefA/coefB: smem float[C].
+__device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, int plane, int C, double n_per_group, int tid, int nthr,
+                                                    double* fin, float* coefA, float* coefB) {
+    if (tid < 64) {
+        const double* pp = S.part2 + (static_cast<size_t>(b) * 3 + plane) * S.nsg * 64 + tid;
+        double acc = 0.0;
+        int g = 0;
+        for (; g + 8 <= S.nsg; g += 8) {
             double v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __ldcg(pp + static_cast<size_t>(sl + 8 * k) * 64 + gw);
+            for (int k = 0; k < 8; ++k) v[k] = __ldcg(pp + (g + k) * 64);
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc += v[k];
         }
-        for (; sl < nslots; sl += 8) acc += __ldcg(pp + static_cast<size_t>(sl) * 64 + gw);
-        fin[slice * 64 + gw] = acc;
+        for (; g < S.nsg; ++g) acc += __ldcg(pp + g * 64);
+        fin[tid] = acc;
     }
-    sync();
-    if (tid < 64) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc += fin[k * 64 + tid];
-        fin[tid] = acc;          // slice 0 now holds the totals (tid < 64 only touches column tid)
-    }
-    sync();
-    const int C = S.C, cpg = C / kGroups;
+    __syncthreads();
+    const int cpg = C / kGroups;
     const float* film = nullptr;
     if (S.film) film = S.film + static_cast<size_t>(S.film_row ? S.film_row[b] : b) * S.film_dim + S.film_off;
-    float* co = S.coef + (static_cast<size_t>(b) * 3 + plane) * C * 2;
     for (int c = tid; c < C; c += nthr) {
         const int g = c / cpg;
         const double mean = fin[g * 2] / n_per_group;
@@ -81,10 +101,10 @@ __device__ __forceinline__ void stats_finalize_tail(const StatsSink& S, int b, i
             ga *= sc;
             be = fmaf(be, sc, sh);
         }
-        co[c * 2] = ga;
-        co[c * 2 + 1] = be;
+        coefA[c] = ga;
+        coefB[c] = be;
     }
-    if (tid == 0) S.ticket[b * 3 + plane] = 0u;   // re-arm for the next launch
+    __syncthreads();
 }
 
 // Block-wide reduction of per-thread (sum, sum-sq) float4 pairs laid out as block (C/4, NY) into this CTA's slot.
@@ -107,7 +127,7 @@ __device__ __forceinline__ void stats_block_partial(const StatsSink& S, float4 s
     }
     __syncthreads();
     const int cpg = C / kGroups;
-    double* part = S.partial + ((static_cast<size_t>(b) * 3 + plane) * nslots + slot) * kGroups * 2;
+    double* part = S.partial + ((static_cast<size_t>(b) * 3 + plane) * S.nslots + slot) * kGroups * 2;
     if (tid < 2 * kGroups) {
         const int g = tid >> 1, which = tid & 1;
         double acc = 0.0;
@@ -120,7 +140,6 @@ __device__ __forceinline__ void stats_block_partial(const StatsSink& S, float4 s
 // grid (nslots, 3, B), block (C/4, NY)
 __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink S, int nslots) {
     extern __shared__ float red[];   // [(NY*2 + 2) * C]
-    __shared__ double fin[64 * 8];
     __shared__ int flag;
     const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
     const int C = S.C, tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
@@ -143,9 +162,8 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink
         }
     }
     stats_block_partial(S, s, q, b, plane, slot, nslots, red);
-    const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
-    stats_finalize_tail(S, b, plane, nslots, static_cast<unsigned int>(nslots), static_cast<double>(npx) * (C / kGroups), tid, nthr,
-                        [] { __syncthreads(); }, fin, &flag);
+    const int tid = ty * blockDim.x + tx;
+    stats_group_tail(S, b, plane, slot, nslots, 1, tid, [] { __syncthreads(); }, &flag);
 }
 
 // -------------------------------------------------------------------------------------
@@ -156,12 +174,10 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink
 // -------------------------------------------------------------------------------------
 #define S3D_PRODUCER_TAIL(S, s, q, npx, red)                                                                              \
     if ((S).partial) {                                                                                                    \
-        __shared__ double fin_[64 * 8];                                                                                   \
         __shared__ int flag_;                                                                                             \
         stats_block_partial(S, s, q, b, plane, slot, nslots, red);                                                        \
-        stats_finalize_tail(S, b, plane, nslots, static_cast<unsigned int>(nslots),                                      \
-                            static_cast<double>(npx) * ((S).C / kGroups), static_cast<int>(threadIdx.y * blockDim.x + threadIdx.x), \
-                            static_cast<int>(blockDim.x * blockDim.y), [] { __syncthreads(); }, fin_, &flag_);            \
+        stats_group_tail(S, b, plane, slot, nslots, 1, static_cast<int>(threadIdx.y * blockDim.x + threadIdx.x),          \
+                         [] { __syncthreads(); }, &flag_);                                                                \
     }
 
 __device__ __forceinline__ void acc_sq(float4& s, float4& q, const float4& v) {
@@ -337,7 +353,7 @@ struct GnSiluArgs {
     TriCF x;          // fp32 [B][rows][cols][C]
     TriDims d;
     int C;
-    const float* coef;        // [B][3][C][2] from the statistics tail
+    StatsSrc st;              // group sums of x + this layer's norm parameters
     TriH a;                   // out [2][B][rows][cols][C]
     TriH x16;                 // optional raw copy of x as (hi, lo) for the 1x1 skip GEMM
     unsigned long long* sums; // [B][total_len][C] fixed point, zero between launches; nullptr when rollout is off
@@ -367,8 +383,9 @@ __device__ __forceinline__ void means_finalize(unsigned long long* sp, __half* m
 }
 
 __global__ void __launch_bounds__(256, 4) k_gn_silu(GnSiluArgs A, int B) {
-    extern __shared__ float red[];   // [ny][4][C]
+    extern __shared__ float gsm[];   // coefA[C], coefB[C], red[ny][4][C]
     __shared__ int last_row, last_col;
+    __shared__ double fin[64];
     const int plane = blockIdx.y, b = blockIdx.z;
     const int rows = A.d.rows[plane], cols = A.d.cols[plane], C = A.C;
     const int tx = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
@@ -380,31 +397,37 @@ __global__ void __launch_bounds__(256, 4) k_gn_silu(GnSiluArgs A, int B) {
     const int nr = min(kGsRows, rows - r0);
     const int c = ct * ny + ty;
     const bool cvalid = c < cols;
-    const float4* cf4 = reinterpret_cast<const float4*>(A.coef + (static_cast<size_t>(b) * 3 + plane) * C * 2) + tx * 2;
-    const float4 k0 = __ldg(cf4), k1 = __ldg(cf4 + 1);       // (A0,B0,A1,B1), (A2,B2,A3,B3)
+    float* coefA = gsm;
+    float* coefB = gsm + C;
+    float* red = gsm + 2 * C;
     const size_t plane_elems = static_cast<size_t>(rows) * cols * C;
     const size_t sample_off = static_cast<size_t>(b) * plane_elems;
     const size_t lo_off = static_cast<size_t>(B) * plane_elems;
     const float* xp = A.x.p[plane] + sample_off;
     __half* ap = A.a.p[plane] + sample_off;
     __half* xq = A.x16.p[plane] ? A.x16.p[plane] + sample_off : nullptr;
-    float4 y[kGsRows];
+    float4 y[kGsRows], v[kGsRows];
 #pragma unroll
-    for (int r = 0; r < kGsRows; ++r) y[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < kGsRows; ++r) y[r] = v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cvalid) {
-        float4 v[kGsRows];
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r)
             if (r < nr) v[r] = __ldg(reinterpret_cast<const float4*>(xp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4));
+    }
+    // the group sums arrive while the activation loads above are in flight
+    stats_coef_prologue(A.st, b, plane, C, static_cast<double>(rows) * cols * (C / kGroups), tid, nthr, fin, coefA, coefB);
+    const float4 ca = *reinterpret_cast<const float4*>(coefA + tx * 4);
+    const float4 cb = *reinterpret_cast<const float4*>(coefB + tx * 4);
+    if (cvalid) {
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r) {
             if (r < nr) {
                 const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
                 if (xq) store_split4(xq + off, xq + lo_off + off, v[r]);
-                y[r].x = silu_f(fmaf(v[r].x, k0.x, k0.y));
-                y[r].y = silu_f(fmaf(v[r].y, k0.z, k0.w));
-                y[r].z = silu_f(fmaf(v[r].z, k1.x, k1.y));
-                y[r].w = silu_f(fmaf(v[r].w, k1.z, k1.w));
+                y[r].x = silu_f(fmaf(v[r].x, ca.x, cb.x));
+                y[r].y = silu_f(fmaf(v[r].y, ca.y, cb.y));
+                y[r].z = silu_f(fmaf(v[r].z, ca.z, cb.z));
+                y[r].w = silu_f(fmaf(v[r].w, ca.w, cb.w));
                 store_split4(ap + off, ap + lo_off + off, y[r]);
             }
         }
@@ -611,8 +634,8 @@ __global__ void __launch_bounds__(256) k_conv_ffma(ConvFfmaArgs A, int B) {
 // blockIdx.y == 3 zero-fills the D x D corner.  reference unet_triplane.py:441-445, triplane_util.py:7-17
 // grid (ceil(max(max_px, D*D)/128), 4, B), block 128 (one thread per pixel)
 // =====================================================================================
-__global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int Cout, const float* __restrict__ coef,
-                                                  TriCF w, TriCF bias, float* __restrict__ out, int H, int W, int Dd) {
+__global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int Cout, StatsSrc st, TriCF w, TriCF bias,
+                                                  float* __restrict__ out, int H, int W, int Dd) {
     extern __shared__ float sm[];   // coefA[C], coefB[C], ws[Cout][C], bs[Cout]
     const int plane = blockIdx.y, b = blockIdx.z;
     const int Hc = H + Dd, Wc = W + Dd;
@@ -631,11 +654,8 @@ __global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int
     float* coefB = sm + C;
     float* ws = sm + 2 * C;
     float* bs = ws + Cout * C;
-    const float* cf = coef + (static_cast<size_t>(b) * 3 + plane) * C * 2;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        coefA[c] = cf[c * 2];
-        coefB[c] = cf[c * 2 + 1];
-    }
+    __shared__ double fin[64];
+    stats_coef_prologue(st, b, plane, C, static_cast<double>(npx) * (C / kGroups), threadIdx.x, blockDim.x, fin, coefA, coefB);
     for (int k = threadIdx.x; k < Cout * C; k += blockDim.x) ws[k] = w.p[plane][k];
     for (int k = threadIdx.x; k < Cout; k += blockDim.x) bs[k] = bias.p[plane][k];
     __syncthreads();

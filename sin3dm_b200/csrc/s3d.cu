@@ -469,8 +469,8 @@ static void finalize(s3d_unet* u) {
 // GroupNorm statistics attached to a tensor by its producer kernel.  The buffers exist from the start; the consumer
 // arms the box with its norm parameters (attach_norm) before the plan runs, and an un-armed box is skipped at launch.
 struct SinkBox {
-    StatsSink s{};
-    int nslots = 0;
+    StatsSink s{};       // producer view
+    StatsSrc src{};      // consumer view (norm parameters filled in by the consumer)
     bool armed = false;
     bool use_film = false;
 };
@@ -558,83 +558,73 @@ struct PlanBuilder {
         return S;
     }
 
-    // ---- GroupNorm statistics -> per-channel affine coefficients of the consuming norm layer
-    StatsSink make_sink(int C, int nslots, const DevNorm& n, int film_off) {
-        StatsSink S{};
-        S.partial = dev_alloc<double>(P->allocs, static_cast<size_t>(B) * 3 * nslots * kGroups * 2);
-        S.ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3);
-        CUDA_TRY(cudaMemset(S.ticket, 0, sizeof(unsigned int) * B * 3));
-        S.coef = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 3 * C * 2);
-        S.gamma = cf3(n.gamma);
-        S.beta = cf3(n.beta);
-        S.film_dim = u->film_dim;
-        S.film_off = film_off;
-        S.C = C;
-        return S;
-    }
+    // ---- GroupNorm statistics (two-level partial sums; see StatsSink / StatsSrc in kernels.cuh)
     std::shared_ptr<SinkBox> make_box(int C, int nslots) {
         auto bx = std::make_shared<SinkBox>();
-        bx->nslots = nslots;
         StatsSink& S = bx->s;
-        S.partial = dev_alloc<double>(P->allocs, static_cast<size_t>(B) * 3 * nslots * kGroups * 2);
-        CUDA_TRY(cudaMemset(S.partial, 0, sizeof(double) * static_cast<size_t>(B) * 3 * nslots * kGroups * 2));
-        S.ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3);
-        CUDA_TRY(cudaMemset(S.ticket, 0, sizeof(unsigned int) * B * 3));
-        S.coef = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * 3 * C * 2);
-        S.film_dim = u->film_dim;
-        S.film_off = -1;
+        const int nsg = (nslots + kStatGroup - 1) / kStatGroup;
+        const size_t np = static_cast<size_t>(B) * 3 * nslots * 64, n2 = static_cast<size_t>(B) * 3 * nsg * 64;
+        S.partial = dev_alloc<double>(P->allocs, np);
+        CUDA_TRY(cudaMemset(S.partial, 0, sizeof(double) * np));
+        S.part2 = dev_alloc<double>(P->allocs, n2);
+        CUDA_TRY(cudaMemset(S.part2, 0, sizeof(double) * n2));
+        S.ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3 * nsg);
+        CUDA_TRY(cudaMemset(S.ticket, 0, sizeof(unsigned int) * B * 3 * nsg));
+        S.nslots = nslots;
         S.C = C;
+        bx->src.part2 = S.part2;
+        bx->src.nsg = nsg;
+        bx->src.film_dim = u->film_dim;
+        bx->src.film_off = -1;
         return bx;
     }
     // sink as seen by a producer launch: disabled unless a consumer armed it
-    static StatsSink live_sink(const std::shared_ptr<SinkBox>& bx, const Plan* Pp) {
+    static StatsSink live_sink(const std::shared_ptr<SinkBox>& bx) {
         StatsSink S{};
-        if (bx && bx->armed) {
-            S = bx->s;
-            if (bx->use_film) {
-                S.film = Pp->film;
-                S.film_row = Pp->film_row;
-            }
+        if (bx && bx->armed) S = bx->s;
+        return S;
+    }
+    // consumer view at launch time (binds the conditioning rows of this call)
+    static StatsSrc live_src(const std::shared_ptr<SinkBox>& bx, const Plan* Pp) {
+        StatsSrc S = bx->src;
+        if (bx->use_film) {
+            S.film = Pp->film;
+            S.film_row = Pp->film_row;
         }
         return S;
     }
-    // coefficients of `n` (+FiLM at film_off) applied to x: fused into x's producer when it supports it
-    float* stats(const ActF& x, const DevNorm& n, int film_off) {
-        if (x.sink) {
-            SinkBox& bx = *x.sink;
-            S3D_CHECK(!bx.armed, "tensor normalised twice");
-            bx.s.gamma = cf3(n.gamma);
-            bx.s.beta = cf3(n.beta);
-            bx.s.film_off = film_off;
-            bx.use_film = film_off >= 0;
-            bx.armed = true;
-            return bx.s.coef;
-        }
+    // group sums of x for the norm layer `n` (+FiLM at film_off): emitted by x's producer when it supports it,
+    // else by a stand-alone k_gn_stats pass
+    std::shared_ptr<SinkBox> stats(const ActF& x, const DevNorm& n, int film_off) {
+        std::shared_ptr<SinkBox> bx = x.sink;
+        const bool standalone = !bx;
         const int level = x.level, C = x.C;
         S3D_CHECK(C % kGroups == 0 && C % 4 == 0 && C / 4 <= 128, "unsupported channel count for GroupNorm32");
         const int nslots = std::max(1, std::min(128, max_px(level) / 48));
-        StatsSink S = make_sink(C, nslots, n, film_off);
-        TriCF xc = cf(x.p);
-        TriDims d = dims[level];
-        const int Bv = B;
-        const bool use_film = film_off >= 0;
-        Plan* Pp = P;
-        add_op("k_gn_stats", 0.0, [=](cudaStream_t s) {
-            StatsSink Sl = S;
-            if (use_film) {
-                Sl.film = Pp->film;
-                Sl.film_row = Pp->film_row;
-            }
-            const int ny = std::max(1, std::min(16, 1024 / (C / 4)));
-            dim3 grid(nslots, 3, Bv), block(C / 4, ny);
-            k_gn_stats<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, d, Sl, nslots);
-            LAUNCH_CHECK("k_gn_stats");
-        });
-        return S.coef;
+        if (standalone) bx = make_box(C, nslots);
+        S3D_CHECK(!bx->armed, "tensor normalised twice");
+        bx->src.gamma = cf3(n.gamma);
+        bx->src.beta = cf3(n.beta);
+        bx->src.film_off = film_off;
+        bx->use_film = film_off >= 0;
+        bx->armed = true;
+        if (standalone) {
+            TriCF xc = cf(x.p);
+            TriDims d = dims[level];
+            const int Bv = B;
+            StatsSink S = bx->s;
+            add_op("k_gn_stats", 0.0, [=](cudaStream_t s) {
+                const int ny = std::max(1, std::min(16, 1024 / (C / 4)));
+                dim3 grid(nslots, 3, Bv), block(C / 4, ny);
+                k_gn_stats<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, d, S, nslots);
+                LAUNCH_CHECK("k_gn_stats");
+            });
+        }
+        return bx;
     }
 
     // ---- GN apply + SiLU (+FiLM) -> fp16 operands (+ raw x16) (+ axis means)
-    void gn_silu(const ActF& x, const float* coef, const Act16& a, const Act16* x16, const Sums* S) {
+    void gn_silu(const ActF& x, const std::shared_ptr<SinkBox>& st, const Act16& a, const Act16* x16, const Sums* S) {
         const int level = x.level, C = x.C;
         const TriDims d = dims[level];
         const int bx = C / 4;
@@ -647,7 +637,6 @@ struct PlanBuilder {
         A.x = cf(x.p);
         A.d = d;
         A.C = C;
-        A.coef = coef;
         A.a = a.p;
         if (x16) A.x16 = x16->p;
         if (S) {
@@ -659,12 +648,15 @@ struct PlanBuilder {
             for (int i = 0; i < 6; ++i) A.seg_off[i] = S->seg_off[i];
             A.total_len = S->total_len;
         }
-        const size_t smem = sizeof(float) * static_cast<size_t>(ny) * kGsRows * C;
+        const size_t smem = sizeof(float) * (2 + static_cast<size_t>(ny) * kGsRows) * C;
         S3D_CHECK(smem <= 100 * 1024, "k_gn_silu shared memory");
         const int Bv = B;
+        Plan* Pp = P;
         add_op("k_gn_silu", 0.0, [=](cudaStream_t s) {
+            GnSiluArgs Al = A;
+            Al.st = live_src(st, Pp);
             dim3 grid(gx, 3, Bv), block(bx, ny);
-            k_gn_silu<<<grid, block, smem, s>>>(A, Bv);
+            k_gn_silu<<<grid, block, smem, s>>>(Al, Bv);
             LAUNCH_CHECK("k_gn_silu");
         });
     }
@@ -856,7 +848,6 @@ struct PlanBuilder {
             for (int p = 0; p < 3; ++p) max_tiles = std::max(max_tiles, A.tile_start[p + 1] - A.tile_start[p]);
             box = make_box(cv.Cout, max_tiles);
             out.sink = box;
-            A.sink_slots = max_tiles;
         }
         FusedRoll F{};
         auto rmaps = std::make_shared<RollTcMaps>();
@@ -871,7 +862,7 @@ struct PlanBuilder {
         }
         add_op("k_conv_tc", conv_flops(level, cv), [=](cudaStream_t s) {
             ConvTcArgs Al = A;
-            Al.sink = live_sink(box, Pp);
+            Al.sink = live_sink(box);
             if (use_emb) {
                 Al.e.embadd = Pp->film;
                 Al.e.film_row = Pp->film_row;
@@ -895,7 +886,7 @@ struct PlanBuilder {
             s1 = alloc_sums(level, b.cin);
             s2 = alloc_sums(level, b.cout);
         }
-        float* st1 = stats(x, w.n1, -1);
+        auto st1 = stats(x, w.n1, -1);
         Act16 a1 = alloc16(level, b.cin);
         Act16 x16{};
         if (b.has_skip) x16 = alloc16(level, b.cin);
@@ -904,7 +895,7 @@ struct PlanBuilder {
         if (ro) t1 = roll1d(s1, level, w.c1);
         ActF h1 = allocF(level, b.cout, b.name + ".h1");
         conv(a1, level, w.c1, ro ? &t1 : nullptr, nullptr, nullptr, ssn ? -1 : b.film_off, h1);
-        float* st2 = stats(h1, w.n2, ssn ? b.film_off : -1);
+        auto st2 = stats(h1, w.n2, ssn ? b.film_off : -1);
         Act16 a2 = alloc16(level, b.cout);
         gn_silu(h1, st2, a2, nullptr, ro ? &s2 : nullptr);
         TBuf t2{};
@@ -928,7 +919,7 @@ struct PlanBuilder {
         add_op("k_avgpool2", 0.0, [=](cudaStream_t s) {
             const int ny = std::max(1, 256 / (C / 4));
             dim3 grid(nslots, 3, Bv), block(C / 4, ny);
-            k_avgpool2<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, di, dd, C, op, live_sink(box, Pp), nslots);
+            k_avgpool2<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, di, dd, C, op, live_sink(box), nslots);
             LAUNCH_CHECK("k_avgpool2");
         });
         return o;
@@ -952,7 +943,7 @@ struct PlanBuilder {
             const int ny = std::max(1, 256 / (Ct / 4));
             dim3 grid(nslots, 3, Bv), block(Ct / 4, ny);
             k_upcat<<<grid, block, sizeof(float) * (ny * 2 + 2) * Ct, s>>>(lc, dl, Cu, sc, Cs, dout, op, do_up ? 1 : 0,
-                                                                           live_sink(box, Pp), nslots);
+                                                                           live_sink(box), nslots);
             LAUNCH_CHECK("k_upcat");
         });
         return o;
@@ -999,7 +990,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         S3D_CHECK(smem <= 100 * 1024, "k_in_conv shared memory");
         pb.add_op("k_in_conv", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * Cin * c0, [=](cudaStream_t s) {
             dim3 grid(nslots, 3, B), block(c0 / 4, ny);
-            k_in_conv<<<grid, block, smem, s>>>(P->x, d0, H, W, D, Cin, c0, w, bb, op, PlanBuilder::live_sink(box, P), nslots);
+            k_in_conv<<<grid, block, smem, s>>>(P->x, d0, H, W, D, Cin, c0, w, bb, op, PlanBuilder::live_sink(box), nslots);
             LAUNCH_CHECK("k_in_conv");
         });
     }
@@ -1039,7 +1030,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     }
     S3D_CHECK(!pending_up && h.level == 0, "decoder structure");
     // ---- out head
-    float* st = pb.stats(h, u->out_norm, -1);
+    auto st = pb.stats(h, u->out_norm, -1);
     {
         const TriDims d0 = pb.dims[0];
         const int C = h.C, Cout = c.out_channels;
@@ -1050,7 +1041,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         S3D_CHECK(smem <= 100 * 1024, "k_out_head shared memory");
         pb.add_op("k_out_head", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * C * Cout, [=](cudaStream_t s) {
             dim3 grid((mp + 127) / 128, 4, B);
-            k_out_head<<<grid, 128, smem, s>>>(xc, d0, C, Cout, st, w, bb, P->out, H, W, D);
+            k_out_head<<<grid, 128, smem, s>>>(xc, d0, C, Cout, PlanBuilder::live_src(st, P), w, bb, P->out, H, W, D);
             LAUNCH_CHECK("k_out_head");
         });
     }
