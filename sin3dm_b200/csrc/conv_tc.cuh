@@ -23,16 +23,20 @@
 
 namespace s3d {
 
-constexpr int kTileH = 8, kTileW = 16;
+constexpr int kTileH = 16, kTileW = 8;     // conv M tile = 16 rows x 8 cols of one plane (m = h*8 + w)
+constexpr int kHaloH = kTileH + 2, kHaloW = 16;   // halo patch rows / (padded) cols: row pitch 16 px = 2048 B keeps every
+                                                   // 8-pixel row group on the same 128B-swizzle phase
 constexpr int kBM = 128, kBN = 64, kBK = 64;
-constexpr int kABytes = kBM * kBK * 2;   // 16 KiB
-constexpr int kBBytes = kBN * kBK * 2;   //  8 KiB
-constexpr int kConvThreads = 192;
+constexpr int kABytes = kBM * kBK * 2;             // 16 KiB: plain 128-row A tile (skip / rollout groups)
+constexpr int kAHaloBytes = kHaloH * kHaloW * kBK * 2;   // 36 KiB: halo patch of one 64-channel block
+constexpr int kBBytes = kBN * kBK * 2;             //  8 KiB
+constexpr int kConvThreads = 224;                  // warps: 0 A-producer, 1 MMA, 2..5 epilogue, 6 B-producer
+constexpr int kRollThreads = 192;
 
 struct ConvTcMaps {
-    CUtensorMap a[3];   // activations  (C, cols, rows, B, 2) fp16
-    CUtensorMap x[3];   // skip input   (Cs, cols, rows, B, 2) fp16 (unused when Cs == 0)
-    CUtensorMap w[3];   // weights      (Ktot, Cout, 2) fp16, K = tap*C + c, then the Cs skip channels
+    CUtensorMap a[3];   // activations (C, cols, rows, B, 2) fp16, box {64, 16, 18}: halo patch
+    CUtensorMap x[3];   // skip input  (Cs, cols, rows, B, 2) fp16, box {64, 8, 16} (unused when Cs == 0)
+    CUtensorMap w[3];   // weights     (Ktot, Cout, 2) fp16, K = tap*C + c, then the Cs skip channels
 };
 
 struct ConvTcArgs {
@@ -42,10 +46,11 @@ struct ConvTcArgs {
     int tile_start[4];   // prefix sum of tiles per plane
     ConvEpi e;
     StatsSink sink;      // GroupNorm partials of the output (sink.partial == nullptr: none); needs 64 % (Cout/32) == 0
+    int bo_zero;         // bring-up switch (S3D_HALO_BO0=1): leave the descriptor base_offset at 0 for shifted taps
 };
 
 struct RollTcMaps {
-    CUtensorMap a[6];   // means of source s: (C, L, 1, B, 2) fp16
+    CUtensorMap a[6];   // means of source s: (C, L, 1, B, 2) fp16, box {64, 128, 1}
     CUtensorMap w[6];   // class-summed 1-D weights: (3C, 4*Cout, 2) fp16, K = along*C + c
 };
 struct RollTcArgs {
@@ -54,10 +59,9 @@ struct RollTcArgs {
     int tile_start[7];
     int C, Cout;
 };
-
 // Fused launch: the rollout 1-D GEMM tiles ("roll tiles") are the first tile indices of the persistent conv kernel; the
 // conv tiles' epilogues wait on a device counter until every roll tile has been written (roll tiles never wait on
-// anything and are the first tile of the lowest-numbered CTAs, so the wait cannot deadlock).
+// anything and are the first tiles of the lowest-numbered CTAs, so the wait cannot deadlock).
 struct FusedRoll {
     RollTcArgs R;
     int n_roll;              // number of roll tiles (0: none; Trow/Tcol come from a separate launch or are absent)
@@ -67,12 +71,19 @@ struct FusedRoll {
 
 template <int NSPLIT>
 struct ConvTcCfg {
-    static constexpr int kStageBytes = (NSPLIT == 3 ? 2 : 1) * (kABytes + kBBytes);
-    static constexpr int kStages = NSPLIT == 3 ? 4 : 8;
+    static constexpr int kASlotBytes = (NSPLIT == 3 ? 2 : 1) * kAHaloBytes;   // hi at +0, lo at +kAHaloBytes
+    static constexpr int kBSlotBytes = (NSPLIT == 3 ? 2 : 1) * kBBytes;       // hi at +0, lo at +kBBytes
+    static constexpr int kASlots = 2;
+    static constexpr int kBSlots = NSPLIT == 3 ? 3 : 6;
+    static constexpr int kRingBytes = kASlots * kASlotBytes + kBSlots * kBSlotBytes;
     static constexpr int kAccCols = NSPLIT == 3 ? 128 : 64;     // TMEM columns of one accumulator stage
     static constexpr int kTmemCols = 2 * kAccCols;              // double-buffered accumulators
     static constexpr int kStatBytes = kBM * 33 * 4 + 4 * 2 * 32 * 4 + 2 * kBN * 4 + 64 * 8 * 8 + 16;   // epilogue statistics scratch
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStatBytes;
+    static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStatBytes;
+    // stand-alone k_roll_tc keeps the simple 4-stage {A,B} ring
+    static constexpr int kStageBytes = (NSPLIT == 3 ? 2 : 1) * (kABytes + kBBytes);
+    static constexpr int kStages = NSPLIT == 3 ? 4 : 8;
+    static constexpr int kRollSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
 struct ConvTile {
@@ -117,9 +128,14 @@ __device__ __forceinline__ RollTile roll_tile_decode(const FusedRoll& F, int t) 
     return T;
 }
 
-// Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer and the MMA
-// issuer run ahead across tile boundaries (shared-memory ring) and the accumulators are double-buffered in TMEM, so the
-// epilogue of tile i overlaps the main loop of tile i+1.
+// Persistent implicit-GEMM convolution, one CTA per SM, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+//
+// Operand traffic is what bounds this kernel (64 B/clk per SM from L2), so the A operand is fetched ONCE per 64-channel
+// block as an 18 x 16-pixel halo patch and all nine taps read it in place: tap (kh, kw) is the same shared-memory patch
+// addressed from row (kh*16 + kw) with an 8-row-group stride of 2048 B (UMMA descriptor start / SBO / base_offset), i.e.
+// 1/6 of the activation bytes of a tap-by-tap im2col.  Only the 8 KiB weight tile changes per tap.
+// Two independent TMA producers (A patches, B tiles), one MMA issuer, four epilogue warps; accumulators double-buffered
+// in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 template <int NSPLIT>
 __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_constant__ ConvTcMaps M,
                                                              const __grid_constant__ RollTcMaps RM, const ConvTcArgs A,
@@ -128,13 +144,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-    uint64_t* empty_bar = full_bar + Cfg::kStages;
-    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;      // [2]
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + Cfg::kASlots * Cfg::kASlotBytes;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes);
+    uint64_t* emptyA = fullA + Cfg::kASlots;
+    uint64_t* fullB = emptyA + Cfg::kASlots;
+    uint64_t* emptyB = fullB + Cfg::kBSlots;
+    uint64_t* tmem_full_bar = emptyB + Cfg::kBSlots;         // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     // epilogue statistics scratch (behind the 256-byte barrier block)
-    double* stat_fin = reinterpret_cast<double*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // [64*8]
+    double* stat_fin = reinterpret_cast<double*>(smem + Cfg::kRingBytes + 256);                     // [64*8] (spare)
     float* stat_stage = reinterpret_cast<float*>(stat_fin + 64 * 8);                               // [128][33]
     float* stat_colp = stat_stage + kBM * 33;                                                      // [4][2][32]
     float* stat_tot = stat_colp + 4 * 2 * 32;                                                      // [2][64]
@@ -142,8 +162,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cblks = A.C / kBK;
-    const int nk_main = 9 * cblks;
-    const int nk = nk_main + A.Cs / kBK;
+    const int nskip = A.Cs / kBK;
+    constexpr uint32_t kALo = kAHaloBytes, kBLo = kBBytes;
+    constexpr uint32_t kAStdTx = (NSPLIT == 3 ? 2 : 1) * kABytes, kAHaloTx = (NSPLIT == 3 ? 2 : 1) * kAHaloBytes;
 
     if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -162,9 +183,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < Cfg::kStages; ++s) {
-                ptx::mbar_init(&full_bar[s], 1);
-                ptx::mbar_init(&empty_bar[s], 1);
+            for (int s = 0; s < Cfg::kASlots; ++s) {
+                ptx::mbar_init(&fullA[s], 1);
+                ptx::mbar_init(&emptyA[s], 1);
+            }
+            for (int s = 0; s < Cfg::kBSlots; ++s) {
+                ptx::mbar_init(&fullB[s], 1);
+                ptx::mbar_init(&emptyB[s], 1);
             }
             for (int s = 0; s < 2; ++s) {
                 ptx::mbar_init(&tmem_full_bar[s], 1);
@@ -181,88 +206,119 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer: A operand groups =====================
         if (lane == 0) {
-            int it = 0;
+            int ga = 0;
+            auto slot_wait = [&](uint32_t tx) -> uint8_t* {
+                const int s = ga % Cfg::kASlots;
+                ptx::mbar_wait(&emptyA[s], ((ga / Cfg::kASlots) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&fullA[s], tx);
+                return smem_a + s * Cfg::kASlotBytes;
+            };
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 if (t < F.n_roll) {
                     const RollTile T = roll_tile_decode(F, t);
-                    for (int i = 0; i < 3 * cblks; ++i, ++it) {
-                        const int s = it % Cfg::kStages;
-                        const uint32_t ph = (it / Cfg::kStages) & 1;
-                        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                        uint8_t* st = smem + s * Cfg::kStageBytes;
-                        ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                    for (int i = 0; i < 3 * cblks; ++i, ++ga) {
+                        uint8_t* st = slot_wait(kAStdTx);
+                        const int s = ga % Cfg::kASlots;
                         const int al = i / cblks, cb = i - al * cblks;
-                        ptx::tma_load_5d(st, &RM.a[T.src], &full_bar[s], cb * kBK, T.p0 + al - 1, 0, T.b, 0);
-                        ptx::tma_load_3d(st + kABytes, &RM.w[T.src], &full_bar[s], i * kBK, T.n0, 0);
-                        if (NSPLIT == 3) {
-                            ptx::tma_load_5d(st + kABytes + kBBytes, &RM.a[T.src], &full_bar[s], cb * kBK, T.p0 + al - 1, 0, T.b, 1);
-                            ptx::tma_load_3d(st + 2 * kABytes + kBBytes, &RM.w[T.src], &full_bar[s], i * kBK, T.n0, 1);
-                        }
+                        ptx::tma_load_5d(st, &RM.a[T.src], &fullA[s], cb * kBK, T.p0 + al - 1, 0, T.b, 0);
+                        if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &RM.a[T.src], &fullA[s], cb * kBK, T.p0 + al - 1, 0, T.b, 1);
                     }
                     continue;
                 }
                 const ConvTile T = conv_tile_decode(A, t - F.n_roll);
-                for (int i = 0; i < nk; ++i, ++it) {
-                    const int s = it % Cfg::kStages;
-                    const uint32_t ph = (it / Cfg::kStages) & 1;
-                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* st = smem + s * Cfg::kStageBytes;
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                    const CUtensorMap* amap;
-                    int c0, wc, hc;
-                    if (i < nk_main) {
-                        const int tap = i / cblks, cb = i - tap * cblks;
-                        const int kh = tap / 3, kw = tap - kh * 3;
-                        amap = &M.a[T.plane];
-                        c0 = cb * kBK; wc = T.w0 + kw - 1; hc = T.h0 + kh - 1;
-                    } else {
-                        amap = &M.x[T.plane];
-                        c0 = (i - nk_main) * kBK; wc = T.w0; hc = T.h0;
-                    }
-                    ptx::tma_load_5d(st, amap, &full_bar[s], c0, wc, hc, T.b, 0);
-                    ptx::tma_load_3d(st + kABytes, &M.w[T.plane], &full_bar[s], i * kBK, T.n0, 0);
-                    if (NSPLIT == 3) {
-                        ptx::tma_load_5d(st + kABytes + kBBytes, amap, &full_bar[s], c0, wc, hc, T.b, 1);
-                        ptx::tma_load_3d(st + 2 * kABytes + kBBytes, &M.w[T.plane], &full_bar[s], i * kBK, T.n0, 1);
-                    }
+                for (int cb = 0; cb < cblks; ++cb, ++ga) {
+                    uint8_t* st = slot_wait(kAHaloTx);
+                    const int s = ga % Cfg::kASlots;
+                    ptx::tma_load_5d(st, &M.a[T.plane], &fullA[s], cb * kBK, T.w0 - 1, T.h0 - 1, T.b, 0);
+                    if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &M.a[T.plane], &fullA[s], cb * kBK, T.w0 - 1, T.h0 - 1, T.b, 1);
                 }
+                for (int j = 0; j < nskip; ++j, ++ga) {
+                    uint8_t* st = slot_wait(kAStdTx);
+                    const int s = ga % Cfg::kASlots;
+                    ptx::tma_load_5d(st, &M.x[T.plane], &fullA[s], j * kBK, T.w0, T.h0, T.b, 0);
+                    if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &M.x[T.plane], &fullA[s], j * kBK, T.w0, T.h0, T.b, 1);
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================== TMA producer: B (weight) tiles =====================
+        if (lane == 0) {
+            int gb = 0;
+            auto load_b = [&](const CUtensorMap* wm, int kchunk, int n0) {
+                const int s = gb % Cfg::kBSlots;
+                ptx::mbar_wait(&emptyB[s], ((gb / Cfg::kBSlots) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&fullB[s], Cfg::kBSlotBytes);
+                uint8_t* st = smem_b + s * Cfg::kBSlotBytes;
+                ptx::tma_load_3d(st, wm, &fullB[s], kchunk * kBK, n0, 0);
+                if (NSPLIT == 3) ptx::tma_load_3d(st + kBLo, wm, &fullB[s], kchunk * kBK, n0, 1);
+                ++gb;
+            };
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                if (t < F.n_roll) {
+                    const RollTile T = roll_tile_decode(F, t);
+                    for (int i = 0; i < 3 * cblks; ++i) load_b(&RM.w[T.src], i, T.n0);
+                    continue;
+                }
+                const ConvTile T = conv_tile_decode(A, t - F.n_roll);
+                for (int cb = 0; cb < cblks; ++cb)
+                    for (int tap = 0; tap < 9; ++tap) load_b(&M.w[T.plane], tap * cblks + cb, T.n0);
+                for (int j = 0; j < nskip; ++j) load_b(&M.w[T.plane], 9 * cblks + j, T.n0);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, kBN);
-            int it = 0, lt = 0;
+            int ga = 0, gb = 0, lt = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
                 const int as = lt & 1;
-                const uint32_t aph = (lt >> 1) & 1;
-                ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1);        // epilogue has drained this accumulator stage
+                ptx::mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator stage
                 ptx::tc_fence_after();
                 const uint32_t d1 = tmem_base + as * Cfg::kAccCols, d2 = d1 + kBN;
-                const int nk_t = t < F.n_roll ? 3 * cblks : nk;
-                for (int i = 0; i < nk_t; ++i, ++it) {
-                    const int s = it % Cfg::kStages;
-                    const uint32_t ph = (it / Cfg::kStages) & 1;
-                    ptx::mbar_wait(&full_bar[s], ph);
-                    ptx::tc_fence_after();
-                    const uint32_t st = ptx::smem_u32(smem + s * Cfg::kStageBytes);
-                    const uint64_t a_hi = ptx::make_sw128_kmajor_desc(st);
-                    const uint64_t b_hi = ptx::make_sw128_kmajor_desc(st + kABytes);
-                    const uint64_t a_lo = ptx::make_sw128_kmajor_desc(st + kABytes + kBBytes);
-                    const uint64_t b_lo = ptx::make_sw128_kmajor_desc(st + 2 * kABytes + kBBytes);
-#pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) {
-                        const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);   // +32 B along K inside the swizzle atom
-                        const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-                        ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
-                        if (NSPLIT == 3) {
-                            ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, acc);
-                            ptx::umma_f16(d2, a_hi + ko, b_lo + ko, idesc, 1u);
+                const bool roll = t < F.n_roll;
+                const int n_halo = roll ? 0 : cblks;
+                const int n_groups = roll ? 3 * cblks : cblks + nskip;
+                bool first = true;
+                for (int g = 0; g < n_groups; ++g, ++ga) {
+                    const int sa = ga % Cfg::kASlots;
+                    ptx::mbar_wait(&fullA[sa], (ga / Cfg::kASlots) & 1);
+                    const uint32_t a_base = ptx::smem_u32(smem_a + sa * Cfg::kASlotBytes);
+                    const bool halo = g < n_halo;
+                    const int nb = halo ? 9 : 1;
+                    for (int tap = 0; tap < nb; ++tap, ++gb) {
+                        const int sb = gb % Cfg::kBSlots;
+                        ptx::mbar_wait(&fullB[sb], (gb / Cfg::kBSlots) & 1);
+                        ptx::tc_fence_after();
+                        const uint32_t b_base = ptx::smem_u32(smem_b + sb * Cfg::kBSlotBytes);
+                        uint64_t a_hi, a_lo;
+                        if (halo) {
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            const uint32_t off = static_cast<uint32_t>(kh * kHaloW + kw) * 128u;
+                            const uint32_t bo = A.bo_zero ? 0u : static_cast<uint32_t>(kw);
+                            a_hi = ptx::make_sw128_desc(a_base + off, kHaloW * 128u, bo);
+                            a_lo = ptx::make_sw128_desc(a_base + kALo + off, kHaloW * 128u, bo);
+                        } else {
+                            a_hi = ptx::make_sw128_desc(a_base, 1024u, 0);
+                            a_lo = ptx::make_sw128_desc(a_base + kALo, 1024u, 0);
                         }
+                        const uint64_t b_hi = ptx::make_sw128_desc(b_base, 1024u, 0);
+                        const uint64_t b_lo = ptx::make_sw128_desc(b_base + kBLo, 1024u, 0);
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);   // +32 B along K inside the swizzle atom
+                            const uint32_t acc = (!first || k > 0) ? 1u : 0u;
+                            ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
+                            if (NSPLIT == 3) {
+                                ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, acc);
+                                ptx::umma_f16(d2, a_hi + ko, b_lo + ko, idesc, 1u);
+                            }
+                        }
+                        first = false;
+                        ptx::umma_commit(&emptyB[sb]);    // weight slot free once the MMAs above retire
                     }
-                    ptx::umma_commit(&empty_bar[s]);      // frees this smem stage once the MMAs above retire
+                    ptx::umma_commit(&emptyA[sa]);        // A patch free once every tap has read it
                 }
                 ptx::umma_commit(&tmem_full_bar[as]);     // this tile's accumulators are complete
             }
@@ -271,21 +327,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int m = quarter * 32 + lane;
-        int lt = 0;
-        const int et = threadIdx.x - 64;                  // 0..127 among the epilogue threads
+        const int et = threadIdx.x - 64;              // 0..127 among the epilogue threads
         bool roll_ready = F.n_roll == 0;
+        int lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int as = lt & 1;
+            const uint32_t aph = (lt >> 1) & 1;
+            const uint32_t lane_addr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(quarter * 32) << 16);
             if (t < F.n_roll) {
                 // ---------- rollout 1-D GEMM tile: T[b][cls][pos][co] = accumulator ----------
                 const RollTile T = roll_tile_decode(F, t);
                 const int pos = T.p0 + m, L = F.R.L[T.src];
                 const int cls = T.n0 / A.Cout, co0 = T.n0 - cls * A.Cout;
                 float* __restrict__ outp = F.R.T[T.src] + ((static_cast<size_t>(T.b) * 4 + cls) * L + pos) * A.Cout + co0;
-                const int as = lt & 1;
-                ptx::mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
+                ptx::mbar_wait(&tmem_full_bar[as], aph);
                 __syncwarp();
                 ptx::tc_fence_after();
-                const uint32_t lane_addr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v1[32], v2[32];
@@ -317,7 +374,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             }
             const ConvTile T = conv_tile_decode(A, t - F.n_roll);
             const int plane = T.plane, n0 = T.n0, b = T.b;
-            const int r = T.h0 + (m >> 4), c = T.w0 + (m & 15);
+            const int r = T.h0 + (m >> 3), c = T.w0 + (m & 7);
             const int rows = A.d.rows[plane], cols = A.d.cols[plane];
             const bool valid = r < rows && c < cols;
             const size_t px = static_cast<size_t>(b) * rows * cols + static_cast<size_t>(r) * cols + c;
@@ -337,6 +394,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
 #pragma unroll
                     for (int j = 0; j < kBN / 4; ++j) {
                         const float4 v = __ldg(e4 + j);
+                        pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w;
+                    }
+                }
+                if (valid && A.e.resid.p[plane]) {
+                    const float4* rs = reinterpret_cast<const float4*>(A.e.resid.p[plane] + px * A.Cout + n0);
+#pragma unroll
+                    for (int j = 0; j < kBN / 4; ++j) {
+                        const float4 v = __ldg(rs + j);
                         pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w;
                     }
                 }
@@ -364,22 +429,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         pre[4 * j + 3] += v.w + u.w;
                     }
                 }
-                if (valid && A.e.resid.p[plane]) {
-                    const float4* rs = reinterpret_cast<const float4*>(A.e.resid.p[plane] + px * A.Cout + n0);
-#pragma unroll
-                    for (int j = 0; j < kBN / 4; ++j) {
-                        const float4 v = __ldg(rs + j);
-                        pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w;
-                    }
-                }
             }
             float* __restrict__ outp = A.e.out.p[plane] + px * A.Cout + n0;
-            const int as = lt & 1;
-            const uint32_t aph = (lt >> 1) & 1;
             ptx::mbar_wait(&tmem_full_bar[as], aph);
             __syncwarp();
             ptx::tc_fence_after();
-            const uint32_t lane_addr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(quarter * 32) << 16);
             const bool do_stats = A.sink.partial != nullptr;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -471,7 +525,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
 // grid (sum over the 6 sources of ceil(L/128), 4*Cout/64, B)
 // =====================================================================================
 template <int NSPLIT>
-__global__ void __launch_bounds__(kConvThreads, 1) k_roll_tc(const __grid_constant__ RollTcMaps M, const RollTcArgs A) {
+__global__ void __launch_bounds__(kRollThreads, 1) k_roll_tc(const __grid_constant__ RollTcMaps M, const RollTcArgs A) {
     using Cfg = ConvTcCfg<NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -540,10 +594,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_roll_tc(const __grid_consta
                 ptx::mbar_wait(&full_bar[s], ph);
                 ptx::tc_fence_after();
                 const uint32_t st = ptx::smem_u32(smem + s * Cfg::kStageBytes);
-                const uint64_t a_hi = ptx::make_sw128_kmajor_desc(st);
-                const uint64_t b_hi = ptx::make_sw128_kmajor_desc(st + kABytes);
-                const uint64_t a_lo = ptx::make_sw128_kmajor_desc(st + kABytes + kBBytes);
-                const uint64_t b_lo = ptx::make_sw128_kmajor_desc(st + 2 * kABytes + kBBytes);
+                const uint64_t a_hi = ptx::make_sw128_desc1024(st);
+                const uint64_t b_hi = ptx::make_sw128_desc1024(st + kABytes);
+                const uint64_t a_lo = ptx::make_sw128_desc1024(st + kABytes + kBBytes);
+                const uint64_t b_lo = ptx::make_sw128_desc1024(st + 2 * kABytes + kBBytes);
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
                     const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);

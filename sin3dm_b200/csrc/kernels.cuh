@@ -70,6 +70,18 @@ __device__ __forceinline__ void stats_group_tail(const StatsSink& S, int b, int 
 // FiLM'ed) from the group sums.  All threads of the CTA call it; fin: smem double[64]; coefA/coefB: smem float[C].
 __device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, int plane, int C, double n_per_group, int tid, int nthr,
                                                     double* fin, float* coefA, float* coefB) {
+    // norm parameters of the first channel this thread owns are fetched together with the group sums (one round trip)
+    const float* film = nullptr;
+    if (S.film) film = S.film + static_cast<size_t>(S.film_row ? S.film_row[b] : b) * S.film_dim + S.film_off;
+    float g0 = 0.f, b0 = 0.f, f0 = 0.f, f1 = 0.f;
+    if (tid < C) {
+        g0 = __ldg(S.gamma.p[plane] + tid);
+        b0 = __ldg(S.beta.p[plane] + tid);
+        if (film) {
+            f0 = __ldg(film + tid);
+            f1 = __ldg(film + C + tid);
+        }
+    }
     if (tid < 64) {
         const double* pp = S.part2 + (static_cast<size_t>(b) * 3 + plane) * S.nsg * 64 + tid;
         double acc = 0.0;
@@ -86,18 +98,17 @@ __device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, in
     }
     __syncthreads();
     const int cpg = C / kGroups;
-    const float* film = nullptr;
-    if (S.film) film = S.film + static_cast<size_t>(S.film_row ? S.film_row[b] : b) * S.film_dim + S.film_off;
     for (int c = tid; c < C; c += nthr) {
         const int g = c / cpg;
         const double mean = fin[g * 2] / n_per_group;
         double var = fin[g * 2 + 1] / n_per_group - mean * mean;
         if (var < 0.0) var = 0.0;
         const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
-        float ga = S.gamma.p[plane][c] * rstd;
-        float be = S.beta.p[plane][c] - static_cast<float>(mean) * ga;
+        const bool first = c == tid;
+        float ga = (first ? g0 : S.gamma.p[plane][c]) * rstd;
+        float be = (first ? b0 : S.beta.p[plane][c]) - static_cast<float>(mean) * ga;
         if (film) {
-            const float sc = 1.f + film[c], sh = film[C + c];
+            const float sc = 1.f + (first ? f0 : film[c]), sh = first ? f1 : film[C + c];
             ga *= sc;
             be = fmaf(be, sc, sh);
         }

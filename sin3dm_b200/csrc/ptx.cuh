@@ -117,18 +117,21 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 64 x 16-bit (128 B),
-// 8-row swizzle atoms 1024 B apart (SBO), sm_100 descriptor version 1.
-// (bit layout: cute/arch/mma_sm100_desc.hpp UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 64 x 16-bit (128 B), sm_100 descriptor
+// version 1 (bit layout: cute/arch/mma_sm100_desc.hpp UMMA::SmemDescriptor).
+//   sbo_bytes   : distance between consecutive 8-row groups (1024 for a dense tile; 2048 for a 16-pixel-pitch halo patch)
+//   base_offset : (start address >> 7) & 7 when the start is not aligned to the 1024-byte swizzle repeat
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);        // start address  [0,14)
     d |= static_cast<uint64_t>(1) << 16;                           // LBO (ignored for swizzled K-major) [16,30)
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // SBO = 1024 B   [32,46)
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;              // SBO            [32,46)
     d |= static_cast<uint64_t>(1) << 46;                           // version = 1    [46,48)
+    d |= static_cast<uint64_t>(base_offset & 7) << 49;             // base offset    [49,52)
     d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B   [61,64)
     return d;
 }
+__device__ __forceinline__ uint64_t make_sw128_desc1024(uint32_t smem_addr) { return make_sw128_desc(smem_addr, 1024u, 0u); }
 // Instruction descriptor for kind::f16: A,B = fp16 K-major, D = fp32, M x N tile.
 // (bit layout: UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {

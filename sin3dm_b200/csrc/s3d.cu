@@ -191,6 +191,7 @@ struct s3d_unet {
     int last_launches = 0;
     int num_sms = 148;
     bool fuse_roll = true;   // S3D_FUSE_ROLL=0 launches the rollout 1-D GEMM separately
+    bool halo_bo_zero = false;
 };
 
 static int ch_of(const s3d_unet_config& c, int level) { return c.channel_mult[level] * c.model_channels; }
@@ -457,8 +458,8 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_gn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kRollSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kRollSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_out_head, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_in_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaDeviceSynchronize());
@@ -757,8 +758,8 @@ struct PlanBuilder {
         }
         add_op("k_roll_tc", 0.0, [=](cudaStream_t s) {
             dim3 grid(total, ntn, Bv);
-            if (nsplit == 3) k_roll_tc<3><<<grid, kConvThreads, ConvTcCfg<3>::kSmemBytes, s>>>(*maps, A);
-            else k_roll_tc<1><<<grid, kConvThreads, ConvTcCfg<1>::kSmemBytes, s>>>(*maps, A);
+            if (nsplit == 3) k_roll_tc<3><<<grid, kRollThreads, ConvTcCfg<3>::kRollSmemBytes, s>>>(*maps, A);
+            else k_roll_tc<1><<<grid, kRollThreads, ConvTcCfg<1>::kRollSmemBytes, s>>>(*maps, A);
             LAUNCH_CHECK("k_roll_tc");
         });
         return T;
@@ -816,16 +817,18 @@ struct PlanBuilder {
         A.Cout = cv.Cout;
         A.Cs = cv.Cs;
         A.e = e;
+        A.bo_zero = u->halo_bo_zero ? 1 : 0;
         int total = 0;
         for (int p = 0; p < 3; ++p) {
             const uint64_t adims[5] = {static_cast<uint64_t>(cv.C), static_cast<uint64_t>(d.cols[p]),
                                        static_cast<uint64_t>(d.rows[p]), static_cast<uint64_t>(B), 2};
-            const uint32_t abox[5] = {kBK, kTileW, kTileH, 1, 1};
+            const uint32_t abox[5] = {kBK, kHaloW, kHaloH, 1, 1};      // halo patch (cols w0-1.., rows h0-1..)
+            const uint32_t xbox[5] = {kBK, kTileW, kTileH, 1, 1};      // plain tile for the 1x1 skip chunks
             make_tmap(&maps->a[p], a.p.p[p], 5, adims, abox);
             if (cv.Cs) {
                 const uint64_t xdims[5] = {static_cast<uint64_t>(cv.Cs), static_cast<uint64_t>(d.cols[p]),
                                            static_cast<uint64_t>(d.rows[p]), static_cast<uint64_t>(B), 2};
-                make_tmap(&maps->x[p], x16->p.p[p], 5, xdims, abox);
+                make_tmap(&maps->x[p], x16->p.p[p], 5, xdims, xbox);
             } else {
                 maps->x[p] = maps->a[p];
             }
@@ -1121,6 +1124,7 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     u->device = device;
     u->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("S3D_FUSE_ROLL")) u->fuse_roll = atoi(e) != 0;
+    if (const char* e = getenv("S3D_HALO_BO0")) u->halo_bo_zero = atoi(e) != 0;
     build_structure(u.get());
     *out = u.release();
     API_END
