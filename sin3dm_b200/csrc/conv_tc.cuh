@@ -46,7 +46,8 @@ struct ConvTcArgs {
     int tile_start[4];   // prefix sum of tiles per plane
     ConvEpi e;
     StatsSink sink;      // GroupNorm partials of the output (sink.partial == nullptr: none); needs 64 % (Cout/32) == 0
-    int bo_zero;         // bring-up switch (S3D_HALO_BO0=1): leave the descriptor base_offset at 0 for shifted taps
+    int bo_kw;           // bring-up switch (S3D_HALO_BO_KW=1): put kw into the descriptor base_offset (measured WRONG on B200:
+                         // the tensor core derives the swizzle phase from the absolute shared-memory address)
 };
 
 struct RollTcMaps {
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         if (halo) {
                             const int kh = tap / 3, kw = tap - kh * 3;
                             const uint32_t off = static_cast<uint32_t>(kh * kHaloW + kw) * 128u;
-                            const uint32_t bo = A.bo_zero ? 0u : static_cast<uint32_t>(kw);
+                            const uint32_t bo = A.bo_kw ? static_cast<uint32_t>(kw) : 0u;
                             a_hi = ptx::make_sw128_desc(a_base + off, kHaloW * 128u, bo);
                             a_lo = ptx::make_sw128_desc(a_base + kALo + off, kHaloW * 128u, bo);
                         } else {

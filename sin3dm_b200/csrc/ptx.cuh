@@ -120,7 +120,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 64 x 16-bit (128 B), sm_100 descriptor
 // version 1 (bit layout: cute/arch/mma_sm100_desc.hpp UMMA::SmemDescriptor).
 //   sbo_bytes   : distance between consecutive 8-row groups (1024 for a dense tile; 2048 for a 16-pixel-pitch halo patch)
-//   base_offset : (start address >> 7) & 7 when the start is not aligned to the 1024-byte swizzle repeat
+//   base_offset : leave 0.  Measured on B200 (gpurun r1, tools/gpu_diag.py): for a start address that is a multiple of
+//                 128 B but not of 1024 B the hardware takes the swizzle phase from the absolute smem address; writing
+//                 (addr >> 7) & 7 here breaks the result.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);        // start address  [0,14)

@@ -191,7 +191,7 @@ struct s3d_unet {
     int last_launches = 0;
     int num_sms = 148;
     bool fuse_roll = true;   // S3D_FUSE_ROLL=0 launches the rollout 1-D GEMM separately
-    bool halo_bo_zero = false;
+    bool halo_bo_kw = false;
 };
 
 static int ch_of(const s3d_unet_config& c, int level) { return c.channel_mult[level] * c.model_channels; }
@@ -817,7 +817,7 @@ struct PlanBuilder {
         A.Cout = cv.Cout;
         A.Cs = cv.Cs;
         A.e = e;
-        A.bo_zero = u->halo_bo_zero ? 1 : 0;
+        A.bo_kw = u->halo_bo_kw ? 1 : 0;
         int total = 0;
         for (int p = 0; p < 3; ++p) {
             const uint64_t adims[5] = {static_cast<uint64_t>(cv.C), static_cast<uint64_t>(d.cols[p]),
@@ -1124,7 +1124,7 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     u->device = device;
     u->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("S3D_FUSE_ROLL")) u->fuse_roll = atoi(e) != 0;
-    if (const char* e = getenv("S3D_HALO_BO0")) u->halo_bo_zero = atoi(e) != 0;
+    if (const char* e = getenv("S3D_HALO_BO_KW")) u->halo_bo_kw = atoi(e) != 0;
     build_structure(u.get());
     *out = u.release();
     API_END
