@@ -28,6 +28,13 @@ constexpr int kGroups = 32;        // GroupNorm32(32, C), reference src/diffusio
 constexpr float kGnEps = 1e-5f;    // torch.nn.GroupNorm default
 constexpr float kLoScale = 2048.f; // lo = (v - fp16(v)) * 2^11 keeps the residual in fp16 normal range
 
+// Programmatic dependent launch (PDL): every kernel of the step is launched with programmaticStreamSerialization, so
+// its CTAs may become resident while the previous kernel is still draining.  pdl_wait() blocks until the previous grid
+// has completed and its writes are visible; nothing that reads or writes activations may precede it.  pdl_trigger()
+// lets the NEXT kernel start launching (it will block in its own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float silu_f(float v) {
     // x * sigmoid(x), reference src/diffusion/nn.py:12-14.  ex2.approx + rcp: ~1e-6 relative.
     return __fdividef(v, 1.f + __expf(-v));

@@ -205,10 +205,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // PDL: everything above (barriers, TMEM, descriptor prefetch) and the weight-tile producer below overlap the tail of the
+    // previous kernel; threads that touch activations / statistics / rollout terms wait for it first.
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================== TMA producer: A operand groups =====================
         if (lane == 0) {
+            pdl_wait();
             int ga = 0;
             auto slot_wait = [&](uint32_t tx) -> uint8_t* {
                 const int s = ga % Cfg::kASlots;
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, kBN);
+            constexpr uint32_t idesc2 = ptx::make_idesc_f16(kBM, 2 * kBN);
             int ga = 0, gb = 0, lt = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
                 const int as = lt & 1;
@@ -305,15 +310,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                             a_lo = ptx::make_sw128_desc(a_base + kALo, 1024u, 0);
                         }
                         const uint64_t b_hi = ptx::make_sw128_desc(b_base, 1024u, 0);
-                        const uint64_t b_lo = ptx::make_sw128_desc(b_base + kBLo, 1024u, 0);
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k) {
                             const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);   // +32 B along K inside the swizzle atom
                             const uint32_t acc = (!first || k > 0) ? 1u : 0u;
-                            ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
                             if (NSPLIT == 3) {
-                                ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, acc);
-                                ptx::umma_f16(d2, a_hi + ko, b_lo + ko, idesc, 1u);
+                                // [D1 | D2] (+)= Ah * [Bh | Bl]  (one N=128 MMA: the lo weight tile sits right behind the hi
+                                // tile in shared memory and D2 right behind D1 in TMEM), then D2 += Al * Bh
+                                ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc2, acc);
+                                ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, 1u);
+                            } else {
+                                ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
                             }
                         }
                         first = false;
@@ -331,6 +338,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         const int et = threadIdx.x - 64;              // 0..127 among the epilogue threads
         bool roll_ready = F.n_roll == 0;
         int lt = 0;
+        pdl_wait();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int as = lt & 1;
             const uint32_t aph = (lt >> 1) & 1;
@@ -493,11 +501,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     const int gl = et >> 1, which = et & 1;
                     double acc = 0.0;
                     for (int cc = gl * cpg; cc < (gl + 1) * cpg; ++cc) acc += static_cast<double>(stat_tot[which * kBN + cc]);
-                    A.sink.partial[((static_cast<size_t>(b) * 3 + plane) * A.sink.nslots + T.ip) * (kGroups * 2) + (g0 + gl) * 2 + which] = acc;
+                    A.sink.partial[((static_cast<size_t>(b) * 3 + plane) * A.sink.nslots + T.ip) * (kGroups * 2) + (g0 + gl) * 2 + which] =
+                        static_cast<float>(acc);
                 }
-                const int tiles_p = A.tile_start[plane + 1] - A.tile_start[plane];
-                stats_group_tail(A.sink, b, plane, T.ip, tiles_p, A.Cout / kBN, et,
-                                 [] { asm volatile("bar.sync 1, 128;" ::: "memory"); }, stat_flag);
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // stat_tot is reused by the next tile
             }
         }
     }
@@ -527,6 +534,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
 // =====================================================================================
 template <int NSPLIT>
 __global__ void __launch_bounds__(kRollThreads, 1) k_roll_tc(const __grid_constant__ RollTcMaps M, const RollTcArgs A) {
+    pdl_wait();
+    pdl_trigger();
     using Cfg = ConvTcCfg<NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -577,17 +586,20 @@ __global__ void __launch_bounds__(kRollThreads, 1) k_roll_tc(const __grid_consta
                 uint8_t* st = smem + s * Cfg::kStageBytes;
                 ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
                 const int al = i / cblks, cb = i - al * cblks;
+                // stage layout: [A hi][A lo][B hi][B lo]  (B lo directly behind B hi: one N=128 MMA reads both)
+                constexpr int kBOff = (NSPLIT == 3 ? 2 : 1) * kABytes;
                 ptx::tma_load_5d(st, &M.a[src], &full_bar[s], cb * kBK, p0 + al - 1, 0, b, 0);
-                ptx::tma_load_3d(st + kABytes, &M.w[src], &full_bar[s], i * kBK, n0, 0);
+                ptx::tma_load_3d(st + kBOff, &M.w[src], &full_bar[s], i * kBK, n0, 0);
                 if (NSPLIT == 3) {
-                    ptx::tma_load_5d(st + kABytes + kBBytes, &M.a[src], &full_bar[s], cb * kBK, p0 + al - 1, 0, b, 1);
-                    ptx::tma_load_3d(st + 2 * kABytes + kBBytes, &M.w[src], &full_bar[s], i * kBK, n0, 1);
+                    ptx::tma_load_5d(st + kABytes, &M.a[src], &full_bar[s], cb * kBK, p0 + al - 1, 0, b, 1);
+                    ptx::tma_load_3d(st + kBOff + kBBytes, &M.w[src], &full_bar[s], i * kBK, n0, 1);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, kBN);
+            constexpr uint32_t idesc2 = ptx::make_idesc_f16(kBM, 2 * kBN);
             const uint32_t d1 = tmem_base, d2 = tmem_base + kBN;
             for (int i = 0; i < nk; ++i) {
                 const int s = i % Cfg::kStages;
@@ -595,18 +607,19 @@ __global__ void __launch_bounds__(kRollThreads, 1) k_roll_tc(const __grid_consta
                 ptx::mbar_wait(&full_bar[s], ph);
                 ptx::tc_fence_after();
                 const uint32_t st = ptx::smem_u32(smem + s * Cfg::kStageBytes);
+                constexpr uint32_t kBOff = (NSPLIT == 3 ? 2 : 1) * kABytes;
                 const uint64_t a_hi = ptx::make_sw128_desc1024(st);
-                const uint64_t b_hi = ptx::make_sw128_desc1024(st + kABytes);
-                const uint64_t a_lo = ptx::make_sw128_desc1024(st + kABytes + kBBytes);
-                const uint64_t b_lo = ptx::make_sw128_desc1024(st + 2 * kABytes + kBBytes);
+                const uint64_t a_lo = ptx::make_sw128_desc1024(st + kABytes);
+                const uint64_t b_hi = ptx::make_sw128_desc1024(st + kBOff);
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
                     const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);
                     const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-                    ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
                     if (NSPLIT == 3) {
-                        ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, acc);
-                        ptx::umma_f16(d2, a_hi + ko, b_lo + ko, idesc, 1u);
+                        ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc2, acc);     // [D1 | D2] (+)= Ah * [Bh | Bl]
+                        ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, 1u);       // D2 += Al * Bh
+                    } else {
+                        ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
                     }
                 }
                 ptx::umma_commit(&empty_bar[s]);

@@ -14,63 +14,27 @@ namespace s3d {
 //     y = x * coef[c][0] + coef[c][1]   ==  GroupNorm(x) * gamma + beta   (optionally * (1 + scale) + shift)
 // so consumers need no statistics pass, no shared memory and no barrier before their first load.
 // =====================================================================================
-constexpr int kStatGroup = 8;      // slots per first-level group
-
 struct StatsSink {                 // producer side
-    double* partial;          // [B][3][nslots][64]   per-slot (sum, sum-sq) of the 32 groups
-    unsigned int* ticket;     // [B][3][nsg]          first-level tickets, nsg = ceil(nslots / 8)
-    double* part2;            // [B][3][nsg][64]      per-slot-group sums (what consumers read)
-    int nslots;               // slot stride of `partial`
+    float* partial;           // [B][3][nslots][64]   per-slot (sum, sum-sq) of the 32 groups; nullptr: not wanted
+    int nslots;               // slot stride of `partial` (slots a plane does not use stay zero)
     int C;
 };
 struct StatsSrc {                  // consumer side
-    const double* part2;      // [B][3][nsg][64]
-    int nsg;
+    const float* partial;     // [B][3][nslots][64]
+    int nslots;
     TriCF gamma, beta;        // consumer norm parameters [C]
     const float* film;        // [rows][film_dim] or nullptr
     const int* film_row;
     int film_dim, film_off;   // scale at film_off, shift at film_off + C
 };
 
-// Two-level deterministic reduction.  A producer CTA calls this (all `nthr` >= 64 threads, after writing its slot):
-// the last contributor of a group of 8 slots adds them in slot order into part2.  `plane_slots` = slots this plane
-// really has, `per_slot` = CTAs contributing to one slot.  Consumers add the <= 16 group sums themselves
-// (stats_coef_prologue), so no single CTA ever walks the whole partial list.
-template <class Sync>
-__device__ __forceinline__ void stats_group_tail(const StatsSink& S, int b, int plane, int slot, int plane_slots, int per_slot, int tid,
-                                                 Sync sync, int* flag /*smem*/) {
-    const int nsg = (S.nslots + kStatGroup - 1) / kStatGroup;
-    const int g1 = slot / kStatGroup;
-    const int in_group = min(kStatGroup, plane_slots - g1 * kStatGroup);
-    __threadfence();
-    sync();
-    if (tid == 0) {
-        unsigned int* tk = S.ticket + (static_cast<size_t>(b) * 3 + plane) * nsg + g1;
-        const unsigned int prev = atomicAdd(tk, 1u);
-        const int last = prev == static_cast<unsigned int>(in_group * per_slot - 1);
-        if (last) *tk = 0u;          // re-arm for the next launch
-        *flag = last;
-    }
-    sync();
-    if (!*flag) return;
-    __threadfence();
-    if (tid < 64) {
-        const double* pp = S.partial + ((static_cast<size_t>(b) * 3 + plane) * S.nslots + g1 * kStatGroup) * 64 + tid;
-        double v[kStatGroup];
-#pragma unroll
-        for (int k = 0; k < kStatGroup; ++k) v[k] = k < in_group ? __ldcg(pp + k * 64) : 0.0;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < kStatGroup; ++k) acc += v[k];
-        S.part2[((static_cast<size_t>(b) * 3 + plane) * nsg + g1) * 64 + tid] = acc;
-    }
-}
-
-// Consumer prologue: per-channel affine coefficients  y = x * coefA[c] + coefB[c]  ==  GroupNorm(x)*gamma+beta (optionally
-// FiLM'ed) from the group sums.  All threads of the CTA call it; fin: smem double[64]; coefA/coefB: smem float[C].
+// Consumer prologue: every consumer CTA adds the producer's per-slot partial sums itself (fixed order, fp64) and turns them
+// into per-channel affine coefficients  y = x * coefA[c] + coefB[c]  ==  GroupNorm(x)*gamma+beta (optionally FiLM'ed).
+// Producers therefore need no fence, ticket or tail: the kernel boundary publishes their partials, and all loads below are
+// independent (one L2 round trip, overlapped with the caller's activation loads).
+// All threads of the CTA call it (nthr >= 64); fin: smem double[64 * 9]; coefA/coefB: smem float[C].
 __device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, int plane, int C, double n_per_group, int tid, int nthr,
                                                     double* fin, float* coefA, float* coefB) {
-    // norm parameters of the first channel this thread owns are fetched together with the group sums (one round trip)
     const float* film = nullptr;
     if (S.film) film = S.film + static_cast<size_t>(S.film_row ? S.film_row[b] : b) * S.film_dim + S.film_off;
     float g0 = 0.f, b0 = 0.f, f0 = 0.f, f1 = 0.f;
@@ -82,18 +46,26 @@ __device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, in
             f1 = __ldg(film + C + tid);
         }
     }
-    if (tid < 64) {
-        const double* pp = S.part2 + (static_cast<size_t>(b) * 3 + plane) * S.nsg * 64 + tid;
+    const int nsl = min(nthr >> 6, 8);                   // slices of 64 threads
+    if (tid < nsl * 64) {
+        const int slice = tid >> 6, e = tid & 63;
+        const float* pp = S.partial + (static_cast<size_t>(b) * 3 + plane) * S.nslots * 64 + e;
         double acc = 0.0;
-        int g = 0;
-        for (; g + 8 <= S.nsg; g += 8) {
-            double v[8];
+        int sl = slice;
+        for (; sl + 15 * nsl < S.nslots; sl += 16 * nsl) {
+            float v[16];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __ldcg(pp + (g + k) * 64);
+            for (int k = 0; k < 16; ++k) v[k] = __ldg(pp + static_cast<size_t>(sl + k * nsl) * 64);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc += v[k];
+            for (int k = 0; k < 16; ++k) acc += static_cast<double>(v[k]);
         }
-        for (; g < S.nsg; ++g) acc += __ldcg(pp + g * 64);
+        for (; sl < S.nslots; sl += nsl) acc += static_cast<double>(__ldg(pp + static_cast<size_t>(sl) * 64));
+        fin[64 + slice * 64 + e] = acc;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        double acc = 0.0;
+        for (int k = 0; k < nsl; ++k) acc += fin[64 + k * 64 + tid];
         fin[tid] = acc;
     }
     __syncthreads();
@@ -138,20 +110,21 @@ __device__ __forceinline__ void stats_block_partial(const StatsSink& S, float4 s
     }
     __syncthreads();
     const int cpg = C / kGroups;
-    double* part = S.partial + ((static_cast<size_t>(b) * 3 + plane) * S.nslots + slot) * kGroups * 2;
+    float* part = S.partial + ((static_cast<size_t>(b) * 3 + plane) * S.nslots + slot) * kGroups * 2;
     if (tid < 2 * kGroups) {
         const int g = tid >> 1, which = tid & 1;
         double acc = 0.0;
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(tot[which * C + c]);
-        part[g * 2 + which] = acc;
+        part[g * 2 + which] = static_cast<float>(acc);
     }
 }
 
 // Stand-alone statistics pass (used where the producer kernel does not emit partials itself).
 // grid (nslots, 3, B), block (C/4, NY)
 __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink S, int nslots) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float red[];   // [(NY*2 + 2) * C]
-    __shared__ int flag;
     const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
     const int C = S.C, tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
     const int npx = d.rows[plane] * d.cols[plane];
@@ -173,8 +146,6 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink
         }
     }
     stats_block_partial(S, s, q, b, plane, slot, nslots, red);
-    const int tid = ty * blockDim.x + tx;
-    stats_group_tail(S, b, plane, slot, nslots, 1, tid, [] { __syncthreads(); }, &flag);
 }
 
 // -------------------------------------------------------------------------------------
@@ -183,13 +154,8 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink
 // of what they wrote, so the consumer's statistics need no extra pass over the tensor.
 // grid (nslots, 3, B)
 // -------------------------------------------------------------------------------------
-#define S3D_PRODUCER_TAIL(S, s, q, npx, red)                                                                              \
-    if ((S).partial) {                                                                                                    \
-        __shared__ int flag_;                                                                                             \
-        stats_block_partial(S, s, q, b, plane, slot, nslots, red);                                                        \
-        stats_group_tail(S, b, plane, slot, nslots, 1, static_cast<int>(threadIdx.y * blockDim.x + threadIdx.x),          \
-                         [] { __syncthreads(); }, &flag_);                                                                \
-    }
+#define S3D_PRODUCER_TAIL(S, s, q, npx, red) \
+    if ((S).partial) stats_block_partial(S, s, q, b, plane, slot, nslots, red);
 
 __device__ __forceinline__ void acc_sq(float4& s, float4& q, const float4& v) {
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -201,6 +167,8 @@ __device__ __forceinline__ void acc_sq(float4& s, float4& q, const float4& v) {
 // smem: xs[Cin][64], wT[Cin][Cout], bias[Cout], red[(NY*2+2)*Cout]
 __global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, TriDims d, int H, int W, int Dd, int Cin,
                                                  int Cout, TriCF w, TriCF bias, TriF out, StatsSink S, int nslots) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float smi[];
     constexpr int PB = 64;
     const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
@@ -253,6 +221,8 @@ __global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, Tr
 
 // 2x2 average pool, stride 2, floor on odd sizes.  reference unet_triplane.py:127-145.  smem: red[(NY*2+2)*C]
 __global__ void __launch_bounds__(256) k_avgpool2(TriCF x, TriDims din, TriDims dout, int C, TriF out, StatsSink S, int nslots) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float smi[];
     const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
     const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
@@ -291,6 +261,8 @@ __device__ __forceinline__ void bilin_src(int dst, int in_size, float scale, int
 
 __global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, TriCF skip, int Cs, TriDims dout, TriF out,
                                                int do_up, StatsSink S, int nslots) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float smi[];
     const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
     const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
@@ -394,9 +366,11 @@ __device__ __forceinline__ void means_finalize(unsigned long long* sp, __half* m
 }
 
 __global__ void __launch_bounds__(256, 4) k_gn_silu(GnSiluArgs A, int B) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float gsm[];   // coefA[C], coefB[C], red[ny][4][C]
     __shared__ int last_row, last_col;
-    __shared__ double fin[64];
+    __shared__ double fin[64 * 9];
     const int plane = blockIdx.y, b = blockIdx.z;
     const int rows = A.d.rows[plane], cols = A.d.cols[plane], C = A.C;
     const int tx = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
@@ -521,6 +495,8 @@ struct Roll1dArgs {
 };
 
 __global__ void __launch_bounds__(128) k_roll1d(Roll1dArgs A) {
+    pdl_wait();
+    pdl_trigger();
     constexpr int POS = 16, NT = 64;
     extern __shared__ __align__(16) float sm1[];     // means[(POS+2)][C+4]
     const int src_id = blockIdx.y / A.ntn, nt = blockIdx.y - src_id * A.ntn;
@@ -593,6 +569,8 @@ struct ConvFfmaArgs {
 };
 
 __global__ void __launch_bounds__(256) k_conv_ffma(ConvFfmaArgs A, int B) {
+    pdl_wait();
+    pdl_trigger();
     const int plane = blockIdx.y, b = blockIdx.z;
     const int rows = A.d.rows[plane], cols = A.d.cols[plane];
     const int npx = rows * cols;
@@ -647,6 +625,8 @@ __global__ void __launch_bounds__(256) k_conv_ffma(ConvFfmaArgs A, int B) {
 // =====================================================================================
 __global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int Cout, StatsSrc st, TriCF w, TriCF bias,
                                                   float* __restrict__ out, int H, int W, int Dd) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float sm[];   // coefA[C], coefB[C], ws[Cout][C], bs[Cout]
     const int plane = blockIdx.y, b = blockIdx.z;
     const int Hc = H + Dd, Wc = W + Dd;
@@ -665,7 +645,7 @@ __global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int
     float* coefB = sm + C;
     float* ws = sm + 2 * C;
     float* bs = ws + Cout * C;
-    __shared__ double fin[64];
+    __shared__ double fin[64 * 9];
     stats_coef_prologue(st, b, plane, C, static_cast<double>(npx) * (C / kGroups), threadIdx.x, blockDim.x, fin, coefA, coefB);
     for (int k = threadIdx.x; k < Cout * C; k += blockDim.x) ws[k] = w.p[plane][k];
     for (int k = threadIdx.x; k < Cout; k += blockDim.x) bs[k] = bias.p[plane][k];
@@ -705,6 +685,8 @@ __global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int
 // =====================================================================================
 __global__ void k_sinusoid(const float* __restrict__ t, const float* __restrict__ freqs, int half, float* __restrict__ out,
                            int n) {
+    pdl_wait();
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * half) return;
     const int r = i / half, k = i - r * half;
@@ -717,6 +699,8 @@ __global__ void k_sinusoid(const float* __restrict__ t, const float* __restrict_
 __global__ void __launch_bounds__(256) k_linear(const float* __restrict__ x, const float* __restrict__ W,
                                                 const float* __restrict__ bias, float* __restrict__ y, int K, int N,
                                                 int silu_in) {
+    pdl_wait();
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * 8 + warp, r = blockIdx.y;
     if (n >= N) return;
@@ -791,6 +775,8 @@ __device__ __forceinline__ float sched_one(const SchedArgs& A, const float* cf, 
 }
 
 __global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ bool is_last;
     const int b = blockIdx.y;
     const int t = A.t_idx[b];
@@ -860,6 +846,8 @@ __global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
 __global__ void __launch_bounds__(256) k_q_sample(const float* __restrict__ x0, const float* __restrict__ noise,
                                                   float* __restrict__ out, const float* __restrict__ coef,
                                                   const int* __restrict__ t_idx, long long n) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.y, t = t_idx[b];
     const float a = coef[static_cast<size_t>(t) * 12 + 10], s = coef[static_cast<size_t>(t) * 12 + 11];
     const size_t base = static_cast<size_t>(b) * n;
@@ -870,6 +858,8 @@ __global__ void __launch_bounds__(256) k_q_sample(const float* __restrict__ x0, 
 
 __global__ void __launch_bounds__(256) k_philox_normal(float* __restrict__ out, long long n, unsigned long long seed,
                                                        unsigned int sample_base, unsigned int step) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.y;
     const long long n4 = (n + 3) / 4;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;

@@ -45,6 +45,25 @@ struct S3dError {
         if (_e != cudaSuccess) throw S3dError{std::string("launch ") + name + ": " + cudaGetErrorString(_e)}; \
     } while (0)
 
+// ------------------------------------------------------------------------------------ launches
+// Every kernel goes out with programmatic stream serialization (PDL) unless S3D_PDL=0: see pdl_wait()/pdl_trigger().
+static bool g_pdl = true;
+template <typename... KArgs, typename... Args>
+static void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+    if (e != cudaSuccess) throw S3dError{std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e)};
+}
+
 // ------------------------------------------------------------------------------------ driver entry (TMA descriptors)
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -563,18 +582,13 @@ struct PlanBuilder {
     std::shared_ptr<SinkBox> make_box(int C, int nslots) {
         auto bx = std::make_shared<SinkBox>();
         StatsSink& S = bx->s;
-        const int nsg = (nslots + kStatGroup - 1) / kStatGroup;
-        const size_t np = static_cast<size_t>(B) * 3 * nslots * 64, n2 = static_cast<size_t>(B) * 3 * nsg * 64;
-        S.partial = dev_alloc<double>(P->allocs, np);
-        CUDA_TRY(cudaMemset(S.partial, 0, sizeof(double) * np));
-        S.part2 = dev_alloc<double>(P->allocs, n2);
-        CUDA_TRY(cudaMemset(S.part2, 0, sizeof(double) * n2));
-        S.ticket = dev_alloc<unsigned int>(P->allocs, static_cast<size_t>(B) * 3 * nsg);
-        CUDA_TRY(cudaMemset(S.ticket, 0, sizeof(unsigned int) * B * 3 * nsg));
+        const size_t np = static_cast<size_t>(B) * 3 * nslots * 64;
+        S.partial = dev_alloc<float>(P->allocs, np);
+        CUDA_TRY(cudaMemset(S.partial, 0, sizeof(float) * np));
         S.nslots = nslots;
         S.C = C;
-        bx->src.part2 = S.part2;
-        bx->src.nsg = nsg;
+        bx->src.partial = S.partial;
+        bx->src.nslots = nslots;
         bx->src.film_dim = u->film_dim;
         bx->src.film_off = -1;
         return bx;
@@ -617,7 +631,7 @@ struct PlanBuilder {
             add_op("k_gn_stats", 0.0, [=](cudaStream_t s) {
                 const int ny = std::max(1, std::min(16, 1024 / (C / 4)));
                 dim3 grid(nslots, 3, Bv), block(C / 4, ny);
-                k_gn_stats<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, d, S, nslots);
+                launch(k_gn_stats, dim3(grid), dim3(block), sizeof(float) * (ny * 2 + 2) * C, s, xc, d, S, nslots);
                 LAUNCH_CHECK("k_gn_stats");
             });
         }
@@ -657,7 +671,7 @@ struct PlanBuilder {
             GnSiluArgs Al = A;
             Al.st = live_src(st, Pp);
             dim3 grid(gx, 3, Bv), block(bx, ny);
-            k_gn_silu<<<grid, block, smem, s>>>(Al, Bv);
+            launch(k_gn_silu, dim3(grid), dim3(block), smem, s, Al, Bv);
             LAUNCH_CHECK("k_gn_silu");
         });
     }
@@ -721,7 +735,7 @@ struct PlanBuilder {
             const size_t smem = sizeof(float) * static_cast<size_t>(18) * (C + 4);
             add_op("k_roll1d", 0.0, [=](cudaStream_t s) {
                 dim3 grid((Lmax + 15) / 16, 6 * ntn, Bv);
-                k_roll1d<<<grid, 128, smem, s>>>(A);
+                launch(k_roll1d, dim3(grid), dim3(128), smem, s, A);
                 LAUNCH_CHECK("k_roll1d");
             });
             return T;
@@ -758,8 +772,8 @@ struct PlanBuilder {
         }
         add_op("k_roll_tc", 0.0, [=](cudaStream_t s) {
             dim3 grid(total, ntn, Bv);
-            if (nsplit == 3) k_roll_tc<3><<<grid, kRollThreads, ConvTcCfg<3>::kRollSmemBytes, s>>>(*maps, A);
-            else k_roll_tc<1><<<grid, kRollThreads, ConvTcCfg<1>::kRollSmemBytes, s>>>(*maps, A);
+            if (nsplit == 3) launch(k_roll_tc<3>, dim3(grid), dim3(kRollThreads), ConvTcCfg<3>::kRollSmemBytes, s, *maps, A);
+            else launch(k_roll_tc<1>, dim3(grid), dim3(kRollThreads), ConvTcCfg<1>::kRollSmemBytes, s, *maps, A);
             LAUNCH_CHECK("k_roll_tc");
         });
         return T;
@@ -803,7 +817,7 @@ struct PlanBuilder {
                     Al.e.film_row = Pp->film_row;
                 }
                 dim3 grid((mp + 3) / 4, 3, Bv), block(64, 4);
-                k_conv_ffma<<<grid, block, 0, s>>>(Al, Bv);
+                launch(k_conv_ffma, dim3(grid), dim3(block), 0, s, Al, Bv);
                 LAUNCH_CHECK("k_conv_ffma");
             });
             return;
@@ -872,8 +886,8 @@ struct PlanBuilder {
             }
             const int total_tiles = total * ntile_n * Bv + F.n_roll;
             dim3 grid(std::min(total_tiles, num_sms));
-            if (nsplit == 3) k_conv_tc<3><<<grid, kConvThreads, ConvTcCfg<3>::kSmemBytes, s>>>(*maps, *rmaps, Al, F, total_tiles);
-            else k_conv_tc<1><<<grid, kConvThreads, ConvTcCfg<1>::kSmemBytes, s>>>(*maps, *rmaps, Al, F, total_tiles);
+            if (nsplit == 3) launch(k_conv_tc<3>, dim3(grid), dim3(kConvThreads), ConvTcCfg<3>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
+            else launch(k_conv_tc<1>, dim3(grid), dim3(kConvThreads), ConvTcCfg<1>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
             LAUNCH_CHECK("k_conv_tc");
         });
     }
@@ -922,7 +936,7 @@ struct PlanBuilder {
         add_op("k_avgpool2", 0.0, [=](cudaStream_t s) {
             const int ny = std::max(1, 256 / (C / 4));
             dim3 grid(nslots, 3, Bv), block(C / 4, ny);
-            k_avgpool2<<<grid, block, sizeof(float) * (ny * 2 + 2) * C, s>>>(xc, di, dd, C, op, live_sink(box), nslots);
+            launch(k_avgpool2, dim3(grid), dim3(block), sizeof(float) * (ny * 2 + 2) * C, s, xc, di, dd, C, op, live_sink(box), nslots);
             LAUNCH_CHECK("k_avgpool2");
         });
         return o;
@@ -945,7 +959,7 @@ struct PlanBuilder {
         add_op("k_upcat", 0.0, [=](cudaStream_t s) {
             const int ny = std::max(1, 256 / (Ct / 4));
             dim3 grid(nslots, 3, Bv), block(Ct / 4, ny);
-            k_upcat<<<grid, block, sizeof(float) * (ny * 2 + 2) * Ct, s>>>(lc, dl, Cu, sc, Cs, dout, op, do_up ? 1 : 0,
+            launch(k_upcat, dim3(grid), dim3(block), sizeof(float) * (ny * 2 + 2) * Ct, s, lc, dl, Cu, sc, Cs, dout, op, do_up ? 1 : 0,
                                                                            live_sink(box), nslots);
             LAUNCH_CHECK("k_upcat");
         });
@@ -993,7 +1007,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         S3D_CHECK(smem <= 100 * 1024, "k_in_conv shared memory");
         pb.add_op("k_in_conv", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * Cin * c0, [=](cudaStream_t s) {
             dim3 grid(nslots, 3, B), block(c0 / 4, ny);
-            k_in_conv<<<grid, block, smem, s>>>(P->x, d0, H, W, D, Cin, c0, w, bb, op, PlanBuilder::live_sink(box), nslots);
+            launch(k_in_conv, dim3(grid), dim3(block), smem, s, P->x, d0, H, W, D, Cin, c0, w, bb, op, PlanBuilder::live_sink(box), nslots);
             LAUNCH_CHECK("k_in_conv");
         });
     }
@@ -1044,7 +1058,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         S3D_CHECK(smem <= 100 * 1024, "k_out_head shared memory");
         pb.add_op("k_out_head", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * C * Cout, [=](cudaStream_t s) {
             dim3 grid((mp + 127) / 128, 4, B);
-            k_out_head<<<grid, 128, smem, s>>>(xc, d0, C, Cout, PlanBuilder::live_src(st, P), w, bb, P->out, H, W, D);
+            launch(k_out_head, dim3(grid), dim3(128), smem, s, xc, d0, C, Cout, PlanBuilder::live_src(st, P), w, bb, P->out, H, W, D);
             LAUNCH_CHECK("k_out_head");
         });
     }
@@ -1066,13 +1080,13 @@ static void run_film(s3d_unet* u, Plan* P, const float* t_dev, int n, float* fil
     }
     const int mc = u->cfg.model_channels, half = mc / 2, E = u->emb_dim;
     S3D_CHECK(mc % 2 == 0, "odd model_channels");
-    k_sinusoid<<<(n * half + 255) / 256, 256, 0, s>>>(t_dev, u->freqs, half, P->emb_tmp[0], n);
+    launch(k_sinusoid, dim3((n * half + 255) / 256), dim3(256), 0, s, t_dev, u->freqs, half, P->emb_tmp[0], n);
     LAUNCH_CHECK("k_sinusoid");
-    k_linear<<<dim3((E + 7) / 8, n), 256, 0, s>>>(P->emb_tmp[0], u->te_w0, u->te_b0, P->emb_tmp[1], mc, E, 0);
+    launch(k_linear, dim3(dim3((E + 7) / 8, n)), dim3(256), 0, s, P->emb_tmp[0], u->te_w0, u->te_b0, P->emb_tmp[1], mc, E, 0);
     LAUNCH_CHECK("k_linear");
-    k_linear<<<dim3((E + 7) / 8, n), 256, 0, s>>>(P->emb_tmp[1], u->te_w2, u->te_b2, P->emb_tmp[2], E, E, 1);
+    launch(k_linear, dim3(dim3((E + 7) / 8, n)), dim3(256), 0, s, P->emb_tmp[1], u->te_w2, u->te_b2, P->emb_tmp[2], E, E, 1);
     LAUNCH_CHECK("k_linear");
-    k_linear<<<dim3((u->film_dim + 7) / 8, n), 256, 0, s>>>(P->emb_tmp[2], u->film_w, u->film_b, film_dev, E, u->film_dim, 1);
+    launch(k_linear, dim3(dim3((u->film_dim + 7) / 8, n)), dim3(256), 0, s, P->emb_tmp[2], u->film_w, u->film_b, film_dev, E, u->film_dim, 1);
     LAUNCH_CHECK("k_linear");
 }
 
@@ -1085,7 +1099,7 @@ static void launch_sched(const SchedArgs& A, cudaStream_t s) {
     const long long n4 = (A.n + 3) / 4;
     int gx = static_cast<int>(std::min<long long>((n4 + 255) / 256, 148LL * 8));
     gx = std::max(gx, 1);
-    k_sched_step<<<dim3(gx, A.B), 256, 0, s>>>(A);
+    launch(k_sched_step, dim3(dim3(gx, A.B)), dim3(256), 0, s, A);
     LAUNCH_CHECK("k_sched_step");
 }
 
@@ -1124,6 +1138,7 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     u->device = device;
     u->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("S3D_FUSE_ROLL")) u->fuse_roll = atoi(e) != 0;
+    if (const char* e = getenv("S3D_PDL")) g_pdl = atoi(e) != 0;
     if (const char* e = getenv("S3D_HALO_BO_KW")) u->halo_bo_kw = atoi(e) != 0;
     build_structure(u.get());
     *out = u.release();
@@ -1260,7 +1275,7 @@ int s3d_q_sample(const float* x0_dev, const float* noise_dev, float* out_dev, co
     API_BEGIN
     S3D_CHECK(x0_dev && noise_dev && out_dev && coef_dev && t_idx_dev && B >= 1 && n >= 1, "bad argument");
     int gx = static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 8));
-    k_q_sample<<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(x0_dev, noise_dev, out_dev, coef_dev, t_idx_dev, n);
+    launch(k_q_sample, dim3(dim3(gx, B)), dim3(256), 0, static_cast<cudaStream_t>(stream), x0_dev, noise_dev, out_dev, coef_dev, t_idx_dev, n);
     LAUNCH_CHECK("k_q_sample");
     API_END
 }
@@ -1269,7 +1284,7 @@ int s3d_philox_normal(float* out_dev, int B, int64_t n, uint64_t seed, uint32_t 
     API_BEGIN
     S3D_CHECK(out_dev && B >= 1 && n >= 1, "bad argument");
     int gx = static_cast<int>(std::min<long long>(((n + 3) / 4 + 255) / 256, 148LL * 8));
-    k_philox_normal<<<dim3(gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, n, seed, sample_base, step);
+    launch(k_philox_normal, dim3(dim3(gx, B)), dim3(256), 0, static_cast<cudaStream_t>(stream), out_dev, n, seed, sample_base, step);
     LAUNCH_CHECK("k_philox_normal");
     API_END
 }
@@ -1297,7 +1312,7 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
         CUDA_TRY(cudaMemset(P->ticket, 0, sizeof(unsigned int)));
         P->model_out = dev_alloc<float>(P->allocs, static_cast<size_t>(a->B) * n);
     }
-    k_fill_int<<<(a->B + 255) / 256, 256, 0, s>>>(P->t_idx, a->B, a->n_steps - 1);
+    launch(k_fill_int, dim3((a->B + 255) / 256), dim3(256), 0, s, P->t_idx, a->B, a->n_steps - 1);
     LAUNCH_CHECK("k_fill_int");
     P->x = a->x_dev;
     P->out = P->model_out;
