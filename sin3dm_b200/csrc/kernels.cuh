@@ -162,63 +162,6 @@ __device__ __forceinline__ void acc_sq(float4& s, float4& q, const float4& v) {
     q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
 }
 
-// in_conv: per-plane 1x1 conv straight off the composed NCHW boundary tensor.
-// reference src/diffusion/unet_triplane.py:378 (TriplaneConv k=1, no rollout) + triplane_util.py:20-25
-// smem: xs[Cin][64], wT[Cin][Cout], bias[Cout], red[(NY*2+2)*Cout]
-__global__ void __launch_bounds__(256) k_in_conv(const float* __restrict__ x, TriDims d, int H, int W, int Dd, int Cin,
-                                                 int Cout, TriCF w, TriCF bias, TriF out, StatsSink S, int nslots) {
-    pdl_wait();
-    pdl_trigger();
-    extern __shared__ float smi[];
-    constexpr int PB = 64;
-    const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
-    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
-    const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
-    float* xs = smi;
-    float* wT = xs + Cin * PB;
-    float* bs = wT + Cin * Cout;
-    float* red = bs + Cout;
-    const int npx = d.rows[plane] * d.cols[plane];
-    const int ppc = (npx + nslots - 1) / nslots;
-    const int p0 = slot * ppc, p1 = min(npx, p0 + ppc);
-    const int Hc = H + Dd, Wc = W + Dd;
-    const float* xb = x + static_cast<size_t>(b) * Cin * Hc * Wc;
-    for (int i = tid; i < Cin * Cout; i += nthr) {
-        const int c = i / Cout, co = i - c * Cout;
-        wT[i] = w.p[plane][co * Cin + c];
-    }
-    for (int i = tid; i < Cout; i += nthr) bs[i] = bias.p[plane][i];
-    float* op = out.p[plane] + static_cast<size_t>(b) * npx * Cout;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-    for (int pb = p0; pb < p1; pb += PB) {
-        const int nb = min(PB, p1 - pb);
-        __syncthreads();
-        for (int i = tid; i < Cin * PB; i += nthr) {
-            const int c = i / PB, p = i - c * PB;
-            float v = 0.f;
-            if (p < nb) {
-                const int px = pb + p, r = px / d.cols[plane], cc = px - r * d.cols[plane];
-                v = __ldg(xb + static_cast<size_t>(c) * Hc * Wc + composed_offset(plane, r, cc, H, W, Wc));
-            }
-            xs[i] = v;
-        }
-        __syncthreads();
-        const float4 b4 = *reinterpret_cast<const float4*>(bs + tx * 4);
-        for (int p = ty; p < nb; p += NY) {
-            float4 a = b4;
-            for (int c = 0; c < Cin; ++c) {
-                const float xv = xs[c * PB + p];
-                const float4 w4 = *reinterpret_cast<const float4*>(wT + c * Cout + tx * 4);
-                a.x = fmaf(xv, w4.x, a.x); a.y = fmaf(xv, w4.y, a.y); a.z = fmaf(xv, w4.z, a.z); a.w = fmaf(xv, w4.w, a.w);
-            }
-            *reinterpret_cast<float4*>(op + static_cast<size_t>(pb + p) * Cout + tx * 4) = a;
-            acc_sq(s, q, a);
-        }
-    }
-    __syncthreads();
-    S3D_PRODUCER_TAIL(S, s, q, npx, red)
-}
-
 // 2x2 average pool, stride 2, floor on odd sizes.  reference unet_triplane.py:127-145.  smem: red[(NY*2+2)*C]
 __global__ void __launch_bounds__(256) k_avgpool2(TriCF x, TriDims din, TriDims dout, int C, TriF out, StatsSink S, int nslots) {
     pdl_wait();
@@ -407,17 +350,30 @@ __global__ void __launch_bounds__(256, 4) k_gn_silu(GnSiluArgs A, int B) {
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r) {
             if (r < nr) {
-                const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
-                if (xq) store_split4(xq + off, xq + lo_off + off, v[r]);
                 y[r].x = silu_f(fmaf(v[r].x, ca.x, cb.x));
                 y[r].y = silu_f(fmaf(v[r].y, ca.y, cb.y));
                 y[r].z = silu_f(fmaf(v[r].z, ca.z, cb.z));
                 y[r].w = silu_f(fmaf(v[r].w, ca.w, cb.w));
-                store_split4(ap + off, ap + lo_off + off, y[r]);
             }
         }
     }
-    if (!A.sums) return;
+    // The operand stores are issued AFTER the axis-sum atomics and the completion tickets, so the memory fence in front of
+    // the tickets only has the handful of atomics to wait for (the stores need no ordering: the kernel boundary publishes them).
+    auto store_operands = [&]() {
+        if (!cvalid) return;
+#pragma unroll
+        for (int r = 0; r < kGsRows; ++r) {
+            if (r < nr) {
+                const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
+                if (xq) store_split4(xq + off, xq + lo_off + off, v[r]);
+                store_split4(ap + off, ap + lo_off + off, y[r]);
+            }
+        }
+    };
+    if (!A.sums) {
+        store_operands();
+        return;
+    }
     unsigned long long* sb = A.sums + static_cast<size_t>(b) * A.total_len * C;
     unsigned long long* srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
     unsigned long long* scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
@@ -455,6 +411,7 @@ __global__ void __launch_bounds__(256, 4) k_gn_silu(GnSiluArgs A, int B) {
             if (last_col) tk[strips + ct] = 0u;
         }
     }
+    store_operands();                  // overlaps the ticket round trip
     __syncthreads();
     if (!last_row && !last_col) return;
     __threadfence();
@@ -615,67 +572,6 @@ __global__ void __launch_bounds__(256) k_conv_ffma(ConvFfmaArgs A, int B) {
         const size_t oo = (static_cast<size_t>(b) * npx + px) * A.Cout + co;
         if (A.e.resid.p[plane]) acc += A.e.resid.p[plane][oo];
         A.e.out.p[plane][oo] = acc;
-    }
-}
-
-// =====================================================================================
-// out head: GroupNorm + SiLU + 1x1 conv (C -> Cout), written into the composed NCHW boundary tensor,
-// blockIdx.y == 3 zero-fills the D x D corner.  reference unet_triplane.py:441-445, triplane_util.py:7-17
-// grid (ceil(max(max_px, D*D)/128), 4, B), block 128 (one thread per pixel)
-// =====================================================================================
-__global__ void __launch_bounds__(128) k_out_head(TriCF x, TriDims d, int C, int Cout, StatsSrc st, TriCF w, TriCF bias,
-                                                  float* __restrict__ out, int H, int W, int Dd) {
-    pdl_wait();
-    pdl_trigger();
-    extern __shared__ float sm[];   // coefA[C], coefB[C], ws[Cout][C], bs[Cout]
-    const int plane = blockIdx.y, b = blockIdx.z;
-    const int Hc = H + Dd, Wc = W + Dd;
-    float* ob = out + static_cast<size_t>(b) * Cout * Hc * Wc;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (plane == 3) {
-        if (i < Dd * Dd) {
-            int r = i / Dd, c = i - r * Dd;
-            for (int co = 0; co < Cout; ++co) ob[(static_cast<size_t>(co) * Hc + H + r) * Wc + W + c] = 0.f;
-        }
-        return;
-    }
-    const int rows = d.rows[plane], cols = d.cols[plane], npx = rows * cols;
-    if (blockIdx.x * blockDim.x >= npx) return;
-    float* coefA = sm;
-    float* coefB = sm + C;
-    float* ws = sm + 2 * C;
-    float* bs = ws + Cout * C;
-    __shared__ double fin[64 * 9];
-    stats_coef_prologue(st, b, plane, C, static_cast<double>(npx) * (C / kGroups), threadIdx.x, blockDim.x, fin, coefA, coefB);
-    for (int k = threadIdx.x; k < Cout * C; k += blockDim.x) ws[k] = w.p[plane][k];
-    for (int k = threadIdx.x; k < Cout; k += blockDim.x) bs[k] = bias.p[plane][k];
-    __syncthreads();
-    if (i >= npx) return;
-    const int r = i / cols, c = i - r * cols;
-    const float4* xp = reinterpret_cast<const float4*>(x.p[plane] + (static_cast<size_t>(b) * npx + i) * C);
-    float acc[16];
-    float* op = ob + composed_offset(plane, r, c, H, W, Wc);
-    for (int co0 = 0; co0 < Cout; co0 += 16) {
-        const int nco = min(16, Cout - co0);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = k < nco ? bs[co0 + k] : 0.f;
-        for (int v = 0; v < C / 4; ++v) {
-            float4 t = __ldg(xp + v);
-            float y0 = silu_f(fmaf(t.x, coefA[4 * v], coefB[4 * v]));
-            float y1 = silu_f(fmaf(t.y, coefA[4 * v + 1], coefB[4 * v + 1]));
-            float y2 = silu_f(fmaf(t.z, coefA[4 * v + 2], coefB[4 * v + 2]));
-            float y3 = silu_f(fmaf(t.w, coefA[4 * v + 3], coefB[4 * v + 3]));
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if (k < nco) {
-                    const float* wk = ws + (co0 + k) * C + 4 * v;
-                    acc[k] = fmaf(y0, wk[0], fmaf(y1, wk[1], fmaf(y2, wk[2], fmaf(y3, wk[3], acc[k]))));
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (k < nco) op[static_cast<size_t>(co0 + k) * Hc * Wc] = acc[k];
     }
 }
 
@@ -867,6 +763,204 @@ __global__ void __launch_bounds__(256) k_philox_normal(float* __restrict__ out, 
         float4 z = philox_normal4(seed, sample_base + b, step, static_cast<uint32_t>(i));
         float zz[4] = {z.x, z.y, z.z, z.w};
         for (int k = 0; k < 4 && i * 4 + k < n; ++k) out[static_cast<size_t>(b) * n + i * 4 + k] = zz[k];
+    }
+}
+
+
+// =====================================================================================
+// Step boundary: the output head, the scheduler update and the next step's input conv are all per-pixel maps, so the
+// sampling loop runs them as ONE kernel (MODE_FUSED); the stand-alone forward uses the same code as two kernels
+// (MODE_INCONV at the start, MODE_HEAD at the end), which keeps both paths bit-identical.
+//   head   : GroupNorm + SiLU + 1x1 conv C0 -> Cf, composed NCHW output        reference unet_triplane.py:441-445
+//   sched  : DDPM / DDIM update of x with the model output of this pixel        (see k_sched_step)
+//   in_conv: 1x1 conv Cf -> C0 off the composed tensor + GroupNorm partials      reference unet_triplane.py:378
+// A pixel is handled by LG = C0/4 adjacent lanes (4 channels each, LG in {16, 32}); the Cf-wide dot products are reduced
+// with xor-shuffles inside the lane group.  grid (nslots, 4, B): blockIdx.y == 3 is the dead D x D corner, which the
+// network never sees (zero model output) but the sampler still evolves.  block (LG, 256/LG).
+// smem: coefA[C0], coefB[C0], wout[Cf][C0], bout[Cf], win[Cf][C0], bin[C0], red[(NY*2+2)*C0]
+// =====================================================================================
+enum { MODE_HEAD = 0, MODE_INCONV = 1, MODE_FUSED = 2 };
+constexpr int kMaxCf = 16;
+
+struct BoundaryArgs {
+    TriCF h;              // last activation [B][rows][cols][C0]                  (HEAD / FUSED)
+    TriDims d;
+    int C0, Cf, H, W, Dd;
+    StatsSrc st;          // statistics of h + out-norm parameters
+    TriCF w_out, b_out;   // [Cf][C0], [Cf]
+    float* model_out;     // composed [B][Cf][H+D][W+D]                           (HEAD)
+    const float* x_in;    // composed input                                        (INCONV)
+    TriCF w_in, b_in;     // [C0][Cf], [C0]
+    TriF h0;              // in_conv output [B][rows][cols][C0]                    (INCONV / FUSED)
+    StatsSink sink;       // GroupNorm partials of h0
+    SchedArgs sch;        // x, sample (in place), coefficient table, step index   (FUSED)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ float smb[];
+    __shared__ double fin[64 * 9];
+    __shared__ bool is_last;
+    const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
+    const int C0 = A.C0, Cf = A.Cf, LG = blockDim.x, NY = blockDim.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * LG + tx, nthr = LG * NY;
+    const int Hc = A.H + A.Dd, Wc = A.W + A.Dd;
+    const long long nper = static_cast<long long>(Cf) * Hc * Wc;
+    float* coefA = smb;
+    float* coefB = coefA + C0;
+    float* wout = coefB + C0;           // [Cf][C0]
+    float* bout = wout + Cf * C0;       // [Cf]
+    float* win = bout + Cf;             // [Cf][C0]  (transposed: win[c][co])
+    float* bin = win + Cf * C0;         // [C0]
+    float* red = bin + C0;
+
+    // scheduler scalars of this sample (FUSED)
+    int t = 0;
+    float cf[12];
+    float nz = 0.f;
+    if (MODE == MODE_FUSED) {
+        t = A.sch.t_idx[b];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) cf[k] = __ldg(A.sch.coef + static_cast<size_t>(t) * 12 + k);
+        nz = t != 0 ? 1.f : 0.f;
+    }
+    auto sched_elem = [&](long long e, float mo) -> float {       // e: element index inside the sample; returns x_{t-1}
+        const size_t gi = static_cast<size_t>(b) * nper + e;
+        const float xo = A.sch.x[gi];
+        float nv = 0.f;
+        if (A.sch.noise) {
+            nv = A.sch.noise[static_cast<size_t>(t) * A.sch.noise_step_stride + gi];
+        } else {
+            const float4 z = philox_normal4(A.sch.seed, A.sch.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(e >> 2));
+            const int k = static_cast<int>(e & 3);
+            nv = k == 0 ? z.x : (k == 1 ? z.y : (k == 2 ? z.z : z.w));
+        }
+        const float y0 = A.sch.y0 ? A.sch.y0[gi] : 0.f, mk = A.sch.y0 ? A.sch.mask[gi] : 0.f;
+        float x0;
+        const float xn = sched_one(A.sch, cf, nz, mo, xo, nv, y0, mk, x0);
+        A.sch.sample[gi] = xn;
+        if (A.sch.x0_out) A.sch.x0_out[gi] = x0;
+        return xn;
+    };
+
+    if (plane == 3) {
+        // ---- dead corner [H:, W:]: zero model output
+        const int ncorner = A.Dd * A.Dd;
+        const int per = (ncorner + nslots - 1) / nslots;
+        const int e0 = slot * per, e1 = min(ncorner, e0 + per);
+        if (MODE != MODE_INCONV) {
+            for (int i = e0 + tid; i < e1; i += nthr) {
+                const int r = i / A.Dd, c = i - r * A.Dd;
+                for (int co = 0; co < Cf; ++co) {
+                    const long long e = (static_cast<long long>(co) * Hc + A.H + r) * Wc + A.W + c;
+                    if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + e] = 0.f;
+                    else sched_elem(e, 0.f);
+                }
+            }
+        }
+    } else {
+        const int rows = A.d.rows[plane], cols = A.d.cols[plane], npx = rows * cols;
+        const int ppc = (npx + nslots - 1) / nslots;
+        const int p0 = slot * ppc, p1 = min(npx, p0 + ppc);
+        // ---- per-CTA constants
+        if (MODE != MODE_INCONV) {
+            for (int i = tid; i < Cf * C0; i += nthr) wout[i] = A.w_out.p[plane][i];
+            for (int i = tid; i < Cf; i += nthr) bout[i] = A.b_out.p[plane][i];
+            stats_coef_prologue(A.st, b, plane, C0, static_cast<double>(npx) * (C0 / kGroups), tid, nthr, fin, coefA, coefB);
+        }
+        if (MODE != MODE_HEAD) {
+            for (int i = tid; i < Cf * C0; i += nthr) {
+                const int c = i / C0, co = i - c * C0;
+                win[i] = A.w_in.p[plane][co * Cf + c];
+            }
+            for (int i = tid; i < C0; i += nthr) bin[i] = A.b_in.p[plane][i];
+        }
+        __syncthreads();
+        float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), cb = ca;
+        if (MODE != MODE_INCONV) {
+            ca = *reinterpret_cast<const float4*>(coefA + tx * 4);
+            cb = *reinterpret_cast<const float4*>(coefB + tx * 4);
+        }
+        const float* hp = MODE != MODE_INCONV ? A.h.p[plane] + static_cast<size_t>(b) * npx * C0 : nullptr;
+        float* h0p = MODE != MODE_HEAD ? A.h0.p[plane] + static_cast<size_t>(b) * npx * C0 : nullptr;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+        // all lanes of a group walk the same pixels; groups whose pixel is out of range still run the shuffles
+        for (int pb = p0; pb < p1; pb += NY) {
+            const int px = pb + ty;
+            const bool pv = px < p1;
+            const int r = pv ? px / cols : 0, c = pv ? px - r * cols : 0;
+            const long long pe = composed_offset(plane, r, c, A.H, A.W, Wc);     // offset inside one channel image
+            float xn_mine = 0.f;                                                 // lane co < Cf: new x of channel co
+            if (MODE != MODE_INCONV) {
+                float part[kMaxCf];
+                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pv) {
+                    const float4 hv = __ldg(reinterpret_cast<const float4*>(hp + static_cast<size_t>(px) * C0) + tx);
+                    y.x = silu_f(fmaf(hv.x, ca.x, cb.x));
+                    y.y = silu_f(fmaf(hv.y, ca.y, cb.y));
+                    y.z = silu_f(fmaf(hv.z, ca.z, cb.z));
+                    y.w = silu_f(fmaf(hv.w, ca.w, cb.w));
+                }
+#pragma unroll
+                for (int co = 0; co < kMaxCf; ++co) {
+                    if (co < Cf) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wout + co * C0 + tx * 4);
+                        part[co] = fmaf(y.x, w4.x, fmaf(y.y, w4.y, fmaf(y.z, w4.z, y.w * w4.w)));
+                    }
+                }
+                for (int off = LG >> 1; off > 0; off >>= 1) {
+#pragma unroll
+                    for (int co = 0; co < kMaxCf; ++co)
+                        if (co < Cf) part[co] += __shfl_xor_sync(0xffffffffu, part[co], off, LG);
+                }
+                // lane co owns output channel co of this pixel
+                float mo = 0.f;
+#pragma unroll
+                for (int co = 0; co < kMaxCf; ++co)
+                    if (co < Cf && tx == co) mo = part[co] + bout[co];
+                if (pv && tx < Cf) {
+                    const long long e = static_cast<long long>(tx) * Hc * Wc + pe;
+                    if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + e] = mo;
+                    else xn_mine = sched_elem(e, mo);
+                }
+            } else if (pv && tx < Cf) {
+                xn_mine = __ldg(A.x_in + static_cast<size_t>(b) * nper + static_cast<long long>(tx) * Hc * Wc + pe);
+            }
+            if (MODE != MODE_HEAD) {
+                float4 a = *reinterpret_cast<const float4*>(bin + tx * 4);
+#pragma unroll
+                for (int cc = 0; cc < kMaxCf; ++cc) {
+                    if (cc < Cf) {
+                        const float xv = __shfl_sync(0xffffffffu, xn_mine, cc, LG);
+                        const float4 w4 = *reinterpret_cast<const float4*>(win + cc * C0 + tx * 4);
+                        a.x = fmaf(xv, w4.x, a.x); a.y = fmaf(xv, w4.y, a.y); a.z = fmaf(xv, w4.z, a.z); a.w = fmaf(xv, w4.w, a.w);
+                    }
+                }
+                if (pv) {
+                    *reinterpret_cast<float4*>(h0p + static_cast<size_t>(px) * C0 + tx * 4) = a;
+                    acc_sq(s, q, a);
+                }
+            }
+        }
+        if (MODE != MODE_HEAD && A.sink.partial) {
+            __syncthreads();
+            stats_block_partial(A.sink, s, q, b, plane, slot, nslots, red);
+        }
+    }
+    if (MODE == MODE_FUSED && A.sch.advance) {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int prev = atomicAdd(A.sch.ticket, 1u);
+            is_last = prev == gridDim.x * gridDim.y * gridDim.z - 1;
+        }
+        __syncthreads();
+        if (is_last && tid == 0) {
+            for (int k = 0; k < A.sch.B; ++k) A.sch.t_idx[k] -= 1;
+            *A.sch.ticket = 0u;
+        }
     }
 }
 

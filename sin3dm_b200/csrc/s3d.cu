@@ -46,8 +46,8 @@ struct S3dError {
     } while (0)
 
 // ------------------------------------------------------------------------------------ launches
-// Every kernel goes out with programmatic stream serialization (PDL) unless S3D_PDL=0: see pdl_wait()/pdl_trigger().
-static bool g_pdl = true;
+// S3D_PDL=1 sends every kernel out with programmatic stream serialization (PDL): see pdl_wait()/pdl_trigger().
+static bool g_pdl = false;     // measured on B200 (r1): PDL on every launch is ~2.5% slower than plain graph edges at batch 1
 template <typename... KArgs, typename... Args>
 static void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg{};
@@ -173,6 +173,7 @@ struct Plan {
     size_t alloc_bytes = 0;
     std::vector<void*> allocs;
     std::vector<NamedBuf> named;
+    std::function<void(cudaStream_t, const SchedArgs&)> fused_boundary;   // out head + scheduler + next in_conv (sampling loop)
     float* film_own = nullptr;      // [B][film_dim] used by s3d_unet_forward
     float* emb_tmp[3] = {};         // scratch for the embedding MLP (grown on demand)
     int emb_rows = 0;
@@ -479,8 +480,6 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_roll1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kRollSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kRollSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_out_head, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_in_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaDeviceSynchronize());
     u->finalized = true;
 }
@@ -992,23 +991,32 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     // ---- in_conv
     const int c0 = ch_of(c, 0);
     ActF h = pb.allocF(0, c0, "in_conv");
+    S3D_CHECK(c0 / 4 == 16 || c0 / 4 == 32, "channel_mult[0] * model_channels must be 64 or 128 (boundary kernels use one lane group per pixel)");
+    S3D_CHECK(c.in_channels <= kMaxCf && c.out_channels <= kMaxCf, "at most 16 triplane channels are supported");
+    const int bnd_lg = c0 / 4, bnd_ny = 256 / bnd_lg;
+    const int bnd_slots = std::max(1, std::min(128, pb.max_px(0) / 64));
+    auto bnd_smem = [&](int Cf) {
+        return sizeof(float) * (static_cast<size_t>(2) * c0 + 2 * static_cast<size_t>(Cf) * c0 + Cf + c0 + static_cast<size_t>(bnd_ny * 2 + 2) * c0);
+    };
+    BoundaryArgs bnd{};      // fields shared by the three modes
+    bnd.d = pb.dims[0];
+    bnd.C0 = c0;
+    bnd.H = H; bnd.W = W; bnd.Dd = D;
+    bnd.w_in = PlanBuilder::cf3(u->in_w);
+    bnd.b_in = PlanBuilder::cf3(u->in_b);
+    bnd.h0 = h.p;
+    auto in_box = pb.make_box(c0, bnd_slots);
+    h.sink = in_box;
     {
-        const TriDims d0 = pb.dims[0];
         const int Cin = c.in_channels;
-        TriCF w = PlanBuilder::cf3(u->in_w), bb = PlanBuilder::cf3(u->in_b);
-        TriF op = h.p;
-        const int nslots = std::max(1, std::min(128, pb.max_px(0) / 64));
-        auto box = pb.make_box(c0, nslots);
-        h.sink = box;
-        S3D_CHECK(c0 / 4 <= 256, "channel count too large for k_in_conv");
-        const int ny = std::max(1, 256 / (c0 / 4));
-        const size_t smem = sizeof(float) * (static_cast<size_t>(Cin) * 64 + static_cast<size_t>(Cin) * c0 + c0 +
-                                             static_cast<size_t>(ny * 2 + 2) * c0);
-        S3D_CHECK(smem <= 100 * 1024, "k_in_conv shared memory");
-        pb.add_op("k_in_conv", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * Cin * c0, [=](cudaStream_t s) {
-            dim3 grid(nslots, 3, B), block(c0 / 4, ny);
-            launch(k_in_conv, dim3(grid), dim3(block), smem, s, P->x, d0, H, W, D, Cin, c0, w, bb, op, PlanBuilder::live_sink(box), nslots);
-            LAUNCH_CHECK("k_in_conv");
+        const size_t smem = bnd_smem(Cin);
+        pb.add_op("k_boundary<in_conv>", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * Cin * c0, [=](cudaStream_t s) {
+            BoundaryArgs Al = bnd;
+            Al.Cf = Cin;
+            Al.x_in = P->x;
+            Al.sink = PlanBuilder::live_sink(in_box);
+            launch(k_boundary<MODE_INCONV>, dim3(bnd_slots, 3, B), dim3(bnd_lg, bnd_ny), smem, s, Al, bnd_slots);
+            LAUNCH_CHECK("k_boundary<in_conv>");
         });
     }
     // ---- encoder
@@ -1046,21 +1054,35 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         }
     }
     S3D_CHECK(!pending_up && h.level == 0, "decoder structure");
-    // ---- out head
+    // ---- out head (stand-alone forward) and the fused step boundary (sampling loop)
     auto st = pb.stats(h, u->out_norm, -1);
     {
-        const TriDims d0 = pb.dims[0];
-        const int C = h.C, Cout = c.out_channels;
-        TriCF xc = PlanBuilder::cf(h.p);
-        TriCF w = PlanBuilder::cf3(u->out_w), bb = PlanBuilder::cf3(u->out_b);
-        const int mp = std::max(pb.max_px(0), D * D);
-        const size_t smem = sizeof(float) * (2 * C + static_cast<size_t>(Cout) * C + Cout);
-        S3D_CHECK(smem <= 100 * 1024, "k_out_head shared memory");
-        pb.add_op("k_out_head", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * C * Cout, [=](cudaStream_t s) {
-            dim3 grid((mp + 127) / 128, 4, B);
-            launch(k_out_head, dim3(grid), dim3(128), smem, s, xc, d0, C, Cout, PlanBuilder::live_src(st, P), w, bb, P->out, H, W, D);
-            LAUNCH_CHECK("k_out_head");
+        const int Cout = c.out_channels;
+        S3D_CHECK(h.C == c0, "decoder output width");
+        BoundaryArgs bo = bnd;
+        bo.h = PlanBuilder::cf(h.p);
+        bo.w_out = PlanBuilder::cf3(u->out_w);
+        bo.b_out = PlanBuilder::cf3(u->out_b);
+        const size_t smem = bnd_smem(Cout);
+        pb.add_op("k_boundary<head>", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * c0 * Cout, [=](cudaStream_t s) {
+            BoundaryArgs Al = bo;
+            Al.Cf = Cout;
+            Al.st = PlanBuilder::live_src(st, P);
+            Al.model_out = P->out;
+            launch(k_boundary<MODE_HEAD>, dim3(bnd_slots, 4, B), dim3(bnd_lg, bnd_ny), smem, s, Al, bnd_slots);
+            LAUNCH_CHECK("k_boundary<head>");
         });
+        if (c.in_channels == c.out_channels) {
+            P->fused_boundary = [=](cudaStream_t s, const SchedArgs& sch) {
+                BoundaryArgs Al = bo;
+                Al.Cf = Cout;
+                Al.st = PlanBuilder::live_src(st, P);
+                Al.sink = PlanBuilder::live_sink(in_box);
+                Al.sch = sch;
+                launch(k_boundary<MODE_FUSED>, dim3(bnd_slots, 4, B), dim3(bnd_lg, bnd_ny), smem, s, Al, bnd_slots);
+                LAUNCH_CHECK("k_boundary<fused>");
+            };
+        }
     }
     CUDA_TRY(cudaDeviceSynchronize());
 }
@@ -1339,18 +1361,28 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
     A.sample_base = a->sample_base;
     A.advance = 1;
     A.ticket = P->ticket;
+    // Loop structure: in_conv once, then per step [blocks ..., fused (out head + scheduler + next step's in_conv)].
+    const bool fused = static_cast<bool>(P->fused_boundary) && !getenv("S3D_NO_FUSED_BOUNDARY");
+    const size_t nops = P->ops.size();
     auto one_step = [&](cudaStream_t st) {
-        run_ops(u, P, st);
-        launch_sched(A, st);
+        if (fused) {
+            for (size_t i = 1; i + 1 < nops; ++i) P->ops[i](st);
+            P->fused_boundary(st, A);
+        } else {
+            run_ops(u, P, st);
+            launch_sched(A, st);
+        }
     };
+    if (fused) P->ops[0](s);
     if (!a->use_graph) {
         for (int i = 0; i < a->n_steps; ++i) one_step(s);
     } else {
         // The graph bakes every pointer and scalar of one step; only the step index (device memory) changes.
         char key[512];
-        snprintf(key, sizeof(key), "%d|%d|%d|%d|%p|%p|%p|%p|%p|%p|%p|%llu|%u", a->kind, a->mean_type, a->clip_denoised,
+        snprintf(key, sizeof(key), "%d|%d|%d|%d|%p|%p|%p|%p|%p|%p|%p|%llu|%u|%d", a->kind, a->mean_type, a->clip_denoised,
                  a->is_mask_t0, (void*)a->x_dev, (void*)a->pred_xstart_dev, (void*)a->coef_dev, (void*)a->film_dev,
-                 (void*)a->step_noise_dev, (void*)a->y0_dev, (void*)a->mask_dev, (unsigned long long)a->seed, a->sample_base);
+                 (void*)a->step_noise_dev, (void*)a->y0_dev, (void*)a->mask_dev, (unsigned long long)a->seed, a->sample_base,
+                 fused ? 1 : 0);
         if (!P->graph_exec || P->graph_key != key) {
             if (P->graph_exec) {
                 cudaGraphExecDestroy(P->graph_exec);
@@ -1379,8 +1411,8 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
             P->graph_key = key;
         }
         for (int i = 0; i < a->n_steps; ++i) CUDA_TRY(cudaGraphLaunch(P->graph_exec, s));
-        u->last_launches = static_cast<int>(P->ops.size());
     }
+    u->last_launches = fused ? static_cast<int>(nops) - 2 : static_cast<int>(nops);
     u->last_launches += 1;   // scheduler kernel
     API_END
 }
