@@ -70,12 +70,13 @@ __device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, in
     }
     __syncthreads();
     const int cpg = C / kGroups;
+    const double inv_n = 1.0 / n_per_group;
     for (int c = tid; c < C; c += nthr) {
         const int g = c / cpg;
-        const double mean = fin[g * 2] / n_per_group;
-        double var = fin[g * 2 + 1] / n_per_group - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kGnEps)));
+        // E[x^2] - mean^2 is formed in fp64 (cancellation), the rest in fp32 like torch's GroupNorm
+        const double mean = fin[g * 2] * inv_n;
+        const float var = fmaxf(static_cast<float>(fin[g * 2 + 1] * inv_n - mean * mean), 0.f);
+        const float rstd = rsqrtf(var + kGnEps);
         const bool first = c == tid;
         float ga = (first ? g0 : S.gamma.p[plane][c]) * rstd;
         float be = (first ? b0 : S.beta.p[plane][c]) - static_cast<float>(mean) * ga;
@@ -263,15 +264,15 @@ __global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, 
 // =====================================================================================
 // Fused GroupNorm-apply (+FiLM) + SiLU -> fp16 (hi, lo) conv operand, plus the rollout axis means.
 // reference unet_triplane.py:63-95 (norm, SiLU), :285-297 (FiLM), :37-46 (axis means)
-// One CTA = a 4-row x ny-column tile of one plane of one sample (one column per thread: many small CTAs keep
-// enough loads in flight at batch 1).  grid (max tiles, 3, B), block (C/4, ny).
+// One CTA = an 8-row x ny-column tile of one plane of one sample (one column per thread, 8 independent loads in flight;
+// the per-CTA statistics prologue is amortised over 8 rows).  grid (max tiles, 3, B), block (C/4, ny).
 // Axis sums are accumulated as 64-bit fixed point (value * 2^24) with integer atomics: exact, hence independent of
 // tile order / batch composition / GPU count.  sums[b][seg_off[plane*2+kind] + pos][C], kind 0 = sum over columns
 // (indexed by row), kind 1 = sum over rows (indexed by column).  The CTA that completes a row strip / a column tile
 // (per-strip and per-column-tile tickets) turns those sums into fp16 (hi, lo) means [2][B][total_len][C] — the A operand
 // of the rollout 1-D GEMM — and re-zeroes them, so no separate finalize / memset pass exists.
 // =====================================================================================
-constexpr int kGsRows = 4;
+constexpr int kGsRows = 8;
 constexpr float kFixScale = 16777216.f;          // 2^24
 constexpr double kFixInv = 1.0 / 16777216.0;
 
@@ -308,7 +309,7 @@ __device__ __forceinline__ void means_finalize(unsigned long long* sp, __half* m
     }
 }
 
-__global__ void __launch_bounds__(256, 4) k_gn_silu(GnSiluArgs A, int B) {
+__global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
     pdl_wait();
     pdl_trigger();
     extern __shared__ float gsm[];   // coefA[C], coefB[C], red[ny][4][C]
@@ -378,11 +379,11 @@ __global__ void __launch_bounds__(256, 4) k_gn_silu(GnSiluArgs A, int B) {
     unsigned long long* srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
     unsigned long long* scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
     if (cvalid) {
-        float4 cacc;
-        cacc.x = (y[0].x + y[1].x) + (y[2].x + y[3].x);
-        cacc.y = (y[0].y + y[1].y) + (y[2].y + y[3].y);
-        cacc.z = (y[0].z + y[1].z) + (y[2].z + y[3].z);
-        cacc.w = (y[0].w + y[1].w) + (y[2].w + y[3].w);
+        float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kGsRows; ++r) {
+            cacc.x += y[r].x; cacc.y += y[r].y; cacc.z += y[r].z; cacc.w += y[r].w;
+        }
         unsigned long long* p = scol + static_cast<size_t>(c) * C + tx * 4;
         fix_add(p, cacc.x); fix_add(p + 1, cacc.y); fix_add(p + 2, cacc.z); fix_add(p + 3, cacc.w);
     }
@@ -827,9 +828,8 @@ __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
         for (int k = 0; k < 12; ++k) cf[k] = __ldg(A.sch.coef + static_cast<size_t>(t) * 12 + k);
         nz = t != 0 ? 1.f : 0.f;
     }
-    auto sched_elem = [&](long long e, float mo) -> float {       // e: element index inside the sample; returns x_{t-1}
+    auto sched_elem = [&](long long e, float mo, float xo) -> float {   // e: element index inside the sample; returns x_{t-1}
         const size_t gi = static_cast<size_t>(b) * nper + e;
-        const float xo = A.sch.x[gi];
         float nv = 0.f;
         if (A.sch.noise) {
             nv = A.sch.noise[static_cast<size_t>(t) * A.sch.noise_step_stride + gi];
@@ -852,12 +852,27 @@ __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
         const int per = (ncorner + nslots - 1) / nslots;
         const int e0 = slot * per, e1 = min(ncorner, e0 + per);
         if (MODE != MODE_INCONV) {
-            for (int i = e0 + tid; i < e1; i += nthr) {
-                const int r = i / A.Dd, c = i - r * A.Dd;
-                for (int co = 0; co < Cf; ++co) {
-                    const long long e = (static_cast<long long>(co) * Hc + A.H + r) * Wc + A.W + c;
-                    if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + e] = 0.f;
-                    else sched_elem(e, 0.f);
+            const int nitems = (e1 - e0) * Cf;
+            for (int i0 = 0; i0 < nitems; i0 += nthr * 4) {
+                long long ee[4];
+                float xo[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = i0 + k * nthr + tid;
+                    ee[k] = -1;
+                    xo[k] = 0.f;
+                    if (i < nitems) {
+                        const int co = i / (e1 - e0), el = e0 + (i - co * (e1 - e0));
+                        const int r = el / A.Dd, c = el - r * A.Dd;
+                        ee[k] = (static_cast<long long>(co) * Hc + A.H + r) * Wc + A.W + c;
+                        if (MODE == MODE_FUSED) xo[k] = A.sch.x[static_cast<size_t>(b) * nper + ee[k]];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (ee[k] < 0) continue;
+                    if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + ee[k]] = 0.f;
+                    else sched_elem(ee[k], 0.f, xo[k]);
                 }
             }
         }
@@ -887,61 +902,81 @@ __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
         const float* hp = MODE != MODE_INCONV ? A.h.p[plane] + static_cast<size_t>(b) * npx * C0 : nullptr;
         float* h0p = MODE != MODE_HEAD ? A.h0.p[plane] + static_cast<size_t>(b) * npx * C0 : nullptr;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-        // all lanes of a group walk the same pixels; groups whose pixel is out of range still run the shuffles
-        for (int pb = p0; pb < p1; pb += NY) {
-            const int px = pb + ty;
-            const bool pv = px < p1;
-            const int r = pv ? px / cols : 0, c = pv ? px - r * cols : 0;
-            const long long pe = composed_offset(plane, r, c, A.H, A.W, Wc);     // offset inside one channel image
-            float xn_mine = 0.f;                                                 // lane co < Cf: new x of channel co
-            if (MODE != MODE_INCONV) {
-                float part[kMaxCf];
-                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pv) {
-                    const float4 hv = __ldg(reinterpret_cast<const float4*>(hp + static_cast<size_t>(px) * C0) + tx);
-                    y.x = silu_f(fmaf(hv.x, ca.x, cb.x));
-                    y.y = silu_f(fmaf(hv.y, ca.y, cb.y));
-                    y.z = silu_f(fmaf(hv.z, ca.z, cb.z));
-                    y.w = silu_f(fmaf(hv.w, ca.w, cb.w));
-                }
+        // All lanes of a group walk the same pixels; groups whose pixel is out of range still run the shuffles.
+        // Pixels are taken NPB at a time with every global load of the batch issued first: the loop body ends in stores
+        // to buffers the compiler cannot prove distinct from the inputs, so without this the iterations serialise on
+        // two L2 round trips each.
+        constexpr int NPB = 4;
+        for (int pb = p0; pb < p1; pb += NY * NPB) {
+            float4 hv[NPB];
+            float xo[NPB];
+            long long pe[NPB];
+            bool pv[NPB];
 #pragma unroll
-                for (int co = 0; co < kMaxCf; ++co) {
-                    if (co < Cf) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(wout + co * C0 + tx * 4);
-                        part[co] = fmaf(y.x, w4.x, fmaf(y.y, w4.y, fmaf(y.z, w4.z, y.w * w4.w)));
+            for (int j = 0; j < NPB; ++j) {
+                const int px = pb + j * NY + ty;
+                pv[j] = px < p1;
+                const int r = pv[j] ? px / cols : 0, c = pv[j] ? px - r * cols : 0;
+                pe[j] = composed_offset(plane, r, c, A.H, A.W, Wc);     // offset inside one channel image
+                hv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xo[j] = 0.f;
+                if (pv[j]) {
+                    if (MODE != MODE_INCONV) hv[j] = __ldg(reinterpret_cast<const float4*>(hp + static_cast<size_t>(px) * C0) + tx);
+                    if (tx < Cf) {
+                        const size_t gi = static_cast<size_t>(b) * nper + static_cast<long long>(tx) * Hc * Wc + pe[j];
+                        if (MODE == MODE_INCONV) xo[j] = __ldg(A.x_in + gi);
+                        if (MODE == MODE_FUSED) xo[j] = A.sch.x[gi];
                     }
                 }
-                for (int off = LG >> 1; off > 0; off >>= 1) {
+            }
+#pragma unroll
+            for (int j = 0; j < NPB; ++j) {
+                const int px = pb + j * NY + ty;
+                float xn_mine = xo[j];                                           // lane co < Cf: (new) x of channel co
+                if (MODE != MODE_INCONV) {
+                    float part[kMaxCf];
+                    float4 y;
+                    y.x = silu_f(fmaf(hv[j].x, ca.x, cb.x));
+                    y.y = silu_f(fmaf(hv[j].y, ca.y, cb.y));
+                    y.z = silu_f(fmaf(hv[j].z, ca.z, cb.z));
+                    y.w = silu_f(fmaf(hv[j].w, ca.w, cb.w));
+#pragma unroll
+                    for (int co = 0; co < kMaxCf; ++co) {
+                        if (co < Cf) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(wout + co * C0 + tx * 4);
+                            part[co] = fmaf(y.x, w4.x, fmaf(y.y, w4.y, fmaf(y.z, w4.z, y.w * w4.w)));
+                        }
+                    }
+                    for (int off = LG >> 1; off > 0; off >>= 1) {
+#pragma unroll
+                        for (int co = 0; co < kMaxCf; ++co)
+                            if (co < Cf) part[co] += __shfl_xor_sync(0xffffffffu, part[co], off, LG);
+                    }
+                    // lane co owns output channel co of this pixel
+                    float mo = 0.f;
 #pragma unroll
                     for (int co = 0; co < kMaxCf; ++co)
-                        if (co < Cf) part[co] += __shfl_xor_sync(0xffffffffu, part[co], off, LG);
-                }
-                // lane co owns output channel co of this pixel
-                float mo = 0.f;
-#pragma unroll
-                for (int co = 0; co < kMaxCf; ++co)
-                    if (co < Cf && tx == co) mo = part[co] + bout[co];
-                if (pv && tx < Cf) {
-                    const long long e = static_cast<long long>(tx) * Hc * Wc + pe;
-                    if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + e] = mo;
-                    else xn_mine = sched_elem(e, mo);
-                }
-            } else if (pv && tx < Cf) {
-                xn_mine = __ldg(A.x_in + static_cast<size_t>(b) * nper + static_cast<long long>(tx) * Hc * Wc + pe);
-            }
-            if (MODE != MODE_HEAD) {
-                float4 a = *reinterpret_cast<const float4*>(bin + tx * 4);
-#pragma unroll
-                for (int cc = 0; cc < kMaxCf; ++cc) {
-                    if (cc < Cf) {
-                        const float xv = __shfl_sync(0xffffffffu, xn_mine, cc, LG);
-                        const float4 w4 = *reinterpret_cast<const float4*>(win + cc * C0 + tx * 4);
-                        a.x = fmaf(xv, w4.x, a.x); a.y = fmaf(xv, w4.y, a.y); a.z = fmaf(xv, w4.z, a.z); a.w = fmaf(xv, w4.w, a.w);
+                        if (co < Cf && tx == co) mo = part[co] + bout[co];
+                    if (pv[j] && tx < Cf) {
+                        const long long e = static_cast<long long>(tx) * Hc * Wc + pe[j];
+                        if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + e] = mo;
+                        else xn_mine = sched_elem(e, mo, xo[j]);
                     }
                 }
-                if (pv) {
-                    *reinterpret_cast<float4*>(h0p + static_cast<size_t>(px) * C0 + tx * 4) = a;
-                    acc_sq(s, q, a);
+                if (MODE != MODE_HEAD) {
+                    float4 a = *reinterpret_cast<const float4*>(bin + tx * 4);
+#pragma unroll
+                    for (int cc = 0; cc < kMaxCf; ++cc) {
+                        if (cc < Cf) {
+                            const float xv = __shfl_sync(0xffffffffu, xn_mine, cc, LG);
+                            const float4 w4 = *reinterpret_cast<const float4*>(win + cc * C0 + tx * 4);
+                            a.x = fmaf(xv, w4.x, a.x); a.y = fmaf(xv, w4.y, a.y); a.z = fmaf(xv, w4.z, a.z); a.w = fmaf(xv, w4.w, a.w);
+                        }
+                    }
+                    if (pv[j]) {
+                        *reinterpret_cast<float4*>(h0p + static_cast<size_t>(px) * C0 + tx * 4) = a;
+                        acc_sq(s, q, a);
+                    }
                 }
             }
         }

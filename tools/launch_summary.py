@@ -22,7 +22,9 @@ def main(path, per_step=None, skip=None):
             rows[i]["act"] = v
     seq = [rows[i] for i in order]
     # a step ends with k_sched_step
-    ends = [k for k, r in enumerate(seq) if r["name"].startswith("k_sched_step")]
+    ends = [k for k, r in enumerate(seq) if r["name"].startswith("k_boundary<2>") or r["name"].startswith("k_boundary<(s3d::MODE)2>")]
+    if len(ends) < 3:
+        ends = [k for k, r in enumerate(seq) if r["name"].startswith("k_sched_step")]
     if len(ends) >= 3:
         step = seq[ends[-2] + 1: ends[-1] + 1]
     else:
@@ -38,8 +40,11 @@ def main(path, per_step=None, skip=None):
         print(f"{k:22s} {n:3d} {us:8.1f} {act / 1e3:12.1f}")
     print(f"{'TOTAL':22s} {len(step):3d} {sum(v[1] for v in tot.values()):8.1f} {sum(v[2] for v in tot.values()) / 1e3:12.1f}")
     if "-v" in sys.argv:
-        for i, r in enumerate(step):
-            print(i, r["name"], round(r.get("us", 0), 2), r["grid"], r["block"], round(r.get("act", 0)))
+        try:
+            for i, r in enumerate(step):
+                print(i, r["name"], round(r.get("us", 0), 2), r["grid"], r["block"], round(r.get("act", 0)))
+        except BrokenPipeError:
+            pass
 
 
 if __name__ == "__main__":
