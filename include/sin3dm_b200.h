@@ -97,10 +97,12 @@ typedef struct {
     int clip_denoised;
     int is_mask_t0;
     int B;
+    int C;                  /* channels of the composed tensor */
     int64_t n_per_sample;   /* C*(H+D)*(W+D) */
     const float* model_out; /* [B, n] */
     const float* x;         /* [B, n] x_t */
-    const float* noise;     /* [B, n] or NULL -> Philox4x32-10 keyed (seed, sample_base+b, t_idx[b]) */
+    const float* noise;     /* [B, n] or NULL -> Philox4x32-10: element (c, pixel) = component c&3 of the block with counter
+                               (pixel*ceil(C/4) + c/4, t_idx[b], sample_base+b), key = seed  (oracle/philox_ref.py) */
     const float* y0;        /* optional inpainting target (ddim_sample y0/mask), NULL if unused */
     const float* mask;
     float* sample;          /* [B, n] may alias x */
@@ -115,8 +117,8 @@ int s3d_sched_step(const s3d_sched_args* a, void* stream);
 /* q_sample: x_t = coef[t][10]*x0 + coef[t][11]*noise (gaussian_diffusion.py:189-207). */
 int s3d_q_sample(const float* x0_dev, const float* noise_dev, float* out_dev, const float* coef_dev, const int* t_idx_dev,
                  int B, int64_t n_per_sample, void* stream);
-/* N(0,1) fill with the same counter-based generator the sampler uses (noise of sample s at step i). */
-int s3d_philox_normal(float* out_dev, int B, int64_t n_per_sample, uint64_t seed, uint32_t sample_base, uint32_t step,
+/* N(0,1) fill [B, C, hw] with the same counter-based generator the sampler uses (noise of sample s at step i). */
+int s3d_philox_normal(float* out_dev, int B, int C, int64_t hw, uint64_t seed, uint32_t sample_base, uint32_t step,
                       void* stream);
 
 /* ---- whole sampling loop (replaces p_sample_loop / ddim_sample_loop, gaussian_diffusion.py:442-536, 640-734) ----

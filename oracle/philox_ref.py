@@ -4,7 +4,7 @@ Philox4x32-10 (Salmon et al., SC'11) + Box-Muller, keyed so that the noise of sa
 ``i`` does not depend on batch composition or GPU count:
 
     key     = (seed_lo, seed_hi)
-    counter = (elem_idx / 4, step, sample_global_idx, stream)      # 4 normals per counter
+    counter = (pixel * ceil(C/4) + c // 4, step, sample_global_idx, stream)      # 4 channels of one pixel per block
 
 The reference draws torch.randn_like on whichever device it runs (gaussian_diffusion.py:431,591);
 CPU mt19937 and CUDA Philox streams differ, so parity tests inject noise and this file only pins
@@ -32,9 +32,13 @@ def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
     return c
 
 
-def normals(seed: int, sample_idx: int, step: int, n: int, stream: int = 0) -> np.ndarray:
-    """n standard normals (fp32) for one sample at one step; element e uses counter e//4, lane e%4."""
-    nctr = (n + 3) // 4
+def normals(seed: int, sample_idx: int, step: int, C: int, hw: int, stream: int = 0) -> np.ndarray:
+    """[C, hw] standard normals (fp32) of one sample at one step.
+
+    Element (c, pixel) is component c & 3 of the Philox block whose counter is
+    (pixel * ceil(C/4) + c // 4, step, sample_idx, stream): one block per (pixel, channel quad)."""
+    nq = (C + 3) // 4
+    nctr = hw * nq
     ctr = np.zeros((nctr, 4), dtype=np.uint32)
     ctr[:, 0] = np.arange(nctr, dtype=np.uint32)
     ctr[:, 1] = np.uint32(step)
@@ -49,5 +53,6 @@ def normals(seed: int, sample_idx: int, step: int, n: int, stream: int = 0) -> n
     rad1 = np.sqrt(np.float32(-2.0) * np.log(u[:, 2]), dtype=np.float32)
     th0 = np.float32(2.0 * np.pi) * u[:, 1]
     th1 = np.float32(2.0 * np.pi) * u[:, 3]
-    z = np.stack([rad0 * np.cos(th0), rad0 * np.sin(th0), rad1 * np.cos(th1), rad1 * np.sin(th1)], axis=1)
-    return z.reshape(-1)[:n].astype(np.float32)
+    z = np.stack([rad0 * np.cos(th0), rad0 * np.sin(th0), rad1 * np.cos(th1), rad1 * np.sin(th1)], axis=1)   # [hw*nq, 4]
+    z = z.reshape(hw, nq * 4).T[:C]                                        # [C, hw]
+    return np.ascontiguousarray(z).astype(np.float32)

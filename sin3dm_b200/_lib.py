@@ -24,7 +24,7 @@ class UNetConfig(C.Structure):
 
 class SchedArgs(C.Structure):
     _fields_ = [("kind", C.c_int), ("mean_type", C.c_int), ("clip_denoised", C.c_int), ("is_mask_t0", C.c_int),
-                ("B", C.c_int), ("n_per_sample", C.c_int64), ("model_out", C.c_void_p), ("x", C.c_void_p),
+                ("B", C.c_int), ("C", C.c_int), ("n_per_sample", C.c_int64), ("model_out", C.c_void_p), ("x", C.c_void_p),
                 ("noise", C.c_void_p), ("y0", C.c_void_p), ("mask", C.c_void_p), ("sample", C.c_void_p),
                 ("pred_xstart", C.c_void_p), ("coef_dev", C.c_void_p), ("t_idx_dev", C.c_void_p),
                 ("seed", C.c_uint64), ("sample_base", C.c_uint32)]
@@ -63,7 +63,7 @@ _SIGNATURES = {
     "s3d_sched_step": (C.c_int, [C.POINTER(SchedArgs), C.c_void_p]),
     "s3d_q_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                C.c_void_p]),
-    "s3d_philox_normal": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32,
+    "s3d_philox_normal": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32,
                                     C.c_void_p]),
     "s3d_sample_loop": (C.c_int, [C.c_void_p, C.POINTER(LoopArgs), C.c_void_p]),
     "s3d_unet_debug_count": (C.c_int, [C.c_void_p]),

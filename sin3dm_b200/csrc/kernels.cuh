@@ -290,6 +290,7 @@ struct GnSiluArgs {
     int total_tickets;
     int seg_off[6];
     int total_len;
+    int dbg;                  // timing experiments only (S3D_DBG_GNSILU): 1 = no atomics, 2 = no tickets/finalize, 3 = both
 };
 
 __device__ __forceinline__ void fix_add(unsigned long long* p, float v) {
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
     unsigned long long* sb = A.sums + static_cast<size_t>(b) * A.total_len * C;
     unsigned long long* srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
     unsigned long long* scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
-    if (cvalid) {
+    if (cvalid && !(A.dbg & 1)) {
         float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r) {
@@ -395,7 +396,11 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
         int r = i / C, ch = i - r * C;
         float acc = 0.f;
         for (int yy = 0; yy < ny; ++yy) acc += red[(static_cast<size_t>(yy) * kGsRows + r) * C + ch];
-        fix_add(srow + static_cast<size_t>(r0 + r) * C + ch, acc);
+        if (!(A.dbg & 1)) fix_add(srow + static_cast<size_t>(r0 + r) * C + ch, acc);
+    }
+    if (A.dbg & 2) {
+        store_operands();
+        return;
     }
     // ---- whoever completes this row strip / this column tile converts it to fp16 means and re-zeroes it
     __threadfence();
@@ -623,7 +628,9 @@ __global__ void __launch_bounds__(256) k_linear(const float* __restrict__ x, con
 struct SchedArgs {
     int kind, mean_type, clip, is_mask_t0;
     int B;
-    long long n;            // per sample, multiple of 4 not required
+    long long n;            // per sample = C * hw
+    int C;                  // channels
+    long long hw;           // (H+D)*(W+D)
     const float* model_out;
     const float* x;
     const float* noise;     // nullptr -> philox
@@ -671,6 +678,10 @@ __device__ __forceinline__ float sched_one(const SchedArgs& A, const float* cf, 
     return res;
 }
 
+// Noise layout (shared with k_boundary<MODE_FUSED>, k_philox_normal and oracle/philox_ref.py): the N(0,1) of element
+// (c, pixel) is component c & 3 of the Philox block with counter (pixel * ceil(C/4) + c / 4, step, global sample index), so
+// one block serves the four channels c..c+3 of a pixel — the unit both kernels naturally own.
+// One thread = one (pixel, channel quad).  grid (ceil(hw*nq/256) capped, B)
 __global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
     pdl_wait();
     pdl_trigger();
@@ -683,47 +694,37 @@ __global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
     const float nz = t != 0 ? 1.f : 0.f;
     const size_t base = static_cast<size_t>(b) * A.n;
     const float* noise = A.noise ? A.noise + static_cast<size_t>(t) * A.noise_step_stride + base : nullptr;
-    const long long n4 = (A.n + 3) / 4;
-    const bool vec = (A.n % 4) == 0;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+    const int nq = (A.C + 3) / 4;
+    const long long items = A.hw * nq;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < items;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        float o[4], xv[4], nv[4], yv[4] = {0, 0, 0, 0}, mv[4] = {0, 0, 0, 0}, rs[4], x0[4];
-        const long long e0 = i * 4;
-        const int cnt = static_cast<int>(min(4LL, A.n - e0));
-        if (vec) {
-            float4 t4 = *reinterpret_cast<const float4*>(A.model_out + base + e0);
-            o[0] = t4.x; o[1] = t4.y; o[2] = t4.z; o[3] = t4.w;
-            t4 = *reinterpret_cast<const float4*>(A.x + base + e0);
-            xv[0] = t4.x; xv[1] = t4.y; xv[2] = t4.z; xv[3] = t4.w;
-        } else {
-            for (int k = 0; k < 4; ++k) {
-                o[k] = k < cnt ? A.model_out[base + e0 + k] : 0.f;
-                xv[k] = k < cnt ? A.x[base + e0 + k] : 0.f;
+        const int quad = static_cast<int>(i / A.hw);           // pixel fastest: adjacent threads -> adjacent addresses
+        const long long pix = i - quad * A.hw;
+        const int c0 = quad * 4, cnt = min(4, A.C - c0);
+        float o[4], xv[4], nv[4] = {0, 0, 0, 0}, yv[4] = {0, 0, 0, 0}, mv[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t e = static_cast<size_t>(c0 + k) * A.hw + pix;
+            o[k] = k < cnt ? A.model_out[base + e] : 0.f;
+            xv[k] = k < cnt ? A.x[base + e] : 0.f;
+            if (noise && k < cnt) nv[k] = noise[e];
+            if (A.y0 && k < cnt) {
+                yv[k] = A.y0[base + e];
+                mv[k] = A.mask[base + e];
             }
         }
-        if (noise) {
-            for (int k = 0; k < 4; ++k) nv[k] = k < cnt ? noise[e0 + k] : 0.f;
-        } else if (A.kind != 2) {
-            float4 z = philox_normal4(A.seed, A.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(i));
+        if (!noise && A.kind != 2) {
+            const float4 z = philox_normal4(A.seed, A.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(pix * nq + quad));
             nv[0] = z.x; nv[1] = z.y; nv[2] = z.z; nv[3] = z.w;
-        } else {
-            nv[0] = nv[1] = nv[2] = nv[3] = 0.f;
-        }
-        if (A.y0) {
-            for (int k = 0; k < 4; ++k) {
-                yv[k] = k < cnt ? A.y0[base + e0 + k] : 0.f;
-                mv[k] = k < cnt ? A.mask[base + e0 + k] : 0.f;
-            }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) rs[k] = sched_one(A, cf, nz, o[k], xv[k], nv[k], yv[k], mv[k], x0[k]);
-        if (vec) {
-            *reinterpret_cast<float4*>(A.sample + base + e0) = make_float4(rs[0], rs[1], rs[2], rs[3]);
-            if (A.x0_out) *reinterpret_cast<float4*>(A.x0_out + base + e0) = make_float4(x0[0], x0[1], x0[2], x0[3]);
-        } else {
-            for (int k = 0; k < cnt; ++k) {
-                A.sample[base + e0 + k] = rs[k];
-                if (A.x0_out) A.x0_out[base + e0 + k] = x0[k];
+        for (int k = 0; k < 4; ++k) {
+            if (k < cnt) {
+                float x0;
+                const float rs = sched_one(A, cf, nz, o[k], xv[k], nv[k], yv[k], mv[k], x0);
+                const size_t e = static_cast<size_t>(c0 + k) * A.hw + pix;
+                A.sample[base + e] = rs;
+                if (A.x0_out) A.x0_out[base + e] = x0;
             }
         }
     }
@@ -753,20 +754,23 @@ __global__ void __launch_bounds__(256) k_q_sample(const float* __restrict__ x0, 
         out[base + i] = __fadd_rn(__fmul_rn(a, x0[base + i]), __fmul_rn(s, noise[base + i]));
 }
 
-__global__ void __launch_bounds__(256) k_philox_normal(float* __restrict__ out, long long n, unsigned long long seed,
+__global__ void __launch_bounds__(256) k_philox_normal(float* __restrict__ out, int C, long long hw, unsigned long long seed,
                                                        unsigned int sample_base, unsigned int step) {
     pdl_wait();
     pdl_trigger();
     const int b = blockIdx.y;
-    const long long n4 = (n + 3) / 4;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+    const int nq = (C + 3) / 4;
+    const long long items = hw * nq;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < items;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        float4 z = philox_normal4(seed, sample_base + b, step, static_cast<uint32_t>(i));
-        float zz[4] = {z.x, z.y, z.z, z.w};
-        for (int k = 0; k < 4 && i * 4 + k < n; ++k) out[static_cast<size_t>(b) * n + i * 4 + k] = zz[k];
+        const int quad = static_cast<int>(i / hw);
+        const long long pix = i - quad * hw;
+        const float4 z = philox_normal4(seed, sample_base + b, step, static_cast<uint32_t>(pix * nq + quad));
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+        for (int k = 0; k < 4 && quad * 4 + k < C; ++k)
+            out[(static_cast<size_t>(b) * C + quad * 4 + k) * hw + pix] = zz[k];
     }
 }
-
 
 // =====================================================================================
 // Step boundary: the output head, the scheduler update and the next step's input conv are all per-pixel maps, so the
@@ -828,16 +832,12 @@ __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
         for (int k = 0; k < 12; ++k) cf[k] = __ldg(A.sch.coef + static_cast<size_t>(t) * 12 + k);
         nz = t != 0 ? 1.f : 0.f;
     }
-    auto sched_elem = [&](long long e, float mo, float xo) -> float {   // e: element index inside the sample; returns x_{t-1}
+    const int nq = (Cf + 3) / 4;
+    const long long hw = static_cast<long long>(Hc) * Wc;
+    // e: element index inside the sample, nv: its N(0,1) draw (ignored when a noise buffer is given); returns x_{t-1}
+    auto sched_elem = [&](long long e, float mo, float xo, float nv) -> float {
         const size_t gi = static_cast<size_t>(b) * nper + e;
-        float nv = 0.f;
-        if (A.sch.noise) {
-            nv = A.sch.noise[static_cast<size_t>(t) * A.sch.noise_step_stride + gi];
-        } else {
-            const float4 z = philox_normal4(A.sch.seed, A.sch.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(e >> 2));
-            const int k = static_cast<int>(e & 3);
-            nv = k == 0 ? z.x : (k == 1 ? z.y : (k == 2 ? z.z : z.w));
-        }
+        if (A.sch.noise) nv = A.sch.noise[static_cast<size_t>(t) * A.sch.noise_step_stride + gi];
         const float y0 = A.sch.y0 ? A.sch.y0[gi] : 0.f, mk = A.sch.y0 ? A.sch.mask[gi] : 0.f;
         float x0;
         const float xn = sched_one(A.sch, cf, nz, mo, xo, nv, y0, mk, x0);
@@ -852,27 +852,29 @@ __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
         const int per = (ncorner + nslots - 1) / nslots;
         const int e0 = slot * per, e1 = min(ncorner, e0 + per);
         if (MODE != MODE_INCONV) {
-            const int nitems = (e1 - e0) * Cf;
-            for (int i0 = 0; i0 < nitems; i0 += nthr * 4) {
-                long long ee[4];
-                float xo[4];
+            const int nitems = (e1 - e0) * nq;                 // one item = the (up to) 4 channels of a quad at one corner pixel
+            for (int i = tid; i < nitems; i += nthr) {
+                const int quad = i / (e1 - e0), el = e0 + (i - quad * (e1 - e0));
+                const int r = el / A.Dd, c = el - r * A.Dd;
+                const long long pix = static_cast<long long>(A.H + r) * Wc + A.W + c;
+                const int c0 = quad * 4, cnt = min(4, Cf - c0);
+                float xo[4] = {0.f, 0.f, 0.f, 0.f};
+                if (MODE == MODE_FUSED) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = i0 + k * nthr + tid;
-                    ee[k] = -1;
-                    xo[k] = 0.f;
-                    if (i < nitems) {
-                        const int co = i / (e1 - e0), el = e0 + (i - co * (e1 - e0));
-                        const int r = el / A.Dd, c = el - r * A.Dd;
-                        ee[k] = (static_cast<long long>(co) * Hc + A.H + r) * Wc + A.W + c;
-                        if (MODE == MODE_FUSED) xo[k] = A.sch.x[static_cast<size_t>(b) * nper + ee[k]];
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        if (k < cnt) xo[k] = A.sch.x[static_cast<size_t>(b) * nper + static_cast<long long>(c0 + k) * hw + pix];
                 }
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MODE == MODE_FUSED && !A.sch.noise)
+                    z = philox_normal4(A.sch.seed, A.sch.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(pix * nq + quad));
+                const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (ee[k] < 0) continue;
-                    if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + ee[k]] = 0.f;
-                    else sched_elem(ee[k], 0.f, xo[k]);
+                    if (k < cnt) {
+                        const long long e = static_cast<long long>(c0 + k) * hw + pix;
+                        if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + e] = 0.f;
+                        else sched_elem(e, 0.f, xo[k], zz[k]);
+                    }
                 }
             }
         }
@@ -957,10 +959,23 @@ __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
 #pragma unroll
                     for (int co = 0; co < kMaxCf; ++co)
                         if (co < Cf && tx == co) mo = part[co] + bout[co];
+                    float nv = 0.f;
+                    if (MODE == MODE_FUSED && !A.sch.noise) {
+                        // one Philox block per channel quad: the quad's first lane draws, the other three fetch their component
+                        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pv[j] && tx < 4 * nq && (tx & 3) == 0)
+                            z = philox_normal4(A.sch.seed, A.sch.sample_base + b, static_cast<uint32_t>(t),
+                                               static_cast<uint32_t>(pe[j] * nq + (tx >> 2)));
+                        const int leader = tx & ~3;
+                        const float zx = __shfl_sync(0xffffffffu, z.x, leader, LG), zy = __shfl_sync(0xffffffffu, z.y, leader, LG);
+                        const float zz = __shfl_sync(0xffffffffu, z.z, leader, LG), zw = __shfl_sync(0xffffffffu, z.w, leader, LG);
+                        const int k = tx & 3;
+                        nv = k == 0 ? zx : (k == 1 ? zy : (k == 2 ? zz : zw));
+                    }
                     if (pv[j] && tx < Cf) {
                         const long long e = static_cast<long long>(tx) * Hc * Wc + pe[j];
                         if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + e] = mo;
-                        else xn_mine = sched_elem(e, mo, xo[j]);
+                        else xn_mine = sched_elem(e, mo, xo[j], nv);
                     }
                 }
                 if (MODE != MODE_HEAD) {

@@ -652,6 +652,7 @@ struct PlanBuilder {
         A.d = d;
         A.C = C;
         A.a = a.p;
+        if (const char* e = getenv("S3D_DBG_GNSILU")) A.dbg = atoi(e);
         if (x16) A.x16 = x16->p;
         if (S) {
             A.sums = S->buf;
@@ -1118,7 +1119,7 @@ static void run_ops(s3d_unet* u, Plan* P, cudaStream_t s) {
 }
 
 static void launch_sched(const SchedArgs& A, cudaStream_t s) {
-    const long long n4 = (A.n + 3) / 4;
+    const long long n4 = A.hw * ((A.C + 3) / 4);
     int gx = static_cast<int>(std::min<long long>((n4 + 255) / 256, 148LL * 8));
     gx = std::max(gx, 1);
     launch(k_sched_step, dim3(dim3(gx, A.B)), dim3(256), 0, s, A);
@@ -1268,6 +1269,8 @@ static SchedArgs to_sched(const s3d_sched_args* a) {
     A.is_mask_t0 = a->is_mask_t0;
     A.B = a->B;
     A.n = a->n_per_sample;
+    A.C = a->C;
+    A.hw = a->n_per_sample / a->C;
     A.model_out = a->model_out;
     A.x = a->x;
     A.noise = a->noise;
@@ -1287,7 +1290,7 @@ int s3d_sched_step(const s3d_sched_args* a, void* stream) {
     S3D_CHECK(a && a->model_out && a->x && a->sample && a->coef_dev && a->t_idx_dev, "null argument");
     S3D_CHECK(a->kind >= 0 && a->kind <= 2 && (a->mean_type == 0 || a->mean_type == 1), "bad kind / mean_type");
     S3D_CHECK((a->y0 == nullptr) == (a->mask == nullptr), "y0 and mask go together");
-    S3D_CHECK(a->B >= 1 && a->n_per_sample >= 1, "bad shape");
+    S3D_CHECK(a->B >= 1 && a->n_per_sample >= 1 && a->C >= 1 && a->n_per_sample % a->C == 0, "bad shape");
     launch_sched(to_sched(a), static_cast<cudaStream_t>(stream));
     API_END
 }
@@ -1302,11 +1305,11 @@ int s3d_q_sample(const float* x0_dev, const float* noise_dev, float* out_dev, co
     API_END
 }
 
-int s3d_philox_normal(float* out_dev, int B, int64_t n, uint64_t seed, uint32_t sample_base, uint32_t step, void* stream) {
+int s3d_philox_normal(float* out_dev, int B, int C, int64_t hw, uint64_t seed, uint32_t sample_base, uint32_t step, void* stream) {
     API_BEGIN
-    S3D_CHECK(out_dev && B >= 1 && n >= 1, "bad argument");
-    int gx = static_cast<int>(std::min<long long>(((n + 3) / 4 + 255) / 256, 148LL * 8));
-    launch(k_philox_normal, dim3(dim3(gx, B)), dim3(256), 0, static_cast<cudaStream_t>(stream), out_dev, n, seed, sample_base, step);
+    S3D_CHECK(out_dev && B >= 1 && C >= 1 && hw >= 1, "bad argument");
+    int gx = static_cast<int>(std::min<long long>((hw * ((C + 3) / 4) + 255) / 256, 148LL * 8));
+    launch(k_philox_normal, dim3(dim3(gx, B)), dim3(256), 0, static_cast<cudaStream_t>(stream), out_dev, C, hw, seed, sample_base, step);
     LAUNCH_CHECK("k_philox_normal");
     API_END
 }
@@ -1347,6 +1350,8 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
     A.is_mask_t0 = a->is_mask_t0;
     A.B = a->B;
     A.n = n;
+    A.C = u->cfg.out_channels;
+    A.hw = static_cast<long long>(Hc) * Wc;
     A.model_out = P->model_out;
     A.x = a->x_dev;
     A.noise = a->step_noise_dev;

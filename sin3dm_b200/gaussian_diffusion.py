@@ -241,7 +241,7 @@ class GaussianDiffusion:
         sample, x0 = th.empty_like(x), th.empty_like(x)
         a = _lib.SchedArgs()
         a.kind, a.mean_type, a.clip_denoised, a.is_mask_t0 = kind, self._mean_code(), int(bool(clip)), int(bool(is_mask_t0))
-        a.B, a.n_per_sample = B, x[0].numel()
+        a.B, a.C, a.n_per_sample = B, x.shape[1], x[0].numel()
         keep = [x, mo, sample, x0]
         a.model_out, a.x, a.sample, a.pred_xstart = mo.data_ptr(), x.data_ptr(), sample.data_ptr(), x0.data_ptr()
         if noise is not None:

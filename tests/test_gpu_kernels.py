@@ -68,13 +68,13 @@ def test_ddim_reverse_and_q_sample_bit_exact():
 
 def test_philox_matches_oracle():
     import ctypes as C
-    n, B = 4099, 3
-    out = torch.empty(B, n, device="cuda")
-    _lib.check(_lib.lib().s3d_philox_normal(C.c_void_p(out.data_ptr()), B, n, 0x1234567890ABCDEF, 5, 17,
+    Cc, hw, B = 10, 4099, 3
+    out = torch.empty(B, Cc, hw, device="cuda")
+    _lib.check(_lib.lib().s3d_philox_normal(C.c_void_p(out.data_ptr()), B, Cc, hw, 0x1234567890ABCDEF, 5, 17,
                                             _lib.current_stream_ptr()))
     got = out.cpu().numpy()
     for b in range(B):
-        want = philox_ref.normals(0x1234567890ABCDEF, 5 + b, 17, n)
+        want = philox_ref.normals(0x1234567890ABCDEF, 5 + b, 17, Cc, hw)
         assert np.allclose(got[b], want, rtol=0, atol=2e-6), np.abs(got[b] - want).max()
     assert abs(got.mean()) < 0.05 and abs(got.std() - 1) < 0.05
 
@@ -89,6 +89,7 @@ def test_in_kernel_noise_equals_philox_fill():
     t = torch.tensor([5, 5]).cuda()
     a = d.p_sample(lambda xx, tt, **k: out, x, t, _seed=99, _sample_base=3)
     nz = torch.empty(shape, device="cuda")
-    _lib.check(_lib.lib().s3d_philox_normal(C.c_void_p(nz.data_ptr()), 2, nz[0].numel(), 99, 3, 5, _lib.current_stream_ptr()))
+    _lib.check(_lib.lib().s3d_philox_normal(C.c_void_p(nz.data_ptr()), 2, shape[1], shape[2] * shape[3], 99, 3, 5,
+                                            _lib.current_stream_ptr()))
     b = d.p_sample(lambda xx, tt, **k: out, x, t, noise=nz)
     assert torch.equal(a["sample"], b["sample"])

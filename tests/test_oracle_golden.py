@@ -103,8 +103,11 @@ def test_philox_known_answer():
 
 
 def test_philox_normals_moments():
-    z = philox_ref.normals(seed=12345, sample_idx=3, step=7, n=200000)
+    z = philox_ref.normals(seed=12345, sample_idx=3, step=7, C=12, hw=20000)
+    assert z.shape == (12, 20000)
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
-    z2 = philox_ref.normals(seed=12345, sample_idx=3, step=7, n=1000)
-    assert np.array_equal(z[:1000], z2)
-    assert not np.array_equal(z2, philox_ref.normals(seed=12345, sample_idx=4, step=7, n=1000))
+    z2 = philox_ref.normals(seed=12345, sample_idx=3, step=7, C=10, hw=20000)      # same quad count: same stream
+    assert np.array_equal(z[:10], z2)
+    z3 = philox_ref.normals(seed=12345, sample_idx=3, step=7, C=8, hw=20000)       # 2 quads per pixel instead of 3
+    assert not np.array_equal(z[:8], z3)
+    assert not np.array_equal(z, philox_ref.normals(seed=12345, sample_idx=4, step=7, C=12, hw=20000))
