@@ -67,7 +67,15 @@ struct FusedRoll {
     RollTcArgs R;
     int n_roll;              // number of roll tiles (0: none; Trow/Tcol come from a separate launch or are absent)
     int ntn;                 // N tiles per roll M tile
-    unsigned int* counters;  // [2]: roll tiles done, CTAs exited (both return to 0 when the kernel ends)
+    unsigned int* counters;  // [3]: roll tiles done, CTAs exited, CTAs whose share of the means is converted
+                             //      (all return to 0 when the kernel ends)
+    // Phase 0 (every CTA, epilogue warps): axis sums (64-bit fixed point, accumulated by k_gn_silu) -> fp16 (hi, lo) means,
+    // the A operand the roll tiles then fetch by TMA; the accumulators are re-zeroed on the way.
+    unsigned long long* sums;     // [B][total_len][C]   nullptr: means16 already finalised by k_gn_silu
+    __half* means16;              // [2][B][total_len][C]
+    int total_len, B;
+    int seg_end[6];               // cumulative segment ends (positions) in a sample's block
+    float seg_scale[6];           // 2^-24 / (length of the averaged axis)
 };
 
 template <int NSPLIT>
@@ -214,6 +222,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         if (lane == 0) {
             pdl_wait();
             int ga = 0;
+            bool means_ready = false;
             auto slot_wait = [&](uint32_t tx) -> uint8_t* {
                 const int s = ga % Cfg::kASlots;
                 ptx::mbar_wait(&emptyA[s], ((ga / Cfg::kASlots) & 1) ^ 1);
@@ -222,6 +231,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             };
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 if (t < F.n_roll) {
+                    if (F.sums && !means_ready) {
+                        // every CTA converts a share of the means in its phase 0: wait for all of them, then order the
+                        // generic-proxy observation before the async-proxy (TMA) reads
+                        const volatile unsigned int* cnt = F.counters + 2;
+                        long long spins = 0;
+                        while (*cnt < gridDim.x) {
+                            if (++spins > (1LL << 31)) __trap();     // never hang the device
+                        }
+                        __threadfence();
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        means_ready = true;
+                    }
                     const RollTile T = roll_tile_decode(F, t);
                     for (int i = 0; i < 3 * cblks; ++i, ++ga) {
                         uint8_t* st = slot_wait(kAStdTx);
@@ -339,6 +360,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         bool roll_ready = F.n_roll == 0;
         int lt = 0;
         pdl_wait();
+        if (F.n_roll && F.sums) {
+            const int C = A.C;
+            const long long per_sample = static_cast<long long>(F.total_len) * C;
+            const long long total = per_sample * F.B;
+            const size_t lo_off = static_cast<size_t>(total);
+            for (long long i = static_cast<long long>(blockIdx.x) * 128 + et; i < total; i += static_cast<long long>(gridDim.x) * 128) {
+                const int pos = static_cast<int>((i % per_sample) / C);
+                int seg = 0;
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    if (pos >= F.seg_end[k]) seg = k + 1;
+                const long long sv = static_cast<long long>(__ldcg(F.sums + i));
+                F.sums[i] = 0ull;
+                const float mean = __ll2float_rn(sv) * F.seg_scale[seg];
+                __half hi, lo;
+                split_f16(mean, hi, lo);
+                F.means16[i] = hi;
+                F.means16[lo_off + i] = lo;
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) atomicAdd(&F.counters[2], 1u);
+        }
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int as = lt & 1;
             const uint32_t aph = (lt >> 1) & 1;
@@ -418,7 +462,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     // the rollout terms are produced by this very launch (roll tiles): wait until all of them are written
                     if (lane == 0) {
                         const volatile unsigned int* cnt = F.counters;
+                        long long spins = 0;
                         while (*cnt < static_cast<unsigned int>(F.n_roll)) {
+                            if (++spins > (1LL << 31)) __trap();     // never hang the device
                         }
                     }
                     __syncwarp();
@@ -520,6 +566,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         if (prev == gridDim.x - 1) {
             F.counters[0] = 0u;
             F.counters[1] = 0u;
+            F.counters[2] = 0u;
         }
     }
 }

@@ -290,7 +290,8 @@ struct GnSiluArgs {
     int total_tickets;
     int seg_off[6];
     int total_len;
-    int dbg;                  // timing experiments only (S3D_DBG_GNSILU): 1 = no atomics, 2 = no tickets/finalize, 3 = both
+    int finalize;             // 1: the last CTA of a strip / column tile converts the sums to fp16 means itself (stand-alone roll
+                              //    kernels); 0: k_conv_tc does it in its phase 0 and this kernel ends right after the atomics
 };
 
 __device__ __forceinline__ void fix_add(unsigned long long* p, float v) {
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
     unsigned long long* sb = A.sums + static_cast<size_t>(b) * A.total_len * C;
     unsigned long long* srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
     unsigned long long* scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
-    if (cvalid && !(A.dbg & 1)) {
+    if (cvalid) {
         float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r) {
@@ -396,9 +397,9 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
         int r = i / C, ch = i - r * C;
         float acc = 0.f;
         for (int yy = 0; yy < ny; ++yy) acc += red[(static_cast<size_t>(yy) * kGsRows + r) * C + ch];
-        if (!(A.dbg & 1)) fix_add(srow + static_cast<size_t>(r0 + r) * C + ch, acc);
+        fix_add(srow + static_cast<size_t>(r0 + r) * C + ch, acc);
     }
-    if (A.dbg & 2) {
+    if (!A.finalize) {
         store_operands();
         return;
     }

@@ -652,7 +652,7 @@ struct PlanBuilder {
         A.d = d;
         A.C = C;
         A.a = a.p;
-        if (const char* e = getenv("S3D_DBG_GNSILU")) A.dbg = atoi(e);
+        A.finalize = (u->cfg.conv_impl == 1 || !u->fuse_roll) ? 1 : 0;
         if (x16) A.x16 = x16->p;
         if (S) {
             A.sums = S->buf;
@@ -681,6 +681,7 @@ struct PlanBuilder {
         std::shared_ptr<RollTcMaps> roll_maps;   // set when the 1-D GEMM tiles are to be fused into the conv launch
         RollTcArgs roll_args{};
         int roll_mtiles = 0, roll_ntn = 0;
+        Sums sums{};
     };
     // ---- rollout 1-D terms (tensor-core GEMM; SIMT cross-check kernel when conv_impl == 1)
     TBuf roll1d(const Sums& S, int level, const DevConv3& cv) {
@@ -768,6 +769,7 @@ struct PlanBuilder {
             T.roll_args = A;
             T.roll_mtiles = total;
             T.roll_ntn = ntn;
+            T.sums = S;
             return T;
         }
         add_op("k_roll_tc", 0.0, [=](cudaStream_t s) {
@@ -874,8 +876,19 @@ struct PlanBuilder {
             F.R = T->roll_args;
             F.ntn = T->roll_ntn;
             F.n_roll = T->roll_mtiles * T->roll_ntn * B;
-            F.counters = dev_alloc<unsigned int>(P->allocs, 2);
-            CUDA_TRY(cudaMemset(F.counters, 0, 2 * sizeof(unsigned int)));
+            F.counters = dev_alloc<unsigned int>(P->allocs, 3);
+            CUDA_TRY(cudaMemset(F.counters, 0, 3 * sizeof(unsigned int)));
+            // phase 0 of the kernel finalises the means (k_gn_silu only accumulated the sums)
+            F.sums = T->sums.buf;
+            F.means16 = T->sums.means16;
+            F.total_len = T->sums.total_len;
+            F.B = B;
+            for (int p = 0; p < 3; ++p)
+                for (int kind = 0; kind < 2; ++kind) {
+                    const int i = p * 2 + kind;
+                    F.seg_end[i] = T->sums.seg_off[i] + (kind == 0 ? d.rows[p] : d.cols[p]);
+                    F.seg_scale[i] = static_cast<float>(1.0 / 16777216.0 / static_cast<double>(kind == 0 ? d.cols[p] : d.rows[p]));
+                }
         }
         add_op("k_conv_tc", conv_flops(level, cv), [=](cudaStream_t s) {
             ConvTcArgs Al = A;
@@ -1367,7 +1380,9 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
     A.advance = 1;
     A.ticket = P->ticket;
     // Loop structure: in_conv once, then per step [blocks ..., fused (out head + scheduler + next step's in_conv)].
-    const bool fused = static_cast<bool>(P->fused_boundary) && !getenv("S3D_NO_FUSED_BOUNDARY");
+    // measured on B200 (r1): the lane-group fused kernel is slower than head + scheduler + in_conv separately, so it is opt-in
+    const char* fb = getenv("S3D_FUSED_BOUNDARY");
+    const bool fused = static_cast<bool>(P->fused_boundary) && fb && atoi(fb) != 0;
     const size_t nops = P->ops.size();
     auto one_step = [&](cudaStream_t st) {
         if (fused) {
