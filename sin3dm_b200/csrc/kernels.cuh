@@ -780,10 +780,11 @@ __global__ void __launch_bounds__(256) k_philox_normal(float* __restrict__ out, 
 //   head   : GroupNorm + SiLU + 1x1 conv C0 -> Cf, composed NCHW output        reference unet_triplane.py:441-445
 //   sched  : DDPM / DDIM update of x with the model output of this pixel        (see k_sched_step)
 //   in_conv: 1x1 conv Cf -> C0 off the composed tensor + GroupNorm partials      reference unet_triplane.py:378
-// A pixel is handled by LG = C0/4 adjacent lanes (4 channels each, LG in {16, 32}); the Cf-wide dot products are reduced
-// with xor-shuffles inside the lane group.  grid (nslots, 4, B): blockIdx.y == 3 is the dead D x D corner, which the
-// network never sees (zero model output) but the sampler still evolves.  block (LG, 256/LG).
-// smem: coefA[C0], coefB[C0], wout[Cf][C0], bout[Cf], win[Cf][C0], bin[C0], red[(NY*2+2)*C0]
+// A pixel is handled by 4 adjacent lanes; lane l owns C0/4 consecutive hidden channels (as NV = C0/16 float4 chunks) and the
+// triplane channel quad 4l..4l+3 (its Philox block, its scheduler update).  The Cf-wide dot products of the head are reduced
+// with two xor-shuffles inside the lane quad.  grid (nslots, 4, B): blockIdx.y == 3 is the dead D x D corner, which the
+// network never sees (zero model output) but the sampler still evolves.  block 256 = 64 pixels x 4 lanes.
+// smem: coefA[C0], coefB[C0], wout[Cf][C0], bout[Cf], win[Cf][C0], bin[C0], red[2][64][C0]
 // =====================================================================================
 enum { MODE_HEAD = 0, MODE_INCONV = 1, MODE_FUSED = 2 };
 constexpr int kMaxCf = 16;
@@ -802,26 +803,30 @@ struct BoundaryArgs {
     SchedArgs sch;        // x, sample (in place), coefficient table, step index   (FUSED)
 };
 
-template <int MODE>
+template <int MODE, int NV>      // NV = C0 / 16 float4 chunks per lane (4: C0 = 64, 8: C0 = 128)
 __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
+    constexpr int kBndMaxNV = NV;
     pdl_wait();
     pdl_trigger();
     extern __shared__ float smb[];
     __shared__ double fin[64 * 9];
     __shared__ bool is_last;
     const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
-    const int C0 = A.C0, Cf = A.Cf, LG = blockDim.x, NY = blockDim.y;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * LG + tx, nthr = LG * NY;
+    const int C0 = A.C0, Cf = A.Cf;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 3, pg = tid >> 2, npg = nthr >> 2;
+    const int CPL = C0 >> 2;                            // channels per lane
+    const int nq = (Cf + 3) / 4;
     const int Hc = A.H + A.Dd, Wc = A.W + A.Dd;
-    const long long nper = static_cast<long long>(Cf) * Hc * Wc;
+    const long long hw = static_cast<long long>(Hc) * Wc;
+    const long long nper = static_cast<long long>(Cf) * hw;
     float* coefA = smb;
     float* coefB = coefA + C0;
     float* wout = coefB + C0;           // [Cf][C0]
     float* bout = wout + Cf * C0;       // [Cf]
     float* win = bout + Cf;             // [Cf][C0]  (transposed: win[c][co])
     float* bin = win + Cf * C0;         // [C0]
-    float* red = bin + C0;
+    float* red = bin + C0;              // [2][npg][C0]
 
     // scheduler scalars of this sample (FUSED)
     int t = 0;
@@ -833,18 +838,26 @@ __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
         for (int k = 0; k < 12; ++k) cf[k] = __ldg(A.sch.coef + static_cast<size_t>(t) * 12 + k);
         nz = t != 0 ? 1.f : 0.f;
     }
-    const int nq = (Cf + 3) / 4;
-    const long long hw = static_cast<long long>(Hc) * Wc;
-    // e: element index inside the sample, nv: its N(0,1) draw (ignored when a noise buffer is given); returns x_{t-1}
-    auto sched_elem = [&](long long e, float mo, float xo, float nv) -> float {
-        const size_t gi = static_cast<size_t>(b) * nper + e;
-        if (A.sch.noise) nv = A.sch.noise[static_cast<size_t>(t) * A.sch.noise_step_stride + gi];
-        const float y0 = A.sch.y0 ? A.sch.y0[gi] : 0.f, mk = A.sch.y0 ? A.sch.mask[gi] : 0.f;
-        float x0;
-        const float xn = sched_one(A.sch, cf, nz, mo, xo, nv, y0, mk, x0);
-        A.sch.sample[gi] = xn;
-        if (A.sch.x0_out) A.sch.x0_out[gi] = x0;
-        return xn;
+    // scheduler update of the (up to) 4 channels of quad `quad` at composed pixel `pix`; xo: x_t, mo: model output
+    auto sched_quad = [&](int quad, long long pix, const float (&mo)[4], const float (&xo)[4], float (&xn)[4]) {
+        const int c0 = quad * 4, cnt = min(4, Cf - c0);
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!A.sch.noise && A.sch.kind != 2)
+            z = philox_normal4(A.sch.seed, A.sch.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(pix * nq + quad));
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            xn[k] = 0.f;
+            if (k < cnt) {
+                const size_t gi = static_cast<size_t>(b) * nper + static_cast<long long>(c0 + k) * hw + pix;
+                const float nv = A.sch.noise ? A.sch.noise[static_cast<size_t>(t) * A.sch.noise_step_stride + gi] : zz[k];
+                const float y0 = A.sch.y0 ? A.sch.y0[gi] : 0.f, mk = A.sch.y0 ? A.sch.mask[gi] : 0.f;
+                float x0;
+                xn[k] = sched_one(A.sch, cf, nz, mo[k], xo[k], nv, y0, mk, x0);
+                A.sch.sample[gi] = xn[k];
+                if (A.sch.x0_out) A.sch.x0_out[gi] = x0;
+            }
+        }
     };
 
     if (plane == 3) {
@@ -853,29 +866,21 @@ __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
         const int per = (ncorner + nslots - 1) / nslots;
         const int e0 = slot * per, e1 = min(ncorner, e0 + per);
         if (MODE != MODE_INCONV) {
-            const int nitems = (e1 - e0) * nq;                 // one item = the (up to) 4 channels of a quad at one corner pixel
+            const int nitems = (e1 - e0) * nq;                 // one item = one channel quad at one corner pixel
             for (int i = tid; i < nitems; i += nthr) {
                 const int quad = i / (e1 - e0), el = e0 + (i - quad * (e1 - e0));
                 const int r = el / A.Dd, c = el - r * A.Dd;
                 const long long pix = static_cast<long long>(A.H + r) * Wc + A.W + c;
                 const int c0 = quad * 4, cnt = min(4, Cf - c0);
-                float xo[4] = {0.f, 0.f, 0.f, 0.f};
-                if (MODE == MODE_FUSED) {
+                if (MODE == MODE_HEAD) {
+                    for (int k = 0; k < cnt; ++k) A.model_out[static_cast<size_t>(b) * nper + static_cast<long long>(c0 + k) * hw + pix] = 0.f;
+                } else {
+                    float xo[4] = {0.f, 0.f, 0.f, 0.f}, xn[4];
+                    const float mo[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if (k < cnt) xo[k] = A.sch.x[static_cast<size_t>(b) * nper + static_cast<long long>(c0 + k) * hw + pix];
-                }
-                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (MODE == MODE_FUSED && !A.sch.noise)
-                    z = philox_normal4(A.sch.seed, A.sch.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(pix * nq + quad));
-                const float zz[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < cnt) {
-                        const long long e = static_cast<long long>(c0 + k) * hw + pix;
-                        if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + e] = 0.f;
-                        else sched_elem(e, 0.f, xo[k], zz[k]);
-                    }
+                    sched_quad(quad, pix, mo, xo, xn);
                 }
             }
         }
@@ -897,108 +902,148 @@ __global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
             for (int i = tid; i < C0; i += nthr) bin[i] = A.b_in.p[plane][i];
         }
         __syncthreads();
-        float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), cb = ca;
-        if (MODE != MODE_INCONV) {
-            ca = *reinterpret_cast<const float4*>(coefA + tx * 4);
-            cb = *reinterpret_cast<const float4*>(coefB + tx * 4);
-        }
         const float* hp = MODE != MODE_INCONV ? A.h.p[plane] + static_cast<size_t>(b) * npx * C0 : nullptr;
         float* h0p = MODE != MODE_HEAD ? A.h0.p[plane] + static_cast<size_t>(b) * npx * C0 : nullptr;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-        // All lanes of a group walk the same pixels; groups whose pixel is out of range still run the shuffles.
-        // Pixels are taken NPB at a time with every global load of the batch issued first: the loop body ends in stores
-        // to buffers the compiler cannot prove distinct from the inputs, so without this the iterations serialise on
-        // two L2 round trips each.
-        constexpr int NPB = 4;
-        for (int pb = p0; pb < p1; pb += NY * NPB) {
-            float4 hv[NPB];
-            float xo[NPB];
-            long long pe[NPB];
+        const int ch0 = lane * CPL;                      // first hidden channel of this lane
+        float4 s[kBndMaxNV], q[kBndMaxNV];
+#pragma unroll
+        for (int k = 0; k < kBndMaxNV; ++k) s[k] = q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // Pixels are taken two at a time with every global load of the pair issued first (the stores at the end of the body
+        // cannot be proven distinct from the inputs, so the compiler will not hoist loads across iterations itself).
+        constexpr int NPB = MODE == MODE_FUSED ? 1 : 2;
+        for (int pb = p0; pb < p1; pb += npg * NPB) {
+            float4 hv[NPB][kBndMaxNV];
+            float xo[NPB][4];
+            long long pix[NPB];
             bool pv[NPB];
 #pragma unroll
             for (int j = 0; j < NPB; ++j) {
-                const int px = pb + j * NY + ty;
+                const int px = pb + j * npg + pg;
                 pv[j] = px < p1;
                 const int r = pv[j] ? px / cols : 0, c = pv[j] ? px - r * cols : 0;
-                pe[j] = composed_offset(plane, r, c, A.H, A.W, Wc);     // offset inside one channel image
-                hv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                xo[j] = 0.f;
-                if (pv[j]) {
-                    if (MODE != MODE_INCONV) hv[j] = __ldg(reinterpret_cast<const float4*>(hp + static_cast<size_t>(px) * C0) + tx);
-                    if (tx < Cf) {
-                        const size_t gi = static_cast<size_t>(b) * nper + static_cast<long long>(tx) * Hc * Wc + pe[j];
-                        if (MODE == MODE_INCONV) xo[j] = __ldg(A.x_in + gi);
-                        if (MODE == MODE_FUSED) xo[j] = A.sch.x[gi];
+                pix[j] = composed_offset(plane, r, c, A.H, A.W, Wc);
+#pragma unroll
+                for (int k = 0; k < kBndMaxNV; ++k) {
+                    hv[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE != MODE_INCONV && pv[j] && k < NV)
+                        hv[j][k] = __ldg(reinterpret_cast<const float4*>(hp + static_cast<size_t>(px) * C0 + ch0) + k);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    xo[j][k] = 0.f;
+                    if (MODE != MODE_HEAD && pv[j] && lane * 4 + k < Cf) {
+                        const size_t gi = static_cast<size_t>(b) * nper + static_cast<long long>(lane * 4 + k) * hw + pix[j];
+                        xo[j][k] = MODE == MODE_INCONV ? __ldg(A.x_in + gi) : A.sch.x[gi];
                     }
                 }
             }
 #pragma unroll
             for (int j = 0; j < NPB; ++j) {
-                const int px = pb + j * NY + ty;
-                float xn_mine = xo[j];                                           // lane co < Cf: (new) x of channel co
+                const int px = pb + j * npg + pg;
+                float xn[4] = {xo[j][0], xo[j][1], xo[j][2], xo[j][3]};       // (new) x of this lane's channel quad
                 if (MODE != MODE_INCONV) {
                     float part[kMaxCf];
-                    float4 y;
-                    y.x = silu_f(fmaf(hv[j].x, ca.x, cb.x));
-                    y.y = silu_f(fmaf(hv[j].y, ca.y, cb.y));
-                    y.z = silu_f(fmaf(hv[j].z, ca.z, cb.z));
-                    y.w = silu_f(fmaf(hv[j].w, ca.w, cb.w));
+#pragma unroll
+                    for (int co = 0; co < kMaxCf; ++co) part[co] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < kBndMaxNV; ++k) {
+                        if (k < NV) {
+                            const float4 ca = *reinterpret_cast<const float4*>(coefA + ch0 + 4 * k);
+                            const float4 cb = *reinterpret_cast<const float4*>(coefB + ch0 + 4 * k);
+                            float4 y;
+                            y.x = silu_f(fmaf(hv[j][k].x, ca.x, cb.x));
+                            y.y = silu_f(fmaf(hv[j][k].y, ca.y, cb.y));
+                            y.z = silu_f(fmaf(hv[j][k].z, ca.z, cb.z));
+                            y.w = silu_f(fmaf(hv[j][k].w, ca.w, cb.w));
+#pragma unroll
+                            for (int co = 0; co < kMaxCf; ++co) {
+                                if (co < Cf) {
+                                    const float4 w4 = *reinterpret_cast<const float4*>(wout + co * C0 + ch0 + 4 * k);
+                                    part[co] = fmaf(y.x, w4.x, fmaf(y.y, w4.y, fmaf(y.z, w4.z, fmaf(y.w, w4.w, part[co]))));
+                                }
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int co = 0; co < kMaxCf; ++co) {
                         if (co < Cf) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(wout + co * C0 + tx * 4);
-                            part[co] = fmaf(y.x, w4.x, fmaf(y.y, w4.y, fmaf(y.z, w4.z, y.w * w4.w)));
+                            part[co] += __shfl_xor_sync(0xffffffffu, part[co], 1, 4);
+                            part[co] += __shfl_xor_sync(0xffffffffu, part[co], 2, 4);
                         }
                     }
-                    for (int off = LG >> 1; off > 0; off >>= 1) {
-#pragma unroll
-                        for (int co = 0; co < kMaxCf; ++co)
-                            if (co < Cf) part[co] += __shfl_xor_sync(0xffffffffu, part[co], off, LG);
-                    }
-                    // lane co owns output channel co of this pixel
-                    float mo = 0.f;
+                    // this lane's quad of model outputs
+                    float mo[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int co = 0; co < kMaxCf; ++co)
-                        if (co < Cf && tx == co) mo = part[co] + bout[co];
-                    float nv = 0.f;
-                    if (MODE == MODE_FUSED && !A.sch.noise) {
-                        // one Philox block per channel quad: the quad's first lane draws, the other three fetch their component
-                        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (pv[j] && tx < 4 * nq && (tx & 3) == 0)
-                            z = philox_normal4(A.sch.seed, A.sch.sample_base + b, static_cast<uint32_t>(t),
-                                               static_cast<uint32_t>(pe[j] * nq + (tx >> 2)));
-                        const int leader = tx & ~3;
-                        const float zx = __shfl_sync(0xffffffffu, z.x, leader, LG), zy = __shfl_sync(0xffffffffu, z.y, leader, LG);
-                        const float zz = __shfl_sync(0xffffffffu, z.z, leader, LG), zw = __shfl_sync(0xffffffffu, z.w, leader, LG);
-                        const int k = tx & 3;
-                        nv = k == 0 ? zx : (k == 1 ? zy : (k == 2 ? zz : zw));
-                    }
-                    if (pv[j] && tx < Cf) {
-                        const long long e = static_cast<long long>(tx) * Hc * Wc + pe[j];
-                        if (MODE == MODE_HEAD) A.model_out[static_cast<size_t>(b) * nper + e] = mo;
-                        else xn_mine = sched_elem(e, mo, xo[j], nv);
+                        if (co < Cf && (co >> 2) == lane) mo[co & 3] = part[co] + bout[co];
+                    if (pv[j] && lane < nq) {
+                        if (MODE == MODE_HEAD) {
+                            for (int k = 0; k < 4 && lane * 4 + k < Cf; ++k)
+                                A.model_out[static_cast<size_t>(b) * nper + static_cast<long long>(lane * 4 + k) * hw + pix[j]] = mo[k];
+                        } else {
+                            sched_quad(lane, pix[j], mo, xo[j], xn);
+                        }
                     }
                 }
                 if (MODE != MODE_HEAD) {
-                    float4 a = *reinterpret_cast<const float4*>(bin + tx * 4);
+                    float4 a[kBndMaxNV];
+#pragma unroll
+                    for (int k = 0; k < kBndMaxNV; ++k)
+                        if (k < NV) a[k] = *reinterpret_cast<const float4*>(bin + ch0 + 4 * k);
 #pragma unroll
                     for (int cc = 0; cc < kMaxCf; ++cc) {
                         if (cc < Cf) {
-                            const float xv = __shfl_sync(0xffffffffu, xn_mine, cc, LG);
-                            const float4 w4 = *reinterpret_cast<const float4*>(win + cc * C0 + tx * 4);
-                            a.x = fmaf(xv, w4.x, a.x); a.y = fmaf(xv, w4.y, a.y); a.z = fmaf(xv, w4.z, a.z); a.w = fmaf(xv, w4.w, a.w);
+                            const int kk = cc & 3;
+                            const float mine = kk == 0 ? xn[0] : (kk == 1 ? xn[1] : (kk == 2 ? xn[2] : xn[3]));
+                            const float xv = __shfl_sync(0xffffffffu, mine, cc >> 2, 4);
+#pragma unroll
+                            for (int k = 0; k < kBndMaxNV; ++k) {
+                                if (k < NV) {
+                                    const float4 w4 = *reinterpret_cast<const float4*>(win + cc * C0 + ch0 + 4 * k);
+                                    a[k].x = fmaf(xv, w4.x, a[k].x); a[k].y = fmaf(xv, w4.y, a[k].y);
+                                    a[k].z = fmaf(xv, w4.z, a[k].z); a[k].w = fmaf(xv, w4.w, a[k].w);
+                                }
+                            }
                         }
                     }
                     if (pv[j]) {
-                        *reinterpret_cast<float4*>(h0p + static_cast<size_t>(px) * C0 + tx * 4) = a;
-                        acc_sq(s, q, a);
+#pragma unroll
+                        for (int k = 0; k < kBndMaxNV; ++k) {
+                            if (k < NV) {
+                                *reinterpret_cast<float4*>(h0p + static_cast<size_t>(px) * C0 + ch0 + 4 * k) = a[k];
+                                acc_sq(s[k], q[k], a[k]);
+                            }
+                        }
                     }
                 }
             }
         }
         if (MODE != MODE_HEAD && A.sink.partial) {
+            // per-channel (sum, sum-sq) over this CTA's pixels: red[which][pg][C0], then fixed-order column sums
             __syncthreads();
-            stats_block_partial(A.sink, s, q, b, plane, slot, nslots, red);
+#pragma unroll
+            for (int k = 0; k < kBndMaxNV; ++k) {
+                if (k < NV) {
+                    *reinterpret_cast<float4*>(red + (static_cast<size_t>(0) * npg + pg) * C0 + ch0 + 4 * k) = s[k];
+                    *reinterpret_cast<float4*>(red + (static_cast<size_t>(1) * npg + pg) * C0 + ch0 + 4 * k) = q[k];
+                }
+            }
+            __syncthreads();
+            float* tot = coefA;         // coefA/coefB (2*C0 floats) are free now
+            for (int i = tid; i < 2 * C0; i += nthr) {
+                const int which = i / C0, c = i - which * C0;
+                float acc = 0.f;
+                for (int g = 0; g < npg; ++g) acc += red[(static_cast<size_t>(which) * npg + g) * C0 + c];
+                tot[i] = acc;
+            }
+            __syncthreads();
+            const int cpg = C0 / kGroups;
+            if (tid < 2 * kGroups) {
+                const int g = tid >> 1, which = tid & 1;
+                double acc = 0.0;
+                for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(tot[which * C0 + c]);
+                A.sink.partial[((static_cast<size_t>(b) * 3 + plane) * A.sink.nslots + slot) * (kGroups * 2) + g * 2 + which] = static_cast<float>(acc);
+            }
         }
     }
     if (MODE == MODE_FUSED && A.sch.advance) {

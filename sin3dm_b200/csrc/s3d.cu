@@ -477,6 +477,12 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_gn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_FUSED, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_HEAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_INCONV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_FUSED, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_HEAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_INCONV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kRollSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kRollSmemBytes));
@@ -1005,12 +1011,11 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     // ---- in_conv
     const int c0 = ch_of(c, 0);
     ActF h = pb.allocF(0, c0, "in_conv");
-    S3D_CHECK(c0 / 4 == 16 || c0 / 4 == 32, "channel_mult[0] * model_channels must be 64 or 128 (boundary kernels use one lane group per pixel)");
+    S3D_CHECK(c0 == 64 || c0 == 128, "channel_mult[0] * model_channels must be 64 or 128 (boundary kernels: 4 lanes per pixel, <= 32 channels per lane)");
     S3D_CHECK(c.in_channels <= kMaxCf && c.out_channels <= kMaxCf, "at most 16 triplane channels are supported");
-    const int bnd_lg = c0 / 4, bnd_ny = 256 / bnd_lg;
     const int bnd_slots = std::max(1, std::min(128, pb.max_px(0) / 64));
     auto bnd_smem = [&](int Cf) {
-        return sizeof(float) * (static_cast<size_t>(2) * c0 + 2 * static_cast<size_t>(Cf) * c0 + Cf + c0 + static_cast<size_t>(bnd_ny * 2 + 2) * c0);
+        return sizeof(float) * (static_cast<size_t>(2) * c0 + 2 * static_cast<size_t>(Cf) * c0 + Cf + c0 + static_cast<size_t>(2) * 64 * c0);
     };
     BoundaryArgs bnd{};      // fields shared by the three modes
     bnd.d = pb.dims[0];
@@ -1029,7 +1034,8 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
             Al.Cf = Cin;
             Al.x_in = P->x;
             Al.sink = PlanBuilder::live_sink(in_box);
-            launch(k_boundary<MODE_INCONV>, dim3(bnd_slots, 3, B), dim3(bnd_lg, bnd_ny), smem, s, Al, bnd_slots);
+            if (c0 == 64) launch(k_boundary<MODE_INCONV, 4>, dim3(bnd_slots, 3, B), dim3(256), smem, s, Al, bnd_slots);
+            else launch(k_boundary<MODE_INCONV, 8>, dim3(bnd_slots, 3, B), dim3(256), smem, s, Al, bnd_slots);
             LAUNCH_CHECK("k_boundary<in_conv>");
         });
     }
@@ -1083,7 +1089,8 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
             Al.Cf = Cout;
             Al.st = PlanBuilder::live_src(st, P);
             Al.model_out = P->out;
-            launch(k_boundary<MODE_HEAD>, dim3(bnd_slots, 4, B), dim3(bnd_lg, bnd_ny), smem, s, Al, bnd_slots);
+            if (c0 == 64) launch(k_boundary<MODE_HEAD, 4>, dim3(bnd_slots, 4, B), dim3(256), smem, s, Al, bnd_slots);
+            else launch(k_boundary<MODE_HEAD, 8>, dim3(bnd_slots, 4, B), dim3(256), smem, s, Al, bnd_slots);
             LAUNCH_CHECK("k_boundary<head>");
         });
         if (c.in_channels == c.out_channels) {
@@ -1093,7 +1100,8 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
                 Al.st = PlanBuilder::live_src(st, P);
                 Al.sink = PlanBuilder::live_sink(in_box);
                 Al.sch = sch;
-                launch(k_boundary<MODE_FUSED>, dim3(bnd_slots, 4, B), dim3(bnd_lg, bnd_ny), smem, s, Al, bnd_slots);
+                if (c0 == 64) launch(k_boundary<MODE_FUSED, 4>, dim3(bnd_slots, 4, B), dim3(256), smem, s, Al, bnd_slots);
+            else launch(k_boundary<MODE_FUSED, 8>, dim3(bnd_slots, 4, B), dim3(256), smem, s, Al, bnd_slots);
                 LAUNCH_CHECK("k_boundary<fused>");
             };
         }
@@ -1459,24 +1467,46 @@ int s3d_unet_profile_ops(s3d_unet* u, int iters, float* ms_out, void* stream) {
     CUDA_TRY(cudaSetDevice(u->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = P->ops.size();
-    std::vector<cudaEvent_t> ev(2 * n);
+    // The ops are captured into ONE graph with an event-record node between consecutive launches and the graph is replayed
+    // back to back: op i's time = event[i+1] - event[i] in steady state (warm caches, graph launch latencies), which is what
+    // the sampling loop sees.  Eager launches would mostly measure the host's launch rate at these kernel sizes.
+    std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
-    std::vector<double> acc(n, 0.0);
-    for (int it = 0; it < iters + 1; ++it) {          // first pass is a warm-up
+    cudaStream_t cs;
+    CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    try {
+        CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         for (size_t i = 0; i < n; ++i) {
-            CUDA_TRY(cudaEventRecord(ev[2 * i], s));
-            P->ops[i](s);
-            CUDA_TRY(cudaEventRecord(ev[2 * i + 1], s));
+            CUDA_TRY(cudaEventRecord(ev[i], cs));
+            P->ops[i](cs);
         }
-        CUDA_TRY(cudaStreamSynchronize(s));
-        if (it == 0) continue;
-        for (size_t i = 0; i < n; ++i) {
-            float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
-            acc[i] += ms;
+        CUDA_TRY(cudaEventRecord(ev[n], cs));
+        CUDA_TRY(cudaStreamEndCapture(cs, &g));
+        CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
+        std::vector<double> acc(n, 0.0);
+        for (int it = 0; it < 3; ++it) CUDA_TRY(cudaGraphLaunch(ge, s));        // warm-up
+        for (int it = 0; it < iters; ++it) {
+            CUDA_TRY(cudaGraphLaunch(ge, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            for (size_t i = 0; i < n; ++i) {
+                float ms = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                acc[i] += ms;
+            }
         }
+        for (size_t i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
+    } catch (...) {
+        if (ge) cudaGraphExecDestroy(ge);
+        if (g) cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
+        for (auto& e : ev) cudaEventDestroy(e);
+        throw;
     }
-    for (size_t i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
+    cudaGraphExecDestroy(ge);
+    cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
     for (auto& e : ev) cudaEventDestroy(e);
     API_END
 }
