@@ -287,10 +287,12 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
         _lib.check(L.s3d_unet_profile_ops(h, 20, msv, _lib.current_stream_ptr()))
         conv_ms = conv_fl = tot_ms = 0.0
+        op_rows = []
         for i in range(nops):
             nm, fl = C.c_char_p(), C.c_double()
             _lib.check(L.s3d_unet_op_info(h, i, C.byref(nm), C.byref(fl)))
             k = nm.value.decode()
+            op_rows.append(f"{i:3d} {k:24s} {msv[i] * 1e3:9.2f} us {fl.value / 1e9:9.3f} GFLOP")
             e = per_kernel.setdefault(k, dict(launches=0, ms=0.0, dense_gflop=0.0))
             e["launches"] += 1
             e["ms"] += msv[i]
@@ -299,13 +301,25 @@ def run_ours(args, wl):
             if k == "k_conv_tc":
                 conv_ms += msv[i]
                 conv_fl += fl.value
+        if args.dump_ops:
+            with open(args.dump_ops, "w") as f:
+                f.write("\n".join(op_rows) + f"\nsum {tot_ms * 1e3:.2f} us; step in the loop {ms / K * 1e3:.2f} us\n")
         peaks = load_peaks()
         if conv_ms > 0:
             ach = conv_fl / (conv_ms * 1e-3) / 1e12
+            traffic = None
+            try:        # DRAM bytes per conv launch from the committed ncu --set full capture of this workload
+                tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_conv_traffic.json")))
+                if tj["workload"] == args.workload and B == 1:
+                    traffic = tj["traffic_bytes_per_launch"]
+            except (OSError, KeyError, ValueError):
+                pass
             roof = dict(bound="tensor", kernel="k_conv_tc (8 launches/step, fp16x3 split => 3 tcgen05.mma per dense MAC tile)",
-                        achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=None,
+                        achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=traffic,
+                        traffic_unit="DRAM bytes per k_conv_tc launch (mean of the 8 launches of a step; profiles/r1_summary.md)",
                         peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
                         flops_per_step_dense=conv_fl, conv_ms_per_step=conv_ms, conv_share_of_event_timed_step=conv_ms / tot_ms,
+                        timing="graph replay with event-record nodes" if L.s3d_unet_profile_mode(h) == 1 else "eager launches",
                         note="achieved = dense algorithmic conv FLOPs (rollout channels counted, SURVEY §8d) / summed CUDA-event "
                              "time of the conv launches of one step; executed MMA FLOPs are the same number (1/3 after the "
                              "exact rollout fold, x3 for the hi/lo split)")
@@ -354,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default=None, help="write the per-launch steady-state times of one step to this file")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -77,9 +77,13 @@ int64_t s3d_unet_workspace_bytes(const s3d_unet* u);
 /* Launch list of the current plan: kernel name and the dense algorithmic FLOPs the op stands for (convs). */
 int s3d_unet_op_count(const s3d_unet* u);
 int s3d_unet_op_info(const s3d_unet* u, int index, const char** kernel, double* dense_flops);
-/* Mean device time (ms) of every op of the plan, CUDA events around each launch on `stream`; synchronises.
+/* Mean device time (ms) of every op of the plan; synchronises.  The step is captured into one CUDA graph with an
+ * event-record node before every launch and replayed `iters` times on `stream` (steady-state times, as the sampling
+ * loop sees them); if the driver refuses that, falls back to eager launches with events around each.
  * Uses the tensors bound by the last forward / sampling loop (bench.py's roofline leg). */
 int s3d_unet_profile_ops(s3d_unet* u, int iters, float* ms_out, void* stream);
+/* How the last s3d_unet_profile_ops measured: 1 = graph replay, 0 = eager launches, -1 = never ran. */
+int s3d_unet_profile_mode(const s3d_unet* u);
 
 /* ---- scheduler step (replaces p_sample / ddim_sample / ddim_reverse_sample element-wise math) ----
  * coef_dev is [T][S3D_NCOEF] fp32, built by the host mirror from the fp64 tables exactly as

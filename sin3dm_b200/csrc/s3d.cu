@@ -212,6 +212,7 @@ struct s3d_unet {
     int num_sms = 148;
     bool fuse_roll = true;   // S3D_FUSE_ROLL=0 launches the rollout 1-D GEMM separately
     bool halo_bo_kw = false;
+    int profile_mode = -1;   // last s3d_unet_profile_ops: 1 = graph replay with event nodes, 0 = eager launches
 };
 
 static int ch_of(const s3d_unet_config& c, int level) { return c.channel_mult[level] * c.model_channels; }
@@ -1467,49 +1468,77 @@ int s3d_unet_profile_ops(s3d_unet* u, int iters, float* ms_out, void* stream) {
     CUDA_TRY(cudaSetDevice(u->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = P->ops.size();
-    // The ops are captured into ONE graph with an event-record node between consecutive launches and the graph is replayed
-    // back to back: op i's time = event[i+1] - event[i] in steady state (warm caches, graph launch latencies), which is what
-    // the sampling loop sees.  Eager launches would mostly measure the host's launch rate at these kernel sizes.
-    std::vector<cudaEvent_t> ev(n + 1);
-    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
-    cudaStream_t cs;
-    CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    cudaGraph_t g = nullptr;
-    cudaGraphExec_t ge = nullptr;
-    try {
-        CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        for (size_t i = 0; i < n; ++i) {
-            CUDA_TRY(cudaEventRecord(ev[i], cs));
-            P->ops[i](cs);
+    std::vector<double> acc(n, 0.0);
+    // Preferred: the ops are captured into ONE graph with an external event-record node between consecutive launches and
+    // the graph is replayed: op i's time = event[i+1] - event[i] in steady state (warm caches, graph launch latencies),
+    // which is what the sampling loop sees.  Eager launches mostly measure the host's launch rate at these kernel sizes;
+    // they are the fallback when the driver refuses timing on graph-recorded events.
+    bool graph_ok = false;
+    {
+        std::vector<cudaEvent_t> ev(n + 1);
+        for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+        cudaStream_t cs = nullptr;
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ge = nullptr;
+        bool ok = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess;
+        bool capturing = false;
+        try {
+            if (ok) {
+                CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+                capturing = true;
+                for (size_t i = 0; i < n && ok; ++i) {
+                    ok = cudaEventRecordWithFlags(ev[i], cs, cudaEventRecordExternal) == cudaSuccess;
+                    if (ok) P->ops[i](cs);
+                }
+                ok = ok && cudaEventRecordWithFlags(ev[n], cs, cudaEventRecordExternal) == cudaSuccess;
+                capturing = false;
+                ok = (cudaStreamEndCapture(cs, &g) == cudaSuccess) && ok;
+                ok = ok && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
+            }
+            for (int it = 0; ok && it < iters + 3; ++it) {                          // 3 warm-up replays
+                ok = cudaGraphLaunch(ge, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess;
+                for (size_t i = 0; ok && i < n && it >= 3; ++i) {
+                    float ms = 0.f;
+                    ok = cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess;
+                    acc[i] += ms;
+                }
+            }
+        } catch (...) {
+            if (capturing) cudaStreamEndCapture(cs, &g);
+            ok = false;
         }
-        CUDA_TRY(cudaEventRecord(ev[n], cs));
-        CUDA_TRY(cudaStreamEndCapture(cs, &g));
-        CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
-        std::vector<double> acc(n, 0.0);
-        for (int it = 0; it < 3; ++it) CUDA_TRY(cudaGraphLaunch(ge, s));        // warm-up
-        for (int it = 0; it < iters; ++it) {
-            CUDA_TRY(cudaGraphLaunch(ge, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
+        (void)cudaGetLastError();
+        if (ge) cudaGraphExecDestroy(ge);
+        if (g) cudaGraphDestroy(g);
+        if (cs) cudaStreamDestroy(cs);
+        for (auto& e : ev) cudaEventDestroy(e);
+        graph_ok = ok;
+    }
+    if (!graph_ok) {
+        std::fill(acc.begin(), acc.end(), 0.0);
+        std::vector<cudaEvent_t> ev(2 * n);
+        for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+        for (int it = 0; it < iters + 1; ++it) {          // first pass is a warm-up
             for (size_t i = 0; i < n; ++i) {
+                CUDA_TRY(cudaEventRecord(ev[2 * i], s));
+                P->ops[i](s);
+                CUDA_TRY(cudaEventRecord(ev[2 * i + 1], s));
+            }
+            CUDA_TRY(cudaStreamSynchronize(s));
+            for (size_t i = 0; i < n && it > 0; ++i) {
                 float ms = 0.f;
-                CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                CUDA_TRY(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
                 acc[i] += ms;
             }
         }
-        for (size_t i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
-    } catch (...) {
-        if (ge) cudaGraphExecDestroy(ge);
-        if (g) cudaGraphDestroy(g);
-        cudaStreamDestroy(cs);
         for (auto& e : ev) cudaEventDestroy(e);
-        throw;
     }
-    cudaGraphExecDestroy(ge);
-    cudaGraphDestroy(g);
-    cudaStreamDestroy(cs);
-    for (auto& e : ev) cudaEventDestroy(e);
+    for (size_t i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
+    u->profile_mode = graph_ok ? 1 : 0;
     API_END
 }
+
+int s3d_unet_profile_mode(const s3d_unet* u) { return u ? u->profile_mode : -1; }
 
 int s3d_unet_debug_count(const s3d_unet* u) { return (u && u->plan) ? static_cast<int>(u->plan->named.size()) : 0; }
 
