@@ -85,6 +85,14 @@ int s3d_unet_profile_ops(s3d_unet* u, int iters, float* ms_out, void* stream);
 /* How the last s3d_unet_profile_ops measured: 1 = graph replay, 0 = eager launches, -1 = never ran. */
 int s3d_unet_profile_mode(const s3d_unet* u);
 
+/* Opt-in phase trace (bring-up / profiling): when enabled, one thread per CTA of every kernel of the plan stamps
+ * %globaltimer (ns) and clock64 at s3d_trace_slots() named points.  s3d_unet_trace_read copies the stamps of op
+ * `op_index` (-1: the scheduler kernel of s3d_sample_loop) as [max_ctas][2][slots] (0 = never stamped), then clears
+ * them; it synchronises.  Enabling / disabling drops the current launch plan.  tools/trace_step.py prints a timeline. */
+int s3d_unet_trace_enable(s3d_unet* u, int on);
+int s3d_trace_slots(void);
+int s3d_unet_trace_read(s3d_unet* u, int op_index, uint64_t* host_out, int max_ctas);
+
 /* ---- scheduler step (replaces p_sample / ddim_sample / ddim_reverse_sample element-wise math) ----
  * coef_dev is [T][S3D_NCOEF] fp32, built by the host mirror from the fp64 tables exactly as
  * _extract_into_tensor rounds them (gaussian_diffusion.py:934-947):

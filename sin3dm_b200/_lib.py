@@ -61,6 +61,9 @@ _SIGNATURES = {
     "s3d_unet_op_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double)]),
     "s3d_unet_profile_ops": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "s3d_unet_profile_mode": (C.c_int, [C.c_void_p]),
+    "s3d_unet_trace_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "s3d_trace_slots": (C.c_int, []),
+    "s3d_unet_trace_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "s3d_sched_step": (C.c_int, [C.POINTER(SchedArgs), C.c_void_p]),
     "s3d_q_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                C.c_void_p]),

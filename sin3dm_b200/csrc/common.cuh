@@ -57,6 +57,25 @@ __device__ __forceinline__ void store_split4(__half* hi_ptr, __half* lo_ptr, flo
     *reinterpret_cast<uint2*>(lo_ptr) = *reinterpret_cast<uint2*>(l);
 }
 
+// Opt-in device trace (s3d_unet_trace_enable): one thread per CTA stamps %globaltimer (ns, chip-wide) and clock64 (SM
+// cycles) at named points of a kernel; tools/trace_step.py turns the stamps into a timeline of one step.
+constexpr int kTraceSlots = 24;
+struct Trace {
+    unsigned long long* buf;   // [max_ctas][2][kTraceSlots]; nullptr: tracing off
+    int max_ctas;
+};
+__device__ __forceinline__ void trace_mark(const Trace& T, int slot) {
+    if (T.buf) {
+        const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (cta < static_cast<unsigned>(T.max_ctas)) {
+            unsigned long long g;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+            T.buf[static_cast<size_t>(cta) * 2 * kTraceSlots + slot] = g;
+            T.buf[static_cast<size_t>(cta) * 2 * kTraceSlots + kTraceSlots + slot] = static_cast<unsigned long long>(clock64());
+        }
+    }
+}
+
 // Composed-layout address of plane pixel (r, c): [H+D, W+D] with yz stored transposed.
 __device__ __forceinline__ int composed_offset(int plane, int r, int c, int H, int W, int Wc) {
     if (plane == 0) return r * Wc + c;

@@ -45,7 +45,8 @@ struct ConvTcArgs {
     int tiles_x[3];
     int tile_start[4];   // prefix sum of tiles per plane
     ConvEpi e;
-    StatsSink sink;      // GroupNorm partials of the output (sink.partial == nullptr: none); needs 64 % (Cout/32) == 0
+    StatsSink sink;      // GroupNorm group sums of the output (sink.acc == nullptr: none); needs 64 % (Cout/32) == 0
+    Trace tr;            // opt-in phase stamps (common.cuh)
     int bo_kw;           // bring-up switch (S3D_HALO_BO_KW=1): put kw into the descriptor base_offset (measured WRONG on B200:
                          // the tensor core derives the swizzle phase from the absolute shared-memory address)
 };
@@ -170,6 +171,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     int* stat_flag = reinterpret_cast<int*>(stat_tot + 2 * kBN);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // trace slots: 0 entry, 1 set-up done, 2 phase 0 done, 3 means visible to the A producer, 22 exit; per local tile lt < 3 at
+    // 4 + 6*lt: +0 first operands landed, +1 all MMAs issued, +2 epilogue addends gathered, +3 accumulator complete,
+    // +4 epilogue done, +5 A loads issued
+    if (threadIdx.x == 0) trace_mark(A.tr, 0);
     const int cblks = A.C / kBK;
     const int nskip = A.Cs / kBK;
     constexpr uint32_t kALo = kAHaloBytes, kBLo = kBBytes;
@@ -213,6 +218,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (threadIdx.x == 0) trace_mark(A.tr, 1);
     // PDL: everything above (barriers, TMEM, descriptor prefetch) and the weight-tile producer below overlap the tail of the
     // previous kernel; threads that touch activations / statistics / rollout terms wait for it first.
     pdl_trigger();
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         // ===================== TMA producer: A operand groups =====================
         if (lane == 0) {
             pdl_wait();
-            int ga = 0;
+            int ga = 0, ltp = 0;
             bool means_ready = false;
             auto slot_wait = [&](uint32_t tx) -> uint8_t* {
                 const int s = ga % Cfg::kASlots;
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 ptx::mbar_arrive_expect_tx(&fullA[s], tx);
                 return smem_a + s * Cfg::kASlotBytes;
             };
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ltp) {
                 if (t < F.n_roll) {
                     if (F.sums && !means_ready) {
                         // every CTA converts a share of the means in its phase 0: wait for all of them, then order the
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         __threadfence();
                         asm volatile("fence.proxy.async;" ::: "memory");
                         means_ready = true;
+                        trace_mark(A.tr, 3);
                     }
                     const RollTile T = roll_tile_decode(F, t);
                     for (int i = 0; i < 3 * cblks; ++i, ++ga) {
@@ -251,6 +258,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         ptx::tma_load_5d(st, &RM.a[T.src], &fullA[s], cb * kBK, T.p0 + al - 1, 0, T.b, 0);
                         if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &RM.a[T.src], &fullA[s], cb * kBK, T.p0 + al - 1, 0, T.b, 1);
                     }
+                    if (ltp < 3) trace_mark(A.tr, 4 + 6 * ltp + 5);
                     continue;
                 }
                 const ConvTile T = conv_tile_decode(A, t - F.n_roll);
@@ -266,6 +274,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     ptx::tma_load_5d(st, &M.x[T.plane], &fullA[s], j * kBK, T.w0, T.h0, T.b, 0);
                     if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &M.x[T.plane], &fullA[s], j * kBK, T.w0, T.h0, T.b, 1);
                 }
+                if (ltp < 3) trace_mark(A.tr, 4 + 6 * ltp + 5);
             }
         }
     } else if (warp == 6) {
@@ -318,6 +327,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         const int sb = gb % Cfg::kBSlots;
                         ptx::mbar_wait(&fullB[sb], (gb / Cfg::kBSlots) & 1);
                         ptx::tc_fence_after();
+                        if (first && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 0);
                         const uint32_t b_base = ptx::smem_u32(smem_b + sb * Cfg::kBSlotBytes);
                         uint64_t a_hi, a_lo;
                         if (halo) {
@@ -350,6 +360,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     ptx::umma_commit(&emptyA[sa]);        // A patch free once every tap has read it
                 }
                 ptx::umma_commit(&tmem_full_bar[as]);     // this tile's accumulators are complete
+                if (lt < 3) trace_mark(A.tr, 4 + 6 * lt + 1);
             }
         }
     } else {
@@ -382,6 +393,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             __threadfence();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et == 0) atomicAdd(&F.counters[2], 1u);
+            if (et == 0) trace_mark(A.tr, 2);
         }
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int as = lt & 1;
@@ -394,6 +406,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 const int cls = T.n0 / A.Cout, co0 = T.n0 - cls * A.Cout;
                 float* __restrict__ outp = F.R.T[T.src] + ((static_cast<size_t>(T.b) * 4 + cls) * L + pos) * A.Cout + co0;
                 ptx::mbar_wait(&tmem_full_bar[as], aph);
+                if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 3);
                 __syncwarp();
                 ptx::tc_fence_after();
 #pragma unroll
@@ -423,6 +436,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (et == 0) atomicAdd(&F.counters[0], 1u);
+                if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 4);
                 continue;
             }
             const ConvTile T = conv_tile_decode(A, t - F.n_roll);
@@ -486,10 +500,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 }
             }
             float* __restrict__ outp = A.e.out.p[plane] + px * A.Cout + n0;
+            if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 2);
             ptx::mbar_wait(&tmem_full_bar[as], aph);
+            if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 3);
             __syncwarp();
             ptx::tc_fence_after();
-            const bool do_stats = A.sink.partial != nullptr;
+            const bool do_stats = A.sink.acc != nullptr;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t v1[32], v2[32];
@@ -547,11 +563,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     const int gl = et >> 1, which = et & 1;
                     double acc = 0.0;
                     for (int cc = gl * cpg; cc < (gl + 1) * cpg; ++cc) acc += static_cast<double>(stat_tot[which * kBN + cc]);
-                    A.sink.partial[((static_cast<size_t>(b) * 3 + plane) * A.sink.nslots + T.ip) * (kGroups * 2) + (g0 + gl) * 2 + which] =
-                        static_cast<float>(acc);
+                    gn_fix_add(A.sink.acc + (static_cast<size_t>(b) * 3 + plane) * 64 + (g0 + gl) * 2 + which, acc);
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // stat_tot is reused by the next tile
             }
+            if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 4);
         }
     }
     ptx::tc_fence_before();
@@ -560,6 +576,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         __syncwarp();
         ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
+    if (threadIdx.x == 0) trace_mark(A.tr, 22);
     if (F.n_roll && threadIdx.x == 0) {
         // the last CTA to leave re-arms the counters for the next launch
         const unsigned int prev = atomicAdd(&F.counters[1], 1u);

@@ -9,65 +9,41 @@ namespace s3d {
 // =====================================================================================
 // GroupNorm statistics -> per-channel affine coefficients.
 // reference src/diffusion/nn.py:17-19 (GroupNorm32 computes in fp32), unet_triplane.py:63-84, FiLM :285-297
-// Producers write one (sum, sum-sq) pair per group per CTA ("slot") in fp64; the LAST CTA of a (sample, plane)
-// (atomic ticket) reduces the slots in a fixed order and emits, for the consumer's norm layer,
-//     y = x * coef[c][0] + coef[c][1]   ==  GroupNorm(x) * gamma + beta   (optionally * (1 + scale) + shift)
-// so consumers need no statistics pass, no shared memory and no barrier before their first load.
+// Every kernel that writes a tensor which is normalised next also adds its share of the 32 groups' (sum, sum-sq) to 64
+// accumulators per (sample, plane): 64-bit fixed point (value * 2^20) with integer atomics, so the totals are exact sums of
+// the per-CTA partials — independent of CTA order, batch composition and GPU count.  The consumer turns them into
+//     y = x * coefA[c] + coefB[c]   ==  GroupNorm(x) * gamma + beta   (optionally * (1 + scale) + shift)
+// with one 64-value load per CTA (no statistics pass, no partial-slot reduction).  The accumulators of a tensor are re-zeroed
+// by the NEXT consumer kernel in the step (its `zero` job), i.e. after their only reader has finished.
 // =====================================================================================
+constexpr double kGnFix = 1048576.0;              // 2^20
+constexpr double kGnFixInv = 1.0 / 1048576.0;
 struct StatsSink {                 // producer side
-    float* partial;           // [B][3][nslots][64]   per-slot (sum, sum-sq) of the 32 groups; nullptr: not wanted
-    int nslots;               // slot stride of `partial` (slots a plane does not use stay zero)
+    unsigned long long* acc;  // [B][3][64]  (sum, sum-sq) of the 32 groups, fixed point; nullptr: not wanted
     int C;
 };
 struct StatsSrc {                  // consumer side
-    const float* partial;     // [B][3][nslots][64]
-    int nslots;
+    const unsigned long long* acc;   // [B][3][64]
     TriCF gamma, beta;        // consumer norm parameters [C]
     const float* film;        // [rows][film_dim] or nullptr
     const int* film_row;
     int film_dim, film_off;   // scale at film_off, shift at film_off + C
+    unsigned long long* zero; // accumulators of the previous consumer's tensor (already read): re-zeroed by CTA 0
+    int zero_n;
 };
+__device__ __forceinline__ void gn_fix_add(unsigned long long* p, double v) {
+    atomicAdd(p, static_cast<unsigned long long>(__double2ll_rn(v * kGnFix)));
+}
 
-// Consumer prologue: every consumer CTA adds the producer's per-slot partial sums itself (fixed order, fp64) and turns them
-// into per-channel affine coefficients  y = x * coefA[c] + coefB[c]  ==  GroupNorm(x)*gamma+beta (optionally FiLM'ed).
-// Producers therefore need no fence, ticket or tail: the kernel boundary publishes their partials, and all loads below are
-// independent (one L2 round trip, overlapped with the caller's activation loads).
-// All threads of the CTA call it (nthr >= 64); fin: smem double[64 * 9]; coefA/coefB: smem float[C].
+// Consumer prologue (all threads of the CTA, nthr >= 64); fin: smem double[64]; coefA/coefB: smem float[C].
 __device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, int plane, int C, double n_per_group, int tid, int nthr,
                                                     double* fin, float* coefA, float* coefB) {
     const float* film = nullptr;
     if (S.film) film = S.film + static_cast<size_t>(S.film_row ? S.film_row[b] : b) * S.film_dim + S.film_off;
-    float g0 = 0.f, b0 = 0.f, f0 = 0.f, f1 = 0.f;
-    if (tid < C) {
-        g0 = __ldg(S.gamma.p[plane] + tid);
-        b0 = __ldg(S.beta.p[plane] + tid);
-        if (film) {
-            f0 = __ldg(film + tid);
-            f1 = __ldg(film + C + tid);
-        }
-    }
-    const int nsl = min(nthr >> 6, 8);                   // slices of 64 threads
-    if (tid < nsl * 64) {
-        const int slice = tid >> 6, e = tid & 63;
-        const float* pp = S.partial + (static_cast<size_t>(b) * 3 + plane) * S.nslots * 64 + e;
-        double acc = 0.0;
-        int sl = slice;
-        for (; sl + 15 * nsl < S.nslots; sl += 16 * nsl) {
-            float v[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = __ldg(pp + static_cast<size_t>(sl + k * nsl) * 64);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) acc += static_cast<double>(v[k]);
-        }
-        for (; sl < S.nslots; sl += nsl) acc += static_cast<double>(__ldg(pp + static_cast<size_t>(sl) * 64));
-        fin[64 + slice * 64 + e] = acc;
-    }
-    __syncthreads();
-    if (tid < 64) {
-        double acc = 0.0;
-        for (int k = 0; k < nsl; ++k) acc += fin[64 + k * 64 + tid];
-        fin[tid] = acc;
-    }
+    if (tid < 64)
+        fin[tid] = static_cast<double>(static_cast<long long>(__ldcg(S.acc + (static_cast<size_t>(b) * 3 + plane) * 64 + tid))) * kGnFixInv;
+    if (S.zero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        for (int i = tid; i < S.zero_n; i += nthr) S.zero[i] = 0ull;
     __syncthreads();
     const int cpg = C / kGroups;
     const double inv_n = 1.0 / n_per_group;
@@ -77,11 +53,10 @@ __device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, in
         const double mean = fin[g * 2] * inv_n;
         const float var = fmaxf(static_cast<float>(fin[g * 2 + 1] * inv_n - mean * mean), 0.f);
         const float rstd = rsqrtf(var + kGnEps);
-        const bool first = c == tid;
-        float ga = (first ? g0 : S.gamma.p[plane][c]) * rstd;
-        float be = (first ? b0 : S.beta.p[plane][c]) - static_cast<float>(mean) * ga;
+        float ga = __ldg(S.gamma.p[plane] + c) * rstd;
+        float be = __ldg(S.beta.p[plane] + c) - static_cast<float>(mean) * ga;
         if (film) {
-            const float sc = 1.f + (first ? f0 : film[c]), sh = first ? f1 : film[C + c];
+            const float sc = 1.f + __ldg(film + c), sh = __ldg(film + C + c);
             ga *= sc;
             be = fmaf(be, sc, sh);
         }
@@ -91,10 +66,9 @@ __device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, in
     __syncthreads();
 }
 
-// Block-wide reduction of per-thread (sum, sum-sq) float4 pairs laid out as block (C/4, NY) into this CTA's slot.
+// Block-wide reduction of per-thread (sum, sum-sq) float4 pairs laid out as block (C/4, NY), added to the accumulators.
 // red: smem [(NY*2 + 2) * C] floats.
-__device__ __forceinline__ void stats_block_partial(const StatsSink& S, float4 s, float4 q, int b, int plane, int slot, int nslots,
-                                                    float* red) {
+__device__ __forceinline__ void stats_block_add(const StatsSink& S, float4 s, float4 q, int b, int plane, float* red) {
     const int C = S.C, tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
     const int tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
     float* rs = red + (ty * 2 + 0) * C + tx * 4;
@@ -111,12 +85,11 @@ __device__ __forceinline__ void stats_block_partial(const StatsSink& S, float4 s
     }
     __syncthreads();
     const int cpg = C / kGroups;
-    float* part = S.partial + ((static_cast<size_t>(b) * 3 + plane) * S.nslots + slot) * kGroups * 2;
     if (tid < 2 * kGroups) {
         const int g = tid >> 1, which = tid & 1;
         double acc = 0.0;
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(tot[which * C + c]);
-        part[g * 2 + which] = static_cast<float>(acc);
+        gn_fix_add(S.acc + (static_cast<size_t>(b) * 3 + plane) * 64 + g * 2 + which, acc);
     }
 }
 
@@ -146,7 +119,7 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink
             q.z = fmaf(v[k].z, v[k].z, q.z); q.w = fmaf(v[k].w, v[k].w, q.w);
         }
     }
-    stats_block_partial(S, s, q, b, plane, slot, nslots, red);
+    stats_block_add(S, s, q, b, plane, red);
 }
 
 // -------------------------------------------------------------------------------------
@@ -156,7 +129,7 @@ __global__ void __launch_bounds__(1024) k_gn_stats(TriCF x, TriDims d, StatsSink
 // grid (nslots, 3, B)
 // -------------------------------------------------------------------------------------
 #define S3D_PRODUCER_TAIL(S, s, q, npx, red) \
-    if ((S).partial) stats_block_partial(S, s, q, b, plane, slot, nslots, red);
+    if ((S).acc) stats_block_add(S, s, q, b, plane, red);
 
 __device__ __forceinline__ void acc_sq(float4& s, float4& q, const float4& v) {
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -164,9 +137,11 @@ __device__ __forceinline__ void acc_sq(float4& s, float4& q, const float4& v) {
 }
 
 // 2x2 average pool, stride 2, floor on odd sizes.  reference unet_triplane.py:127-145.  smem: red[(NY*2+2)*C]
-__global__ void __launch_bounds__(256) k_avgpool2(TriCF x, TriDims din, TriDims dout, int C, TriF out, StatsSink S, int nslots) {
+__global__ void __launch_bounds__(256) k_avgpool2(TriCF x, TriDims din, TriDims dout, int C, TriF out, StatsSink S, int nslots,
+                                                  Trace tr) {
     pdl_wait();
     pdl_trigger();
+    if (threadIdx.x + threadIdx.y == 0) trace_mark(tr, 0);
     extern __shared__ float smi[];
     const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
     const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
@@ -190,7 +165,9 @@ __global__ void __launch_bounds__(256) k_avgpool2(TriCF x, TriDims din, TriDims 
         op[static_cast<size_t>(px) * c4 + tx] = o;
         acc_sq(s, q, o);
     }
+    if (threadIdx.x + threadIdx.y == 0) trace_mark(tr, 1);
     S3D_PRODUCER_TAIL(S, s, q, npx, smi)
+    if (threadIdx.x + threadIdx.y == 0) trace_mark(tr, 2);
 }
 
 // Bilinear x2 upsample (align_corners=False) [+ bilinear resize to the skip's size when they differ]
@@ -204,9 +181,10 @@ __device__ __forceinline__ void bilin_src(int dst, int in_size, float scale, int
 }
 
 __global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, TriCF skip, int Cs, TriDims dout, TriF out,
-                                               int do_up, StatsSink S, int nslots) {
+                                               int do_up, StatsSink S, int nslots, Trace tr) {
     pdl_wait();
     pdl_trigger();
+    if (threadIdx.x + threadIdx.y == 0) trace_mark(tr, 0);
     extern __shared__ float smi[];
     const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
     const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
@@ -241,31 +219,85 @@ __global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, 
         return lerp4(at(r0, c0), at(r0, c1), at(r1, c0), at(r1, c1), lr, lc);
     };
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-    for (int px = p0 + ty; px < p1; px += NY) {
-        const int r = px / ocols, c = px - r * ocols;
-        float4 o;
-        if (tx >= u4) {
-            o = __ldg(sp + static_cast<size_t>(px) * (Cs / 4) + (tx - u4));
-        } else if (!resize) {
-            o = up_at(r, c);
+    // Four pixels per iteration with every gather of the batch issued before the first use (the loop is latency bound
+    // otherwise).  The common case (plain x2 upsample, or plain copy) is written branch-free for that; the resize-to-skip
+    // case (odd sizes) takes 16 gathers per pixel and goes one pixel at a time.
+    constexpr int kUpBatch = 4;
+    const bool is_skip = tx >= u4;
+    for (int pb = p0 + ty; pb < p1; pb += kUpBatch * NY) {
+        float4 o[kUpBatch];
+        if (resize && !is_skip) {
+#pragma unroll
+            for (int j = 0; j < kUpBatch; ++j) {
+                const int px = pb + j * NY;
+                o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (px < p1) {
+                    const int r = px / ocols, c = px - r * ocols;
+                    int r0, r1, c0, c1;
+                    float lr, lc;
+                    bilin_src(r, urows, static_cast<float>(urows) / static_cast<float>(orows), r0, r1, lr);
+                    bilin_src(c, ucols, static_cast<float>(ucols) / static_cast<float>(ocols), c0, c1, lc);
+                    o[j] = lerp4(up_at(r0, c0), up_at(r0, c1), up_at(r1, c0), up_at(r1, c1), lr, lc);
+                }
+            }
         } else {
-            int r0, r1, c0, c1;
-            float lr, lc;
-            bilin_src(r, urows, static_cast<float>(urows) / static_cast<float>(orows), r0, r1, lr);
-            bilin_src(c, ucols, static_cast<float>(ucols) / static_cast<float>(ocols), c0, c1, lc);
-            o = lerp4(up_at(r0, c0), up_at(r0, c1), up_at(r1, c0), up_at(r1, c1), lr, lc);
+            const float4* src[kUpBatch][4];
+            float lr[kUpBatch], lc[kUpBatch];
+#pragma unroll
+            for (int j = 0; j < kUpBatch; ++j) {
+                const int px = min(pb + j * NY, p1 - 1);          // clamped: the tail re-reads a valid pixel and drops it
+                const int r = px / ocols, c = px - r * ocols;
+                if (is_skip) {
+                    src[j][0] = src[j][1] = src[j][2] = src[j][3] = sp + static_cast<size_t>(px) * (Cs / 4) + (tx - u4);
+                    lr[j] = lc[j] = 0.f;
+                } else {
+                    int r0 = r, r1 = r, c0 = c, c1 = c;
+                    lr[j] = lc[j] = 0.f;
+                    if (do_up) {
+                        bilin_src(r, lrows, 0.5f, r0, r1, lr[j]);
+                        bilin_src(c, lcols, 0.5f, c0, c1, lc[j]);
+                    }
+                    src[j][0] = lp + (static_cast<size_t>(r0) * lcols + c0) * u4 + tx;
+                    src[j][1] = lp + (static_cast<size_t>(r0) * lcols + c1) * u4 + tx;
+                    src[j][2] = lp + (static_cast<size_t>(r1) * lcols + c0) * u4 + tx;
+                    src[j][3] = lp + (static_cast<size_t>(r1) * lcols + c1) * u4 + tx;
+                }
+            }
+            float4 g[kUpBatch][4];
+            const bool one = is_skip || !do_up;                   // a single source element per pixel
+#pragma unroll
+            for (int j = 0; j < kUpBatch; ++j) {
+                g[j][0] = __ldg(src[j][0]);
+                if (!one) {
+                    g[j][1] = __ldg(src[j][1]);
+                    g[j][2] = __ldg(src[j][2]);
+                    g[j][3] = __ldg(src[j][3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kUpBatch; ++j) o[j] = one ? g[j][0] : lerp4(g[j][0], g[j][1], g[j][2], g[j][3], lr[j], lc[j]);
         }
-        op[static_cast<size_t>(px) * c4 + tx] = o;
-        acc_sq(s, q, o);
+#pragma unroll
+        for (int j = 0; j < kUpBatch; ++j) {
+            const int px = pb + j * NY;
+            if (px < p1) {
+                op[static_cast<size_t>(px) * c4 + tx] = o[j];
+                acc_sq(s, q, o[j]);
+            }
+        }
     }
+    if (threadIdx.x + threadIdx.y == 0) trace_mark(tr, 1);
     S3D_PRODUCER_TAIL(S, s, q, npx, smi)
+    if (threadIdx.x + threadIdx.y == 0) trace_mark(tr, 2);
 }
 
 // =====================================================================================
 // Fused GroupNorm-apply (+FiLM) + SiLU -> fp16 (hi, lo) conv operand, plus the rollout axis means.
 // reference unet_triplane.py:63-95 (norm, SiLU), :285-297 (FiLM), :37-46 (axis means)
-// One CTA = an 8-row x ny-column tile of one plane of one sample (one column per thread, 8 independent loads in flight;
-// the per-CTA statistics prologue is amortised over 8 rows).  grid (max tiles, 3, B), block (C/4, ny).
+// One CTA = an 8-row x (ny * ncg)-column tile of one plane of one sample, walked as ncg groups of ny columns (one column per
+// thread per group, 8 independent loads in flight, the next group's loads issued under the current group's math; the per-CTA
+// statistics prologue is amortised over the tile).  The host picks ncg so that the launch is a single wave when it can be.
+// grid (max tiles, 3, B), block (C/4, ny).
 // Axis sums are accumulated as 64-bit fixed point (value * 2^24) with integer atomics: exact, hence independent of
 // tile order / batch composition / GPU count.  sums[b][seg_off[plane*2+kind] + pos][C], kind 0 = sum over columns
 // (indexed by row), kind 1 = sum over rows (indexed by column).  The CTA that completes a row strip / a column tile
@@ -290,6 +322,8 @@ struct GnSiluArgs {
     int total_tickets;
     int seg_off[6];
     int total_len;
+    Trace tr;                 // slots: 0 entry, 1 coefficients ready, 2 column atomics issued, 3 row atomics + operand stores issued
+    int ncg;                  // column groups per CTA: the CTA's tile is kGsRows rows x (blockDim.y * ncg) columns
     int finalize;             // 1: the last CTA of a strip / column tile converts the sums to fp16 means itself (stand-alone roll
                               //    kernels); 0: k_conv_tc does it in its phase 0 and this kernel ends right after the atomics
 };
@@ -314,20 +348,21 @@ __device__ __forceinline__ void means_finalize(unsigned long long* sp, __half* m
 __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
     pdl_wait();
     pdl_trigger();
-    extern __shared__ float gsm[];   // coefA[C], coefB[C], red[ny][4][C]
+    extern __shared__ float gsm[];   // coefA[C], coefB[C], red[ny][8][C]
     __shared__ int last_row, last_col;
-    __shared__ double fin[64 * 9];
+    __shared__ double fin[64];
     const int plane = blockIdx.y, b = blockIdx.z;
     const int rows = A.d.rows[plane], cols = A.d.cols[plane], C = A.C;
     const int tx = threadIdx.x, ty = threadIdx.y, ny = blockDim.y;
     const int tid = ty * blockDim.x + tx, nthr = blockDim.x * ny;
-    const int ctiles = (cols + ny - 1) / ny, strips = (rows + kGsRows - 1) / kGsRows;
+    const int ncg = A.ncg, tw = ny * ncg;                    // the CTA's tile is kGsRows x tw pixels, ncg column groups of ny
+    const int ctiles = (cols + tw - 1) / tw, strips = (rows + kGsRows - 1) / kGsRows;
     if (static_cast<int>(blockIdx.x) >= ctiles * strips) return;
+    if (tid == 0) trace_mark(A.tr, 0);
     const int strip = blockIdx.x / ctiles, ct = blockIdx.x - strip * ctiles;
     const int r0 = strip * kGsRows;
     const int nr = min(kGsRows, rows - r0);
-    const int c = ct * ny + ty;
-    const bool cvalid = c < cols;
+    const int cbase = ct * tw;
     float* coefA = gsm;
     float* coefB = gsm + C;
     float* red = gsm + 2 * C;
@@ -337,33 +372,18 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
     const float* xp = A.x.p[plane] + sample_off;
     __half* ap = A.a.p[plane] + sample_off;
     __half* xq = A.x16.p[plane] ? A.x16.p[plane] + sample_off : nullptr;
-    float4 y[kGsRows], v[kGsRows];
-#pragma unroll
-    for (int r = 0; r < kGsRows; ++r) y[r] = v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cvalid) {
+    float4 v[kGsRows], y[kGsRows];
+    auto load_group = [&](int cg) {
+        const int c = cbase + cg * ny + ty;
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r)
-            if (r < nr) v[r] = __ldg(reinterpret_cast<const float4*>(xp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4));
-    }
-    // the group sums arrive while the activation loads above are in flight
-    stats_coef_prologue(A.st, b, plane, C, static_cast<double>(rows) * cols * (C / kGroups), tid, nthr, fin, coefA, coefB);
-    const float4 ca = *reinterpret_cast<const float4*>(coefA + tx * 4);
-    const float4 cb = *reinterpret_cast<const float4*>(coefB + tx * 4);
-    if (cvalid) {
-#pragma unroll
-        for (int r = 0; r < kGsRows; ++r) {
-            if (r < nr) {
-                y[r].x = silu_f(fmaf(v[r].x, ca.x, cb.x));
-                y[r].y = silu_f(fmaf(v[r].y, ca.y, cb.y));
-                y[r].z = silu_f(fmaf(v[r].z, ca.z, cb.z));
-                y[r].w = silu_f(fmaf(v[r].w, ca.w, cb.w));
-            }
-        }
-    }
-    // The operand stores are issued AFTER the axis-sum atomics and the completion tickets, so the memory fence in front of
-    // the tickets only has the handful of atomics to wait for (the stores need no ordering: the kernel boundary publishes them).
-    auto store_operands = [&]() {
-        if (!cvalid) return;
+            v[r] = (c < cols && r < nr) ? __ldg(reinterpret_cast<const float4*>(xp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // operand stores of one column group (fire and forget: the kernel boundary publishes them)
+    auto store_group = [&](int cg) {
+        const int c = cbase + cg * ny + ty;
+        if (c >= cols) return;
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r) {
             if (r < nr) {
@@ -373,25 +393,61 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
             }
         }
     };
-    if (!A.sums) {
-        store_operands();
-        return;
-    }
-    unsigned long long* sb = A.sums + static_cast<size_t>(b) * A.total_len * C;
-    unsigned long long* srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
-    unsigned long long* scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
-    if (cvalid) {
+    load_group(0);
+    // the group sums arrive while the activation loads above are in flight
+    stats_coef_prologue(A.st, b, plane, C, static_cast<double>(rows) * cols * (C / kGroups), tid, nthr, fin, coefA, coefB);
+    const float4 ca = *reinterpret_cast<const float4*>(coefA + tx * 4);
+    const float4 cb = *reinterpret_cast<const float4*>(coefB + tx * 4);
+    if (tid == 0) trace_mark(A.tr, 1);
+    unsigned long long* sb = A.sums ? A.sums + static_cast<size_t>(b) * A.total_len * C : nullptr;
+    unsigned long long* srow = A.sums ? sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C : nullptr;
+    unsigned long long* scol = A.sums ? sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C : nullptr;
+    int last_cg = 0;
+    for (int cg = 0; cg < ncg; ++cg) {
+        if (cbase + cg * ny >= cols) break;                  // uniform: no columns left for this CTA
+        const int c = cbase + cg * ny + ty;
+        const bool cvalid = c < cols;
+        if (cg > 0) {
+            store_group(cg - 1);                             // behind the previous group's atomics
+            load_group(cg);
+        }
+        last_cg = cg;
         float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r) {
+            y[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cvalid && r < nr) {
+                y[r].x = silu_f(fmaf(v[r].x, ca.x, cb.x));
+                y[r].y = silu_f(fmaf(v[r].y, ca.y, cb.y));
+                y[r].z = silu_f(fmaf(v[r].z, ca.z, cb.z));
+                y[r].w = silu_f(fmaf(v[r].w, ca.w, cb.w));
+            }
             cacc.x += y[r].x; cacc.y += y[r].y; cacc.z += y[r].z; cacc.w += y[r].w;
         }
-        unsigned long long* p = scol + static_cast<size_t>(c) * C + tx * 4;
-        fix_add(p, cacc.x); fix_add(p + 1, cacc.y); fix_add(p + 2, cacc.z); fix_add(p + 3, cacc.w);
-    }
+        if (!A.sums) continue;
+        // the axis-sum atomics go out first: they are what the kernel's completion waits for
+        if (cvalid) {
+            unsigned long long* p = scol + static_cast<size_t>(c) * C + tx * 4;
+            fix_add(p, cacc.x); fix_add(p + 1, cacc.y); fix_add(p + 2, cacc.z); fix_add(p + 3, cacc.w);
+        }
+        // row sums of this thread's column accumulate in its own shared-memory cell across the column groups
 #pragma unroll
-    for (int r = 0; r < kGsRows; ++r)
-        *reinterpret_cast<float4*>(red + (static_cast<size_t>(ty) * kGsRows + r) * C + tx * 4) = y[r];
+        for (int r = 0; r < kGsRows; ++r) {
+            float4* cell = reinterpret_cast<float4*>(red + (static_cast<size_t>(ty) * kGsRows + r) * C + tx * 4);
+            if (cg == 0) {
+                *cell = y[r];
+            } else {
+                float4 o = *cell;
+                o.x += y[r].x; o.y += y[r].y; o.z += y[r].z; o.w += y[r].w;
+                *cell = o;
+            }
+        }
+    }
+    if (tid == 0) trace_mark(A.tr, 2);
+    if (!A.sums) {
+        store_group(last_cg);
+        return;
+    }
     __syncthreads();
     for (int i = tid; i < nr * C; i += nthr) {
         int r = i / C, ch = i - r * C;
@@ -399,10 +455,9 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
         for (int yy = 0; yy < ny; ++yy) acc += red[(static_cast<size_t>(yy) * kGsRows + r) * C + ch];
         fix_add(srow + static_cast<size_t>(r0 + r) * C + ch, acc);
     }
-    if (!A.finalize) {
-        store_operands();
-        return;
-    }
+    store_group(last_cg);
+    if (tid == 0) trace_mark(A.tr, 3);
+    if (!A.finalize) return;
     // ---- whoever completes this row strip / this column tile converts it to fp16 means and re-zeroes it
     __threadfence();
     __syncthreads();
@@ -418,7 +473,6 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
             if (last_col) tk[strips + ct] = 0u;
         }
     }
-    store_operands();                  // overlaps the ticket round trip
     __syncthreads();
     if (!last_row && !last_col) return;
     __threadfence();
@@ -429,8 +483,8 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
         means_finalize(sb + o, mb + o, mb + mlo + o, nr * C, kFixInv / static_cast<double>(cols), tid, nthr);
     }
     if (last_col) {
-        const int c0 = ct * ny, nc = min(ny, cols - c0);
-        const size_t o = (static_cast<size_t>(A.seg_off[plane * 2 + 1]) + c0) * C;
+        const int nc = min(tw, cols - cbase);
+        const size_t o = (static_cast<size_t>(A.seg_off[plane * 2 + 1]) + cbase) * C;
         means_finalize(sb + o, mb + o, mb + mlo + o, nc * C, kFixInv / static_cast<double>(rows), tid, nthr);
     }
 }
@@ -646,6 +700,7 @@ struct SchedArgs {
     int advance;            // loop mode: t_idx[b] -= 1 after the step (by the last CTA)
     unsigned int* ticket;
     long long noise_step_stride;   // loop mode with a noise buffer: noise + t*stride
+    Trace tr;               // slots: 0 entry, 1 element loop done
 };
 
 __device__ __forceinline__ float sched_one(const SchedArgs& A, const float* cf, float nz, float out, float x, float nzv,
@@ -687,6 +742,7 @@ __global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
     pdl_wait();
     pdl_trigger();
     __shared__ bool is_last;
+    if (threadIdx.x == 0) trace_mark(A.tr, 0);
     const int b = blockIdx.y;
     const int t = A.t_idx[b];
     float cf[12];
@@ -729,6 +785,7 @@ __global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
             }
         }
     }
+    if (threadIdx.x == 0) trace_mark(A.tr, 1);
     if (!A.advance) return;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -770,293 +827,6 @@ __global__ void __launch_bounds__(256) k_philox_normal(float* __restrict__ out, 
         const float zz[4] = {z.x, z.y, z.z, z.w};
         for (int k = 0; k < 4 && quad * 4 + k < C; ++k)
             out[(static_cast<size_t>(b) * C + quad * 4 + k) * hw + pix] = zz[k];
-    }
-}
-
-// =====================================================================================
-// Step boundary: the output head, the scheduler update and the next step's input conv are all per-pixel maps, so the
-// sampling loop runs them as ONE kernel (MODE_FUSED); the stand-alone forward uses the same code as two kernels
-// (MODE_INCONV at the start, MODE_HEAD at the end), which keeps both paths bit-identical.
-//   head   : GroupNorm + SiLU + 1x1 conv C0 -> Cf, composed NCHW output        reference unet_triplane.py:441-445
-//   sched  : DDPM / DDIM update of x with the model output of this pixel        (see k_sched_step)
-//   in_conv: 1x1 conv Cf -> C0 off the composed tensor + GroupNorm partials      reference unet_triplane.py:378
-// A pixel is handled by 4 adjacent lanes; lane l owns C0/4 consecutive hidden channels (as NV = C0/16 float4 chunks) and the
-// triplane channel quad 4l..4l+3 (its Philox block, its scheduler update).  The Cf-wide dot products of the head are reduced
-// with two xor-shuffles inside the lane quad.  grid (nslots, 4, B): blockIdx.y == 3 is the dead D x D corner, which the
-// network never sees (zero model output) but the sampler still evolves.  block 256 = 64 pixels x 4 lanes.
-// smem: coefA[C0], coefB[C0], wout[Cf][C0], bout[Cf], win[Cf][C0], bin[C0], red[2][64][C0]
-// =====================================================================================
-enum { MODE_HEAD = 0, MODE_INCONV = 1, MODE_FUSED = 2 };
-constexpr int kMaxCf = 16;
-
-struct BoundaryArgs {
-    TriCF h;              // last activation [B][rows][cols][C0]                  (HEAD / FUSED)
-    TriDims d;
-    int C0, Cf, H, W, Dd;
-    StatsSrc st;          // statistics of h + out-norm parameters
-    TriCF w_out, b_out;   // [Cf][C0], [Cf]
-    float* model_out;     // composed [B][Cf][H+D][W+D]                           (HEAD)
-    const float* x_in;    // composed input                                        (INCONV)
-    TriCF w_in, b_in;     // [C0][Cf], [C0]
-    TriF h0;              // in_conv output [B][rows][cols][C0]                    (INCONV / FUSED)
-    StatsSink sink;       // GroupNorm partials of h0
-    SchedArgs sch;        // x, sample (in place), coefficient table, step index   (FUSED)
-};
-
-template <int MODE, int NV>      // NV = C0 / 16 float4 chunks per lane (4: C0 = 64, 8: C0 = 128)
-__global__ void __launch_bounds__(256) k_boundary(BoundaryArgs A, int nslots) {
-    constexpr int kBndMaxNV = NV;
-    pdl_wait();
-    pdl_trigger();
-    extern __shared__ float smb[];
-    __shared__ double fin[64 * 9];
-    __shared__ bool is_last;
-    const int plane = blockIdx.y, b = blockIdx.z, slot = blockIdx.x;
-    const int C0 = A.C0, Cf = A.Cf;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 3, pg = tid >> 2, npg = nthr >> 2;
-    const int CPL = C0 >> 2;                            // channels per lane
-    const int nq = (Cf + 3) / 4;
-    const int Hc = A.H + A.Dd, Wc = A.W + A.Dd;
-    const long long hw = static_cast<long long>(Hc) * Wc;
-    const long long nper = static_cast<long long>(Cf) * hw;
-    float* coefA = smb;
-    float* coefB = coefA + C0;
-    float* wout = coefB + C0;           // [Cf][C0]
-    float* bout = wout + Cf * C0;       // [Cf]
-    float* win = bout + Cf;             // [Cf][C0]  (transposed: win[c][co])
-    float* bin = win + Cf * C0;         // [C0]
-    float* red = bin + C0;              // [2][npg][C0]
-
-    // scheduler scalars of this sample (FUSED)
-    int t = 0;
-    float cf[12];
-    float nz = 0.f;
-    if (MODE == MODE_FUSED) {
-        t = A.sch.t_idx[b];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) cf[k] = __ldg(A.sch.coef + static_cast<size_t>(t) * 12 + k);
-        nz = t != 0 ? 1.f : 0.f;
-    }
-    // scheduler update of the (up to) 4 channels of quad `quad` at composed pixel `pix`; xo: x_t, mo: model output
-    auto sched_quad = [&](int quad, long long pix, const float (&mo)[4], const float (&xo)[4], float (&xn)[4]) {
-        const int c0 = quad * 4, cnt = min(4, Cf - c0);
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!A.sch.noise && A.sch.kind != 2)
-            z = philox_normal4(A.sch.seed, A.sch.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(pix * nq + quad));
-        const float zz[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            xn[k] = 0.f;
-            if (k < cnt) {
-                const size_t gi = static_cast<size_t>(b) * nper + static_cast<long long>(c0 + k) * hw + pix;
-                const float nv = A.sch.noise ? A.sch.noise[static_cast<size_t>(t) * A.sch.noise_step_stride + gi] : zz[k];
-                const float y0 = A.sch.y0 ? A.sch.y0[gi] : 0.f, mk = A.sch.y0 ? A.sch.mask[gi] : 0.f;
-                float x0;
-                xn[k] = sched_one(A.sch, cf, nz, mo[k], xo[k], nv, y0, mk, x0);
-                A.sch.sample[gi] = xn[k];
-                if (A.sch.x0_out) A.sch.x0_out[gi] = x0;
-            }
-        }
-    };
-
-    if (plane == 3) {
-        // ---- dead corner [H:, W:]: zero model output
-        const int ncorner = A.Dd * A.Dd;
-        const int per = (ncorner + nslots - 1) / nslots;
-        const int e0 = slot * per, e1 = min(ncorner, e0 + per);
-        if (MODE != MODE_INCONV) {
-            const int nitems = (e1 - e0) * nq;                 // one item = one channel quad at one corner pixel
-            for (int i = tid; i < nitems; i += nthr) {
-                const int quad = i / (e1 - e0), el = e0 + (i - quad * (e1 - e0));
-                const int r = el / A.Dd, c = el - r * A.Dd;
-                const long long pix = static_cast<long long>(A.H + r) * Wc + A.W + c;
-                const int c0 = quad * 4, cnt = min(4, Cf - c0);
-                if (MODE == MODE_HEAD) {
-                    for (int k = 0; k < cnt; ++k) A.model_out[static_cast<size_t>(b) * nper + static_cast<long long>(c0 + k) * hw + pix] = 0.f;
-                } else {
-                    float xo[4] = {0.f, 0.f, 0.f, 0.f}, xn[4];
-                    const float mo[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k < cnt) xo[k] = A.sch.x[static_cast<size_t>(b) * nper + static_cast<long long>(c0 + k) * hw + pix];
-                    sched_quad(quad, pix, mo, xo, xn);
-                }
-            }
-        }
-    } else {
-        const int rows = A.d.rows[plane], cols = A.d.cols[plane], npx = rows * cols;
-        const int ppc = (npx + nslots - 1) / nslots;
-        const int p0 = slot * ppc, p1 = min(npx, p0 + ppc);
-        // ---- per-CTA constants
-        if (MODE != MODE_INCONV) {
-            for (int i = tid; i < Cf * C0; i += nthr) wout[i] = A.w_out.p[plane][i];
-            for (int i = tid; i < Cf; i += nthr) bout[i] = A.b_out.p[plane][i];
-            stats_coef_prologue(A.st, b, plane, C0, static_cast<double>(npx) * (C0 / kGroups), tid, nthr, fin, coefA, coefB);
-        }
-        if (MODE != MODE_HEAD) {
-            for (int i = tid; i < Cf * C0; i += nthr) {
-                const int c = i / C0, co = i - c * C0;
-                win[i] = A.w_in.p[plane][co * Cf + c];
-            }
-            for (int i = tid; i < C0; i += nthr) bin[i] = A.b_in.p[plane][i];
-        }
-        __syncthreads();
-        const float* hp = MODE != MODE_INCONV ? A.h.p[plane] + static_cast<size_t>(b) * npx * C0 : nullptr;
-        float* h0p = MODE != MODE_HEAD ? A.h0.p[plane] + static_cast<size_t>(b) * npx * C0 : nullptr;
-        const int ch0 = lane * CPL;                      // first hidden channel of this lane
-        float4 s[kBndMaxNV], q[kBndMaxNV];
-#pragma unroll
-        for (int k = 0; k < kBndMaxNV; ++k) s[k] = q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        // Pixels are taken two at a time with every global load of the pair issued first (the stores at the end of the body
-        // cannot be proven distinct from the inputs, so the compiler will not hoist loads across iterations itself).
-        constexpr int NPB = MODE == MODE_FUSED ? 1 : 2;
-        for (int pb = p0; pb < p1; pb += npg * NPB) {
-            float4 hv[NPB][kBndMaxNV];
-            float xo[NPB][4];
-            long long pix[NPB];
-            bool pv[NPB];
-#pragma unroll
-            for (int j = 0; j < NPB; ++j) {
-                const int px = pb + j * npg + pg;
-                pv[j] = px < p1;
-                const int r = pv[j] ? px / cols : 0, c = pv[j] ? px - r * cols : 0;
-                pix[j] = composed_offset(plane, r, c, A.H, A.W, Wc);
-#pragma unroll
-                for (int k = 0; k < kBndMaxNV; ++k) {
-                    hv[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (MODE != MODE_INCONV && pv[j] && k < NV)
-                        hv[j][k] = __ldg(reinterpret_cast<const float4*>(hp + static_cast<size_t>(px) * C0 + ch0) + k);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    xo[j][k] = 0.f;
-                    if (MODE != MODE_HEAD && pv[j] && lane * 4 + k < Cf) {
-                        const size_t gi = static_cast<size_t>(b) * nper + static_cast<long long>(lane * 4 + k) * hw + pix[j];
-                        xo[j][k] = MODE == MODE_INCONV ? __ldg(A.x_in + gi) : A.sch.x[gi];
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NPB; ++j) {
-                const int px = pb + j * npg + pg;
-                float xn[4] = {xo[j][0], xo[j][1], xo[j][2], xo[j][3]};       // (new) x of this lane's channel quad
-                if (MODE != MODE_INCONV) {
-                    float part[kMaxCf];
-#pragma unroll
-                    for (int co = 0; co < kMaxCf; ++co) part[co] = 0.f;
-#pragma unroll
-                    for (int k = 0; k < kBndMaxNV; ++k) {
-                        if (k < NV) {
-                            const float4 ca = *reinterpret_cast<const float4*>(coefA + ch0 + 4 * k);
-                            const float4 cb = *reinterpret_cast<const float4*>(coefB + ch0 + 4 * k);
-                            float4 y;
-                            y.x = silu_f(fmaf(hv[j][k].x, ca.x, cb.x));
-                            y.y = silu_f(fmaf(hv[j][k].y, ca.y, cb.y));
-                            y.z = silu_f(fmaf(hv[j][k].z, ca.z, cb.z));
-                            y.w = silu_f(fmaf(hv[j][k].w, ca.w, cb.w));
-#pragma unroll
-                            for (int co = 0; co < kMaxCf; ++co) {
-                                if (co < Cf) {
-                                    const float4 w4 = *reinterpret_cast<const float4*>(wout + co * C0 + ch0 + 4 * k);
-                                    part[co] = fmaf(y.x, w4.x, fmaf(y.y, w4.y, fmaf(y.z, w4.z, fmaf(y.w, w4.w, part[co]))));
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int co = 0; co < kMaxCf; ++co) {
-                        if (co < Cf) {
-                            part[co] += __shfl_xor_sync(0xffffffffu, part[co], 1, 4);
-                            part[co] += __shfl_xor_sync(0xffffffffu, part[co], 2, 4);
-                        }
-                    }
-                    // this lane's quad of model outputs
-                    float mo[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int co = 0; co < kMaxCf; ++co)
-                        if (co < Cf && (co >> 2) == lane) mo[co & 3] = part[co] + bout[co];
-                    if (pv[j] && lane < nq) {
-                        if (MODE == MODE_HEAD) {
-                            for (int k = 0; k < 4 && lane * 4 + k < Cf; ++k)
-                                A.model_out[static_cast<size_t>(b) * nper + static_cast<long long>(lane * 4 + k) * hw + pix[j]] = mo[k];
-                        } else {
-                            sched_quad(lane, pix[j], mo, xo[j], xn);
-                        }
-                    }
-                }
-                if (MODE != MODE_HEAD) {
-                    float4 a[kBndMaxNV];
-#pragma unroll
-                    for (int k = 0; k < kBndMaxNV; ++k)
-                        if (k < NV) a[k] = *reinterpret_cast<const float4*>(bin + ch0 + 4 * k);
-#pragma unroll
-                    for (int cc = 0; cc < kMaxCf; ++cc) {
-                        if (cc < Cf) {
-                            const int kk = cc & 3;
-                            const float mine = kk == 0 ? xn[0] : (kk == 1 ? xn[1] : (kk == 2 ? xn[2] : xn[3]));
-                            const float xv = __shfl_sync(0xffffffffu, mine, cc >> 2, 4);
-#pragma unroll
-                            for (int k = 0; k < kBndMaxNV; ++k) {
-                                if (k < NV) {
-                                    const float4 w4 = *reinterpret_cast<const float4*>(win + cc * C0 + ch0 + 4 * k);
-                                    a[k].x = fmaf(xv, w4.x, a[k].x); a[k].y = fmaf(xv, w4.y, a[k].y);
-                                    a[k].z = fmaf(xv, w4.z, a[k].z); a[k].w = fmaf(xv, w4.w, a[k].w);
-                                }
-                            }
-                        }
-                    }
-                    if (pv[j]) {
-#pragma unroll
-                        for (int k = 0; k < kBndMaxNV; ++k) {
-                            if (k < NV) {
-                                *reinterpret_cast<float4*>(h0p + static_cast<size_t>(px) * C0 + ch0 + 4 * k) = a[k];
-                                acc_sq(s[k], q[k], a[k]);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        if (MODE != MODE_HEAD && A.sink.partial) {
-            // per-channel (sum, sum-sq) over this CTA's pixels: red[which][pg][C0], then fixed-order column sums
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < kBndMaxNV; ++k) {
-                if (k < NV) {
-                    *reinterpret_cast<float4*>(red + (static_cast<size_t>(0) * npg + pg) * C0 + ch0 + 4 * k) = s[k];
-                    *reinterpret_cast<float4*>(red + (static_cast<size_t>(1) * npg + pg) * C0 + ch0 + 4 * k) = q[k];
-                }
-            }
-            __syncthreads();
-            float* tot = coefA;         // coefA/coefB (2*C0 floats) are free now
-            for (int i = tid; i < 2 * C0; i += nthr) {
-                const int which = i / C0, c = i - which * C0;
-                float acc = 0.f;
-                for (int g = 0; g < npg; ++g) acc += red[(static_cast<size_t>(which) * npg + g) * C0 + c];
-                tot[i] = acc;
-            }
-            __syncthreads();
-            const int cpg = C0 / kGroups;
-            if (tid < 2 * kGroups) {
-                const int g = tid >> 1, which = tid & 1;
-                double acc = 0.0;
-                for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(tot[which * C0 + c]);
-                A.sink.partial[((static_cast<size_t>(b) * 3 + plane) * A.sink.nslots + slot) * (kGroups * 2) + g * 2 + which] = static_cast<float>(acc);
-            }
-        }
-    }
-    if (MODE == MODE_FUSED && A.sch.advance) {
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int prev = atomicAdd(A.sch.ticket, 1u);
-            is_last = prev == gridDim.x * gridDim.y * gridDim.z - 1;
-        }
-        __syncthreads();
-        if (is_last && tid == 0) {
-            for (int k = 0; k < A.sch.B; ++k) A.sch.t_idx[k] -= 1;
-            *A.sch.ticket = 0u;
-        }
     }
 }
 

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/sin3dm_b200.h"
+#include "boundary.cuh"
 #include "conv_tc.cuh"
 #include "kernels.cuh"
 
@@ -170,6 +171,13 @@ struct Plan {
     std::vector<std::function<void(cudaStream_t)>> ops;
     std::vector<std::string> op_names;   // kernel:layer, parallel to ops
     std::vector<double> op_flops;        // dense algorithmic FLOPs of the op as the reference executes it (convs only)
+    std::vector<Trace> op_trace;         // per-op phase stamps (buf == nullptr unless s3d_unet_trace_enable)
+    Trace sched_trace{}, fused_trace{};
+    // The fused step boundary runs the NEXT step's in_conv, so after a fused loop the accumulators of in_conv's output hold
+    // one contribution too many: whoever launches in_conv stand-alone next clears them first.
+    unsigned long long* in_acc = nullptr;
+    size_t in_acc_n = 0;
+    bool in_acc_stale = false;
     size_t alloc_bytes = 0;
     std::vector<void*> allocs;
     std::vector<NamedBuf> named;
@@ -212,6 +220,7 @@ struct s3d_unet {
     int num_sms = 148;
     bool fuse_roll = true;   // S3D_FUSE_ROLL=0 launches the rollout 1-D GEMM separately
     bool halo_bo_kw = false;
+    bool trace_on = false;   // s3d_unet_trace_enable
     int profile_mode = -1;   // last s3d_unet_profile_ops: 1 = graph replay with event nodes, 0 = eager launches
 };
 
@@ -478,12 +487,6 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_gn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_FUSED, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_HEAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_INCONV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_FUSED, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_HEAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(k_boundary<MODE_INCONV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kRollSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kRollSmemBytes));
@@ -517,10 +520,21 @@ struct PlanBuilder {
     std::vector<TriDims> dims;   // per level
     int B;
 
-    void add_op(const char* name, double flops, std::function<void(cudaStream_t)> fn) {
+    void add_op(const char* name, double flops, std::function<void(cudaStream_t)> fn, Trace tr = Trace{}) {
         P->ops.push_back(std::move(fn));
         P->op_names.push_back(name);
         P->op_flops.push_back(flops);
+        P->op_trace.push_back(tr);
+    }
+    static constexpr int kTraceCtas = 2048;
+    Trace new_trace() {
+        Trace t{};
+        if (!u->trace_on) return t;
+        const size_t n = static_cast<size_t>(kTraceCtas) * 2 * kTraceSlots;
+        t.buf = dev_alloc<unsigned long long>(P->allocs, n);
+        CUDA_TRY(cudaMemset(t.buf, 0, n * sizeof(unsigned long long)));
+        t.max_ctas = kTraceCtas;
+        return t;
     }
     // dense FLOPs of one TriplaneConv 3x3 (+ its 1x1 skip) as the reference executes it: rollout channels counted
     double conv_flops(int level, const DevConv3& cv) const {
@@ -584,20 +598,35 @@ struct PlanBuilder {
         return S;
     }
 
-    // ---- GroupNorm statistics (two-level partial sums; see StatsSink / StatsSrc in kernels.cuh)
-    std::shared_ptr<SinkBox> make_box(int C, int nslots) {
+    // ---- GroupNorm statistics (fixed-point group-sum accumulators; see StatsSink / StatsSrc in kernels.cuh)
+    std::shared_ptr<SinkBox> make_box(int C) {
         auto bx = std::make_shared<SinkBox>();
         StatsSink& S = bx->s;
-        const size_t np = static_cast<size_t>(B) * 3 * nslots * 64;
-        S.partial = dev_alloc<float>(P->allocs, np);
-        CUDA_TRY(cudaMemset(S.partial, 0, sizeof(float) * np));
-        S.nslots = nslots;
+        const size_t n = static_cast<size_t>(B) * 3 * 64;
+        S.acc = dev_alloc<unsigned long long>(P->allocs, n);
+        CUDA_TRY(cudaMemset(S.acc, 0, sizeof(unsigned long long) * n));
         S.C = C;
-        bx->src.partial = S.partial;
-        bx->src.nslots = nslots;
+        bx->src.acc = S.acc;
         bx->src.film_dim = u->film_dim;
         bx->src.film_off = -1;
         return bx;
+    }
+    // Re-zeroing chain: the accumulators a consumer has read are cleared by the NEXT consumer kernel of the step (the first
+    // consumer clears the last one's, which is a step old by then).
+    std::shared_ptr<SinkBox> first_consumed, last_consumed;
+    void chain_zero(const std::shared_ptr<SinkBox>& bx) {
+        if (last_consumed) {
+            bx->src.zero = last_consumed->s.acc;
+            bx->src.zero_n = B * 3 * 64;
+        }
+        if (!first_consumed) first_consumed = bx;
+        last_consumed = bx;
+    }
+    void close_zero_chain() {
+        if (first_consumed && last_consumed) {
+            first_consumed->src.zero = last_consumed->s.acc;
+            first_consumed->src.zero_n = B * 3 * 64;
+        }
     }
     // sink as seen by a producer launch: disabled unless a consumer armed it
     static StatsSink live_sink(const std::shared_ptr<SinkBox>& bx) {
@@ -622,8 +651,9 @@ struct PlanBuilder {
         const int level = x.level, C = x.C;
         S3D_CHECK(C % kGroups == 0 && C % 4 == 0 && C / 4 <= 128, "unsupported channel count for GroupNorm32");
         const int nslots = std::max(1, std::min(128, max_px(level) / 48));
-        if (standalone) bx = make_box(C, nslots);
+        if (standalone) bx = make_box(C);
         S3D_CHECK(!bx->armed, "tensor normalised twice");
+        chain_zero(bx);
         bx->src.gamma = cf3(n.gamma);
         bx->src.beta = cf3(n.beta);
         bx->src.film_off = film_off;
@@ -651,10 +681,20 @@ struct PlanBuilder {
         const int bx = C / 4;
         S3D_CHECK(bx <= 256, "channel count too large for k_gn_silu");
         const int ny = std::max(1, 256 / bx);
-        int gx = 0;
-        for (int p = 0; p < 3; ++p)
-            gx = std::max(gx, ((d.rows[p] + kGsRows - 1) / kGsRows) * ((d.cols[p] + ny - 1) / ny));
+        // column groups per CTA: the smallest tile width that keeps one sample's CTAs in one wave (2 CTAs / SM)
+        int ncg = 1, gx = 0;
+        for (;; ++ncg) {
+            int active = 0;
+            gx = 0;
+            for (int p = 0; p < 3; ++p) {
+                const int n = ((d.rows[p] + kGsRows - 1) / kGsRows) * ((d.cols[p] + ny * ncg - 1) / (ny * ncg));
+                gx = std::max(gx, n);
+                active += n;
+            }
+            if (active <= 2 * u->num_sms || ncg == 4) break;     // per sample: the geometry (hence every rounding) must not depend on B
+        }
         GnSiluArgs A{};
+        A.ncg = ncg;
         A.x = cf(x.p);
         A.d = d;
         A.C = C;
@@ -672,6 +712,7 @@ struct PlanBuilder {
         }
         const size_t smem = sizeof(float) * (2 + static_cast<size_t>(ny) * kGsRows) * C;
         S3D_CHECK(smem <= 100 * 1024, "k_gn_silu shared memory");
+        A.tr = new_trace();
         const int Bv = B;
         Plan* Pp = P;
         add_op("k_gn_silu", 0.0, [=](cudaStream_t s) {
@@ -680,7 +721,7 @@ struct PlanBuilder {
             dim3 grid(gx, 3, Bv), block(bx, ny);
             launch(k_gn_silu, dim3(grid), dim3(block), smem, s, Al, Bv);
             LAUNCH_CHECK("k_gn_silu");
-        });
+        }, A.tr);
     }
 
     struct TBuf {
@@ -841,6 +882,7 @@ struct PlanBuilder {
         A.Cs = cv.Cs;
         A.e = e;
         A.bo_kw = u->halo_bo_kw ? 1 : 0;
+        A.tr = new_trace();
         int total = 0;
         for (int p = 0; p < 3; ++p) {
             const uint64_t adims[5] = {static_cast<uint64_t>(cv.C), static_cast<uint64_t>(d.cols[p]),
@@ -870,9 +912,7 @@ struct PlanBuilder {
         // the epilogue can emit the output's GroupNorm partials when a 64-channel N tile holds whole groups
         std::shared_ptr<SinkBox> box;
         if (cv.Cout % kGroups == 0 && kBN % (cv.Cout / kGroups) == 0) {
-            int max_tiles = 0;
-            for (int p = 0; p < 3; ++p) max_tiles = std::max(max_tiles, A.tile_start[p + 1] - A.tile_start[p]);
-            box = make_box(cv.Cout, max_tiles);
+            box = make_box(cv.Cout);
             out.sink = box;
         }
         FusedRoll F{};
@@ -909,7 +949,7 @@ struct PlanBuilder {
             if (nsplit == 3) launch(k_conv_tc<3>, dim3(grid), dim3(kConvThreads), ConvTcCfg<3>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
             else launch(k_conv_tc<1>, dim3(grid), dim3(kConvThreads), ConvTcCfg<1>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
             LAUNCH_CHECK("k_conv_tc");
-        });
+        }, A.tr);
     }
 
     ActF res_block(int bi, const ActF& x) {
@@ -949,16 +989,16 @@ struct PlanBuilder {
         TriCF xc = cf(x.p);
         TriF op = o.p;
         const int nslots = std::max(1, std::min(128, max_px(x.level + 1) / 16));
-        auto box = make_box(C, nslots);
+        auto box = make_box(C);
         o.sink = box;
-        Plan* Pp = P;
         S3D_CHECK(C / 4 <= 256, "channel count too large for k_avgpool2");
+        const Trace tr = new_trace();
         add_op("k_avgpool2", 0.0, [=](cudaStream_t s) {
             const int ny = std::max(1, 256 / (C / 4));
             dim3 grid(nslots, 3, Bv), block(C / 4, ny);
-            launch(k_avgpool2, dim3(grid), dim3(block), sizeof(float) * (ny * 2 + 2) * C, s, xc, di, dd, C, op, live_sink(box), nslots);
+            launch(k_avgpool2, dim3(grid), dim3(block), sizeof(float) * (ny * 2 + 2) * C, s, xc, di, dd, C, op, live_sink(box), nslots, tr);
             LAUNCH_CHECK("k_avgpool2");
-        });
+        }, tr);
         return o;
     }
 
@@ -972,17 +1012,18 @@ struct PlanBuilder {
         TriF op = o.p;
         const int Cu = low.C, Bv = B, Ct = Cu + Cs;
         S3D_CHECK(Ct / 4 <= 256 && Cu % 4 == 0 && Cs % 4 == 0, "channel counts unsupported by k_upcat");
-        const int nslots = std::max(1, std::min(128, max_px(out_level) / 32));
-        auto box = make_box(Ct, nslots);
+        // one wave at 2 CTAs / SM (the gather loop is latency bound: fewer, longer CTAs with 4 pixels in flight per thread)
+        const int nslots = std::max(1, std::min(2 * u->num_sms / 3, max_px(out_level) / 32));
+        auto box = make_box(Ct);
         o.sink = box;
-        Plan* Pp = P;
+        const Trace tr = new_trace();
         add_op("k_upcat", 0.0, [=](cudaStream_t s) {
             const int ny = std::max(1, 256 / (Ct / 4));
             dim3 grid(nslots, 3, Bv), block(Ct / 4, ny);
             launch(k_upcat, dim3(grid), dim3(block), sizeof(float) * (ny * 2 + 2) * Ct, s, lc, dl, Cu, sc, Cs, dout, op, do_up ? 1 : 0,
-                                                                           live_sink(box), nslots);
+                   live_sink(box), nslots, tr);
             LAUNCH_CHECK("k_upcat");
-        });
+        }, tr);
         return o;
     }
 };
@@ -1012,33 +1053,46 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     // ---- in_conv
     const int c0 = ch_of(c, 0);
     ActF h = pb.allocF(0, c0, "in_conv");
-    S3D_CHECK(c0 == 64 || c0 == 128, "channel_mult[0] * model_channels must be 64 or 128 (boundary kernels: 4 lanes per pixel, <= 32 channels per lane)");
+    S3D_CHECK(c0 == 64 || c0 == 128, "channel_mult[0] * model_channels must be 64 or 128 (boundary kernels: one lane per channel quad of a pixel)");
     S3D_CHECK(c.in_channels <= kMaxCf && c.out_channels <= kMaxCf, "at most 16 triplane channels are supported");
-    const int bnd_slots = std::max(1, std::min(128, pb.max_px(0) / 64));
-    auto bnd_smem = [&](int Cf) {
-        return sizeof(float) * (static_cast<size_t>(2) * c0 + 2 * static_cast<size_t>(Cf) * c0 + Cf + c0 + static_cast<size_t>(2) * 64 * c0);
-    };
     BoundaryArgs bnd{};      // fields shared by the three modes
     bnd.d = pb.dims[0];
     bnd.C0 = c0;
     bnd.H = H; bnd.W = W; bnd.Dd = D;
+    {
+        // 4 x 32-pixel tiles, the 32 along the axis that is contiguous in the composed tensor (rows for the transposed yz plane)
+        int total = 0;
+        for (int p = 0; p < 4; ++p) {
+            const int rows = p < 3 ? bnd.d.rows[p] : D, cols = p < 3 ? bnd.d.cols[p] : D;
+            const int fast = p == 2 ? rows : cols, slow = p == 2 ? cols : rows;
+            bnd.tiles_fast[p] = (fast + kBndFast - 1) / kBndFast;
+            const int n = bnd.tiles_fast[p] * ((slow + kBndSlow - 1) / kBndSlow);
+            bnd.tile_start[p] = total;
+            total += n;
+        }
+        bnd.tile_start[4] = total;
+    }
     bnd.w_in = PlanBuilder::cf3(u->in_w);
     bnd.b_in = PlanBuilder::cf3(u->in_b);
     bnd.h0 = h.p;
-    auto in_box = pb.make_box(c0, bnd_slots);
+    auto in_box = pb.make_box(c0);
     h.sink = in_box;
+    P->in_acc = in_box->s.acc;
+    P->in_acc_n = static_cast<size_t>(B) * 3 * 64;
     {
         const int Cin = c.in_channels;
-        const size_t smem = bnd_smem(Cin);
+        const Trace tr = pb.new_trace();
         pb.add_op("k_boundary<in_conv>", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * Cin * c0, [=](cudaStream_t s) {
             BoundaryArgs Al = bnd;
             Al.Cf = Cin;
+            Al.tr = tr;
             Al.x_in = P->x;
             Al.sink = PlanBuilder::live_sink(in_box);
-            if (c0 == 64) launch(k_boundary<MODE_INCONV, 4>, dim3(bnd_slots, 3, B), dim3(256), smem, s, Al, bnd_slots);
-            else launch(k_boundary<MODE_INCONV, 8>, dim3(bnd_slots, 3, B), dim3(256), smem, s, Al, bnd_slots);
+            const dim3 grid(bnd.tile_start[3], B);
+            if (c0 == 64) launch(k_boundary<MODE_INCONV, 16>, dim3(grid), dim3(256), 0, s, Al);
+            else launch(k_boundary<MODE_INCONV, 32>, dim3(grid), dim3(256), 0, s, Al);
             LAUNCH_CHECK("k_boundary<in_conv>");
-        });
+        }, tr);
     }
     // ---- encoder
     std::vector<ActF> stack;
@@ -1084,29 +1138,37 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         bo.h = PlanBuilder::cf(h.p);
         bo.w_out = PlanBuilder::cf3(u->out_w);
         bo.b_out = PlanBuilder::cf3(u->out_b);
-        const size_t smem = bnd_smem(Cout);
+        const Trace tr = pb.new_trace();
         pb.add_op("k_boundary<head>", 2.0 * B * (pb.px(0, 0) + pb.px(0, 1) + pb.px(0, 2)) * c0 * Cout, [=](cudaStream_t s) {
             BoundaryArgs Al = bo;
             Al.Cf = Cout;
+            Al.tr = tr;
             Al.st = PlanBuilder::live_src(st, P);
             Al.model_out = P->out;
-            if (c0 == 64) launch(k_boundary<MODE_HEAD, 4>, dim3(bnd_slots, 4, B), dim3(256), smem, s, Al, bnd_slots);
-            else launch(k_boundary<MODE_HEAD, 8>, dim3(bnd_slots, 4, B), dim3(256), smem, s, Al, bnd_slots);
+            const dim3 grid(bo.tile_start[4], B);
+            if (c0 == 64) launch(k_boundary<MODE_HEAD, 16>, dim3(grid), dim3(256), 0, s, Al);
+            else launch(k_boundary<MODE_HEAD, 32>, dim3(grid), dim3(256), 0, s, Al);
             LAUNCH_CHECK("k_boundary<head>");
-        });
+        }, tr);
         if (c.in_channels == c.out_channels) {
+            const Trace trf = pb.new_trace();
+            P->fused_trace = trf;
             P->fused_boundary = [=](cudaStream_t s, const SchedArgs& sch) {
                 BoundaryArgs Al = bo;
                 Al.Cf = Cout;
+                Al.tr = trf;
                 Al.st = PlanBuilder::live_src(st, P);
                 Al.sink = PlanBuilder::live_sink(in_box);
                 Al.sch = sch;
-                if (c0 == 64) launch(k_boundary<MODE_FUSED, 4>, dim3(bnd_slots, 4, B), dim3(256), smem, s, Al, bnd_slots);
-            else launch(k_boundary<MODE_FUSED, 8>, dim3(bnd_slots, 4, B), dim3(256), smem, s, Al, bnd_slots);
+                const dim3 grid(bo.tile_start[4], B);
+                if (c0 == 64) launch(k_boundary<MODE_FUSED, 16>, dim3(grid), dim3(256), 0, s, Al);
+                else launch(k_boundary<MODE_FUSED, 32>, dim3(grid), dim3(256), 0, s, Al);
                 LAUNCH_CHECK("k_boundary<fused>");
             };
         }
     }
+    pb.close_zero_chain();
+    P->sched_trace = pb.new_trace();
     CUDA_TRY(cudaDeviceSynchronize());
 }
 
@@ -1135,6 +1197,12 @@ static void run_film(s3d_unet* u, Plan* P, const float* t_dev, int n, float* fil
     LAUNCH_CHECK("k_linear");
 }
 
+static void clear_stale_in_acc(Plan* P, cudaStream_t s) {
+    if (P->in_acc_stale) {
+        CUDA_TRY(cudaMemsetAsync(P->in_acc, 0, P->in_acc_n * sizeof(unsigned long long), s));
+        P->in_acc_stale = false;
+    }
+}
 static void run_ops(s3d_unet* u, Plan* P, cudaStream_t s) {
     for (auto& op : P->ops) op(s);
     u->last_launches = static_cast<int>(P->ops.size());
@@ -1262,6 +1330,7 @@ int s3d_unet_forward_film(s3d_unet* u, const float* x_dev, const float* film_dev
     P->out = out_dev;
     P->film = film_dev;
     P->film_row = row_dev;
+    clear_stale_in_acc(P, static_cast<cudaStream_t>(stream));
     run_ops(u, P, static_cast<cudaStream_t>(stream));
     API_END
 }
@@ -1278,6 +1347,7 @@ int s3d_unet_forward(s3d_unet* u, const float* x_dev, const float* t_dev, float*
     P->out = out_dev;
     P->film = P->film_own;
     P->film_row = nullptr;
+    clear_stale_in_acc(P, s);
     run_ops(u, P, s);
     u->last_launches += 4;
     API_END
@@ -1388,10 +1458,11 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
     A.sample_base = a->sample_base;
     A.advance = 1;
     A.ticket = P->ticket;
+    A.tr = P->sched_trace;
     // Loop structure: in_conv once, then per step [blocks ..., fused (out head + scheduler + next step's in_conv)].
-    // measured on B200 (r1): the lane-group fused kernel is slower than head + scheduler + in_conv separately, so it is opt-in
+    // S3D_FUSED_BOUNDARY=0 runs head, scheduler and in_conv as three launches instead (same device code, identical values)
     const char* fb = getenv("S3D_FUSED_BOUNDARY");
-    const bool fused = static_cast<bool>(P->fused_boundary) && fb && atoi(fb) != 0;
+    const bool fused = static_cast<bool>(P->fused_boundary) && !(fb && atoi(fb) == 0);
     const size_t nops = P->ops.size();
     auto one_step = [&](cudaStream_t st) {
         if (fused) {
@@ -1402,6 +1473,7 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
             launch_sched(A, st);
         }
     };
+    clear_stale_in_acc(P, s);
     if (fused) P->ops[0](s);
     if (!a->use_graph) {
         for (int i = 0; i < a->n_steps; ++i) one_step(s);
@@ -1441,6 +1513,7 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
         }
         for (int i = 0; i < a->n_steps; ++i) CUDA_TRY(cudaGraphLaunch(P->graph_exec, s));
     }
+    if (fused) P->in_acc_stale = true;
     u->last_launches = fused ? static_cast<int>(nops) - 2 : static_cast<int>(nops);
     u->last_launches += 1;   // scheduler kernel
     API_END
@@ -1467,6 +1540,7 @@ int s3d_unet_profile_ops(s3d_unet* u, int iters, float* ms_out, void* stream) {
     S3D_CHECK(P->x && P->out && P->film, "run a forward or a sampling loop first");
     CUDA_TRY(cudaSetDevice(u->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    clear_stale_in_acc(P, s);
     const size_t n = P->ops.size();
     std::vector<double> acc(n, 0.0);
     // Preferred: the ops are captured into ONE graph with an external event-record node between consecutive launches and
@@ -1539,6 +1613,35 @@ int s3d_unet_profile_ops(s3d_unet* u, int iters, float* ms_out, void* stream) {
 }
 
 int s3d_unet_profile_mode(const s3d_unet* u) { return u ? u->profile_mode : -1; }
+
+int s3d_unet_trace_enable(s3d_unet* u, int on) {
+    API_BEGIN
+    S3D_CHECK(u, "null handle");
+    if (u->trace_on != (on != 0)) {
+        CUDA_TRY(cudaSetDevice(u->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        destroy_plan(u);          // the next forward / loop rebuilds it with (or without) stamp buffers
+        u->trace_on = on != 0;
+    }
+    API_END
+}
+
+int s3d_trace_slots(void) { return kTraceSlots; }
+
+int s3d_unet_trace_read(s3d_unet* u, int op_index, uint64_t* host_out, int max_ctas) {
+    API_BEGIN
+    S3D_CHECK(u && u->plan && host_out && max_ctas >= 1, "bad argument");
+    const Plan* P = u->plan.get();
+    S3D_CHECK(op_index >= -2 && op_index < static_cast<int>(P->ops.size()), "bad op index");
+    const Trace t = op_index == -2 ? P->fused_trace : (op_index < 0 ? P->sched_trace : P->op_trace[op_index]);
+    S3D_CHECK(t.buf != nullptr, "tracing is off (s3d_unet_trace_enable)");
+    CUDA_TRY(cudaSetDevice(u->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const int n = std::min(max_ctas, t.max_ctas);
+    CUDA_TRY(cudaMemcpy(host_out, t.buf, sizeof(uint64_t) * n * 2 * kTraceSlots, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(t.buf, 0, sizeof(uint64_t) * static_cast<size_t>(t.max_ctas) * 2 * kTraceSlots));
+    API_END
+}
 
 int s3d_unet_debug_count(const s3d_unet* u) { return (u && u->plan) ? static_cast<int>(u->plan->named.size()) : 0; }
 
