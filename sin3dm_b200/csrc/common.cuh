@@ -76,6 +76,24 @@ __device__ __forceinline__ void trace_mark(const Trace& T, int slot) {
     }
 }
 
+// (hi, lo) pair -> fp32, exactly what a reader of the pair sees: hi + lo / 2048
+__device__ __forceinline__ float4 join_halves4(uint2 hi, uint2 lo) {
+    const __half2 h0 = *reinterpret_cast<const __half2*>(&hi.x), h1 = *reinterpret_cast<const __half2*>(&hi.y);
+    const __half2 l0 = *reinterpret_cast<const __half2*>(&lo.x), l1 = *reinterpret_cast<const __half2*>(&lo.y);
+    const float2 a = __half22float2(h0), b = __half22float2(h1), c = __half22float2(l0), d = __half22float2(l1);
+    return make_float4(fmaf(c.x, 1.f / kLoScale, a.x), fmaf(c.y, 1.f / kLoScale, a.y), fmaf(d.x, 1.f / kLoScale, b.x),
+                       fmaf(d.y, 1.f / kLoScale, b.y));
+}
+// value of v after a round trip through store_split4 (no memory access: recomputed from the same roundings)
+__device__ __forceinline__ float4 roundtrip_split4(float4 v) {
+    __half h[4], l[4];
+    split_f16(v.x, h[0], l[0]);
+    split_f16(v.y, h[1], l[1]);
+    split_f16(v.z, h[2], l[2]);
+    split_f16(v.w, h[3], l[3]);
+    return join_halves4(*reinterpret_cast<uint2*>(h), *reinterpret_cast<uint2*>(l));
+}
+
 // Composed-layout address of plane pixel (r, c): [H+D, W+D] with yz stored transposed.
 __device__ __forceinline__ int composed_offset(int plane, int r, int c, int H, int W, int Wc) {
     if (plane == 0) return r * Wc + c;

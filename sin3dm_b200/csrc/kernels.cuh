@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(256) k_avgpool2(TriCF x, TriDims din, TriDims 
 }
 
 // Bilinear x2 upsample (align_corners=False) [+ bilinear resize to the skip's size when they differ]
-// + channel concat with the skip.  reference unet_triplane.py:106-124, 494-503.  out [B][rows][cols][Cu+Cs]
+// + channel concat with the skip.  reference unet_triplane.py:106-124, 494-503.
+// out: (hi, lo) fp16 pair [2][B][rows][cols][Cu+Cs] — the only form its two readers need (k_gn_silu re-joins the halves,
+// k_conv_tc's 1x1 skip GEMM reads them as they are), which saves writing the tensor a second time.
 __device__ __forceinline__ void bilin_src(int dst, int in_size, float scale, int& i0, int& i1, float& l1) {
     // ATen area_pixel_compute_source_index(align_corners=false): scale*(dst+0.5)-0.5 clamped at 0
     float s = fmaxf(scale * (static_cast<float>(dst) + 0.5f) - 0.5f, 0.f);
@@ -180,7 +182,7 @@ __device__ __forceinline__ void bilin_src(int dst, int in_size, float scale, int
     l1 = s - static_cast<float>(i0);
 }
 
-__global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, TriCF skip, int Cs, TriDims dout, TriF out,
+__global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, TriCF skip, int Cs, TriDims dout, TriH out, int B,
                                                int do_up, StatsSink S, int nslots, Trace tr) {
     pdl_wait();
     pdl_trigger();
@@ -196,7 +198,8 @@ __global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, 
     const int p0 = slot * ppc, p1 = min(npx, p0 + ppc);
     const float4* sp = Cs ? reinterpret_cast<const float4*>(skip.p[plane] + static_cast<size_t>(b) * npx * Cs) : nullptr;
     const float4* lp = reinterpret_cast<const float4*>(low.p[plane] + static_cast<size_t>(b) * lrows * lcols * Cu);
-    float4* op = reinterpret_cast<float4*>(out.p[plane] + static_cast<size_t>(b) * npx * Ct);
+    __half* op = out.p[plane] + static_cast<size_t>(b) * npx * Ct;
+    const size_t lo_off = static_cast<size_t>(B) * npx * Ct;
     const int urows = do_up ? 2 * lrows : lrows, ucols = do_up ? 2 * lcols : lcols;
     const bool resize = urows != orows || ucols != ocols;
     auto at = [&](int rr, int cc) { return __ldg(lp + (static_cast<size_t>(rr) * lcols + cc) * u4 + tx); };
@@ -281,8 +284,10 @@ __global__ void __launch_bounds__(256) k_upcat(TriCF low, TriDims dlow, int Cu, 
         for (int j = 0; j < kUpBatch; ++j) {
             const int px = pb + j * NY;
             if (px < p1) {
-                op[static_cast<size_t>(px) * c4 + tx] = o[j];
-                acc_sq(s, q, o[j]);
+                __half* dst = op + static_cast<size_t>(px) * Ct + tx * 4;
+                store_split4(dst, dst + lo_off, o[j]);
+                // the statistics are those of the values the consumer will see (the re-joined halves)
+                acc_sq(s, q, roundtrip_split4(o[j]));
             }
         }
     }
@@ -309,7 +314,8 @@ constexpr float kFixScale = 16777216.f;          // 2^24
 constexpr double kFixInv = 1.0 / 16777216.0;
 
 struct GnSiluArgs {
-    TriCF x;          // fp32 [B][rows][cols][C]
+    TriCF x;          // fp32 [B][rows][cols][C]   (or nullptr, then:)
+    TriCH xh;         // (hi, lo) fp16 [2][B][rows][cols][C] input, read as hi + lo / 2048
     TriDims d;
     int C;
     StatsSrc st;              // group sums of x + this layer's norm parameters
@@ -369,16 +375,32 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
     const size_t plane_elems = static_cast<size_t>(rows) * cols * C;
     const size_t sample_off = static_cast<size_t>(b) * plane_elems;
     const size_t lo_off = static_cast<size_t>(B) * plane_elems;
-    const float* xp = A.x.p[plane] + sample_off;
+    const float* xp = A.x.p[plane] ? A.x.p[plane] + sample_off : nullptr;
+    const __half* xhp = A.xh.p[plane] ? A.xh.p[plane] + sample_off : nullptr;
     __half* ap = A.a.p[plane] + sample_off;
     __half* xq = A.x16.p[plane] ? A.x16.p[plane] + sample_off : nullptr;
     float4 v[kGsRows], y[kGsRows];
     auto load_group = [&](int cg) {
         const int c = cbase + cg * ny + ty;
+        if (xp) {
 #pragma unroll
-        for (int r = 0; r < kGsRows; ++r)
-            v[r] = (c < cols && r < nr) ? __ldg(reinterpret_cast<const float4*>(xp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < kGsRows; ++r)
+                v[r] = (c < cols && r < nr) ? __ldg(reinterpret_cast<const float4*>(xp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            uint2 hh[kGsRows], ll[kGsRows];
+#pragma unroll
+            for (int r = 0; r < kGsRows; ++r) {
+                hh[r] = ll[r] = make_uint2(0u, 0u);
+                if (c < cols && r < nr) {
+                    const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
+                    hh[r] = __ldg(reinterpret_cast<const uint2*>(xhp + off));
+                    ll[r] = __ldg(reinterpret_cast<const uint2*>(xhp + lo_off + off));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kGsRows; ++r) v[r] = join_halves4(hh[r], ll[r]);
+        }
     };
     // operand stores of one column group (fire and forget: the kernel boundary publishes them)
     auto store_group = [&](int cg) {

@@ -320,6 +320,74 @@ static T* dev_upload(std::vector<void*>& owner, const std::vector<T>& h) {
     CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     return p;
 }
+// Activation arena.  Everything a step touches should stay inside the L2 (126 MB), so activations are carved out of a few
+// big chunks with first-fit and handed back as soon as their last consumer has been planned (launches are stream ordered, so
+// a later op may overwrite a buffer whose readers were enqueued before it).  S3D_KEEP_ACTS=1 turns the reuse off (bring-up:
+// s3d_unet_debug_read then sees every intermediate activation).
+struct Arena {
+    struct Blk {
+        size_t off, size;
+        bool free;
+    };
+    struct Chunk {
+        char* base;
+        size_t size, peak;
+        std::vector<Blk> blks;
+    };
+    static constexpr size_t kChunk = static_cast<size_t>(48) << 20, kAlign = 1024;
+    std::vector<Chunk> chunks;
+    bool reuse = true;
+    void* alloc(size_t bytes, std::vector<void*>& owner) {
+        const size_t need = (std::max<size_t>(bytes, 1) + kAlign - 1) / kAlign * kAlign;
+        for (;;) {
+            for (auto& c : chunks)
+                for (size_t i = 0; i < c.blks.size(); ++i) {
+                    if (!c.blks[i].free || c.blks[i].size < need) continue;
+                    const Blk b = c.blks[i];
+                    c.blks[i] = Blk{b.off, need, false};
+                    if (b.size > need) c.blks.insert(c.blks.begin() + i + 1, Blk{b.off + need, b.size - need, true});
+                    c.peak = std::max(c.peak, b.off + need);
+                    return c.base + b.off;
+                }
+            Chunk c{};
+            c.size = std::max(kChunk, need);
+            void* p = nullptr;
+            CUDA_TRY(cudaMalloc(&p, c.size));
+            owner.push_back(p);
+            c.base = static_cast<char*>(p);
+            c.blks.push_back(Blk{0, c.size, true});
+            chunks.push_back(c);
+        }
+    }
+    void release(void* p) {
+        if (!reuse || !p) return;
+        for (auto& c : chunks) {
+            if (p < c.base || p >= c.base + c.size) continue;
+            const size_t off = static_cast<size_t>(static_cast<char*>(p) - c.base);
+            for (size_t i = 0; i < c.blks.size(); ++i) {
+                if (c.blks[i].off != off) continue;
+                if (c.blks[i].free) throw S3dError{"internal: activation released twice"};
+                c.blks[i].free = true;
+                if (i + 1 < c.blks.size() && c.blks[i + 1].free) {
+                    c.blks[i].size += c.blks[i + 1].size;
+                    c.blks.erase(c.blks.begin() + i + 1);
+                }
+                if (i > 0 && c.blks[i - 1].free) {
+                    c.blks[i - 1].size += c.blks[i].size;
+                    c.blks.erase(c.blks.begin() + i);
+                }
+                return;
+            }
+        }
+        throw S3dError{"internal: release of an unknown activation"};
+    }
+    size_t touched() const {
+        size_t n = 0;
+        for (const auto& c : chunks) n += c.peak;
+        return n;
+    }
+};
+
 static const TensorSpec& T_(const s3d_unet* u, const std::string& n) {
     auto it = u->index.find(n);
     if (it == u->index.end()) throw S3dError{"internal: unknown tensor " + n};
@@ -519,6 +587,7 @@ struct PlanBuilder {
     Plan* P;
     std::vector<TriDims> dims;   // per level
     int B;
+    Arena arena;
 
     void add_op(const char* name, double flops, std::function<void(cudaStream_t)> fn, Trace tr = Trace{}) {
         P->ops.push_back(std::move(fn));
@@ -548,15 +617,23 @@ struct PlanBuilder {
         ActF a;
         a.C = C;
         a.level = level;
-        for (int p = 0; p < 3; ++p) a.p.p[p] = dev_alloc<float>(P->allocs, static_cast<size_t>(B) * px(level, p) * C);
-        if (!name.empty()) P->named.push_back({name, a.p, C, dims[level]});
+        for (int p = 0; p < 3; ++p)
+            a.p.p[p] = static_cast<float*>(arena.alloc(sizeof(float) * B * px(level, p) * C, P->allocs));
+        if (!name.empty() && !arena.reuse) P->named.push_back({name, a.p, C, dims[level]});
         return a;
     }
     Act16 alloc16(int level, int C) {
         Act16 a;
         a.C = C;
-        for (int p = 0; p < 3; ++p) a.p.p[p] = dev_alloc<__half>(P->allocs, static_cast<size_t>(2) * B * px(level, p) * C);
+        for (int p = 0; p < 3; ++p)
+            a.p.p[p] = static_cast<__half*>(arena.alloc(sizeof(__half) * 2 * B * px(level, p) * C, P->allocs));
         return a;
+    }
+    void release(const ActF& a) {
+        for (int p = 0; p < 3; ++p) arena.release(a.p.p[p]);
+    }
+    void release(const Act16& a) {
+        for (int p = 0; p < 3; ++p) arena.release(a.p.p[p]);
     }
     static TriCF cf(const TriF& t) { return TriCF{{t.p[0], t.p[1], t.p[2]}}; }
     static TriCF cf3(float* const* t) { return TriCF{{t[0], t[1], t[2]}}; }
@@ -675,7 +752,8 @@ struct PlanBuilder {
     }
 
     // ---- GN apply + SiLU (+FiLM) -> fp16 operands (+ raw x16) (+ axis means)
-    void gn_silu(const ActF& x, const std::shared_ptr<SinkBox>& st, const Act16& a, const Act16* x16, const Sums* S) {
+    // x: fp32 input, or (xh != nullptr) the (hi, lo) fp16 input written by k_upcat
+    void gn_silu(const ActF& x, const Act16* xh, const std::shared_ptr<SinkBox>& st, const Act16& a, const Act16* x16, const Sums* S) {
         const int level = x.level, C = x.C;
         const TriDims d = dims[level];
         const int bx = C / 4;
@@ -695,7 +773,8 @@ struct PlanBuilder {
         }
         GnSiluArgs A{};
         A.ncg = ncg;
-        A.x = cf(x.p);
+        if (xh) A.xh = TriCH{{xh->p.p[0], xh->p.p[1], xh->p.p[2]}};
+        else A.x = cf(x.p);
         A.d = d;
         A.C = C;
         A.a = a.p;
@@ -952,33 +1031,47 @@ struct PlanBuilder {
         }, A.tr);
     }
 
-    ActF res_block(int bi, const ActF& x) {
+    // One TriplaneResBlock (unet_triplane.py:269-311).  The input is either the fp32 residual stream `x`, or — for the decoder
+    // blocks behind a concat — the (hi, lo) fp16 tensor `xh` that k_upcat wrote (it doubles as the skip GEMM's operand).
+    // Buffers go back to the arena as soon as their last reader is planned; the caller releases the block's input.
+    ActF res_block(int bi, const ActF* x, const Act16* xh, const std::shared_ptr<SinkBox>& xh_sink, int level) {
         const BlockSpec& b = u->blocks[bi];
         const DevBlock& w = u->dblocks[bi];
-        const int level = x.level;
         const bool ro = u->cfg.rollout, ssn = u->cfg.use_scale_shift_norm;
-        S3D_CHECK(x.C == b.cin, "res block input width");
+        S3D_CHECK((x ? x->C : xh->C) == b.cin, "res block input width");
+        S3D_CHECK(x || b.has_skip, "a (hi, lo) input needs the 1x1 skip GEMM");
         Sums s1{}, s2{};
         if (ro) {
             s1 = alloc_sums(level, b.cin);
             s2 = alloc_sums(level, b.cout);
         }
-        auto st1 = stats(x, w.n1, -1);
+        ActF xin{};
+        if (x) xin = *x;
+        else {
+            xin.C = xh->C;
+            xin.level = level;
+            xin.sink = xh_sink;
+        }
+        auto st1 = stats(xin, w.n1, -1);
         Act16 a1 = alloc16(level, b.cin);
         Act16 x16{};
-        if (b.has_skip) x16 = alloc16(level, b.cin);
-        gn_silu(x, st1, a1, b.has_skip ? &x16 : nullptr, ro ? &s1 : nullptr);
+        if (b.has_skip) x16 = x ? alloc16(level, b.cin) : *xh;
+        gn_silu(xin, x ? nullptr : xh, st1, a1, (b.has_skip && x) ? &x16 : nullptr, ro ? &s1 : nullptr);
         TBuf t1{};
         if (ro) t1 = roll1d(s1, level, w.c1);
         ActF h1 = allocF(level, b.cout, b.name + ".h1");
         conv(a1, level, w.c1, ro ? &t1 : nullptr, nullptr, nullptr, ssn ? -1 : b.film_off, h1);
+        release(a1);
         auto st2 = stats(h1, w.n2, ssn ? b.film_off : -1);
         Act16 a2 = alloc16(level, b.cout);
-        gn_silu(h1, st2, a2, nullptr, ro ? &s2 : nullptr);
+        gn_silu(h1, nullptr, st2, a2, nullptr, ro ? &s2 : nullptr);
+        release(h1);
         TBuf t2{};
         if (ro) t2 = roll1d(s2, level, w.c2);
         ActF out = allocF(level, b.cout, b.name + ".out");
-        conv(a2, level, w.c2, ro ? &t2 : nullptr, b.has_skip ? &x16 : nullptr, b.has_skip ? nullptr : &x, -1, out);
+        conv(a2, level, w.c2, ro ? &t2 : nullptr, b.has_skip ? &x16 : nullptr, b.has_skip ? nullptr : x, -1, out);
+        release(a2);
+        if (b.has_skip && x) release(x16);
         return out;
     }
 
@@ -1002,25 +1095,25 @@ struct PlanBuilder {
         return o;
     }
 
-    // x2 bilinear of `low` (+ resize to the skip's size) and concat with `skip` (may be null: plain upsample)
-    ActF upcat(const ActF& low, const ActF* skip, int out_level, bool do_up, const std::string& name) {
-        const int Cs = skip ? skip->C : 0;
-        ActF o = allocF(out_level, low.C + Cs, name);
+    // x2 bilinear of `low` (+ resize to the skip's size) and concat with `skip`; the result is written once, as the (hi, lo)
+    // fp16 pair that both of its readers want (the 1x1 skip GEMM directly, GroupNorm + SiLU after re-joining the halves)
+    Act16 upcat(const ActF& low, const ActF& skip, int out_level, bool do_up, std::shared_ptr<SinkBox>& sink_out) {
+        const int Cs = skip.C;
+        Act16 o = alloc16(out_level, low.C + Cs);
         const TriDims dl = dims[low.level], dout = dims[out_level];
-        TriCF lc = cf(low.p), sc{};
-        if (skip) sc = cf(skip->p);
-        TriF op = o.p;
+        TriCF lc = cf(low.p), sc = cf(skip.p);
+        TriH op = o.p;
         const int Cu = low.C, Bv = B, Ct = Cu + Cs;
         S3D_CHECK(Ct / 4 <= 256 && Cu % 4 == 0 && Cs % 4 == 0, "channel counts unsupported by k_upcat");
         // one wave at 2 CTAs / SM (the gather loop is latency bound: fewer, longer CTAs with 4 pixels in flight per thread)
         const int nslots = std::max(1, std::min(2 * u->num_sms / 3, max_px(out_level) / 32));
         auto box = make_box(Ct);
-        o.sink = box;
+        sink_out = box;
         const Trace tr = new_trace();
         add_op("k_upcat", 0.0, [=](cudaStream_t s) {
             const int ny = std::max(1, 256 / (Ct / 4));
             dim3 grid(nslots, 3, Bv), block(Ct / 4, ny);
-            launch(k_upcat, dim3(grid), dim3(block), sizeof(float) * (ny * 2 + 2) * Ct, s, lc, dl, Cu, sc, Cs, dout, op, do_up ? 1 : 0,
+            launch(k_upcat, dim3(grid), dim3(block), sizeof(float) * (ny * 2 + 2) * Ct, s, lc, dl, Cu, sc, Cs, dout, op, Bv, do_up ? 1 : 0,
                    live_sink(box), nslots, tr);
             LAUNCH_CHECK("k_upcat");
         }, tr);
@@ -1040,6 +1133,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     } guard(&P->alloc_bytes);
     const auto& c = u->cfg;
     PlanBuilder pb{u, P, {}, B};
+    if (const char* e = getenv("S3D_KEEP_ACTS")) pb.arena.reuse = atoi(e) == 0;
     TriDims d{{H, H, W}, {W, D, D}};
     for (int l = 0; l < c.n_levels; ++l) {
         S3D_CHECK(d.rows[0] >= 1 && d.rows[2] >= 1 && d.cols[1] >= 1, "triplane too small for the number of levels");
@@ -1098,8 +1192,13 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     std::vector<ActF> stack;
     for (int l = 0; l < c.n_levels; ++l) {
         for (const auto& op : u->downs[l]) {
-            if (op.kind == 1) h = pb.down(h, l);
-            else h = pb.res_block(op.block, h);
+            if (op.kind == 1) {
+                h = pb.down(h, l);            // its input stays alive: it is the previous level's skip
+            } else {
+                ActF o = pb.res_block(op.block, &h, nullptr, nullptr, h.level);
+                pb.release(h);
+                h = o;
+            }
         }
         stack.push_back(h);
     }
@@ -1107,6 +1206,8 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     bool pending_up = false;    // an Upsample2x closed the previous output block
     for (int j = 0; j < c.n_levels; ++j) {
         const int level = c.n_levels - 1 - j;
+        Act16 hcat{};
+        std::shared_ptr<SinkBox> hcat_sink;
         if (j == 0) {
             h = stack.back();
             stack.pop_back();
@@ -1120,12 +1221,22 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
                                   2 * pb.dims[level + 1].cols[p] == pb.dims[level].cols[p],
                               "TriplaneUNetModelSmallRaw needs even plane sizes at every level (torch.cat would fail)");
             }
-            h = pb.upcat(h, &skip, level, pending_up, "upcat." + std::to_string(j));
+            hcat = pb.upcat(h, skip, level, pending_up, hcat_sink);
+            pb.release(h);
+            pb.release(skip);
             pending_up = false;
         }
         for (const auto& op : u->ups[j]) {
-            if (op.kind == 2) pending_up = true;     // fused into the next level's upcat
-            else h = pb.res_block(op.block, h);
+            if (op.kind == 2) {
+                pending_up = true;     // fused into the next level's upcat
+            } else if (j == 0) {
+                ActF o = pb.res_block(op.block, &h, nullptr, nullptr, level);
+                pb.release(h);
+                h = o;
+            } else {
+                h = pb.res_block(op.block, nullptr, &hcat, hcat_sink, level);
+                pb.release(hcat);
+            }
         }
     }
     S3D_CHECK(!pending_up && h.level == 0, "decoder structure");
@@ -1168,6 +1279,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         }
     }
     pb.close_zero_chain();
+    P->alloc_bytes += pb.arena.touched();
     P->sched_trace = pb.new_trace();
     CUDA_TRY(cudaDeviceSynchronize());
 }
