@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256, 2) k_boundary(BoundaryArgs A) {
                     for (int w = 0; w < 8; ++w) cs += red[w][which][ch];
                     acc += static_cast<double>(cs);
                 }
-                gn_fix_add(A.sink.acc + (static_cast<size_t>(b) * 3 + plane) * 64 + g * 2 + which, acc);
+                gn_fix_add(gn_acc(A.sink.acc, b, plane, ip) + g * 2 + which, acc);
             }
         }
     }

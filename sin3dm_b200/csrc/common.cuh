@@ -59,7 +59,7 @@ __device__ __forceinline__ void store_split4(__half* hi_ptr, __half* lo_ptr, flo
 
 // Opt-in device trace (s3d_unet_trace_enable): one thread per CTA stamps %globaltimer (ns, chip-wide) and clock64 (SM
 // cycles) at named points of a kernel; tools/trace_step.py turns the stamps into a timeline of one step.
-constexpr int kTraceSlots = 24;
+constexpr int kTraceSlots = 32;
 struct Trace {
     unsigned long long* buf;   // [max_ctas][2][kTraceSlots]; nullptr: tracing off
     int max_ctas;

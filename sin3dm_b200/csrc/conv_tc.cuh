@@ -52,7 +52,7 @@ struct ConvTcArgs {
 };
 
 struct RollTcMaps {
-    CUtensorMap a[6];   // means of source s: (C, L, 1, B, 2) fp16, box {64, 128, 1}
+    CUtensorMap a[6];   // means of source s: (C, L, 1, B, 2) fp16, box {64, 128, 1}  (stand-alone k_roll_tc only)
     CUtensorMap w[6];   // class-summed 1-D weights: (3C, 4*Cout, 2) fp16, K = along*C + c
 };
 struct RollTcArgs {
@@ -60,23 +60,23 @@ struct RollTcArgs {
     float* T[6];        // [B][4][L][Cout]
     int tile_start[7];
     int C, Cout;
+    int soff[6];        // position offset of source s inside a sample's block of axis sums
+    float scale[6];     // 2^-24 / (length of the averaged axis): fixed-point sum -> mean
 };
 // Fused launch: the rollout 1-D GEMM tiles ("roll tiles") are the first tile indices of the persistent conv kernel; the
 // conv tiles' epilogues wait on a device counter until every roll tile has been written (roll tiles never wait on
 // anything and are the first tiles of the lowest-numbered CTAs, so the wait cannot deadlock).
+// A roll tile's A operand is built in place: the (otherwise idle) epilogue warps read the 64-bit fixed-point axis sums that
+// k_gn_silu accumulated, turn them into (hi, lo) fp16 means and write them into an A slot in the 128-byte-swizzled layout the
+// tensor core expects — one 130-row patch per 64-channel block, which the three taps of the 1-D conv address with a start
+// offset of 0 / 1 / 2 rows.  No conversion pass, no grid-wide wait, no TMA round trip in front of the roll tiles.
 struct FusedRoll {
     RollTcArgs R;
     int n_roll;              // number of roll tiles (0: none; Trow/Tcol come from a separate launch or are absent)
     int ntn;                 // N tiles per roll M tile
-    unsigned int* counters;  // [3]: roll tiles done, CTAs exited, CTAs whose share of the means is converted
-                             //      (all return to 0 when the kernel ends)
-    // Phase 0 (every CTA, epilogue warps): axis sums (64-bit fixed point, accumulated by k_gn_silu) -> fp16 (hi, lo) means,
-    // the A operand the roll tiles then fetch by TMA; the accumulators are re-zeroed on the way.
-    unsigned long long* sums;     // [B][total_len][C]   nullptr: means16 already finalised by k_gn_silu
-    __half* means16;              // [2][B][total_len][C]
-    int total_len, B;
-    int seg_end[6];               // cumulative segment ends (positions) in a sample's block
-    float seg_scale[6];           // 2^-24 / (length of the averaged axis)
+    unsigned int* counters;  // [2]: roll tiles done, CTAs exited (both return to 0 when the kernel ends)
+    const unsigned long long* sums;   // [B][total_len][C] (re-zeroed by the next k_gn_silu of the step)
+    int total_len;
 };
 
 template <int NSPLIT>
@@ -84,12 +84,12 @@ struct ConvTcCfg {
     static constexpr int kASlotBytes = (NSPLIT == 3 ? 2 : 1) * kAHaloBytes;   // hi at +0, lo at +kAHaloBytes
     static constexpr int kBSlotBytes = (NSPLIT == 3 ? 2 : 1) * kBBytes;       // hi at +0, lo at +kBBytes
     static constexpr int kASlots = 2;
-    static constexpr int kBSlots = NSPLIT == 3 ? 3 : 6;
+    static constexpr int kBSlots = NSPLIT == 3 ? 4 : 8;
     static constexpr int kRingBytes = kASlots * kASlotBytes + kBSlots * kBSlotBytes;
     static constexpr int kAccCols = NSPLIT == 3 ? 128 : 64;     // TMEM columns of one accumulator stage
     static constexpr int kTmemCols = 2 * kAccCols;              // double-buffered accumulators
-    static constexpr int kStatBytes = kBM * 33 * 4 + 4 * 2 * 32 * 4 + 2 * kBN * 4 + 64 * 8 * 8 + 16;   // epilogue statistics scratch
-    static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStatBytes;
+    static constexpr int kEpiBytes = 4 * 32 * 32 * 4 + 64;      // epilogue staging: [32 rows][32 cols] fp32 per epilogue warp
+    static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
     // stand-alone k_roll_tc keeps the simple 4-stage {A,B} ring
     static constexpr int kStageBytes = (NSPLIT == 3 ? 2 : 1) * (kABytes + kBBytes);
     static constexpr int kStages = NSPLIT == 3 ? 4 : 8;
@@ -97,7 +97,7 @@ struct ConvTcCfg {
 };
 
 struct ConvTile {
-    int ip;    // tile index inside its plane (statistics slot)
+    int ip;    // tile index inside its plane
     int plane, h0, w0, n0, b;
 };
 __device__ __forceinline__ ConvTile conv_tile_decode(const ConvTcArgs& A, int t) {
@@ -138,14 +138,20 @@ __device__ __forceinline__ RollTile roll_tile_decode(const FusedRoll& F, int t) 
     return T;
 }
 
+constexpr int kRollRows = kBM + 2;      // rows of a roll tile's A patch: positions p0-1 .. p0+128
+
 // Persistent implicit-GEMM convolution, one CTA per SM, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
 //
-// Operand traffic is what bounds this kernel (64 B/clk per SM from L2), so the A operand is fetched ONCE per 64-channel
-// block as an 18 x 16-pixel halo patch and all nine taps read it in place: tap (kh, kw) is the same shared-memory patch
-// addressed from row (kh*16 + kw) with an 8-row-group stride of 2048 B (UMMA descriptor start / SBO / base_offset), i.e.
-// 1/6 of the activation bytes of a tap-by-tap im2col.  Only the 8 KiB weight tile changes per tap.
-// Two independent TMA producers (A patches, B tiles), one MMA issuer, four epilogue warps; accumulators double-buffered
-// in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+// Operand traffic is what bounds the main loop (L2 -> SM), so the A operand is fetched ONCE per 64-channel block as an
+// 18 x 16-pixel halo patch and all nine taps read it in place: tap (kh, kw) is the same shared-memory patch addressed from
+// row (kh*16 + kw) with an 8-row-group stride of 2048 B (UMMA descriptor start / SBO), i.e. 1/6 of the activation bytes of a
+// tap-by-tap im2col.  Only the 8 KiB weight tile changes per tap.
+// Warps: 0 = A producer (TMA), 6 = B producer (TMA), 1 = MMA issuer, 2..5 = epilogue.  Accumulators are double-buffered in
+// TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+// Epilogue: every epilogue warp is self-contained (no CTA-wide barrier): it owns the 32 accumulator rows of its TMEM lane
+// quarter (4 image rows x 8 pixels), moves them 32 columns at a time TMEM -> registers -> its own 4 KiB staging block
+// (16-byte XOR swizzle), and re-reads the block transposed so that 8 consecutive lanes cover 128 contiguous bytes of one pixel:
+// + bias + rollout 1-D terms + residual, fp32 NHWC store, and the GroupNorm group sums of what it stored (fixed-point atomics).
 template <int NSPLIT>
 __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_constant__ ConvTcMaps M,
                                                              const __grid_constant__ RollTcMaps RM, const ConvTcArgs A,
@@ -163,16 +169,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     uint64_t* tmem_full_bar = emptyB + Cfg::kBSlots;         // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    // epilogue statistics scratch (behind the 256-byte barrier block)
-    double* stat_fin = reinterpret_cast<double*>(smem + Cfg::kRingBytes + 256);                     // [64*8] (spare)
-    float* stat_stage = reinterpret_cast<float*>(stat_fin + 64 * 8);                               // [128][33]
-    float* stat_colp = stat_stage + kBM * 33;                                                      // [4][2][32]
-    float* stat_tot = stat_colp + 4 * 2 * 32;                                                      // [2][64]
-    int* stat_flag = reinterpret_cast<int*>(stat_tot + 2 * kBN);
+    float* stage = reinterpret_cast<float*>(smem + Cfg::kRingBytes + 256);      // [4 warps][32 rows][32 cols], 16-byte chunk k of row r at k ^ (r & 7)
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // trace slots: 0 entry, 1 set-up done, 2 phase 0 done, 3 means visible to the A producer, 22 exit; per local tile lt < 3 at
-    // 4 + 6*lt: +0 first operands landed, +1 all MMAs issued, +2 epilogue addends gathered, +3 accumulator complete,
+    // warp index through a shuffle: provably warp-uniform, so that everything the single-issuer roles compute from it lives in
+    // uniform registers (a role written under `if (lane == 0)` makes the compiler wrap every TMA / MMA issue in an
+    // elect-and-broadcast loop: measured ~117 cycles per tcgen05.mma instead of the 32-64 the tensor core needs)
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    // trace slots: 0 entry, 1 set-up done, 3 first roll patch filled, 22 exit; per local tile lt < 3 at 4 + 6*lt:
+    // +0 first operands landed, +1 all MMAs issued, +2 epilogue addends of the first batch requested, +3 accumulator complete,
     // +4 epilogue done, +5 A loads issued
     if (threadIdx.x == 0) trace_mark(A.tr, 0);
     const int cblks = A.C / kBK;
@@ -189,10 +193,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         }
         if (F.n_roll) {
 #pragma unroll
-            for (int p = 0; p < 6; ++p) {
-                ptx::prefetch_tmap(&RM.a[p]);
-                ptx::prefetch_tmap(&RM.w[p]);
-            }
+            for (int p = 0; p < 6; ++p) ptx::prefetch_tmap(&RM.w[p]);
         }
     }
     if (warp == 1) {
@@ -224,187 +225,207 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     pdl_trigger();
 
     if (warp == 0) {
-        // ===================== TMA producer: A operand groups =====================
-        if (lane == 0) {
-            pdl_wait();
-            int ga = 0, ltp = 0;
-            bool means_ready = false;
-            auto slot_wait = [&](uint32_t tx) -> uint8_t* {
+        // ===================== TMA producer: A operand groups (conv tiles; roll tiles are filled by the epilogue warps) =====
+        // The whole warp walks the loop converged; one elected lane issues.
+        if (lane == 0) trace_mark(A.tr, 24);
+        pdl_wait();
+        int ga = 0, ltp = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ltp) {
+            if (t < F.n_roll) {
+                ga += cblks;
+                continue;
+            }
+            const ConvTile T = conv_tile_decode(A, t - F.n_roll);
+            if (ltp == 0 && lane == 0) trace_mark(A.tr, 25);
+            for (int cb = 0; cb < cblks; ++cb, ++ga) {
                 const int s = ga % Cfg::kASlots;
                 ptx::mbar_wait(&emptyA[s], ((ga / Cfg::kASlots) & 1) ^ 1);
-                ptx::mbar_arrive_expect_tx(&fullA[s], tx);
-                return smem_a + s * Cfg::kASlotBytes;
-            };
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ltp) {
-                if (t < F.n_roll) {
-                    if (F.sums && !means_ready) {
-                        // every CTA converts a share of the means in its phase 0: wait for all of them, then order the
-                        // generic-proxy observation before the async-proxy (TMA) reads
-                        const volatile unsigned int* cnt = F.counters + 2;
-                        long long spins = 0;
-                        while (*cnt < gridDim.x) {
-                            if (++spins > (1LL << 31)) __trap();     // never hang the device
-                        }
-                        __threadfence();
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                        means_ready = true;
-                        trace_mark(A.tr, 3);
-                    }
-                    const RollTile T = roll_tile_decode(F, t);
-                    for (int i = 0; i < 3 * cblks; ++i, ++ga) {
-                        uint8_t* st = slot_wait(kAStdTx);
-                        const int s = ga % Cfg::kASlots;
-                        const int al = i / cblks, cb = i - al * cblks;
-                        ptx::tma_load_5d(st, &RM.a[T.src], &fullA[s], cb * kBK, T.p0 + al - 1, 0, T.b, 0);
-                        if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &RM.a[T.src], &fullA[s], cb * kBK, T.p0 + al - 1, 0, T.b, 1);
-                    }
-                    if (ltp < 3) trace_mark(A.tr, 4 + 6 * ltp + 5);
-                    continue;
-                }
-                const ConvTile T = conv_tile_decode(A, t - F.n_roll);
-                for (int cb = 0; cb < cblks; ++cb, ++ga) {
-                    uint8_t* st = slot_wait(kAHaloTx);
-                    const int s = ga % Cfg::kASlots;
+                if (ltp == 0 && cb == 0 && lane == 0) trace_mark(A.tr, 26);
+                uint8_t* st = smem_a + s * Cfg::kASlotBytes;
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&fullA[s], kAHaloTx);
                     ptx::tma_load_5d(st, &M.a[T.plane], &fullA[s], cb * kBK, T.w0 - 1, T.h0 - 1, T.b, 0);
                     if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &M.a[T.plane], &fullA[s], cb * kBK, T.w0 - 1, T.h0 - 1, T.b, 1);
                 }
-                for (int j = 0; j < nskip; ++j, ++ga) {
-                    uint8_t* st = slot_wait(kAStdTx);
-                    const int s = ga % Cfg::kASlots;
+                __syncwarp();
+            }
+            for (int j = 0; j < nskip; ++j, ++ga) {
+                const int s = ga % Cfg::kASlots;
+                ptx::mbar_wait(&emptyA[s], ((ga / Cfg::kASlots) & 1) ^ 1);
+                uint8_t* st = smem_a + s * Cfg::kASlotBytes;
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&fullA[s], kAStdTx);
                     ptx::tma_load_5d(st, &M.x[T.plane], &fullA[s], j * kBK, T.w0, T.h0, T.b, 0);
                     if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &M.x[T.plane], &fullA[s], j * kBK, T.w0, T.h0, T.b, 1);
                 }
-                if (ltp < 3) trace_mark(A.tr, 4 + 6 * ltp + 5);
+                __syncwarp();
             }
+            if (ltp < 3 && lane == 0) trace_mark(A.tr, 4 + 6 * ltp + 5);
         }
     } else if (warp == 6) {
         // ===================== TMA producer: B (weight) tiles =====================
-        if (lane == 0) {
-            int gb = 0;
-            auto load_b = [&](const CUtensorMap* wm, int kchunk, int n0) {
-                const int s = gb % Cfg::kBSlots;
-                ptx::mbar_wait(&emptyB[s], ((gb / Cfg::kBSlots) & 1) ^ 1);
+        if (lane == 0) trace_mark(A.tr, 27);
+        int gb = 0;
+        auto load_b = [&](const CUtensorMap* wm, int kchunk, int n0) {
+            const int s = gb % Cfg::kBSlots;
+            ptx::mbar_wait(&emptyB[s], ((gb / Cfg::kBSlots) & 1) ^ 1);
+            uint8_t* st = smem_b + s * Cfg::kBSlotBytes;
+            if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&fullB[s], Cfg::kBSlotBytes);
-                uint8_t* st = smem_b + s * Cfg::kBSlotBytes;
                 ptx::tma_load_3d(st, wm, &fullB[s], kchunk * kBK, n0, 0);
                 if (NSPLIT == 3) ptx::tma_load_3d(st + kBLo, wm, &fullB[s], kchunk * kBK, n0, 1);
-                ++gb;
-            };
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                if (t < F.n_roll) {
-                    const RollTile T = roll_tile_decode(F, t);
-                    for (int i = 0; i < 3 * cblks; ++i) load_b(&RM.w[T.src], i, T.n0);
-                    continue;
-                }
-                const ConvTile T = conv_tile_decode(A, t - F.n_roll);
-                for (int cb = 0; cb < cblks; ++cb)
-                    for (int tap = 0; tap < 9; ++tap) load_b(&M.w[T.plane], tap * cblks + cb, T.n0);
-                for (int j = 0; j < nskip; ++j) load_b(&M.w[T.plane], 9 * cblks + j, T.n0);
             }
+            __syncwarp();
+            if (gb == 0 && lane == 0) trace_mark(A.tr, 28);
+            if (gb == 8 && lane == 0) trace_mark(A.tr, 29);
+            ++gb;
+        };
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            if (t < F.n_roll) {
+                const RollTile T = roll_tile_decode(F, t);
+                for (int cb = 0; cb < cblks; ++cb)
+                    for (int al = 0; al < 3; ++al) load_b(&RM.w[T.src], al * cblks + cb, T.n0);
+                continue;
+            }
+            const ConvTile T = conv_tile_decode(A, t - F.n_roll);
+            for (int cb = 0; cb < cblks; ++cb)
+                for (int tap = 0; tap < 9; ++tap) load_b(&M.w[T.plane], tap * cblks + cb, T.n0);
+            for (int j = 0; j < nskip; ++j) load_b(&M.w[T.plane], 9 * cblks + j, T.n0);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, kBN);
-            constexpr uint32_t idesc2 = ptx::make_idesc_f16(kBM, 2 * kBN);
-            int ga = 0, gb = 0, lt = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-                const int as = lt & 1;
-                ptx::mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator stage
-                ptx::tc_fence_after();
-                const uint32_t d1 = tmem_base + as * Cfg::kAccCols, d2 = d1 + kBN;
-                const bool roll = t < F.n_roll;
-                const int n_halo = roll ? 0 : cblks;
-                const int n_groups = roll ? 3 * cblks : cblks + nskip;
-                bool first = true;
-                for (int g = 0; g < n_groups; ++g, ++ga) {
-                    const int sa = ga % Cfg::kASlots;
-                    ptx::mbar_wait(&fullA[sa], (ga / Cfg::kASlots) & 1);
-                    const uint32_t a_base = ptx::smem_u32(smem_a + sa * Cfg::kASlotBytes);
-                    const bool halo = g < n_halo;
-                    const int nb = halo ? 9 : 1;
-                    for (int tap = 0; tap < nb; ++tap, ++gb) {
-                        const int sb = gb % Cfg::kBSlots;
-                        ptx::mbar_wait(&fullB[sb], (gb / Cfg::kBSlots) & 1);
-                        ptx::tc_fence_after();
-                        if (first && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 0);
-                        const uint32_t b_base = ptx::smem_u32(smem_b + sb * Cfg::kBSlotBytes);
-                        uint64_t a_hi, a_lo;
-                        if (halo) {
-                            const int kh = tap / 3, kw = tap - kh * 3;
-                            const uint32_t off = static_cast<uint32_t>(kh * kHaloW + kw) * 128u;
-                            const uint32_t bo = A.bo_kw ? static_cast<uint32_t>(kw) : 0u;
-                            a_hi = ptx::make_sw128_desc(a_base + off, kHaloW * 128u, bo);
-                            a_lo = ptx::make_sw128_desc(a_base + kALo + off, kHaloW * 128u, bo);
-                        } else {
-                            a_hi = ptx::make_sw128_desc(a_base, 1024u, 0);
-                            a_lo = ptx::make_sw128_desc(a_base + kALo, 1024u, 0);
-                        }
-                        const uint64_t b_hi = ptx::make_sw128_desc(b_base, 1024u, 0);
+        constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, kBN);
+        constexpr uint32_t idesc2 = ptx::make_idesc_f16(kBM, 2 * kBN);
+        int ga = 0, gb = 0, lt = 0;
+        if (lane == 0) trace_mark(A.tr, 31);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int as = lt & 1;
+            ptx::mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator stage
+            ptx::tc_fence_after();
+            const uint32_t d1 = tmem_base + as * Cfg::kAccCols, d2 = d1 + kBN;
+            const bool roll = t < F.n_roll;
+            const int n_patch = cblks;                       // groups whose taps share one A patch (halo / roll patch)
+            const int n_groups = roll ? cblks : cblks + nskip;
+            uint32_t acc = 0u;                               // 0 for the very first MMA of the tile
+            for (int g = 0; g < n_groups; ++g, ++ga) {
+                const int sa = ga % Cfg::kASlots;
+                ptx::mbar_wait(&fullA[sa], (ga / Cfg::kASlots) & 1);
+                const uint32_t a_base = ptx::smem_u32(smem_a + sa * Cfg::kASlotBytes);
+                const bool patch = g < n_patch;
+                const int nb = patch ? (roll ? 3 : 9) : 1;
+                // start offset of tap 0 and its step per tap / per row of taps inside the shared patch
+                const uint32_t sbo = (patch && !roll) ? kHaloW * 128u : 1024u;
+                for (int tap = 0; tap < nb; ++tap, ++gb) {
+                    const int sb = gb % Cfg::kBSlots;
+                    ptx::mbar_wait(&fullB[sb], (gb / Cfg::kBSlots) & 1);
+                    ptx::tc_fence_after();
+                    if (acc == 0u && lt < 3 && lane == 0) trace_mark(A.tr, 4 + 6 * lt + 0);
+                    const uint32_t b_base = ptx::smem_u32(smem_b + sb * Cfg::kBSlotBytes);
+                    uint32_t off = 0;
+                    if (patch && !roll) {
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        off = static_cast<uint32_t>(kh * kHaloW + kw) * 128u;
+                    } else if (patch) {
+                        off = static_cast<uint32_t>(tap) * 128u;     // 1-D tap: rows tap .. tap+127 of the 130-row patch
+                    }
+                    const uint64_t a_hi = ptx::make_sw128_desc(a_base + off, sbo, 0);
+                    const uint64_t a_lo = ptx::make_sw128_desc(a_base + kALo + off, sbo, 0);
+                    const uint64_t b_hi = ptx::make_sw128_desc(b_base, 1024u, 0);
+                    if (ptx::elect_one()) {
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k) {
                             const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);   // +32 B along K inside the swizzle atom
-                            const uint32_t acc = (!first || k > 0) ? 1u : 0u;
                             if (NSPLIT == 3) {
                                 // [D1 | D2] (+)= Ah * [Bh | Bl]  (one N=128 MMA: the lo weight tile sits right behind the hi
                                 // tile in shared memory and D2 right behind D1 in TMEM), then D2 += Al * Bh
-                                ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc2, acc);
+                                ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc2, k == 0 ? acc : 1u);
                                 ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, 1u);
                             } else {
-                                ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, acc);
+                                ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, k == 0 ? acc : 1u);
                             }
                         }
-                        first = false;
                         ptx::umma_commit(&emptyB[sb]);    // weight slot free once the MMAs above retire
                     }
-                    ptx::umma_commit(&emptyA[sa]);        // A patch free once every tap has read it
+                    __syncwarp();
+                    acc = 1u;
                 }
-                ptx::umma_commit(&tmem_full_bar[as]);     // this tile's accumulators are complete
-                if (lt < 3) trace_mark(A.tr, 4 + 6 * lt + 1);
+                if (ptx::elect_one()) ptx::umma_commit(&emptyA[sa]);        // A patch free once every tap has read it
+                __syncwarp();
             }
+            if (ptx::elect_one()) ptx::umma_commit(&tmem_full_bar[as]);     // this tile's accumulators are complete
+            __syncwarp();
+            if (lt < 3 && lane == 0) trace_mark(A.tr, 4 + 6 * lt + 1);
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-        const int m = quarter * 32 + lane;
+        const int m = quarter * 32 + lane;            // accumulator row (pixel of the tile / position of the roll tile)
         const int et = threadIdx.x - 64;              // 0..127 among the epilogue threads
+        const int k8 = lane & 7, rloc = lane >> 3;    // transposed pass: 16-byte chunk k8 of staged rows rloc, rloc + 4, ...
+        float* wst = stage + quarter * 1024;          // this warp's staging block
         bool roll_ready = F.n_roll == 0;
-        int lt = 0;
+        int lt = 0, ga = 0;
+        if (et == 0) trace_mark(A.tr, 30);
         pdl_wait();
-        if (F.n_roll && F.sums) {
-            const int C = A.C;
-            const long long per_sample = static_cast<long long>(F.total_len) * C;
-            const long long total = per_sample * F.B;
-            const size_t lo_off = static_cast<size_t>(total);
-            for (long long i = static_cast<long long>(blockIdx.x) * 128 + et; i < total; i += static_cast<long long>(gridDim.x) * 128) {
-                const int pos = static_cast<int>((i % per_sample) / C);
-                int seg = 0;
-#pragma unroll
-                for (int k = 0; k < 5; ++k)
-                    if (pos >= F.seg_end[k]) seg = k + 1;
-                const long long sv = static_cast<long long>(__ldcg(F.sums + i));
-                F.sums[i] = 0ull;
-                const float mean = __ll2float_rn(sv) * F.seg_scale[seg];
-                __half hi, lo;
-                split_f16(mean, hi, lo);
-                F.means16[i] = hi;
-                F.means16[lo_off + i] = lo;
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) atomicAdd(&F.counters[2], 1u);
-            if (et == 0) trace_mark(A.tr, 2);
-        }
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int as = lt & 1;
             const uint32_t aph = (lt >> 1) & 1;
             const uint32_t lane_addr = tmem_base + as * Cfg::kAccCols + (static_cast<uint32_t>(quarter * 32) << 16);
             if (t < F.n_roll) {
-                // ---------- rollout 1-D GEMM tile: T[b][cls][pos][co] = accumulator ----------
+                // ---------- rollout 1-D GEMM tile ----------
                 const RollTile T = roll_tile_decode(F, t);
-                const int pos = T.p0 + m, L = F.R.L[T.src];
+                const int L = F.R.L[T.src];
+                // (1) A operand: axis sums -> (hi, lo) fp16 means, written swizzled into the A slots (one per 64-channel block)
+                {
+                    const unsigned long long* sp = F.sums + (static_cast<size_t>(T.b) * F.total_len + F.R.soff[T.src]) * A.C;
+                    const float scale = F.R.scale[T.src];
+                    constexpr int kChunks = kRollRows * 8;                  // 16-byte chunks (8 channels) of one patch
+                    constexpr int kIters = (kChunks + 127) / 128, kBatch = kIters;     // every load of a patch in flight at once
+                    for (int cb = 0; cb < cblks; ++cb, ++ga) {
+                        const int s = ga % Cfg::kASlots;
+                        if (et == 0 && lt == 0 && cb == 0) trace_mark(A.tr, 2);
+                        ptx::mbar_wait(&emptyA[s], ((ga / Cfg::kASlots) & 1) ^ 1);
+                        if (et == 0 && lt == 0 && cb == 0) trace_mark(A.tr, 16);
+                        uint8_t* hi = smem_a + s * Cfg::kASlotBytes;
+                        uint8_t* lo = hi + kALo;
+#pragma unroll
+                        for (int half = 0; half < 1; ++half) {
+                            ulonglong2 raw[kBatch][4];
+#pragma unroll
+                            for (int i = 0; i < kBatch; ++i) {
+                                const int q = et + 128 * (half * kBatch + i), j = q >> 3, k = q & 7, pos = T.p0 - 1 + j;
+                                const bool ok = q < kChunks && pos >= 0 && pos < L;
+                                const ulonglong2* src = reinterpret_cast<const ulonglong2*>(sp + static_cast<size_t>(ok ? pos : 0) * A.C + cb * kBK + k * 8);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) raw[i][e] = ok ? __ldcg(src + e) : make_ulonglong2(0ull, 0ull);
+                            }
+                            if (et == 0 && lt == 0 && cb == 0) trace_mark(A.tr, 17);
+#pragma unroll
+                            for (int i = 0; i < kBatch; ++i) {
+                                const int q = et + 128 * (half * kBatch + i), j = q >> 3, k = q & 7;
+                                if (q < kChunks) {
+                                    __half h[8], l[8];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        split_f16(__ll2float_rn(static_cast<long long>(raw[i][e].x)) * scale, h[2 * e], l[2 * e]);
+                                        split_f16(__ll2float_rn(static_cast<long long>(raw[i][e].y)) * scale, h[2 * e + 1], l[2 * e + 1]);
+                                    }
+                                    const uint32_t off = static_cast<uint32_t>(j) * 128u + (static_cast<uint32_t>(k ^ (j & 7)) << 4);
+                                    *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
+                                    if (NSPLIT == 3) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+                                }
+                            }
+                        }
+                        if (et == 0 && lt == 0 && cb == 0) trace_mark(A.tr, 18);
+                        ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (et == 0) ptx::mbar_arrive(&fullA[s]);
+                    }
+                    if (et == 0 && lt == 0) trace_mark(A.tr, 3);
+                }
+                // (2) T[b][cls][pos][co] = accumulator, through the warp's staging block so that the global stores are coalesced
                 const int cls = T.n0 / A.Cout, co0 = T.n0 - cls * A.Cout;
-                float* __restrict__ outp = F.R.T[T.src] + ((static_cast<size_t>(T.b) * 4 + cls) * L + pos) * A.Cout + co0;
+                float* __restrict__ outp = F.R.T[T.src] + ((static_cast<size_t>(T.b) * 4 + cls) * L + T.p0 + quarter * 32) * A.Cout + co0;
                 ptx::mbar_wait(&tmem_full_bar[as], aph);
                 if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 3);
                 __syncwarp();
@@ -420,94 +441,141 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
                     }
-                    if (pos < L) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float o[4];
+                    for (int j = 0; j < 32; j += 4) {
+                        float o[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                o[q] = __uint_as_float(v1[j + q]);
-                                if (NSPLIT == 3) o[q] = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, o[q]);
-                            }
-                            __stcg(reinterpret_cast<float4*>(outp + half * 32 + j), make_float4(o[0], o[1], o[2], o[3]));
+                        for (int q = 0; q < 4; ++q) {
+                            o[q] = __uint_as_float(v1[j + q]);
+                            if (NSPLIT == 3) o[q] = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, o[q]);
                         }
+                        *reinterpret_cast<float4*>(wst + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
                     }
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int ml = it * 4 + rloc;
+                        if (T.p0 + quarter * 32 + ml < L)
+                            __stcg(reinterpret_cast<float4*>(outp + static_cast<size_t>(ml) * A.Cout + half * 32) + k8,
+                                   *reinterpret_cast<const float4*>(wst + ml * 32 + ((k8 ^ (ml & 7)) << 2)));
+                    }
+                    __syncwarp();
                 }
+                if (et == 0 && lt == 0) trace_mark(A.tr, 19);
+                if (et == 0 && lt == 0) trace_mark(A.tr, 20);
                 __threadfence();
+                if (et == 0 && lt == 0) trace_mark(A.tr, 21);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (et == 0) atomicAdd(&F.counters[0], 1u);
                 if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 4);
                 continue;
             }
+            // ---------- conv tile ----------
+            ga += cblks + nskip;                       // A groups this tile consumes (keeps the ring index of the roll fills in step)
             const ConvTile T = conv_tile_decode(A, t - F.n_roll);
             const int plane = T.plane, n0 = T.n0, b = T.b;
-            const int r = T.h0 + (m >> 3), c = T.w0 + (m & 7);
             const int rows = A.d.rows[plane], cols = A.d.cols[plane];
-            const bool valid = r < rows && c < cols;
-            const size_t px = static_cast<size_t>(b) * rows * cols + static_cast<size_t>(r) * cols + c;
-            // Everything the epilogue adds to the accumulator (bias + rollout 1-D terms + additive embedding + identity
-            // residual) is gathered into registers while the MMA pipeline of this tile is still running.
-            float pre[kBN];
-            {
-                const float4* bias4 = reinterpret_cast<const float4*>(A.e.bias.p[plane] + n0);
-#pragma unroll
-                for (int j = 0; j < kBN / 4; ++j) {
-                    const float4 v = __ldg(bias4 + j);
-                    pre[4 * j] = v.x; pre[4 * j + 1] = v.y; pre[4 * j + 2] = v.z; pre[4 * j + 3] = v.w;
+            const size_t px0 = static_cast<size_t>(b) * rows * cols;
+            const int Cout = A.Cout;
+            const float* __restrict__ resid = A.e.resid.p[plane];
+            const float* __restrict__ Trow = A.e.Trow.p[plane];
+            const float* __restrict__ Tcol = A.e.Tcol.p[plane];
+            float* __restrict__ outb = A.e.out.p[plane];
+            if (Trow && !roll_ready) {
+                // the rollout terms are produced by this very launch (roll tiles): wait until all of them are written
+                if (lane == 0) {
+                    long long spins = 0;
+                    for (;;) {
+                        unsigned int v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(F.counters) : "memory");
+                        if (v >= static_cast<unsigned int>(F.n_roll)) break;
+                        if (++spins > (1LL << 31)) __trap();     // never hang the device
+                    }
                 }
+                __syncwarp();
+                roll_ready = true;
+                if (et == 0) trace_mark(A.tr, 23);
+            }
+            // Geometry of the transposed pass: lane (rloc = lane / 8, k8 = lane % 8) reads 16-byte chunk k8 of staged row
+            // ml = it*4 + rloc, it = 0..7, i.e. pixel (r0 + it/2, w0 + (it & 1)*4 + rloc): four image rows and two columns per
+            // thread.  What is added to the accumulator of one 32-channel half — residual, row-indexed and column-indexed
+            // rollout terms — is requested before the accumulator is awaited.
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int r0 = T.h0 + quarter * 4;
+            const int cx[2] = {T.w0 + rloc, T.w0 + 4 + rloc};
+            // Requests are issued as a block (`fetch`), folded into one addend per pixel (`fold`) only when they are needed: the
+            // first half's requests fly while the MMAs finish, the second half's while the first half is stored.
+            struct Addends {
+                float4 rs[8], trow[2][4], tcol[2][4], bias;
+            };
+            auto fetch = [&](int half, Addends& D) {
+                const int ch = n0 + half * 32;
+                // per-channel addends of this thread's quad: bias (+ additive timestep embedding)
+                D.bias = __ldg(reinterpret_cast<const float4*>(A.e.bias.p[plane] + ch) + k8);
                 if (A.e.embadd) {
-                    const float4* e4 = reinterpret_cast<const float4*>(
-                        A.e.embadd + static_cast<size_t>(A.e.film_row ? A.e.film_row[b] : b) * A.e.film_dim + A.e.film_off + n0);
-#pragma unroll
-                    for (int j = 0; j < kBN / 4; ++j) {
-                        const float4 v = __ldg(e4 + j);
-                        pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w;
-                    }
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(
+                        A.e.embadd + static_cast<size_t>(A.e.film_row ? A.e.film_row[b] : b) * A.e.film_dim + A.e.film_off + ch) + k8);
+                    D.bias.x += v.x; D.bias.y += v.y; D.bias.z += v.z; D.bias.w += v.w;
                 }
-                if (valid && A.e.resid.p[plane]) {
-                    const float4* rs = reinterpret_cast<const float4*>(A.e.resid.p[plane] + px * A.Cout + n0);
 #pragma unroll
-                    for (int j = 0; j < kBN / 4; ++j) {
-                        const float4 v = __ldg(rs + j);
-                        pre[4 * j] += v.x; pre[4 * j + 1] += v.y; pre[4 * j + 2] += v.z; pre[4 * j + 3] += v.w;
-                    }
+                for (int it = 0; it < 8; ++it) {
+                    const int r = r0 + (it >> 1), c = cx[it & 1];
+                    D.rs[it] = zero4;
+                    if (resid && r < rows && c < cols)
+                        D.rs[it] = __ldg(reinterpret_cast<const float4*>(resid + (px0 + static_cast<size_t>(r) * cols + c) * Cout + ch) + k8);
                 }
-                if (A.e.Trow.p[plane] && !roll_ready) {
-                    // the rollout terms are produced by this very launch (roll tiles): wait until all of them are written
-                    if (lane == 0) {
-                        const volatile unsigned int* cnt = F.counters;
-                        long long spins = 0;
-                        while (*cnt < static_cast<unsigned int>(F.n_roll)) {
-                            if (++spins > (1LL << 31)) __trap();     // never hang the device
+#pragma unroll
+                for (int x = 0; x < 2; ++x)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) D.trow[x][j] = D.tcol[x][j] = zero4;
+                if (Trow) {
+                    const size_t bo = static_cast<size_t>(b) * 4;
+                    // written by this launch: L2-coherent loads.  Equal edge classes share one load.
+                    const int cc0 = edge_class(min(cx[0], cols - 1), cols), cc1 = edge_class(min(cx[1], cols - 1), cols);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = min(r0 + j, rows - 1);
+                        D.trow[0][j] = __ldcg(reinterpret_cast<const float4*>(Trow + ((bo + cc0) * rows + r) * Cout + ch) + k8);
+                        D.trow[1][j] = cc1 == cc0 ? D.trow[0][j]
+                                                  : __ldcg(reinterpret_cast<const float4*>(Trow + ((bo + cc1) * rows + r) * Cout + ch) + k8);
+                    }
+#pragma unroll
+                    for (int x = 0; x < 2; ++x) {
+                        const int c = min(cx[x], cols - 1);
+                        int prev = -1;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int rc = edge_class(min(r0 + j, rows - 1), rows);
+                            if (j > 0 && rc == prev) D.tcol[x][j] = D.tcol[x][j - 1];
+                            else D.tcol[x][j] = __ldcg(reinterpret_cast<const float4*>(Tcol + ((bo + rc) * cols + c) * Cout + ch) + k8);
+                            prev = rc;
                         }
                     }
-                    __syncwarp();
-                    __threadfence();
-                    roll_ready = true;
                 }
-                if (valid && A.e.Trow.p[plane]) {
-                    const size_t bo = static_cast<size_t>(b) * 4;
-                    const float4* tr = reinterpret_cast<const float4*>(
-                        A.e.Trow.p[plane] + ((bo + edge_class(c, cols)) * rows + r) * A.Cout + n0);
-                    const float4* tc = reinterpret_cast<const float4*>(
-                        A.e.Tcol.p[plane] + ((bo + edge_class(r, rows)) * cols + c) * A.Cout + n0);
+            };
+            auto fold = [&](const Addends& D, float4 (&add)[8]) {
 #pragma unroll
-                    for (int j = 0; j < kBN / 4; ++j) {
-                        const float4 v = __ldcg(tr + j), u = __ldcg(tc + j);      // written by this launch: L2-coherent loads
-                        pre[4 * j] += v.x + u.x; pre[4 * j + 1] += v.y + u.y; pre[4 * j + 2] += v.z + u.z;
-                        pre[4 * j + 3] += v.w + u.w;
-                    }
+                for (int it = 0; it < 8; ++it) {
+                    const float4 tr = D.trow[it & 1][it >> 1], tc = D.tcol[it & 1][it >> 1], rs = D.rs[it];
+                    add[it].x = D.bias.x + rs.x + (tr.x + tc.x);
+                    add[it].y = D.bias.y + rs.y + (tr.y + tc.y);
+                    add[it].z = D.bias.z + rs.z + (tr.z + tc.z);
+                    add[it].w = D.bias.w + rs.w + (tr.w + tc.w);
                 }
-            }
-            float* __restrict__ outp = A.e.out.p[plane] + px * A.Cout + n0;
+            };
+            Addends D;
+            float4 add0[8], add1[8];
+            fetch(0, D);
             if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 2);
             ptx::mbar_wait(&tmem_full_bar[as], aph);
             if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 3);
             __syncwarp();
             ptx::tc_fence_after();
+            fold(D, add0);
+            fetch(1, D);
             const bool do_stats = A.sink.acc != nullptr;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            float4 ssum[2] = {zero4, zero4}, ssq[2] = {zero4, zero4};
+            auto half_pass = [&](int half, const float4 (&add)[8]) {
                 uint32_t v1[32], v2[32];
                 ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
                 if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
@@ -523,49 +591,77 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     float o[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float acc = __uint_as_float(v1[j + q]);
-                        if (NSPLIT == 3) acc = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, acc);
-                        o[q] = acc + pre[half * 32 + j + q];
+                        o[q] = __uint_as_float(v1[j + q]);
+                        if (NSPLIT == 3) o[q] = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, o[q]);
                     }
-                    if (valid) *reinterpret_cast<float4*>(outp + half * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
-                    if (do_stats) {
+                    *reinterpret_cast<float4*>(wst + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                __syncwarp();
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) stat_stage[m * 33 + j + q] = valid ? o[q] : 0.f;
+                for (int it = 0; it < 8; ++it) {
+                    const int ml = it * 4 + rloc, r = r0 + (it >> 1), c = cx[it & 1];
+                    if (r < rows && c < cols) {
+                        const float4 a = *reinterpret_cast<const float4*>(wst + ml * 32 + ((k8 ^ (ml & 7)) << 2));
+                        float4 o;
+                        o.x = a.x + add[it].x;
+                        o.y = a.y + add[it].y;
+                        o.z = a.z + add[it].z;
+                        o.w = a.w + add[it].w;
+                        *reinterpret_cast<float4*>(outb + (px0 + static_cast<size_t>(r) * cols + c) * Cout + n0 + half * 32 + 4 * k8) = o;
+                        ssum[half].x += o.x; ssum[half].y += o.y; ssum[half].z += o.z; ssum[half].w += o.w;
+                        ssq[half].x = fmaf(o.x, o.x, ssq[half].x); ssq[half].y = fmaf(o.y, o.y, ssq[half].y);
+                        ssq[half].z = fmaf(o.z, o.z, ssq[half].z); ssq[half].w = fmaf(o.w, o.w, ssq[half].w);
                     }
                 }
-                if (do_stats) {
-                    // per-channel (sum, sum-sq) of this tile's 128 pixels, fixed summation order
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    {
-                        const int cc = et & 31, qq = et >> 5;
-                        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                        for (int p = 0; p < 32; ++p) {
-                            const float v = stat_stage[(qq * 32 + p) * 33 + cc];
-                            s1 += v;
-                            s2 = fmaf(v, v, s2);
-                        }
-                        stat_colp[(qq * 2 + 0) * 32 + cc] = s1;
-                        stat_colp[(qq * 2 + 1) * 32 + cc] = s2;
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (et < 64) {
-                        const int which = et >> 5, cc = et & 31;
-                        stat_tot[which * kBN + half * 32 + cc] = (stat_colp[(0 * 2 + which) * 32 + cc] + stat_colp[(1 * 2 + which) * 32 + cc]) +
-                                                                 (stat_colp[(2 * 2 + which) * 32 + cc] + stat_colp[(3 * 2 + which) * 32 + cc]);
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
-            }
+                __syncwarp();                      // the staging block is rewritten by the next half / tile
+            };
+            half_pass(0, add0);
+            fold(D, add1);
+            half_pass(1, add1);
             if (do_stats) {
-                const int cpg = A.Cout / kGroups, gpt = kBN / cpg, g0 = n0 / cpg;
-                if (et < 2 * gpt) {
-                    const int gl = et >> 1, which = et & 1;
-                    double acc = 0.0;
-                    for (int cc = gl * cpg; cc < (gl + 1) * cpg; ++cc) acc += static_cast<double>(stat_tot[which * kBN + cc]);
-                    gn_fix_add(A.sink.acc + (static_cast<size_t>(b) * 3 + plane) * 64 + (g0 + gl) * 2 + which, acc);
+                // (sum, sum-sq) per channel over the warp's 32 pixels: the four row groups of a lane column are added in a fixed
+                // order, then every GroupNorm group goes out as one fixed-point atomic (exact, so the order of the warps and
+                // tiles does not matter)
+                constexpr unsigned kFull = 0xffffffffu;
+                const int cpg = Cout / kGroups;              // 2, 4 or 8 (host-checked)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float v[8] = {ssum[half].x, ssum[half].y, ssum[half].z, ssum[half].w, ssq[half].x, ssq[half].y, ssq[half].z, ssq[half].w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        v[e] += __shfl_xor_sync(kFull, v[e], 8);
+                        v[e] += __shfl_xor_sync(kFull, v[e], 16);
+                    }
+                    // lanes 0..7 now hold channels n0 + half*32 + 4*k8 .. +3
+                    double gs[2][2];                          // [group inside the quad][sum / sum-sq]
+                    if (cpg == 2) {
+                        gs[0][0] = static_cast<double>(v[0]) + static_cast<double>(v[1]);
+                        gs[1][0] = static_cast<double>(v[2]) + static_cast<double>(v[3]);
+                        gs[0][1] = static_cast<double>(v[4]) + static_cast<double>(v[5]);
+                        gs[1][1] = static_cast<double>(v[6]) + static_cast<double>(v[7]);
+                    } else {
+                        gs[0][0] = (static_cast<double>(v[0]) + static_cast<double>(v[1])) + (static_cast<double>(v[2]) + static_cast<double>(v[3]));
+                        gs[0][1] = (static_cast<double>(v[4]) + static_cast<double>(v[5])) + (static_cast<double>(v[6]) + static_cast<double>(v[7]));
+                        gs[1][0] = gs[1][1] = 0.0;
+                        if (cpg == 8) {                       // a group spans two neighbouring lanes
+                            gs[0][0] += __shfl_xor_sync(kFull, gs[0][0], 1);
+                            gs[0][1] += __shfl_xor_sync(kFull, gs[0][1], 1);
+                        }
+                    }
+                    if (lane < 8) {
+                        const int ch = n0 + half * 32 + 4 * k8;
+                        unsigned long long* acc = gn_acc(A.sink.acc, b, plane, T.ip * 4 + quarter);
+                        if (cpg == 2) {
+                            gn_fix_add(acc + (ch / 2) * 2, gs[0][0]);
+                            gn_fix_add(acc + (ch / 2) * 2 + 1, gs[0][1]);
+                            gn_fix_add(acc + (ch / 2 + 1) * 2, gs[1][0]);
+                            gn_fix_add(acc + (ch / 2 + 1) * 2 + 1, gs[1][1]);
+                        } else if (cpg == 4 || (lane & 1) == 0) {
+                            gn_fix_add(acc + (ch / cpg) * 2, gs[0][0]);
+                            gn_fix_add(acc + (ch / cpg) * 2 + 1, gs[0][1]);
+                        }
+                    }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // stat_tot is reused by the next tile
             }
             if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 4);
         }
@@ -583,7 +679,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         if (prev == gridDim.x - 1) {
             F.counters[0] = 0u;
             F.counters[1] = 0u;
-            F.counters[2] = 0u;
         }
     }
 }

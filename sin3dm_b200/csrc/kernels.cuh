@@ -16,14 +16,16 @@ namespace s3d {
 // with one 64-value load per CTA (no statistics pass, no partial-slot reduction).  The accumulators of a tensor are re-zeroed
 // by the NEXT consumer kernel in the step (its `zero` job), i.e. after their only reader has finished.
 // =====================================================================================
+constexpr int kGnRep = 8;                         // replicas of the accumulators: same-address atomics serialise in the L2
+                                                  // (~25 ns each, measured), so producers spread over kGnRep copies
 constexpr double kGnFix = 1048576.0;              // 2^20
 constexpr double kGnFixInv = 1.0 / 1048576.0;
 struct StatsSink {                 // producer side
-    unsigned long long* acc;  // [B][3][64]  (sum, sum-sq) of the 32 groups, fixed point; nullptr: not wanted
+    unsigned long long* acc;  // [B][3][kGnRep][64]  (sum, sum-sq) of the 32 groups, fixed point; nullptr: not wanted
     int C;
 };
 struct StatsSrc {                  // consumer side
-    const unsigned long long* acc;   // [B][3][64]
+    const unsigned long long* acc;   // [B][3][kGnRep][64]
     TriCF gamma, beta;        // consumer norm parameters [C]
     const float* film;        // [rows][film_dim] or nullptr
     const int* film_row;
@@ -34,14 +36,26 @@ struct StatsSrc {                  // consumer side
 __device__ __forceinline__ void gn_fix_add(unsigned long long* p, double v) {
     atomicAdd(p, static_cast<unsigned long long>(__double2ll_rn(v * kGnFix)));
 }
+// accumulator block of (sample b, plane) for a producer that identifies itself by `who` (tile / CTA index)
+__device__ __forceinline__ unsigned long long* gn_acc(unsigned long long* acc, int b, int plane, int who) {
+    return acc + ((static_cast<size_t>(b) * 3 + plane) * kGnRep + (who & (kGnRep - 1))) * 64;
+}
 
 // Consumer prologue (all threads of the CTA, nthr >= 64); fin: smem double[64]; coefA/coefB: smem float[C].
 __device__ __forceinline__ void stats_coef_prologue(const StatsSrc& S, int b, int plane, int C, double n_per_group, int tid, int nthr,
                                                     double* fin, float* coefA, float* coefB) {
     const float* film = nullptr;
     if (S.film) film = S.film + static_cast<size_t>(S.film_row ? S.film_row[b] : b) * S.film_dim + S.film_off;
-    if (tid < 64)
-        fin[tid] = static_cast<double>(static_cast<long long>(__ldcg(S.acc + (static_cast<size_t>(b) * 3 + plane) * 64 + tid))) * kGnFixInv;
+    if (tid < 64) {
+        const unsigned long long* p = S.acc + (static_cast<size_t>(b) * 3 + plane) * kGnRep * 64 + tid;
+        unsigned long long v[kGnRep];
+#pragma unroll
+        for (int r = 0; r < kGnRep; ++r) v[r] = __ldcg(p + r * 64);
+        unsigned long long tot = 0ull;                  // integer sum of the replicas: exact, order-free
+#pragma unroll
+        for (int r = 0; r < kGnRep; ++r) tot += v[r];
+        fin[tid] = static_cast<double>(static_cast<long long>(tot)) * kGnFixInv;
+    }
     if (S.zero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
         for (int i = tid; i < S.zero_n; i += nthr) S.zero[i] = 0ull;
     __syncthreads();
@@ -89,7 +103,7 @@ __device__ __forceinline__ void stats_block_add(const StatsSink& S, float4 s, fl
         const int g = tid >> 1, which = tid & 1;
         double acc = 0.0;
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) acc += static_cast<double>(tot[which * C + c]);
-        gn_fix_add(S.acc + (static_cast<size_t>(b) * 3 + plane) * 64 + g * 2 + which, acc);
+        gn_fix_add(gn_acc(S.acc, b, plane, blockIdx.x) + g * 2 + which, acc);
     }
 }
 
@@ -329,6 +343,8 @@ struct GnSiluArgs {
     int seg_off[6];
     int total_len;
     Trace tr;                 // slots: 0 entry, 1 coefficients ready, 2 column atomics issued, 3 row atomics + operand stores issued
+    unsigned long long* zero_sums;   // axis sums of an earlier site whose reader (a conv's roll tiles) is done: cleared here
+    long long zero_sums_n;
     int ncg;                  // column groups per CTA: the CTA's tile is kGsRows rows x (blockDim.y * ncg) columns
     int finalize;             // 1: the last CTA of a strip / column tile converts the sums to fp16 means itself (stand-alone roll
                               //    kernels); 0: k_conv_tc does it in its phase 0 and this kernel ends right after the atomics
@@ -363,6 +379,11 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
     const int tid = ty * blockDim.x + tx, nthr = blockDim.x * ny;
     const int ncg = A.ncg, tw = ny * ncg;                    // the CTA's tile is kGsRows x tw pixels, ncg column groups of ny
     const int ctiles = (cols + tw - 1) / tw, strips = (rows + kGsRows - 1) / kGsRows;
+    if (A.zero_sums) {
+        const long long cta = blockIdx.x + static_cast<long long>(gridDim.x) * (blockIdx.y + gridDim.y * blockIdx.z);
+        const long long ncta = static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z;
+        for (long long i = cta * nthr + tid; i < A.zero_sums_n; i += ncta * nthr) A.zero_sums[i] = 0ull;
+    }
     if (static_cast<int>(blockIdx.x) >= ctiles * strips) return;
     if (tid == 0) trace_mark(A.tr, 0);
     const int strip = blockIdx.x / ctiles, ct = blockIdx.x - strip * ctiles;

@@ -679,7 +679,7 @@ struct PlanBuilder {
     std::shared_ptr<SinkBox> make_box(int C) {
         auto bx = std::make_shared<SinkBox>();
         StatsSink& S = bx->s;
-        const size_t n = static_cast<size_t>(B) * 3 * 64;
+        const size_t n = static_cast<size_t>(B) * 3 * kGnRep * 64;
         S.acc = dev_alloc<unsigned long long>(P->allocs, n);
         CUDA_TRY(cudaMemset(S.acc, 0, sizeof(unsigned long long) * n));
         S.C = C;
@@ -694,16 +694,23 @@ struct PlanBuilder {
     void chain_zero(const std::shared_ptr<SinkBox>& bx) {
         if (last_consumed) {
             bx->src.zero = last_consumed->s.acc;
-            bx->src.zero_n = B * 3 * 64;
+            bx->src.zero_n = B * 3 * kGnRep * 64;
         }
         if (!first_consumed) first_consumed = bx;
         last_consumed = bx;
     }
+    struct ZeroJob {
+        unsigned long long* p = nullptr;
+        long long n = 0;
+    };
+    ZeroJob last_sums{};
+    std::shared_ptr<ZeroJob> first_zero_job;
     void close_zero_chain() {
         if (first_consumed && last_consumed) {
             first_consumed->src.zero = last_consumed->s.acc;
-            first_consumed->src.zero_n = B * 3 * 64;
+            first_consumed->src.zero_n = B * 3 * kGnRep * 64;
         }
+        if (first_zero_job && last_sums.p) *first_zero_job = last_sums;
     }
     // sink as seen by a producer launch: disabled unless a consumer armed it
     static StatsSink live_sink(const std::shared_ptr<SinkBox>& bx) {
@@ -792,11 +799,22 @@ struct PlanBuilder {
         const size_t smem = sizeof(float) * (2 + static_cast<size_t>(ny) * kGsRows) * C;
         S3D_CHECK(smem <= 100 * 1024, "k_gn_silu shared memory");
         A.tr = new_trace();
+        // Axis sums that a conv's roll tiles read raw are cleared by the NEXT k_gn_silu of the step (all its CTAs share the
+        // work); the first one clears the last one's, which is a step old by then.  (With A.finalize the kernel converts and
+        // clears its own sums.)
+        auto zj = std::make_shared<ZeroJob>();
+        if (S && !A.finalize) {
+            if (last_sums.p) *zj = last_sums;
+            if (!first_zero_job) first_zero_job = zj;
+            last_sums = ZeroJob{S->buf, static_cast<long long>(B) * S->total_len * C};
+        }
         const int Bv = B;
         Plan* Pp = P;
         add_op("k_gn_silu", 0.0, [=](cudaStream_t s) {
             GnSiluArgs Al = A;
             Al.st = live_src(st, Pp);
+            Al.zero_sums = zj->p;
+            Al.zero_sums_n = zj->n;
             dim3 grid(gx, 3, Bv), block(bx, ny);
             launch(k_gn_silu, dim3(grid), dim3(block), smem, s, Al, Bv);
             LAUNCH_CHECK("k_gn_silu");
@@ -879,6 +897,12 @@ struct PlanBuilder {
             A.L[i] = L[i];
             A.ncls[i] = ncls[i];
             A.T[i] = Tp[i];
+            A.soff[i] = soff[i];
+            {
+                const SrcDef sd = def[i / 2][i % 2];
+                const int avg_len = sd.kind == 0 ? d.cols[sd.sp] : d.rows[sd.sp];     // length of the axis the mean runs over
+                A.scale[i] = static_cast<float>(1.0 / 16777216.0 / static_cast<double>(avg_len));
+            }
             A.tile_start[i] = total;
             total += (L[i] + kBM - 1) / kBM;
             const uint64_t adims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L[i]), 1, static_cast<uint64_t>(B), 2};
@@ -988,9 +1012,10 @@ struct PlanBuilder {
         const int nsplit = u->cfg.precision == 1 ? 1 : 3;
         const int ntile_n = cv.Cout / kBN;
         const int num_sms = u->num_sms;
-        // the epilogue can emit the output's GroupNorm partials when a 64-channel N tile holds whole groups
+        // the epilogue emits the output's GroupNorm group sums when a group is 2, 4 or 8 channels wide (Cout = 64, 128, 256)
         std::shared_ptr<SinkBox> box;
-        if (cv.Cout % kGroups == 0 && kBN % (cv.Cout / kGroups) == 0) {
+        const int cpg_out = cv.Cout / kGroups;
+        if (cv.Cout % kGroups == 0 && (cpg_out == 2 || cpg_out == 4 || cpg_out == 8)) {
             box = make_box(cv.Cout);
             out.sink = box;
         }
@@ -1002,19 +1027,11 @@ struct PlanBuilder {
             F.R = T->roll_args;
             F.ntn = T->roll_ntn;
             F.n_roll = T->roll_mtiles * T->roll_ntn * B;
-            F.counters = dev_alloc<unsigned int>(P->allocs, 3);
-            CUDA_TRY(cudaMemset(F.counters, 0, 3 * sizeof(unsigned int)));
-            // phase 0 of the kernel finalises the means (k_gn_silu only accumulated the sums)
+            F.counters = dev_alloc<unsigned int>(P->allocs, 2);
+            CUDA_TRY(cudaMemset(F.counters, 0, 2 * sizeof(unsigned int)));
+            // the roll tiles read the raw axis sums k_gn_silu accumulated (re-zeroed by the next k_gn_silu of the step)
             F.sums = T->sums.buf;
-            F.means16 = T->sums.means16;
             F.total_len = T->sums.total_len;
-            F.B = B;
-            for (int p = 0; p < 3; ++p)
-                for (int kind = 0; kind < 2; ++kind) {
-                    const int i = p * 2 + kind;
-                    F.seg_end[i] = T->sums.seg_off[i] + (kind == 0 ? d.rows[p] : d.cols[p]);
-                    F.seg_scale[i] = static_cast<float>(1.0 / 16777216.0 / static_cast<double>(kind == 0 ? d.cols[p] : d.rows[p]));
-                }
         }
         add_op("k_conv_tc", conv_flops(level, cv), [=](cudaStream_t s) {
             ConvTcArgs Al = A;
@@ -1172,7 +1189,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     auto in_box = pb.make_box(c0);
     h.sink = in_box;
     P->in_acc = in_box->s.acc;
-    P->in_acc_n = static_cast<size_t>(B) * 3 * 64;
+    P->in_acc_n = static_cast<size_t>(B) * 3 * kGnRep * 64;
     {
         const int Cin = c.in_channels;
         const Trace tr = pb.new_trace();
@@ -1316,6 +1333,17 @@ static void clear_stale_in_acc(Plan* P, cudaStream_t s) {
     }
 }
 static void run_ops(s3d_unet* u, Plan* P, cudaStream_t s) {
+    // experiment switch (timing only, results are wrong): S3D_DUP_OPS=1 launches every op twice back to back, so that the
+    // trace of the second launch shows what a warm instruction / constant cache is worth
+    static const bool dup = getenv("S3D_DUP_OPS") && atoi(getenv("S3D_DUP_OPS")) != 0;
+    if (dup) {
+        for (auto& op : P->ops) {
+            op(s);
+            op(s);
+        }
+        u->last_launches = static_cast<int>(P->ops.size());
+        return;
+    }
     for (auto& op : P->ops) op(s);
     u->last_launches = static_cast<int>(P->ops.size());
 }

@@ -17,9 +17,11 @@ import numpy as np
 import torch
 
 SLOT_NAMES = {
-    "k_conv_tc": {0: "entry", 1: "setup", 2: "phase0", 3: "means_vis", 22: "exit",
-                  **{4 + 6 * lt + k: f"t{lt}.{n}" for lt in range(3)
-                     for k, n in enumerate(("opnd", "mma_iss", "pre", "acc", "epi", "a_iss"))}},
+    "k_conv_tc": {**{4 + 6 * lt + k: f"t{lt}.{n}" for lt in range(3)
+                     for k, n in enumerate(("opnd", "mma_iss", "pre", "acc", "epi", "a_iss"))},
+                  0: "entry", 1: "setup", 2: "roll.begin", 16: "roll.slot", 17: "roll.ldiss", 18: "roll.filled", 3: "roll.A_done",
+                  19: "roll.staged", 20: "roll.stored", 21: "roll.fenced", 23: "roll_seen", 22: "exit",
+                  24: "A.role", 25: "A.decoded", 26: "A.slot", 27: "B.role", 28: "B.first", 29: "B.ninth", 30: "epi.role", 31: "mma.role"},
     "k_gn_silu": {0: "entry", 1: "coef", 2: "stored", 3: "row_atom"},
     "k_boundary<in_conv>": {0: "entry", 1: "head", 2: "sched", 3: "in_conv"},
     "k_boundary<head>": {0: "entry", 1: "head", 2: "sched", 3: "in_conv"},
