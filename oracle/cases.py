@@ -71,3 +71,37 @@ def make_step_noise(case, n_steps):
     x_T = torch.randn(shape, generator=g)
     noises = {i: torch.randn(shape, generator=g) for i in range(n_steps - 1, -1, -1)}
     return x_T, noises
+
+
+# ---------------------------------------------------------------------------- triplane decoder
+DECODER_CASES = {
+    # default auto-encoder (parser_util.py:19-26), ragged plane sizes, points inside and a little outside the box
+    "default": dict(spec=dict(), wseed=51, HWD=(20, 28, 18), n=777, aabb=[-0.7, -1.0, -0.6, 0.7, 1.0, 0.66], seed=61,
+                    spill=1.15),
+    # H > W > D
+    "tall": dict(spec=dict(), wseed=52, HWD=(26, 14, 9), n=300, aabb=[-1.0, -0.5, -0.3, 1.0, 0.55, 0.35], seed=62,
+                 spill=1.0),
+    # data_type == "sdf": geometry branch only
+    "sdf_only": dict(spec=dict(use_tex=False, tex_feat_channels=0), wseed=53, HWD=(12, 16, 12), n=257,
+                     aabb=[-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], seed=63, spill=1.3),
+    # decode_grid (model.py:335-349) over sample_grid_points_aabb (utils3d.py:13-25)
+    "grid": dict(spec=dict(), wseed=54, HWD=(16, 22, 12), grid=20, aabb=[-0.72, -1.0, -0.55, 0.72, 1.0, 0.55], seed=64),
+}
+
+
+def make_decoder_inputs(case):
+    """-> (feat_maps [xy, xz, yz] each [1, c, ., .] in (-1, 1) like the encoder's tanh output, points [n, 3] or None,
+    aabb [6])."""
+    from oracle.decoder_ref import DecoderSpec
+    spec = DecoderSpec(**case["spec"])
+    c = spec.geo_feat_channels + (spec.tex_feat_channels if spec.use_tex else 0)
+    H, W, D = case["HWD"]
+    g = torch.Generator().manual_seed(case["seed"])
+    maps = [torch.tanh(torch.randn(1, c, a, b, generator=g)) for a, b in ((H, W), (H, D), (W, D))]
+    aabb = torch.tensor(case["aabb"], dtype=torch.float32)
+    pts = None
+    if "n" in case:
+        u = torch.rand(case["n"], 3, generator=g) * 2 - 1
+        centre, half = (aabb[3:] + aabb[:3]) / 2, (aabb[3:] - aabb[:3]) / 2
+        pts = centre + u * half * case["spill"]
+    return maps, pts, aabb

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "s3d.cu")
 OUT = os.path.join(HERE, "lib", "libsin3dm_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("s3d.cu", "kernels.cuh", "conv_tc.cuh", "common.cuh", "ptx.cuh")] + \
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("s3d.cu", "kernels.cuh", "conv_tc.cuh", "boundary.cuh", "common.cuh", "ptx.cuh")] + \
        [os.path.join(os.path.dirname(HERE), "include", "sin3dm_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
