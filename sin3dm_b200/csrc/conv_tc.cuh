@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     uint64_t* emptyB = fullB + Cfg::kBSlots;
     uint64_t* tmem_full_bar = emptyB + Cfg::kBSlots;         // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* roll_filled_bar = tmem_empty_bar + 2;          // the CTA's last roll tile has written its A patches
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(roll_filled_bar + 1);
     float* stage = reinterpret_cast<float*>(smem + Cfg::kRingBytes + 256);      // [4 warps][32 rows][32 cols], 16-byte chunk k of row r at k ^ (r & 7)
 
     // warp index through a shuffle: provably warp-uniform, so that everything the single-issuer roles compute from it lives in
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 ptx::mbar_init(&tmem_full_bar[s], 1);
                 ptx::mbar_init(&tmem_empty_bar[s], 4);       // one arrive per epilogue warp
             }
+            ptx::mbar_init(roll_filled_bar, 1);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -230,10 +232,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
         if (lane == 0) trace_mark(A.tr, 24);
         pdl_wait();
         int ga = 0, ltp = 0;
+        bool ring_synced = false;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ltp) {
             if (t < F.n_roll) {
                 ga += cblks;
                 continue;
+            }
+            // The A ring has two producers: the epilogue warps fill it for the roll tiles, this warp for the conv tiles.  A
+            // parity wait only tells neighbouring phases apart, so this warp may not enter the ring two or more phases ahead
+            // of the consumer: when the CTA's roll tiles take 2 * kASlots groups or more (several roll tiles per CTA at large
+            // batch), wait until the last of them has been written (then every earlier group but the last per slot has been
+            // released, and the in-order chain below is exact again).
+            if (!ring_synced) {
+                ring_synced = true;
+                if (ga >= 2 * Cfg::kASlots) ptx::mbar_wait(roll_filled_bar, 0);
             }
             const ConvTile T = conv_tile_decode(A, t - F.n_roll);
             if (ltp == 0 && lane == 0) trace_mark(A.tr, 25);
@@ -421,6 +433,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         asm volatile("bar.sync 1, 128;" ::: "memory");
                         if (et == 0) ptx::mbar_arrive(&fullA[s]);
                     }
+                    if (et == 0 && t + static_cast<int>(gridDim.x) >= F.n_roll) ptx::mbar_arrive(roll_filled_bar);
                     if (et == 0 && lt == 0) trace_mark(A.tr, 3);
                 }
                 // (2) T[b][cls][pos][co] = accumulator, through the warp's staging block so that the global stores are coalesced

@@ -94,3 +94,25 @@ def test_reference_checkpoint_keys_roundtrip(tmp_path):
     with torch.no_grad():
         out = m2(torch.randn(1, 12, 24, 24).cuda(), torch.tensor([3]).cuda(), H=16, W=16, D=8)
     assert torch.all(out == 0)      # zero-initialised out conv: a fresh model predicts exactly 0
+
+
+@pytest.mark.parametrize("B", [8, 20])
+def test_large_batch_several_roll_tiles_per_cta(B):
+    """More rollout 1-D tiles than CTAs (batch >= 5 at the half-resolution level): a CTA then runs several roll tiles
+    before its first conv tile, and the two producers of the A ring (epilogue warps / TMA warp) must stay in step.
+    Sample b of the batch must equal the same sample run alone, bit for bit, and the oracle within tolerance."""
+    spec = ur.UNetSpec(in_channels=8, model_channels=64, out_channels=8)
+    sd = ur.synthetic_state_dict(spec, 91)
+    H, W, D = 12, 16, 10
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, 8, H + D, W + D, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    m = make_cuda_model(spec, sd, 3, "tc")
+    with torch.no_grad():
+        out = m(x.cuda(), t.cuda(), H=H, W=W, D=D)
+        one = m(x[B - 1:].cuda(), t[B - 1:].cuda(), H=H, W=W, D=D)
+    torch.cuda.synchronize()
+    assert torch.equal(out[B - 1:], one)
+    want = ur.unet_forward(sd, spec, x[:2], t[:2], H, W, D)
+    rel, mx = plane_errors(out[:2].cpu(), want, H, W, D)
+    assert rel < TOL and mx < TOL, (rel, mx)
