@@ -157,6 +157,55 @@ typedef struct {
 
 int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream);
 
+
+/* ---- triplane decoder (replaces AutoEncoderGroupSkip.decode and ShapeAutoEncoder.decode_batch / decode_grid:
+ *      reference src/encoding/networks.py:134-223, src/encoding/model.py:319-349) ----
+ * Latent planes in, SDF + texture at query points out.  The two TriplaneGroupResnetBlocks (blocks.py:189-256) depend on
+ * the latent only: s3d_decoder_set_planes runs them ONCE and keeps the 64(+64)-channel feature planes on the device; the
+ * reference recomputes them for every 16 384-point chunk.  s3d_decoder_decode[_grid] is one fused launch: aabb
+ * normalisation -> bilinear gather-sum over the three planes (F.grid_sample border / align_corners=False,
+ * networks.py:182-190) -> DecoderMLPSkipConcat (blocks.py:65-91) on tcgen05 -> sigmoid on the texture head (+ the [0,1]
+ * clamp of decode_batch, model.py:332). */
+typedef struct s3d_decoder s3d_decoder;
+
+/* Constructor arguments of the reference auto-encoder that matter for decode (networks.py:134-136) + implementation knobs. */
+typedef struct {
+    int geo_feat_channels;         /* fdim_geo (parser_util.py:22), 4 */
+    int tex_feat_channels;         /* fdim_tex, 8 */
+    int feat_channel_up;           /* fdim_up, must be 64 */
+    int mlp_hidden_channels;       /* hidden_dim, 256 for the tensor-core kernel */
+    int mlp_hidden_layers;         /* n_hidden_layers, 4 for the tensor-core kernel */
+    int use_tex;                   /* data_type != "sdf" */
+    int tex_channels;              /* 3 */
+    int ks;                        /* kernel size of the TriplaneGroupResnetBlock convs (5, networks.py:152-153) */
+    int precision;                 /* 3: fp16 hi/lo split, 3 MMAs (fp32-grade, default); 1: single fp16 MMA */
+    int mlp_impl;                  /* 0: tcgen05 fused MLP; 1: CUDA-core fp32 kernel (cross-check / other MLP shapes) */
+} s3d_decoder_config;
+
+int s3d_decoder_create(const s3d_decoder_config* cfg, int device, s3d_decoder** out);
+int s3d_decoder_destroy(s3d_decoder* d);
+/* Expected checkpoint tensors in reference state_dict() order (aabb and the encoder Conv3d weights are accepted and unused). */
+int s3d_decoder_num_tensors(const s3d_decoder* d);
+int s3d_decoder_tensor_info(const s3d_decoder* d, int index, const char** name, int* ndim, int64_t shape[5]);
+int s3d_decoder_load_tensor(s3d_decoder* d, const char* name, const float* host_data, const int64_t* shape, int ndim);
+/* Re-pack for the kernels (per-plane conv taps, transposed fp32 MLP weights, power-of-two-scaled fp16 hi/lo MLP weights +
+ * TMA descriptors).  Fails if a decode-side tensor is missing.  Synchronises the device. */
+int s3d_decoder_finalize(s3d_decoder* d);
+/* feat_maps of decode(): xy [1,c,H,W], xz [1,c,H,D], yz [1,c,W,D] fp32 NCHW, c = geo (+ tex) channels. */
+int s3d_decoder_set_planes(s3d_decoder* d, const float* xy_dev, const float* xz_dev, const float* yz_dev, int H, int W, int D,
+                           void* stream);
+/* decode(x, feat_maps, aabb): pts_dev [n,3] -> out_dev [n, 1 (+ tex_channels)].  aabb is HOST memory (6 floats). */
+int s3d_decoder_decode(s3d_decoder* d, const float* pts_dev, int64_t n, const float aabb[6], int clamp_tex, float* out_dev,
+                       void* stream);
+/* decode_grid: the points are the meshgrid (indexing 'ij') of the three coordinate vectors of sample_grid_points_aabb
+ * (utils3d.py:13-25), formed inside the kernel; out_dev [nx, ny, nz, 1 (+ tex_channels)]. */
+int s3d_decoder_decode_grid(s3d_decoder* d, const float* xs_dev, const float* ys_dev, const float* zs_dev, int nx, int ny, int nz,
+                            const float aabb[6], int clamp_tex, float* out_dev, void* stream);
+/* Kernel launches issued by the last set_planes / decode call (bench accounting). */
+int s3d_decoder_last_launches(const s3d_decoder* d);
+/* Bring-up hook: the up-convolved feature plane `plane` as [rows][cols][64 (+64)] fp32 (geo channels first). Synchronises. */
+int s3d_decoder_planes_read(s3d_decoder* d, int plane, float* host_out, int64_t n_floats);
+
 /* ---- test / bring-up hooks (not part of the drop-in surface) ----
  * After a forward, intermediate fp32 activations of the last plan can be read back by name
  * ("in_conv", "<block>.h1", "<block>.out", "down.<l>", "upcat.<j>"); plane 0/1/2 = xy/xz/yz, layout

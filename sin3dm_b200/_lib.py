@@ -38,6 +38,12 @@ class LoopArgs(C.Structure):
                 ("mask_dev", C.c_void_p), ("seed", C.c_uint64), ("sample_base", C.c_uint32), ("use_graph", C.c_int)]
 
 
+class DecoderConfig(C.Structure):
+    _fields_ = [("geo_feat_channels", C.c_int), ("tex_feat_channels", C.c_int), ("feat_channel_up", C.c_int),
+                ("mlp_hidden_channels", C.c_int), ("mlp_hidden_layers", C.c_int), ("use_tex", C.c_int),
+                ("tex_channels", C.c_int), ("ks", C.c_int), ("precision", C.c_int), ("mlp_impl", C.c_int)]
+
+
 # every symbol include/sin3dm_b200.h declares: (restype, argtypes)
 _SIGNATURES = {
     "s3d_abi_version": (C.c_int, []),
@@ -70,6 +76,21 @@ _SIGNATURES = {
     "s3d_philox_normal": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32,
                                     C.c_void_p]),
     "s3d_sample_loop": (C.c_int, [C.c_void_p, C.POINTER(LoopArgs), C.c_void_p]),
+    "s3d_decoder_create": (C.c_int, [C.POINTER(DecoderConfig), C.c_int, C.POINTER(C.c_void_p)]),
+    "s3d_decoder_destroy": (C.c_int, [C.c_void_p]),
+    "s3d_decoder_num_tensors": (C.c_int, [C.c_void_p]),
+    "s3d_decoder_tensor_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int64)]),
+    "s3d_decoder_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "s3d_decoder_finalize": (C.c_int, [C.c_void_p]),
+    "s3d_decoder_set_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p]),
+    "s3d_decoder_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_int, C.c_void_p,
+                                     C.c_void_p]),
+    "s3d_decoder_decode_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_float), C.c_int, C.c_void_p, C.c_void_p]),
+    "s3d_decoder_last_launches": (C.c_int, [C.c_void_p]),
+    "s3d_decoder_planes_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "s3d_unet_debug_count": (C.c_int, [C.c_void_p]),
     "s3d_unet_debug_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

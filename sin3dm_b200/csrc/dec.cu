@@ -1,0 +1,539 @@
+// Host side of the triplane decoder: handle, checkpoint ingestion / weight packing, C ABI.
+// See include/sin3dm_b200.h (s3d_decoder_*) for the contract and the reference file:line each entry point replaces.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sin3dm_b200.h"
+#include "dec_kernels.cuh"
+#include "host_util.cuh"
+
+using namespace s3d;
+
+namespace {
+
+const char* kPlaneName[3] = {"xy", "xz", "yz"};
+
+struct DTensor {
+    std::string name;
+    std::vector<int64_t> shape;
+    std::vector<float> host;
+    bool loaded = false, needed = true;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+struct Branch {
+    int c0 = 0, cin = 0, n_out = 0;
+    float *w_in = nullptr, *b_in = nullptr, *w_out = nullptr, *b_out = nullptr, *ws = nullptr, *bs = nullptr;
+    float *gamma = nullptr, *beta = nullptr;
+    DecMlpF32 mf{};                         // CUDA-core kernel: transposed fp32 weights
+    uint16_t* w16[kDecLayers] = {};         // tensor-core kernel: [2][256][K] fp16 (hi, lo) of scale * W
+    float inv_scale[kDecLayers] = {};
+    float *w_last = nullptr, *b_last = nullptr;
+    CUtensorMap maps[kDecLayers];
+};
+
+}  // namespace
+
+struct s3d_decoder {
+    s3d_decoder_config cfg{};
+    int device = 0;
+    std::vector<DTensor> tensors;
+    std::map<std::string, int> index;
+    bool finalized = false, tc_ok = false;
+    std::vector<void*> owned;
+    Branch br[2];
+    int nb = 1, n_sm = 148;
+    // feature planes of the current latent
+    std::vector<void*> plane_owned;
+    float* F[3] = {nullptr, nullptr, nullptr};
+    float* h1[3] = {nullptr, nullptr, nullptr};
+    double* partial = nullptr;
+    float* coef = nullptr;
+    int rows[3] = {0, 0, 0}, cols[3] = {0, 0, 0}, max_strips = 0;
+    bool planes_set = false;
+    int last_launches = 0;
+};
+
+namespace {
+
+void add_tensor(s3d_decoder* d, const std::string& name, std::vector<int64_t> shape, bool needed = true) {
+    DTensor t;
+    t.name = name;
+    t.shape = std::move(shape);
+    t.needed = needed;
+    d->index[name] = static_cast<int>(d->tensors.size());
+    d->tensors.push_back(std::move(t));
+}
+
+// first_layers / second_layers of DecoderMLPSkipConcat in evaluation order (blocks.py:65-83)
+struct LinName {
+    std::string key;
+    int cin, cout;
+};
+std::vector<LinName> mlp_layers(const s3d_decoder_config& c, const std::string& prefix, int n_out, int* n_first) {
+    std::vector<LinName> v;
+    const int nh = c.mlp_hidden_layers, up = c.feat_channel_up, hid = c.mlp_hidden_channels;
+    const int nf = 1 + nh / 2, ns = 1 + std::max(nh / 2 - 1, 0) + 1;
+    for (int j = 0; j < nf; ++j) v.push_back({prefix + "first_layers." + std::to_string(2 * j), j == 0 ? up : hid, hid});
+    for (int j = 0; j < ns; ++j)
+        v.push_back({prefix + "second_layers." + std::to_string(2 * j), j == 0 ? up + hid : hid, j == ns - 1 ? n_out : hid});
+    *n_first = nf;
+    return v;
+}
+
+// state_dict() order of the reference module (networks.py:134-162)
+void build_structure(s3d_decoder* d) {
+    const auto& c = d->cfg;
+    add_tensor(d, "aabb", {6}, false);
+    add_tensor(d, "geo_encoder.weight", {c.geo_feat_channels, 1, 4, 4, 4}, false);
+    add_tensor(d, "geo_encoder.bias", {c.geo_feat_channels}, false);
+    if (c.use_tex) {
+        add_tensor(d, "tex_encoder.weight", {c.tex_feat_channels, c.tex_channels + 1, 4, 4, 4}, false);
+        add_tensor(d, "tex_encoder.bias", {c.tex_feat_channels}, false);
+    }
+    const int up = c.feat_channel_up;
+    for (int b = 0; b < d->nb; ++b) {
+        const std::string n = b == 0 ? "geo" : "tex";
+        const int cin = b == 0 ? c.geo_feat_channels : c.tex_feat_channels, n_out = b == 0 ? 1 : c.tex_channels;
+        const std::string p = n + "_convs.";
+        add_tensor(d, p + "in_layers.0.weight", {3 * up, cin, c.ks, c.ks});
+        add_tensor(d, p + "in_layers.0.bias", {3 * up});
+        for (int pl = 0; pl < 3; ++pl) {
+            add_tensor(d, p + "norm_" + kPlaneName[pl] + ".weight", {up});
+            add_tensor(d, p + "norm_" + kPlaneName[pl] + ".bias", {up});
+        }
+        add_tensor(d, p + "out_layers.1.weight", {3 * up, up, c.ks, c.ks});
+        add_tensor(d, p + "out_layers.1.bias", {3 * up});
+        add_tensor(d, p + "shortcut.weight", {3 * up, cin, 1, 1});
+        add_tensor(d, p + "shortcut.bias", {3 * up});
+        int nf;
+        for (const auto& l : mlp_layers(c, n + "_decoder.", n_out, &nf)) {
+            add_tensor(d, l.key + ".weight", {l.cout, l.cin});
+            add_tensor(d, l.key + ".bias", {l.cout});
+        }
+    }
+}
+
+const DTensor& T_(const s3d_decoder* d, const std::string& n) {
+    auto it = d->index.find(n);
+    if (it == d->index.end()) throw S3dError{"internal: unknown tensor " + n};
+    const DTensor& t = d->tensors[it->second];
+    if (!t.loaded) throw S3dError{"checkpoint tensor not loaded: " + n};
+    return t;
+}
+
+template <typename T>
+T* dev_alloc(std::vector<void*>& owner, size_t n) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    owner.push_back(p);
+    return static_cast<T*>(p);
+}
+template <typename T>
+T* dev_upload(std::vector<void*>& owner, const std::vector<T>& h) {
+    T* p = dev_alloc<T>(owner, h.size());
+    CUDA_TRY(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+uint16_t f2h_bits(float f) {
+    __half h = __float2half_rn(f);
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+float h2f(uint16_t b) {
+    __half h;
+    memcpy(&h, &b, 2);
+    return __half2float(h);
+}
+
+// grouped conv weight (3*up, cin, ks, ks) -> [plane][tap][ci][co]
+std::vector<float> pack_gconv(const std::vector<float>& w, int up, int cin, int ks) {
+    std::vector<float> o(static_cast<size_t>(3) * ks * ks * cin * up);
+    for (int p = 0; p < 3; ++p)
+        for (int co = 0; co < up; ++co)
+            for (int ci = 0; ci < cin; ++ci)
+                for (int t = 0; t < ks * ks; ++t)
+                    o[((static_cast<size_t>(p) * ks * ks + t) * cin + ci) * up + co] =
+                        w[((static_cast<size_t>(p) * up + co) * cin + ci) * ks * ks + t];
+    return o;
+}
+
+void finalize(s3d_decoder* d) {
+    const auto& c = d->cfg;
+    const int up = c.feat_channel_up, hid = c.mlp_hidden_channels;
+    for (const auto& t : d->tensors)
+        if (t.needed && !t.loaded) throw S3dError{"checkpoint tensor not loaded: " + t.name};
+    for (void* p : d->owned) cudaFree(p);
+    d->owned.clear();
+    d->tc_ok = up == kDecUp && hid == kDecHid && c.mlp_hidden_layers == 4 && c.tex_channels <= 4;
+    for (int b = 0; b < d->nb; ++b) {
+        Branch& B = d->br[b];
+        const std::string n = b == 0 ? "geo" : "tex";
+        B.cin = b == 0 ? c.geo_feat_channels : c.tex_feat_channels;
+        B.c0 = b == 0 ? 0 : c.geo_feat_channels;
+        B.n_out = b == 0 ? 1 : c.tex_channels;
+        const std::string p = n + "_convs.";
+        B.w_in = dev_upload(d->owned, pack_gconv(T_(d, p + "in_layers.0.weight").host, up, B.cin, c.ks));
+        B.b_in = dev_upload(d->owned, T_(d, p + "in_layers.0.bias").host);
+        B.w_out = dev_upload(d->owned, pack_gconv(T_(d, p + "out_layers.1.weight").host, up, up, c.ks));
+        B.b_out = dev_upload(d->owned, T_(d, p + "out_layers.1.bias").host);
+        B.ws = dev_upload(d->owned, pack_gconv(T_(d, p + "shortcut.weight").host, up, B.cin, 1));
+        B.bs = dev_upload(d->owned, T_(d, p + "shortcut.bias").host);
+        std::vector<float> g(3 * up), be(3 * up);
+        for (int pl = 0; pl < 3; ++pl) {
+            const auto& gw = T_(d, p + "norm_" + kPlaneName[pl] + ".weight").host;
+            const auto& gb = T_(d, p + "norm_" + kPlaneName[pl] + ".bias").host;
+            std::copy(gw.begin(), gw.end(), g.begin() + pl * up);
+            std::copy(gb.begin(), gb.end(), be.begin() + pl * up);
+        }
+        B.gamma = dev_upload(d->owned, g);
+        B.beta = dev_upload(d->owned, be);
+
+        int nf;
+        const auto layers = mlp_layers(c, n + "_decoder.", B.n_out, &nf);
+        S3D_CHECK(layers.size() <= 8, "too many MLP layers");
+        B.mf = DecMlpF32{};
+        B.mf.n_first = nf;
+        B.mf.n_layers = static_cast<int>(layers.size());
+        for (size_t l = 0; l < layers.size(); ++l) {
+            const auto& w = T_(d, layers[l].key + ".weight").host;       // [cout][cin]
+            const int K = layers[l].cin, N = layers[l].cout;
+            std::vector<float> wt(static_cast<size_t>(K) * N);
+            for (int nn = 0; nn < N; ++nn)
+                for (int k = 0; k < K; ++k) wt[static_cast<size_t>(k) * N + nn] = w[static_cast<size_t>(nn) * K + k];
+            B.mf.wt[l] = dev_upload(d->owned, wt);
+            B.mf.b[l] = dev_upload(d->owned, T_(d, layers[l].key + ".bias").host);
+            B.mf.K[l] = K;
+            B.mf.N[l] = N;
+        }
+        if (d->tc_ok) {
+            for (int l = 0; l < kDecLayers; ++l) {
+                const auto& w = T_(d, layers[l].key + ".weight").host;
+                const int K = layers[l].cin;
+                float mx = 0.f;
+                for (float v : w) mx = std::max(mx, std::fabs(v));
+                // power-of-two scale: the largest weight lands in [2048, 4096), so the (unscaled) lo halves of all but
+                // vanishing weights stay in fp16 normal range
+                const int e = mx > 0.f ? static_cast<int>(std::floor(std::log2(4096.0 / mx))) : 0;
+                const float s = std::ldexp(1.f, std::min(std::max(e, -20), 30));
+                std::vector<uint16_t> w16(static_cast<size_t>(2) * kDecHid * K);
+                for (int nn = 0; nn < kDecHid; ++nn)
+                    for (int k = 0; k < K; ++k) {
+                        const float v = std::min(std::max(w[static_cast<size_t>(nn) * K + k] * s, -65504.f), 65504.f);
+                        const uint16_t hi = f2h_bits(v);
+                        w16[static_cast<size_t>(nn) * K + k] = hi;
+                        w16[(static_cast<size_t>(kDecHid) + nn) * K + k] = f2h_bits(v - h2f(hi));
+                    }
+                B.w16[l] = dev_upload(d->owned, w16);
+                B.inv_scale[l] = 1.f / s;
+                const uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(kDecHid), 2};
+                const uint32_t box[3] = {64, 128, 1};
+                make_tmap(&B.maps[l], B.w16[l], 3, dims, box);
+            }
+            B.w_last = const_cast<float*>(dev_upload(d->owned, T_(d, layers[kDecLayers].key + ".weight").host));
+            B.b_last = const_cast<float*>(dev_upload(d->owned, T_(d, layers[kDecLayers].key + ".bias").host));
+        }
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    d->finalized = true;
+}
+
+void set_planes(s3d_decoder* d, const float* xy, const float* xz, const float* yz, int H, int W, int D, cudaStream_t st) {
+    S3D_CHECK(d->finalized, "s3d_decoder_finalize has not run");
+    S3D_CHECK(H > 0 && W > 0 && D > 0, "plane sizes must be positive");
+    const int rows[3] = {H, H, W}, cols[3] = {W, D, D};
+    const int CF = kDecUp * d->nb;
+    bool same = d->F[0] != nullptr;
+    for (int p = 0; p < 3; ++p) same = same && rows[p] == d->rows[p] && cols[p] == d->cols[p];
+    if (!same) {
+        for (void* p : d->plane_owned) cudaFree(p);
+        d->plane_owned.clear();
+        int mx = 0;
+        for (int p = 0; p < 3; ++p) {
+            d->rows[p] = rows[p];
+            d->cols[p] = cols[p];
+            const size_t n = static_cast<size_t>(rows[p]) * cols[p];
+            d->F[p] = dev_alloc<float>(d->plane_owned, n * CF);
+            d->h1[p] = dev_alloc<float>(d->plane_owned, n * kDecUp);
+            mx = std::max(mx, static_cast<int>((n + kDecStripPix - 1) / kDecStripPix));
+        }
+        d->max_strips = mx;
+        d->partial = dev_alloc<double>(d->plane_owned, static_cast<size_t>(3) * mx * 64 * 2);
+        d->coef = dev_alloc<float>(d->plane_owned, 3 * 64 * 2);
+    }
+    const float* x[3] = {xy, xz, yz};
+    const int ks = d->cfg.ks, hw = kDecTile + ks - 1, hstride = (hw * hw) | 1;
+    d->last_launches = 0;
+    for (int b = 0; b < d->nb; ++b) {
+        const Branch& B = d->br[b];
+        DecConvArgs a{};
+        int ts = 0;
+        for (int p = 0; p < 3; ++p) {
+            a.rows[p] = rows[p];
+            a.cols[p] = cols[p];
+            a.tiles_x[p] = (cols[p] + kDecTile - 1) / kDecTile;
+            a.tile_start[p] = ts;
+            ts += a.tiles_x[p] * ((rows[p] + kDecTile - 1) / kDecTile);
+            a.h1[p] = d->h1[p];
+            a.F[p] = d->F[p];
+        }
+        a.tile_start[3] = ts;
+        a.CF = CF;
+        a.foff = b * kDecUp;
+        a.ks = ks;
+        // conv ks x ks (c -> 64) + 1x1 shortcut
+        DecConvArgs a0 = a;
+        for (int p = 0; p < 3; ++p) a0.x[p] = x[p];
+        a0.c0 = B.c0;
+        a0.cin = B.cin;
+        a0.w = B.w_in;
+        a0.bias = B.b_in;
+        a0.ws = B.ws;
+        a0.bs = B.bs;
+        const size_t sm0 = static_cast<size_t>(B.cin) * (hstride + 64) * sizeof(float);
+        CUDA_TRY(cudaFuncSetAttribute(k_dec_conv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm0)));
+        launch(k_dec_conv<0>, dim3(ts), dim3(256), sm0, st, a0);
+        // InstanceNorm statistics of h1
+        const int n0 = rows[0] * cols[0], n1 = rows[1] * cols[1], n2 = rows[2] * cols[2];
+        launch(k_dec_in_stats, dim3(d->max_strips, 3), dim3(256), 0, st, d->h1[0], d->h1[1], d->h1[2], n0, n1, n2, d->partial,
+               d->max_strips);
+        launch(k_dec_in_finalize, dim3(3), dim3(64), 0, st, d->partial, d->max_strips, n0, n1, n2, B.gamma, B.beta, d->coef);
+        // norm + SiLU + conv ks x ks (64 -> 64), added onto the shortcut
+        DecConvArgs a1 = a;
+        for (int p = 0; p < 3; ++p) a1.x[p] = d->h1[p];
+        a1.cin = kDecUp;
+        a1.w = B.w_out;
+        a1.bias = B.b_out;
+        a1.coef = d->coef;
+        const size_t sm1 = static_cast<size_t>(kDecUp) * (hstride + 64) * sizeof(float);
+        CUDA_TRY(cudaFuncSetAttribute(k_dec_conv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm1)));
+        launch(k_dec_conv<1>, dim3(ts), dim3(256), sm1, st, a1);
+        d->last_launches += 4;
+    }
+    d->planes_set = true;
+}
+
+void decode(s3d_decoder* d, const DecPoints& P, int clamp_tex, float* out, cudaStream_t st) {
+    S3D_CHECK(d->planes_set, "s3d_decoder_set_planes has not run");
+    if (P.n <= 0) return;
+    DecArgs a{};
+    for (int p = 0; p < 3; ++p) {
+        a.G.F[p] = d->F[p];
+        a.G.rows[p] = d->rows[p];
+        a.G.cols[p] = d->cols[p];
+    }
+    a.G.CF = kDecUp * d->nb;
+    a.P = P;
+    a.nb = d->nb;
+    a.oc = 1 + (d->cfg.use_tex ? d->cfg.tex_channels : 0);
+    a.tex_channels = d->cfg.tex_channels;
+    a.clamp_tex = clamp_tex;
+    a.out = out;
+    if (d->cfg.mlp_impl == 1) {
+        const int hid = d->cfg.mlp_hidden_channels;
+        const size_t sm = (static_cast<size_t>(32) * kDecUp + static_cast<size_t>(64) * hid) * sizeof(float);
+        CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_ffma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
+        const long long blocks = (P.n + 31) / 32;
+        S3D_CHECK(blocks < (1LL << 31), "too many points for one launch");
+        launch(k_dec_mlp_ffma, dim3(static_cast<unsigned>(blocks)), dim3(256), sm, st, a, d->br[0].mf, d->br[d->nb - 1].mf, hid);
+        d->last_launches = 1;
+        return;
+    }
+    S3D_CHECK(d->tc_ok, "the tensor-core decoder is specialised for feat_channel_up=64, hidden_dim=256, n_hidden_layers=4 "
+                        "(the reference defaults); use mlp_impl=1 for other shapes");
+    DecTcMaps maps{};
+    DecTcArgs ta{};
+    ta.D = a;
+    for (int b = 0; b < d->nb; ++b) {
+        const Branch& B = d->br[b];
+        for (int l = 0; l < kDecLayers; ++l) {
+            maps.w[b][l] = B.maps[l];
+            ta.bias[b][l] = B.mf.b[l];
+            ta.inv_scale[b][l] = B.inv_scale[l];
+        }
+        ta.w_last[b] = B.w_last;
+        ta.b_last[b] = B.b_last;
+        ta.n_out[b] = B.n_out;
+    }
+    ta.n_tiles = (P.n + kDecPts - 1) / kDecPts;
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(ta.n_tiles, d->n_sm));
+    if (d->cfg.precision == 1) {
+        using Cfg = DecTcCfg<1>;
+        CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        launch(k_dec_mlp_tc<1>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta);
+    } else {
+        using Cfg = DecTcCfg<3>;
+        CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        launch(k_dec_mlp_tc<3>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta);
+    }
+    d->last_launches = 1;
+}
+
+void fill_aabb(DecPoints& P, const float* aabb) {
+    for (int i = 0; i < 3; ++i) {
+        P.amin[i] = aabb[i];
+        P.asize[i] = aabb[3 + i] - aabb[i];      // fp32 subtraction, as aabb[3:] - aabb[:3] (networks.py:196)
+    }
+}
+
+}  // namespace
+
+#define DEC_API_BEGIN try {
+#define DEC_API_END                   \
+    }                                 \
+    catch (const S3dError& e) {       \
+        return fail(e.msg);           \
+    }                                 \
+    catch (const std::exception& e) { \
+        return fail(e.what());        \
+    }                                 \
+    return 0;
+
+extern "C" {
+
+int s3d_decoder_create(const s3d_decoder_config* cfg, int device, s3d_decoder** out) {
+    DEC_API_BEGIN
+    S3D_CHECK(cfg && out, "null argument");
+    S3D_CHECK(cfg->feat_channel_up == kDecUp, "feat_channel_up must be 64 (the reference default)");
+    S3D_CHECK(cfg->geo_feat_channels >= 1 && cfg->geo_feat_channels <= 32, "geo_feat_channels out of range");
+    S3D_CHECK(!cfg->use_tex || (cfg->tex_feat_channels >= 1 && cfg->tex_feat_channels <= 32), "tex_feat_channels out of range");
+    S3D_CHECK(cfg->ks >= 1 && cfg->ks <= kDecMaxKs && (cfg->ks & 1), "ks must be odd and <= 7");
+    S3D_CHECK(cfg->mlp_hidden_channels >= 32 && cfg->mlp_hidden_channels <= 256 && cfg->mlp_hidden_channels % 32 == 0,
+              "mlp_hidden_channels must be a multiple of 32 in [32, 256]");
+    S3D_CHECK(cfg->mlp_hidden_layers >= 2 && cfg->mlp_hidden_layers % 2 == 0 && cfg->mlp_hidden_layers <= 8,
+              "mlp_hidden_layers must be even, 2..8");
+    S3D_CHECK(cfg->tex_channels >= 1 && cfg->tex_channels <= 8, "tex_channels out of range");
+    S3D_CHECK(cfg->precision == 1 || cfg->precision == 3, "precision must be 1 or 3");
+    S3D_CHECK(cfg->mlp_impl == 0 || cfg->mlp_impl == 1, "mlp_impl must be 0 or 1");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    S3D_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    S3D_CHECK(prop.major == 10, "libsin3dm_b200 is built for sm_100a only (no fallback)");
+    CUDA_TRY(cudaSetDevice(device));
+    auto* d = new s3d_decoder();
+    d->cfg = *cfg;
+    d->device = device;
+    d->nb = cfg->use_tex ? 2 : 1;
+    d->n_sm = prop.multiProcessorCount;
+    build_structure(d);
+    *out = d;
+    DEC_API_END
+}
+
+int s3d_decoder_destroy(s3d_decoder* d) {
+    if (!d) return 0;
+    cudaSetDevice(d->device);
+    for (void* p : d->owned) cudaFree(p);
+    for (void* p : d->plane_owned) cudaFree(p);
+    delete d;
+    return 0;
+}
+
+int s3d_decoder_num_tensors(const s3d_decoder* d) { return d ? static_cast<int>(d->tensors.size()) : 0; }
+
+int s3d_decoder_tensor_info(const s3d_decoder* d, int index, const char** name, int* ndim, int64_t shape[5]) {
+    DEC_API_BEGIN
+    S3D_CHECK(d && index >= 0 && index < static_cast<int>(d->tensors.size()), "tensor index out of range");
+    const DTensor& t = d->tensors[index];
+    if (name) *name = t.name.c_str();
+    if (ndim) *ndim = static_cast<int>(t.shape.size());
+    if (shape)
+        for (size_t i = 0; i < t.shape.size(); ++i) shape[i] = t.shape[i];
+    DEC_API_END
+}
+
+int s3d_decoder_load_tensor(s3d_decoder* d, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+    DEC_API_BEGIN
+    S3D_CHECK(d && name && host_data && shape, "null argument");
+    auto it = d->index.find(name);
+    if (it == d->index.end()) throw S3dError{std::string("unexpected checkpoint tensor: ") + name};
+    DTensor& t = d->tensors[it->second];
+    bool ok = ndim == static_cast<int>(t.shape.size());
+    for (int i = 0; ok && i < ndim; ++i) ok = shape[i] == t.shape[i];
+    if (!ok) throw S3dError{std::string("shape mismatch for ") + name};
+    t.host.assign(host_data, host_data + t.numel());
+    t.loaded = true;
+    d->finalized = false;
+    DEC_API_END
+}
+
+int s3d_decoder_finalize(s3d_decoder* d) {
+    DEC_API_BEGIN
+    S3D_CHECK(d, "null handle");
+    CUDA_TRY(cudaSetDevice(d->device));
+    finalize(d);
+    DEC_API_END
+}
+
+int s3d_decoder_set_planes(s3d_decoder* d, const float* xy_dev, const float* xz_dev, const float* yz_dev, int H, int W, int D,
+                           void* stream) {
+    DEC_API_BEGIN
+    S3D_CHECK(d && xy_dev && xz_dev && yz_dev, "null argument");
+    CUDA_TRY(cudaSetDevice(d->device));
+    set_planes(d, xy_dev, xz_dev, yz_dev, H, W, D, static_cast<cudaStream_t>(stream));
+    DEC_API_END
+}
+
+int s3d_decoder_decode(s3d_decoder* d, const float* pts_dev, int64_t n, const float aabb[6], int clamp_tex, float* out_dev,
+                       void* stream) {
+    DEC_API_BEGIN
+    S3D_CHECK(d && aabb && (n == 0 || (pts_dev && out_dev)), "null argument");
+    CUDA_TRY(cudaSetDevice(d->device));
+    DecPoints P{};
+    P.pts = pts_dev;
+    P.n = n;
+    P.ny = P.nz = 1;
+    fill_aabb(P, aabb);
+    decode(d, P, clamp_tex, out_dev, static_cast<cudaStream_t>(stream));
+    DEC_API_END
+}
+
+int s3d_decoder_decode_grid(s3d_decoder* d, const float* xs_dev, const float* ys_dev, const float* zs_dev, int nx, int ny, int nz,
+                            const float aabb[6], int clamp_tex, float* out_dev, void* stream) {
+    DEC_API_BEGIN
+    S3D_CHECK(d && aabb && xs_dev && ys_dev && zs_dev && out_dev, "null argument");
+    S3D_CHECK(nx > 0 && ny > 0 && nz > 0, "grid sizes must be positive");
+    CUDA_TRY(cudaSetDevice(d->device));
+    DecPoints P{};
+    P.pts = nullptr;
+    P.xs = xs_dev;
+    P.ys = ys_dev;
+    P.zs = zs_dev;
+    P.ny = ny;
+    P.nz = nz;
+    P.n = static_cast<long long>(nx) * ny * nz;
+    fill_aabb(P, aabb);
+    decode(d, P, clamp_tex, out_dev, static_cast<cudaStream_t>(stream));
+    DEC_API_END
+}
+
+int s3d_decoder_last_launches(const s3d_decoder* d) { return d ? d->last_launches : 0; }
+
+int s3d_decoder_planes_read(s3d_decoder* d, int plane, float* host_out, int64_t n_floats) {
+    DEC_API_BEGIN
+    S3D_CHECK(d && d->planes_set && plane >= 0 && plane < 3 && host_out, "bad argument");
+    CUDA_TRY(cudaSetDevice(d->device));
+    const int64_t n = static_cast<int64_t>(d->rows[plane]) * d->cols[plane] * kDecUp * d->nb;
+    S3D_CHECK(n_floats == n, "buffer size mismatch");
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(host_out, d->F[plane], n * sizeof(float), cudaMemcpyDeviceToHost));
+    DEC_API_END
+}
+
+}  // extern "C"

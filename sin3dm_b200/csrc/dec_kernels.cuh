@@ -1,0 +1,691 @@
+// Triplane decoder kernels: latent planes -> up-convolved feature planes (once per latent), then
+// points -> bilinear gather from the three planes -> skip-concat MLP -> SDF + texture.
+//
+//   reference: AutoEncoderGroupSkip.decode            src/encoding/networks.py:192-220
+//              sample_feature_plane2D                 src/encoding/networks.py:182-190 (F.grid_sample bilinear / border)
+//              TriplaneGroupResnetBlock.forward       src/encoding/blocks.py:232-256
+//              DecoderMLPSkipConcat.forward           src/encoding/blocks.py:84-91
+//              ShapeAutoEncoder.decode_batch / _grid  src/encoding/model.py:319-349
+//
+// The grouped convolutions of the reference run on a zero-padded channel-wise composition of the three planes
+// (blocks.py:164-177); a group never mixes planes and the padding is zero before and after the norm + SiLU, so each plane
+// is simply convolved on its own with zero padding — which is what these kernels do.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace s3d {
+
+constexpr int kDecUp = 64;          // feat_channel_up (parser_util.py:24); the kernels are specialised for it
+constexpr int kDecHid = 256;        // mlp hidden width of the tensor-core kernel (parser_util.py:25)
+constexpr float kInEps = 1e-6f;     // blocks.py:213-215  InstanceNorm2d(eps=1e-6)
+constexpr int kDecTile = 16;        // conv tile edge (pixels)
+constexpr int kDecMaxKs = 7;
+
+struct DecPlanes {
+    const float* F[3];   // [rows][cols][CF] fp32: channels [0,64) geo, [64,128) tex
+    int rows[3], cols[3];
+    int CF;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_dec_conv: ks x ks convolution of one plane, 64 output channels, CUDA cores (fp32).  Runs twice per branch and latent.
+//   MODE 0: input = `cin` channels of the NCHW latent plane (no activation); writes h1 = conv + bias (NHWC, 64 ch) and the
+//           1x1 shortcut (+ bias) into the feature plane F.
+//   MODE 1: input = h1 (NHWC, 64 ch) with the InstanceNorm affine + SiLU applied on load; F += conv + bias.
+// grid (tiles of the three planes), block 256 = one 16 x 16 pixel tile, thread = pixel, 64 accumulators.
+// ------------------------------------------------------------------------------------------------------------------
+struct DecConvArgs {
+    const float* x[3];       // MODE 0: latent plane [c_total][rows][cols]; MODE 1: h1 [rows][cols][64]
+    int c0, cin;             // MODE 0: first channel / channel count of this branch inside the latent
+    const float* w;          // [3 planes][ks*ks][cin][64]
+    const float* bias;       // [3][64]
+    const float* ws;         // MODE 0: shortcut [3][cin][64]   (nullptr: identity shortcut, cin == 64)
+    const float* bs;         // MODE 0: shortcut bias [3][64]
+    const float* coef;       // MODE 1: [3][64][2] = (gamma * rstd, beta - mean * gamma * rstd)
+    float* h1[3];            // MODE 0 output
+    float* F[3];             // feature plane [rows][cols][CF]
+    int CF, foff;            // channel stride / channel offset of this branch in F
+    int rows[3], cols[3];
+    int tiles_x[3], tile_start[4];
+    int ks;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_dec_conv(const DecConvArgs A) {
+    extern __shared__ float dsm[];
+    int plane = 0;
+#pragma unroll
+    for (int p = 1; p < 3; ++p)
+        if (static_cast<int>(blockIdx.x) >= A.tile_start[p]) plane = p;
+    const int ip = blockIdx.x - A.tile_start[plane];
+    const int ty0 = (ip / A.tiles_x[plane]) * kDecTile, tx0 = (ip % A.tiles_x[plane]) * kDecTile;
+    const int rows = A.rows[plane], cols = A.cols[plane];
+    const int ks = A.ks, pad = (ks - 1) / 2, hw = kDecTile + ks - 1, hpix = hw * hw, hstride = hpix | 1;
+    const int cin = MODE == 0 ? A.cin : kDecUp;
+    float* sIn = dsm;                          // [cin][hstride]
+    float* sW = dsm + cin * hstride;           // [cin][64] of the current tap
+    const int tid = threadIdx.x;
+
+    // ---- input halo tile
+    if (MODE == 0) {
+        const float* xp = A.x[plane] + static_cast<size_t>(A.c0) * rows * cols;
+        for (int i = tid; i < cin * hpix; i += 256) {
+            const int ci = i / hpix, q = i - ci * hpix;
+            const int r = ty0 - pad + q / hw, c = tx0 - pad + q % hw;
+            sIn[ci * hstride + q] = (r >= 0 && r < rows && c >= 0 && c < cols) ? __ldg(xp + (static_cast<size_t>(ci) * rows + r) * cols + c) : 0.f;
+        }
+    } else {
+        const int ch = tid & 63;
+        const float ca = A.coef[(plane * 64 + ch) * 2], cb = A.coef[(plane * 64 + ch) * 2 + 1];
+        const float* hp = A.x[plane];
+        for (int q = tid >> 6; q < hpix; q += 4) {
+            const int r = ty0 - pad + q / hw, c = tx0 - pad + q % hw;
+            float v = 0.f;                     // zero padding applies to the activated tensor (blocks.py:248-251)
+            if (r >= 0 && r < rows && c >= 0 && c < cols) {
+                const float h = __ldg(hp + (static_cast<size_t>(r) * cols + c) * 64 + ch);
+                const float n = fmaf(h, ca, cb);
+                v = n / (1.f + expf(-n));
+            }
+            sIn[ch * hstride + q] = v;
+        }
+    }
+    const int py = tid >> 4, px = tid & 15;
+    const int r = ty0 + py, c = tx0 + px;
+    const bool valid = r < rows && c < cols;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+
+    const float* wp = A.w + static_cast<size_t>(plane) * ks * ks * cin * 64;
+    for (int tap = 0; tap < ks * ks; ++tap) {
+        __syncthreads();                       // previous tap's weights consumed (first pass: halo tile complete)
+        for (int i = tid; i < cin * 16; i += 256)
+            reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(tap) * cin * 64) + i);
+        __syncthreads();
+        const int kh = tap / ks, kw = tap - kh * ks;
+        const float* ip0 = sIn + (py + kh) * hw + px + kw;
+        for (int ci = 0; ci < cin; ++ci) {
+            const float a = ip0[ci * hstride];
+            const float4* w4 = reinterpret_cast<const float4*>(sW + ci * 64);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 w = w4[j];
+                acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]);
+                acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]);
+                acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
+            }
+        }
+    }
+    const float4* b4 = reinterpret_cast<const float4*>(A.bias + plane * 64);
+    if (MODE == 0) {
+        if (valid) {
+            float4* o = reinterpret_cast<float4*>(A.h1[plane] + (static_cast<size_t>(r) * cols + c) * 64);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 b = __ldg(b4 + j);
+                o[j] = make_float4(acc[4 * j] + b.x, acc[4 * j + 1] + b.y, acc[4 * j + 2] + b.z, acc[4 * j + 3] + b.w);
+            }
+        }
+        // 1x1 shortcut on the raw input (blocks.py:227-230, 254)
+        __syncthreads();
+        for (int i = tid; i < cin * 16; i += 256)
+            reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(A.ws + static_cast<size_t>(plane) * cin * 64) + i);
+        __syncthreads();
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+            const float* ip0 = sIn + (py + pad) * hw + px + pad;
+            for (int ci = 0; ci < cin; ++ci) {
+                const float a = ip0[ci * hstride];
+                const float4* w4 = reinterpret_cast<const float4*>(sW + ci * 64);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 w = w4[j];
+                    acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]);
+                    acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
+                    acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]);
+                    acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
+                }
+            }
+            const float4* s4 = reinterpret_cast<const float4*>(A.bs + plane * 64);
+            float4* o = reinterpret_cast<float4*>(A.F[plane] + (static_cast<size_t>(r) * cols + c) * A.CF + A.foff);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 b = __ldg(s4 + j);
+                o[j] = make_float4(acc[4 * j] + b.x, acc[4 * j + 1] + b.y, acc[4 * j + 2] + b.z, acc[4 * j + 3] + b.w);
+            }
+        }
+    } else if (valid) {
+        float4* o = reinterpret_cast<float4*>(A.F[plane] + (static_cast<size_t>(r) * cols + c) * A.CF + A.foff);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(b4 + j);
+            float4 v = o[j];
+            // h + shortcut(x): the conv result (with its bias) is formed first, then added (blocks.py:253-254)
+            v.x = (acc[4 * j] + b.x) + v.x;
+            v.y = (acc[4 * j + 1] + b.y) + v.y;
+            v.z = (acc[4 * j + 2] + b.z) + v.z;
+            v.w = (acc[4 * j + 3] + b.w) + v.w;
+            o[j] = v;
+        }
+    }
+}
+
+// InstanceNorm statistics of h1 (per plane, per channel, biased variance): deterministic two-level reduction in fp64.
+// grid (strips, 3), block 256 = 64 channels x 4 pixel phases; partial[plane][strip][64][2]
+constexpr int kDecStripPix = 256;
+__global__ void __launch_bounds__(256) k_dec_in_stats(const float* h0, const float* h1, const float* h2, int n0, int n1, int n2,
+                                                      double* __restrict__ partial, int max_strips) {
+    const int plane = blockIdx.y;
+    const float* h = plane == 0 ? h0 : (plane == 1 ? h1 : h2);
+    const int n = plane == 0 ? n0 : (plane == 1 ? n1 : n2);
+    const int p0 = blockIdx.x * kDecStripPix;
+    if (p0 >= n) return;
+    const int ch = threadIdx.x & 63, ph = threadIdx.x >> 6;
+    double s = 0.0, q = 0.0;
+    for (int p = p0 + ph; p < min(p0 + kDecStripPix, n); p += 4) {
+        const double v = static_cast<double>(__ldg(h + static_cast<size_t>(p) * 64 + ch));
+        s += v;
+        q += v * v;
+    }
+    __shared__ double sm[2][4][64];
+    sm[0][ph][ch] = s;
+    sm[1][ph][ch] = q;
+    __syncthreads();
+    if (ph == 0) {
+        double* o = partial + ((static_cast<size_t>(plane) * max_strips + blockIdx.x) * 64 + ch) * 2;
+        o[0] = (sm[0][0][ch] + sm[0][1][ch]) + (sm[0][2][ch] + sm[0][3][ch]);
+        o[1] = (sm[1][0][ch] + sm[1][1][ch]) + (sm[1][2][ch] + sm[1][3][ch]);
+    }
+}
+// grid 3, block 64: coef[plane][ch] = (gamma * rstd, beta - mean * gamma * rstd)
+__global__ void k_dec_in_finalize(const double* __restrict__ partial, int max_strips, int n0, int n1, int n2,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ coef) {
+    const int plane = blockIdx.x, ch = threadIdx.x;
+    const int n = plane == 0 ? n0 : (plane == 1 ? n1 : n2);
+    const int strips = (n + kDecStripPix - 1) / kDecStripPix;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < strips; ++i) {
+        const double* p = partial + ((static_cast<size_t>(plane) * max_strips + i) * 64 + ch) * 2;
+        s += p[0];
+        q += p[1];
+    }
+    const double mean = s / n, var = fmax(q / n - mean * mean, 0.0);
+    const double a = static_cast<double>(gamma[plane * 64 + ch]) / sqrt(var + static_cast<double>(kInEps));
+    coef[(plane * 64 + ch) * 2] = static_cast<float>(a);
+    coef[(plane * 64 + ch) * 2 + 1] = static_cast<float>(static_cast<double>(beta[plane * 64 + ch]) - mean * a);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Point sampling shared by both MLP kernels.
+// ------------------------------------------------------------------------------------------------------------------
+struct DecPoints {
+    const float* pts;              // [n][3], or nullptr: grid mode
+    const float *xs, *ys, *zs;     // grid mode: coordinate vectors (utils3d.py:21-23), point g = (ix*ny + iy)*nz + iz
+    int ny, nz;
+    long long n;
+    float amin[3], asize[3];       // aabb min, (aabb max - aabb min)
+};
+__device__ __forceinline__ void dec_point(const DecPoints& P, long long g, float (&xn)[3]) {
+    float p[3];
+    if (P.pts) {
+        p[0] = __ldg(P.pts + g * 3);
+        p[1] = __ldg(P.pts + g * 3 + 1);
+        p[2] = __ldg(P.pts + g * 3 + 2);
+    } else {
+        const int iz = static_cast<int>(g % P.nz);
+        const long long t = g / P.nz;
+        p[0] = __ldg(P.xs + t / P.ny);
+        p[1] = __ldg(P.ys + t % P.ny);
+        p[2] = __ldg(P.zs + iz);
+    }
+    // networks.py:196  x = 2 * (x - aabb[:3]) / (aabb[3:] - aabb[:3]) - 1
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xn[i] = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(p[i], P.amin[i])), P.asize[i]), 1.f);
+}
+// F.grid_sample(bilinear, padding_mode="border", align_corners=False) source index + weights along one axis
+__device__ __forceinline__ void dec_axis(float coord, int size, int& i0, int& i1, float& w0, float& w1) {
+    float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(coord, 1.f), static_cast<float>(size)), 1.f), 0.5f);
+    ix = fminf(static_cast<float>(size - 1), fmaxf(ix, 0.f));
+    const float f = floorf(ix);
+    i0 = static_cast<int>(f);
+    i1 = min(i0 + 1, size - 1);          // weight of the clamped neighbour is exactly 0 when it would fall outside
+    w1 = ix - f;
+    w0 = (f + 1.f) - ix;
+}
+// plane p is sampled with rows <- coordinate kRowAxis[p], cols <- coordinate kColAxis[p] (networks.py:201 + .flip(-1))
+__device__ __constant__ int kDecRowAxis[3] = {0, 0, 1};
+__device__ __constant__ int kDecColAxis[3] = {1, 2, 2};
+
+struct DecCorners {
+    int off[12];       // pixel index (r * cols + c) of the 4 corners of the 3 planes
+    float w[12];
+};
+__device__ __forceinline__ void dec_corners(const DecPlanes& G, const float (&xn)[3], DecCorners& K) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        int r0, r1, c0, c1;
+        float wr0, wr1, wc0, wc1;
+        dec_axis(xn[p == 2 ? 1 : 0], G.rows[p], r0, r1, wr0, wr1);
+        dec_axis(xn[p == 0 ? 1 : 2], G.cols[p], c0, c1, wc0, wc1);
+        K.off[4 * p + 0] = r0 * G.cols[p] + c0;  K.w[4 * p + 0] = wc0 * wr0;     // nw
+        K.off[4 * p + 1] = r0 * G.cols[p] + c1;  K.w[4 * p + 1] = wc1 * wr0;     // ne
+        K.off[4 * p + 2] = r1 * G.cols[p] + c0;  K.w[4 * p + 2] = wc0 * wr1;     // sw
+        K.off[4 * p + 3] = r1 * G.cols[p] + c1;  K.w[4 * p + 3] = wc1 * wr1;     // se
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_dec_mlp_ffma: CUDA-core fp32 decoder (mlp_impl = 1): exact-precision cross-check of the tensor-core kernel and the
+// path for MLP shapes the tensor-core kernel is not specialised for.  block 256 = 32 points; thread = hidden unit.
+// ------------------------------------------------------------------------------------------------------------------
+struct DecMlpF32 {
+    const float* wt[8];    // layer l: transposed weights [K_l][N_l]
+    const float* b[8];
+    int K[8], N[8];
+    int n_first;           // layers before the skip concat (first_layers)
+    int n_layers;          // all linear layers
+};
+struct DecArgs {
+    DecPlanes G;
+    DecPoints P;
+    int nb;                // branches: 1 (geo) or 2 (geo, tex)
+    int oc;                // output channels per point (1 + tex_channels)
+    int tex_channels;
+    int clamp_tex;         // decode_batch's clamp of the colour channels (model.py:332)
+    float* out;            // [n][oc]
+};
+
+__global__ void __launch_bounds__(256) k_dec_mlp_ffma(const DecArgs A, const DecMlpF32 M0, const DecMlpF32 M1, int hid) {
+    extern __shared__ float dsm[];
+    float* sX = dsm;                    // [32][64]
+    float* sA = sX + 32 * kDecUp;       // [32][hid]
+    float* sB = sA + 32 * hid;          // [32][hid]
+    const int tid = threadIdx.x;
+    const long long g0 = static_cast<long long>(blockIdx.x) * 32;
+    for (int br = 0; br < A.nb; ++br) {
+        const DecMlpF32& M = br == 0 ? M0 : M1;
+        __syncthreads();
+        {   // gather: 8 lanes per point, lane j owns channels [8j, 8j+8)
+            const int pt = tid >> 3, j = tid & 7;
+            const long long g = min(g0 + pt, A.P.n - 1);
+            float xn[3];
+            dec_point(A.P, g, xn);
+            DecCorners K;
+            dec_corners(A.G, xn, K);
+            float h[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h[e] = 0.f;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                float s[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s[e] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4* f = reinterpret_cast<const float4*>(A.G.F[p] + static_cast<size_t>(K.off[4 * p + k]) * A.G.CF + br * kDecUp + j * 8);
+                    const float4 a = __ldg(f), b = __ldg(f + 1);
+                    const float w = K.w[4 * p + k];
+                    s[0] = fmaf(a.x, w, s[0]); s[1] = fmaf(a.y, w, s[1]); s[2] = fmaf(a.z, w, s[2]); s[3] = fmaf(a.w, w, s[3]);
+                    s[4] = fmaf(b.x, w, s[4]); s[5] = fmaf(b.y, w, s[5]); s[6] = fmaf(b.z, w, s[6]); s[7] = fmaf(b.w, w, s[7]);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h[e] += s[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sX[pt * kDecUp + j * 8 + e] = h[e];
+        }
+        __syncthreads();
+        const float* in = sX;
+        int in_stride = kDecUp;
+        float* bufs[2] = {sA, sB};
+        int cur = 0;
+        for (int l = 0; l < M.n_layers; ++l) {
+            const int K = M.K[l], N = M.N[l];
+            const bool last = l == M.n_layers - 1;
+            const bool concat = l == M.n_first;          // input = cat[x, h]  (blocks.py:88)
+            float* outb = bufs[cur];
+            if (tid < N) {
+                float acc[32];
+#pragma unroll
+                for (int p = 0; p < 32; ++p) acc[p] = 0.f;
+                const float* wt = M.wt[l];
+                int k = 0;
+                if (concat) {
+                    for (; k < kDecUp; ++k) {
+                        const float w = __ldg(wt + static_cast<size_t>(k) * N + tid);
+#pragma unroll
+                        for (int p = 0; p < 32; ++p) acc[p] = fmaf(sX[p * kDecUp + k], w, acc[p]);
+                    }
+                }
+                const int kofs = concat ? kDecUp : 0;
+                for (; k < K; ++k) {
+                    const float w = __ldg(wt + static_cast<size_t>(k) * N + tid);
+#pragma unroll
+                    for (int p = 0; p < 32; ++p) acc[p] = fmaf(in[p * in_stride + k - kofs], w, acc[p]);
+                }
+                const float bias = __ldg(M.b[l] + tid);
+                if (!last) {
+#pragma unroll
+                    for (int p = 0; p < 32; ++p) outb[p * hid + tid] = fmaxf(acc[p] + bias, 0.f);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < 32; ++p) {
+                        float v = acc[p] + bias;
+                        if (br == 1) {
+                            v = 1.f / (1.f + expf(-v));                       // networks.py:216  .sigmoid()
+                            if (A.clamp_tex) v = fminf(fmaxf(v, 0.f), 1.f);
+                        }
+                        if (g0 + p < A.P.n) A.out[(g0 + p) * A.oc + (br == 0 ? 0 : 1) + tid] = v;
+                    }
+                }
+            }
+            __syncthreads();
+            in = outb;
+            in_stride = hid;
+            cur ^= 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_dec_mlp_tc: the decoder on the sm_100a tensor cores.  Persistent, one CTA per SM, tile = 128 points.
+//
+//   per tile and branch:  gather (X: 128 x 64)  ->  L1: X*W1 -> ReLU -> L2 -> ReLU -> L3 -> ReLU
+//                         -> L4: [X | H3]*W4 -> ReLU -> L5 -> ReLU -> 256 -> out (CUDA cores, in L5's epilogue)
+//
+// Activations never leave the SM: every layer's epilogue (TMEM -> registers -> +bias, ReLU -> fp16 (hi, lo) -> shared
+// memory, written directly in the 128-byte-swizzled K-major layout tcgen05.mma reads) produces the next layer's A operand in
+// place.  Weights ([256 x K] per layer, fp16 (hi, lo), pre-scaled by a power of two so that lo stays in fp16 normal range
+// unscaled) stream through a TMA ring as [128 N x 64 K] tiles; they are the same for every tile and stay L2-resident.
+// NSPLIT == 3:  D += Ah*Bh + Al*Bh + Ah*Bl  (fp32 accumulate in TMEM; error ~2^-21 per operand, i.e. fp32-grade).
+// NSPLIT == 1:  D += Ah*Bh.
+// Warps: 0 = TMA producer (weights), 1 = TMEM owner + MMA issuer, 2..5 = gather + epilogues (thread = point = TMEM lane).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDecPts = 128;
+constexpr int kDecTcThreads = 192;
+constexpr int kDecChunkBytes = kDecPts * 128;       // one 64-wide K chunk of an A operand: 128 rows x 128 B
+constexpr int kDecBSlotBytes = 128 * 128;           // [128 N rows][64 K] fp16
+constexpr int kDecLayers = 5;                       // tensor-core layers per branch (the 256 -> out layer runs in L5's epilogue)
+
+template <int NSPLIT>
+struct DecTcCfg {
+    static constexpr int kParts = NSPLIT == 3 ? 2 : 1;
+    static constexpr int kXBytes = kParts * kDecChunkBytes;
+    static constexpr int kActBytes = kParts * 4 * kDecChunkBytes;
+    static constexpr int kBSlots = NSPLIT == 3 ? 4 : 8;
+    static constexpr int kRingBytes = kBSlots * kDecBSlotBytes;
+    static constexpr int kSmemBytes = kXBytes + kActBytes + kRingBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct DecTcMaps {
+    CUtensorMap w[2][kDecLayers];     // [branch][layer]: (K, 256, 2) fp16, box {64, 128, 1}
+};
+struct DecTcArgs {
+    DecArgs D;
+    const float* bias[2][kDecLayers];     // fp32 [256]
+    float inv_scale[2][kDecLayers];       // 1 / (power-of-two weight scale)
+    const float* w_last[2];               // fp32 [n_out][256]
+    const float* b_last[2];
+    int n_out[2];
+    long long n_tiles;
+};
+
+__device__ __forceinline__ void split_f16_plain(float v, __half& hi, __half& lo) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_constant__ DecTcMaps M, const DecTcArgs A) {
+    using Cfg = DecTcCfg<NSPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sx = smem;                                  // X hi | X lo
+    uint8_t* sact = smem + Cfg::kXBytes;                 // ACT hi (4 chunks) | ACT lo (4 chunks)
+    uint8_t* sb = sact + Cfg::kActBytes;                 // weight ring
+    uint64_t* fullB = reinterpret_cast<uint64_t*>(sb + Cfg::kRingBytes);
+    uint64_t* emptyB = fullB + Cfg::kBSlots;
+    uint64_t* opnd_ready = emptyB + Cfg::kBSlots;        // epilogue warps -> MMA warp: the next A operand is in shared memory
+    uint64_t* d_full = opnd_ready + 1;                   // MMA warp -> epilogue warps: the layer's accumulator is complete
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(d_full + 1);
+    constexpr uint32_t kXLo = kDecChunkBytes, kActLo = 4 * kDecChunkBytes;
+
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int nb = A.D.nb;
+
+    if (warp == 0 && lane == 0) {
+        for (int br = 0; br < nb; ++br)
+            for (int l = 0; l < kDecLayers; ++l) ptx::prefetch_tmap(&M.w[br][l]);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < Cfg::kBSlots; ++s) {
+                ptx::mbar_init(&fullB[s], 1);
+                ptx::mbar_init(&emptyB[s], 1);
+            }
+            ptx::mbar_init(opnd_ready, 1);
+            ptx::mbar_init(d_full, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc<512>(tmem_ptr_smem);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // K chunks of layer l: layer 0 reads X, layer 3 reads [X | ACT], the others ACT
+    auto n_chunks = [](int l) { return l == 0 ? 1 : (l == 3 ? 5 : 4); };
+
+    if (warp == 0) {
+        // ===================== TMA producer: weight tiles, in the order the MMA warp consumes them =====================
+        int gb = 0;
+        for (long long t = blockIdx.x; t < A.n_tiles; t += gridDim.x)
+            for (int br = 0; br < nb; ++br)
+                for (int l = 0; l < kDecLayers; ++l) {
+                    const int nk = n_chunks(l);
+                    for (int kc = 0; kc < nk; ++kc)
+                        for (int nh = 0; nh < 2; ++nh)
+                            for (int part = 0; part < Cfg::kParts; ++part, ++gb) {
+                                const int s = gb % Cfg::kBSlots;
+                                ptx::mbar_wait(&emptyB[s], ((gb / Cfg::kBSlots) & 1) ^ 1);
+                                if (ptx::elect_one()) {
+                                    ptx::mbar_arrive_expect_tx(&fullB[s], kDecBSlotBytes);
+                                    ptx::tma_load_3d(sb + s * kDecBSlotBytes, &M.w[br][l], &fullB[s], kc * 64, nh * 128, part);
+                                }
+                                __syncwarp();
+                            }
+                }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = ptx::make_idesc_f16(128, 128);
+        int gb = 0;
+        uint32_t it = 0;                // operand hand-overs so far (phase of opnd_ready)
+        for (long long t = blockIdx.x; t < A.n_tiles; t += gridDim.x)
+            for (int br = 0; br < nb; ++br)
+                for (int l = 0; l < kDecLayers; ++l, ++it) {
+                    ptx::mbar_wait(opnd_ready, it & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d = tmem_base + (l & 1) * 256;
+                    const int nk = n_chunks(l);
+                    for (int kc = 0; kc < nk; ++kc) {
+                        // A chunk: X for the first chunk of layers 0 and 3, else ACT chunk
+                        const bool from_x = (l == 0) || (l == 3 && kc == 0);
+                        const int ac = l == 3 ? kc - 1 : kc;
+                        const uint32_t a_hi = ptx::smem_u32(from_x ? sx : sact + ac * kDecChunkBytes);
+                        const uint32_t a_lo = ptx::smem_u32(from_x ? sx + kXLo : sact + kActLo + ac * kDecChunkBytes);
+                        for (int nh = 0; nh < 2; ++nh)
+                            for (int part = 0; part < Cfg::kParts; ++part, ++gb) {
+                                const int s = gb % Cfg::kBSlots;
+                                ptx::mbar_wait(&fullB[s], (gb / Cfg::kBSlots) & 1);
+                                ptx::tc_fence_after();
+                                const uint64_t da_hi = ptx::make_sw128_desc1024(a_hi), da_lo = ptx::make_sw128_desc1024(a_lo);
+                                const uint64_t db = ptx::make_sw128_desc1024(ptx::smem_u32(sb + s * kDecBSlotBytes));
+                                const uint32_t dn = d + nh * 128;
+                                if (ptx::elect_one()) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);
+                                        if (part == 0) {
+                                            ptx::umma_f16(dn, da_hi + ko, db + ko, idesc, (kc == 0 && k == 0) ? 0u : 1u);
+                                            if (NSPLIT == 3) ptx::umma_f16(dn, da_lo + ko, db + ko, idesc, 1u);
+                                        } else {
+                                            ptx::umma_f16(dn, da_hi + ko, db + ko, idesc, 1u);
+                                        }
+                                    }
+                                    ptx::umma_commit(&emptyB[s]);
+                                }
+                                __syncwarp();
+                            }
+                    }
+                    if (ptx::elect_one()) ptx::umma_commit(d_full);
+                    __syncwarp();
+                }
+    } else {
+        // ===================== gather + epilogues (warps 2..5) =====================
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;                 // point of the tile == TMEM lane == A operand row
+        const int et = threadIdx.x - 64;
+        uint32_t dphase = 0;                               // d_full completions consumed so far
+        const uint32_t sw = static_cast<uint32_t>(m & 7);
+        for (long long t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
+            const long long g0 = t * kDecPts;
+            for (int br = 0; br < nb; ++br) {
+                // ---- gather: 8 lanes per point (lane j owns channels [8j, 8j+8) of the branch), 4 points per warp pass
+                {
+                    const int j = lane & 7;
+#pragma unroll 1
+                    for (int pass = 0; pass < 8; ++pass) {
+                        const int pm = quarter * 32 + pass * 4 + (lane >> 3);
+                        const long long g = min(g0 + pm, A.D.P.n - 1);
+                        float xn[3];
+                        dec_point(A.D.P, g, xn);
+                        DecCorners K;
+                        dec_corners(A.D.G, xn, K);
+                        float4 fa[12], fb[12];
+#pragma unroll
+                        for (int c = 0; c < 12; ++c) {
+                            const float4* f = reinterpret_cast<const float4*>(A.D.G.F[c >> 2] + static_cast<size_t>(K.off[c]) * A.D.G.CF + br * kDecUp + j * 8);
+                            fa[c] = __ldg(f);
+                            fb[c] = __ldg(f + 1);
+                        }
+                        float h[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) h[e] = 0.f;
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) {
+                            float s[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) s[e] = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float4 a = fa[4 * p + k], b = fb[4 * p + k];
+                                const float w = K.w[4 * p + k];
+                                s[0] = fmaf(a.x, w, s[0]); s[1] = fmaf(a.y, w, s[1]); s[2] = fmaf(a.z, w, s[2]); s[3] = fmaf(a.w, w, s[3]);
+                                s[4] = fmaf(b.x, w, s[4]); s[5] = fmaf(b.y, w, s[5]); s[6] = fmaf(b.z, w, s[6]); s[7] = fmaf(b.w, w, s[7]);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) h[e] += s[e];
+                        }
+                        __half hh[8], hl[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) split_f16_plain(h[e], hh[e], hl[e]);
+                        const uint32_t off = static_cast<uint32_t>(pm) * 128u + (static_cast<uint32_t>(j ^ (pm & 7)) << 4);
+                        *reinterpret_cast<uint4*>(sx + off) = *reinterpret_cast<const uint4*>(hh);
+                        if (NSPLIT == 3) *reinterpret_cast<uint4*>(sx + kXLo + off) = *reinterpret_cast<const uint4*>(hl);
+                    }
+                    ptx::fence_proxy_async();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) ptx::mbar_arrive(opnd_ready);
+                }
+                // ---- layer epilogues
+                float o_acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const int n_out = A.n_out[br];
+                for (int l = 0; l < kDecLayers; ++l, ++dphase) {
+                    ptx::mbar_wait(d_full, dphase & 1);
+                    __syncwarp();
+                    ptx::tc_fence_after();
+                    const uint32_t lane_addr = tmem_base + (l & 1) * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+                    const float inv = A.inv_scale[br][l];
+                    const float* __restrict__ bias = A.bias[br][l];
+                    const bool last = l == kDecLayers - 1;
+#pragma unroll 1
+                    for (int cb = 0; cb < 8; ++cb) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32b_x32(lane_addr + cb * 32, v);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int n0 = cb * 32 + q * 8;
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
+                            float r[8];
+                            r[0] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 0]), inv, b0.x), 0.f);
+                            r[1] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 1]), inv, b0.y), 0.f);
+                            r[2] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 2]), inv, b0.z), 0.f);
+                            r[3] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 3]), inv, b0.w), 0.f);
+                            r[4] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 4]), inv, b1.x), 0.f);
+                            r[5] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 5]), inv, b1.y), 0.f);
+                            r[6] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 6]), inv, b1.z), 0.f);
+                            r[7] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 7]), inv, b1.w), 0.f);
+                            if (!last) {
+                                __half hh[8], hl[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) split_f16_plain(r[e], hh[e], hl[e]);
+                                // chunk (n0 / 64), row m, 16-byte unit ((n0 % 64) / 8) ^ (m & 7)
+                                const uint32_t off = static_cast<uint32_t>(n0 >> 6) * kDecChunkBytes + static_cast<uint32_t>(m) * 128u +
+                                                     ((static_cast<uint32_t>((n0 & 63) >> 3) ^ sw) << 4);
+                                *reinterpret_cast<uint4*>(sact + off) = *reinterpret_cast<const uint4*>(hh);
+                                if (NSPLIT == 3) *reinterpret_cast<uint4*>(sact + kActLo + off) = *reinterpret_cast<const uint4*>(hl);
+                            } else {
+                                // 256 -> n_out on the CUDA cores (second_layers' last Linear, blocks.py:80)
+#pragma unroll
+                                for (int o = 0; o < 4; ++o) {
+                                    if (o < n_out) {
+                                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(A.w_last[br] + o * kDecHid + n0));
+                                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(A.w_last[br] + o * kDecHid + n0) + 1);
+                                        float a = o_acc[o];
+                                        a = fmaf(r[0], w0.x, a); a = fmaf(r[1], w0.y, a); a = fmaf(r[2], w0.z, a); a = fmaf(r[3], w0.w, a);
+                                        a = fmaf(r[4], w1.x, a); a = fmaf(r[5], w1.y, a); a = fmaf(r[6], w1.z, a); a = fmaf(r[7], w1.w, a);
+                                        o_acc[o] = a;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    ptx::tc_fence_before();
+                    if (!last) {
+                        ptx::fence_proxy_async();
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (et == 0) ptx::mbar_arrive(opnd_ready);
+                    } else if (g0 + m < A.D.P.n) {
+                        float* op = A.D.out + (g0 + m) * A.D.oc + (br == 0 ? 0 : 1);
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            if (o < n_out) {
+                                float v = o_acc[o] + __ldg(A.b_last[br] + o);
+                                if (br == 1) {
+                                    v = 1.f / (1.f + expf(-v));
+                                    if (A.D.clamp_tex) v = fminf(fmaxf(v, 0.f), 1.f);
+                                }
+                                op[o] = v;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace s3d

@@ -106,3 +106,31 @@ def test_abi_exports_every_declared_symbol():
     # struct sizes agree with the header layout (no compute call: there is no GPU here)
     import ctypes as C
     assert C.sizeof(_lib.UNetConfig) == 4 * (5 + 8 + 4)
+    assert C.sizeof(_lib.DecoderConfig) == 4 * 10
+
+
+@pytest.mark.parametrize("use_tex", [True, False])
+def test_decoder_state_dict_layout(use_tex):
+    """The decoder mirror carries the reference checkpoint keys (networks.py:134-162) in state_dict() order."""
+    from oracle import decoder_ref as de
+    from sin3dm_b200.encoding import AutoEncoderGroupSkip
+    spec = de.DecoderSpec(use_tex=use_tex, tex_feat_channels=8 if use_tex else 0)
+    m = AutoEncoderGroupSkip(4, spec.tex_feat_channels, 64, 256, 4, use_tex=use_tex, tex_channels=3)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s in de.param_shapes(spec)]
+    m.load_state_dict(de.synthetic_state_dict(spec, 1))
+    # zero_module on the second conv of each block (blocks.py:222-224)
+    m2 = AutoEncoderGroupSkip(4, spec.tex_feat_channels, 64, 256, 4, use_tex=use_tex)
+    assert (m2.geo_convs.out_layers[1].weight == 0).all()
+    with pytest.raises(_lib.S3DError), torch.no_grad():
+        m.decode(torch.zeros(4, 3), [torch.zeros(1, spec.geo_feat_channels + spec.tex_feat_channels, 8, 8)] * 3)
+    with pytest.raises(NotImplementedError):
+        m.encode(torch.zeros(1, 4, 8, 8, 8))
+
+
+def test_grid_axes_match_oracle():
+    from oracle import decoder_ref as de
+    from sin3dm_b200.encoding import sample_grid_points_axes
+    for aabb, reso in (([-0.72, -1.0, -0.55, 0.72, 1.0, 0.55], 20), ([-1, -1, -1, 1, 1, 1], 7), ([-0.3, -1, -1, 0.3, 1, 0.9], 33)):
+        a = torch.tensor(aabb, dtype=torch.float32)
+        for u, v in zip(sample_grid_points_axes(a, reso), de.grid_axes(a, reso)):
+            assert torch.equal(u, v)
