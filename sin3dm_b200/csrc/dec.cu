@@ -41,7 +41,7 @@ struct Branch {
     DecMlpF32 mf{};                         // CUDA-core kernel: transposed fp32 weights
     uint16_t* w16[kDecLayers] = {};         // tensor-core kernel: [2][256][K] fp16 (hi, lo) of scale * W
     float inv_scale[kDecLayers] = {};
-    float *w_last = nullptr, *b_last = nullptr;
+    std::vector<float> bias_h[kDecLayers], w_last_h, b_last_h;     // host copies: they travel as kernel parameters
     CUtensorMap maps[kDecLayers];
 };
 
@@ -240,12 +240,15 @@ void finalize(s3d_decoder* d) {
                     }
                 B.w16[l] = dev_upload(d->owned, w16);
                 B.inv_scale[l] = 1.f / s;
+                B.bias_h[l] = T_(d, layers[l].key + ".bias").host;
+                S3D_CHECK(B.bias_h[l].size() == static_cast<size_t>(kDecHid), "hidden bias size");
                 const uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(kDecHid), 2};
                 const uint32_t box[3] = {64, 128, 1};
                 make_tmap(&B.maps[l], B.w16[l], 3, dims, box);
             }
-            B.w_last = const_cast<float*>(dev_upload(d->owned, T_(d, layers[kDecLayers].key + ".weight").host));
-            B.b_last = const_cast<float*>(dev_upload(d->owned, T_(d, layers[kDecLayers].key + ".bias").host));
+            B.w_last_h = T_(d, layers[kDecLayers].key + ".weight").host;      // [n_out][256]
+            B.b_last_h = T_(d, layers[kDecLayers].key + ".bias").host;
+            S3D_CHECK(B.n_out >= 1 && B.n_out <= 4 && B.w_last_h.size() == static_cast<size_t>(B.n_out) * kDecHid, "output layer shape");
         }
     }
     CUDA_TRY(cudaDeviceSynchronize());
@@ -357,16 +360,18 @@ void decode(s3d_decoder* d, const DecPoints& P, int clamp_tex, float* out, cudaS
                         "(the reference defaults); use mlp_impl=1 for other shapes");
     DecTcMaps maps{};
     DecTcArgs ta{};
+    static thread_local DecTcConst tc;          // 18.5 KB: kept off the stack
+    std::memset(&tc, 0, sizeof(tc));
     ta.D = a;
     for (int b = 0; b < d->nb; ++b) {
         const Branch& B = d->br[b];
         for (int l = 0; l < kDecLayers; ++l) {
             maps.w[b][l] = B.maps[l];
-            ta.bias[b][l] = B.mf.b[l];
             ta.inv_scale[b][l] = B.inv_scale[l];
+            std::copy(B.bias_h[l].begin(), B.bias_h[l].end(), tc.bias[b][l]);
         }
-        ta.w_last[b] = B.w_last;
-        ta.b_last[b] = B.b_last;
+        std::copy(B.w_last_h.begin(), B.w_last_h.end(), &tc.w_last[b][0][0]);
+        std::copy(B.b_last_h.begin(), B.b_last_h.end(), tc.b_last[b]);
         ta.n_out[b] = B.n_out;
     }
     ta.n_tiles = (P.n + kDecPts - 1) / kDecPts;
@@ -374,11 +379,11 @@ void decode(s3d_decoder* d, const DecPoints& P, int clamp_tex, float* out, cudaS
     if (d->cfg.precision == 1) {
         using Cfg = DecTcCfg<1>;
         CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        launch(k_dec_mlp_tc<1>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta);
+        launch(k_dec_mlp_tc<1>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
     } else {
         using Cfg = DecTcCfg<3>;
         CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        launch(k_dec_mlp_tc<3>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta);
+        launch(k_dec_mlp_tc<3>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
     }
     d->last_launches = 1;
 }

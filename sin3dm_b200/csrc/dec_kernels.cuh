@@ -425,12 +425,17 @@ struct DecTcMaps {
 };
 struct DecTcArgs {
     DecArgs D;
-    const float* bias[2][kDecLayers];     // fp32 [256]
     float inv_scale[2][kDecLayers];       // 1 / (power-of-two weight scale)
-    const float* w_last[2];               // fp32 [n_out][256]
-    const float* b_last[2];
     int n_out[2];
     long long n_tiles;
+};
+// Epilogue constants travel as a kernel parameter (18.5 KB of the 32 KB parameter space): every thread of a warp reads the same
+// element, so they come out of the constant cache instead of stalling the epilogue on global loads (ncu r1: 38 % of the
+// epilogue warps' samples sat behind the bias __ldg).
+struct DecTcConst {
+    float bias[2][kDecLayers][kDecHid];   // [branch][layer][channel]
+    float w_last[2][4][kDecHid];          // second_layers' last Linear, [branch][out][channel]
+    float b_last[2][4];
 };
 
 __device__ __forceinline__ void split_f16_plain(float v, __half& hi, __half& lo) {
@@ -440,7 +445,8 @@ __device__ __forceinline__ void split_f16_plain(float v, __half& hi, __half& lo)
 }
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_constant__ DecTcMaps M, const DecTcArgs A) {
+__global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_constant__ DecTcMaps M, const DecTcArgs A,
+                                                                  const __grid_constant__ DecTcConst C) {
     using Cfg = DecTcCfg<NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -449,8 +455,9 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
     uint8_t* sb = sact + Cfg::kActBytes;                 // weight ring
     uint64_t* fullB = reinterpret_cast<uint64_t*>(sb + Cfg::kRingBytes);
     uint64_t* emptyB = fullB + Cfg::kBSlots;
-    uint64_t* opnd_ready = emptyB + Cfg::kBSlots;        // epilogue warps -> MMA warp: the next A operand is in shared memory
-    uint64_t* d_full = opnd_ready + 1;                   // MMA warp -> epilogue warps: the layer's accumulator is complete
+    uint64_t* x_ready = emptyB + Cfg::kBSlots;           // gather -> MMA warp: X (layer 0 / the concat chunk) is in shared memory
+    uint64_t* chunk_ready = x_ready + 1;                 // [4] epilogue -> MMA warp: 64-channel chunk c of the next A operand is written
+    uint64_t* d_full = chunk_ready + 4;                  // MMA warp -> epilogue warps: the layer's accumulator is complete
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(d_full + 1);
     constexpr uint32_t kXLo = kDecChunkBytes, kActLo = 4 * kDecChunkBytes;
 
@@ -467,7 +474,8 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                 ptx::mbar_init(&fullB[s], 1);
                 ptx::mbar_init(&emptyB[s], 1);
             }
-            ptx::mbar_init(opnd_ready, 1);
+            ptx::mbar_init(x_ready, 4);
+            for (int c = 0; c < 4; ++c) ptx::mbar_init(&chunk_ready[c], 4);
             ptx::mbar_init(d_full, 1);
             ptx::fence_barrier_init();
         }
@@ -504,19 +512,22 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = ptx::make_idesc_f16(128, 128);
+        // The A operand is handed over per 64-channel chunk: layer l+1's MMAs over chunk c start as soon as layer l's epilogue
+        // has written it, so the tensor pipe works under the rest of that epilogue instead of after it.
         int gb = 0;
-        uint32_t it = 0;                // operand hand-overs so far (phase of opnd_ready)
+        uint32_t xit = 0;               // gathers consumed so far (phase of x_ready)
         for (long long t = blockIdx.x; t < A.n_tiles; t += gridDim.x)
-            for (int br = 0; br < nb; ++br)
-                for (int l = 0; l < kDecLayers; ++l, ++it) {
-                    ptx::mbar_wait(opnd_ready, it & 1);
-                    ptx::tc_fence_after();
+            for (int br = 0; br < nb; ++br, ++xit)
+                for (int l = 0; l < kDecLayers; ++l) {
                     const uint32_t d = tmem_base + (l & 1) * 256;
                     const int nk = n_chunks(l);
                     for (int kc = 0; kc < nk; ++kc) {
                         // A chunk: X for the first chunk of layers 0 and 3, else ACT chunk
                         const bool from_x = (l == 0) || (l == 3 && kc == 0);
                         const int ac = l == 3 ? kc - 1 : kc;
+                        if (l == 0) ptx::mbar_wait(x_ready, xit & 1);
+                        else if (!from_x) ptx::mbar_wait(&chunk_ready[ac], (l - 1) & 1);     // 4 producing epilogues per branch
+                        ptx::tc_fence_after();
                         const uint32_t a_hi = ptx::smem_u32(from_x ? sx : sact + ac * kDecChunkBytes);
                         const uint32_t a_lo = ptx::smem_u32(from_x ? sx + kXLo : sact + kActLo + ac * kDecChunkBytes);
                         for (int nh = 0; nh < 2; ++nh)
@@ -550,7 +561,6 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
         // ===================== gather + epilogues (warps 2..5) =====================
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;                 // point of the tile == TMEM lane == A operand row
-        const int et = threadIdx.x - 64;
         uint32_t dphase = 0;                               // d_full completions consumed so far
         const uint32_t sw = static_cast<uint32_t>(m & 7);
         for (long long t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
@@ -599,9 +609,9 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                         *reinterpret_cast<uint4*>(sx + off) = *reinterpret_cast<const uint4*>(hh);
                         if (NSPLIT == 3) *reinterpret_cast<uint4*>(sx + kXLo + off) = *reinterpret_cast<const uint4*>(hl);
                     }
-                    ptx::fence_proxy_async();
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (et == 0) ptx::mbar_arrive(opnd_ready);
+                    ptx::fence_proxy_async();           // a warp writes only rows of its own quarter: per-warp arrival
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(x_ready);
                 }
                 // ---- layer epilogues
                 float o_acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -612,26 +622,16 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                     ptx::tc_fence_after();
                     const uint32_t lane_addr = tmem_base + (l & 1) * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
                     const float inv = A.inv_scale[br][l];
-                    const float* __restrict__ bias = A.bias[br][l];
+                    const float* bias = C.bias[br][l];                 // constant bank (kernel parameter)
                     const bool last = l == kDecLayers - 1;
-#pragma unroll 1
-                    for (int cb = 0; cb < 8; ++cb) {
-                        uint32_t v[32];
-                        ptx::tmem_ld_32x32b_x32(lane_addr + cb * 32, v);
-                        ptx::tmem_ld_wait();
+                    // 32 accumulator columns -> +bias, ReLU -> next operand (or the 256 -> n_out layer on the CUDA cores)
+                    auto consume = [&](const uint32_t (&v)[32], int cb) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int n0 = cb * 32 + q * 8;
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
                             float r[8];
-                            r[0] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 0]), inv, b0.x), 0.f);
-                            r[1] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 1]), inv, b0.y), 0.f);
-                            r[2] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 2]), inv, b0.z), 0.f);
-                            r[3] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 3]), inv, b0.w), 0.f);
-                            r[4] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 4]), inv, b1.x), 0.f);
-                            r[5] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 5]), inv, b1.y), 0.f);
-                            r[6] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 6]), inv, b1.z), 0.f);
-                            r[7] = fmaxf(fmaf(__uint_as_float(v[q * 8 + 7]), inv, b1.w), 0.f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) r[e] = fmaxf(fmaf(__uint_as_float(v[q * 8 + e]), inv, bias[n0 + e]), 0.f);
                             if (!last) {
                                 __half hh[8], hl[8];
 #pragma unroll
@@ -646,28 +646,41 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
 #pragma unroll
                                 for (int o = 0; o < 4; ++o) {
                                     if (o < n_out) {
-                                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(A.w_last[br] + o * kDecHid + n0));
-                                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(A.w_last[br] + o * kDecHid + n0) + 1);
+                                        const float* w = C.w_last[br][o] + n0;
                                         float a = o_acc[o];
-                                        a = fmaf(r[0], w0.x, a); a = fmaf(r[1], w0.y, a); a = fmaf(r[2], w0.z, a); a = fmaf(r[3], w0.w, a);
-                                        a = fmaf(r[4], w1.x, a); a = fmaf(r[5], w1.y, a); a = fmaf(r[6], w1.z, a); a = fmaf(r[7], w1.w, a);
+#pragma unroll
+                                        for (int e = 0; e < 8; ++e) a = fmaf(r[e], w[e], a);
                                         o_acc[o] = a;
                                     }
                                 }
                             }
                         }
+                        if (!last && (cb & 1)) {
+                            // chunk cb/2 of the next layer's A operand is complete for this warp's 32 rows
+                            ptx::fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive(&chunk_ready[cb >> 1]);
+                        }
+                    };
+                    // TMEM loads run one 32-column block ahead of the arithmetic
+                    uint32_t va[32], vb[32];
+                    ptx::tmem_ld_32x32b_x32(lane_addr, va);
+#pragma unroll 1
+                    for (int cb = 0; cb < 8; cb += 2) {
+                        ptx::tmem_ld_wait();
+                        ptx::tmem_ld_32x32b_x32(lane_addr + (cb + 1) * 32, vb);
+                        consume(va, cb);
+                        ptx::tmem_ld_wait();
+                        if (cb + 2 < 8) ptx::tmem_ld_32x32b_x32(lane_addr + (cb + 2) * 32, va);
+                        consume(vb, cb + 1);
                     }
                     ptx::tc_fence_before();
-                    if (!last) {
-                        ptx::fence_proxy_async();
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
-                        if (et == 0) ptx::mbar_arrive(opnd_ready);
-                    } else if (g0 + m < A.D.P.n) {
+                    if (last && g0 + m < A.D.P.n) {
                         float* op = A.D.out + (g0 + m) * A.D.oc + (br == 0 ? 0 : 1);
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
                             if (o < n_out) {
-                                float v = o_acc[o] + __ldg(A.b_last[br] + o);
+                                float v = o_acc[o] + C.b_last[br][o];
                                 if (br == 1) {
                                     v = 1.f / (1.f + expf(-v));
                                     if (A.D.clamp_tex) v = fminf(fmaxf(v, 0.f), 1.f);
