@@ -402,10 +402,11 @@ __global__ void __launch_bounds__(256) k_dec_mlp_ffma(const DecArgs A, const Dec
 // unscaled) stream through a TMA ring as [128 N x 64 K] tiles; they are the same for every tile and stay L2-resident.
 // NSPLIT == 3:  D += Ah*Bh + Al*Bh + Ah*Bl  (fp32 accumulate in TMEM; error ~2^-21 per operand, i.e. fp32-grade).
 // NSPLIT == 1:  D += Ah*Bh.
-// Warps: 0 = TMA producer (weights), 1 = TMEM owner + MMA issuer, 2..5 = gather + epilogues (thread = point = TMEM lane).
+// Warps: 0 = TMA producer (weights), 1 = TMEM owner + MMA issuer, 2..9 = gather + epilogues (thread = point = TMEM lane; the two
+// warps of a TMEM lane quarter take alternate 32-column blocks, so both work on the chunk the MMA warp is waiting for).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kDecPts = 128;
-constexpr int kDecTcThreads = 192;
+constexpr int kDecTcThreads = 320;               // TMA warp + MMA warp + 8 gather/epilogue warps
 constexpr int kDecChunkBytes = kDecPts * 128;       // one 64-wide K chunk of an A operand: 128 rows x 128 B
 constexpr int kDecBSlotBytes = 128 * 128;           // [128 N rows][64 K] fp16
 constexpr int kDecLayers = 5;                       // tensor-core layers per branch (the 256 -> out layer runs in L5's epilogue)
@@ -474,8 +475,8 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                 ptx::mbar_init(&fullB[s], 1);
                 ptx::mbar_init(&emptyB[s], 1);
             }
-            ptx::mbar_init(x_ready, 4);
-            for (int c = 0; c < 4; ++c) ptx::mbar_init(&chunk_ready[c], 4);
+            ptx::mbar_init(x_ready, 8);
+            for (int c = 0; c < 4; ++c) ptx::mbar_init(&chunk_ready[c], 8);
             ptx::mbar_init(d_full, 1);
             ptx::fence_barrier_init();
         }
@@ -558,11 +559,13 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                     __syncwarp();
                 }
     } else {
-        // ===================== gather + epilogues (warps 2..5) =====================
-        const int quarter = warp & 3;
+        // ===================== gather + epilogues (warps 2..9) =====================
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may read (warp id % 4)
+        const int half = (warp - 2) >> 2;                  // which of the quarter's two warps
         const int m = quarter * 32 + lane;                 // point of the tile == TMEM lane == A operand row
         uint32_t dphase = 0;                               // d_full completions consumed so far
         const uint32_t sw = static_cast<uint32_t>(m & 7);
+        const uint32_t sact_u32 = ptx::smem_u32(sact);
         for (long long t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
             const long long g0 = t * kDecPts;
             for (int br = 0; br < nb; ++br) {
@@ -570,7 +573,7 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                 {
                     const int j = lane & 7;
 #pragma unroll 1
-                    for (int pass = 0; pass < 8; ++pass) {
+                    for (int pass = half * 4; pass < half * 4 + 4; ++pass) {
                         const int pm = quarter * 32 + pass * 4 + (lane >> 3);
                         const long long g = min(g0 + pm, A.D.P.n - 1);
                         float xn[3];
@@ -635,12 +638,16 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                             if (!last) {
                                 __half hh[8], hl[8];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) split_f16_plain(r[e], hh[e], hl[e]);
+                                for (int e = 0; e < 8; ++e) {          // r >= 0 after the ReLU: only the upper clamp
+                                    const float c = fminf(r[e], 65504.f);
+                                    hh[e] = __float2half_rn(c);
+                                    hl[e] = __float2half_rn(c - __half2float(hh[e]));
+                                }
                                 // chunk (n0 / 64), row m, 16-byte unit ((n0 % 64) / 8) ^ (m & 7)
                                 const uint32_t off = static_cast<uint32_t>(n0 >> 6) * kDecChunkBytes + static_cast<uint32_t>(m) * 128u +
                                                      ((static_cast<uint32_t>((n0 & 63) >> 3) ^ sw) << 4);
-                                *reinterpret_cast<uint4*>(sact + off) = *reinterpret_cast<const uint4*>(hh);
-                                if (NSPLIT == 3) *reinterpret_cast<uint4*>(sact + kActLo + off) = *reinterpret_cast<const uint4*>(hl);
+                                ptx::st_shared_v4(sact_u32 + off, *reinterpret_cast<const uint4*>(hh));
+                                if (NSPLIT == 3) ptx::st_shared_v4(sact_u32 + kActLo + off, *reinterpret_cast<const uint4*>(hl));
                             } else {
                                 // 256 -> n_out on the CUDA cores (second_layers' last Linear, blocks.py:80)
 #pragma unroll
@@ -655,27 +662,38 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                                 }
                             }
                         }
-                        if (!last && (cb & 1)) {
-                            // chunk cb/2 of the next layer's A operand is complete for this warp's 32 rows
+                        if (!last) {
+                            // this warp's half of chunk cb/2 of the next layer's A operand is written (32 rows x 32 channels)
                             ptx::fence_proxy_async();
                             __syncwarp();
                             if (lane == 0) ptx::mbar_arrive(&chunk_ready[cb >> 1]);
                         }
                     };
-                    // TMEM loads run one 32-column block ahead of the arithmetic
+                    // TMEM loads run one 32-column block ahead of the arithmetic; this warp owns blocks half, half + 2, ...
                     uint32_t va[32], vb[32];
-                    ptx::tmem_ld_32x32b_x32(lane_addr, va);
+                    ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, va);
 #pragma unroll 1
-                    for (int cb = 0; cb < 8; cb += 2) {
+                    for (int cb = half; cb < 8; cb += 4) {
                         ptx::tmem_ld_wait();
-                        ptx::tmem_ld_32x32b_x32(lane_addr + (cb + 1) * 32, vb);
+                        ptx::tmem_ld_32x32b_x32(lane_addr + (cb + 2) * 32, vb);
                         consume(va, cb);
                         ptx::tmem_ld_wait();
-                        if (cb + 2 < 8) ptx::tmem_ld_32x32b_x32(lane_addr + (cb + 2) * 32, va);
-                        consume(vb, cb + 1);
+                        if (cb + 4 < 8) ptx::tmem_ld_32x32b_x32(lane_addr + (cb + 4) * 32, va);
+                        consume(vb, cb + 2);
                     }
                     ptx::tc_fence_before();
-                    if (last && g0 + m < A.D.P.n) {
+                    if (last) {
+                        // the two warps of a quarter hold partial sums over alternate column blocks: combine through the (now idle)
+                        // activation buffer; nothing writes it again before every epilogue warp has arrived on x_ready
+                        float4* xch = reinterpret_cast<float4*>(sact) + m;
+                        if (half == 1) *xch = make_float4(o_acc[0], o_acc[1], o_acc[2], o_acc[3]);
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (half == 0) {
+                            const float4 o = *xch;
+                            o_acc[0] += o.x; o_acc[1] += o.y; o_acc[2] += o.z; o_acc[3] += o.w;
+                        }
+                    }
+                    if (last && half == 0 && g0 + m < A.D.P.n) {
                         float* op = A.D.out + (g0 + m) * A.D.oc + (br == 0 ? 0 : 1);
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
