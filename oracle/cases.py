@@ -105,3 +105,24 @@ def make_decoder_inputs(case):
         centre, half = (aabb[3:] + aabb[:3]) / 2, (aabb[3:] - aabb[:3]) / 2
         pts = centre + u * half * case["spill"]
     return maps, pts, aabb
+
+
+# ---------------------------------------------------------------------------- variational bound
+BPD_CASES = {
+    "startx_large": dict(spec=dict(**SMALL), wseed=71, HWD=(8, 12, 8), B=2, T=1000, respacing="6", nseed=81),
+    "eps_small_noclip": dict(spec=dict(**SMALL), wseed=72, HWD=(8, 8, 10), B=1, T=1000, respacing="5", mean_type="epsilon",
+                             var_type="fixed_small", clip=False, nseed=82),
+}
+
+
+def make_bpd_inputs(case, n_steps):
+    """-> (x_start in [-1, 1], {step: q_sample noise}); x_start holds a few exact +-1 so both edge branches of the
+    discretised likelihood (losses.py:71-75) are exercised."""
+    H, W, D = case["HWD"]
+    shape = (case["B"], case["spec"]["in_channels"], H + D, W + D)
+    g = torch.Generator().manual_seed(case["nseed"])
+    x0 = torch.rand(shape, generator=g) * 2 - 1
+    x0.view(-1)[::17] = 1.0
+    x0.view(-1)[5::23] = -1.0
+    noises = {i: torch.randn(shape, generator=g) for i in range(n_steps - 1, -1, -1)}
+    return x0, noises

@@ -10,6 +10,8 @@ Restates, with numpy fp64 tables and torch fp32 element-wise math in the referen
   * ``ddim_sample`` (eta, y0/mask)     gaussian_diffusion.py:538-600
   * ``ddim_reverse_sample``            gaussian_diffusion.py:602-638
   * ``q_sample`` / ``training_losses`` (MSE, per-plane)   gaussian_diffusion.py:189-207, 771-856
+  * ``_vb_terms_bpd`` / ``_prior_bpd`` / ``calc_bpd_loop``  gaussian_diffusion.py:736-769, 858-931
+  * ``normal_kl`` / ``discretized_gaussian_log_likelihood``  src/diffusion/losses.py:12-77
 
 Tables are fp64; every use rounds the looked-up scalar to fp32 first, exactly like
 ``_extract_into_tensor`` (gaussian_diffusion.py:944).
@@ -195,6 +197,61 @@ class RefDiffusion:
             terms[f"mse_{name}"] = d.mean(dim=(1, 2, 3))
         terms["loss"] = terms["mse_xy"] + terms["mse_xz"] + terms["mse_yz"]
         return terms
+
+    # -- variational bound (bits per dimension)
+    @staticmethod
+    def normal_kl(mean1, logvar1, mean2, logvar2):
+        """losses.py:12-41."""
+        return 0.5 * (-1.0 + logvar2 - logvar1 + torch.exp(logvar1 - logvar2) + ((mean1 - mean2) ** 2) * torch.exp(-logvar2))
+
+    @staticmethod
+    def discretized_gaussian_log_likelihood(x, means, log_scales):
+        """losses.py:44-77 (tanh approximation of the normal CDF, bins of width 2/255)."""
+        cdf = lambda v: 0.5 * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (v + 0.044715 * torch.pow(v, 3))))
+        centered = x - means
+        inv_stdv = torch.exp(-log_scales)
+        cdf_plus = cdf(inv_stdv * (centered + 1.0 / 255.0))
+        cdf_min = cdf(inv_stdv * (centered - 1.0 / 255.0))
+        log_cdf_plus = torch.log(cdf_plus.clamp(min=1e-12))
+        log_one_minus_cdf_min = torch.log((1.0 - cdf_min).clamp(min=1e-12))
+        cdf_delta = cdf_plus - cdf_min
+        return torch.where(x < -0.999, log_cdf_plus,
+                           torch.where(x > 0.999, log_one_minus_cdf_min, torch.log(cdf_delta.clamp(min=1e-12))))
+
+    def vb_terms_bpd(self, model, x_start, x_t, t, clip=True):
+        """:736-769 -> dict(output [N], pred_xstart)."""
+        T = self.tab
+        true_mean = self._x(T["posterior_mean_coef1"], t, x_t) * x_start + self._x(T["posterior_mean_coef2"], t, x_t) * x_t
+        true_logvar = self._x(T["posterior_log_variance_clipped"], t, x_t).expand_as(x_t)
+        out = self.p_mean_variance(model, x_t, t, clip)
+        flat = lambda v: v.mean(dim=list(range(1, v.dim())))
+        kl = flat(self.normal_kl(true_mean, true_logvar, out["mean"], out["log_variance"])) / np.log(2.0)
+        nll = flat(-self.discretized_gaussian_log_likelihood(x_start, out["mean"], 0.5 * out["log_variance"])) / np.log(2.0)
+        return dict(output=torch.where(t == 0, nll, kl), pred_xstart=out["pred_xstart"])
+
+    def prior_bpd(self, x_start):
+        """:858-874."""
+        t = torch.full((x_start.shape[0],), self.num_timesteps - 1, dtype=torch.long)
+        mean = self._x(self.tab["sqrt_alphas_cumprod"], t, x_start) * x_start
+        logvar = self._x(self.tab["log_one_minus_alphas_cumprod"], t, x_start).expand_as(x_start)
+        kl = self.normal_kl(mean, logvar, torch.tensor(0.0), torch.tensor(0.0))
+        return kl.mean(dim=list(range(1, kl.dim()))) / np.log(2.0)
+
+    def calc_bpd_loop(self, model, x_start, step_noise: Callable[[int], torch.Tensor], clip=True):
+        """:876-931; ``step_noise(t)`` is the N(0,1) tensor q_sample uses at step t."""
+        flat = lambda v: v.mean(dim=list(range(1, v.dim())))
+        vb, xm, em = [], [], []
+        for i in range(self.num_timesteps - 1, -1, -1):
+            t = torch.full((x_start.shape[0],), i, dtype=torch.long)
+            noise = step_noise(i)
+            x_t = self.q_sample(x_start, t, noise)
+            o = self.vb_terms_bpd(model, x_start, x_t, t, clip)
+            vb.append(o["output"])
+            xm.append(flat((o["pred_xstart"] - x_start) ** 2))
+            em.append(flat((self.eps_from_x0(x_t, t, o["pred_xstart"]) - noise) ** 2))
+        vb, xm, em = torch.stack(vb, dim=1), torch.stack(xm, dim=1), torch.stack(em, dim=1)
+        prior = self.prior_bpd(x_start)
+        return dict(total_bpd=vb.sum(dim=1) + prior, prior_bpd=prior, vb=vb, xstart_mse=xm, mse=em)
 
     def sample_loop(self, model, x_T, step_noise: Callable[[int], torch.Tensor], ddim=False, progressive=False,
                     **kw):

@@ -476,10 +476,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 }
                 if (et == 0 && lt == 0) trace_mark(A.tr, 19);
                 if (et == 0 && lt == 0) trace_mark(A.tr, 20);
-                __threadfence();
-                if (et == 0 && lt == 0) trace_mark(A.tr, 21);
+                // publish: CTA barrier, then ONE release-scoped reduction (cumulative over the stores the barrier ordered before
+                // it) instead of a device-wide fence in each of the 128 threads
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) atomicAdd(&F.counters[0], 1u);
+                if (et == 0) {
+                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(F.counters), "r"(1u) : "memory");
+                    if (lt == 0) trace_mark(A.tr, 21);
+                }
                 if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 4);
                 continue;
             }
