@@ -129,6 +129,29 @@ int s3d_sched_step(const s3d_sched_args* a, void* stream);
 /* q_sample: x_t = coef[t][10]*x0 + coef[t][11]*noise (gaussian_diffusion.py:189-207). */
 int s3d_q_sample(const float* x0_dev, const float* noise_dev, float* out_dev, const float* coef_dev, const int* t_idx_dev,
                  int B, int64_t n_per_sample, void* stream);
+/* ---- variational-bound terms (replaces GaussianDiffusion._vb_terms_bpd, gaussian_diffusion.py:736-769, and the two MSEs
+ * calc_bpd_loop adds per step, :912-916; normal_kl / discretized_gaussian_log_likelihood are src/diffusion/losses.py:12-77).
+ * One fused pass + a fixed-order fp64 reduction: out[b] = { KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)) in bits per dimension,
+ * or the discretised decoder NLL where t_idx[b] == 0; mean (pred_xstart - x_start)^2; mean (eps - noise)^2 (0 if noise == NULL) }.
+ * logvar_dev is [T][2] fp32: posterior_log_variance_clipped, model log-variance (FIXED_LARGE / FIXED_SMALL table). */
+typedef struct {
+    int mean_type;          /* S3D_START_X / S3D_EPSILON */
+    int clip_denoised;
+    int B;
+    int64_t n_per_sample;
+    const float* x_start;   /* [B, n] */
+    const float* x_t;       /* [B, n] */
+    const float* model_out; /* [B, n] */
+    const float* noise;     /* [B, n] the noise x_t was drawn with, or NULL */
+    float* pred_xstart;     /* [B, n] or NULL */
+    const float* coef_dev;  /* [T][S3D_NCOEF] */
+    const float* logvar_dev;
+    const int* t_idx_dev;   /* [B] */
+    void* workspace;        /* s3d_vb_workspace_bytes(B, n) bytes of device memory */
+    float* out;             /* [B][3] */
+} s3d_vb_args;
+int64_t s3d_vb_workspace_bytes(int B, int64_t n_per_sample);
+int s3d_vb_terms(const s3d_vb_args* a, void* stream);
 /* N(0,1) fill [B, C, hw] with the same counter-based generator the sampler uses (noise of sample s at step i). */
 int s3d_philox_normal(float* out_dev, int B, int C, int64_t hw, uint64_t seed, uint32_t sample_base, uint32_t step,
                       void* stream);

@@ -30,6 +30,13 @@ class SchedArgs(C.Structure):
                 ("seed", C.c_uint64), ("sample_base", C.c_uint32)]
 
 
+class VbArgs(C.Structure):
+    _fields_ = [("mean_type", C.c_int), ("clip_denoised", C.c_int), ("B", C.c_int), ("n_per_sample", C.c_int64),
+                ("x_start", C.c_void_p), ("x_t", C.c_void_p), ("model_out", C.c_void_p), ("noise", C.c_void_p),
+                ("pred_xstart", C.c_void_p), ("coef_dev", C.c_void_p), ("logvar_dev", C.c_void_p),
+                ("t_idx_dev", C.c_void_p), ("workspace", C.c_void_p), ("out", C.c_void_p)]
+
+
 class LoopArgs(C.Structure):
     _fields_ = [("kind", C.c_int), ("mean_type", C.c_int), ("clip_denoised", C.c_int), ("is_mask_t0", C.c_int),
                 ("n_steps", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("D", C.c_int),
@@ -75,6 +82,8 @@ _SIGNATURES = {
                                C.c_void_p]),
     "s3d_philox_normal": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32,
                                     C.c_void_p]),
+    "s3d_vb_workspace_bytes": (C.c_int64, [C.c_int, C.c_int64]),
+    "s3d_vb_terms": (C.c_int, [C.POINTER(VbArgs), C.c_void_p]),
     "s3d_sample_loop": (C.c_int, [C.c_void_p, C.POINTER(LoopArgs), C.c_void_p]),
     "s3d_decoder_create": (C.c_int, [C.POINTER(DecoderConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "s3d_decoder_destroy": (C.c_int, [C.c_void_p]),

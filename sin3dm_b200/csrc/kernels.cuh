@@ -855,6 +855,91 @@ __global__ void __launch_bounds__(256) k_q_sample(const float* __restrict__ x0, 
         out[base + i] = __fadd_rn(__fmul_rn(a, x0[base + i]), __fmul_rn(s, noise[base + i]));
 }
 
+// ---------------------------------------------------------------- variational-bound terms (bits per dimension)
+//   reference: GaussianDiffusion._vb_terms_bpd, gaussian_diffusion.py:736-769 (+ the two MSEs calc_bpd_loop adds, :912-916),
+//              normal_kl / discretized_gaussian_log_likelihood, src/diffusion/losses.py:12-77
+// One pass over (x_start, x_t, model_out[, noise]): per element the posterior KL or — at t == 0 — the discretised decoder NLL,
+// (pred_xstart - x_start)^2 and (eps - noise)^2, reduced per sample.  Block sums are fp64 and are added by k_vb_finalize in
+// block order, so the result does not depend on scheduling.  grid (gx, B)
+struct VbArgs {
+    int mean_type, clip, B;
+    long long n;
+    const float *x_start, *x_t, *model_out, *noise;
+    float* x0_out;              // pred_xstart (nullable)
+    const float* coef;          // [T][12]
+    const float* logvar;        // [T][2]: posterior_log_variance_clipped, model log-variance
+    const int* t_idx;
+    double* partial;            // [B][gx][3]
+    float* out;                 // [B][3]: vb term (bits), mean (pred_xstart - x_start)^2, mean (eps - noise)^2
+};
+__device__ __forceinline__ float vb_cdf(float v) {       // losses.py:44-49
+    return 0.5f * (1.0f + tanhf(0.7978845608028654f * (v + 0.044715f * (v * v * v))));
+}
+__global__ void __launch_bounds__(256) k_vb_terms(VbArgs A) {
+    const int b = blockIdx.y, t = A.t_idx[b];
+    float cf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cf[k] = __ldg(A.coef + static_cast<size_t>(t) * 12 + k);
+    const float lv1 = __ldg(A.logvar + 2 * t), lv2 = __ldg(A.logvar + 2 * t + 1);
+    const float e12 = expf(lv1 - lv2), einv2 = expf(-lv2), inv_stdv = expf(-(0.5f * lv2));
+    const size_t base = static_cast<size_t>(b) * A.n;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < A.n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float xs = A.x_start[base + i], xt = A.x_t[base + i], mo = A.model_out[base + i];
+        float x0 = A.mean_type == 0 ? mo : __fsub_rn(__fmul_rn(cf[0], xt), __fmul_rn(cf[1], mo));
+        if (A.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        if (A.x0_out) A.x0_out[base + i] = x0;
+        const float true_mean = __fadd_rn(__fmul_rn(cf[2], xs), __fmul_rn(cf[3], xt));
+        const float mean = __fadd_rn(__fmul_rn(cf[2], x0), __fmul_rn(cf[3], xt));
+        float term;
+        if (t != 0) {
+            const float d = true_mean - mean;
+            term = 0.5f * (-1.0f + lv2 - lv1 + e12 + (d * d) * einv2);
+        } else {
+            const float c = xs - mean;
+            const float cdf_plus = vb_cdf(inv_stdv * (c + 1.0f / 255.0f)), cdf_min = vb_cdf(inv_stdv * (c - 1.0f / 255.0f));
+            float lp;
+            if (xs < -0.999f) lp = logf(fmaxf(cdf_plus, 1e-12f));
+            else if (xs > 0.999f) lp = logf(fmaxf(1.0f - cdf_min, 1e-12f));
+            else lp = logf(fmaxf(cdf_plus - cdf_min, 1e-12f));
+            term = -lp;
+        }
+        acc[0] += static_cast<double>(term);
+        const float dx = x0 - xs;
+        acc[1] += static_cast<double>(dx * dx);
+        if (A.noise) {
+            const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(cf[0], xt), x0), cf[1]);
+            const float de = eps - A.noise[base + i];
+            acc[2] += static_cast<double>(de * de);
+        }
+    }
+    __shared__ double red[3][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        A.partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = s;
+    }
+}
+// grid B, block 32: lane k < 3 adds the gx block sums of term k in order
+__global__ void k_vb_finalize(VbArgs A, int gx) {
+    const int b = blockIdx.x, k = threadIdx.x;
+    if (k >= 3) return;
+    double s = 0.0;
+    for (int j = 0; j < gx; ++j) s += A.partial[(static_cast<size_t>(b) * gx + j) * 3 + k];
+    double m = s / static_cast<double>(A.n);
+    if (k == 0) m /= 0.6931471805599453;        // nats -> bits (np.log(2.0))
+    A.out[b * 3 + k] = static_cast<float>(m);
+}
+
 __global__ void __launch_bounds__(256) k_philox_normal(float* __restrict__ out, int C, long long hw, unsigned long long seed,
                                                        unsigned int sample_base, unsigned int step) {
     pdl_wait();

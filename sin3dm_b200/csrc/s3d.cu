@@ -1444,6 +1444,36 @@ int s3d_q_sample(const float* x0_dev, const float* noise_dev, float* out_dev, co
     API_END
 }
 
+static int vb_grid(int64_t n) { return static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 4)); }
+int64_t s3d_vb_workspace_bytes(int B, int64_t n) { return static_cast<int64_t>(B) * vb_grid(n) * 3 * sizeof(double); }
+int s3d_vb_terms(const s3d_vb_args* a, void* stream) {
+    API_BEGIN
+    S3D_CHECK(a && a->x_start && a->x_t && a->model_out && a->coef_dev && a->logvar_dev && a->t_idx_dev && a->workspace && a->out &&
+                  a->B >= 1 && a->n_per_sample >= 1, "bad argument");
+    S3D_CHECK(a->mean_type == S3D_START_X || a->mean_type == S3D_EPSILON, "mean_type");
+    VbArgs A{};
+    A.mean_type = a->mean_type;
+    A.clip = a->clip_denoised;
+    A.B = a->B;
+    A.n = a->n_per_sample;
+    A.x_start = a->x_start;
+    A.x_t = a->x_t;
+    A.model_out = a->model_out;
+    A.noise = a->noise;
+    A.x0_out = a->pred_xstart;
+    A.coef = a->coef_dev;
+    A.logvar = a->logvar_dev;
+    A.t_idx = a->t_idx_dev;
+    A.partial = static_cast<double*>(a->workspace);
+    A.out = a->out;
+    const int gx = vb_grid(A.n);
+    launch(k_vb_terms, dim3(gx, A.B), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
+    LAUNCH_CHECK("k_vb_terms");
+    launch(k_vb_finalize, dim3(A.B), dim3(32), 0, static_cast<cudaStream_t>(stream), A, gx);
+    LAUNCH_CHECK("k_vb_finalize");
+    API_END
+}
+
 int s3d_philox_normal(float* out_dev, int B, int C, int64_t hw, uint64_t seed, uint32_t sample_base, uint32_t step, void* stream) {
     API_BEGIN
     S3D_CHECK(out_dev && B >= 1 && C >= 1 && hw >= 1, "bad argument");

@@ -421,6 +421,68 @@ class GaussianDiffusion:
                                      sample_base, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
                                      model_kwargs=model_kwargs, eta=eta, y0=y0, mask=mask, is_mask_t0=is_mask_t0)
 
+    # ------------------------------------------------------------------ variational bound (bits per dimension)
+    def _vb_device(self, model, x_start, x_t, t, clip_denoised, model_kwargs, noise=None):
+        """model -> fused k_vb_terms.  Returns (out [B, 3] fp32: vb term, xstart mse, eps mse; pred_xstart)."""
+        if not x_t.is_cuda:
+            raise _lib.S3DError("sin3dm_b200 runs on CUDA only (no CPU fallback)")
+        xs, xt = x_start.float().contiguous(), x_t.float().contiguous()
+        mo = self._call_model(model, xt, t, model_kwargs).float().contiguous()
+        assert mo.shape == xs.shape == xt.shape
+        B, n = xs.shape[0], xs[0].numel()
+        dev = xs.device
+        key = ("logvar", str(dev))
+        if key not in self._coef_cache:
+            _, logvar = self._model_variance_tables()
+            self._coef_cache[key] = th.stack([_f32(self.posterior_log_variance_clipped), _f32(logvar)], dim=1).contiguous().to(dev)
+        a = _lib.VbArgs()
+        a.mean_type, a.clip_denoised, a.B, a.n_per_sample = self._mean_code(), int(bool(clip_denoised)), B, n
+        pred, out = th.empty_like(xs), th.empty(B, 3, device=dev, dtype=th.float32)
+        ws = th.empty(_lib.lib().s3d_vb_workspace_bytes(B, n), device=dev, dtype=th.uint8)
+        ti = t.to(dev, th.int32).contiguous()
+        coef = self.coef_table(dev)
+        nz = noise.to(dev, th.float32).contiguous() if noise is not None else None
+        a.x_start, a.x_t, a.model_out, a.pred_xstart = xs.data_ptr(), xt.data_ptr(), mo.data_ptr(), pred.data_ptr()
+        a.noise = nz.data_ptr() if nz is not None else None
+        a.coef_dev, a.logvar_dev, a.t_idx_dev = coef.data_ptr(), self._coef_cache[key].data_ptr(), ti.data_ptr()
+        a.workspace, a.out = ws.data_ptr(), out.data_ptr()
+        with th.cuda.device(dev):
+            _lib.check(_lib.lib().s3d_vb_terms(C.byref(a), _lib.current_stream_ptr()))
+        return out, pred
+
+    def _vb_terms_bpd(self, model, x_start, x_t, t, clip_denoised=True, model_kwargs=None):
+        """:736-769.  {'output': [N] KL (decoder NLL where t == 0) in bits per dimension, 'pred_xstart'}."""
+        out, pred = self._vb_device(model, x_start, x_t, t, clip_denoised, model_kwargs)
+        return {"output": out[:, 0].clone(), "pred_xstart": pred}
+
+    def _prior_bpd(self, x_start):
+        """:858-874: KL(q(x_T | x_0) || N(0, I)) in bits per dimension (depends on the schedule only; tiny element-wise host
+        expression on the device tensor, evaluated once per calc_bpd_loop)."""
+        B = x_start.shape[0]
+        t = th.tensor([self.num_timesteps - 1] * B, device=x_start.device)
+        mean, _, logvar = self.q_mean_variance(x_start, t)
+        kl = 0.5 * (-1.0 - logvar + th.exp(logvar) + mean ** 2)
+        return kl.mean(dim=list(range(1, kl.dim()))) / np.log(2.0)
+
+    def calc_bpd_loop(self, model, x_start, clip_denoised=True, model_kwargs=None):
+        """:876-931.  Per step: q_sample (fused) -> model -> k_vb_terms (vb term + both MSEs in one pass)."""
+        dev = x_start.device
+        B = x_start.shape[0]
+        vb, xstart_mse, mse = [], [], []
+        for i in range(self.num_timesteps - 1, -1, -1):
+            t_batch = th.tensor([i] * B, device=dev)
+            noise = th.randn_like(x_start)
+            x_t = self.q_sample(x_start=x_start, t=t_batch, noise=noise)
+            with th.no_grad():
+                out, _ = self._vb_device(model, x_start, x_t, t_batch, clip_denoised, model_kwargs, noise=noise)
+            vb.append(out[:, 0])
+            xstart_mse.append(out[:, 1])
+            mse.append(out[:, 2])
+        vb, xstart_mse, mse = th.stack(vb, dim=1), th.stack(xstart_mse, dim=1), th.stack(mse, dim=1)
+        prior_bpd = self._prior_bpd(x_start)
+        return {"total_bpd": vb.sum(dim=1) + prior_bpd, "prior_bpd": prior_bpd, "vb": vb, "xstart_mse": xstart_mse,
+                "mse": mse}
+
     # ------------------------------------------------------------------ training objective (forward values)
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
         """:771-856, MSE branch: q_sample (fused kernel) -> model -> per-plane mean squared error."""
