@@ -224,7 +224,14 @@ int s3d_decoder_decode(s3d_decoder* d, const float* pts_dev, int64_t n, const fl
  * (utils3d.py:13-25), formed inside the kernel; out_dev [nx, ny, nz, 1 (+ tex_channels)]. */
 int s3d_decoder_decode_grid(s3d_decoder* d, const float* xs_dev, const float* ys_dev, const float* zs_dev, int nx, int ny, int nz,
                             const float aabb[6], int clamp_tex, float* out_dev, void* stream);
-/* Kernel launches issued by the last set_planes / decode call (bench accounting). */
+/* Encoder half (replaces AutoEncoderGroupSkip.encode, src/encoding/networks.py:164-180): vol_dev [1 (+ tex_channels), X, Y, Z]
+ * fp32 -> the three latent planes xy [C, H, W], xz [C, H, D], yz [C, W, D], C = geo (+ tex) feature channels and
+ * (H, W, D) = ((X-2)/2+1, (Y-2)/2+1, (Z-2)/2+1) (Conv3d k 4, stride 2, pad 1).  The strided convolutions, the three axis means
+ * (64-bit fixed-point sums: results do not depend on tile order), InstanceNorm2d and tanh(x/2) run in two launches; the
+ * [C, H, W, D] feature volume is never written.  Needs the geo_encoder.* (+ tex_encoder.*) tensors loaded. */
+int s3d_decoder_encode(s3d_decoder* d, const float* vol_dev, int X, int Y, int Z, float* xy_dev, float* xz_dev, float* yz_dev,
+                       void* stream);
+/* Kernel launches issued by the last set_planes / decode / encode call (bench accounting). */
 int s3d_decoder_last_launches(const s3d_decoder* d);
 /* Bring-up hook: the up-convolved feature plane `plane` as [rows][cols][64 (+64)] fp32 (geo channels first). Synchronises. */
 int s3d_decoder_planes_read(s3d_decoder* d, int plane, float* host_out, int64_t n_floats);

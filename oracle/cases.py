@@ -126,3 +126,27 @@ def make_bpd_inputs(case, n_steps):
     x0.view(-1)[5::23] = -1.0
     noises = {i: torch.randn(shape, generator=g) for i in range(n_steps - 1, -1, -1)}
     return x0, noises
+
+
+# ---------------------------------------------------------------------------- encoder
+ENCODER_CASES = {
+    # even / odd volume sizes (odd: the stride-2 conv drops the last voxel), not multiples of the kernel's tile
+    "default": dict(spec=dict(), wseed=91, XYZ=(22, 36, 70), seed=95),
+    "odd": dict(spec=dict(), wseed=92, XYZ=(15, 9, 33), seed=96),
+    "sdf_only": dict(spec=dict(use_tex=False, tex_feat_channels=0), wseed=93, XYZ=(12, 20, 16), seed=97),
+}
+
+
+def make_encoder_inputs(case):
+    """-> vol [1, 1 (+3), X, Y, Z]: a smooth signed-distance-like channel plus colour channels in [0, 1]."""
+    from oracle.decoder_ref import DecoderSpec
+    spec = DecoderSpec(**case["spec"])
+    X, Y, Z = case["XYZ"]
+    g = torch.Generator().manual_seed(case["seed"])
+    ax = [torch.linspace(-1, 1, n) for n in (X, Y, Z)]
+    gx, gy, gz = torch.meshgrid(*ax, indexing="ij")
+    sdf = (gx ** 2 + 0.7 * gy ** 2 + 1.3 * gz ** 2).sqrt() - 0.6 + 0.05 * torch.randn(X, Y, Z, generator=g)
+    chans = [sdf.clamp(-0.2, 0.2) / 0.2]
+    if spec.use_tex:
+        chans += [torch.rand(X, Y, Z, generator=g) for _ in range(spec.tex_channels)]
+    return torch.stack(chans, dim=0)[None].contiguous()

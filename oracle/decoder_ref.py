@@ -10,6 +10,7 @@ Functional fp32 restatement, over a flat ``state_dict`` with the reference's own
   * ``DecoderMLPSkipConcat.forward``          reference src/encoding/blocks.py:65-91
   * ``ShapeAutoEncoder.decode_batch / decode_grid``  reference src/encoding/model.py:319-349
   * ``sample_grid_points_aabb``               reference src/encoding/utils3d.py:13-25
+  * ``AutoEncoderGroupSkip.encode``           reference src/encoding/networks.py:164-180
 
 Written against plain ``torch.nn.functional`` on CPU tensors.  No module objects, no autograd.
 """
@@ -104,6 +105,16 @@ def synthetic_state_dict(spec: DecoderSpec, seed: int) -> Dict[str, torch.Tensor
                 fan_in *= s
             sd[k] = torch.randn(shp, generator=g) * (1.5 / fan_in ** 0.5)
     return sd
+
+
+# --------------------------------------------------------------------------- encoder
+def encode(sd, spec: DecoderSpec, vol):
+    """AutoEncoderGroupSkip.encode (networks.py:164-180): vol [1, 1 (+tex_channels), X, Y, Z] -> [xy, xz, yz] latent planes.
+    Conv3d(k 4, stride 2, pad 1) per branch, mean over one volume axis, InstanceNorm2d(eps 1e-5, no affine), tanh(x / 2)."""
+    feat = F.conv3d(vol[:, :1], sd["geo_encoder.weight"], sd["geo_encoder.bias"], stride=2, padding=1)
+    if spec.use_tex:
+        feat = torch.cat([feat, F.conv3d(vol, sd["tex_encoder.weight"], sd["tex_encoder.bias"], stride=2, padding=1)], dim=1)
+    return [(F.instance_norm(feat.mean(dim=d), eps=1e-5) * 0.5).tanh() for d in (4, 3, 2)]
 
 
 # --------------------------------------------------------------------------- feature planes

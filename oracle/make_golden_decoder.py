@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 from oracle import decoder_ref as de
-from oracle.cases import DECODER_CASES, make_decoder_inputs
+from oracle.cases import DECODER_CASES, ENCODER_CASES, make_decoder_inputs, make_encoder_inputs
 
 
 def ref_grid_fn():
@@ -81,6 +81,25 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"decoder_{name}.npz"), **save)
         print("decoder", name, "n", pts.shape[0], "oracle-vs-ref max abs", err, "out absmax", preds.abs().max().item(),
               "sdf range", preds[:, 0].min().item(), preds[:, 0].max().item())
+
+    # ---- encoder half (networks.py:164-180)
+    for name, case in ENCODER_CASES.items():
+        spec = de.DecoderSpec(**case["spec"])
+        sd = de.synthetic_state_dict(spec, case["wseed"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = AutoEncoderGroupSkip(spec.geo_feat_channels, spec.tex_feat_channels, spec.feat_channel_up,
+                                       spec.mlp_hidden_channels, spec.mlp_hidden_layers, use_tex=spec.use_tex,
+                                       tex_channels=spec.tex_channels)
+        net.load_state_dict(sd)
+        net.eval()
+        vol = make_encoder_inputs(case)
+        with torch.no_grad():
+            want = net.encode(vol)
+        got = de.encode(sd, spec, vol)
+        err = max((a - b).abs().max().item() for a, b in zip(want, got))
+        assert err <= 1e-6, (name, err)
+        np.savez_compressed(os.path.join(OUT, f"encoder_{name}.npz"), xy=want[0].numpy(), xz=want[1].numpy(), yz=want[2].numpy())
+        print("encoder", name, [tuple(w.shape) for w in want], "oracle-vs-ref max abs", err)
 
 
 if __name__ == "__main__":

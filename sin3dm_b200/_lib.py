@@ -98,6 +98,8 @@ _SIGNATURES = {
                                      C.c_void_p]),
     "s3d_decoder_decode_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(C.c_float), C.c_int, C.c_void_p, C.c_void_p]),
+    "s3d_decoder_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
     "s3d_decoder_last_launches": (C.c_int, [C.c_void_p]),
     "s3d_decoder_planes_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "s3d_unet_debug_count": (C.c_int, [C.c_void_p]),

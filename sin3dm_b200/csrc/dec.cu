@@ -65,6 +65,9 @@ struct s3d_decoder {
     int rows[3] = {0, 0, 0}, cols[3] = {0, 0, 0}, max_strips = 0;
     bool planes_set = false;
     int last_launches = 0;
+    // encoder: fixed-point axis sums of the current volume
+    unsigned long long* enc_sums = nullptr;
+    size_t enc_sums_count = 0;
 };
 
 namespace {
@@ -388,6 +391,62 @@ void decode(s3d_decoder* d, const DecPoints& P, int clamp_tex, float* out, cudaS
     d->last_launches = 1;
 }
 
+template <int GEO, int TEX, int CT>
+void launch_encode(s3d_decoder* d, const EncArgs& a, cudaStream_t st) {
+    static thread_local EncW<GEO, TEX, CT> w;        // ~9 KB of kernel parameters
+    std::memset(&w, 0, sizeof(w));
+    const auto& wg = T_(d, "geo_encoder.weight").host;            // [GEO][1][4][4][4]
+    const auto& bg = T_(d, "geo_encoder.bias").host;
+    for (int g = 0; g < GEO; ++g) {
+        std::copy(wg.begin() + g * 64, wg.begin() + (g + 1) * 64, w.wg[g]);
+        w.bias[g] = bg[g];
+    }
+    if (TEX > 0) {
+        const auto& wt = T_(d, "tex_encoder.weight").host;        // [TEX][CT][4][4][4]
+        const auto& bt = T_(d, "tex_encoder.bias").host;
+        for (int t = 0; t < TEX; ++t) {
+            for (int c = 0; c < CT; ++c) std::copy(wt.begin() + (t * CT + c) * 64, wt.begin() + (t * CT + c + 1) * 64, w.wt[t][c]);
+            w.bias[GEO + t] = bt[t];
+        }
+    }
+    constexpr int CV = CT > 0 ? CT : 1;
+    const size_t smem = (static_cast<size_t>(CV) * kEncIH * kEncIW * 2 * kEncZP + static_cast<size_t>(GEO + TEX) * 8 * 32) * sizeof(float);
+    CUDA_TRY(cudaFuncSetAttribute(k_enc_conv3d<GEO, TEX, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const dim3 grid((a.D + kEncTD - 1) / kEncTD, (a.W + kEncTW - 1) / kEncTW, (a.H + kEncTH - 1) / kEncTH);
+    S3D_CHECK(grid.y < 65536 && grid.z < 65536, "volume too large for one launch");
+    launch(k_enc_conv3d<GEO, TEX, CT>, grid, dim3(256), smem, st, w, a);
+    launch(k_enc_finalize, dim3(GEO + TEX, 3), dim3(256), 0, st, a);
+}
+
+// AutoEncoderGroupSkip.encode (networks.py:164-180)
+void encode(s3d_decoder* d, const float* vol, int X, int Y, int Z, float* xy, float* xz, float* yz, cudaStream_t st) {
+    S3D_CHECK(d->finalized, "s3d_decoder_finalize has not run");
+    S3D_CHECK(X >= 2 && Y >= 2 && Z >= 2, "volume must be at least 2 voxels along every axis");
+    const auto& c = d->cfg;
+    const int C = c.geo_feat_channels + (c.use_tex ? c.tex_feat_channels : 0);
+    EncArgs a{};
+    a.vol = vol;
+    a.X = X; a.Y = Y; a.Z = Z;
+    a.H = (X - 2) / 2 + 1; a.W = (Y - 2) / 2 + 1; a.D = (Z - 2) / 2 + 1;       // Conv3d(k 4, stride 2, pad 1)
+    const size_t n[3] = {static_cast<size_t>(a.H) * a.W, static_cast<size_t>(a.H) * a.D, static_cast<size_t>(a.W) * a.D};
+    const size_t total = C * (n[0] + n[1] + n[2]);
+    if (d->enc_sums_count < total) {
+        if (d->enc_sums) CUDA_TRY(cudaFree(d->enc_sums));
+        d->enc_sums = nullptr;
+        CUDA_TRY(cudaMalloc(&d->enc_sums, total * sizeof(unsigned long long)));
+        d->enc_sums_count = total;
+    }
+    CUDA_TRY(cudaMemsetAsync(d->enc_sums, 0, total * sizeof(unsigned long long), st));
+    a.sums[0] = d->enc_sums;
+    a.sums[1] = a.sums[0] + C * n[0];
+    a.sums[2] = a.sums[1] + C * n[1];
+    a.out[0] = xy; a.out[1] = xz; a.out[2] = yz;
+    if (c.geo_feat_channels == 4 && c.use_tex && c.tex_feat_channels == 8 && c.tex_channels == 3) launch_encode<4, 8, 4>(d, a, st);
+    else if (c.geo_feat_channels == 4 && !c.use_tex) launch_encode<4, 0, 0>(d, a, st);
+    else S3D_CHECK(false, "the encoder kernel is specialised for the reference defaults: fdim_geo 4 and (sdf only | fdim_tex 8 with rgb)");
+    d->last_launches = 2;
+}
+
 void fill_aabb(DecPoints& P, const float* aabb) {
     for (int i = 0; i < 3; ++i) {
         P.amin[i] = aabb[i];
@@ -446,6 +505,7 @@ int s3d_decoder_destroy(s3d_decoder* d) {
     cudaSetDevice(d->device);
     for (void* p : d->owned) cudaFree(p);
     for (void* p : d->plane_owned) cudaFree(p);
+    if (d->enc_sums) cudaFree(d->enc_sums);
     delete d;
     return 0;
 }
@@ -525,6 +585,15 @@ int s3d_decoder_decode_grid(s3d_decoder* d, const float* xs_dev, const float* ys
     P.n = static_cast<long long>(nx) * ny * nz;
     fill_aabb(P, aabb);
     decode(d, P, clamp_tex, out_dev, static_cast<cudaStream_t>(stream));
+    DEC_API_END
+}
+
+int s3d_decoder_encode(s3d_decoder* d, const float* vol_dev, int X, int Y, int Z, float* xy_dev, float* xz_dev, float* yz_dev,
+                       void* stream) {
+    DEC_API_BEGIN
+    S3D_CHECK(d && vol_dev && xy_dev && xz_dev && yz_dev, "null argument");
+    CUDA_TRY(cudaSetDevice(d->device));
+    encode(d, vol_dev, X, Y, Z, xy_dev, xz_dev, yz_dev, static_cast<cudaStream_t>(stream));
     DEC_API_END
 }
 

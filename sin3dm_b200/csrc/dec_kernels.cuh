@@ -719,4 +719,163 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Encoder half of the auto-encoder: volume -> latent planes.
+//   reference: AutoEncoderGroupSkip.encode, src/encoding/networks.py:164-180
+//     vol_feat = cat[Conv3d(1 -> GEO, k4 s2 p1)(vol[:, :1]), Conv3d(CT -> TEX, k4 s2 p1)(vol)]     [C, H, W, D]
+//     plane    = tanh(InstanceNorm2d(mean over one volume axis) / 2)                               xy / xz / yz
+// k_enc_conv3d never writes vol_feat: each thread forms the C conv outputs of one voxel (weights are FFMA constant-bank
+// operands: they travel as a kernel parameter and every index is a compile-time constant), and the CTA adds its tile's three
+// axis sums to 64-bit fixed-point accumulators (value * 2^40, integer atomics: exact, hence independent of the tile order).
+// Tile = 2 x 4 x 32 output voxels (thread = voxel, lane = z: the smem reads of a warp are unit-stride because the input tile
+// is stored de-interleaved in z), input tile 6 x 10 x 66 per volume channel staged in shared memory.
+// k_enc_finalize: one CTA per (plane, channel): axis mean, instance statistics in fp64, tanh.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kEncTH = 2, kEncTW = 4, kEncTD = 32;
+constexpr int kEncIH = 2 * kEncTH + 2, kEncIW = 2 * kEncTW + 2, kEncIZ = 2 * kEncTD + 2;       // 6, 10, 66
+constexpr int kEncZP = kEncIZ / 2;                                                               // 33 even + 33 odd
+constexpr double kEncFix = 1099511627776.0;                                                      // 2^40
+
+template <int GEO, int TEX, int CT>
+struct EncW {
+    float wg[GEO][64];                                  // [co][kx*16 + ky*4 + kz]
+    float wt[TEX > 0 ? TEX : 1][CT > 0 ? CT : 1][64];   // [co][ci][tap]
+    float bias[GEO + TEX];
+};
+struct EncArgs {
+    const float* vol;                 // [CV][X][Y][Z]
+    int X, Y, Z, H, W, D;             // volume and conv-output sizes
+    unsigned long long* sums[3];      // xy [C][H][W], xz [C][H][D], yz [C][W][D]
+    float* out[3];
+};
+
+template <int GEO, int TEX, int CT>
+__global__ void __launch_bounds__(256) k_enc_conv3d(const __grid_constant__ EncW<GEO, TEX, CT> Wt, const EncArgs A) {
+    constexpr int CV = CT > 0 ? CT : 1, C = GEO + TEX;
+    extern __shared__ float enc_smem[];
+    float* tile = enc_smem;                                        // [CV][IH][IW][2][ZP]
+    float* red = enc_smem + CV * kEncIH * kEncIW * 2 * kEncZP;     // [C][8][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d0 = blockIdx.x * kEncTD, w0 = blockIdx.y * kEncTW, h0 = blockIdx.z * kEncTH;
+    // ---- stage the input tile: one warp per (channel, x, y) row of 66 z values, zero padding outside the volume
+    const int iz0 = 2 * d0 - 1;
+    for (int row = warp; row < CV * kEncIH * kEncIW; row += 8) {
+        const int c = row / (kEncIH * kEncIW), rem = row - c * (kEncIH * kEncIW);
+        const int ix = 2 * h0 - 1 + rem / kEncIW, iy = 2 * w0 - 1 + rem % kEncIW;
+        const bool in = ix >= 0 && ix < A.X && iy >= 0 && iy < A.Y;
+        const float* src = A.vol + ((static_cast<size_t>(c) * A.X + (in ? ix : 0)) * A.Y + (in ? iy : 0)) * A.Z;
+        float* dst = tile + static_cast<size_t>(row) * 2 * kEncZP;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int j = lane + 32 * k;
+            if (j < kEncIZ) {
+                const int iz = iz0 + j;
+                dst[(j & 1) * kEncZP + (j >> 1)] = (in && iz >= 0 && iz < A.Z) ? __ldg(src + iz) : 0.f;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- one voxel per thread
+    const int hl = warp >> 2, wl = warp & 3;
+    const int h = h0 + hl, w = w0 + wl, d = d0 + lane;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = Wt.bias[c];
+#pragma unroll
+    for (int c = 0; c < CV; ++c)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+                const float* rowp = tile + ((static_cast<size_t>(c) * kEncIH + 2 * hl + kx) * kEncIW + 2 * wl + ky) * 2 * kEncZP + lane;
+#pragma unroll
+                for (int kz = 0; kz < 4; ++kz) {
+                    const float v = rowp[(kz & 1) * kEncZP + (kz >> 1)];
+                    const int tap = kx * 16 + ky * 4 + kz;
+                    if (c == 0) {
+#pragma unroll
+                        for (int g = 0; g < GEO; ++g) acc[g] = fmaf(v, Wt.wg[g][tap], acc[g]);
+                    }
+                    if (TEX > 0) {
+#pragma unroll
+                        for (int t = 0; t < TEX; ++t) acc[GEO + t] = fmaf(v, Wt.wt[t][c][tap], acc[GEO + t]);
+                    }
+                }
+            }
+    const bool valid = h < A.H && w < A.W && d < A.D;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        if (!valid) acc[c] = 0.f;
+        red[(c * 8 + warp) * 32 + lane] = acc[c];
+    }
+    // ---- xy: sum over z inside the warp (fixed butterfly), one atomic per (channel, h, w)
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float s = acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && h < A.H && w < A.W)
+            atomicAdd(A.sums[0] + (static_cast<size_t>(c) * A.H + h) * A.W + w,
+                      static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(s) * kEncFix)));
+    }
+    __syncthreads();
+    // ---- xz: sum over the tile's 4 y;  yz: over its 2 x  (fixed order), atomics coalesced along z
+    for (int i = threadIdx.x; i < C * kEncTH * 32; i += 256) {
+        const int c = i / (kEncTH * 32), r = i - c * (kEncTH * 32), th = r >> 5, z = r & 31;
+        const float* b = red + (c * 8 + th * 4) * 32 + z;
+        const float s = (b[0] + b[32]) + (b[64] + b[96]);
+        if (h0 + th < A.H && d0 + z < A.D)
+            atomicAdd(A.sums[1] + (static_cast<size_t>(c) * A.H + h0 + th) * A.D + d0 + z,
+                      static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(s) * kEncFix)));
+    }
+    for (int i = threadIdx.x; i < C * kEncTW * 32; i += 256) {
+        const int c = i / (kEncTW * 32), r = i - c * (kEncTW * 32), tw = r >> 5, z = r & 31;
+        const float* b = red + (c * 8 + tw) * 32 + z;
+        const float s = b[0] + b[4 * 32];
+        if (w0 + tw < A.W && d0 + z < A.D)
+            atomicAdd(A.sums[2] + (static_cast<size_t>(c) * A.W + w0 + tw) * A.D + d0 + z,
+                      static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(s) * kEncFix)));
+    }
+}
+
+// grid (C, 3), block 256
+__global__ void __launch_bounds__(256) k_enc_finalize(const EncArgs A) {
+    const int c = blockIdx.x, p = blockIdx.y;
+    const int rows = p == 2 ? A.W : A.H, cols = p == 0 ? A.W : A.D;
+    const int n = rows * cols;
+    const float len = static_cast<float>(p == 0 ? A.D : (p == 1 ? A.W : A.H));     // length of the averaged axis
+    const unsigned long long* s = A.sums[p] + static_cast<size_t>(c) * n;
+    float* o = A.out[p] + static_cast<size_t>(c) * n;
+    __shared__ double sh[8];
+    __shared__ double stat[2];
+    auto val = [&](int i) { return static_cast<float>(static_cast<double>(static_cast<long long>(s[i])) * (1.0 / kEncFix)) / len; };
+    auto block_sum = [&](double v) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k];
+        return t;
+    };
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) a += static_cast<double>(val(i));
+    const double mean = block_sum(a) / n;
+    a = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double dv = static_cast<double>(val(i)) - mean;
+        a += dv * dv;
+    }
+    const double var = block_sum(a) / n;                       // biased (InstanceNorm2d)
+    if (threadIdx.x == 0) {
+        stat[0] = mean;
+        stat[1] = 1.0 / sqrt(var + 1e-5);
+    }
+    __syncthreads();
+    const float mu = static_cast<float>(stat[0]), rstd = static_cast<float>(stat[1]);
+    for (int i = threadIdx.x; i < n; i += 256) o[i] = tanhf(((val(i) - mu) * rstd) * 0.5f);
+}
+
 }  // namespace s3d

@@ -6,8 +6,8 @@
 
 ``AutoEncoderGroupSkip`` keeps the reference constructor signature, parameter names (so a reference ``.pt`` loads with
 ``load_state_dict``) and ``decode`` / ``reset_aabb``; the arithmetic runs in ``libsin3dm_b200.so`` (``s3d_decoder_*``,
-include/sin3dm_b200.h).  The encoder half (``encode``: Conv3d + axis means) is out of scope: its
-parameters are held so checkpoints round-trip, calling it raises.  There is no CPU / torch fallback.
+include/sin3dm_b200.h), including the encoder half (``encode``: Conv3d + axis means + InstanceNorm + tanh, SURVEY §8(f)
+rank 3, ``s3d_decoder_encode``).  Inference only (no autograd).  There is no CPU / torch fallback.
 """
 import ctypes as C
 import os
@@ -115,8 +115,23 @@ class AutoEncoderGroupSkip(nn.Module):
         self.aabb = aabb.to(self.geo_encoder.weight.device)
 
     def encode(self, vol):
-        raise NotImplementedError("the encoder (Conv3d + axis means, networks.py:164-180) is outside the sampling/decoding "
-                                  "path this library replaces (SURVEY §8(f) rank 3)")
+        """vol [1, 1 (+ tex_channels), X, Y, Z] -> [xy [1,C,H,W], xz [1,C,H,D], yz [1,C,W,D]]  (networks.py:164-180).
+        Inference only: strided Conv3d + axis means + InstanceNorm2d + tanh(x/2) in two launches (s3d_decoder_encode)."""
+        h = self.handle()
+        dev = self.geo_encoder.weight.device
+        cv = 1 + (self.tex_channels if self.use_tex else 0)
+        if vol.dim() != 5 or vol.shape[0] != 1 or vol.shape[1] != cv:
+            raise ValueError(f"vol must have shape [1, {cv}, X, Y, Z]; got {tuple(vol.shape)}")
+        v = vol.detach().to(dev, torch.float32).contiguous()
+        X, Y, Z = v.shape[2:]
+        H, W, D = ((n - 2) // 2 + 1 for n in (X, Y, Z))
+        c = self.geo_feat_dim + (self.tex_feat_dim if self.use_tex else 0)
+        xy, xz, yz = (torch.empty(1, c, a, b, device=dev, dtype=torch.float32) for a, b in ((H, W), (H, D), (W, D)))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().s3d_decoder_encode(h, C.c_void_p(v.data_ptr()), X, Y, Z, C.c_void_p(xy.data_ptr()),
+                                                     C.c_void_p(xz.data_ptr()), C.c_void_p(yz.data_ptr()),
+                                                     _lib.current_stream_ptr()))
+        return [xy, xz, yz]
 
     def forward(self, vol, x, aabb=None):
         return self.decode(x, self.encode(vol), aabb=aabb)

@@ -115,3 +115,57 @@ def test_empty_and_single_point():
     assert net.decode(torch.zeros(0, 3).cuda(), maps).shape == (0, 4)
     one = net.decode(torch.zeros(1, 3).cuda(), maps)
     assert one.shape == (1, 4) and torch.isfinite(one).all()
+
+
+# ------------------------------------------------------------------------------------------------ encoder half
+@pytest.mark.parametrize("name", ["default", "odd", "sdf_only"])
+def test_encode_matches_reference_golden(golden_dir, name):
+    """AutoEncoderGroupSkip.encode (networks.py:164-180) through s3d_decoder_encode vs the real reference's planes."""
+    from oracle.cases import ENCODER_CASES, make_encoder_inputs
+    case = ENCODER_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"encoder_{name}.npz"))
+    spec = de.DecoderSpec(**case["spec"])
+    net = make_net(spec, de.synthetic_state_dict(spec, case["wseed"]))
+    vol = make_encoder_inputs(case)
+    got = net.encode(vol.cuda())
+    for pl, a in zip(de.PLANES, got):
+        w = g[pl]
+        assert tuple(a.shape) == w.shape
+        err = np.abs(a.cpu().numpy() - w).max()
+        print(name, pl, "max abs", err)
+        assert err < 2e-5, (name, pl, err)              # outputs are tanh values in (-1, 1): absolute == relative to full scale
+    # fixed-point axis sums: a second run is bit-identical
+    again = net.encode(vol.cuda())
+    assert all(torch.equal(a, b) for a, b in zip(got, again))
+
+
+def test_encode_then_decode_round_trip_runs_through_forward():
+    """forward(vol, x) = decode(x, encode(vol)) (networks.py:222-224) against the oracle chain at the default-latent scale."""
+    from oracle.cases import ENCODER_CASES, make_encoder_inputs
+    case = ENCODER_CASES["default"]
+    spec = de.DecoderSpec(**case["spec"])
+    sd = de.synthetic_state_dict(spec, case["wseed"])
+    net = make_net(spec, sd)
+    vol = make_encoder_inputs(case)
+    g = torch.Generator().manual_seed(3)
+    pts = torch.rand(500, 3, generator=g) * 2 - 1
+    want = de.decode(sd, spec, pts, de.encode(sd, spec, vol))
+    got = net(vol.cuda(), pts.cuda()).cpu()
+    rel, mx = errors(got, want)
+    assert rel < TOL_SPLIT * 5 and mx < TOL, (rel, mx)
+
+
+def test_encode_full_size_properties():
+    """BASELINE-size volume (184 x 256 x 184 -> the cfg2 latent 92 x 128 x 92): shapes, range, finiteness, and the
+    InstanceNorm invariant atanh(2*plane) has zero mean / unit variance per channel."""
+    spec = de.DecoderSpec()
+    net = make_net(spec, de.synthetic_state_dict(spec, 7))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    vol = torch.rand(1, 4, 184, 256, 184, device="cuda", generator=g) * 2 - 1
+    planes = net.encode(vol)
+    assert [tuple(p.shape) for p in planes] == [(1, 12, 92, 128), (1, 12, 92, 92), (1, 12, 128, 92)]
+    for p in planes:
+        assert torch.isfinite(p).all() and p.abs().max() < 1
+        y = 2 * torch.atanh(p.double())
+        assert y.mean(dim=(2, 3)).abs().max() < 1e-4
+        assert (y.var(dim=(2, 3), unbiased=False) - 1).abs().max() < 1e-3

@@ -123,8 +123,8 @@ def test_decoder_state_dict_layout(use_tex):
     assert (m2.geo_convs.out_layers[1].weight == 0).all()
     with pytest.raises(_lib.S3DError), torch.no_grad():
         m.decode(torch.zeros(4, 3), [torch.zeros(1, spec.geo_feat_channels + spec.tex_feat_channels, 8, 8)] * 3)
-    with pytest.raises(NotImplementedError):
-        m.encode(torch.zeros(1, 4, 8, 8, 8))
+    with pytest.raises(_lib.S3DError), torch.no_grad():        # encode runs on the GPU only, like decode
+        m.encode(torch.zeros(1, 4 if use_tex else 1, 8, 8, 8))
 
 
 def test_grid_axes_match_oracle():

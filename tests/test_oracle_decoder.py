@@ -43,3 +43,17 @@ def test_hoisted_planes_equal_per_chunk_recompute():
     a = de.decode_batch(sd, spec, maps, pts, batch_size=128, aabb=aabb, hoist=True)
     b = de.decode_batch(sd, spec, maps, pts, batch_size=128, aabb=aabb, hoist=False)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["default", "odd", "sdf_only"])
+def test_encoder_oracle_matches_reference(golden_dir, name):
+    """oracle encode (networks.py:164-180 restated) against the planes the real reference produced."""
+    from oracle.cases import ENCODER_CASES, make_encoder_inputs
+    case = ENCODER_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"encoder_{name}.npz"))
+    spec = de.DecoderSpec(**case["spec"])
+    sd = de.synthetic_state_dict(spec, case["wseed"])
+    planes = de.encode(sd, spec, make_encoder_inputs(case))
+    for pl, a in zip(de.PLANES, planes):
+        assert a.shape == g[pl].shape
+        assert np.abs(a.numpy() - g[pl]).max() <= 1e-6
