@@ -157,7 +157,7 @@ def test_encode_then_decode_round_trip_runs_through_forward():
 
 def test_encode_full_size_properties():
     """BASELINE-size volume (184 x 256 x 184 -> the cfg2 latent 92 x 128 x 92): shapes, range, finiteness, and the
-    InstanceNorm invariant atanh(2*plane) has zero mean / unit variance per channel."""
+    InstanceNorm invariant: 2*atanh(plane) has zero mean and variance var/(var+eps) per channel."""
     spec = de.DecoderSpec()
     net = make_net(spec, de.synthetic_state_dict(spec, 7))
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -168,4 +168,5 @@ def test_encode_full_size_properties():
         assert torch.isfinite(p).all() and p.abs().max() < 1
         y = 2 * torch.atanh(p.double())
         assert y.mean(dim=(2, 3)).abs().max() < 1e-4
-        assert (y.var(dim=(2, 3), unbiased=False) - 1).abs().max() < 1e-3
+        v = y.var(dim=(2, 3), unbiased=False)             # = var / (var + 1e-5): just below 1
+        assert v.max() <= 1 + 1e-6 and v.min() > 0.99
