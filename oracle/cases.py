@@ -134,6 +134,8 @@ ENCODER_CASES = {
     "default": dict(spec=dict(), wseed=91, XYZ=(22, 36, 70), seed=95),
     "odd": dict(spec=dict(), wseed=92, XYZ=(15, 9, 33), seed=96),
     "sdf_only": dict(spec=dict(use_tex=False, tex_feat_channels=0), wseed=93, XYZ=(12, 20, 16), seed=97),
+    # Z % 4 == 0 with colour: the TMA-staged kernel, several z tiles with a ragged last one
+    "aligned": dict(spec=dict(), wseed=94, XYZ=(10, 14, 148), seed=98),
 }
 
 

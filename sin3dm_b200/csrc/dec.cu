@@ -414,8 +414,19 @@ void launch_encode(s3d_decoder* d, const EncArgs& a, cudaStream_t st) {
     CUDA_TRY(cudaFuncSetAttribute(k_enc_conv3d<GEO, TEX, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const dim3 grid((a.D + kEncTD - 1) / kEncTD, (a.W + kEncTW - 1) / kEncTW, (a.H + kEncTH - 1) / kEncTH);
     S3D_CHECK(grid.y < 65536 && grid.z < 65536, "volume too large for one launch");
-    launch(k_enc_conv3d<GEO, TEX, CT>, grid, dim3(256), smem, st, w, a);
-    launch(k_enc_finalize, dim3(GEO + TEX, 3), dim3(256), 0, st, a);
+    if (a.Z % 4 == 0 && (reinterpret_cast<uintptr_t>(a.vol) & 15) == 0) {
+        // 16-byte global strides: the input tile is one TMA box
+        CUtensorMap vmap;
+        const uint64_t dims[4] = {static_cast<uint64_t>(a.Z), static_cast<uint64_t>(a.Y), static_cast<uint64_t>(a.X), static_cast<uint64_t>(CV)};
+        const uint32_t box[4] = {kEncZPitch, kEncIW, kEncIH, CV};
+        make_tmap_f32(&vmap, a.vol, 4, dims, box);
+        const size_t smem_t = (static_cast<size_t>(CV) * kEncIH * kEncIW * kEncZPitch + static_cast<size_t>(GEO + TEX) * 8 * 32) * sizeof(float) + 16;
+        CUDA_TRY(cudaFuncSetAttribute(k_enc_conv3d_tma<GEO, TEX, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t)));
+        launch(k_enc_conv3d_tma<GEO, TEX, CT>, grid, dim3(128), smem_t, st, vmap, w, a);
+    } else {
+        launch(k_enc_conv3d<GEO, TEX, CT>, grid, dim3(256), smem, st, w, a);
+    }
+    launch(k_enc_finalize, dim3(GEO + TEX, 3), dim3(kEncFinThreads), 0, st, a);
 }
 
 // AutoEncoderGroupSkip.encode (networks.py:164-180)

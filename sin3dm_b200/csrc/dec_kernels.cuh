@@ -769,11 +769,17 @@ __global__ void __launch_bounds__(256) k_enc_conv3d(const __grid_constant__ EncW
         for (int k = 0; k < 3; ++k) {
             const int j = lane + 32 * k;
             if (j < kEncIZ) {
+                // asynchronous 4-byte copies (zero-filled outside the volume): every row of the tile is in flight at once
                 const int iz = iz0 + j;
-                dst[(j & 1) * kEncZP + (j >> 1)] = (in && iz >= 0 && iz < A.Z) ? __ldg(src + iz) : 0.f;
+                const bool ok = in && iz >= 0 && iz < A.Z;
+                const unsigned sz = ok ? 4u : 0u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ptx::smem_u32(dst + (j & 1) * kEncZP + (j >> 1))),
+                             "l"(ok ? src + iz : A.vol), "r"(sz) : "memory");
             }
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- one voxel per thread
     const int hl = warp >> 2, wl = warp & 3;
@@ -838,15 +844,114 @@ __global__ void __launch_bounds__(256) k_enc_conv3d(const __grid_constant__ EncW
     }
 }
 
-// grid (C, 3), block 256
-__global__ void __launch_bounds__(256) k_enc_finalize(const EncArgs A) {
+// k_enc_conv3d_tma: the same tile, staged by ONE 4-D TMA box {72 z, 10 y, 6 x, CV} (out-of-volume elements are the TMA unit's
+// zero fill == the conv's padding, no index arithmetic in the kernel), natural z order in shared memory.  128 threads, each
+// forms two z-adjacent voxels from three shared loads per (channel, kx, ky): 4608 FFMA per 192 loads.
+// Needs Z % 4 == 0 (16-byte global strides); other volumes take k_enc_conv3d.  Measured on B200 (tools/probe/tma_f32_probe.cu):
+// with INTERLEAVE_NONE the innermost TMA coordinate must be a multiple of 16 bytes (z0 = -1 raises "illegal instruction"), so
+// the box starts at z = 2*d0 - 4 and the window of a thread sits 3 floats into it.
+constexpr int kEncZPitch = 72;
+template <int GEO, int TEX, int CT>
+__global__ void __launch_bounds__(128) k_enc_conv3d_tma(const __grid_constant__ CUtensorMap vmap,
+                                                        const __grid_constant__ EncW<GEO, TEX, CT> Wt, const EncArgs A) {
+    constexpr int CV = CT > 0 ? CT : 1, C = GEO + TEX;
+    constexpr uint32_t kTileBytes = CV * kEncIH * kEncIW * kEncZPitch * 4;
+    extern __shared__ __align__(128) float enc_smem_t[];
+    float* tile = enc_smem_t;                                  // [CV][IH][IW][72]
+    float* red = enc_smem_t + kTileBytes / 4;                  // [C][8][32]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + C * 8 * 32);
+    const int d0 = blockIdx.x * kEncTD, w0 = blockIdx.y * kEncTW, h0 = blockIdx.z * kEncTH;
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(bar, 1);
+        ptx::fence_barrier_init();
+        ptx::mbar_arrive_expect_tx(bar, kTileBytes);
+        ptx::tma_load_4d(tile, &vmap, bar, 2 * d0 - 4, 2 * w0 - 1, 2 * h0 - 1, 0);
+    }
+    __syncthreads();
+    ptx::mbar_wait(bar, 0);
+    const int combo = threadIdx.x >> 4, L = threadIdx.x & 15;
+    const int hl = combo >> 2, wl = combo & 3;
+    const int h = h0 + hl, w = w0 + wl, d = d0 + 2 * L;
+    float acc0[C], acc1[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc0[c] = acc1[c] = Wt.bias[c];
+#pragma unroll
+    for (int c = 0; c < CV; ++c)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+                // inputs z = 2*d - 1 .. 2*d + 4 of the pair = floats 4L+3 .. 4L+8 of the row
+                const float* rowp = tile + ((c * kEncIH + 2 * hl + kx) * kEncIW + 2 * wl + ky) * kEncZPitch + 4 * L;
+                const float a0 = rowp[3];
+                const float4 a = *reinterpret_cast<const float4*>(rowp + 4);
+                const float a5 = rowp[8];
+                const float in[6] = {a0, a.x, a.y, a.z, a.w, a5};
+#pragma unroll
+                for (int kz = 0; kz < 4; ++kz) {
+                    const int tap = kx * 16 + ky * 4 + kz;
+                    if (c == 0) {
+#pragma unroll
+                        for (int g = 0; g < GEO; ++g) {
+                            acc0[g] = fmaf(in[kz], Wt.wg[g][tap], acc0[g]);
+                            acc1[g] = fmaf(in[kz + 2], Wt.wg[g][tap], acc1[g]);
+                        }
+                    }
+                    if (TEX > 0) {
+#pragma unroll
+                        for (int t = 0; t < TEX; ++t) {
+                            acc0[GEO + t] = fmaf(in[kz], Wt.wt[t][c][tap], acc0[GEO + t]);
+                            acc1[GEO + t] = fmaf(in[kz + 2], Wt.wt[t][c][tap], acc1[GEO + t]);
+                        }
+                    }
+                }
+            }
+    const bool hw_ok = h < A.H && w < A.W;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        if (!(hw_ok && d < A.D)) acc0[c] = 0.f;
+        if (!(hw_ok && d + 1 < A.D)) acc1[c] = 0.f;
+        *reinterpret_cast<float2*>(red + (c * 8 + combo) * 32 + 2 * L) = make_float2(acc0[c], acc1[c]);
+    }
+    // ---- xy: sum over the tile's 32 z (pair, then a fixed butterfly over the 16 lanes of the (h, w) group)
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float s = acc0[c] + acc1[c];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (L == 0 && hw_ok)
+            atomicAdd(A.sums[0] + (static_cast<size_t>(c) * A.H + h) * A.W + w,
+                      static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(s) * kEncFix)));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * kEncTH * 32; i += 128) {
+        const int c = i / (kEncTH * 32), r = i - c * (kEncTH * 32), th = r >> 5, z = r & 31;
+        const float* b = red + (c * 8 + th * 4) * 32 + z;
+        const float s = (b[0] + b[32]) + (b[64] + b[96]);
+        if (h0 + th < A.H && d0 + z < A.D)
+            atomicAdd(A.sums[1] + (static_cast<size_t>(c) * A.H + h0 + th) * A.D + d0 + z,
+                      static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(s) * kEncFix)));
+    }
+    for (int i = threadIdx.x; i < C * kEncTW * 32; i += 128) {
+        const int c = i / (kEncTW * 32), r = i - c * (kEncTW * 32), tw = r >> 5, z = r & 31;
+        const float* b = red + (c * 8 + tw) * 32 + z;
+        const float s = b[0] + b[4 * 32];
+        if (w0 + tw < A.W && d0 + z < A.D)
+            atomicAdd(A.sums[2] + (static_cast<size_t>(c) * A.W + w0 + tw) * A.D + d0 + z,
+                      static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(s) * kEncFix)));
+    }
+}
+
+// grid (C, 3), block 1024: the plane's values are formed once and kept in registers (<= 16 per thread covers 128 x 128)
+constexpr int kEncFinThreads = 1024, kEncFinKeep = 16;
+__global__ void __launch_bounds__(kEncFinThreads) k_enc_finalize(const EncArgs A) {
     const int c = blockIdx.x, p = blockIdx.y;
     const int rows = p == 2 ? A.W : A.H, cols = p == 0 ? A.W : A.D;
     const int n = rows * cols;
     const float len = static_cast<float>(p == 0 ? A.D : (p == 1 ? A.W : A.H));     // length of the averaged axis
     const unsigned long long* s = A.sums[p] + static_cast<size_t>(c) * n;
     float* o = A.out[p] + static_cast<size_t>(c) * n;
-    __shared__ double sh[8];
+    __shared__ double sh[32];
     __shared__ double stat[2];
     auto val = [&](int i) { return static_cast<float>(static_cast<double>(static_cast<long long>(s[i])) * (1.0 / kEncFix)) / len; };
     auto block_sum = [&](double v) {
@@ -857,14 +962,27 @@ __global__ void __launch_bounds__(256) k_enc_finalize(const EncArgs A) {
         __syncthreads();
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += sh[k];
+        for (int k = 0; k < kEncFinThreads / 32; ++k) t += sh[k];
         return t;
     };
+    float keep[kEncFinKeep];
+#pragma unroll
+    for (int k = 0; k < kEncFinKeep; ++k) {
+        const int i = threadIdx.x + k * kEncFinThreads;
+        keep[k] = i < n ? val(i) : 0.f;
+    }
     double a = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) a += static_cast<double>(val(i));
+#pragma unroll
+    for (int k = 0; k < kEncFinKeep; ++k) a += static_cast<double>(keep[k]);            // zeros beyond n
+    for (int i = threadIdx.x + kEncFinKeep * kEncFinThreads; i < n; i += kEncFinThreads) a += static_cast<double>(val(i));
     const double mean = block_sum(a) / n;
     a = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) {
+#pragma unroll
+    for (int k = 0; k < kEncFinKeep; ++k) {
+        const double dv = static_cast<double>(keep[k]) - mean;
+        if (threadIdx.x + k * kEncFinThreads < n) a += dv * dv;
+    }
+    for (int i = threadIdx.x + kEncFinKeep * kEncFinThreads; i < n; i += kEncFinThreads) {
         const double dv = static_cast<double>(val(i)) - mean;
         a += dv * dv;
     }
@@ -875,7 +993,12 @@ __global__ void __launch_bounds__(256) k_enc_finalize(const EncArgs A) {
     }
     __syncthreads();
     const float mu = static_cast<float>(stat[0]), rstd = static_cast<float>(stat[1]);
-    for (int i = threadIdx.x; i < n; i += 256) o[i] = tanhf(((val(i) - mu) * rstd) * 0.5f);
+#pragma unroll
+    for (int k = 0; k < kEncFinKeep; ++k) {
+        const int i = threadIdx.x + k * kEncFinThreads;
+        if (i < n) o[i] = tanhf(((keep[k] - mu) * rstd) * 0.5f);
+    }
+    for (int i = threadIdx.x + kEncFinKeep * kEncFinThreads; i < n; i += kEncFinThreads) o[i] = tanhf(((val(i) - mu) * rstd) * 0.5f);
 }
 
 }  // namespace s3d

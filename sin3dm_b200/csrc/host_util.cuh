@@ -83,6 +83,24 @@ inline void make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t
     if (r != CUDA_SUCCESS) throw S3dError{"cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))};
 }
 
+// dense fp32 tensor, dims innermost-first, no swizzle, zero OOB fill (row bytes of the box must be a multiple of 16)
+inline void make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t bx[5], es[5];
+    uint64_t stride = 4;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstride[i] = stride;
+    }
+    CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gdim, gstride, bx, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw S3dError{"cuTensorMapEncodeTiled (fp32) failed with CUresult " + std::to_string(static_cast<int>(r))};
+}
+
 // same, with explicit byte strides for dims 1..rank-1
 inline void make_tmap_strided(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                               const uint32_t* box) {

@@ -133,11 +133,88 @@ def run(reso=256, iters=5, cpu_baseline=True, precision=3, device=0):
     return line
 
 
+def run_encode(iters=10, cpu_baseline=True, device=0):
+    """Encoder half (AutoEncoderGroupSkip.encode): the 184 x 256 x 184 sdf+rgb volume of the cfg2 latent -> three planes."""
+    import torch
+    from oracle import decoder_ref as de
+    from sin3dm_b200.encoding import AutoEncoderGroupSkip
+    import bench as B
+
+    torch.cuda.set_device(device)
+    spec = de.DecoderSpec()
+    sd = de.synthetic_state_dict(spec, 1234)
+    net = AutoEncoderGroupSkip(4, 8, 64, 256, 4, use_tex=True, tex_channels=3)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    X, Y, Z = 184, 256, 184
+    g = torch.Generator().manual_seed(0)
+    host_vol = (torch.rand(1, 4, X, Y, Z, generator=g) * 2 - 1).pin_memory()
+    vol = host_vol.cuda()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        planes = net.encode(vol)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        planes = net.encode(vol)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    host_out = [torch.empty(p.shape).pin_memory() for p in planes]
+
+    def e2e_once():
+        v = host_vol.to("cuda", non_blocking=True)
+        for h, p in zip(host_out, net.encode(v)):
+            h.copy_(p, non_blocking=True)
+    e2e_once()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        e2e_once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / iters
+    peaks = B.load_peaks()
+    H, W, D = X // 2, Y // 2, Z // 2
+    nvox = H * W * D
+    in_bytes = host_vol.numel() * 4
+    out_bytes = sum(p.numel() for p in planes) * 4
+    flops = 2.0 * nvox * (64 * 4 + 64 * 4 * 8)
+    gbs = (in_bytes + out_bytes) / (ms * 1e-3) / 1e9
+    line = dict(metric="volume encode output voxels/sec (AutoEncoderGroupSkip.encode)", value=nvox / (ms * 1e-3), unit="voxels/s",
+                n_gpus=1, steps=iters, ms_per_step=ms, higher_is_better=True, data="synthetic", dtype="f32",
+                config=dict(workload=f"encode: sdf+rgb volume 4 x {X} x {Y} x {Z} -> planes 12 x ({H},{W},{D})", voxels=nvox,
+                            gflop=flops / 1e9, fp32_tflops=flops / (ms * 1e-3) / 1e12),
+                e2e=dict(value=nvox / (ms_e2e * 1e-3), unit="voxels/s", ms=ms_e2e, h2d_bytes_per_step=in_bytes,
+                         d2h_bytes_per_step=out_bytes, api="AutoEncoderGroupSkip.encode (host volume -> host planes)"),
+                gpu_launches=2 * iters, launches_per_step=2,
+                roofline=dict(bound="hbm", kernel="k_enc_conv3d", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
+                              traffic=None, note="algorithmic bytes = the volume read once + the three planes written "
+                              f"({(in_bytes + out_bytes) / 1e6:.1f} MB); the kernel also executes {flops / 1e9:.2f} GFLOP of fp32 FFMA "
+                              "(2304 per output voxel), which is what bounds it on the CUDA cores",
+                              peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peaks['src']})"))
+    if cpu_baseline:
+        torch.set_num_threads(min(os.cpu_count() or 1, 32))
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            want = de.encode(sd, spec, host_vol)
+            dt = time.perf_counter() - t0
+        err = max(float((a.cpu() - b).abs().max()) for a, b in zip(planes, want))
+        line["cpu_baseline"] = dict(value=nvox / dt, unit="voxels/s", cores=torch.get_num_threads(), kind="port",
+                                    sample=f"one full encode of the same volume ({dt:.2f} s)")
+        line["parity_vs_oracle_max_abs"] = err
+    return line
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
+    ap.add_argument("--encode", action="store_true", help="benchmark the encoder half instead of decode_grid")
     ap.add_argument("--reso", type=int, default=256)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--precision", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    if a.encode:
+        print(json.dumps(run_encode(a.iters, not a.no_cpu_baseline)), flush=True)
+        sys.exit(0)
     print(json.dumps(run(a.reso, a.iters, not a.no_cpu_baseline, a.precision)), flush=True)
