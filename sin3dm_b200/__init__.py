@@ -10,9 +10,10 @@ raises if it is missing — there is no CPU / torch fallback.
 from .gaussian_diffusion import (GaussianDiffusion, LossType, ModelMeanType, ModelVarType,  # noqa: F401
                                  get_named_beta_schedule)
 from .respace import SpacedDiffusion, space_timesteps  # noqa: F401
-from .triplane_util import compose_featmaps, decompose_featmaps  # noqa: F401
+from .triplane_util import (compose_featmaps, decompose_featmaps, load_triplane_data, pad_composed_featmaps,  # noqa: F401
+                            save_triplane_data)
 from .unet_triplane import TriplaneUNetModelSmall, TriplaneUNetModelSmallRaw  # noqa: F401
 
 __all__ = ["GaussianDiffusion", "SpacedDiffusion", "space_timesteps", "TriplaneUNetModelSmall",
            "TriplaneUNetModelSmallRaw", "ModelMeanType", "ModelVarType", "LossType", "get_named_beta_schedule",
-           "compose_featmaps", "decompose_featmaps"]
+           "compose_featmaps", "decompose_featmaps", "pad_composed_featmaps", "save_triplane_data", "load_triplane_data"]

@@ -134,3 +134,28 @@ def test_grid_axes_match_oracle():
         a = torch.tensor(aabb, dtype=torch.float32)
         for u, v in zip(sample_grid_points_axes(a, reso), de.grid_axes(a, reso)):
             assert torch.equal(u, v)
+
+
+def test_triplane_io_round_trip_and_pad(tmp_path):
+    """save/load_triplane_data and pad_composed_featmaps (reference src/utils/triplane_util.py:28-61) against the reference's
+    definitions restated inline: npz keys feat_xy/xz/yz, compose on load, zero padding per plane."""
+    import numpy as np
+    import sin3dm_b200 as s3
+    g = torch.Generator().manual_seed(0)
+    H, W, D, C = 5, 7, 4, 3
+    xy, xz, yz = torch.randn(C, H, W, generator=g), torch.randn(C, H, D, generator=g), torch.randn(C, W, D, generator=g)
+    p = str(tmp_path / "sub" / "feat.npz")
+    s3.save_triplane_data(p, xy, xz, yz)
+    assert sorted(np.load(p).files) == ["feat_xy", "feat_xz", "feat_yz"]
+    comp, sizes = s3.load_triplane_data(p, device="cpu")
+    assert sizes == (H, W, D) and comp.shape == (C, H + D, W + D)
+    a, b, c = s3.decompose_featmaps(comp, sizes)
+    assert torch.equal(a, xy) and torch.equal(b, xz) and torch.equal(c, yz)
+    assert (comp[..., H:, W:] == 0).all()
+    planes = s3.load_triplane_data(p, device="cpu", compose=False)
+    assert torch.equal(planes[2], yz)
+    padded, ns = s3.pad_composed_featmaps(comp, sizes, [[1, 2], [0, 3], [2, 0]])
+    assert ns == (H + 3, W + 3, D + 2)
+    pa, pb, pc = s3.decompose_featmaps(padded, ns)
+    assert torch.equal(pa[..., 1:1 + H, 0:W], xy) and int((pa != 0).sum()) == int((xy != 0).sum())
+    assert torch.equal(pb[..., 1:1 + H, 2:2 + D], xz) and torch.equal(pc[..., 0:W, 2:2 + D], yz)
