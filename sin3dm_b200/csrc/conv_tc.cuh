@@ -30,7 +30,8 @@ constexpr int kBM = 128, kBN = 64, kBK = 64;
 constexpr int kABytes = kBM * kBK * 2;             // 16 KiB: plain 128-row A tile (skip / rollout groups)
 constexpr int kAHaloBytes = kHaloH * kHaloW * kBK * 2;   // 36 KiB: halo patch of one 64-channel block
 constexpr int kBBytes = kBN * kBK * 2;             //  8 KiB
-constexpr int kConvThreads = 224;                  // warps: 0 A-producer, 1 MMA, 2..5 epilogue, 6 B-producer
+constexpr int kConvThreads = 352;                  // warps: 0 A-producer, 1 MMA, 2..9 epilogue, 10 B-producer
+constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;
 constexpr int kRollThreads = 192;
 
 struct ConvTcMaps {
@@ -84,11 +85,11 @@ struct ConvTcCfg {
     static constexpr int kASlotBytes = (NSPLIT == 3 ? 2 : 1) * kAHaloBytes;   // hi at +0, lo at +kAHaloBytes
     static constexpr int kBSlotBytes = (NSPLIT == 3 ? 2 : 1) * kBBytes;       // hi at +0, lo at +kBBytes
     static constexpr int kASlots = 2;
-    static constexpr int kBSlots = NSPLIT == 3 ? 4 : 8;
+    static constexpr int kBSlots = NSPLIT == 3 ? 3 : 8;     // 3 x 16 KiB: the fourth slot's 16 KiB went to the epilogue staging of warps 6..9
     static constexpr int kRingBytes = kASlots * kASlotBytes + kBSlots * kBSlotBytes;
     static constexpr int kAccCols = NSPLIT == 3 ? 128 : 64;     // TMEM columns of one accumulator stage
     static constexpr int kTmemCols = 2 * kAccCols;              // double-buffered accumulators
-    static constexpr int kEpiBytes = 4 * 32 * 32 * 4 + 64;      // epilogue staging: [32 rows][32 cols] fp32 per epilogue warp
+    static constexpr int kEpiBytes = kEpiWarps * 32 * 32 * 4 + 64;   // epilogue staging: [32 rows][32 cols] fp32 per epilogue warp
     static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
     // stand-alone k_roll_tc keeps the simple 4-stage {A,B} ring
     static constexpr int kStageBytes = (NSPLIT == 3 ? 2 : 1) * (kABytes + kBBytes);
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             }
             for (int s = 0; s < 2; ++s) {
                 ptx::mbar_init(&tmem_full_bar[s], 1);
-                ptx::mbar_init(&tmem_empty_bar[s], 4);       // one arrive per epilogue warp
+                ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps);       // one arrive per epilogue warp
             }
             ptx::mbar_init(roll_filled_bar, 1);
             ptx::fence_barrier_init();
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             }
             if (ltp < 3 && lane == 0) trace_mark(A.tr, 4 + 6 * ltp + 5);
         }
-    } else if (warp == 6) {
+    } else if (warp == 2 + kEpiWarps) {
         // ===================== TMA producer: B (weight) tiles =====================
         if (lane == 0) trace_mark(A.tr, 27);
         int gb = 0;
@@ -283,9 +284,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             ptx::mbar_wait(&emptyB[s], ((gb / Cfg::kBSlots) & 1) ^ 1);
             uint8_t* st = smem_b + s * Cfg::kBSlotBytes;
             if (ptx::elect_one()) {
+                // ONE box {64 K, 64 N, hi|lo}: the lo tile lands right behind the hi tile (a TMA op costs ~250 cycles of producer
+                // time whatever its size, tools/tma_bw.cu)
                 ptx::mbar_arrive_expect_tx(&fullB[s], Cfg::kBSlotBytes);
                 ptx::tma_load_3d(st, wm, &fullB[s], kchunk * kBK, n0, 0);
-                if (NSPLIT == 3) ptx::tma_load_3d(st + kBLo, wm, &fullB[s], kchunk * kBK, n0, 1);
             }
             __syncwarp();
             if (gb == 0 && lane == 0) trace_mark(A.tr, 28);
@@ -371,10 +373,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which 32 of the tile's 64 output channels: the two warps of a quarter split them
         const int m = quarter * 32 + lane;            // accumulator row (pixel of the tile / position of the roll tile)
-        const int et = threadIdx.x - 64;              // 0..127 among the epilogue threads
+        const int et = threadIdx.x - 64;              // 0..255 among the epilogue threads
         const int k8 = lane & 7, rloc = lane >> 3;    // transposed pass: 16-byte chunk k8 of staged rows rloc, rloc + 4, ...
-        float* wst = stage + quarter * 1024;          // this warp's staging block
+        float* wst = stage + (warp - 2) * 1024;       // this warp's staging block
         bool roll_ready = F.n_roll == 0;
         int lt = 0, ga = 0;
         if (et == 0) trace_mark(A.tr, 30);
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     const unsigned long long* sp = F.sums + (static_cast<size_t>(T.b) * F.total_len + F.R.soff[T.src]) * A.C;
                     const float scale = F.R.scale[T.src];
                     constexpr int kChunks = kRollRows * 8;                  // 16-byte chunks (8 channels) of one patch
-                    constexpr int kIters = (kChunks + 127) / 128, kBatch = kIters;     // every load of a patch in flight at once
+                    constexpr int kIters = (kChunks + kEpiThreads - 1) / kEpiThreads, kBatch = kIters;     // every load of a patch in flight at once
                     for (int cb = 0; cb < cblks; ++cb, ++ga) {
                         const int s = ga % Cfg::kASlots;
                         if (et == 0 && lt == 0 && cb == 0) trace_mark(A.tr, 2);
@@ -401,11 +404,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         uint8_t* hi = smem_a + s * Cfg::kASlotBytes;
                         uint8_t* lo = hi + kALo;
 #pragma unroll
-                        for (int half = 0; half < 1; ++half) {
+                        for (int hb = 0; hb < 1; ++hb) {
                             ulonglong2 raw[kBatch][4];
 #pragma unroll
                             for (int i = 0; i < kBatch; ++i) {
-                                const int q = et + 128 * (half * kBatch + i), j = q >> 3, k = q & 7, pos = T.p0 - 1 + j;
+                                const int q = et + kEpiThreads * (hb * kBatch + i), j = q >> 3, k = q & 7, pos = T.p0 - 1 + j;
                                 const bool ok = q < kChunks && pos >= 0 && pos < L;
                                 const ulonglong2* src = reinterpret_cast<const ulonglong2*>(sp + static_cast<size_t>(ok ? pos : 0) * A.C + cb * kBK + k * 8);
 #pragma unroll
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                             if (et == 0 && lt == 0 && cb == 0) trace_mark(A.tr, 17);
 #pragma unroll
                             for (int i = 0; i < kBatch; ++i) {
-                                const int q = et + 128 * (half * kBatch + i), j = q >> 3, k = q & 7;
+                                const int q = et + kEpiThreads * (hb * kBatch + i), j = q >> 3, k = q & 7;
                                 if (q < kChunks) {
                                     __half h[8], l[8];
 #pragma unroll
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         }
                         if (et == 0 && lt == 0 && cb == 0) trace_mark(A.tr, 18);
                         ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                         if (et == 0) ptx::mbar_arrive(&fullA[s]);
                     }
                     if (et == 0 && t + static_cast<int>(gridDim.x) >= F.n_roll) ptx::mbar_arrive(roll_filled_bar);
@@ -443,13 +446,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 3);
                 __syncwarp();
                 ptx::tc_fence_after();
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                {
                     uint32_t v1[32], v2[32];
                     ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
                     if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
                     ptx::tmem_ld_wait();
-                    if (half == 1) {
+                    {
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 if (et == 0 && lt == 0) trace_mark(A.tr, 20);
                 // publish: CTA barrier, then ONE release-scoped reduction (cumulative over the stores the barrier ordered before
                 // it) instead of a device-wide fence in each of the 128 threads
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 if (et == 0) {
                     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(F.counters), "r"(1u) : "memory");
                     if (lt == 0) trace_mark(A.tr, 21);
@@ -524,8 +526,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             struct Addends {
                 float4 rs[8], trow[2][4], tcol[2][4], bias;
             };
-            auto fetch = [&](int half, Addends& D) {
-                const int ch = n0 + half * 32;
+            auto fetch = [&](int hf, Addends& D) {
+                const int ch = n0 + hf * 32;
                 // per-channel addends of this thread's quad: bias (+ additive timestep embedding)
                 D.bias = __ldg(reinterpret_cast<const float4*>(A.e.bias.p[plane] + ch) + k8);
                 if (A.e.embadd) {
@@ -580,24 +582,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 }
             };
             Addends D;
-            float4 add0[8], add1[8];
-            fetch(0, D);
+            float4 add[8];
+            fetch(half, D);
             if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 2);
             ptx::mbar_wait(&tmem_full_bar[as], aph);
             if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 3);
             __syncwarp();
             ptx::tc_fence_after();
-            fold(D, add0);
-            fetch(1, D);
+            fold(D, add);
             const bool do_stats = A.sink.acc != nullptr;
-            float4 ssum[2] = {zero4, zero4}, ssq[2] = {zero4, zero4};
-            auto half_pass = [&](int half, const float4 (&add)[8]) {
+            float4 ssum = zero4, ssq = zero4;
+            {
                 uint32_t v1[32], v2[32];
                 ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
                 if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
                 ptx::tmem_ld_wait();
-                if (half == 1) {
-                    // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA issuer
+                {
+                    // this warp's TMEM reads of the tile are done: hand the accumulator stage back to the MMA issuer (8 arrivals)
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
@@ -624,25 +625,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         o.z = a.z + add[it].z;
                         o.w = a.w + add[it].w;
                         *reinterpret_cast<float4*>(outb + (px0 + static_cast<size_t>(r) * cols + c) * Cout + n0 + half * 32 + 4 * k8) = o;
-                        ssum[half].x += o.x; ssum[half].y += o.y; ssum[half].z += o.z; ssum[half].w += o.w;
-                        ssq[half].x = fmaf(o.x, o.x, ssq[half].x); ssq[half].y = fmaf(o.y, o.y, ssq[half].y);
-                        ssq[half].z = fmaf(o.z, o.z, ssq[half].z); ssq[half].w = fmaf(o.w, o.w, ssq[half].w);
+                        ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
+                        ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
+                        ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
                     }
                 }
-                __syncwarp();                      // the staging block is rewritten by the next half / tile
-            };
-            half_pass(0, add0);
-            fold(D, add1);
-            half_pass(1, add1);
+                __syncwarp();                      // the staging block is rewritten by the next tile
+            }
             if (do_stats) {
                 // (sum, sum-sq) per channel over the warp's 32 pixels: the four row groups of a lane column are added in a fixed
                 // order, then every GroupNorm group goes out as one fixed-point atomic (exact, so the order of the warps and
                 // tiles does not matter)
                 constexpr unsigned kFull = 0xffffffffu;
                 const int cpg = Cout / kGroups;              // 2, 4 or 8 (host-checked)
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float v[8] = {ssum[half].x, ssum[half].y, ssum[half].z, ssum[half].w, ssq[half].x, ssq[half].y, ssq[half].z, ssq[half].w};
+                {
+                    float v[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         v[e] += __shfl_xor_sync(kFull, v[e], 8);
@@ -764,11 +761,8 @@ __global__ void __launch_bounds__(kRollThreads, 1) k_roll_tc(const __grid_consta
                 // stage layout: [A hi][A lo][B hi][B lo]  (B lo directly behind B hi: one N=128 MMA reads both)
                 constexpr int kBOff = (NSPLIT == 3 ? 2 : 1) * kABytes;
                 ptx::tma_load_5d(st, &M.a[src], &full_bar[s], cb * kBK, p0 + al - 1, 0, b, 0);
-                ptx::tma_load_3d(st + kBOff, &M.w[src], &full_bar[s], i * kBK, n0, 0);
-                if (NSPLIT == 3) {
-                    ptx::tma_load_5d(st + kABytes, &M.a[src], &full_bar[s], cb * kBK, p0 + al - 1, 0, b, 1);
-                    ptx::tma_load_3d(st + kBOff + kBBytes, &M.w[src], &full_bar[s], i * kBK, n0, 1);
-                }
+                ptx::tma_load_3d(st + kBOff, &M.w[src], &full_bar[s], i * kBK, n0, 0);     // box {64, 64, hi|lo}: both weight tiles
+                if (NSPLIT == 3) ptx::tma_load_5d(st + kABytes, &M.a[src], &full_bar[s], cb * kBK, p0 + al - 1, 0, b, 1);
             }
         }
     } else if (warp == 1) {

@@ -817,7 +817,7 @@ struct PlanBuilder {
             const uint32_t abox[5] = {kBK, kBM, 1, 1, 1};
             make_tmap_strided(&maps->a[i], S.means16 + static_cast<size_t>(soff[i]) * C, 5, adims, astr, abox);
             const uint64_t wdims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(4 * Cout), 2};
-            const uint32_t wbox[3] = {kBK, kBN, 1};
+            const uint32_t wbox[3] = {kBK, kBN, u->cfg.precision == 1 ? 1u : 2u};      // hi and lo tile in ONE box (lo lands behind hi)
             make_tmap(&maps->w[i], cv.wr16[i / 2][i % 2], 3, wdims, wbox);
         }
         A.tile_start[6] = total;
@@ -908,7 +908,7 @@ struct PlanBuilder {
                 maps->x[p] = maps->a[p];
             }
             const uint64_t wdims[3] = {static_cast<uint64_t>(cv.Ktot), static_cast<uint64_t>(cv.Cout), 2};
-            const uint32_t wbox[3] = {kBK, kBN, 1};
+            const uint32_t wbox[3] = {kBK, kBN, u->cfg.precision == 1 ? 1u : 2u};       // hi and lo tile in ONE box
             make_tmap(&maps->w[p], cv.w_pack[p], 3, wdims, wbox);
             A.tiles_x[p] = (d.cols[p] + kTileW - 1) / kTileW;
             const int tiles_y = (d.rows[p] + kTileH - 1) / kTileH;

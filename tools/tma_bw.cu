@@ -51,6 +51,61 @@ __global__ void __launch_bounds__(64, 1) k_stream(const __grid_constant__ CUtens
     }
 }
 
+// Cluster-of-2 variant: each CTA fetches HALF of every tile (ROWS/2 rows) and multicasts it to both CTAs, so every CTA still
+// receives the full tile but the pair reads it from L2 once.  A slot is refilled only after BOTH consumers released it
+// (empty barriers count 2, remote arrive through mapa).
+template <int DEPTH, int ROWS>
+__global__ void __launch_bounds__(64, 1) k_stream_mc(const __grid_constant__ CUtensorMap M, int iters, int tiles_per_region, int shared_region,
+                                                     unsigned long long* cyc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kTile = 128 * ROWS;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + DEPTH * kTile);
+    uint64_t* empty = full + DEPTH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DEPTH; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 2);
+        }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&M);
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const int region = shared_region ? 0 : (blockIdx.x >> 1);
+    const long long t0 = clock64();
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < iters; ++i) {
+            const int s = i % DEPTH;
+            ptx::mbar_wait(&empty[s], ((i / DEPTH) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&full[s], kTile);
+            const int tile = region * tiles_per_region + (i % tiles_per_region);
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                ::"r"(ptx::smem_u32(smem + s * kTile + rank * (kTile / 2))), "l"(reinterpret_cast<uint64_t>(&M)), "r"(ptx::smem_u32(&full[s])),
+                "r"(0), "r"(tile * ROWS + static_cast<int>(rank) * (ROWS / 2)), "r"(0), "h"(static_cast<uint16_t>(3))
+                : "memory");
+        }
+    } else if (warp == 1 && lane == 0) {
+        for (int i = 0; i < iters; ++i) {
+            const int s = i % DEPTH;
+            ptx::mbar_wait(&full[s], (i / DEPTH) & 1);
+#pragma unroll
+            for (uint32_t r = 0; r < 2; ++r) {
+                uint32_t ra;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(ptx::smem_u32(&empty[s])), "r"(r));
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+            }
+        }
+        cyc[blockIdx.x] = clock64() - t0;
+    }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -62,10 +117,10 @@ static PFN_encodeTiled get_encode() {
 }
 
 template <int DEPTH, int ROWS>
-static void run(const char* name, void* buf, size_t total_rows, int G, int iters, int tiles_per_region, int shared_region) {
+static void run(const char* name, void* buf, size_t total_rows, int G, int iters, int tiles_per_region, int shared_region, int mc = 0) {
     CUtensorMap m;
     cuuint64_t gdim[3] = {64, total_rows, 1}, gstr[2] = {128, 128 * total_rows};
-    cuuint32_t box[3] = {64, ROWS, 1}, es[3] = {1, 1, 1};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(mc ? ROWS / 2 : ROWS), 1}, es[3] = {1, 1, 1};
     CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, buf, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -76,12 +131,33 @@ static void run(const char* name, void* buf, size_t total_rows, int G, int iters
     cudaMalloc(&cyc, G * sizeof(unsigned long long));
     const size_t smem = 200 * 1024;
     cudaFuncSetAttribute(k_stream<DEPTH, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_stream_mc<DEPTH, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0);
-        k_stream<DEPTH, ROWS><<<G, 64, smem>>>(m, iters, tiles_per_region, shared_region, cyc);
+        if (mc) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(G);
+            cfg.blockDim = dim3(64);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (rep == 0) {
+                int nc = 0;
+                cudaOccupancyMaxActiveClusters(&nc, k_stream_mc<DEPTH, ROWS>, &cfg);
+                printf("[max active clusters of 2: %d] ", nc);
+            }
+            cudaLaunchKernelEx(&cfg, k_stream_mc<DEPTH, ROWS>, m, iters, tiles_per_region, shared_region, cyc);
+        } else {
+            k_stream<DEPTH, ROWS><<<G, 64, smem>>>(m, iters, tiles_per_region, shared_region, cyc);
+        }
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
     }
@@ -115,6 +191,9 @@ int main() {
     run<3, 128>("same region (hot 432 KB), 16 KB tiles", buf, rows128, G, iters, tiles_per_region, 1);
     run<4, 128>("same region (hot 432 KB), 16 KB tiles", buf, rows128, G, iters, tiles_per_region, 1);
     run<8, 128>("same region (hot 432 KB), 16 KB tiles", buf, rows128, G, iters, tiles_per_region, 1);
+    run<4, 128>("MC2 same region (hot), 16 KB tiles", buf, rows128, G, iters, tiles_per_region, 1, 1);
+    run<8, 128>("MC2 same region (hot), 16 KB tiles", buf, rows128, G, iters, tiles_per_region, 1, 1);
+    run<4, 128>("MC2 per-cluster region, 16 KB tiles", buf, rows128, G, iters, tiles_per_region, 0, 1);
     run<8, 64>("own region, 8 KB tiles", buf, rows128, G, iters, tiles_per_region * 2, 0);
     run<8, 64>("same region, 8 KB tiles", buf, rows128, G, iters, tiles_per_region * 2, 1);
     run<3, 128>("own region, 16 KB tiles, 32 CTAs", buf, rows128, 32, iters, tiles_per_region, 0);
