@@ -58,6 +58,8 @@ struct RollTcMaps {
 };
 struct RollTcArgs {
     int L[6], ncls[6];
+    int tm[6];          // positions per roll tile of source s (<= 96): L is cut into equal tiles so that no tile's A patch (64-bit axis
+                        // sums read through ONE SM's load path: what bounds the roll chain every conv epilogue waits for) is a straggler
     float* T[6];        // [B][4][L][Cout]
     int tile_start[7];
     int C, Cout;
@@ -135,11 +137,12 @@ __device__ __forceinline__ RollTile roll_tile_decode(const FusedRoll& F, int t) 
     for (int k = 1; k < 6; ++k)
         if (rem >= F.R.tile_start[k]) src = k;
     T.src = src;
-    T.p0 = (rem - F.R.tile_start[src]) * kBM;
+    T.p0 = (rem - F.R.tile_start[src]) * F.R.tm[src];
     return T;
 }
 
-constexpr int kRollRows = kBM + 2;      // rows of a roll tile's A patch: positions p0-1 .. p0+128
+constexpr int kRollTmMax = 96;           // most positions a roll tile produces (the MMA is M = 128 regardless: rows beyond tm are don't-care)
+constexpr int kRollRows = kRollTmMax + 2;   // most rows of a roll tile's A patch: positions p0-1 .. p0+tm
 
 // Persistent implicit-GEMM convolution, one CTA per SM, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
 //
@@ -394,8 +397,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 {
                     const unsigned long long* sp = F.sums + (static_cast<size_t>(T.b) * F.total_len + F.R.soff[T.src]) * A.C;
                     const float scale = F.R.scale[T.src];
-                    constexpr int kChunks = kRollRows * 8;                  // 16-byte chunks (8 channels) of one patch
-                    constexpr int kIters = (kChunks + kEpiThreads - 1) / kEpiThreads, kBatch = kIters;     // every load of a patch in flight at once
+                    constexpr int kChunksMax = kRollRows * 8;               // 16-byte chunks (8 channels) of one patch
+                    const int kChunks = (F.R.tm[T.src] + 2) * 8;
+                    constexpr int kIters = (kChunksMax + kEpiThreads - 1) / kEpiThreads, kBatch = kIters;     // every load of a patch in flight at once
                     for (int cb = 0; cb < cblks; ++cb, ++ga) {
                         const int s = ga % Cfg::kASlots;
                         if (et == 0 && lt == 0 && cb == 0) trace_mark(A.tr, 2);
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int ml = it * 4 + rloc;
-                        if (T.p0 + quarter * 32 + ml < L)
+                        if (quarter * 32 + ml < F.R.tm[T.src] && T.p0 + quarter * 32 + ml < L)
                             __stcg(reinterpret_cast<float4*>(outp + static_cast<size_t>(ml) * A.Cout + half * 32) + k8,
                                    *reinterpret_cast<const float4*>(wst + ml * 32 + ((k8 ^ (ml & 7)) << 2)));
                     }
@@ -721,7 +725,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) k_roll_tc(const __grid_consta
 #pragma unroll
     for (int k = 1; k < 6; ++k)
         if (static_cast<int>(blockIdx.x) >= A.tile_start[k]) src = k;
-    const int p0 = (blockIdx.x - A.tile_start[src]) * kBM;
+    const int p0 = (blockIdx.x - A.tile_start[src]) * A.tm[src];
     const int n0 = blockIdx.y * kBN;
     const int b = blockIdx.z;
     if (A.T[src] == nullptr || n0 >= A.ncls[src] * A.Cout) return;      // uniform for the whole CTA
@@ -799,7 +803,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) k_roll_tc(const __grid_consta
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;
         const int pos = p0 + m, L = A.L[src];
-        const bool valid = pos < L;
+        const bool valid = pos < L && m < A.tm[src];
         const int cls = n0 / A.Cout, co0 = n0 - cls * A.Cout;
         float* __restrict__ outp = A.T[src] + ((static_cast<size_t>(b) * 4 + cls) * L + pos) * A.Cout + co0;
         ptx::mbar_wait(tmem_full_bar, 0);

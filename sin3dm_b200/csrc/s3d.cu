@@ -811,7 +811,11 @@ struct PlanBuilder {
                 A.scale[i] = static_cast<float>(1.0 / 16777216.0 / static_cast<double>(avg_len));
             }
             A.tile_start[i] = total;
-            total += (L[i] + kBM - 1) / kBM;
+            {
+                const int nt = (L[i] + kRollTmMax - 1) / kRollTmMax;      // equal tiles of at most kRollTmMax positions
+                A.tm[i] = (L[i] + nt - 1) / nt;
+                total += nt;
+            }
             const uint64_t adims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(L[i]), 1, static_cast<uint64_t>(B), 2};
             const uint64_t astr[4] = {static_cast<uint64_t>(C) * 2, seg_bytes, seg_bytes, seg_bytes * B};
             const uint32_t abox[5] = {kBK, kBM, 1, 1, 1};

@@ -116,3 +116,46 @@ def test_large_batch_several_roll_tiles_per_cta(B):
     want = ur.unet_forward(sd, spec, x[:2], t[:2], H, W, D)
     rel, mx = plane_errors(out[:2].cpu(), want, H, W, D)
     assert rel < TOL and mx < TOL, (rel, mx)
+
+
+@pytest.mark.parametrize("name,HWD,B", [("cfg2", (92, 128, 92), 1), ("cfg3_resized", (92, 128, 138), 2)])
+def test_full_size_forward_matches_oracle(name, HWD, B):
+    """BASELINE.json configs[1] / configs[2] shapes (C=12, default triplane; --resize 1 1 1.5 -> D=138): one UNet forward of the
+    tcgen05 path against the CPU oracle at FULL size (the oracle is pinned to the real reference by the golden fixtures)."""
+    spec = ur.UNetSpec(in_channels=12, model_channels=64, out_channels=12)
+    sd = ur.synthetic_state_dict(spec, 78)
+    H, W, D = HWD
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 12, H + D, W + D, generator=g)
+    t = torch.tensor([977, 12][:B])
+    m = make_cuda_model(spec, sd, 3, "tc")
+    with torch.no_grad():
+        got = m(x.cuda(), t.cuda(), H=H, W=W, D=D).cpu()
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    want = ur.unet_forward(sd, spec, x, t, H, W, D)
+    rel, mx = plane_errors(got, want, H, W, D)
+    print(name, "rel_l2", rel, "max", mx)
+    assert rel < TOL and mx < TOL, (rel, mx)
+    assert torch.all(got[..., H:, W:] == 0)
+
+
+def test_full_size_ddim_loop_matches_oracle():
+    """cfg3 shape, DDIM with 3 respaced steps, batch 2, through the CUDA-graph loop vs the oracle's loop (same x_T; eta = 0 so no
+    step noise enters)."""
+    from oracle import diffusion_ref as dr
+    from sin3dm_b200.script_util import create_gaussian_diffusion
+    spec = ur.UNetSpec(in_channels=12, model_channels=64, out_channels=12)
+    sd = ur.synthetic_state_dict(spec, 79)
+    H, W, D = 92, 128, 138
+    g = torch.Generator().manual_seed(4)
+    x_T = torch.randn(2, 12, H + D, W + D, generator=g)
+    m = make_cuda_model(spec, sd, 3, "tc")
+    d = create_gaussian_diffusion(predict_xstart=True, timestep_respacing="3")
+    with torch.no_grad():
+        got = d.ddim_sample_loop(m, list(x_T.shape), noise=x_T, model_kwargs=dict(H=H, W=W, D=D)).cpu()
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    o = dr.RefDiffusion(1000, "3")
+    want = o.sample_loop(lambda xx, tt: ur.unet_forward(sd, spec, xx, tt, H, W, D), x_T, lambda i: torch.zeros_like(x_T), ddim=True)
+    rel, mx = plane_errors(got, want, H, W, D)
+    print("cfg3 ddim-3 rel_l2", rel, "max", mx)
+    assert rel < TOL and mx < TOL, (rel, mx)
