@@ -1,6 +1,7 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum[,smsp__cycles_active.avg] --csv` launch list: one step's kernels."""
 import collections
 import csv
+import re
 import sys
 
 
@@ -22,7 +23,8 @@ def main(path, per_step=None, skip=None):
             rows[i]["act"] = v
     seq = [rows[i] for i in order]
     # a step ends with k_sched_step
-    ends = [k for k, r in enumerate(seq) if r["name"].startswith("k_boundary<2>") or r["name"].startswith("k_boundary<(s3d::MODE)2>")]
+    # a step of the graph-replayed loop ends with the fused boundary kernel k_boundary<2, ...> (out head + scheduler + next in_conv)
+    ends = [k for k, r in enumerate(seq) if re.match(r"k_boundary<(\(s3d::MODE\))?2[,>]", r["name"])]
     if len(ends) < 3:
         ends = [k for k, r in enumerate(seq) if r["name"].startswith("k_sched_step")]
     if len(ends) >= 3:
