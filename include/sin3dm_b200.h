@@ -152,6 +152,11 @@ typedef struct {
 } s3d_vb_args;
 int64_t s3d_vb_workspace_bytes(int B, int64_t n_per_sample);
 int s3d_vb_terms(const s3d_vb_args* a, void* stream);
+/* Per-plane MSE of the training objective (GaussianDiffusion.training_losses, gaussian_diffusion.py:822-851: mean_flat of
+ * (target - output)^2 over the xy, xz and yz planes of the composed tensors [B, C, H+D, W+D]): out_dev [B][3] = mse_xy, mse_xz,
+ * mse_yz.  One pass, fixed-order fp64 reduction.  workspace: s3d_vb_workspace_bytes(B, C*(H+D)*(W+D)) bytes. */
+int s3d_plane_mse(const float* target_dev, const float* output_dev, int B, int C, int H, int W, int D, void* workspace, float* out_dev,
+                  void* stream);
 /* N(0,1) fill [B, C, hw] with the same counter-based generator the sampler uses (noise of sample s at step i). */
 int s3d_philox_normal(float* out_dev, int B, int C, int64_t hw, uint64_t seed, uint32_t sample_base, uint32_t step,
                       void* stream);

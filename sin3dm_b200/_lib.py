@@ -84,6 +84,8 @@ _SIGNATURES = {
                                     C.c_void_p]),
     "s3d_vb_workspace_bytes": (C.c_int64, [C.c_int, C.c_int64]),
     "s3d_vb_terms": (C.c_int, [C.POINTER(VbArgs), C.c_void_p]),
+    "s3d_plane_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
     "s3d_sample_loop": (C.c_int, [C.c_void_p, C.POINTER(LoopArgs), C.c_void_p]),
     "s3d_decoder_create": (C.c_int, [C.POINTER(DecoderConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "s3d_decoder_destroy": (C.c_int, [C.c_void_p]),

@@ -401,22 +401,27 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
     __half* ap = A.a.p[plane] + sample_off;
     __half* xq = A.x16.p[plane] ? A.x16.p[plane] + sample_off : nullptr;
     float4 v[kGsRows], y[kGsRows];
+    // Addresses: one base per column group, then a 32-bit row stride (an element offset inside one sample's plane fits an int);
+    // the 64-bit multiply per row and per stream used to be a third of this kernel's instructions, and it is issue bound.
+    const int row_stride = cols * C;
     auto load_group = [&](int cg) {
         const int c = cbase + cg * ny + ty;
+        const int base = (r0 * cols + min(c, cols - 1)) * C + tx * 4;
         if (xp) {
+            const float* pb = xp + base;
 #pragma unroll
             for (int r = 0; r < kGsRows; ++r)
-                v[r] = (c < cols && r < nr) ? __ldg(reinterpret_cast<const float4*>(xp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[r] = (c < cols && r < nr) ? __ldg(reinterpret_cast<const float4*>(pb + r * row_stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
             uint2 hh[kGsRows], ll[kGsRows];
+            const __half* ph = xhp + base;
+            const __half* pl = ph + lo_off;
 #pragma unroll
             for (int r = 0; r < kGsRows; ++r) {
                 hh[r] = ll[r] = make_uint2(0u, 0u);
                 if (c < cols && r < nr) {
-                    const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
-                    hh[r] = __ldg(reinterpret_cast<const uint2*>(xhp + off));
-                    ll[r] = __ldg(reinterpret_cast<const uint2*>(xhp + lo_off + off));
+                    hh[r] = __ldg(reinterpret_cast<const uint2*>(ph + r * row_stride));
+                    ll[r] = __ldg(reinterpret_cast<const uint2*>(pl + r * row_stride));
                 }
             }
 #pragma unroll
@@ -427,12 +432,16 @@ __global__ void __launch_bounds__(256, 2) k_gn_silu(GnSiluArgs A, int B) {
     auto store_group = [&](int cg) {
         const int c = cbase + cg * ny + ty;
         if (c >= cols) return;
+        const int base = (r0 * cols + c) * C + tx * 4;
+        __half* ah = ap + base;
+        __half* al = ah + lo_off;
+        __half* qh = xq ? xq + base : nullptr;
+        __half* ql = xq ? qh + lo_off : nullptr;
 #pragma unroll
         for (int r = 0; r < kGsRows; ++r) {
             if (r < nr) {
-                const size_t off = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
-                if (xq) store_split4(xq + off, xq + lo_off + off, v[r]);
-                store_split4(ap + off, ap + lo_off + off, y[r]);
+                if (xq) store_split4(qh + r * row_stride, ql + r * row_stride, v[r]);
+                store_split4(ah + r * row_stride, al + r * row_stride, y[r]);
             }
         }
     };
@@ -938,6 +947,55 @@ __global__ void k_vb_finalize(VbArgs A, int gx) {
     double m = s / static_cast<double>(A.n);
     if (k == 0) m /= 0.6931471805599453;        // nats -> bits (np.log(2.0))
     A.out[b * 3 + k] = static_cast<float>(m);
+}
+
+// ---------------------------------------------------------------- per-plane MSE of the training objective
+//   reference: GaussianDiffusion.training_losses, gaussian_diffusion.py:822-851: decompose_featmaps(target / output) and
+//   mean_flat((target - output)^2) per plane (xy, xz, yz).  One pass over the two composed tensors [B, C, H+D, W+D]; the plane of
+//   an element follows from its (row, col) (the D x D corner belongs to none); fp64 block sums, added in block order by
+//   k_plane_mse_finalize.  grid (gx, B)
+struct PlaneMseArgs {
+    const float *target, *output;
+    int C, H, W, D;
+    long long n;               // C * (H+D) * (W+D)
+    double* partial;           // [B][gx][3]
+    float* out;                // [B][3]
+};
+__global__ void __launch_bounds__(256) k_plane_mse(PlaneMseArgs A) {
+    const int b = blockIdx.y;
+    const size_t base = static_cast<size_t>(b) * A.n;
+    const int Wc = A.W + A.D, hw = (A.H + A.D) * Wc;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < A.n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int pix = static_cast<int>(i % hw), r = pix / Wc, c = pix - r * Wc;
+        const float d = A.target[base + i] - A.output[base + i];
+        const double d2 = static_cast<double>(d * d);
+        if (r < A.H) acc[c < A.W ? 0 : 1] += d2;
+        else if (c < A.W) acc[2] += d2;
+    }
+    __shared__ double red[3][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        A.partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
+    }
+}
+__global__ void k_plane_mse_finalize(PlaneMseArgs A, int gx) {
+    const int b = blockIdx.x, k = threadIdx.x;
+    if (k >= 3) return;
+    double t = 0.0;
+    for (int j = 0; j < gx; ++j) t += A.partial[(static_cast<size_t>(b) * gx + j) * 3 + k];
+    const double cnt = static_cast<double>(A.C) * (k == 0 ? A.H * A.W : (k == 1 ? A.H * A.D : A.W * A.D));
+    A.out[b * 3 + k] = static_cast<float>(t / cnt);
 }
 
 __global__ void __launch_bounds__(256) k_philox_normal(float* __restrict__ out, int C, long long hw, unsigned long long seed,

@@ -1478,6 +1478,25 @@ int s3d_vb_terms(const s3d_vb_args* a, void* stream) {
     API_END
 }
 
+int s3d_plane_mse(const float* target_dev, const float* output_dev, int B, int C, int H, int W, int D, void* workspace, float* out_dev,
+                  void* stream) {
+    API_BEGIN
+    S3D_CHECK(target_dev && output_dev && workspace && out_dev && B >= 1 && C >= 1 && H >= 1 && W >= 1 && D >= 1, "bad argument");
+    PlaneMseArgs A{};
+    A.target = target_dev;
+    A.output = output_dev;
+    A.C = C; A.H = H; A.W = W; A.D = D;
+    A.n = static_cast<long long>(C) * (H + D) * (W + D);
+    A.partial = static_cast<double*>(workspace);
+    A.out = out_dev;
+    const int gx = vb_grid(A.n);
+    launch(k_plane_mse, dim3(gx, B), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
+    LAUNCH_CHECK("k_plane_mse");
+    launch(k_plane_mse_finalize, dim3(B), dim3(32), 0, static_cast<cudaStream_t>(stream), A, gx);
+    LAUNCH_CHECK("k_plane_mse_finalize");
+    API_END
+}
+
 int s3d_philox_normal(float* out_dev, int B, int C, int64_t hw, uint64_t seed, uint32_t sample_base, uint32_t step, void* stream) {
     API_BEGIN
     S3D_CHECK(out_dev && B >= 1 && C >= 1 && hw >= 1, "bad argument");

@@ -485,7 +485,8 @@ class GaussianDiffusion:
 
     # ------------------------------------------------------------------ training objective (forward values)
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
-        """:771-856, MSE branch: q_sample (fused kernel) -> model -> per-plane mean squared error."""
+        """:771-856, MSE branch: q_sample (fused kernel) -> model -> per-plane mean squared error (k_plane_mse: one pass over the
+        composed tensors, fixed-order fp64 reduction)."""
         if model_kwargs is None:
             model_kwargs = {}
         if noise is None:
@@ -496,10 +497,14 @@ class GaussianDiffusion:
         model_output = self._call_model(model, x_t, t, model_kwargs)
         target = {ModelMeanType.START_X: x_start, ModelMeanType.EPSILON: noise}[self.model_mean_type]
         assert model_output.shape == target.shape == x_start.shape
-        sizes = (model_kwargs["H"], model_kwargs["W"], model_kwargs["D"])
-        terms = {}
-        for name, tp, op in zip(("xy", "xz", "yz"), decompose_featmaps(target, sizes),
-                                decompose_featmaps(model_output, sizes)):
-            terms[f"mse_{name}"] = ((tp - op) ** 2).mean(dim=(1, 2, 3))
+        H, W, D = (int(model_kwargs[k]) for k in ("H", "W", "D"))
+        tgt, outp = target.float().contiguous(), model_output.float().contiguous()
+        B, Cc = tgt.shape[0], tgt.shape[1]
+        assert tuple(tgt.shape[2:]) == (H + D, W + D)
+        mse = th.empty(B, 3, device=tgt.device, dtype=th.float32)
+        ws = th.empty(_lib.lib().s3d_vb_workspace_bytes(B, tgt[0].numel()), device=tgt.device, dtype=th.uint8)
+        with th.cuda.device(tgt.device):
+            _lib.check(_lib.lib().s3d_plane_mse(_ptr(tgt), _ptr(outp), B, Cc, H, W, D, _ptr(ws), _ptr(mse), _lib.current_stream_ptr()))
+        terms = {"mse_xy": mse[:, 0], "mse_xz": mse[:, 1], "mse_yz": mse[:, 2]}
         terms["loss"] = terms["mse_xy"] + terms["mse_xz"] + terms["mse_yz"]
         return terms

@@ -93,3 +93,23 @@ def test_in_kernel_noise_equals_philox_fill():
                                             _lib.current_stream_ptr()))
     b = d.p_sample(lambda xx, tt, **k: out, x, t, noise=nz)
     assert torch.equal(a["sample"], b["sample"])
+
+
+def test_plane_mse_matches_decomposed_mean():
+    """k_plane_mse vs mean_flat((target - output)^2) over decompose_featmaps' three planes (gaussian_diffusion.py:822-851,
+    triplane_util.py:19-25), ragged sizes, batch 3; the D x D corner must not count."""
+    import ctypes as C
+    g = torch.Generator().manual_seed(11)
+    B, Cc, H, W, D = 3, 5, 13, 18, 7
+    tgt = torch.randn(B, Cc, H + D, W + D, generator=g)
+    out = torch.randn(B, Cc, H + D, W + D, generator=g)
+    out[..., H:, W:] += 100.0                      # garbage in the unused corner
+    a, b = tgt.cuda(), out.cuda()
+    L = _lib.lib()
+    ws = torch.empty(L.s3d_vb_workspace_bytes(B, tgt[0].numel()), dtype=torch.uint8, device="cuda")
+    mse = torch.empty(B, 3, device="cuda")
+    _lib.check(L.s3d_plane_mse(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), B, Cc, H, W, D, C.c_void_p(ws.data_ptr()),
+                               C.c_void_p(mse.data_ptr()), _lib.current_stream_ptr()))
+    want = torch.stack([((tp - op) ** 2).mean(dim=(1, 2, 3)) for tp, op in zip(s3.decompose_featmaps(tgt, (H, W, D)),
+                                                                                 s3.decompose_featmaps(out, (H, W, D)))], dim=1)
+    assert torch.allclose(mse.cpu(), want, rtol=2e-6, atol=0), (mse.cpu(), want)
