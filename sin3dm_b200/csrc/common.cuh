@@ -40,21 +40,33 @@ __device__ __forceinline__ float silu_f(float v) {
     return __fdividef(v, 1.f + __expf(-v));
 }
 
-// fp32 -> (hi, lo) fp16 pair with v ~= hi + lo / 2048, |err| <= 2^-22 |v| (saturating)
+// fp32 -> (hi, lo) fp16 pair with v ~= hi + lo / 2048, |err| <= 2^-22 |v|.  Saturating: the conversions are
+// cvt.rn.satfinite (F2FP.SATFINITE.F16.F32.PACK_AB converts, saturates and packs two values in one instruction — the explicit
+// min/max clamp in front of a plain conversion was a tenth of the element-wise kernels' instructions, and they are issue bound).
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo_elem, float hi_elem) {     // -> {hi_elem : lo_elem} as one 32-bit word
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+// two values at once: hi2 / lo2 hold (a, b) in (low, high) halves
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+    hi2 = cvt_f16x2_sat(a, b);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+    lo2 = cvt_f16x2_sat((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
+}
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
-    v = fminf(fmaxf(v, -65504.f), 65504.f);
-    hi = __float2half_rn(v);
-    lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
+    uint32_t h2, l2;
+    split_f16x2(v, 0.f, h2, l2);
+    hi = __ushort_as_half(static_cast<unsigned short>(h2 & 0xffffu));
+    lo = __ushort_as_half(static_cast<unsigned short>(l2 & 0xffffu));
 }
 
 __device__ __forceinline__ void store_split4(__half* hi_ptr, __half* lo_ptr, float4 v) {
-    __half h[4], l[4];
-    split_f16(v.x, h[0], l[0]);
-    split_f16(v.y, h[1], l[1]);
-    split_f16(v.z, h[2], l[2]);
-    split_f16(v.w, h[3], l[3]);
-    *reinterpret_cast<uint2*>(hi_ptr) = *reinterpret_cast<uint2*>(h);
-    *reinterpret_cast<uint2*>(lo_ptr) = *reinterpret_cast<uint2*>(l);
+    uint2 h, l;
+    split_f16x2(v.x, v.y, h.x, l.x);
+    split_f16x2(v.z, v.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(hi_ptr) = h;
+    *reinterpret_cast<uint2*>(lo_ptr) = l;
 }
 
 // Opt-in device trace (s3d_unet_trace_enable): one thread per CTA stamps %globaltimer (ns, chip-wide) and clock64 (SM
@@ -86,12 +98,10 @@ __device__ __forceinline__ float4 join_halves4(uint2 hi, uint2 lo) {
 }
 // value of v after a round trip through store_split4 (no memory access: recomputed from the same roundings)
 __device__ __forceinline__ float4 roundtrip_split4(float4 v) {
-    __half h[4], l[4];
-    split_f16(v.x, h[0], l[0]);
-    split_f16(v.y, h[1], l[1]);
-    split_f16(v.z, h[2], l[2]);
-    split_f16(v.w, h[3], l[3]);
-    return join_halves4(*reinterpret_cast<uint2*>(h), *reinterpret_cast<uint2*>(l));
+    uint2 h, l;
+    split_f16x2(v.x, v.y, h.x, l.x);
+    split_f16x2(v.z, v.w, h.y, l.y);
+    return join_halves4(h, l);
 }
 
 // Composed-layout address of plane pixel (r, c): [H+D, W+D] with yz stored transposed.

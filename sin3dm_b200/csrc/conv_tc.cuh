@@ -423,15 +423,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                             for (int i = 0; i < kBatch; ++i) {
                                 const int q = et + kEpiThreads * (hb * kBatch + i), j = q >> 3, k = q & 7;
                                 if (q < kChunks) {
-                                    __half h[8], l[8];
+                                    uint32_t h[4], l[4];
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        split_f16(__ll2float_rn(static_cast<long long>(raw[i][e].x)) * scale, h[2 * e], l[2 * e]);
-                                        split_f16(__ll2float_rn(static_cast<long long>(raw[i][e].y)) * scale, h[2 * e + 1], l[2 * e + 1]);
-                                    }
+                                    for (int e = 0; e < 4; ++e)
+                                        split_f16x2(__ll2float_rn(static_cast<long long>(raw[i][e].x)) * scale,
+                                                    __ll2float_rn(static_cast<long long>(raw[i][e].y)) * scale, h[e], l[e]);
                                     const uint32_t off = static_cast<uint32_t>(j) * 128u + (static_cast<uint32_t>(k ^ (j & 7)) << 4);
-                                    *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
-                                    if (NSPLIT == 3) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+                                    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                                    if (NSPLIT == 3) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
                                 }
                             }
                         }
