@@ -37,7 +37,9 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 __device__ __forceinline__ float silu_f(float v) {
     // x * sigmoid(x), reference src/diffusion/nn.py:12-14.  ex2.approx + rcp: ~1e-6 relative.
-    return __fdividef(v, 1.f + __expf(-v));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + __expf(-v)));     // 1 + e^-v >= 1: no range handling needed
+    return v * r;
 }
 
 // fp32 -> (hi, lo) fp16 pair with v ~= hi + lo / 2048, |err| <= 2^-22 |v|.  Saturating: the conversions are
@@ -52,7 +54,9 @@ __device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo_elem, float hi_elem) 
 __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
     hi2 = cvt_f16x2_sat(a, b);
     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
-    lo2 = cvt_f16x2_sat((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
+    // packed fp32x2 arithmetic (sm_100): one FADD2 + one FMUL2 for the pair; both steps are exact in fp32
+    const float2 d = __fmul2_rn(__fadd2_rn(make_float2(a, b), make_float2(-hf.x, -hf.y)), make_float2(kLoScale, kLoScale));
+    lo2 = cvt_f16x2_sat(d.x, d.y);
 }
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
     uint32_t h2, l2;
