@@ -47,6 +47,11 @@ struct ConvTcArgs {
     int tile_start[4];   // prefix sum of tiles per plane
     ConvEpi e;
     StatsSink sink;      // GroupNorm group sums of the output (sink.acc == nullptr: none); needs 64 % (Cout/32) == 0
+    // Fused TriplaneDownsample2x (unet_triplane.py:127-145, avg_pool2d k2 s2, floor on odd sizes): when pool.p[0] != nullptr the
+    // epilogue also writes the 2x2-averaged output [B][rows/2][cols/2][Cout] and its GroupNorm group sums (a tile is 16 x 8 pixels
+    // at an even origin, so every pooled pixel lies inside one warp's rows).  Saves the k_avgpool2 launch and its re-read.
+    TriF pool;
+    StatsSink pool_sink;
     Trace tr;            // opt-in phase stamps (common.cuh)
     int bo_kw;           // bring-up switch (S3D_HALO_BO_KW=1): put kw into the descriptor base_offset (measured WRONG on B200:
                          // the tensor core derives the swizzle phase from the absolute shared-memory address)
@@ -595,6 +600,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             fold(D, add);
             const bool do_stats = A.sink.acc != nullptr;
             float4 ssum = zero4, ssq = zero4;
+            float* __restrict__ poolb = A.pool.p[plane];
+            float4 pv[2][2] = {{zero4, zero4}, {zero4, zero4}};      // [row pair][column half]: vertical sums of this thread's pixels
             {
                 uint32_t v1[32], v2[32];
                 ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
@@ -631,53 +638,79 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
                         ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
                         ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+                        if (poolb) {
+                            float4& a2 = pv[it >> 2][it & 1];
+                            a2.x += o.x; a2.y += o.y; a2.z += o.z; a2.w += o.w;
+                        }
                     }
                 }
                 __syncwarp();                      // the staging block is rewritten by the next tile
             }
-            if (do_stats) {
-                // (sum, sum-sq) per channel over the warp's 32 pixels: the four row groups of a lane column are added in a fixed
-                // order, then every GroupNorm group goes out as one fixed-point atomic (exact, so the order of the warps and
-                // tiles does not matter)
+            // (sum, sum-sq) per channel over the warp's pixels: the four row groups of a lane column are added in a fixed order, then
+            // every GroupNorm group goes out as one fixed-point atomic (exact, so the order of the warps and tiles does not matter)
+            auto emit_stats = [&](const StatsSink& sink, const float4& su, const float4& sq) {
                 constexpr unsigned kFull = 0xffffffffu;
                 const int cpg = Cout / kGroups;              // 2, 4 or 8 (host-checked)
-                {
-                    float v[8] = {ssum.x, ssum.y, ssum.z, ssum.w, ssq.x, ssq.y, ssq.z, ssq.w};
+                float v[8] = {su.x, su.y, su.z, su.w, sq.x, sq.y, sq.z, sq.w};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        v[e] += __shfl_xor_sync(kFull, v[e], 8);
-                        v[e] += __shfl_xor_sync(kFull, v[e], 16);
-                    }
-                    // lanes 0..7 now hold channels n0 + half*32 + 4*k8 .. +3
-                    double gs[2][2];                          // [group inside the quad][sum / sum-sq]
-                    if (cpg == 2) {
-                        gs[0][0] = static_cast<double>(v[0]) + static_cast<double>(v[1]);
-                        gs[1][0] = static_cast<double>(v[2]) + static_cast<double>(v[3]);
-                        gs[0][1] = static_cast<double>(v[4]) + static_cast<double>(v[5]);
-                        gs[1][1] = static_cast<double>(v[6]) + static_cast<double>(v[7]);
-                    } else {
-                        gs[0][0] = (static_cast<double>(v[0]) + static_cast<double>(v[1])) + (static_cast<double>(v[2]) + static_cast<double>(v[3]));
-                        gs[0][1] = (static_cast<double>(v[4]) + static_cast<double>(v[5])) + (static_cast<double>(v[6]) + static_cast<double>(v[7]));
-                        gs[1][0] = gs[1][1] = 0.0;
-                        if (cpg == 8) {                       // a group spans two neighbouring lanes
-                            gs[0][0] += __shfl_xor_sync(kFull, gs[0][0], 1);
-                            gs[0][1] += __shfl_xor_sync(kFull, gs[0][1], 1);
-                        }
-                    }
-                    if (lane < 8) {
-                        const int ch = n0 + half * 32 + 4 * k8;
-                        unsigned long long* acc = gn_acc(A.sink.acc, b, plane, T.ip * 4 + quarter);
-                        if (cpg == 2) {
-                            gn_fix_add(acc + (ch / 2) * 2, gs[0][0]);
-                            gn_fix_add(acc + (ch / 2) * 2 + 1, gs[0][1]);
-                            gn_fix_add(acc + (ch / 2 + 1) * 2, gs[1][0]);
-                            gn_fix_add(acc + (ch / 2 + 1) * 2 + 1, gs[1][1]);
-                        } else if (cpg == 4 || (lane & 1) == 0) {
-                            gn_fix_add(acc + (ch / cpg) * 2, gs[0][0]);
-                            gn_fix_add(acc + (ch / cpg) * 2 + 1, gs[0][1]);
-                        }
+                for (int e = 0; e < 8; ++e) {
+                    v[e] += __shfl_xor_sync(kFull, v[e], 8);
+                    v[e] += __shfl_xor_sync(kFull, v[e], 16);
+                }
+                // lanes 0..7 now hold channels n0 + half*32 + 4*k8 .. +3
+                double gs[2][2];                          // [group inside the quad][sum / sum-sq]
+                if (cpg == 2) {
+                    gs[0][0] = static_cast<double>(v[0]) + static_cast<double>(v[1]);
+                    gs[1][0] = static_cast<double>(v[2]) + static_cast<double>(v[3]);
+                    gs[0][1] = static_cast<double>(v[4]) + static_cast<double>(v[5]);
+                    gs[1][1] = static_cast<double>(v[6]) + static_cast<double>(v[7]);
+                } else {
+                    gs[0][0] = (static_cast<double>(v[0]) + static_cast<double>(v[1])) + (static_cast<double>(v[2]) + static_cast<double>(v[3]));
+                    gs[0][1] = (static_cast<double>(v[4]) + static_cast<double>(v[5])) + (static_cast<double>(v[6]) + static_cast<double>(v[7]));
+                    gs[1][0] = gs[1][1] = 0.0;
+                    if (cpg == 8) {                       // a group spans two neighbouring lanes
+                        gs[0][0] += __shfl_xor_sync(kFull, gs[0][0], 1);
+                        gs[0][1] += __shfl_xor_sync(kFull, gs[0][1], 1);
                     }
                 }
+                if (lane < 8) {
+                    const int ch = n0 + half * 32 + 4 * k8;
+                    unsigned long long* acc = gn_acc(sink.acc, b, plane, T.ip * 4 + quarter);
+                    if (cpg == 2) {
+                        gn_fix_add(acc + (ch / 2) * 2, gs[0][0]);
+                        gn_fix_add(acc + (ch / 2) * 2 + 1, gs[0][1]);
+                        gn_fix_add(acc + (ch / 2 + 1) * 2, gs[1][0]);
+                        gn_fix_add(acc + (ch / 2 + 1) * 2 + 1, gs[1][1]);
+                    } else if (cpg == 4 || (lane & 1) == 0) {
+                        gn_fix_add(acc + (ch / cpg) * 2, gs[0][0]);
+                        gn_fix_add(acc + (ch / cpg) * 2 + 1, gs[0][1]);
+                    }
+                }
+            };
+            if (do_stats) emit_stats(A.sink, ssum, ssq);
+            if (poolb) {
+                // 2x2 average: the vertical pair was added above, the horizontal neighbour (column +1) lives 8 lanes up
+                const int prow_n = rows >> 1, pcol_n = cols >> 1;
+                float4 psum = zero4, psq = zero4;
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+                    for (int hc = 0; hc < 2; ++hc) {
+                        float4 q = pv[pr][hc];
+                        q.x += __shfl_xor_sync(0xffffffffu, q.x, 8);
+                        q.y += __shfl_xor_sync(0xffffffffu, q.y, 8);
+                        q.z += __shfl_xor_sync(0xffffffffu, q.z, 8);
+                        q.w += __shfl_xor_sync(0xffffffffu, q.w, 8);
+                        const int prw = (r0 >> 1) + pr, pcl = (T.w0 >> 1) + hc * 2 + (rloc >> 1);
+                        if ((rloc & 1) == 0 && prw < prow_n && pcl < pcol_n) {
+                            q.x *= 0.25f; q.y *= 0.25f; q.z *= 0.25f; q.w *= 0.25f;
+                            *reinterpret_cast<float4*>(poolb + ((static_cast<size_t>(b) * prow_n + prw) * pcol_n + pcl) * Cout + n0 + half * 32 + 4 * k8) = q;
+                            psum.x += q.x; psum.y += q.y; psum.z += q.z; psum.w += q.w;
+                            psq.x = fmaf(q.x, q.x, psq.x); psq.y = fmaf(q.y, q.y, psq.y);
+                            psq.z = fmaf(q.z, q.z, psq.z); psq.w = fmaf(q.w, q.w, psq.w);
+                        }
+                    }
+                if (A.pool_sink.acc) emit_stats(A.pool_sink, psum, psq);
             }
             if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 4);
         }

@@ -127,6 +127,7 @@ struct s3d_unet {
     int num_sms = 148;
     bool fuse_roll = true;   // S3D_FUSE_ROLL=0 launches the rollout 1-D GEMM separately
     bool halo_bo_kw = false;
+    bool fuse_pool = true;      // S3D_FUSE_POOL=0: stand-alone k_avgpool2 instead of pooling in the conv epilogue
     bool trace_on = false;   // s3d_unet_trace_enable
     int profile_mode = -1;   // last s3d_unet_profile_ops: 1 = graph replay with event nodes, 0 = eager launches
 };
@@ -844,8 +845,9 @@ struct PlanBuilder {
     }
 
     // ---- 3x3 conv (+ fused 1x1 skip)
+    // pool_out != nullptr (tcgen05 path only): the epilogue also writes the 2x2-averaged output and its GroupNorm sums
     void conv(const Act16& a, int level, const DevConv3& cv, const TBuf* T, const Act16* x16, const ActF* resid, int emb_off,
-              ActF& out) {
+              ActF& out, ActF* pool_out = nullptr) {
         const TriDims d = dims[level];
         ConvEpi e{};
         e.bias = cf3(cv.bias);
@@ -930,6 +932,15 @@ struct PlanBuilder {
             box = make_box(cv.Cout);
             out.sink = box;
         }
+        std::shared_ptr<SinkBox> pbox;
+        if (pool_out) {
+            S3D_CHECK(box != nullptr, "fused pooling needs the statistics epilogue");
+            for (int p = 0; p < 3; ++p)
+                S3D_CHECK(dims[level + 1].rows[p] == d.rows[p] / 2 && dims[level + 1].cols[p] == d.cols[p] / 2, "pooled plane size");
+            A.pool = pool_out->p;
+            pbox = make_box(cv.Cout);
+            pool_out->sink = pbox;
+        }
         FusedRoll F{};
         auto rmaps = std::make_shared<RollTcMaps>();
         memset(rmaps.get(), 0, sizeof(RollTcMaps));
@@ -947,6 +958,7 @@ struct PlanBuilder {
         add_op("k_conv_tc", conv_flops(level, cv), [=](cudaStream_t s) {
             ConvTcArgs Al = A;
             Al.sink = live_sink(box);
+            if (pbox) Al.pool_sink = live_sink(pbox);
             if (use_emb) {
                 Al.e.embadd = Pp->film;
                 Al.e.film_row = Pp->film_row;
@@ -962,7 +974,7 @@ struct PlanBuilder {
     // One TriplaneResBlock (unet_triplane.py:269-311).  The input is either the fp32 residual stream `x`, or — for the decoder
     // blocks behind a concat — the (hi, lo) fp16 tensor `xh` that k_upcat wrote (it doubles as the skip GEMM's operand).
     // Buffers go back to the arena as soon as their last reader is planned; the caller releases the block's input.
-    ActF res_block(int bi, const ActF* x, const Act16* xh, const std::shared_ptr<SinkBox>& xh_sink, int level) {
+    ActF res_block(int bi, const ActF* x, const Act16* xh, const std::shared_ptr<SinkBox>& xh_sink, int level, ActF* pool_out = nullptr) {
         const BlockSpec& b = u->blocks[bi];
         const DevBlock& w = u->dblocks[bi];
         const bool ro = u->cfg.rollout, ssn = u->cfg.use_scale_shift_norm;
@@ -997,7 +1009,7 @@ struct PlanBuilder {
         TBuf t2{};
         if (ro) t2 = roll1d(s2, level, w.c2);
         ActF out = allocF(level, b.cout, b.name + ".out");
-        conv(a2, level, w.c2, ro ? &t2 : nullptr, b.has_skip ? &x16 : nullptr, b.has_skip ? nullptr : x, -1, out);
+        conv(a2, level, w.c2, ro ? &t2 : nullptr, b.has_skip ? &x16 : nullptr, b.has_skip ? nullptr : x, -1, out, pool_out);
         release(a2);
         if (b.has_skip && x) release(x16);
         return out;
@@ -1118,12 +1130,30 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     }
     // ---- encoder
     std::vector<ActF> stack;
+    ActF pooled{};
+    bool have_pooled = false;     // the Downsample2x of the next level was produced by the previous block's last conv
     for (int l = 0; l < c.n_levels; ++l) {
-        for (const auto& op : u->downs[l]) {
+        const auto& ops = u->downs[l];
+        for (size_t oi = 0; oi < ops.size(); ++oi) {
+            const auto& op = ops[oi];
             if (op.kind == 1) {
-                h = pb.down(h, l);            // its input stays alive: it is the previous level's skip
+                if (have_pooled) {
+                    h = pooled;               // (the block output stays alive: it is the previous level's skip)
+                    have_pooled = false;
+                } else {
+                    h = pb.down(h, l);        // its input stays alive: it is the previous level's skip
+                }
             } else {
-                ActF o = pb.res_block(op.block, &h, nullptr, nullptr, h.level);
+                // last block of the level, next level opens with a Downsample2x: fuse the pooling into this block's last conv
+                const bool fuse = u->cfg.conv_impl == 0 && u->fuse_pool && oi + 1 == ops.size() && l + 1 < c.n_levels &&
+                                  !u->downs[l + 1].empty() && u->downs[l + 1][0].kind == 1 &&
+                                  (u->blocks[op.block].cout / kGroups == 2 || u->blocks[op.block].cout / kGroups == 4 ||
+                                   u->blocks[op.block].cout / kGroups == 8) && u->blocks[op.block].cout % 64 == 0;
+                if (fuse) {
+                    pooled = pb.allocF(h.level + 1, u->blocks[op.block].cout, "down." + std::to_string(l + 1));
+                    have_pooled = true;
+                }
+                ActF o = pb.res_block(op.block, &h, nullptr, nullptr, h.level, fuse ? &pooled : nullptr);
                 pb.release(h);
                 h = o;
             }
@@ -1304,6 +1334,7 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     if (const char* e = getenv("S3D_FUSE_ROLL")) u->fuse_roll = atoi(e) != 0;
     if (const char* e = getenv("S3D_PDL")) g_pdl = atoi(e) != 0;
     if (const char* e = getenv("S3D_HALO_BO_KW")) u->halo_bo_kw = atoi(e) != 0;
+    if (const char* e = getenv("S3D_FUSE_POOL")) u->fuse_pool = atoi(e) != 0;
     build_structure(u.get());
     *out = u.release();
     API_END
