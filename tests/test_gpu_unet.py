@@ -159,3 +159,25 @@ def test_full_size_ddim_loop_matches_oracle():
     rel, mx = plane_errors(got, want, H, W, D)
     print("cfg3 ddim-3 rel_l2", rel, "max", mx)
     assert rel < TOL and mx < TOL, (rel, mx)
+
+
+@pytest.mark.parametrize("name", ["small_odd", "three_level"])
+def test_fused_pool_equals_standalone_pool(name, monkeypatch):
+    """Downsample2x computed in the conv epilogue (default) vs the stand-alone k_avgpool2 launch (S3D_FUSE_POOL=0): same values up
+    to the order of the four additions, odd plane sizes (floor pooling) included."""
+    case = UNET_CASES[name]
+    spec = ur.UNetSpec(**case["spec"])
+    sd = ur.synthetic_state_dict(spec, case["wseed"])
+    x, t = make_inputs(case)
+    H, W, D = case["HWD"]
+    from sin3dm_b200 import _lib
+    outs, launches = [], []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("S3D_FUSE_POOL", flag)          # read when the handle is created
+        m = make_cuda_model(spec, sd, 3, "tc")
+        with torch.no_grad():
+            outs.append(m(x.cuda(), t.cuda(), H=H, W=W, D=D).cpu())
+        launches.append(_lib.lib().s3d_unet_last_launches(m.handle()))
+    rel, mx = plane_errors(outs[0], outs[1], H, W, D)
+    assert rel < 2e-5 and mx < 2e-5, (rel, mx)
+    assert launches[1] > launches[0], launches          # one k_avgpool2 launch per Downsample2x comes back
