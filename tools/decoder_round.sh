@@ -1,3 +1,4 @@
+# One GPU call for the auto-encoder kernels: decoder parity tests, encode benchmark, ncu capture.  usage: bash tools/decoder_round.sh <tag>
 mkdir -p gpurun_out
 tag=${1:-e1}
 timeout 600 python -m pytest tests/test_gpu_decoder.py -m gpu -x -q > gpurun_out/pytest_dec_$tag.log 2>&1; tail -3 gpurun_out/pytest_dec_$tag.log
