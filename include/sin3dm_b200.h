@@ -233,7 +233,9 @@ int s3d_decoder_decode_grid(s3d_decoder* d, const float* xs_dev, const float* ys
  * fp32 -> the three latent planes xy [C, H, W], xz [C, H, D], yz [C, W, D], C = geo (+ tex) feature channels and
  * (H, W, D) = ((X-2)/2+1, (Y-2)/2+1, (Z-2)/2+1) (Conv3d k 4, stride 2, pad 1).  The strided convolutions, the three axis means
  * (64-bit fixed-point sums: results do not depend on tile order), InstanceNorm2d and tanh(x/2) run in two launches; the
- * [C, H, W, D] feature volume is never written.  Needs the geo_encoder.* (+ tex_encoder.*) tensors loaded. */
+ * [C, H, W, D] feature volume is never written.  Needs the geo_encoder.* (+ tex_encoder.*) tensors loaded.  The reference
+ * defaults (fdim_geo 4; sdf only or fdim_tex 8 + rgb) take the specialised kernels, any other configuration (<= 32 latent
+ * channels) a generic direct convolution. */
 int s3d_decoder_encode(s3d_decoder* d, const float* vol_dev, int X, int Y, int Z, float* xy_dev, float* xz_dev, float* yz_dev,
                        void* stream);
 /* Kernel launches issued by the last set_planes / decode / encode call (bench accounting). */

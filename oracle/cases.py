@@ -136,6 +136,8 @@ ENCODER_CASES = {
     "sdf_only": dict(spec=dict(use_tex=False, tex_feat_channels=0), wseed=93, XYZ=(12, 20, 16), seed=97),
     # Z % 4 == 0 with colour: the TMA-staged kernel, several z tiles with a ragged last one
     "aligned": dict(spec=dict(), wseed=94, XYZ=(10, 14, 148), seed=98),
+    # non-default channel counts (fdim_geo 3, fdim_tex 5, two colour channels): the generic direct-convolution kernel
+    "custom": dict(spec=dict(geo_feat_channels=3, tex_feat_channels=5, tex_channels=2), wseed=99, XYZ=(14, 11, 150), seed=100),
 }
 
 

@@ -68,6 +68,7 @@ struct s3d_decoder {
     // encoder: fixed-point axis sums of the current volume
     unsigned long long* enc_sums = nullptr;
     size_t enc_sums_count = 0;
+    float* enc_w[4] = {nullptr, nullptr, nullptr, nullptr};     // generic-encoder weights (freed with `owned`; reset by finalize)
 };
 
 namespace {
@@ -182,6 +183,7 @@ void finalize(s3d_decoder* d) {
         if (t.needed && !t.loaded) throw S3dError{"checkpoint tensor not loaded: " + t.name};
     for (void* p : d->owned) cudaFree(p);
     d->owned.clear();
+    for (auto& p : d->enc_w) p = nullptr;
     d->tc_ok = up == kDecUp && hid == kDecHid && c.mlp_hidden_layers == 4 && c.tex_channels <= 4;
     for (int b = 0; b < d->nb; ++b) {
         Branch& B = d->br[b];
@@ -454,7 +456,26 @@ void encode(s3d_decoder* d, const float* vol, int X, int Y, int Z, float* xy, fl
     a.out[0] = xy; a.out[1] = xz; a.out[2] = yz;
     if (c.geo_feat_channels == 4 && c.use_tex && c.tex_feat_channels == 8 && c.tex_channels == 3) launch_encode<4, 8, 4>(d, a, st);
     else if (c.geo_feat_channels == 4 && !c.use_tex) launch_encode<4, 0, 0>(d, a, st);
-    else S3D_CHECK(false, "the encoder kernel is specialised for the reference defaults: fdim_geo 4 and (sdf only | fdim_tex 8 with rgb)");
+    else {
+        // other channel configurations: generic direct convolution (weights uploaded on first use)
+        S3D_CHECK(C <= kEncMaxC, "the encoder supports at most 32 latent channels");
+        S3D_CHECK(a.W < 65536 && a.H < 65536, "volume too large for one launch");
+        if (!d->enc_w[0]) {
+            d->enc_w[0] = dev_upload(d->owned, T_(d, "geo_encoder.weight").host);
+            d->enc_w[1] = dev_upload(d->owned, T_(d, "geo_encoder.bias").host);
+            if (c.use_tex) {
+                d->enc_w[2] = dev_upload(d->owned, T_(d, "tex_encoder.weight").host);
+                d->enc_w[3] = dev_upload(d->owned, T_(d, "tex_encoder.bias").host);
+            }
+        }
+        EncGenericW gw{};
+        gw.wg = d->enc_w[0]; gw.bg = d->enc_w[1]; gw.wt = d->enc_w[2]; gw.bt = d->enc_w[3];
+        gw.GEO = c.geo_feat_channels;
+        gw.TEX = c.use_tex ? c.tex_feat_channels : 0;
+        gw.CT = c.use_tex ? c.tex_channels + 1 : 0;
+        launch(k_enc_conv3d_generic, dim3((a.D + 127) / 128, a.W, a.H), dim3(128), 0, st, gw, a);
+        launch(k_enc_finalize, dim3(C, 3), dim3(kEncFinThreads), 0, st, a);
+    }
     d->last_launches = 2;
 }
 

@@ -942,6 +942,65 @@ __global__ void __launch_bounds__(128) k_enc_conv3d_tma(const __grid_constant__ 
     }
 }
 
+// Any channel configuration (fdim_geo / fdim_tex / tex_channels other than the reference defaults): straightforward direct
+// convolution, one thread per output voxel, weights read through the read-only cache.  Same fixed-point axis sums, so
+// k_enc_finalize is shared.  grid (ceil(D/128), W, H), block 128 (lane = z).
+constexpr int kEncMaxC = 32;
+struct EncGenericW {
+    const float *wg, *bg;      // [GEO][1][64], [GEO]
+    const float *wt, *bt;      // [TEX][CT][64], [TEX]   (nullptr without colour)
+    int GEO, TEX, CT;
+};
+__global__ void __launch_bounds__(128) k_enc_conv3d_generic(const EncGenericW Wt, const EncArgs A) {
+    const int d = blockIdx.x * 128 + threadIdx.x, w = blockIdx.y, h = blockIdx.z;
+    const int C = Wt.GEO + Wt.TEX;
+    const bool valid = d < A.D;
+    float acc[kEncMaxC];
+#pragma unroll
+    for (int c = 0; c < kEncMaxC; ++c) acc[c] = 0.f;
+    if (valid) {
+        for (int c = 0; c < Wt.GEO; ++c) acc[c] = __ldg(Wt.bg + c);
+        for (int c = 0; c < Wt.TEX; ++c) acc[Wt.GEO + c] = __ldg(Wt.bt + c);
+        const int nin = Wt.TEX > 0 ? Wt.CT : 1;
+        for (int ci = 0; ci < nin; ++ci)
+            for (int kx = 0; kx < 4; ++kx) {
+                const int ix = 2 * h - 1 + kx;
+                if (ix < 0 || ix >= A.X) continue;
+                for (int ky = 0; ky < 4; ++ky) {
+                    const int iy = 2 * w - 1 + ky;
+                    if (iy < 0 || iy >= A.Y) continue;
+                    const float* row = A.vol + ((static_cast<size_t>(ci) * A.X + ix) * A.Y + iy) * A.Z;
+                    for (int kz = 0; kz < 4; ++kz) {
+                        const int iz = 2 * d - 1 + kz;
+                        if (iz < 0 || iz >= A.Z) continue;
+                        const float v = __ldg(row + iz);
+                        const int tap = kx * 16 + ky * 4 + kz;
+                        if (ci == 0)
+                            for (int c = 0; c < Wt.GEO; ++c) acc[c] = fmaf(v, __ldg(Wt.wg + c * 64 + tap), acc[c]);
+                        for (int c = 0; c < Wt.TEX; ++c) acc[Wt.GEO + c] = fmaf(v, __ldg(Wt.wt + (c * Wt.CT + ci) * 64 + tap), acc[Wt.GEO + c]);
+                    }
+                }
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < kEncMaxC; ++c) {
+        if (c < C) {                                           // uniform
+            const float v = valid ? acc[c] : 0.f;
+            float s = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) == 0)
+                atomicAdd(A.sums[0] + (static_cast<size_t>(c) * A.H + h) * A.W + w,
+                          static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(s) * kEncFix)));
+            if (valid) {
+                const unsigned long long f = static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v) * kEncFix));
+                atomicAdd(A.sums[1] + (static_cast<size_t>(c) * A.H + h) * A.D + d, f);
+                atomicAdd(A.sums[2] + (static_cast<size_t>(c) * A.W + w) * A.D + d, f);
+            }
+        }
+    }
+}
+
 // grid (C, 3), block 1024: the plane's values are formed once and kept in registers (<= 16 per thread covers 128 x 128)
 constexpr int kEncFinThreads = 1024, kEncFinKeep = 16;
 __global__ void __launch_bounds__(kEncFinThreads) k_enc_finalize(const EncArgs A) {

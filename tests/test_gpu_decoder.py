@@ -118,7 +118,7 @@ def test_empty_and_single_point():
 
 
 # ------------------------------------------------------------------------------------------------ encoder half
-@pytest.mark.parametrize("name", ["default", "odd", "sdf_only", "aligned"])
+@pytest.mark.parametrize("name", ["default", "odd", "sdf_only", "aligned", "custom"])
 def test_encode_matches_reference_golden(golden_dir, name):
     """AutoEncoderGroupSkip.encode (networks.py:164-180) through s3d_decoder_encode vs the real reference's planes."""
     from oracle.cases import ENCODER_CASES, make_encoder_inputs
