@@ -316,7 +316,7 @@ def run_ours(args, wl):
                 pass
             roof = dict(bound="tensor", kernel="k_conv_tc (8 launches/step, fp16x3 split => 3 tcgen05.mma per dense MAC tile)",
                         achieved=ach, peak=peaks["tflops"], unit="TFLOP/s", frac=ach / peaks["tflops"], traffic=traffic,
-                        traffic_unit="DRAM bytes per k_conv_tc launch (mean of the 8 launches of a step; profiles/r1c_step_ncu_full.md)",
+                        traffic_unit="DRAM bytes per k_conv_tc launch (mean of the 8 launches of a step; profiles/r1d_step_ncu_full.md)",
                         peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
                         flops_per_step_dense=conv_fl, conv_ms_per_step=conv_ms, conv_share_of_event_timed_step=conv_ms / tot_ms,
                         timing="graph replay with event-record nodes" if L.s3d_unet_profile_mode(h) == 1 else "eager launches",
