@@ -157,6 +157,23 @@ int s3d_vb_terms(const s3d_vb_args* a, void* stream);
  * mse_yz.  One pass, fixed-order fp64 reduction.  workspace: s3d_vb_workspace_bytes(B, C*(H+D)*(W+D)) bytes. */
 int s3d_plane_mse(const float* target_dev, const float* output_dev, int B, int C, int H, int W, int D, void* workspace, float* out_dev,
                   void* stream);
+/* ---- fused optimizer step (replaces torch.optim.AdamW.step() + update_ema of TrainLoop.run_step, train_util.py:82-84, 160-167,
+ * 237-239; nn.py:53-63) over ONE flat fp32 parameter buffer: decoupled weight decay, Adam moments with bias correction, parameter
+ * update, then ema[k] = ema[k] * ema_rate[k] + param * (1 - ema_rate[k]) for up to four EMA copies — a single HBM pass.
+ * `step` is the 1-based count of this update; lr is the (possibly annealed) rate of this step.  All buffers 16-byte aligned. */
+typedef struct {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    float* ema[4];
+    float ema_rate[4];
+    int n_ema;
+    int64_t n;
+    double lr, beta1, beta2, eps, weight_decay;   /* python floats, as torch.optim receives them */
+    int step;
+} s3d_adamw_args;
+int s3d_adamw_ema_step(const s3d_adamw_args* a, void* stream);
 /* N(0,1) fill [B, C, hw] with the same counter-based generator the sampler uses (noise of sample s at step i). */
 int s3d_philox_normal(float* out_dev, int B, int C, int64_t hw, uint64_t seed, uint32_t sample_base, uint32_t step,
                       void* stream);

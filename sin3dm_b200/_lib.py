@@ -37,6 +37,13 @@ class VbArgs(C.Structure):
                 ("t_idx_dev", C.c_void_p), ("workspace", C.c_void_p), ("out", C.c_void_p)]
 
 
+class AdamWArgs(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("ema", C.c_void_p * 4), ("ema_rate", C.c_float * 4), ("n_ema", C.c_int), ("n", C.c_int64),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
+                ("step", C.c_int)]
+
+
 class LoopArgs(C.Structure):
     _fields_ = [("kind", C.c_int), ("mean_type", C.c_int), ("clip_denoised", C.c_int), ("is_mask_t0", C.c_int),
                 ("n_steps", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("D", C.c_int),
@@ -86,6 +93,7 @@ _SIGNATURES = {
     "s3d_vb_terms": (C.c_int, [C.POINTER(VbArgs), C.c_void_p]),
     "s3d_plane_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    "s3d_adamw_ema_step": (C.c_int, [C.POINTER(AdamWArgs), C.c_void_p]),
     "s3d_sample_loop": (C.c_int, [C.c_void_p, C.POINTER(LoopArgs), C.c_void_p]),
     "s3d_decoder_create": (C.c_int, [C.POINTER(DecoderConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "s3d_decoder_destroy": (C.c_int, [C.c_void_p]),

@@ -1528,6 +1528,39 @@ int s3d_plane_mse(const float* target_dev, const float* output_dev, int B, int C
     API_END
 }
 
+int s3d_adamw_ema_step(const s3d_adamw_args* a, void* stream) {
+    API_BEGIN
+    S3D_CHECK(a && a->param && a->grad && a->exp_avg && a->exp_avg_sq && a->n >= 1 && a->step >= 1, "bad argument");
+    S3D_CHECK(a->n_ema >= 0 && a->n_ema <= 4, "at most 4 EMA buffers");
+    S3D_CHECK(((reinterpret_cast<uintptr_t>(a->param) | reinterpret_cast<uintptr_t>(a->grad) | reinterpret_cast<uintptr_t>(a->exp_avg) |
+                reinterpret_cast<uintptr_t>(a->exp_avg_sq)) & 15) == 0, "buffers must be 16-byte aligned");
+    AdamWArgs A{};
+    A.p = a->param;
+    A.g = a->grad;
+    A.m = a->exp_avg;
+    A.v = a->exp_avg_sq;
+    A.n_ema = a->n_ema;
+    for (int k = 0; k < a->n_ema; ++k) {
+        S3D_CHECK(a->ema[k] && (reinterpret_cast<uintptr_t>(a->ema[k]) & 15) == 0, "EMA buffer missing or misaligned");
+        A.ema[k] = a->ema[k];
+        A.ema_rate[k] = a->ema_rate[k];
+    }
+    A.n = a->n;
+    // scalars exactly as torch forms them: python floats (fp64), rounded to fp32 where they meet the tensors
+    const double lr = a->lr, b1 = a->beta1, b2 = a->beta2;
+    A.decay = static_cast<float>(1.0 - lr * a->weight_decay);
+    A.w1 = static_cast<float>(1.0 - b1);
+    A.beta2 = static_cast<float>(b2);
+    A.w2 = static_cast<float>(1.0 - b2);
+    A.bc2_sqrt = static_cast<float>(std::sqrt(1.0 - std::pow(b2, a->step)));
+    A.step_size = static_cast<float>(lr / (1.0 - std::pow(b1, a->step)));
+    A.eps = static_cast<float>(a->eps);
+    const int gx = static_cast<int>(std::min<long long>((A.n / 4 + 255) / 256 + 1, 148LL * 8));
+    launch(k_adamw_ema, dim3(gx), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
+    LAUNCH_CHECK("k_adamw_ema");
+    API_END
+}
+
 int s3d_philox_normal(float* out_dev, int B, int C, int64_t hw, uint64_t seed, uint32_t sample_base, uint32_t step, void* stream) {
     API_BEGIN
     S3D_CHECK(out_dev && B >= 1 && C >= 1 && hw >= 1, "bad argument");
