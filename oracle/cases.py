@@ -154,3 +154,20 @@ def make_encoder_inputs(case):
     if spec.use_tex:
         chans += [torch.rand(X, Y, Z, generator=g) for _ in range(spec.tex_channels)]
     return torch.stack(chans, dim=0)[None].contiguous()
+
+
+# ---------------------------------------------------------------------------- parameter gradients (training row, groundwork)
+GRAD_CASES = {
+    "startx": dict(spec=dict(**SMALL), wseed=111, HWD=(12, 16, 10), B=2, T=1000, respacing="", seed=121, t=[3, 871]),
+    "eps_odd": dict(spec=dict(**SMALL), wseed=112, HWD=(9, 14, 7), B=1, T=1000, respacing="", mean_type="epsilon", seed=122, t=[456]),
+}
+
+
+def make_grad_inputs(case):
+    """-> (x_start in [-1, 1], q_sample noise, t)."""
+    H, W, D = case["HWD"]
+    shape = (case["B"], case["spec"]["in_channels"], H + D, W + D)
+    g = torch.Generator().manual_seed(case["seed"])
+    x0 = torch.rand(shape, generator=g) * 2 - 1
+    nz = torch.randn(shape, generator=g)
+    return x0, nz, torch.tensor(case["t"])
