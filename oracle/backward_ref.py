@@ -14,6 +14,8 @@ that already has their structure:
   * the mean's own adjoint: divide by the averaged length and broadcast back into the source plane.
 
 ``tri_conv_backward_folded`` is checked against torch.autograd through ``oracle.unet_ref.tri_conv`` (tests/test_oracle_backward.py).
+The file also states, in the form a kernel would use, the backward of GroupNorm (+ FiLM) + SiLU (two reductions per group, then one
+apply pass) and the adjoints of the 2x2 average pool and of the bilinear resamplings (gather form), each checked against autograd.
 """
 from typing import Dict, Sequence, Tuple
 
@@ -74,3 +76,77 @@ def tri_conv_backward_folded(sd: Dict[str, torch.Tensor], prefix: str, planes: S
             dplanes[src] += (dvec / n_avg).unsqueeze(axis).expand_as(planes[src])
         grads[f"{prefix}.conv_{name}.weight"] = gw
     return dplanes, grads
+
+
+# --------------------------------------------------------------------------- GroupNorm (+ FiLM) + SiLU
+def gn_film_silu_backward(x, gamma, beta, dy, groups=32, eps=1e-5, scale=None, shift=None):
+    """Backward of y = silu(GN(x) * (1 + scale) + shift) (unet_triplane.py:63-95, 285-297; scale / shift [B, C] or None) in the
+    two-pass form a kernel would use: pass 1 forms, per (sample, channel), S1 = sum dxhat and S2 = sum dxhat * xhat over the plane
+    (plus the parameter / FiLM sums), pass 2 applies dx = rstd * (dxhat - mean_g(S1) - xhat * mean_g(S2)).
+    -> dict(dx, dgamma, dbeta, dscale, dshift)."""
+    B, C, R, Cc = x.shape
+    cpg = C // groups
+    xg = x.reshape(B, groups, cpg * R * Cc)
+    mu = xg.mean(-1, keepdim=True)
+    var = xg.var(-1, unbiased=False, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    xhat = ((xg - mu) * rstd).reshape(B, C, R, Cc)
+    n = xhat * gamma.view(1, C, 1, 1) + beta.view(1, C, 1, 1)
+    if scale is not None:
+        f = n * (1 + scale.view(B, C, 1, 1)) + shift.view(B, C, 1, 1)
+    else:
+        f = n
+    sig = torch.sigmoid(f)
+    df = dy * (sig * (1 + f * (1 - sig)))                            # SiLU'
+    out = {}
+    if scale is not None:
+        out["dscale"] = (df * n).sum(dim=(2, 3))                     # [B, C]
+        out["dshift"] = df.sum(dim=(2, 3))
+        dn = df * (1 + scale.view(B, C, 1, 1))
+    else:
+        out["dscale"] = out["dshift"] = None
+        dn = df
+    out["dgamma"] = (dn * xhat).sum(dim=(0, 2, 3))
+    out["dbeta"] = dn.sum(dim=(0, 2, 3))
+    dxhat = dn * gamma.view(1, C, 1, 1)
+    # pass 1: per-channel sums, then per-group means
+    s1 = dxhat.sum(dim=(2, 3)).reshape(B, groups, cpg).sum(-1) / (cpg * R * Cc)            # [B, G]
+    s2 = (dxhat * xhat).sum(dim=(2, 3)).reshape(B, groups, cpg).sum(-1) / (cpg * R * Cc)
+    # pass 2
+    expand = lambda v: v.repeat_interleave(cpg, dim=1).view(B, C, 1, 1)
+    out["dx"] = expand(rstd.view(B, groups)) * (dxhat - expand(s1) - xhat * expand(s2))
+    return out
+
+
+# --------------------------------------------------------------------------- resampling adjoints (gather form)
+def avgpool2_backward(dy, in_rows, in_cols):
+    """Adjoint of F.avg_pool2d(x, 2) (unet_triplane.py:127-145; floor on odd sizes: the last odd line gets no gradient)."""
+    dx = dy.new_zeros(*dy.shape[:2], in_rows, in_cols)
+    R, Cc = dy.shape[-2:]
+    dx[..., :2 * R, :2 * Cc] = dy.repeat_interleave(2, dim=-2).repeat_interleave(2, dim=-1) * 0.25
+    return dx
+
+
+def _bilinear_weights(out_size, in_size, scale):
+    """ATen area_pixel_compute_source_index(align_corners=False) as a dense [out, in] interpolation matrix."""
+    m = torch.zeros(out_size, in_size, dtype=torch.float64)
+    for o in range(out_size):
+        s = max(scale * (o + 0.5) - 0.5, 0.0)
+        i0 = min(int(s), in_size - 1)
+        i1 = min(i0 + 1, in_size - 1)
+        l1 = s - i0
+        m[o, i0] += 1 - l1
+        m[o, i1] += l1
+    return m
+
+
+def bilinear_resize_backward(dy, in_rows, in_cols, scale_factor=None):
+    """Adjoint of F.interpolate(x, mode="bilinear", align_corners=False) to dy's size — either scale_factor=2
+    (unet_triplane.py:106-124) or an explicit size (the resize-to-skip step, :494-499).  Gather form: every input pixel sums its
+    contributors, i.e. dx = Wr^T dy Wc with the two 1-D interpolation matrices."""
+    R, Cc = dy.shape[-2:]
+    sr = (1.0 / scale_factor) if scale_factor else in_rows / R
+    sc = (1.0 / scale_factor) if scale_factor else in_cols / Cc
+    wr = _bilinear_weights(R, in_rows, sr).to(dy.dtype)
+    wc = _bilinear_weights(Cc, in_cols, sc).to(dy.dtype)
+    return torch.einsum("oi,bcop,pj->bcij", wr, dy, wc)

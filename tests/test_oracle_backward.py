@@ -25,3 +25,50 @@ def test_folded_backward_equals_autograd(C, Cout, HWD, B):
         assert torch.allclose(p.grad, dp, rtol=1e-10, atol=1e-10)
     for k, v in sd.items():
         assert torch.allclose(v.grad, grads[k], rtol=1e-10, atol=1e-10), k
+
+
+@pytest.mark.parametrize("film", [False, True])
+def test_gn_film_silu_backward_equals_autograd(film):
+    g = torch.Generator().manual_seed(7)
+    B, C, R, Cc = 2, 64, 5, 7
+    x = torch.randn(B, C, R, Cc, generator=g, dtype=torch.float64, requires_grad=True)
+    gamma = torch.randn(C, generator=g, dtype=torch.float64, requires_grad=True)
+    beta = torch.randn(C, generator=g, dtype=torch.float64, requires_grad=True)
+    scale = torch.randn(B, C, generator=g, dtype=torch.float64, requires_grad=True) if film else None
+    shift = torch.randn(B, C, generator=g, dtype=torch.float64, requires_grad=True) if film else None
+    n = torch.nn.functional.group_norm(x, 32, gamma, beta, 1e-5)
+    f = n * (1 + scale.view(B, C, 1, 1)) + shift.view(B, C, 1, 1) if film else n
+    y = ur.silu(f)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (y * dy).sum().backward()
+    o = br.gn_film_silu_backward(x.detach(), gamma.detach(), beta.detach(), dy, scale=scale.detach() if film else None,
+                                 shift=shift.detach() if film else None)
+    assert torch.allclose(x.grad, o["dx"], rtol=1e-9, atol=1e-10)
+    assert torch.allclose(gamma.grad, o["dgamma"], rtol=1e-9, atol=1e-10) and torch.allclose(beta.grad, o["dbeta"], rtol=1e-9, atol=1e-10)
+    if film:
+        assert torch.allclose(scale.grad, o["dscale"], rtol=1e-9, atol=1e-10) and torch.allclose(shift.grad, o["dshift"], rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("rows,cols", [(6, 8), (7, 5), (1, 3)])
+def test_resampling_adjoints_equal_autograd(rows, cols):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(rows * 10 + cols)
+    x = torch.randn(2, 3, rows, cols, generator=g, dtype=torch.float64, requires_grad=True)
+    # avg-pool 2x2 (floor)
+    if rows >= 2 and cols >= 2:
+        y = F.avg_pool2d(x, 2)
+        dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+        (y * dy).sum().backward()
+        assert torch.allclose(x.grad, br.avgpool2_backward(dy, rows, cols), atol=1e-12)
+        x.grad = None
+    # bilinear x2
+    y = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (y * dy).sum().backward()
+    assert torch.allclose(x.grad, br.bilinear_resize_backward(dy, rows, cols, scale_factor=2), atol=1e-12)
+    x.grad = None
+    # bilinear to an explicit (odd) size: the resize-to-skip step
+    y = F.interpolate(x, size=(2 * rows + 1, 2 * cols + 1), mode="bilinear", align_corners=False)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (y * dy).sum().backward()
+    assert torch.allclose(x.grad, br.bilinear_resize_backward(dy, rows, cols), atol=1e-12)
