@@ -150,3 +150,183 @@ def bilinear_resize_backward(dy, in_rows, in_cols, scale_factor=None):
     wr = _bilinear_weights(R, in_rows, sr).to(dy.dtype)
     wc = _bilinear_weights(Cc, in_cols, sc).to(dy.dtype)
     return torch.einsum("oi,bcop,pj->bcij", wr, dy, wc)
+
+
+# --------------------------------------------------------------------------- whole-UNet backward from the pieces above
+def unet_param_grads(sd, spec, x, t, H, W, D, dout_fn):
+    """Parameter gradients of the triplane UNet computed WITHOUT autograd: a forward pass that keeps what each adjoint needs, then
+    the adjoints above in reverse order (the order a training step's backward kernels would run in).
+    ``dout_fn(out_planes) -> (d_xy, d_xz, d_yz)`` supplies dL/d(output planes).  -> (output planes, {param name: grad})."""
+    from oracle import unet_ref as ur
+    grads: Dict[str, torch.Tensor] = {}
+    tape = []                                                          # closures, run in reverse
+
+    def acc(name, g):
+        grads[name] = grads[name] + g if name in grads else g
+
+    def linear(xv, wn, bn):
+        w, b = sd[wn], sd[bn]
+        y = F.linear(xv, w, b)
+        return y, (lambda dy: (acc(wn, dy.t() @ xv), acc(bn, dy.sum(0)), dy @ w)[-1])
+
+    def silu_vec(xv):
+        sig = torch.sigmoid(xv)
+        return xv * sig, (lambda dy: dy * (sig * (1 + xv * (1 - sig))))
+
+    def conv1x1(prefix, planes):
+        outs = []
+        for a, n in zip(planes, PLANES):
+            outs.append(F.conv2d(a, sd[f"{prefix}.conv_{n}.weight"], sd[f"{prefix}.conv_{n}.bias"]))
+
+        def back(dys):
+            dxs = []
+            for a, n, dy in zip(planes, PLANES, dys):
+                w = sd[f"{prefix}.conv_{n}.weight"]
+                acc(f"{prefix}.conv_{n}.weight", torch.nn.grad.conv2d_weight(a, w.shape, dy))
+                acc(f"{prefix}.conv_{n}.bias", dy.sum(dim=(0, 2, 3)))
+                dxs.append(F.conv_transpose2d(dy, w))
+            return dxs
+        return tuple(outs), back
+
+    def conv3x3(prefix, planes):
+        outs = ur.tri_conv(sd, prefix, planes, 1, spec.rollout)
+
+        def back(dys):
+            if spec.rollout:
+                dxs, g = tri_conv_backward_folded(sd, prefix, planes, dys)
+            else:
+                dxs, g = [], {}
+                for a, n, dy in zip(planes, PLANES, dys):
+                    w = sd[f"{prefix}.conv_{n}.weight"]
+                    g[f"{prefix}.conv_{n}.weight"] = torch.nn.grad.conv2d_weight(a, w.shape, dy, padding=1)
+                    g[f"{prefix}.conv_{n}.bias"] = dy.sum(dim=(0, 2, 3))
+                    dxs.append(F.conv_transpose2d(dy, w, padding=1))
+            for k, v in g.items():
+                acc(k, v)
+            return dxs
+        return outs, back
+
+    def norm_silu(prefix, planes, scale=None, shift=None):
+        """silu(GN(x) [* (1 + scale) + shift]) per plane.  back -> (dplanes, dscale, dshift)"""
+        outs = []
+        for a, n in zip(planes, PLANES):
+            h = F.group_norm(a, ur.GN_GROUPS, sd[f"{prefix}.norm_{n}.weight"], sd[f"{prefix}.norm_{n}.bias"], ur.GN_EPS)
+            if scale is not None:
+                h = h * (1 + scale[:, :, None, None]) + shift[:, :, None, None]
+            outs.append(ur.silu(h))
+
+        def back(dys):
+            dxs, dsc, dsh = [], None, None
+            for a, n, dy in zip(planes, PLANES, dys):
+                o = gn_film_silu_backward(a, sd[f"{prefix}.norm_{n}.weight"], sd[f"{prefix}.norm_{n}.bias"], dy, ur.GN_GROUPS,
+                                          ur.GN_EPS, scale, shift)
+                acc(f"{prefix}.norm_{n}.weight", o["dgamma"])
+                acc(f"{prefix}.norm_{n}.bias", o["dbeta"])
+                dxs.append(o["dx"])
+                if scale is not None:
+                    dsc = o["dscale"] if dsc is None else dsc + o["dscale"]
+                    dsh = o["dshift"] if dsh is None else dsh + o["dshift"]
+            return dxs, dsc, dsh
+        return tuple(outs), back
+
+    # ---- forward with a tape of adjoint closures; every closure maps output gradient(s) to input gradient(s)
+    emb0 = ur.sinusoid(t, spec.model_channels)
+    e1, b_l0 = linear(emb0, "time_embed.0.weight", "time_embed.0.bias")
+    e2, b_s0 = silu_vec(e1)
+    emb, b_l1 = linear(e2, "time_embed.2.weight", "time_embed.2.bias")
+    demb = [torch.zeros_like(emb)]
+
+    def res_block(prefix, planes):
+        h1, b_n1 = norm_silu(f"{prefix}.in_layers.0", planes)
+        h2, b_c1 = conv3x3(f"{prefix}.in_layers.2", h1)
+        se, b_se = silu_vec(emb)
+        e, b_le = linear(se, f"{prefix}.emb_layers.1.weight", f"{prefix}.emb_layers.1.bias")
+        if spec.use_scale_shift_norm:
+            scale, shift = e.chunk(2, dim=1)
+            h3, b_n2 = norm_silu(f"{prefix}.out_layers.0", h2, scale, shift)
+        else:
+            h2e = tuple(a + e[:, :, None, None] for a in h2)
+            h3, b_n2 = norm_silu(f"{prefix}.out_layers.0", h2e)
+        h4, b_c2 = conv3x3(f"{prefix}.out_layers.2", h3)
+        has_skip = f"{prefix}.skip_connection.conv_xy.weight" in sd
+        if has_skip:
+            s, b_sk = conv1x1(f"{prefix}.skip_connection", planes)
+        else:
+            s, b_sk = planes, None
+        out = tuple(a + b for a, b in zip(h4, s))
+
+        def back(douts):
+            dh3 = b_c2(douts)
+            dh2, dsc, dsh = b_n2(dh3)
+            if spec.use_scale_shift_norm:
+                de = torch.cat([dsc, dsh], dim=1)
+            else:
+                de = sum(d.sum(dim=(2, 3)) for d in dh2)
+            demb[0] = demb[0] + b_se(b_le(de))
+            dh1 = b_c1(dh2)
+            dx, _, _ = b_n1(dh1)
+            dskip = b_sk(douts) if has_skip else douts
+            return [a + b for a, b in zip(dx, dskip)]
+        return out, back
+
+    p = tuple(a.contiguous() for a in ur.split_planes(x, H, W, D))
+    p, b_in = conv1x1("in_conv.0", p)
+    downs, ups = ur.block_plan(spec)
+    stack = []                                    # (planes, index into skip_grads)
+    skip_grads = []
+    seq = []                                      # top-level tape: closures over plane-gradient lists
+    for ops in downs:
+        for op in ops:
+            if op[0] == "down":
+                shp = [a.shape[-2:] for a in p]
+                p = ur.avgpool2(p)
+                seq.append(lambda dys, shp=shp: [avgpool2_backward(dy, r, c) for dy, (r, c) in zip(dys, shp)])
+            else:
+                p, bk = res_block(op[1], p)
+                seq.append(bk)
+        skip_grads.append(None)
+        stack.append((p, len(skip_grads) - 1, len(seq)))          # gradient of this skip joins the chain after closure #len(seq)-1
+    join_at = {}                                   # position in seq (exclusive) -> skip index whose gradient is added there
+    for j, ops in enumerate(ups):
+        if j == 0:
+            p, si, pos = stack.pop()
+            # the deepest skip IS the chain: nothing to add
+        else:
+            s, si, pos = stack.pop()
+            join_at[pos] = si
+            if spec.rollout:
+                shp = [a.shape[-2:] for a in p]
+                tgt = [b.shape[-2:] for b in s]
+                p = tuple(a if a.shape[2:] == b.shape[2:] else F.interpolate(a, size=b.shape[2:], mode="bilinear", align_corners=False)
+                          for a, b in zip(p, s))
+                seq.append(lambda dys, shp=shp, tgt=tgt: [dy if tuple(sh) == tuple(tg) else bilinear_resize_backward(dy, sh[0], sh[1])
+                                                         for dy, sh, tg in zip(dys, shp, tgt)])
+            cu = p[0].shape[1]
+            p = tuple(torch.cat([a, b], dim=1) for a, b in zip(p, s))
+
+            def split_cat(dys, cu=cu, si=si):
+                skip_grads[si] = [dy[:, cu:] for dy in dys]
+                return [dy[:, :cu] for dy in dys]
+            seq.append(split_cat)
+        for op in ops:
+            if op[0] == "up":
+                shp = [a.shape[-2:] for a in p]
+                p = ur.up2(p)
+                seq.append(lambda dys, shp=shp: [bilinear_resize_backward(dy, r, c, scale_factor=2) for dy, (r, c) in zip(dys, shp)])
+            else:
+                p, bk = res_block(op[1], p)
+                seq.append(bk)
+    hN, b_on = norm_silu("out.0", p)
+    outp, b_oc = conv1x1("out.2", hN)
+
+    # ---- backward
+    d = list(dout_fn(outp))
+    d = b_oc(d)
+    d, _, _ = b_on(d)
+    for pos in range(len(seq), 0, -1):
+        if pos in join_at:                         # the skip saved after closure #pos-1 also fed a decoder concat
+            d = [a + b for a, b in zip(d, skip_grads[join_at[pos]])]
+        d = seq[pos - 1](d)
+    b_in(d)
+    b_l0(b_s0(b_l1(demb[0])))
+    return outp, grads

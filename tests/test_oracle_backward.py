@@ -72,3 +72,38 @@ def test_resampling_adjoints_equal_autograd(rows, cols):
     dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
     (y * dy).sum().backward()
     assert torch.allclose(x.grad, br.bilinear_resize_backward(dy, rows, cols), atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["startx", "eps_odd"])
+def test_manual_unet_backward_matches_reference_gradients(golden_dir, name):
+    """The whole UNet backward assembled from the kernel-form adjoints (no autograd) against the gradient fixtures the real
+    reference produced (oracle/make_golden_grads.py)."""
+    import os
+    import numpy as np
+    from oracle import diffusion_ref as dr
+    from oracle.cases import GRAD_CASES, make_grad_inputs
+    from oracle.make_golden_grads import sample_idx
+    case = GRAD_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"grads_{name}.npz"))
+    spec = ur.UNetSpec(**case["spec"])
+    sd = ur.synthetic_state_dict(spec, case["wseed"])
+    H, W, D = case["HWD"]
+    x0, nz, t = make_grad_inputs(case)
+    o = dr.RefDiffusion(case["T"], case["respacing"], "linear", case.get("mean_type", "start_x"))
+    x_t = o.q_sample(x0, t, nz)
+    target = x0 if case.get("mean_type", "start_x") == "start_x" else nz
+    tgt_planes = ur.split_planes(target, H, W, D)
+    B = x0.shape[0]
+
+    def dout(out_planes):          # loss = mean_b sum_planes mean_plane (target - out)^2   (gaussian_diffusion.py:822-851)
+        return [2 * (op - tp) / (op[0].numel() * B) for op, tp in zip(out_planes, tgt_planes)]
+    with torch.no_grad():
+        _, grads = br.unet_param_grads(sd, spec, x_t, o.model_t(t), H, W, D, dout)
+    assert len(grads) == 138
+    for k, gr in grads.items():
+        flat = gr.reshape(-1).numpy()
+        n_ref = float(g[f"norm/{k}"])
+        assert abs(np.linalg.norm(flat.astype(np.float64)) - n_ref) <= 2e-4 * max(n_ref, 1e-12), (k, np.linalg.norm(flat), n_ref)
+        want = g[f"sample/{k}"]
+        tol = 2e-4 * max(np.abs(want).max(), n_ref / np.sqrt(flat.size), 1e-12)
+        assert np.abs(flat[sample_idx(flat.size)] - want).max() <= tol, k
