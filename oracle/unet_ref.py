@@ -59,7 +59,7 @@ def join_planes(xy, xz, yz):
 def sinusoid(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     """nn.py:103-121."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)    # as nn.py:114-116
     ang = t[:, None].float() * freqs[None]
     e = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
     if dim % 2:
