@@ -61,3 +61,40 @@ def test_broadcast_and_gather_world2():
         assert p.exitcode == 0
     for rank, n, same, ok in res:
         assert n == 5 * 7 + 7 + 7 + 7 and same and ok, (rank, n, same, ok)
+
+
+def _sampler_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sin3dm_b200.resample import LossSecondMomentResampler
+
+        class D:
+            num_timesteps = 4
+        r = LossSecondMomentResampler(D(), history_per_term=2, uniform_prob=0.0)
+        # ragged per-rank batches: rank 0 reports steps {0,1,2}, rank 1 reports {3}; twice -> every history is full
+        for rep in range(2):
+            ts = torch.tensor([0, 1, 2]) if rank == 0 else torch.tensor([3])
+            ls = torch.tensor([1.0, 2.0, 3.0]) * (rep + 1) if rank == 0 else torch.tensor([4.0]) * (rep + 1)
+            r.update_with_local_losses(ts, ls)
+        q.put((rank, r.weights().tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_loss_aware_sampler_synchronises_ranks_world2():
+    """LossAwareSampler.update_with_local_losses (resample.py:70-103 in the reference): every rank ends with the same weights."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sampler_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == res[1]
+    rms = [(1 * 1 + 2 * 2) ** 0.5 * k for k in (1.0, 2.0, 3.0, 4.0)]
+    want = [v / sum(rms) for v in rms]
+    assert all(abs(a - b) < 1e-12 for a, b in zip(res[0], want))

@@ -159,3 +159,39 @@ def test_triplane_io_round_trip_and_pad(tmp_path):
     pa, pb, pc = s3.decompose_featmaps(padded, ns)
     assert torch.equal(pa[..., 1:1 + H, 0:W], xy) and int((pa != 0).sum()) == int((xy != 0).sum())
     assert torch.equal(pb[..., 1:1 + H, 2:2 + D], xz) and torch.equal(pc[..., 0:W, 2:2 + D], yz)
+
+
+def test_schedule_samplers_match_reference_values():
+    """sin3dm_b200.resample against values produced by the reference's resample.py under the same numpy seeds (UniformSampler
+    draw, LossSecondMomentResampler weights before / after warm-up and after the history shifts, and a weighted draw)."""
+    import numpy as np
+    from sin3dm_b200.resample import LossSecondMomentResampler, UniformSampler, create_named_schedule_sampler
+
+    class D:
+        def __init__(self, n):
+            self.num_timesteps = n
+    np.random.seed(0)
+    s = create_named_schedule_sampler("uniform", D(1000))
+    assert isinstance(s, UniformSampler)
+    i, w = s.sample(8, "cpu")
+    assert i.dtype == torch.int64 and i.tolist() == [548, 715, 602, 544, 423, 645, 437, 891] and w.tolist() == [1.0] * 8
+    np.random.seed(1)
+    r = LossSecondMomentResampler(D(5), history_per_term=2, uniform_prob=0.01)
+    assert r.weights().tolist() == [1.0] * 5
+    r.update_with_all_losses([0, 1, 2, 3, 4, 0, 1, 2, 3, 4], [1., 2., 3., 4., 5., 2., 1., 0.5, 4., 3.])
+    assert np.allclose(r.weights(), [0.11850279589800725, 0.11850279589800725, 0.160460934259197, 0.29673135105233966,
+                                     0.30580212289244885], rtol=1e-14)
+    r.update_with_local_losses(torch.tensor([0, 0]), torch.tensor([10., 20.]))           # single process: no collective
+    assert np.allclose(r.weights(), [0.5677902587017709, 0.058579025870177104, 0.07895579517861935, 0.1451348716346799,
+                                     0.14954004861475256], rtol=1e-14)
+    i, w = r.sample(6, "cpu")
+    assert i.tolist() == [0, 3, 0, 0, 0, 0]
+    assert np.allclose(w.numpy(), [0.35224273800849915, 1.3780286312103271] + [0.35224273800849915] * 4, rtol=1e-6)
+    with pytest.raises(NotImplementedError):
+        create_named_schedule_sampler("nope", D(3))
+
+
+def test_fused_optimizer_refuses_cpu_parameters():
+    from sin3dm_b200.optim import FusedAdamWEMA
+    with pytest.raises(_lib.S3DError):
+        FusedAdamWEMA([torch.nn.Parameter(torch.zeros(4))], lr=1e-3)
