@@ -41,7 +41,9 @@ typedef struct {
     int channel_mult[S3D_MAX_LEVELS];
     int use_scale_shift_norm;      /* FiLM (unet_triplane.py:285-297) vs additive embedding */
     int rollout;                   /* 1: TriplaneUNetModelSmall, 0: ...SmallRaw */
-    int precision;                 /* 3: fp16 hi/lo split, 3 MMAs (fp32-grade, default); 1: single fp16 MMA */
+    int precision;                 /* conv operand terms (v = hi + lo/2048, fp16 halves): 3: Ah*Bh + Ah*Bl + Al*Bh (fp32-grade);
+                                      2: Ah*(Bh + Bl) (exact weights, fp16 activations); 4: (Ah + Al)*Bh (exact activations, fp16
+                                      weights); 1: Ah*Bh.  DESIGN.md §3 has the measured full-chain error of each. */
     int conv_impl;                 /* 0: tcgen05 implicit GEMM; 1: CUDA-core debug kernel */
 } s3d_unet_config;
 
@@ -186,13 +188,16 @@ typedef struct {
     int mean_type;
     int clip_denoised;
     int is_mask_t0;
-    int n_steps;
+    int n_steps;            /* iterations to run */
+    int t_start;            /* step index of the first iteration (the loop runs t_start, t_start-1, ...; a full chain passes the
+                               table length - 1); needs t_start - n_steps + 1 >= 0 */
     int B, H, W, D;
+    int64_t n_per_sample;   /* elements of one sample of x_dev; must equal out_channels * (H+D) * (W+D) (checked) */
     float* x_dev;           /* in: x_T, out: final sample (in place) [B, C, H+D, W+D] */
     float* pred_xstart_dev; /* optional */
-    const float* coef_dev;  /* [n_steps][S3D_NCOEF] */
-    const float* film_dev;  /* [n_steps][film_dim] conditioning of step index i (already timestep_map'ed) */
-    const float* step_noise_dev; /* NULL -> Philox; else [n_steps][B][n] with row i used at step index i */
+    const float* coef_dev;  /* [T][S3D_NCOEF], T > t_start */
+    const float* film_dev;  /* [T][film_dim] conditioning of step index i (already timestep_map'ed) */
+    const float* step_noise_dev; /* NULL -> Philox; else [T][B][n] with row i used at step index i */
     const float* y0_dev;
     const float* mask_dev;
     uint64_t seed;
@@ -200,7 +205,12 @@ typedef struct {
     int use_graph;          /* 1: CUDA graph replay, 0: plain launches */
 } s3d_loop_args;
 
+/* The captured graph is cached per (sampler options, buffer pointers); seed, sample_base and t_start live in device memory, so
+ * repeated calls with the same buffers replay the cached graph without re-capturing. */
 int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream);
+/* CUDA graphs captured + instantiated by s3d_sample_loop since the handle was created (bench.py asserts that none is built inside
+ * its timed region). */
+int s3d_unet_graph_builds(const s3d_unet* u);
 
 
 /* ---- triplane decoder (replaces AutoEncoderGroupSkip.decode and ShapeAutoEncoder.decode_batch / decode_grid:

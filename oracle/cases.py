@@ -171,3 +171,61 @@ def make_grad_inputs(case):
     x0 = torch.rand(shape, generator=g) * 2 - 1
     nz = torch.randn(shape, generator=g)
     return x0, nz, torch.tensor(case["t"])
+
+
+# ---------------------------------------------------------------------------- full-length BASELINE chains
+# The BASELINE.json configurations end to end: the real reference's final latent for DDPM-1000 at cfg2, DDIM-100 at cfg3 (B=8,
+# D = 138) and a 20-step DDPM chain at the cfg5 shape (B=8).  Fixtures hold sample 0 in full and every FULL_STRIDE-th element of
+# the other samples (the composed tensor, dead corner included: both sides evolve it as pure noise) — see pack_full / full_errors.
+C12 = dict(in_channels=12, model_channels=64, out_channels=12)
+FULL_CASES = {
+    "cfg2_ddpm1000": dict(spec=dict(**C12), wseed=1234, HWD=(92, 128, 92), B=1, T=1000, respacing="", ddim=False, nseed=201),
+    "cfg3_ddim100": dict(spec=dict(**C12), wseed=1234, HWD=(92, 128, 138), B=8, T=1000, respacing="100", ddim=True, nseed=202),
+    "cfg5_ddpm20": dict(spec=dict(**C12), wseed=1234, HWD=(92, 128, 92), B=8, T=1000, respacing="20", ddim=False, nseed=203),
+}
+FULL_STRIDE = 8
+
+
+def pack_full(sample):
+    """final composed latent [B, C, H+D, W+D] -> fixture arrays."""
+    out = dict(sample0=sample[0].numpy())
+    if sample.shape[0] > 1:
+        out["rest_strided"] = sample[1:].reshape(sample.shape[0] - 1, -1)[:, ::FULL_STRIDE].contiguous().numpy()
+    return out
+
+
+def full_errors(got, fixture, H, W, D):
+    """-> (rel-L2 over the three planes of sample 0, rel-L2 over the strided elements of the other samples or 0.0)."""
+    from oracle.unet_ref import split_planes
+    got = torch.as_tensor(got).cpu().double()
+    w0 = torch.from_numpy(fixture["sample0"]).double()
+    num = sum(((a - b) ** 2).sum() for a, b in zip(split_planes(got[0], H, W, D), split_planes(w0, H, W, D)))
+    den = sum((b ** 2).sum() for b in split_planes(w0, H, W, D))
+    rel0 = float((num / den).sqrt())
+    rel_rest = 0.0
+    if "rest_strided" in fixture:
+        wr = torch.from_numpy(fixture["rest_strided"]).double()
+        gr = got[1:].reshape(got.shape[0] - 1, -1)[:, ::FULL_STRIDE]
+        rel_rest = float(((gr - wr) ** 2).sum().sqrt() / (wr ** 2).sum().sqrt())
+    return rel0, rel_rest
+
+
+# ---------------------------------------------------------------------------- guided sampling hooks (SURVEY §8 a9)
+# cond_fn / denoised_fn loops (gaussian_diffusion.py:357-394, 233-327) and q_mean_variance (:172-187)
+COND_CASES = {
+    "ddpm_cond_mean": dict(spec=dict(**SMALL), wseed=131, HWD=(8, 12, 10), B=2, T=1000, respacing="12", ddim=False, nseed=141,
+                           cond=True, denoise=False),
+    "ddim_cond_score": dict(spec=dict(**SMALL), wseed=132, HWD=(10, 8, 8), B=1, T=1000, respacing="ddim10", ddim=True, nseed=142,
+                            cond=True, denoise=True, eta=0.3, rescale_timesteps=True),
+    "ddpm_denoised_fn_eps": dict(spec=dict(**SMALL), wseed=133, HWD=(8, 8, 12), B=1, T=1000, respacing="9", ddim=False, nseed=143,
+                                 cond=False, denoise=True, mean_type="epsilon"),
+}
+
+
+def cond_fn(x, t, **kwargs):
+    """deterministic stand-in for grad log p(y | x): smooth in x, depends on the (mapped) timestep"""
+    return 0.3 * torch.tanh(x) * (1.0 + t.float().view(-1, 1, 1, 1) / 1000.0) - 0.05
+
+
+def denoised_fn(x):
+    return 0.9 * x + 0.05 * torch.sin(3.0 * x)

@@ -152,14 +152,40 @@ class RefDiffusion:
         T = self.tab
         return (self._x(T["sqrt_recip_alphas_cumprod"], t, x) * x - x0) / self._x(T["sqrt_recipm1_alphas_cumprod"], t, x)
 
-    def p_sample(self, model, x, t, noise, clip=True, denoised_fn=None):
+    def q_mean_variance(self, x_start, t):
+        """gaussian_diffusion.py:172-187."""
+        T = self.tab
+        return (self._x(T["sqrt_alphas_cumprod"], t, x_start) * x_start,
+                self._x(1.0 - T["alphas_cumprod"], t, x_start).expand_as(x_start),
+                self._x(T["log_one_minus_alphas_cumprod"], t, x_start).expand_as(x_start))
+
+    def condition_mean(self, cond_fn, o, x, t):
+        """gaussian_diffusion.py:357-370 (cond_fn sees the mapped timesteps: respace.py:96-97)."""
+        return o["mean"].float() + o["variance"] * cond_fn(x, self.model_t(t)).float()
+
+    def condition_score(self, cond_fn, o, x, t):
+        """gaussian_diffusion.py:372-394."""
+        T = self.tab
+        ab = self._x(T["alphas_cumprod"], t, x)
+        eps = self.eps_from_x0(x, t, o["pred_xstart"])
+        eps = eps - (1 - ab).sqrt() * cond_fn(x, self.model_t(t))
+        out = dict(o)
+        out["pred_xstart"] = self._x(T["sqrt_recip_alphas_cumprod"], t, x) * x - self._x(T["sqrt_recipm1_alphas_cumprod"], t, x) * eps
+        out["mean"] = self._x(T["posterior_mean_coef1"], t, x) * out["pred_xstart"] + self._x(T["posterior_mean_coef2"], t, x) * x
+        return out
+
+    def p_sample(self, model, x, t, noise, clip=True, denoised_fn=None, cond_fn=None):
         o = self.p_mean_variance(model, x, t, clip, denoised_fn)
         nz = (t != 0).float().view(-1, *([1] * (x.dim() - 1)))
+        if cond_fn is not None:
+            o["mean"] = self.condition_mean(cond_fn, o, x, t)
         return dict(sample=o["mean"] + nz * torch.exp(0.5 * o["log_variance"]) * noise, pred_xstart=o["pred_xstart"])
 
     def ddim_sample(self, model, x, t, noise, clip=True, denoised_fn=None, eta=0.0, y0=None, mask=None,
-                    is_mask_t0=False):
+                    is_mask_t0=False, cond_fn=None):
         o = self.p_mean_variance(model, x, t, clip, denoised_fn)
+        if cond_fn is not None:
+            o = self.condition_score(cond_fn, o, x, t)
         x0 = o["pred_xstart"]
         nz = (t != 0).float().view(-1, *([1] * (x.dim() - 1)))
         if y0 is not None and mask is not None:

@@ -46,8 +46,8 @@ class AdamWArgs(C.Structure):
 
 class LoopArgs(C.Structure):
     _fields_ = [("kind", C.c_int), ("mean_type", C.c_int), ("clip_denoised", C.c_int), ("is_mask_t0", C.c_int),
-                ("n_steps", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("D", C.c_int),
-                ("x_dev", C.c_void_p), ("pred_xstart_dev", C.c_void_p), ("coef_dev", C.c_void_p),
+                ("n_steps", C.c_int), ("t_start", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("D", C.c_int),
+                ("n_per_sample", C.c_int64), ("x_dev", C.c_void_p), ("pred_xstart_dev", C.c_void_p), ("coef_dev", C.c_void_p),
                 ("film_dev", C.c_void_p), ("step_noise_dev", C.c_void_p), ("y0_dev", C.c_void_p),
                 ("mask_dev", C.c_void_p), ("seed", C.c_uint64), ("sample_base", C.c_uint32), ("use_graph", C.c_int)]
 
@@ -95,6 +95,7 @@ _SIGNATURES = {
                                 C.c_void_p]),
     "s3d_adamw_ema_step": (C.c_int, [C.POINTER(AdamWArgs), C.c_void_p]),
     "s3d_sample_loop": (C.c_int, [C.c_void_p, C.POINTER(LoopArgs), C.c_void_p]),
+    "s3d_unet_graph_builds": (C.c_int, [C.c_void_p]),
     "s3d_decoder_create": (C.c_int, [C.POINTER(DecoderConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "s3d_decoder_destroy": (C.c_int, [C.c_void_p]),
     "s3d_decoder_num_tensors": (C.c_int, [C.c_void_p]),

@@ -108,8 +108,14 @@ __global__ void __launch_bounds__(256, 2) k_boundary(BoundaryArgs A) {
     int tstep = 0;
     float cf[12];
     float nz = 0.f;
+    unsigned long long seed = A.sch.seed;
+    unsigned int sample_base = A.sch.sample_base;
     if (MODE == MODE_FUSED) {
         tstep = A.sch.t_idx[b];
+        if (A.sch.dyn) {
+            seed = __ldg(A.sch.dyn);
+            sample_base = static_cast<unsigned int>(__ldg(A.sch.dyn + 1));
+        }
 #pragma unroll
         for (int k = 0; k < 12; ++k) cf[k] = __ldg(A.sch.coef + static_cast<size_t>(tstep) * 12 + k);
         nz = tstep != 0 ? 1.f : 0.f;
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(256, 2) k_boundary(BoundaryArgs A) {
                 const long long pix = comp(r, c);
                 float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (!A.sch.noise && A.sch.kind != 2)
-                    z = philox_normal4(A.sch.seed, A.sch.sample_base + b, static_cast<uint32_t>(tstep), static_cast<uint32_t>(pix * nq + quad));
+                    z = philox_normal4(seed, sample_base + b, static_cast<uint32_t>(tstep), static_cast<uint32_t>(pix * nq + quad));
                 const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {

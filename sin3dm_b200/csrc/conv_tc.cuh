@@ -87,20 +87,30 @@ struct FusedRoll {
     int total_len;
 };
 
-template <int NSPLIT>
+// Precision modes (operands are fp16 (hi, lo) pairs, v = hi + lo/2048; fp32 accumulation in TMEM):
+//   1: Ah*Bh                           one MMA, fp16-grade products
+//   2: Ah*Bh + Ah*Bl                   one N=128 MMA (lo weight tile behind the hi tile): exact weights, fp16-rounded activations
+//   4: Ah*Bh + Al*Bh                   two MMAs: exact activations, fp16-rounded weights
+//   3: Ah*Bh + Ah*Bl + Al*Bh           fp32-grade (error ~2^-22)
+template <int MODE>
 struct ConvTcCfg {
-    static constexpr int kASlotBytes = (NSPLIT == 3 ? 2 : 1) * kAHaloBytes;   // hi at +0, lo at +kAHaloBytes
-    static constexpr int kBSlotBytes = (NSPLIT == 3 ? 2 : 1) * kBBytes;       // hi at +0, lo at +kBBytes
-    static constexpr int kASlots = 2;
-    static constexpr int kBSlots = NSPLIT == 3 ? 3 : 8;     // 3 x 16 KiB: the fourth slot's 16 KiB went to the epilogue staging of warps 6..9
+    static constexpr bool kAlo = MODE == 3 || MODE == 4;      // the lo halves of the activations are loaded and multiplied
+    static constexpr bool kBlo = MODE == 2 || MODE == 3;      // the lo halves of the weights
+    static constexpr bool kTwo = MODE != 1;                   // a second accumulator D2 (scaled by 1/2048 in the epilogue)
+    static constexpr int kASlotBytes = (kAlo ? 2 : 1) * kAHaloBytes;   // hi at +0, lo at +kAHaloBytes
+    static constexpr int kBSlotBytes = (kBlo ? 2 : 1) * kBBytes;       // hi at +0, lo at +kBBytes
+    static constexpr int kASlots = kAlo ? 2 : 3;
+    static constexpr int kBSlots = MODE == 3 ? 3 : (MODE == 4 ? 6 : (MODE == 2 ? 4 : 8));
     static constexpr int kRingBytes = kASlots * kASlotBytes + kBSlots * kBSlotBytes;
-    static constexpr int kAccCols = NSPLIT == 3 ? 128 : 64;     // TMEM columns of one accumulator stage
+    static constexpr int kAccCols = kTwo ? 128 : 64;            // TMEM columns of one accumulator stage
     static constexpr int kTmemCols = 2 * kAccCols;              // double-buffered accumulators
     static constexpr int kEpiBytes = kEpiWarps * 32 * 32 * 4 + 64;   // epilogue staging: [32 rows][32 cols] fp32 per epilogue warp
     static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
-    // stand-alone k_roll_tc keeps the simple 4-stage {A,B} ring
-    static constexpr int kStageBytes = (NSPLIT == 3 ? 2 : 1) * (kABytes + kBBytes);
-    static constexpr int kStages = NSPLIT == 3 ? 4 : 8;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+    static_assert(2 * kASlots + 2 * kBSlots + 5 <= 30, "barrier block");
+    // stand-alone k_roll_tc (MODE 1 or 3 only) keeps the simple 4-stage {A,B} ring
+    static constexpr int kStageBytes = (MODE == 3 ? 2 : 1) * (kABytes + kBBytes);
+    static constexpr int kStages = MODE == 3 ? 4 : 8;
     static constexpr int kRollSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -161,11 +171,12 @@ constexpr int kRollRows = kRollTmMax + 2;   // most rows of a roll tile's A patc
 // quarter (4 image rows x 8 pixels), moves them 32 columns at a time TMEM -> registers -> its own 4 KiB staging block
 // (16-byte XOR swizzle), and re-reads the block transposed so that 8 consecutive lanes cover 128 contiguous bytes of one pixel:
 // + bias + rollout 1-D terms + residual, fp32 NHWC store, and the GroupNorm group sums of what it stored (fixed-point atomics).
-template <int NSPLIT>
+template <int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_constant__ ConvTcMaps M,
                                                              const __grid_constant__ RollTcMaps RM, const ConvTcArgs A,
                                                              const FusedRoll F, const int total_tiles) {
-    using Cfg = ConvTcCfg<NSPLIT>;
+    using Cfg = ConvTcCfg<MODE>;
+    constexpr bool kAlo = Cfg::kAlo, kBlo = Cfg::kBlo, kTwo = Cfg::kTwo;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     const int cblks = A.C / kBK;
     const int nskip = A.Cs / kBK;
     constexpr uint32_t kALo = kAHaloBytes, kBLo = kBBytes;
-    constexpr uint32_t kAStdTx = (NSPLIT == 3 ? 2 : 1) * kABytes, kAHaloTx = (NSPLIT == 3 ? 2 : 1) * kAHaloBytes;
+    constexpr uint32_t kAStdTx = (kAlo ? 2 : 1) * kABytes, kAHaloTx = (kAlo ? 2 : 1) * kAHaloBytes;
 
     if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(&fullA[s], kAHaloTx);
                     ptx::tma_load_5d(st, &M.a[T.plane], &fullA[s], cb * kBK, T.w0 - 1, T.h0 - 1, T.b, 0);
-                    if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &M.a[T.plane], &fullA[s], cb * kBK, T.w0 - 1, T.h0 - 1, T.b, 1);
+                    if (kAlo) ptx::tma_load_5d(st + kALo, &M.a[T.plane], &fullA[s], cb * kBK, T.w0 - 1, T.h0 - 1, T.b, 1);
                 }
                 __syncwarp();
             }
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(&fullA[s], kAStdTx);
                     ptx::tma_load_5d(st, &M.x[T.plane], &fullA[s], j * kBK, T.w0, T.h0, T.b, 0);
-                    if (NSPLIT == 3) ptx::tma_load_5d(st + kALo, &M.x[T.plane], &fullA[s], j * kBK, T.w0, T.h0, T.b, 1);
+                    if (kAlo) ptx::tma_load_5d(st + kALo, &M.x[T.plane], &fullA[s], j * kBK, T.w0, T.h0, T.b, 1);
                 }
                 __syncwarp();
             }
@@ -357,13 +368,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k) {
                             const uint64_t ko = static_cast<uint64_t>((k * 32) >> 4);   // +32 B along K inside the swizzle atom
-                            if (NSPLIT == 3) {
+                            if (kBlo) {
                                 // [D1 | D2] (+)= Ah * [Bh | Bl]  (one N=128 MMA: the lo weight tile sits right behind the hi
                                 // tile in shared memory and D2 right behind D1 in TMEM), then D2 += Al * Bh
                                 ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc2, k == 0 ? acc : 1u);
-                                ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, 1u);
+                                if (kAlo) ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, 1u);
                             } else {
                                 ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, k == 0 ? acc : 1u);
+                                if (kAlo) ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, k == 0 ? acc : 1u);     // D2 (+)= Al * Bh
                             }
                         }
                         ptx::umma_commit(&emptyB[sb]);    // weight slot free once the MMAs above retire
@@ -435,7 +447,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                                                     __ll2float_rn(static_cast<long long>(raw[i][e].y)) * scale, h[e], l[e]);
                                     const uint32_t off = static_cast<uint32_t>(j) * 128u + (static_cast<uint32_t>(k ^ (j & 7)) << 4);
                                     *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                                    if (NSPLIT == 3) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                                    if (kAlo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
                                 }
                             }
                         }
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 {
                     uint32_t v1[32], v2[32];
                     ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
-                    if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
+                    if (kTwo) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
                     ptx::tmem_ld_wait();
                     {
                         ptx::tc_fence_before();
@@ -470,7 +482,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             o[q] = __uint_as_float(v1[j + q]);
-                            if (NSPLIT == 3) o[q] = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, o[q]);
+                            if (kTwo) o[q] = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, o[q]);
                         }
                         *reinterpret_cast<float4*>(wst + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
                     }
@@ -605,7 +617,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             {
                 uint32_t v1[32], v2[32];
                 ptx::tmem_ld_32x32b_x32(lane_addr + half * 32, v1);
-                if (NSPLIT == 3) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
+                if (kTwo) ptx::tmem_ld_32x32b_x32(lane_addr + kBN + half * 32, v2);
                 ptx::tmem_ld_wait();
                 {
                     // this warp's TMEM reads of the tile are done: hand the accumulator stage back to the MMA issuer (8 arrivals)
@@ -619,7 +631,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         o[q] = __uint_as_float(v1[j + q]);
-                        if (NSPLIT == 3) o[q] = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, o[q]);
+                        if (kTwo) o[q] = fmaf(__uint_as_float(v2[j + q]), 1.f / kLoScale, o[q]);
                     }
                     *reinterpret_cast<float4*>(wst + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
                 }

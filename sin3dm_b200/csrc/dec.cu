@@ -314,12 +314,12 @@ void set_planes(s3d_decoder* d, const float* xy, const float* xz, const float* y
         a0.bs = B.bs;
         const size_t sm0 = static_cast<size_t>(B.cin) * (hstride + 64) * sizeof(float);
         CUDA_TRY(cudaFuncSetAttribute(k_dec_conv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm0)));
-        launch(k_dec_conv<0>, dim3(ts), dim3(256), sm0, st, a0);
+        launch_plain(k_dec_conv<0>, dim3(ts), dim3(256), sm0, st, a0);
         // InstanceNorm statistics of h1
         const int n0 = rows[0] * cols[0], n1 = rows[1] * cols[1], n2 = rows[2] * cols[2];
-        launch(k_dec_in_stats, dim3(d->max_strips, 3), dim3(256), 0, st, d->h1[0], d->h1[1], d->h1[2], n0, n1, n2, d->partial,
+        launch_plain(k_dec_in_stats, dim3(d->max_strips, 3), dim3(256), 0, st, d->h1[0], d->h1[1], d->h1[2], n0, n1, n2, d->partial,
                d->max_strips);
-        launch(k_dec_in_finalize, dim3(3), dim3(64), 0, st, d->partial, d->max_strips, n0, n1, n2, B.gamma, B.beta, d->coef);
+        launch_plain(k_dec_in_finalize, dim3(3), dim3(64), 0, st, d->partial, d->max_strips, n0, n1, n2, B.gamma, B.beta, d->coef);
         // norm + SiLU + conv ks x ks (64 -> 64), added onto the shortcut
         DecConvArgs a1 = a;
         for (int p = 0; p < 3; ++p) a1.x[p] = d->h1[p];
@@ -329,7 +329,7 @@ void set_planes(s3d_decoder* d, const float* xy, const float* xz, const float* y
         a1.coef = d->coef;
         const size_t sm1 = static_cast<size_t>(kDecUp) * (hstride + 64) * sizeof(float);
         CUDA_TRY(cudaFuncSetAttribute(k_dec_conv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm1)));
-        launch(k_dec_conv<1>, dim3(ts), dim3(256), sm1, st, a1);
+        launch_plain(k_dec_conv<1>, dim3(ts), dim3(256), sm1, st, a1);
         d->last_launches += 4;
     }
     d->planes_set = true;
@@ -357,7 +357,7 @@ void decode(s3d_decoder* d, const DecPoints& P, int clamp_tex, float* out, cudaS
         CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_ffma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
         const long long blocks = (P.n + 31) / 32;
         S3D_CHECK(blocks < (1LL << 31), "too many points for one launch");
-        launch(k_dec_mlp_ffma, dim3(static_cast<unsigned>(blocks)), dim3(256), sm, st, a, d->br[0].mf, d->br[d->nb - 1].mf, hid);
+        launch_plain(k_dec_mlp_ffma, dim3(static_cast<unsigned>(blocks)), dim3(256), sm, st, a, d->br[0].mf, d->br[d->nb - 1].mf, hid);
         d->last_launches = 1;
         return;
     }
@@ -384,11 +384,11 @@ void decode(s3d_decoder* d, const DecPoints& P, int clamp_tex, float* out, cudaS
     if (d->cfg.precision == 1) {
         using Cfg = DecTcCfg<1>;
         CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        launch(k_dec_mlp_tc<1>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
+        launch_plain(k_dec_mlp_tc<1>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
     } else {
         using Cfg = DecTcCfg<3>;
         CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        launch(k_dec_mlp_tc<3>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
+        launch_plain(k_dec_mlp_tc<3>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
     }
     d->last_launches = 1;
 }
@@ -424,11 +424,11 @@ void launch_encode(s3d_decoder* d, const EncArgs& a, cudaStream_t st) {
         make_tmap_f32(&vmap, a.vol, 4, dims, box);
         const size_t smem_t = (static_cast<size_t>(CV) * kEncIH * kEncIW * kEncZPitch + static_cast<size_t>(GEO + TEX) * 8 * 32) * sizeof(float) + 16;
         CUDA_TRY(cudaFuncSetAttribute(k_enc_conv3d_tma<GEO, TEX, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t)));
-        launch(k_enc_conv3d_tma<GEO, TEX, CT>, grid, dim3(128), smem_t, st, vmap, w, a);
+        launch_plain(k_enc_conv3d_tma<GEO, TEX, CT>, grid, dim3(128), smem_t, st, vmap, w, a);
     } else {
-        launch(k_enc_conv3d<GEO, TEX, CT>, grid, dim3(256), smem, st, w, a);
+        launch_plain(k_enc_conv3d<GEO, TEX, CT>, grid, dim3(256), smem, st, w, a);
     }
-    launch(k_enc_finalize, dim3(GEO + TEX, 3), dim3(kEncFinThreads), 0, st, a);
+    launch_plain(k_enc_finalize, dim3(GEO + TEX, 3), dim3(kEncFinThreads), 0, st, a);
 }
 
 // AutoEncoderGroupSkip.encode (networks.py:164-180)
@@ -473,8 +473,8 @@ void encode(s3d_decoder* d, const float* vol, int X, int Y, int Z, float* xy, fl
         gw.GEO = c.geo_feat_channels;
         gw.TEX = c.use_tex ? c.tex_feat_channels : 0;
         gw.CT = c.use_tex ? c.tex_channels + 1 : 0;
-        launch(k_enc_conv3d_generic, dim3((a.D + 127) / 128, a.W, a.H), dim3(128), 0, st, gw, a);
-        launch(k_enc_finalize, dim3(C, 3), dim3(kEncFinThreads), 0, st, a);
+        launch_plain(k_enc_conv3d_generic, dim3((a.D + 127) / 128, a.W, a.H), dim3(128), 0, st, gw, a);
+        launch_plain(k_enc_finalize, dim3(C, 3), dim3(kEncFinThreads), 0, st, a);
     }
     d->last_launches = 2;
 }

@@ -49,6 +49,18 @@ static void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
     if (e != cudaSuccess) throw S3dError{std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e)};
 }
+// For kernels that do NOT execute griddepcontrol.wait (helpers off the sampling loop, the decoder / encoder and the training
+// kernels): never launched with programmatic stream serialization, so S3D_PDL=1 cannot let them overtake their producer.
+template <typename... KArgs, typename... Args>
+static void launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+    if (e != cudaSuccess) throw S3dError{std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e)};
+}
 
 // ------------------------------------------------------------------------------------ driver entry (TMA descriptors)
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

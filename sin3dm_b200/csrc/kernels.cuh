@@ -749,6 +749,7 @@ struct SchedArgs {
     int* t_idx;             // [B]
     unsigned long long seed;
     unsigned int sample_base;
+    const unsigned long long* dyn;   // loop mode: {seed, sample_base} in device memory (the captured graph does not bake them)
     int advance;            // loop mode: t_idx[b] -= 1 after the step (by the last CTA)
     unsigned int* ticket;
     long long noise_step_stride;   // loop mode with a noise buffer: noise + t*stride
@@ -802,6 +803,8 @@ __global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
     for (int k = 0; k < 12; ++k) cf[k] = __ldg(A.coef + static_cast<size_t>(t) * 12 + k);
     const float nz = t != 0 ? 1.f : 0.f;
     const size_t base = static_cast<size_t>(b) * A.n;
+    const unsigned long long seed = A.dyn ? __ldg(A.dyn) : A.seed;
+    const unsigned int sample_base = A.dyn ? static_cast<unsigned int>(__ldg(A.dyn + 1)) : A.sample_base;
     const float* noise = A.noise ? A.noise + static_cast<size_t>(t) * A.noise_step_stride + base : nullptr;
     const int nq = (A.C + 3) / 4;
     const long long items = A.hw * nq;
@@ -823,7 +826,7 @@ __global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
             }
         }
         if (!noise && A.kind != 2) {
-            const float4 z = philox_normal4(A.seed, A.sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(pix * nq + quad));
+            const float4 z = philox_normal4(seed, sample_base + b, static_cast<uint32_t>(t), static_cast<uint32_t>(pix * nq + quad));
             nv[0] = z.x; nv[1] = z.y; nv[2] = z.z; nv[3] = z.w;
         }
 #pragma unroll

@@ -101,8 +101,8 @@ struct Plan {
     int* t_idx = nullptr;           // [B]
     unsigned int* ticket = nullptr;
     float* model_out = nullptr;     // [B][Cout][Hc][Wc]
-    cudaGraphExec_t graph_exec = nullptr;
-    std::string graph_key;
+    unsigned long long* dyn = nullptr;   // [2]: seed, sample_base of the running loop
+    std::map<std::string, cudaGraphExec_t> graphs;      // captured steps by (sampler options, buffer pointers)
 };
 
 struct s3d_unet {
@@ -130,8 +130,10 @@ struct s3d_unet {
     bool fuse_pool = true;      // S3D_FUSE_POOL=0: stand-alone k_avgpool2 instead of pooling in the conv epilogue
     bool trace_on = false;   // s3d_unet_trace_enable
     int profile_mode = -1;   // last s3d_unet_profile_ops: 1 = graph replay with event nodes, 0 = eager launches
+    int graph_builds = 0;    // graphs captured + instantiated by s3d_sample_loop
 };
 
+static bool mode_has_blo(int precision) { return precision == 2 || precision == 3; }
 static int ch_of(const s3d_unet_config& c, int level) { return c.channel_mult[level] * c.model_channels; }
 
 static void add_tensor(s3d_unet* u, const std::string& name, std::vector<int64_t> shape) {
@@ -412,7 +414,7 @@ static void free_all(std::vector<void*>& v) {
 }
 static void destroy_plan(s3d_unet* u) {
     if (!u->plan) return;
-    if (u->plan->graph_exec) cudaGraphExecDestroy(u->plan->graph_exec);
+    for (auto& kv : u->plan->graphs) cudaGraphExecDestroy(kv.second);
     free_all(u->plan->allocs);
     u->plan.reset();
 }
@@ -462,6 +464,8 @@ static void finalize(s3d_unet* u) {
     }
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<2>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<4>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_gn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kRollSmemBytes));
@@ -822,7 +826,8 @@ struct PlanBuilder {
             const uint32_t abox[5] = {kBK, kBM, 1, 1, 1};
             make_tmap_strided(&maps->a[i], S.means16 + static_cast<size_t>(soff[i]) * C, 5, adims, astr, abox);
             const uint64_t wdims[3] = {static_cast<uint64_t>(3 * C), static_cast<uint64_t>(4 * Cout), 2};
-            const uint32_t wbox[3] = {kBK, kBN, u->cfg.precision == 1 ? 1u : 2u};      // hi and lo tile in ONE box (lo lands behind hi)
+            const bool blo = u->fuse_roll ? mode_has_blo(u->cfg.precision) : u->cfg.precision != 1;
+            const uint32_t wbox[3] = {kBK, kBN, blo ? 2u : 1u};      // hi and lo tile in ONE box (lo lands behind hi)
             make_tmap(&maps->w[i], cv.wr16[i / 2][i % 2], 3, wdims, wbox);
         }
         A.tile_start[6] = total;
@@ -914,7 +919,7 @@ struct PlanBuilder {
                 maps->x[p] = maps->a[p];
             }
             const uint64_t wdims[3] = {static_cast<uint64_t>(cv.Ktot), static_cast<uint64_t>(cv.Cout), 2};
-            const uint32_t wbox[3] = {kBK, kBN, u->cfg.precision == 1 ? 1u : 2u};       // hi and lo tile in ONE box
+            const uint32_t wbox[3] = {kBK, kBN, mode_has_blo(u->cfg.precision) ? 2u : 1u};       // hi and lo tile in ONE box
             make_tmap(&maps->w[p], cv.w_pack[p], 3, wdims, wbox);
             A.tiles_x[p] = (d.cols[p] + kTileW - 1) / kTileW;
             const int tiles_y = (d.rows[p] + kTileH - 1) / kTileH;
@@ -922,7 +927,7 @@ struct PlanBuilder {
             total += A.tiles_x[p] * tiles_y;
         }
         A.tile_start[3] = total;
-        const int nsplit = u->cfg.precision == 1 ? 1 : 3;
+        const int mode = u->cfg.precision;
         const int ntile_n = cv.Cout / kBN;
         const int num_sms = u->num_sms;
         // the epilogue emits the output's GroupNorm group sums when a group is 2, 4 or 8 channels wide (Cout = 64, 128, 256)
@@ -965,7 +970,9 @@ struct PlanBuilder {
             }
             const int total_tiles = total * ntile_n * Bv + F.n_roll;
             dim3 grid(std::min(total_tiles, num_sms));
-            if (nsplit == 3) launch(k_conv_tc<3>, dim3(grid), dim3(kConvThreads), ConvTcCfg<3>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
+            if (mode == 3) launch(k_conv_tc<3>, dim3(grid), dim3(kConvThreads), ConvTcCfg<3>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
+            else if (mode == 2) launch(k_conv_tc<2>, dim3(grid), dim3(kConvThreads), ConvTcCfg<2>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
+            else if (mode == 4) launch(k_conv_tc<4>, dim3(grid), dim3(kConvThreads), ConvTcCfg<4>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
             else launch(k_conv_tc<1>, dim3(grid), dim3(kConvThreads), ConvTcCfg<1>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
             LAUNCH_CHECK("k_conv_tc");
         }, A.tr);
@@ -1307,7 +1314,7 @@ static void launch_sched(const SchedArgs& A, cudaStream_t s) {
 
 extern "C" {
 
-int s3d_abi_version(void) { return 1; }
+int s3d_abi_version(void) { return 2; }
 const char* s3d_last_error(void) { return g_err.c_str(); }
 
 int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
@@ -1320,7 +1327,7 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     S3D_CHECK(cfg->model_channels > 0 && cfg->model_channels % 64 == 0, "model_channels must be a multiple of 64");
     S3D_CHECK(cfg->in_channels >= 1 && cfg->out_channels >= 1 && cfg->out_channels <= 64, "channel counts out of range");
     for (int l = 0; l < cfg->n_levels; ++l) S3D_CHECK(cfg->channel_mult[l] >= 1, "channel_mult must be >= 1");
-    S3D_CHECK(cfg->precision == 1 || cfg->precision == 3, "precision must be 1 or 3");
+    S3D_CHECK(cfg->precision >= 1 && cfg->precision <= 4, "precision must be 1, 2, 3 or 4");
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     S3D_CHECK(device >= 0 && device < ndev, "no such CUDA device");
@@ -1502,9 +1509,9 @@ int s3d_vb_terms(const s3d_vb_args* a, void* stream) {
     A.partial = static_cast<double*>(a->workspace);
     A.out = a->out;
     const int gx = vb_grid(A.n);
-    launch(k_vb_terms, dim3(gx, A.B), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
+    launch_plain(k_vb_terms, dim3(gx, A.B), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
     LAUNCH_CHECK("k_vb_terms");
-    launch(k_vb_finalize, dim3(A.B), dim3(32), 0, static_cast<cudaStream_t>(stream), A, gx);
+    launch_plain(k_vb_finalize, dim3(A.B), dim3(32), 0, static_cast<cudaStream_t>(stream), A, gx);
     LAUNCH_CHECK("k_vb_finalize");
     API_END
 }
@@ -1521,9 +1528,9 @@ int s3d_plane_mse(const float* target_dev, const float* output_dev, int B, int C
     A.partial = static_cast<double*>(workspace);
     A.out = out_dev;
     const int gx = vb_grid(A.n);
-    launch(k_plane_mse, dim3(gx, B), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
+    launch_plain(k_plane_mse, dim3(gx, B), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
     LAUNCH_CHECK("k_plane_mse");
-    launch(k_plane_mse_finalize, dim3(B), dim3(32), 0, static_cast<cudaStream_t>(stream), A, gx);
+    launch_plain(k_plane_mse_finalize, dim3(B), dim3(32), 0, static_cast<cudaStream_t>(stream), A, gx);
     LAUNCH_CHECK("k_plane_mse_finalize");
     API_END
 }
@@ -1556,7 +1563,7 @@ int s3d_adamw_ema_step(const s3d_adamw_args* a, void* stream) {
     A.step_size = static_cast<float>(lr / (1.0 - std::pow(b1, a->step)));
     A.eps = static_cast<float>(a->eps);
     const int gx = static_cast<int>(std::min<long long>((A.n / 4 + 255) / 256 + 1, 148LL * 8));
-    launch(k_adamw_ema, dim3(gx), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
+    launch_plain(k_adamw_ema, dim3(gx), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
     LAUNCH_CHECK("k_adamw_ema");
     API_END
 }
@@ -1570,9 +1577,14 @@ int s3d_philox_normal(float* out_dev, int B, int C, int64_t hw, uint64_t seed, u
     API_END
 }
 
-__global__ void k_fill_int(int* p, int n, int v) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+// loop state in device memory: step index of every sample, Philox seed and global index of sample 0
+__global__ void k_set_loop_state(int* t_idx, int n, int t_start, unsigned long long* dyn, unsigned long long seed, unsigned int sample_base) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t_idx[i] = t_start;
+    if (i == 0) {
+        dyn[0] = seed;
+        dyn[1] = sample_base;
+    }
 }
 
 int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
@@ -1580,21 +1592,24 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
     S3D_CHECK(u && a && a->x_dev && a->coef_dev && a->film_dev, "null argument");
     S3D_CHECK((a->kind == S3D_DDPM || a->kind == S3D_DDIM) && (a->mean_type == 0 || a->mean_type == 1), "bad kind / mean_type");
     S3D_CHECK((a->y0_dev == nullptr) == (a->mask_dev == nullptr), "y0 and mask go together");
-    S3D_CHECK(a->n_steps >= 1, "n_steps");
+    S3D_CHECK(a->n_steps >= 1 && a->t_start >= a->n_steps - 1, "n_steps / t_start");
     CUDA_TRY(cudaSetDevice(u->device));
-    Plan* P = get_plan(u, a->B, a->H, a->W, a->D);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int Hc = a->H + a->D, Wc = a->W + a->D;
     S3D_CHECK(u->cfg.in_channels == u->cfg.out_channels, "sampling needs in_channels == out_channels");
     const long long n = static_cast<long long>(u->cfg.out_channels) * Hc * Wc;
+    S3D_CHECK(a->n_per_sample == n, "x_dev does not have out_channels * (H+D) * (W+D) elements per sample");
+    Plan* P = get_plan(u, a->B, a->H, a->W, a->D);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (!P->t_idx) {
         P->t_idx = dev_alloc<int>(P->allocs, a->B);
         P->ticket = dev_alloc<unsigned int>(P->allocs, 1);
         CUDA_TRY(cudaMemset(P->ticket, 0, sizeof(unsigned int)));
         P->model_out = dev_alloc<float>(P->allocs, static_cast<size_t>(a->B) * n);
+        P->dyn = dev_alloc<unsigned long long>(P->allocs, 2);
     }
-    launch(k_fill_int, dim3((a->B + 255) / 256), dim3(256), 0, s, P->t_idx, a->B, a->n_steps - 1);
-    LAUNCH_CHECK("k_fill_int");
+    launch_plain(k_set_loop_state, dim3((a->B + 255) / 256), dim3(256), 0, s, P->t_idx, a->B, a->t_start, P->dyn,
+                 static_cast<unsigned long long>(a->seed), a->sample_base);
+    LAUNCH_CHECK("k_set_loop_state");
     P->x = a->x_dev;
     P->out = P->model_out;
     P->film = a->film_dev;
@@ -1618,8 +1633,7 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
     A.x0_out = a->pred_xstart_dev;
     A.coef = a->coef_dev;
     A.t_idx = P->t_idx;
-    A.seed = a->seed;
-    A.sample_base = a->sample_base;
+    A.dyn = P->dyn;
     A.advance = 1;
     A.ticket = P->ticket;
     A.tr = P->sched_trace;
@@ -1642,16 +1656,17 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
     if (!a->use_graph) {
         for (int i = 0; i < a->n_steps; ++i) one_step(s);
     } else {
-        // The graph bakes every pointer and scalar of one step; only the step index (device memory) changes.
+        // The graph bakes the pointers and options of one step; what changes from call to call with the same buffers — step
+        // index, seed, sample_base — lives in device memory, so the cached graph is replayed as is.
         char key[512];
-        snprintf(key, sizeof(key), "%d|%d|%d|%d|%p|%p|%p|%p|%p|%p|%p|%llu|%u|%d", a->kind, a->mean_type, a->clip_denoised,
+        snprintf(key, sizeof(key), "%d|%d|%d|%d|%p|%p|%p|%p|%p|%p|%p|%d", a->kind, a->mean_type, a->clip_denoised,
                  a->is_mask_t0, (void*)a->x_dev, (void*)a->pred_xstart_dev, (void*)a->coef_dev, (void*)a->film_dev,
-                 (void*)a->step_noise_dev, (void*)a->y0_dev, (void*)a->mask_dev, (unsigned long long)a->seed, a->sample_base,
-                 fused ? 1 : 0);
-        if (!P->graph_exec || P->graph_key != key) {
-            if (P->graph_exec) {
-                cudaGraphExecDestroy(P->graph_exec);
-                P->graph_exec = nullptr;
+                 (void*)a->step_noise_dev, (void*)a->y0_dev, (void*)a->mask_dev, fused ? 1 : 0);
+        auto it = P->graphs.find(key);
+        if (it == P->graphs.end()) {
+            if (P->graphs.size() >= 8) {                    // bounded cache: callers that keep changing buffers just re-capture
+                for (auto& kv : P->graphs) cudaGraphExecDestroy(kv.second);
+                P->graphs.clear();
             }
             cudaStream_t cs;
             CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -1670,18 +1685,22 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
             }
             cudaStreamDestroy(cs);
             if (e != cudaSuccess) throw S3dError{std::string("graph capture: ") + cudaGetErrorString(e)};
-            e = cudaGraphInstantiate(&P->graph_exec, g, 0);
+            cudaGraphExec_t ge = nullptr;
+            e = cudaGraphInstantiate(&ge, g, 0);
             cudaGraphDestroy(g);
             if (e != cudaSuccess) throw S3dError{std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)};
-            P->graph_key = key;
+            it = P->graphs.emplace(key, ge).first;
+            ++u->graph_builds;
         }
-        for (int i = 0; i < a->n_steps; ++i) CUDA_TRY(cudaGraphLaunch(P->graph_exec, s));
+        for (int i = 0; i < a->n_steps; ++i) CUDA_TRY(cudaGraphLaunch(it->second, s));
     }
     if (fused) P->in_acc_stale = true;
     u->last_launches = fused ? static_cast<int>(nops) - 2 : static_cast<int>(nops);
     u->last_launches += 1;   // scheduler kernel
     API_END
 }
+
+int s3d_unet_graph_builds(const s3d_unet* u) { return u ? u->graph_builds : 0; }
 
 int64_t s3d_unet_workspace_bytes(const s3d_unet* u) { return (u && u->plan) ? static_cast<int64_t>(u->plan->alloc_bytes) : 0; }
 

@@ -43,6 +43,8 @@ def sample_sharded(sample_fn, n_samples, sample_shape, batch_size=None, gather=T
     """
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
+    if device is None and torch.cuda.is_available():
+        device = torch.device("cuda", torch.cuda.current_device())      # a rank that owns no sample still joins the gather
     start, count = shard_range(n_samples, world, rank)
     bs = batch_size or max(count, 1)
     outs = []

@@ -324,29 +324,56 @@ class GaussianDiffusion:
 
     def _run_device_loop(self, kind, model, shape, noise, clip_denoised, model_kwargs, device, eta, y0, mask, is_mask_t0,
                          step_noise, seed, sample_base, use_graph=True):
-        dev = device if device is not None else next(model.parameters()).device
-        dev = th.device(dev)
+        mdev = next(model.parameters()).device
+        dev = th.device(device) if device is not None else mdev
+        if dev.type == "cuda" and dev.index is None:
+            dev = th.device("cuda", th.cuda.current_device())
+        if dev != mdev:
+            raise ValueError(f"device={dev} but the model lives on {mdev}")
         H, W, D = (int(model_kwargs[k]) for k in ("H", "W", "D"))
-        B = int(shape[0])
-        img = (noise.to(dev, th.float32) if noise is not None else th.randn(*shape, device=dev)).contiguous().clone()
-        assert tuple(img.shape) == tuple(shape)
+        shape = tuple(int(v) for v in shape)
+        # the C side sizes every access as out_channels * (H+D) * (W+D) per sample: refuse anything else here
+        if len(shape) != 4 or shape[1] != model.in_channels or model.in_channels != model.out_channels \
+                or shape[2:] != (H + D, W + D):
+            raise ValueError(f"shape {shape} does not match the model (in/out channels {model.in_channels}/{model.out_channels}) "
+                             f"and (H+D, W+D) = ({H + D}, {W + D})")
+        B = shape[0]
         T = self.num_timesteps
-        steps = th.arange(T, device=dev)
-        film = model.film_table(self._model_timesteps(steps).float())
+        # Persistent buffers: the captured CUDA graph is cached by buffer address, so x lives in a per-shape workspace (the result
+        # is returned as a copy) and the conditioning table is cached per (weights, timesteps).
+        ws = self.__dict__.setdefault("_loop_ws", {})
+        img = ws.get((str(dev), shape))
+        if img is None:
+            if len(ws) >= 4:
+                ws.clear()
+            img = ws[(str(dev), shape)] = th.empty(shape, device=dev, dtype=th.float32)
+        if noise is not None:
+            if tuple(noise.shape) != shape:
+                raise ValueError(f"noise has shape {tuple(noise.shape)}, expected {shape}")
+            img.copy_(noise.to(dev, th.float32))
+        else:
+            img.normal_()
+        film = model.film_table(self._model_timesteps(th.arange(T)).float(), cache=True)
         coef = self.coef_table(dev, eta)
         a = _lib.LoopArgs()
         a.kind, a.mean_type, a.clip_denoised, a.is_mask_t0 = kind, self._mean_code(), int(bool(clip_denoised)), int(bool(is_mask_t0))
-        a.n_steps, a.B, a.H, a.W, a.D = T, B, H, W, D
+        a.n_steps, a.t_start, a.B, a.H, a.W, a.D = T, T - 1, B, H, W, D
+        a.n_per_sample = img[0].numel()
         keep = [img, film, coef]
         a.x_dev, a.coef_dev, a.film_dev = img.data_ptr(), coef.data_ptr(), film.data_ptr()
         if step_noise is not None:
             if callable(step_noise):
                 step_noise = th.stack([step_noise(i).to(dev, th.float32) for i in range(T)])
             sn = step_noise.to(dev, th.float32).contiguous()
-            assert tuple(sn.shape) == (T, *shape), "step_noise must be [n_steps, *shape] indexed by step index"
+            if tuple(sn.shape) != (T, *shape):
+                raise ValueError("step_noise must be [n_steps, *shape] indexed by step index")
             keep.append(sn)
             a.step_noise_dev = sn.data_ptr()
-        if y0 is not None and mask is not None:
+        if (y0 is None) != (mask is None):
+            raise ValueError("y0 and mask go together")
+        if y0 is not None:
+            if tuple(y0.shape) != shape or tuple(mask.shape) != shape:      # the reference asserts the same (:568)
+                raise ValueError(f"y0 / mask must have the sample's shape {shape} (got {tuple(y0.shape)}, {tuple(mask.shape)})")
             y0c, mc = y0.to(dev, th.float32).contiguous(), mask.to(dev, th.float32).contiguous()
             keep += [y0c, mc]
             a.y0_dev, a.mask_dev = y0c.data_ptr(), mc.data_ptr()
@@ -356,8 +383,9 @@ class GaussianDiffusion:
         h = model.handle()
         with th.cuda.device(dev):
             _lib.check(_lib.lib().s3d_sample_loop(h, C.byref(a), _lib.current_stream_ptr()))
+            out = img.clone()
         self._keepalive = keep      # buffers referenced by the cached graph stay alive until the next loop
-        return img
+        return out
 
     def _progressive(self, step_fn, model, shape, noise, device, progress, step_noise, seed, sample_base, **kw):
         if device is None:

@@ -24,6 +24,8 @@ class FusedAdamWEMA:
             raise _lib.S3DError("sin3dm_b200 runs on CUDA only (no CPU fallback)")
         if any(p.device != dev or p.dtype != torch.float32 for p in self.params):
             raise ValueError("all parameters must be fp32 tensors on one CUDA device")
+        if isinstance(ema_rates, str):                      # the reference's flag form: "0.9999,0.999" (train_util.py:52-56)
+            ema_rates = [float(x) for x in ema_rates.split(",")]
         self.ema_rates = [float(r) for r in ([ema_rates] if isinstance(ema_rates, float) else ema_rates)]
         if len(self.ema_rates) > 4:
             raise ValueError("at most 4 EMA rates")
@@ -60,6 +62,9 @@ class FusedAdamWEMA:
         """One AdamW update followed by every EMA update; ``lr`` overrides the base rate (TrainLoop._anneal_lr)."""
         for p, o in zip(self.params, self.offsets):             # a caller may have replaced .grad (e.g. zero_grad(set_to_none))
             if p.grad is None:
+                # torch skips parameters without a gradient; here the flat kernel visits them, so give them a zero gradient
+                # (AdamW still decays them and advances their moments: a parameter that never gets a gradient is not expected)
+                self.grad[o:o + p.numel()].zero_()
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
             elif p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 self.grad[o:o + p.numel()].view_as(p).copy_(p.grad)
@@ -74,3 +79,20 @@ class FusedAdamWEMA:
         a.beta1, a.beta2, a.eps, a.weight_decay, a.step = self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count
         with torch.cuda.device(self.flat.device):
             _lib.check(_lib.lib().s3d_adamw_ema_step(C.byref(a), _lib.current_stream_ptr()))
+        for p in self.params:                                   # the kernel wrote the storage behind torch's back: bump the version
+            p.add_(0)                                           # counters so that weight caches keyed on them repack (handle())
+
+    def state_dict(self):
+        """step count, moments and EMA copies (the reference saves opt*.pt / ema_*.pt, train_util.py:258-281)."""
+        return dict(step_count=self.step_count, exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(),
+                    ema=[e.clone() for e in self.ema], ema_rates=list(self.ema_rates), lr=self.lr, weight_decay=self.weight_decay)
+
+    def load_state_dict(self, sd):
+        if sd["exp_avg"].numel() != self.n or len(sd["ema"]) != len(self.ema):
+            raise ValueError("optimizer state does not match this parameter set")
+        self.step_count = int(sd["step_count"])
+        with torch.no_grad():
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            for e, s in zip(self.ema, sd["ema"]):
+                e.copy_(s)

@@ -19,6 +19,8 @@ from . import _lib
 from .nn import sinusoid_freqs, zero_module
 
 _PLANES = ("xy", "xz", "yz")
+# conv operand terms of the tcgen05 kernels (include/sin3dm_b200.h: s3d_unet_config.precision); S3D_PRECISION overrides
+DEFAULT_PRECISION = 3
 
 
 class _TriConvParams(nn.Module):
@@ -105,7 +107,7 @@ class _S3DUNet(nn.Module):
                                  zero_module(_TriConvParams(c0, out_channels, 1, 0, is_rollout=False)))
 
         # kernel options: fp16x3 split (fp32-grade) unless S3D_PRECISION=1; tcgen05 conv unless S3D_CONV_IMPL=ffma
-        self.s3d_precision = int(os.environ.get("S3D_PRECISION", "3"))
+        self.s3d_precision = int(os.environ.get("S3D_PRECISION", str(DEFAULT_PRECISION)))
         self.s3d_conv_impl = 1 if os.environ.get("S3D_CONV_IMPL", "tc") == "ffma" else 0
         self._handle = None
         self._handle_key = None
@@ -184,14 +186,25 @@ class _S3DUNet(nn.Module):
     def film_dim(self):
         return _lib.lib().s3d_unet_film_dim(self.handle())
 
-    def film_table(self, timesteps):
-        """[n, film_dim] conditioning rows for ``timesteps`` (float32 tensor on the model's device)."""
+    def film_table(self, timesteps, cache=False):
+        """[n, film_dim] conditioning rows for ``timesteps`` (float32 values).  ``cache=True`` keeps the table per (weights,
+        timesteps) so that repeated sampling loops see the same device buffer (the sampling graph is cached by address)."""
         h = self.handle()
+        key = None
+        if cache:
+            key = (self._weights_key, timesteps.detach().to("cpu", th.float32).numpy().tobytes())
+            hit = self.__dict__.setdefault("_film_cache", {}).get(key)
+            if hit is not None:
+                return hit
         t = timesteps.to(self._device(), th.float32).contiguous()
         out = th.empty(t.numel(), self.film_dim, device=t.device, dtype=th.float32)
         with th.cuda.device(t.device):
             _lib.check(_lib.lib().s3d_unet_film(h, C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(out.data_ptr()),
                                                  _lib.current_stream_ptr()))
+        if cache:
+            if len(self._film_cache) >= 4:
+                self._film_cache.clear()
+            self._film_cache[key] = out
         return out
 
     # ------------------------------------------------------------------ forward

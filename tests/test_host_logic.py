@@ -100,7 +100,7 @@ def test_abi_exports_every_declared_symbol():
     declared = set(re.findall(r"\b(s3d_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib._SIGNATURES), declared ^ set(_lib._SIGNATURES)
     L = _lib.lib()            # raises if the .so is missing or a symbol cannot be bound
-    assert L.s3d_abi_version() == 1
+    assert L.s3d_abi_version() == 2
     for name in declared:
         assert hasattr(L, name)
     # struct sizes agree with the header layout (no compute call: there is no GPU here)
@@ -195,3 +195,17 @@ def test_fused_optimizer_refuses_cpu_parameters():
     from sin3dm_b200.optim import FusedAdamWEMA
     with pytest.raises(_lib.S3DError):
         FusedAdamWEMA([torch.nn.Parameter(torch.zeros(4))], lr=1e-3)
+
+
+def test_synthetic_weights_match_the_oracle_recipe():
+    """bench.py's GPU arm draws its checkpoint with sin3dm_b200.synthetic (no oracle import on the product arm); the CPU arm and
+    the parity tests use oracle.unet_ref.synthetic_state_dict.  Same generator, same order, same values."""
+    import torch
+    import sin3dm_b200 as s3
+    from oracle import unet_ref as ur
+    from sin3dm_b200.synthetic import synthetic_state_dict_like
+    m = s3.TriplaneUNetModelSmall(12, 64, 12, 1, 0, (1, 2), use_scale_shift_norm=True)
+    a = synthetic_state_dict_like(m, 1234)
+    b = ur.synthetic_state_dict(ur.UNetSpec(in_channels=12, model_channels=64, out_channels=12), 1234)
+    assert list(a) == list(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)

@@ -111,3 +111,46 @@ def test_philox_normals_moments():
     z3 = philox_ref.normals(seed=12345, sample_idx=3, step=7, C=8, hw=20000)       # 2 quads per pixel instead of 3
     assert not np.array_equal(z[:8], z3)
     assert not np.array_equal(z, philox_ref.normals(seed=12345, sample_idx=4, step=7, C=12, hw=20000))
+
+
+# ---------------------------------------------------------------------------- guided sampling hooks
+def _cond_oracle(case):
+    from oracle.cases import cond_fn, denoised_fn
+    spec = ur.UNetSpec(**case["spec"])
+    sd = ur.synthetic_state_dict(spec, case["wseed"])
+    H, W, D = case["HWD"]
+    o = dr.RefDiffusion(case["T"], case["respacing"], "linear", case.get("mean_type", "start_x"), "fixed_large",
+                        case.get("rescale_timesteps", False))
+    x_T, noises = make_step_noise(case, o.num_timesteps)
+    kw = dict(clip=True, cond_fn=cond_fn if case["cond"] else None, denoised_fn=denoised_fn if case["denoise"] else None)
+    if case["ddim"]:
+        kw["eta"] = case.get("eta", 0.0)
+    return o, x_T, o.sample_loop(lambda xx, tt: ur.unet_forward(sd, spec, xx, tt, H, W, D), x_T, lambda i: noises[i],
+                                 ddim=case["ddim"], **kw)
+
+
+def test_cond_hooks_match_reference(golden_dir):
+    """condition_mean / condition_score / denoised_fn loops and q_mean_variance (gaussian_diffusion.py:172-187, 357-394)."""
+    from oracle.cases import COND_CASES
+    for name, case in COND_CASES.items():
+        g = np.load(os.path.join(golden_dir, f"cond_{name}.npz"))
+        o, x_T, got = _cond_oracle(case)
+        assert np.abs(got.numpy() - g["sample"]).max() <= 1e-4, name
+        qm, qv, qlv = o.q_mean_variance(x_T, torch.from_numpy(g["t"]))
+        assert np.array_equal(qm.numpy(), g["q_mean"])
+        assert np.array_equal(qv[:, 0, 0, 0].numpy(), g["q_var"]) and np.array_equal(qlv[:, 0, 0, 0].numpy(), g["q_logvar"])
+
+
+def test_full_chain_fixtures_are_wellformed(golden_dir):
+    """The full-length BASELINE chains run on the GPU only (tests/test_gpu_full_chains.py); here: the committed fixtures have the
+    shapes oracle.cases.pack_full promises and a clamped final latent (x_0 prediction of the last step is clipped to [-1, 1])."""
+    from oracle.cases import FULL_CASES, FULL_STRIDE
+    for name, case in FULL_CASES.items():
+        g = np.load(os.path.join(golden_dir, f"full_{name}.npz"))
+        H, W, D = case["HWD"]
+        C, B = case["spec"]["in_channels"], case["B"]
+        assert g["sample0"].shape == (C, H + D, W + D)
+        assert np.abs(g["sample0"][:, :H, :W]).max() <= 1.0 + 1e-6
+        if B > 1:
+            n = C * (H + D) * (W + D)
+            assert g["rest_strided"].shape == (B - 1, (n + FULL_STRIDE - 1) // FULL_STRIDE)

@@ -60,8 +60,8 @@ def main():
     x = torch.randn(B, Cc, H + D, W + D, generator=torch.Generator().manual_seed(0)).to(dev)
     a = _lib.LoopArgs()
     a.kind = _lib.DDIM if wl["sampler"] == "ddim" else _lib.DDPM
-    a.mean_type, a.clip_denoised, a.n_steps = _lib.START_X, 1, args.steps
-    a.B, a.H, a.W, a.D = B, H, W, D
+    a.mean_type, a.clip_denoised, a.n_steps, a.t_start = _lib.START_X, 1, args.steps, 999
+    a.B, a.H, a.W, a.D, a.n_per_sample = B, H, W, D, x[0].numel()
     a.x_dev, a.coef_dev, a.film_dev = x.data_ptr(), coef.data_ptr(), film.data_ptr()
     a.seed, a.sample_base, a.use_graph = 1234, 0, 1
     _lib.check(L.s3d_sample_loop(h, C.byref(a), _lib.current_stream_ptr()))
