@@ -213,6 +213,27 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream);
 int s3d_unet_graph_builds(const s3d_unet* u);
 
 
+/* ---- training backward (replaces loss.backward() through TriplaneUNetModelSmall[Raw] in TrainLoop.forward_backward, reference
+ *      src/diffusion/train_util.py:198-235; the forward being differentiated is src/diffusion/unet_triplane.py:465-510) ----
+ * s3d_unet_set_training(u, 1): the next forward builds a plan that keeps every activation and statistics buffer and carries the
+ * backward op list (the sampling loop is refused in this mode).  s3d_unet_backward differentiates the LAST s3d_unet_forward[_film]:
+ *   grad_out_dev : dL/d(out), [B, out_channels, H+D, W+D] fp32 (the composed layout of the forward's output)
+ *   grads_dev    : out, flat fp32 buffer of s3d_unet_grad_numel() floats: the gradient of checkpoint tensor i (reference layout,
+ *                  s3d_unet_tensor_info order) starts at s3d_unet_grad_offset(u, i).  The time_embed.* / emb_layers.* slots are left
+ *                  zero: their gradient is returned through dfilm_dev instead —
+ *   dfilm_dev    : out (optional), [B][film_dim]: dL/d(conditioning row) of every sample, to be pushed through the embedding MLP
+ *                  (time_embed + emb_layers: a [B, 256] GEMV chain the host mirror owns).
+ * x (the forward's input) and the conditioning rows must still be alive.  No gradient w.r.t. x is produced (TrainLoop does not
+ * need one).  Gradients are carried multiplied by a device-chosen power-of-two loss scale and un-scaled at the end. */
+int s3d_unet_set_training(s3d_unet* u, int on);
+int64_t s3d_unet_grad_numel(s3d_unet* u);
+int64_t s3d_unet_grad_offset(s3d_unet* u, int index);
+int s3d_unet_backward(s3d_unet* u, const float* grad_out_dev, float* grads_dev, float* dfilm_dev, void* stream);
+/* Launch list of the backward (kernel name, dense algorithmic FLOPs) and its per-op device times (bench.py --workload cfg4). */
+int s3d_unet_bwd_op_count(const s3d_unet* u);
+int s3d_unet_bwd_op_info(const s3d_unet* u, int index, const char** kernel, double* dense_flops);
+int s3d_unet_profile_bwd_ops(s3d_unet* u, int iters, float* ms_out, void* stream);
+
 /* ---- triplane decoder (replaces AutoEncoderGroupSkip.decode and ShapeAutoEncoder.decode_batch / decode_grid:
  *      reference src/encoding/networks.py:134-223, src/encoding/model.py:319-349) ----
  * Latent planes in, SDF + texture at query points out.  The two TriplaneGroupResnetBlocks (blocks.py:189-256) depend on

@@ -96,6 +96,13 @@ _SIGNATURES = {
     "s3d_adamw_ema_step": (C.c_int, [C.POINTER(AdamWArgs), C.c_void_p]),
     "s3d_sample_loop": (C.c_int, [C.c_void_p, C.POINTER(LoopArgs), C.c_void_p]),
     "s3d_unet_graph_builds": (C.c_int, [C.c_void_p]),
+    "s3d_unet_set_training": (C.c_int, [C.c_void_p, C.c_int]),
+    "s3d_unet_grad_numel": (C.c_int64, [C.c_void_p]),
+    "s3d_unet_grad_offset": (C.c_int64, [C.c_void_p, C.c_int]),
+    "s3d_unet_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "s3d_unet_bwd_op_count": (C.c_int, [C.c_void_p]),
+    "s3d_unet_bwd_op_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double)]),
+    "s3d_unet_profile_bwd_ops": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "s3d_decoder_create": (C.c_int, [C.POINTER(DecoderConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "s3d_decoder_destroy": (C.c_int, [C.c_void_p]),
     "s3d_decoder_num_tensors": (C.c_int, [C.c_void_p]),

@@ -19,6 +19,7 @@
 #include "conv_tc.cuh"
 #include "host_util.cuh"
 #include "kernels.cuh"
+#include "train_kernels.cuh"
 
 using namespace s3d;
 
@@ -56,6 +57,9 @@ struct DevConv3 {        // one 3x3 TriplaneConv (+ optional fused 1x1 skip)
     float* wr[3][2] = {};       // rollout 1-D weights [3C][4Cout] (border classes pre-summed) per (plane, group)
     __half* wr16[3][2] = {};    // same as fp16 (hi, lo) [2][4Cout][3C] (K-major B operand of k_roll_tc)
     float* bias[3] = {};        // conv bias (+ skip bias)
+    // training: operands of the backward GEMMs, re-packed on the device from w_orig / wskip_orig (k_pack_dgrad)
+    __half* wd_pack[3] = {};    // dgrad of the 3x3: [2][C][9*Cout], K = tap'*Cout + co, value W[co][c][2-kh'][2-kw']
+    __half* wsd_pack[3] = {};   // dgrad of the 1x1 skip: [2][Cs][Cout]
 };
 struct DevNorm {
     float* gamma[3] = {};
@@ -101,6 +105,17 @@ struct Plan {
     int* t_idx = nullptr;           // [B]
     unsigned int* ticket = nullptr;
     float* model_out = nullptr;     // [B][Cout][Hc][Wc]
+    // training (s3d_unet_backward)
+    bool train = false;
+    std::vector<std::pair<void*, size_t>> fwd_zero;     // statistics accumulators cleared before every training forward
+    std::vector<std::pair<void*, size_t>> bwd_zero;     // reduction buffers cleared before every backward
+    std::vector<std::function<void(cudaStream_t)>> bwd_ops;
+    std::vector<std::string> bwd_names;
+    std::vector<double> bwd_flops;
+    const float* grad_out = nullptr;    // dL/d(out) bound by s3d_unet_backward
+    float* grads_own = nullptr;         // flat parameter gradients (state_dict order), copied out at the end
+    float* dfilm_own = nullptr;         // [B][film_dim]
+    unsigned int* amax = nullptr;       // max |grad_out| (float bits): the loss scale
     unsigned long long* dyn = nullptr;   // [2]: seed, sample_base of the running loop
     std::map<std::string, cudaGraphExec_t> graphs;      // captured steps by (sampler options, buffer pointers)
 };
@@ -131,6 +146,10 @@ struct s3d_unet {
     bool trace_on = false;   // s3d_unet_trace_enable
     int profile_mode = -1;   // last s3d_unet_profile_ops: 1 = graph replay with event nodes, 0 = eager launches
     int graph_builds = 0;    // graphs captured + instantiated by s3d_sample_loop
+    bool training = false;   // s3d_unet_set_training: plans keep every activation and carry a backward op list
+    std::vector<int64_t> grad_off;   // offset of tensor i inside the flat gradient buffer (multiples of 4 floats)
+    int64_t grad_numel = 0;
+    bool bwd_wgrad_ffma = true;
 };
 
 static bool mode_has_blo(int precision) { return precision == 2 || precision == 3; }
@@ -419,6 +438,8 @@ static void destroy_plan(s3d_unet* u) {
     u->plan.reset();
 }
 
+static void build_dgrad_packs(s3d_unet* u);      // train_host.cuh
+
 static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaSetDevice(u->device));
     destroy_plan(u);
@@ -453,7 +474,7 @@ static void finalize(s3d_unet* u) {
         u->out_b[p] = dev_upload(u->wallocs, T_(u, std::string("out.2.conv_") + kPlane[p] + ".bias").host);
     }
     upload_norm(u, u->out_norm, "out.0");
-    u->dblocks.assign(u->blocks.size(), DevBlock{});
+    u->dblocks.assign(u->blocks.size(), DevBlock{});      // (also forgets the dgrad packs freed with wallocs above)
     for (size_t i = 0; i < u->blocks.size(); ++i) {
         const auto& b = u->blocks[i];
         DevBlock& d = u->dblocks[i];
@@ -471,6 +492,7 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kRollSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kRollSmemBytes));
     CUDA_TRY(cudaDeviceSynchronize());
+    if (u->training) build_dgrad_packs(u);
     u->finalized = true;
 }
 
@@ -500,6 +522,8 @@ struct PlanBuilder {
     std::vector<TriDims> dims;   // per level
     int B;
     Arena arena;
+    bool train = false;          // keep every activation, no in-step re-zeroing chains, record the tape for the backward
+    Arena barena;                // backward temporaries (always with reuse)
 
     void add_op(const char* name, double flops, std::function<void(cudaStream_t)> fn, Trace tr = Trace{}) {
         P->ops.push_back(std::move(fn));
@@ -574,6 +598,7 @@ struct PlanBuilder {
         const size_t n = static_cast<size_t>(B) * off * C;
         S.buf = dev_alloc<unsigned long long>(P->allocs, n);
         CUDA_TRY(cudaMemset(S.buf, 0, sizeof(unsigned long long) * n));
+        if (train) P->fwd_zero.push_back({S.buf, sizeof(unsigned long long) * n});
         S.means16 = dev_alloc<__half>(P->allocs, 2 * n);
         const int ny = std::max(1, 256 / (C / 4));
         int tk = 0;
@@ -594,6 +619,7 @@ struct PlanBuilder {
         const size_t n = static_cast<size_t>(B) * 3 * kGnRep * 64;
         S.acc = dev_alloc<unsigned long long>(P->allocs, n);
         CUDA_TRY(cudaMemset(S.acc, 0, sizeof(unsigned long long) * n));
+        if (train) P->fwd_zero.push_back({S.acc, sizeof(unsigned long long) * n});
         S.C = C;
         bx->src.acc = S.acc;
         bx->src.film_dim = u->film_dim;
@@ -649,7 +675,7 @@ struct PlanBuilder {
         const int nslots = std::max(1, std::min(128, max_px(level) / 48));
         if (standalone) bx = make_box(C);
         S3D_CHECK(!bx->armed, "tensor normalised twice");
-        chain_zero(bx);
+        if (!train) chain_zero(bx);        // training: the sums stay for the backward and are cleared before the next forward
         bx->src.gamma = cf3(n.gamma);
         bx->src.beta = cf3(n.beta);
         bx->src.film_off = film_off;
@@ -715,7 +741,7 @@ struct PlanBuilder {
         // work); the first one clears the last one's, which is a step old by then.  (With A.finalize the kernel converts and
         // clears its own sums.)
         auto zj = std::make_shared<ZeroJob>();
-        if (S && !A.finalize) {
+        if (S && !A.finalize && !train) {
             if (last_sums.p) *zj = last_sums;
             if (!first_zero_job) first_zero_job = zj;
             last_sums = ZeroJob{S->buf, static_cast<long long>(B) * S->total_len * C};
@@ -893,7 +919,7 @@ struct PlanBuilder {
             });
             return;
         }
-        S3D_CHECK(cv.C % kBK == 0 && cv.Cout % kBN == 0 && cv.Cs % kBK == 0, "tcgen05 conv needs channel counts % 64 == 0");
+        S3D_CHECK(cv.C % kBK == 0 && cv.Cout % kBN == 0 && cv.Cs % kBK == 0 && cv.C + cv.Cs > 0, "tcgen05 conv needs channel counts % 64 == 0");
         auto maps = std::make_shared<ConvTcMaps>();
         memset(maps.get(), 0, sizeof(ConvTcMaps));
         ConvTcArgs A{};
@@ -910,11 +936,12 @@ struct PlanBuilder {
                                        static_cast<uint64_t>(d.rows[p]), static_cast<uint64_t>(B), 2};
             const uint32_t abox[5] = {kBK, kHaloW, kHaloH, 1, 1};      // halo patch (cols w0-1.., rows h0-1..)
             const uint32_t xbox[5] = {kBK, kTileW, kTileH, 1, 1};      // plain tile for the 1x1 skip chunks
-            make_tmap(&maps->a[p], a.p.p[p], 5, adims, abox);
+            if (cv.C) make_tmap(&maps->a[p], a.p.p[p], 5, adims, abox);
             if (cv.Cs) {
                 const uint64_t xdims[5] = {static_cast<uint64_t>(cv.Cs), static_cast<uint64_t>(d.cols[p]),
                                            static_cast<uint64_t>(d.rows[p]), static_cast<uint64_t>(B), 2};
                 make_tmap(&maps->x[p], x16->p.p[p], 5, xdims, xbox);
+                if (!cv.C) maps->a[p] = maps->x[p];       // pure 1x1 GEMM (training: the skip conv's dgrad): no 3x3 part
             } else {
                 maps->x[p] = maps->a[p];
             }
@@ -981,6 +1008,25 @@ struct PlanBuilder {
     // One TriplaneResBlock (unet_triplane.py:269-311).  The input is either the fp32 residual stream `x`, or — for the decoder
     // blocks behind a concat — the (hi, lo) fp16 tensor `xh` that k_upcat wrote (it doubles as the skip GEMM's operand).
     // Buffers go back to the arena as soon as their last reader is planned; the caller releases the block's input.
+    struct BlockTape {               // what one TriplaneResBlock's backward reads (training plans)
+        int bi = -1, level = 0;
+        bool x_is_pair = false;
+        ActF x;                      // block input (fp32), or
+        Act16 xh;                    // the (hi, lo) concat input
+        std::shared_ptr<SinkBox> st1, st2;
+        Act16 a1, a2, x16;
+        Sums s1, s2;
+        ActF h1, out;
+    };
+    struct UpTape {
+        ActF low, skip;
+        int out_level = 0;
+        bool do_up = false;
+    };
+    std::vector<BlockTape> enc_tape, dec_tape;      // in forward order
+    std::vector<UpTape> up_tape;                    // up_tape[j] feeds dec_tape[j] (j >= 1)
+    std::vector<BlockTape>* cur_tape = nullptr;
+
     ActF res_block(int bi, const ActF* x, const Act16* xh, const std::shared_ptr<SinkBox>& xh_sink, int level, ActF* pool_out = nullptr) {
         const BlockSpec& b = u->blocks[bi];
         const DevBlock& w = u->dblocks[bi];
@@ -1019,6 +1065,24 @@ struct PlanBuilder {
         conv(a2, level, w.c2, ro ? &t2 : nullptr, b.has_skip ? &x16 : nullptr, b.has_skip ? nullptr : x, -1, out, pool_out);
         release(a2);
         if (b.has_skip && x) release(x16);
+        if (train && cur_tape) {
+            BlockTape T;
+            T.bi = bi;
+            T.level = level;
+            T.x_is_pair = x == nullptr;
+            if (x) T.x = *x;
+            else T.xh = *xh;
+            T.st1 = st1;
+            T.st2 = st2;
+            T.a1 = a1;
+            T.a2 = a2;
+            T.x16 = x16;
+            T.s1 = s1;
+            T.s2 = s2;
+            T.h1 = h1;
+            T.out = out;
+            cur_tape->push_back(T);
+        }
         return out;
     }
 
@@ -1068,6 +1132,8 @@ struct PlanBuilder {
     }
 };
 
+#include "train_host.cuh"
+
 static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     CUDA_TRY(cudaSetDevice(u->device));
     destroy_plan(u);
@@ -1081,6 +1147,11 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
     const auto& c = u->cfg;
     PlanBuilder pb{u, P, {}, B};
     if (const char* e = getenv("S3D_KEEP_ACTS")) pb.arena.reuse = atoi(e) == 0;
+    if (u->training) {
+        S3D_CHECK(u->cfg.conv_impl == 0 && u->fuse_roll, "training needs the tcgen05 conv path with fused roll tiles");
+        pb.train = P->train = true;
+        pb.arena.reuse = false;        // every activation is read again by the backward
+    }
     TriDims d{{H, H, W}, {W, D, D}};
     for (int l = 0; l < c.n_levels; ++l) {
         S3D_CHECK(d.rows[0] >= 1 && d.rows[2] >= 1 && d.cols[1] >= 1, "triplane too small for the number of levels");
@@ -1136,6 +1207,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         }, tr);
     }
     // ---- encoder
+    pb.cur_tape = &pb.enc_tape;
     std::vector<ActF> stack;
     ActF pooled{};
     bool have_pooled = false;     // the Downsample2x of the next level was produced by the previous block's last conv
@@ -1168,6 +1240,8 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         stack.push_back(h);
     }
     // ---- decoder (unet_triplane.py:488-505)
+    pb.cur_tape = &pb.dec_tape;
+    pb.up_tape.assign(c.n_levels, PlanBuilder::UpTape{});
     bool pending_up = false;    // an Upsample2x closed the previous output block
     for (int j = 0; j < c.n_levels; ++j) {
         const int level = c.n_levels - 1 - j;
@@ -1187,6 +1261,7 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
                               "TriplaneUNetModelSmallRaw needs even plane sizes at every level (torch.cat would fail)");
             }
             hcat = pb.upcat(h, skip, level, pending_up, hcat_sink);
+            pb.up_tape[j] = PlanBuilder::UpTape{h, skip, level, pending_up};
             pb.release(h);
             pb.release(skip);
             pending_up = false;
@@ -1244,7 +1319,8 @@ static void build_plan(s3d_unet* u, int B, int H, int W, int D) {
         }
     }
     pb.close_zero_chain();
-    P->alloc_bytes += pb.arena.touched();
+    if (pb.train) build_backward(u, pb, h, st, bnd);
+    P->alloc_bytes += pb.arena.touched() + pb.barena.touched();
     P->sched_trace = pb.new_trace();
     CUDA_TRY(cudaDeviceSynchronize());
 }
@@ -1279,6 +1355,10 @@ static void clear_stale_in_acc(Plan* P, cudaStream_t s) {
         CUDA_TRY(cudaMemsetAsync(P->in_acc, 0, P->in_acc_n * sizeof(unsigned long long), s));
         P->in_acc_stale = false;
     }
+}
+static void train_forward_prologue(Plan* P, cudaStream_t s) {
+    if (!P->train) return;
+    for (auto& z : P->fwd_zero) CUDA_TRY(cudaMemsetAsync(z.first, 0, z.second, s));
 }
 static void run_ops(s3d_unet* u, Plan* P, cudaStream_t s) {
     // experiment switch (timing only, results are wrong): S3D_DUP_OPS=1 launches every op twice back to back, so that the
@@ -1420,6 +1500,7 @@ int s3d_unet_forward_film(s3d_unet* u, const float* x_dev, const float* film_dev
     P->film = film_dev;
     P->film_row = row_dev;
     clear_stale_in_acc(P, static_cast<cudaStream_t>(stream));
+    train_forward_prologue(P, static_cast<cudaStream_t>(stream));
     run_ops(u, P, static_cast<cudaStream_t>(stream));
     API_END
 }
@@ -1437,6 +1518,7 @@ int s3d_unet_forward(s3d_unet* u, const float* x_dev, const float* t_dev, float*
     P->film = P->film_own;
     P->film_row = nullptr;
     clear_stale_in_acc(P, s);
+    train_forward_prologue(P, s);
     run_ops(u, P, s);
     u->last_launches += 4;
     API_END
@@ -1598,6 +1680,7 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
     S3D_CHECK(u->cfg.in_channels == u->cfg.out_channels, "sampling needs in_channels == out_channels");
     const long long n = static_cast<long long>(u->cfg.out_channels) * Hc * Wc;
     S3D_CHECK(a->n_per_sample == n, "x_dev does not have out_channels * (H+D) * (W+D) elements per sample");
+    S3D_CHECK(!u->training, "the sampling loop needs an inference plan: s3d_unet_set_training(u, 0) first");
     Plan* P = get_plan(u, a->B, a->H, a->W, a->D);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (!P->t_idx) {
@@ -1701,6 +1784,96 @@ int s3d_sample_loop(s3d_unet* u, const s3d_loop_args* a, void* stream) {
 }
 
 int s3d_unet_graph_builds(const s3d_unet* u) { return u ? u->graph_builds : 0; }
+
+// ---------------------------------------------------------------------------------- training
+int s3d_unet_set_training(s3d_unet* u, int on) {
+    API_BEGIN
+    S3D_CHECK(u, "null handle");
+    const bool want = on != 0;
+    if (u->training != want) {
+        CUDA_TRY(cudaSetDevice(u->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        destroy_plan(u);              // the next forward rebuilds it with (or without) the tape and the backward list
+        u->training = want;
+        if (want) {
+            if (u->grad_numel == 0) build_grad_layout(u);
+            if (u->finalized) build_dgrad_packs(u);
+        }
+    }
+    API_END
+}
+
+int64_t s3d_unet_grad_numel(s3d_unet* u) {
+    if (!u) return 0;
+    if (u->grad_numel == 0) build_grad_layout(u);
+    return u->grad_numel;
+}
+
+int64_t s3d_unet_grad_offset(s3d_unet* u, int index) {
+    if (!u || index < 0 || index >= static_cast<int>(u->tensors.size())) return -1;
+    if (u->grad_numel == 0) build_grad_layout(u);
+    return u->grad_off[index];
+}
+
+int s3d_unet_backward(s3d_unet* u, const float* grad_out_dev, float* grads_dev, float* dfilm_dev, void* stream) {
+    API_BEGIN
+    S3D_CHECK(u && grad_out_dev && grads_dev, "null argument");
+    S3D_CHECK(u->training && u->plan && u->plan->train, "no training forward to differentiate: s3d_unet_set_training(u, 1), then a forward");
+    Plan* P = u->plan.get();
+    S3D_CHECK(P->x && P->film, "run the forward first");
+    CUDA_TRY(cudaSetDevice(u->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (auto& z : P->bwd_zero) CUDA_TRY(cudaMemsetAsync(z.first, 0, z.second, s));
+    P->grad_out = grad_out_dev;
+    for (auto& op : P->bwd_ops) op(s);
+    CUDA_TRY(cudaMemcpyAsync(grads_dev, P->grads_own, sizeof(float) * static_cast<size_t>(u->grad_numel), cudaMemcpyDeviceToDevice, s));
+    if (dfilm_dev)
+        CUDA_TRY(cudaMemcpyAsync(dfilm_dev, P->dfilm_own, sizeof(float) * static_cast<size_t>(P->B) * u->film_dim, cudaMemcpyDeviceToDevice, s));
+    u->last_launches = static_cast<int>(P->bwd_ops.size());
+    API_END
+}
+
+int s3d_unet_bwd_op_count(const s3d_unet* u) { return (u && u->plan) ? static_cast<int>(u->plan->bwd_ops.size()) : 0; }
+
+int s3d_unet_bwd_op_info(const s3d_unet* u, int index, const char** kernel, double* dense_flops) {
+    API_BEGIN
+    S3D_CHECK(u && u->plan && index >= 0 && index < static_cast<int>(u->plan->bwd_ops.size()), "bad index");
+    if (kernel) *kernel = u->plan->bwd_names[index].c_str();
+    if (dense_flops) *dense_flops = u->plan->bwd_flops[index];
+    API_END
+}
+
+// Mean device time (ms) of every backward op: `iters` eager passes with a CUDA-event pair around each launch.  Needs a completed
+// forward + backward (uses their bindings); synchronises.
+int s3d_unet_profile_bwd_ops(s3d_unet* u, int iters, float* ms_out, void* stream) {
+    API_BEGIN
+    S3D_CHECK(u && u->plan && u->plan->train && ms_out && iters >= 1, "bad argument");
+    Plan* P = u->plan.get();
+    S3D_CHECK(P->grad_out, "run a backward first");
+    CUDA_TRY(cudaSetDevice(u->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n = P->bwd_ops.size();
+    std::vector<double> acc(n, 0.0);
+    std::vector<cudaEvent_t> ev(2 * n);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    for (int it = 0; it < iters + 1; ++it) {          // first pass is a warm-up
+        for (auto& z : P->bwd_zero) CUDA_TRY(cudaMemsetAsync(z.first, 0, z.second, s));
+        for (size_t i = 0; i < n; ++i) {
+            CUDA_TRY(cudaEventRecord(ev[2 * i], s));
+            P->bwd_ops[i](s);
+            CUDA_TRY(cudaEventRecord(ev[2 * i + 1], s));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < n && it > 0; ++i) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+            acc[i] += ms;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    for (size_t i = 0; i < n; ++i) ms_out[i] = static_cast<float>(acc[i] / iters);
+    API_END
+}
 
 int64_t s3d_unet_workspace_bytes(const s3d_unet* u) { return (u && u->plan) ? static_cast<int64_t>(u->plan->alloc_bytes) : 0; }
 

@@ -1,0 +1,787 @@
+// Backward kernels of the triplane UNet (training row).
+//   reference: loss.backward() through TriplaneUNetModelSmall inside TrainLoop.forward_backward
+//              (src/diffusion/train_util.py:198-235; forward being differentiated: src/diffusion/unet_triplane.py:21-145, 175-311,
+//              465-510).  The adjoints are restated op by op in oracle/backward_ref.py (checked against torch.autograd), and these
+//              kernels follow that structure.
+// Every gradient tensor is carried multiplied by the loss scale S = 2^k (chosen on the device from max|dL/dout| so that the fp16
+// (hi, lo) operands of the tensor-core dgrad / wgrad stay in range); parameter gradients are multiplied by 1/S at the very end.
+// Layouts are the forward's: fp32 NHWC [B][rows][cols][C] per plane, conv operands as fp16 (hi, lo) pairs [2][B][rows][cols][C].
+#pragma once
+#include "boundary.cuh"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace s3d {
+
+// ---------------------------------------------------------------- loss scale
+// amax[0] = max |grad_out| as float bits (non-negative floats order like unsigned ints)
+__global__ void __launch_bounds__(256) k_grad_amax(const float* __restrict__ g, long long n, unsigned int* amax) {
+    float m = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+}
+// S = 2^k with amax * S in [32, 64): every kernel derives it from the same word, so all of them agree bit for bit
+__device__ __forceinline__ float loss_scale(const unsigned int* amax) {
+    const float a = fmaxf(__uint_as_float(__ldg(amax)), 1e-30f);
+    return exp2f(floorf(log2f(64.f / a)));
+}
+
+// ---------------------------------------------------------------- GroupNorm statistics -> (mean, rstd) per group
+// same arithmetic as stats_coef_prologue (kernels.cuh), kept for the backward: fin[64] -> mean[g], rstd[g]
+__device__ __forceinline__ void gn_mean_rstd(const unsigned long long* acc, int b, int plane, double n_per_group, int tid, float* mean, float* rstd) {
+    if (tid < kGroups) {
+        const unsigned long long* p = acc + (static_cast<size_t>(b) * 3 + plane) * kGnRep * 64;
+        unsigned long long s = 0ull, q = 0ull;
+#pragma unroll
+        for (int r = 0; r < kGnRep; ++r) {
+            s += __ldcg(p + r * 64 + tid * 2);
+            q += __ldcg(p + r * 64 + tid * 2 + 1);
+        }
+        const double inv_n = 1.0 / n_per_group;
+        const double mu = static_cast<double>(static_cast<long long>(s)) * kGnFixInv * inv_n;
+        const float var = fmaxf(static_cast<float>(static_cast<double>(static_cast<long long>(q)) * kGnFixInv * inv_n - mu * mu), 0.f);
+        mean[tid] = static_cast<float>(mu);
+        rstd[tid] = rsqrtf(var + kGnEps);
+    }
+}
+
+__device__ __forceinline__ float silu_grad(float f) {
+    const float sig = 1.f / (1.f + __expf(-f));
+    return sig * (1.f + f * (1.f - sig));
+}
+
+// =====================================================================================
+// GroupNorm (+FiLM) + SiLU backward, two passes (oracle/backward_ref.py::gn_film_silu_backward).
+//   forward:  xhat = (x - mean_g) rstd_g ; n = xhat gamma + beta ; f = n (1 + sc) + sh ; y = silu(f)
+//   pass A :  P1[b][plane][c] = sum_px df,  P2 = sum_px df xhat,   df = dy silu'(f)
+//   pass B :  dx = rstd_g ( df (1+sc) gamma - S1_g - xhat S2_g ),  S1_g = sum_{c in g} (1+sc) gamma P1 / n,  S2_g likewise with P2
+// x: fp32 [B][rows][cols][C], or the (hi, lo) pair written by k_upcat (xh).  dy: fp32.  grid (slots, 3, B), block (C/4, NY).
+// =====================================================================================
+struct GnBwdArgs {
+    TriCF x;
+    TriCH xh;
+    TriCF dy;
+    TriDims d;
+    int C, B;
+    const unsigned long long* acc;      // forward group sums of x [B][3][kGnRep][64]
+    TriCF gamma, beta;
+    const float* film;                  // [rows][film_dim] or nullptr
+    const int* film_row;
+    int film_dim, film_off;
+    double* psum;                       // [B][3][C][2] (P1, P2), zeroed before pass A
+    TriCF add;                          // pass B: optional fp32 addend (identity-skip gradient), same shape as dx
+    TriF dx;                            // pass B output
+    int nslots;
+};
+
+__device__ __forceinline__ float4 gnb_load_x(const GnBwdArgs& A, int plane, size_t sample_off, size_t lo_off, size_t e) {
+    if (A.x.p[plane]) return __ldg(reinterpret_cast<const float4*>(A.x.p[plane] + sample_off + e));
+    const __half* ph = A.xh.p[plane] + sample_off + e;
+    return join_halves4(__ldg(reinterpret_cast<const uint2*>(ph)), __ldg(reinterpret_cast<const uint2*>(ph + lo_off)));
+}
+
+// per-CTA prologue shared by both passes: per-channel forward coefficients in shared memory
+//   ca, cb : f = x ca + cb        xm, xr : xhat = (x - xm) xr
+__device__ __forceinline__ void gnb_prologue(const GnBwdArgs& A, int b, int plane, int tid, int nthr, float* mean, float* rstd, float* ca,
+                                             float* cb, float* xm, float* xr) {
+    const int C = A.C, cpg = C / kGroups;
+    const double n = static_cast<double>(A.d.rows[plane]) * A.d.cols[plane] * cpg;
+    gn_mean_rstd(A.acc, b, plane, n, tid, mean, rstd);
+    __syncthreads();
+    const float* film = A.film ? A.film + static_cast<size_t>(A.film_row ? A.film_row[b] : b) * A.film_dim + A.film_off : nullptr;
+    for (int c = tid; c < C; c += nthr) {
+        const int g = c / cpg;
+        float ga = __ldg(A.gamma.p[plane] + c) * rstd[g];
+        float be = __ldg(A.beta.p[plane] + c) - mean[g] * ga;
+        if (film) {
+            const float sc = 1.f + __ldg(film + c), sh = __ldg(film + C + c);
+            ga *= sc;
+            be = fmaf(be, sc, sh);
+        }
+        ca[c] = ga;
+        cb[c] = be;
+        xm[c] = mean[g];
+        xr[c] = rstd[g];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_gn_bwd_a(GnBwdArgs A) {
+    extern __shared__ float sm[];      // ca[C] cb[C] xm[C] xr[C] red[NY][2][C]
+    __shared__ float mean[kGroups], rstd[kGroups];
+    const int plane = blockIdx.y, b = blockIdx.z, C = A.C;
+    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y, tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
+    float *ca = sm, *cb = sm + C, *xm = sm + 2 * C, *xr = sm + 3 * C, *red = sm + 4 * C;
+    gnb_prologue(A, b, plane, tid, nthr, mean, rstd, ca, cb, xm, xr);
+    const int npx = A.d.rows[plane] * A.d.cols[plane];
+    const int ppc = (npx + A.nslots - 1) / A.nslots;
+    const int p0 = blockIdx.x * ppc, p1 = min(npx, p0 + ppc);
+    const size_t sample_off = static_cast<size_t>(b) * npx * C, lo_off = static_cast<size_t>(A.B) * npx * C;
+    const float4 a4 = *reinterpret_cast<const float4*>(ca + tx * 4), b4 = *reinterpret_cast<const float4*>(cb + tx * 4);
+    const float4 m4 = *reinterpret_cast<const float4*>(xm + tx * 4), r4 = *reinterpret_cast<const float4*>(xr + tx * 4);
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    for (int px = p0 + ty; px < p1; px += NY) {
+        const size_t e = static_cast<size_t>(px) * C + tx * 4;
+        const float4 x = gnb_load_x(A, plane, sample_off, lo_off, e);
+        const float4 dy = __ldg(reinterpret_cast<const float4*>(A.dy.p[plane] + sample_off + e));
+        const float d0 = dy.x * silu_grad(fmaf(x.x, a4.x, b4.x)), d1 = dy.y * silu_grad(fmaf(x.y, a4.y, b4.y));
+        const float d2 = dy.z * silu_grad(fmaf(x.z, a4.z, b4.z)), d3 = dy.w * silu_grad(fmaf(x.w, a4.w, b4.w));
+        s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
+        s2.x = fmaf(d0, (x.x - m4.x) * r4.x, s2.x); s2.y = fmaf(d1, (x.y - m4.y) * r4.y, s2.y);
+        s2.z = fmaf(d2, (x.z - m4.z) * r4.z, s2.z); s2.w = fmaf(d3, (x.w - m4.w) * r4.w, s2.w);
+    }
+    float* r1 = red + (ty * 2 + 0) * C + tx * 4;
+    float* r2 = red + (ty * 2 + 1) * C + tx * 4;
+    r1[0] = s1.x; r1[1] = s1.y; r1[2] = s1.z; r1[3] = s1.w;
+    r2[0] = s2.x; r2[1] = s2.y; r2[2] = s2.z; r2[3] = s2.w;
+    __syncthreads();
+    for (int i = tid; i < 2 * C; i += nthr) {
+        const int which = i / C, c = i - which * C;
+        double acc = 0.0;
+        for (int y = 0; y < NY; ++y) acc += static_cast<double>(red[(y * 2 + which) * C + c]);
+        atomicAdd(A.psum + ((static_cast<size_t>(b) * 3 + plane) * C + c) * 2 + which, acc);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gn_bwd_b(GnBwdArgs A) {
+    extern __shared__ float sm[];      // ca cb xm xr k1[C] k2[C] k3[C] gs[2*32]
+    __shared__ float mean[kGroups], rstd[kGroups];
+    const int plane = blockIdx.y, b = blockIdx.z, C = A.C, cpg = C / kGroups;
+    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y, tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
+    float *ca = sm, *cb = sm + C, *xm = sm + 2 * C, *xr = sm + 3 * C, *k2 = sm + 4 * C, *k3 = sm + 5 * C, *gs = sm + 6 * C;
+    gnb_prologue(A, b, plane, tid, nthr, mean, rstd, ca, cb, xm, xr);
+    const int npx = A.d.rows[plane] * A.d.cols[plane];
+    // group sums S1_g, S2_g from the per-channel sums of pass A:  dxhat = df * (1+sc) gamma = df * ca / rstd
+    if (tid < 2 * kGroups) {
+        const int g = tid >> 1, which = tid & 1;
+        double acc = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+            acc += static_cast<double>(ca[c] / xr[c]) * A.psum[((static_cast<size_t>(b) * 3 + plane) * C + c) * 2 + which];
+        gs[tid] = static_cast<float>(acc / (static_cast<double>(npx) * cpg));
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += nthr) {
+        const int g = c / cpg;
+        const float r = xr[c], S1 = gs[g * 2], S2 = gs[g * 2 + 1];
+        // dx = df ca - rstd S1 - (x - mean) rstd^2 S2  =  df ca - x k3 - k2
+        k3[c] = r * r * S2;
+        k2[c] = r * S1 - xm[c] * r * r * S2;
+    }
+    __syncthreads();
+    const int ppc = (npx + A.nslots - 1) / A.nslots;
+    const int p0 = blockIdx.x * ppc, p1 = min(npx, p0 + ppc);
+    const size_t sample_off = static_cast<size_t>(b) * npx * C, lo_off = static_cast<size_t>(A.B) * npx * C;
+    const float4 a4 = *reinterpret_cast<const float4*>(ca + tx * 4), b4 = *reinterpret_cast<const float4*>(cb + tx * 4);
+    const float4 q2 = *reinterpret_cast<const float4*>(k2 + tx * 4), q3 = *reinterpret_cast<const float4*>(k3 + tx * 4);
+    const float* addp = A.add.p[plane];
+    float* out = A.dx.p[plane];
+    for (int px = p0 + ty; px < p1; px += NY) {
+        const size_t e = static_cast<size_t>(px) * C + tx * 4;
+        const float4 x = gnb_load_x(A, plane, sample_off, lo_off, e);
+        const float4 dy = __ldg(reinterpret_cast<const float4*>(A.dy.p[plane] + sample_off + e));
+        float4 o;
+        o.x = dy.x * silu_grad(fmaf(x.x, a4.x, b4.x)) * a4.x - x.x * q3.x - q2.x;
+        o.y = dy.y * silu_grad(fmaf(x.y, a4.y, b4.y)) * a4.y - x.y * q3.y - q2.y;
+        o.z = dy.z * silu_grad(fmaf(x.z, a4.z, b4.z)) * a4.z - x.z * q3.z - q2.z;
+        o.w = dy.w * silu_grad(fmaf(x.w, a4.w, b4.w)) * a4.w - x.w * q3.w - q2.w;
+        if (addp) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(addp + sample_off + e));
+            o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + sample_off + e) = o;
+    }
+}
+
+// Parameter / FiLM gradients of one norm site from the pass-A sums (still multiplied by the loss scale).
+//   dgamma[plane][c] = sum_b (1+sc) P2 ; dbeta = sum_b (1+sc) P1 ; dscale[b][c] += gamma P2 + beta P1 ; dshift[b][c] += P1 (over planes)
+// grid 1, block 256
+struct GnFinArgs {
+    const double* psum;      // [B][3][C][2]
+    TriCF gamma, beta;
+    const float* film;
+    const int* film_row;
+    int film_dim, film_off, C, B;
+    float* dgamma[3];
+    float* dbeta[3];
+    float* dfilm;            // [B][film_dim] accumulated (+=), or nullptr
+};
+__global__ void __launch_bounds__(256) k_gn_bwd_fin(GnFinArgs A) {
+    const int C = A.C;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+        const int plane = i / C, c = i - plane * C;
+        double dg = 0.0, db = 0.0;
+        for (int b = 0; b < A.B; ++b) {
+            const double* p = A.psum + ((static_cast<size_t>(b) * 3 + plane) * C + c) * 2;
+            double sc = 1.0;
+            if (A.film) sc += static_cast<double>(A.film[static_cast<size_t>(A.film_row ? A.film_row[b] : b) * A.film_dim + A.film_off + c]);
+            db += sc * p[0];
+            dg += sc * p[1];
+        }
+        A.dgamma[plane][c] = static_cast<float>(dg);
+        A.dbeta[plane][c] = static_cast<float>(db);
+    }
+    if (A.film && A.dfilm) {
+        for (int i = threadIdx.x; i < A.B * C; i += blockDim.x) {
+            const int b = i / C, c = i - b * C;
+            double dsc = 0.0, dsh = 0.0;
+            for (int plane = 0; plane < 3; ++plane) {
+                const double* p = A.psum + ((static_cast<size_t>(b) * 3 + plane) * C + c) * 2;
+                dsc += static_cast<double>(A.gamma.p[plane][c]) * p[1] + static_cast<double>(A.beta.p[plane][c]) * p[0];
+                dsh += p[0];
+            }
+            A.dfilm[static_cast<size_t>(b) * A.film_dim + A.film_off + c] += static_cast<float>(dsc);
+            A.dfilm[static_cast<size_t>(b) * A.film_dim + A.film_off + C + c] += static_cast<float>(dsh);
+        }
+    }
+}
+
+// =====================================================================================
+// Gradient staging: the fp32 gradient of a conv OUTPUT -> what the conv's backward consumes:
+//   * the (hi, lo) fp16 pair (operand of the tensor-core dgrad / wgrad),
+//   * its axis sums (rollout adjoint; oracle/backward_ref.py::_axis_sums): rs[b][seg(plane,0)+row][C] = sum over columns,
+//     cs[b][seg(plane,1)+col][C] = sum over rows  (fp64 atomics, zeroed before),
+//   * the per-channel total (bias gradient) [3][C] summed over the batch, and per (b, c) (additive-embedding gradient).
+// grid (row strips of 8, 3, B), block (C/4, NY)
+// =====================================================================================
+struct StageArgs {
+    TriCF g;              // fp32 [B][rows][cols][C]
+    TriDims d;
+    int C, B;
+    TriH pair;            // out [2][B][rows][cols][C]
+    double* sums;         // [B][total_len][C]
+    int seg_off[6];
+    int total_len;
+    double* bias_sum;     // [3][C]  (+=)
+    double* bc_sum;       // [B][C] (+= over planes) or nullptr
+};
+__global__ void __launch_bounds__(256) k_grad_stage(StageArgs A) {
+    extern __shared__ float sm[];      // red[NY][C]
+    const int plane = blockIdx.y, b = blockIdx.z, C = A.C;
+    const int rows = A.d.rows[plane], cols = A.d.cols[plane];
+    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y, tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
+    const int r0 = blockIdx.x * kGsRows;
+    if (r0 >= rows) return;
+    const int nr = min(kGsRows, rows - r0);
+    const size_t plane_elems = static_cast<size_t>(rows) * cols * C;
+    const float* gp = A.g.p[plane] + static_cast<size_t>(b) * plane_elems;
+    __half* ph = A.pair.p[plane] + static_cast<size_t>(b) * plane_elems;
+    const size_t lo_off = static_cast<size_t>(A.B) * plane_elems;
+    double* sb = A.sums + static_cast<size_t>(b) * A.total_len * C;
+    double* srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
+    double* scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < nr; ++r) {
+        float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = ty; c < cols; c += NY) {
+            const size_t e = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(gp + e));
+            store_split4(ph + e, ph + lo_off + e, v);
+            racc.x += v.x; racc.y += v.y; racc.z += v.z; racc.w += v.w;
+        }
+        float* cell = sm + ty * C + tx * 4;
+        cell[0] = racc.x; cell[1] = racc.y; cell[2] = racc.z; cell[3] = racc.w;
+        __syncthreads();
+        for (int i = tid; i < C; i += nthr) {
+            double acc = 0.0;
+            for (int y = 0; y < NY; ++y) acc += static_cast<double>(sm[y * C + i]);
+            atomicAdd(srow + static_cast<size_t>(r0 + r) * C + i, acc);
+        }
+        __syncthreads();
+        tot.x += racc.x; tot.y += racc.y; tot.z += racc.z; tot.w += racc.w;
+    }
+    // column sums of this strip: one thread per (column, channel quad)
+    for (int c = ty; c < cols; c += NY) {
+        float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < nr; ++r) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(gp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4));
+            cacc.x += v.x; cacc.y += v.y; cacc.z += v.z; cacc.w += v.w;
+        }
+        double* p = scol + static_cast<size_t>(c) * C + tx * 4;
+        atomicAdd(p, static_cast<double>(cacc.x)); atomicAdd(p + 1, static_cast<double>(cacc.y));
+        atomicAdd(p + 2, static_cast<double>(cacc.z)); atomicAdd(p + 3, static_cast<double>(cacc.w));
+    }
+    // per-channel total of the strip
+    float* cell = sm + ty * C + tx * 4;
+    cell[0] = tot.x; cell[1] = tot.y; cell[2] = tot.z; cell[3] = tot.w;
+    __syncthreads();
+    for (int i = tid; i < C; i += nthr) {
+        double acc = 0.0;
+        for (int y = 0; y < NY; ++y) acc += static_cast<double>(sm[y * C + i]);
+        atomicAdd(A.bias_sum + plane * C + i, acc);
+        if (A.bc_sum) atomicAdd(A.bc_sum + static_cast<size_t>(b) * C + i, acc);
+    }
+}
+
+// =====================================================================================
+// Rollout adjoint (oracle/backward_ref.py::tri_conv_backward_folded).  For the source s = (plane p, group g) of a conv with
+// stored weight W[Cout][3C][3][3]: the broadcast vector vec_s[L][C] (an axis mean of another plane) entered plane p's conv along
+// rows (row_varying) or columns.  With Sy_a[pos][co] = the axis sum of dY over the lines the tap `across = a` reaches
+// (a = 0: all but the first line, 1: all, 2: all but the last),
+//   dvec[j][c]             = sum_{along, a, co} Sy_a[j - along + 1][co] W[co][gC + c][along, a]
+//   dW[co][gC + c][along,a] = sum_{b, pos} Sy_a[pos][co] vec[pos + along - 1][c]
+// dvec / n_avg is what every pixel of the source plane's line j receives: written as the Trow / Tcol addend of the dgrad conv
+// (all four edge classes get the same values).
+// =====================================================================================
+struct RollBwdSrc {
+    int plane, g, row_varying;   // plane p whose conv consumed the vector; channel group 1 | 2; vector indexed by p's row or column
+    int L, across_len;           // vector length; number of lines across (cols if row_varying else rows)
+    int sy_off;                  // segment (positions) of dY's axis sums: rs (row_varying) or cs of plane p
+    int vec_off;                 // segment of the forward axis sums of the SOURCE plane (raw fixed point, k_gn_silu)
+    float vec_scale;             // 2^-24 / averaged length: fixed-point sum -> mean
+    float inv_navg;              // 1 / averaged length
+    float* T;                    // dgrad addend of the source plane [B][4][L][C]
+    const float* w;              // W of plane p [Cout][3C][3][3]
+    float* dw;                   // gradient of the same tensor (+=)
+};
+struct RollBwdArgs {
+    RollBwdSrc s[6];
+    TriCF dy;                    // fp32 dY [B][rows][cols][Cout] (first / last lines)
+    TriDims d;
+    const double* sy;            // [B][total_len][Cout]
+    const unsigned long long* fsums;   // forward axis sums [B][total_len][C]
+    int total_len, C, Cout, B;
+};
+// line `which` (0 first, 1 last) across of dY at position pos, channel co
+__device__ __forceinline__ float roll_edge(const RollBwdArgs& A, const RollBwdSrc& S, int b, int pos, int co, int which) {
+    const int rows = A.d.rows[S.plane], cols = A.d.cols[S.plane];
+    const float* p = A.dy.p[S.plane] + static_cast<size_t>(b) * rows * cols * A.Cout;
+    const int line = which ? S.across_len - 1 : 0;
+    const int r = S.row_varying ? pos : line, c = S.row_varying ? line : pos;
+    return __ldg(p + (static_cast<size_t>(r) * cols + c) * A.Cout + co);
+}
+// grid (ceil(L/16), 6, B), block 256: dvec for 16 positions of one source
+__global__ void __launch_bounds__(256) k_roll_bwd_vec(RollBwdArgs A) {
+    extern __shared__ float sm[];      // sy3[3][18][Cout]
+    const RollBwdSrc S = A.s[blockIdx.y];
+    const int b = blockIdx.z, p0 = blockIdx.x * 16, Cout = A.Cout, C = A.C;
+    if (p0 >= S.L) return;
+    const double* sy = A.sy + (static_cast<size_t>(b) * A.total_len + S.sy_off) * Cout;
+    for (int i = threadIdx.x; i < 18 * Cout; i += blockDim.x) {
+        const int j = i / Cout, co = i - j * Cout, pos = p0 + j - 1;
+        float full = 0.f, first = 0.f, last = 0.f;
+        if (pos >= 0 && pos < S.L) {
+            full = static_cast<float>(sy[static_cast<size_t>(pos) * Cout + co]);
+            first = roll_edge(A, S, b, pos, co, 0);
+            last = roll_edge(A, S, b, pos, co, 1);
+        }
+        sm[(0 * 18 + j) * Cout + co] = full - first;
+        sm[(1 * 18 + j) * Cout + co] = full;
+        sm[(2 * 18 + j) * Cout + co] = full - last;
+    }
+    __syncthreads();
+    const int Cw = 3 * C;
+    for (int i = threadIdx.x; i < 16 * C; i += blockDim.x) {
+        const int jl = i / C, c = i - jl * C, j = p0 + jl;
+        if (j >= S.L) continue;
+        float acc = 0.f;
+        for (int co = 0; co < Cout; ++co) {
+            const float* wp = S.w + (static_cast<size_t>(co) * Cw + S.g * C + c) * 9;
+#pragma unroll
+            for (int al = 0; al < 3; ++al)
+#pragma unroll
+                for (int ac = 0; ac < 3; ++ac) {
+                    const float wv = __ldg(wp + (S.row_varying ? al * 3 + ac : ac * 3 + al));
+                    acc = fmaf(sm[(ac * 18 + (jl + 1 - al + 1)) * Cout + co], wv, acc);      // position j - al + 1 -> slot jl + 2 - al
+                }
+        }
+        acc *= S.inv_navg;
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls) S.T[((static_cast<size_t>(b) * 4 + cls) * S.L + j) * C + c] = acc;
+    }
+}
+// grid (ceil(Cout*C / 256), 6): dW of the broadcast channels, one thread per (co, c): 9 taps, loop over (b, pos)
+__global__ void __launch_bounds__(256) k_roll_bwd_w(RollBwdArgs A) {
+    const RollBwdSrc S = A.s[blockIdx.y];
+    const int Cout = A.Cout, C = A.C;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout * C) return;
+    const int co = i / C, c = i - co * C;
+    float acc[3][3] = {};      // [along][across]
+    for (int b = 0; b < A.B; ++b) {
+        const double* sy = A.sy + (static_cast<size_t>(b) * A.total_len + S.sy_off) * Cout;
+        const unsigned long long* fv = A.fsums + (static_cast<size_t>(b) * A.total_len + S.vec_off) * C;
+        for (int pos = 0; pos < S.L; ++pos) {
+            const float full = static_cast<float>(sy[static_cast<size_t>(pos) * Cout + co]);
+            const float s3[3] = {full - roll_edge(A, S, b, pos, co, 0), full, full - roll_edge(A, S, b, pos, co, 1)};
+#pragma unroll
+            for (int al = 0; al < 3; ++al) {
+                const int q = pos + al - 1;
+                if (q < 0 || q >= S.L) continue;
+                const float v = __ll2float_rn(static_cast<long long>(__ldg(fv + static_cast<size_t>(q) * C + c))) * S.vec_scale;
+#pragma unroll
+                for (int ac = 0; ac < 3; ++ac) acc[al][ac] = fmaf(s3[ac], v, acc[al][ac]);
+            }
+        }
+    }
+    float* dp = S.dw + (static_cast<size_t>(co) * 3 * C + S.g * C + c) * 9;
+#pragma unroll
+    for (int al = 0; al < 3; ++al)
+#pragma unroll
+        for (int ac = 0; ac < 3; ++ac) dp[S.row_varying ? al * 3 + ac : ac * 3 + al] += acc[al][ac];
+}
+
+// =====================================================================================
+// Weight gradient of the 3x3 conv's own channels (and of the 1x1 skip conv), CUDA-core version (cross-check / bring-up):
+//   dW[co][c][kh][kw] += sum_{b, px} dY[b][px][co] A[b][px + (kh-1, kw-1)][c]       (zero outside the plane)
+// operands are the (hi, lo) pairs the tensor-core path uses, joined to fp32.  One CTA = a 32 x 32 (co, c) tile of one tap over a
+// chunk of pixels; fp32 atomics at the end.  grid (chunks, ceil(Cout/32) * ceil(C/32) * ntap, 3), block (32, 8).
+// =====================================================================================
+struct WgradArgs {
+    TriCH dy;          // [2][B][rows][cols][Cout]
+    TriCH a;           // [2][B][rows][cols][C]
+    TriDims d;
+    int C, Cout, B, ntap;      // ntap 9 (3x3, pad 1) or 1 (1x1)
+    int Cw;                    // in-channels of the stored weight (3C / C for the 3x3, Cs for the 1x1)
+    float* dw[3];              // [Cout][Cw][ntap]
+    int chunks;
+};
+__global__ void __launch_bounds__(256) k_wgrad_ffma(WgradArgs A) {
+    __shared__ float sy[32][33], sa[32][33];      // [pixel][co] / [pixel][c]
+    const int plane = blockIdx.z, C = A.C, Cout = A.Cout;
+    const int rows = A.d.rows[plane], cols = A.d.cols[plane], npx = rows * cols;
+    const int nco = (Cout + 31) / 32, nc = (C + 31) / 32;
+    int t = blockIdx.y;
+    const int tap = t % A.ntap;
+    t /= A.ntap;
+    const int c0 = (t % nc) * 32, co0 = (t / nc) * 32;
+    const int dh = A.ntap == 9 ? tap / 3 - 1 : 0, dw_ = A.ntap == 9 ? tap % 3 - 1 : 0;
+    const long long total = static_cast<long long>(A.B) * npx;
+    const long long per = (total + A.chunks - 1) / A.chunks;
+    const long long q0 = blockIdx.x * per, q1 = min(total, q0 + per);
+    const int tx = threadIdx.x, ty = threadIdx.y;      // outputs: co = co0 + ty*4 + {0..3}, c = c0 + tx
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const size_t lo_y = static_cast<size_t>(A.B) * npx * Cout, lo_a = static_cast<size_t>(A.B) * npx * C;
+    for (long long base = q0; base < q1; base += 32) {
+        // stage 32 pixels: dY[px][co0..+31], A[px + tap][c0..+31]
+        for (int i = ty; i < 32; i += 8) {
+            const long long q = base + i;
+            float vy = 0.f, va = 0.f;
+            if (q < q1) {
+                const int b = static_cast<int>(q / npx), px = static_cast<int>(q - static_cast<long long>(b) * npx);
+                const int r = px / cols, c = px - r * cols;
+                if (co0 + tx < Cout) {
+                    const size_t e = (static_cast<size_t>(b) * npx + px) * Cout + co0 + tx;
+                    vy = __half2float(A.dy.p[plane][e]) + __half2float(A.dy.p[plane][lo_y + e]) * (1.f / kLoScale);
+                }
+                const int rr = r + dh, cc = c + dw_;
+                if (rr >= 0 && rr < rows && cc >= 0 && cc < cols && c0 + tx < C) {
+                    const size_t e = (static_cast<size_t>(b) * npx + static_cast<size_t>(rr) * cols + cc) * C + c0 + tx;
+                    va = __half2float(A.a.p[plane][e]) + __half2float(A.a.p[plane][lo_a + e]) * (1.f / kLoScale);
+                }
+            }
+            sy[i][tx] = vy;
+            sa[i][tx] = va;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const float av = sa[i][tx];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = fmaf(sy[i][ty * 4 + k], av, acc[k]);
+        }
+        __syncthreads();
+    }
+    if (c0 + tx < C)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int co = co0 + ty * 4 + k;
+            if (co < Cout) atomicAdd(A.dw[plane] + (static_cast<size_t>(co) * A.Cw + c0 + tx) * A.ntap + tap, acc[k]);
+        }
+}
+
+// =====================================================================================
+// Boundary 1x1 convs.
+//   head  (unet_triplane.py:441-445): out[co][px] = b[co] + sum_c w[co][c] y[px][c],  y = silu(GN(h))
+//     k_head_bwd: dy[px][c] = S * sum_co g[co][px] w[co][c] (fp32 NHWC, then the generic GroupNorm backward), and
+//                 dw[co][c] += S * sum_px g y,  db[co] += S * sum_px g             (g = dL/dout in the composed layout)
+//   in_conv (:378): h0[px][co] = b[co] + sum_c w[co][c] x[c][px]
+//     k_inconv_wgrad: dw[co][c] += sum_px dh0[px][co] x[c][px],  db[co] += sum_px dh0[px][co]
+// grid (slots, 3, B), block 256; one warp per pixel at a time (lane = channel pair / quad)
+// =====================================================================================
+struct HeadBwdArgs {
+    const float* g;            // composed [B][Cf][H+D][W+D]
+    const unsigned int* amax;
+    TriCF h;                   // [B][rows][cols][C0]
+    TriDims d;
+    int C0, Cf, H, W, Dd, B;
+    const unsigned long long* acc;
+    TriCF gamma, beta;
+    TriCF w_out;               // [Cf][C0]
+    TriF dy;                   // out [B][rows][cols][C0]
+    float* dw[3];              // [Cf][C0] (+=)
+    float* db[3];              // [Cf] (+=)
+    int nslots;
+};
+__global__ void __launch_bounds__(256) k_head_bwd(HeadBwdArgs A) {
+    extern __shared__ float sm[];      // ca[C0] cb[C0] w[Cf][C0] dwacc[Cf][C0] dbacc[Cf] gbuf[8 warps][Cf]
+    __shared__ float mean[kGroups], rstd[kGroups];
+    const int plane = blockIdx.y, b = blockIdx.z, C0 = A.C0, Cf = A.Cf, cpg = C0 / kGroups;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rows = A.d.rows[plane], cols = A.d.cols[plane], npx = rows * cols;
+    float *ca = sm, *cb = sm + C0, *w = sm + 2 * C0, *dwacc = w + Cf * C0, *dbacc = dwacc + Cf * C0, *gbuf = dbacc + Cf;
+    gn_mean_rstd(A.acc, b, plane, static_cast<double>(npx) * cpg, tid, mean, rstd);
+    __syncthreads();
+    for (int c = tid; c < C0; c += 256) {
+        const int g = c / cpg;
+        const float ga = __ldg(A.gamma.p[plane] + c) * rstd[g];
+        ca[c] = ga;
+        cb[c] = __ldg(A.beta.p[plane] + c) - mean[g] * ga;
+    }
+    for (int i = tid; i < Cf * C0; i += 256) {
+        w[i] = __ldg(A.w_out.p[plane] + i);
+        dwacc[i] = 0.f;
+    }
+    for (int i = tid; i < Cf; i += 256) dbacc[i] = 0.f;
+    __syncthreads();
+    const float S = loss_scale(A.amax);
+    const int Hc = A.H + A.Dd, Wc = A.W + A.Dd;
+    const long long hw = static_cast<long long>(Hc) * Wc;
+    const int ppc = (npx + A.nslots - 1) / A.nslots;
+    const int p0 = blockIdx.x * ppc, p1 = min(npx, p0 + ppc);
+    const float* hp = A.h.p[plane] + static_cast<size_t>(b) * npx * C0;
+    float* dyp = A.dy.p[plane] + static_cast<size_t>(b) * npx * C0;
+    float* gw = gbuf + warp * Cf;
+    // lane owns channels lane, lane + 32, ... (at most 4: C0 <= 128): its dw partials for all Cf outputs stay in registers
+    float dwr[4][kMaxCf] = {};
+    float dbr = 0.f;
+    for (int px = p0 + warp; px < p1; px += 8) {
+        const int r = px / cols, c = px - r * cols;
+        const long long off = composed_offset(plane, r, c, A.H, A.W, Wc);
+        if (lane < Cf) gw[lane] = S * __ldg(A.g + (static_cast<size_t>(b) * Cf + lane) * hw + off);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ch = lane + 32 * q;
+            if (ch < C0) {
+                const float y = silu_f(fmaf(__ldg(hp + static_cast<size_t>(px) * C0 + ch), ca[ch], cb[ch]));
+                float dy = 0.f;
+#pragma unroll
+                for (int co = 0; co < kMaxCf; ++co)
+                    if (co < Cf) {
+                        const float gv = gw[co];
+                        dy = fmaf(gv, w[co * C0 + ch], dy);
+                        dwr[q][co] = fmaf(gv, y, dwr[q][co]);
+                    }
+                dyp[static_cast<size_t>(px) * C0 + ch] = dy;
+            }
+        }
+        if (lane < Cf) dbr += gw[lane];
+        __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ch = lane + 32 * q;
+        if (ch < C0)
+#pragma unroll
+            for (int co = 0; co < kMaxCf; ++co)
+                if (co < Cf) atomicAdd(&dwacc[co * C0 + ch], dwr[q][co]);
+    }
+    if (lane < Cf) atomicAdd(&dbacc[lane], dbr);
+    __syncthreads();
+    for (int i = tid; i < Cf * C0; i += 256) atomicAdd(A.dw[plane] + i, dwacc[i]);
+    for (int i = tid; i < Cf; i += 256) atomicAdd(A.db[plane] + i, dbacc[i]);
+}
+
+struct InconvBwdArgs {
+    const float* x;            // composed input [B][Cf][H+D][W+D]
+    TriCF dh0;                 // [B][rows][cols][C0]
+    TriDims d;
+    int C0, Cf, H, W, Dd, B;
+    float* dw[3];              // [C0][Cf] (+=)
+    float* db[3];              // [C0] (+=)
+    int nslots;
+};
+__global__ void __launch_bounds__(256) k_inconv_wgrad(InconvBwdArgs A) {
+    extern __shared__ float sm[];      // dwacc[C0][Cf] dbacc[C0] xbuf[8][Cf]
+    const int plane = blockIdx.y, b = blockIdx.z, C0 = A.C0, Cf = A.Cf;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rows = A.d.rows[plane], cols = A.d.cols[plane], npx = rows * cols;
+    float *dwacc = sm, *dbacc = sm + C0 * Cf, *xbuf = dbacc + C0;
+    for (int i = tid; i < C0 * Cf + C0; i += 256) sm[i] = 0.f;
+    __syncthreads();
+    const int Hc = A.H + A.Dd, Wc = A.W + A.Dd;
+    const long long hw = static_cast<long long>(Hc) * Wc;
+    const int ppc = (npx + A.nslots - 1) / A.nslots;
+    const int p0 = blockIdx.x * ppc, p1 = min(npx, p0 + ppc);
+    const float* dp = A.dh0.p[plane] + static_cast<size_t>(b) * npx * C0;
+    float* xw = xbuf + warp * Cf;
+    float dwr[4][kMaxCf] = {};     // lane owns output channels lane, lane + 32, ... (C0 <= 128)
+    float dbr[4] = {};
+    for (int px = p0 + warp; px < p1; px += 8) {
+        const int r = px / cols, c = px - r * cols;
+        const long long off = composed_offset(plane, r, c, A.H, A.W, Wc);
+        if (lane < Cf) xw[lane] = __ldg(A.x + (static_cast<size_t>(b) * Cf + lane) * hw + off);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int co = lane + 32 * q;
+            if (co < C0) {
+                const float dv = __ldg(dp + static_cast<size_t>(px) * C0 + co);
+#pragma unroll
+                for (int ch = 0; ch < kMaxCf; ++ch)
+                    if (ch < Cf) dwr[q][ch] = fmaf(dv, xw[ch], dwr[q][ch]);
+                dbr[q] += dv;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int co = lane + 32 * q;
+        if (co < C0) {
+#pragma unroll
+            for (int ch = 0; ch < kMaxCf; ++ch)
+                if (ch < Cf) atomicAdd(&dwacc[co * Cf + ch], dwr[q][ch]);
+            atomicAdd(&dbacc[co], dbr[q]);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < C0 * Cf; i += 256) atomicAdd(A.dw[plane] + i, dwacc[i]);
+    for (int i = tid; i < C0; i += 256) atomicAdd(A.db[plane] + i, dbacc[i]);
+}
+
+// =====================================================================================
+// Resampling adjoints (oracle/backward_ref.py::avgpool2_backward, bilinear_resize_backward).
+// k_upcat_bwd: the concat input of a decoder block was cat[resize(up2(low)) (Cu), skip (Cs)].  Given its gradient dcat
+//   [B][rows][cols][Cu+Cs]: scatters the first Cu channels back through the SAME bilinear weights the forward used (fp32 atomics
+//   into dlow, zeroed before) and writes the skip part (+ the 2x2-average-pool adjoint of `dpool`, when the skip tensor was also
+//   pooled into the next level) as dskip.  grid (slots, 3, B), block (Ct/4, NY)
+// =====================================================================================
+struct UpcatBwdArgs {
+    TriCF dcat;
+    TriDims dout, dlow;
+    int Cu, Cs, B, do_up;
+    TriF dlow_g;               // [B][lrows][lcols][Cu] (+=, atomics)
+    TriF dskip;                // [B][rows][cols][Cs]
+    TriCF dpool;               // gradient of the pooled copy of the skip tensor [B][rows/2][cols/2][Cs], or nullptr
+    int nslots;
+};
+__global__ void __launch_bounds__(256) k_upcat_bwd(UpcatBwdArgs A) {
+    const int plane = blockIdx.y, b = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
+    const int orows = A.dout.rows[plane], ocols = A.dout.cols[plane], lrows = A.dlow.rows[plane], lcols = A.dlow.cols[plane];
+    const int Ct = A.Cu + A.Cs, u4 = A.Cu / 4;
+    const int npx = orows * ocols;
+    const int ppc = (npx + A.nslots - 1) / A.nslots;
+    const int p0 = blockIdx.x * ppc, p1 = min(npx, p0 + ppc);
+    const float* gp = A.dcat.p[plane] + static_cast<size_t>(b) * npx * Ct;
+    float* lp = A.dlow_g.p[plane] + static_cast<size_t>(b) * lrows * lcols * A.Cu;
+    const int urows = A.do_up ? 2 * lrows : lrows, ucols = A.do_up ? 2 * lcols : lcols;
+    const bool resize = urows != orows || ucols != ocols;
+    auto scatter_low = [&](int rr, int cc, float wgt, const float4& v) {       // (rr, cc) on the low-resolution grid
+        float* p = lp + (static_cast<size_t>(rr) * lcols + cc) * A.Cu + tx * 4;
+        atomicAdd(p, wgt * v.x); atomicAdd(p + 1, wgt * v.y); atomicAdd(p + 2, wgt * v.z); atomicAdd(p + 3, wgt * v.w);
+    };
+    auto scatter_up = [&](int ur, int uc, float wgt, const float4& v) {       // (ur, uc) on the (virtual) x2 grid
+        if (!A.do_up) {
+            scatter_low(ur, uc, wgt, v);
+            return;
+        }
+        int r0, r1, c0, c1;
+        float lr, lc;
+        bilin_src(ur, lrows, 0.5f, r0, r1, lr);
+        bilin_src(uc, lcols, 0.5f, c0, c1, lc);
+        scatter_low(r0, c0, wgt * (1.f - lr) * (1.f - lc), v);
+        scatter_low(r0, c1, wgt * (1.f - lr) * lc, v);
+        scatter_low(r1, c0, wgt * lr * (1.f - lc), v);
+        scatter_low(r1, c1, wgt * lr * lc, v);
+    };
+    for (int px = p0 + ty; px < p1; px += NY) {
+        const int r = px / ocols, c = px - r * ocols;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(gp + static_cast<size_t>(px) * Ct + tx * 4));
+        if (tx < u4) {
+            if (resize) {
+                int r0, r1, c0, c1;
+                float lr, lc;
+                bilin_src(r, urows, static_cast<float>(urows) / static_cast<float>(orows), r0, r1, lr);
+                bilin_src(c, ucols, static_cast<float>(ucols) / static_cast<float>(ocols), c0, c1, lc);
+                scatter_up(r0, c0, (1.f - lr) * (1.f - lc), v);
+                scatter_up(r0, c1, (1.f - lr) * lc, v);
+                scatter_up(r1, c0, lr * (1.f - lc), v);
+                scatter_up(r1, c1, lr * lc, v);
+            } else {
+                scatter_up(r, c, 1.f, v);
+            }
+        } else {
+            float4 o = v;
+            const float* dpp = A.dpool.p[plane];
+            if (dpp) {
+                const int pr = orows >> 1, pc = ocols >> 1;
+                if ((r >> 1) < pr && (c >> 1) < pc) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(dpp + ((static_cast<size_t>(b) * pr + (r >> 1)) * pc + (c >> 1)) * A.Cs) + (tx - u4));
+                    o.x = fmaf(0.25f, q.x, o.x); o.y = fmaf(0.25f, q.y, o.y); o.z = fmaf(0.25f, q.z, o.z); o.w = fmaf(0.25f, q.w, o.w);
+                }
+            }
+            *(reinterpret_cast<float4*>(A.dskip.p[plane] + (static_cast<size_t>(b) * npx + px) * A.Cs) + (tx - u4)) = o;
+        }
+    }
+}
+
+// out = a (+ b) element-wise, fp32 (plain gradient joins).  n4 = elements / 4
+__global__ void __launch_bounds__(256) k_grad_add(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, long long n4) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float4 v = a[i];
+        if (b) {
+            const float4 w = b[i];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        out[i] = v;
+    }
+}
+
+// bias gradients: db[plane][c] = bias_sum[plane][c] (fp64 -> fp32); additive-embedding gradient dfilm[b][off + c] += bc_sum[b][c]
+__global__ void __launch_bounds__(256) k_bias_fin(const double* __restrict__ bias_sum, int C, float* d0, float* d1, float* d2, const double* bc_sum, int B,
+                                                  float* dfilm, int film_dim, int film_off, float* s0, float* s1, float* s2) {
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+        const int plane = i / C, c = i - plane * C;
+        const float v = static_cast<float>(bias_sum[i]);
+        float* d = plane == 0 ? d0 : (plane == 1 ? d1 : d2);
+        d[c] = v;
+        float* s = plane == 0 ? s0 : (plane == 1 ? s1 : s2);      // the skip conv's bias sees the same output gradient
+        if (s) s[c] = v;
+    }
+    if (bc_sum && dfilm)
+        for (int i = threadIdx.x; i < B * C; i += blockDim.x) {
+            const int b = i / C, c = i - b * C;
+            dfilm[static_cast<size_t>(b) * film_dim + film_off + c] += static_cast<float>(bc_sum[i]);
+        }
+}
+
+// Operands of the backward GEMMs, re-packed on the device whenever the weights change.
+//   dgrad of a 3x3 conv (pad 1) = the same 3x3 conv of dY with the taps flipped and the channel roles swapped:
+//     wd[half][c][tap' * Cout + co] = split(W[co][c][2 - kh'][2 - kw'])        (own channels c < C only; Cw = stored in-channels)
+//   dgrad of the 1x1 skip conv:  wsd[half][cs][co] = split(Ws[co][cs])
+__global__ void __launch_bounds__(256) k_pack_dgrad(const float* __restrict__ w, int Cout, int Cw, int C, __half* __restrict__ out) {
+    const int K = 9 * Cout;
+    const long long n = static_cast<long long>(C) * K;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(c) * K);
+        const int tap = k / Cout, co = k - tap * Cout;
+        const int kh = 2 - tap / 3, kw = 2 - tap % 3;
+        __half hi, lo;
+        split_f16(w[(static_cast<size_t>(co) * Cw + c) * 9 + kh * 3 + kw], hi, lo);
+        out[i] = hi;
+        out[n + i] = lo;
+    }
+}
+__global__ void __launch_bounds__(256) k_pack_dgrad_1x1(const float* __restrict__ ws, int Cout, int Cs, __half* __restrict__ out) {
+    const long long n = static_cast<long long>(Cs) * Cout;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int cs = static_cast<int>(i / Cout), co = static_cast<int>(i - static_cast<long long>(cs) * Cout);
+        __half hi, lo;
+        split_f16(ws[static_cast<size_t>(co) * Cs + cs], hi, lo);
+        out[i] = hi;
+        out[n + i] = lo;
+    }
+}
+
+// final pass: every gradient was carried times the loss scale
+__global__ void __launch_bounds__(256) k_unscale(float* __restrict__ p, long long n, const unsigned int* amax) {
+    const float inv = 1.f / loss_scale(amax);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) p[i] *= inv;
+}
+
+}  // namespace s3d

@@ -381,6 +381,7 @@ class GaussianDiffusion:
         a.sample_base = int(sample_base)
         a.use_graph = int(bool(use_graph))
         h = model.handle()
+        _lib.check(_lib.lib().s3d_unet_set_training(h, 0))
         with th.cuda.device(dev):
             _lib.check(_lib.lib().s3d_sample_loop(h, C.byref(a), _lib.current_stream_ptr()))
             out = img.clone()
@@ -526,6 +527,15 @@ class GaussianDiffusion:
         target = {ModelMeanType.START_X: x_start, ModelMeanType.EPSILON: noise}[self.model_mean_type]
         assert model_output.shape == target.shape == x_start.shape
         H, W, D = (int(model_kwargs[k]) for k in ("H", "W", "D"))
+        if model_output.requires_grad:
+            # training: the loss has to stay on the autograd tape (TrainLoop.forward_backward calls loss.backward(),
+            # train_util.py:198-235); the three plane means are tiny element-wise reductions on top of the UNet's output, whose
+            # backward is s3d_unet_backward
+            terms = {}
+            for name, a, b in zip(("xy", "xz", "yz"), decompose_featmaps(target, (H, W, D)), decompose_featmaps(model_output, (H, W, D))):
+                terms[f"mse_{name}"] = ((a - b) ** 2).mean(dim=(1, 2, 3))
+            terms["loss"] = terms["mse_xy"] + terms["mse_xz"] + terms["mse_yz"]
+            return terms
         tgt, outp = target.float().contiguous(), model_output.float().contiguous()
         B, Cc = tgt.shape[0], tgt.shape[1]
         assert tuple(tgt.shape[2:]) == (H + D, W + D)

@@ -59,6 +59,40 @@ class _ResBlockParams(nn.Module):
             self.skip_connection = _TriConvParams(channels, out_channels, 1, 0, is_rollout=False)
 
 
+class _UNetFn(th.autograd.Function):
+    """forward = s3d_unet_forward_film on a training plan, backward = s3d_unet_backward (include/sin3dm_b200.h): gradients of every
+    conv / norm parameter come back in one flat buffer, the gradient of the conditioning rows goes on through the embedding MLP
+    (which torch differentiates: a [B, 256] GEMV chain).  Replaces autograd through TriplaneUNetModelSmall in
+    TrainLoop.forward_backward (reference src/diffusion/train_util.py:198-235)."""
+
+    @staticmethod
+    def forward(ctx, module, x, film, H, W, D, *params):
+        L, h = _lib.lib(), module.handle()
+        _lib.check(L.s3d_unet_set_training(h, 1))
+        B = x.shape[0]
+        out = th.empty(B, module.out_channels, H + D, W + D, device=x.device, dtype=th.float32)
+        film = film.detach().to(th.float32).contiguous()
+        with th.cuda.device(x.device):
+            _lib.check(L.s3d_unet_forward_film(h, C.c_void_p(x.data_ptr()), C.c_void_p(film.data_ptr()), None,
+                                               C.c_void_p(out.data_ptr()), B, H, W, D, _lib.current_stream_ptr()))
+        ctx.module, ctx.keep, ctx.n_params = module, (x, film), len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        module = ctx.module
+        L, h = _lib.lib(), module._handle
+        x, film = ctx.keep
+        g = grad_out.to(th.float32).contiguous()
+        flat = th.empty(L.s3d_unet_grad_numel(h), device=g.device, dtype=th.float32)
+        dfilm = th.empty_like(film)
+        with th.cuda.device(g.device):
+            _lib.check(L.s3d_unet_backward(h, C.c_void_p(g.data_ptr()), C.c_void_p(flat.data_ptr()), C.c_void_p(dfilm.data_ptr()),
+                                           _lib.current_stream_ptr()))
+        grads = [flat[o:o + n].view(shape) for o, n, shape in module._kernel_param_slots()]
+        return (None, None, dfilm, None, None, None, *grads)
+
+
 class _S3DUNet(nn.Module):
     _rollout = True
 
@@ -159,6 +193,7 @@ class _S3DUNet(nn.Module):
             h = C.c_void_p()
             _lib.check(L.s3d_unet_create(C.byref(cfg), idx, C.byref(h)))
             self._handle, self._handle_key = h, hkey
+            self._slots = None
             # the C side derives the expected checkpoint layout itself: cross-check with our state_dict
             names = []
             for i in range(L.s3d_unet_num_tensors(h)):
@@ -207,15 +242,41 @@ class _S3DUNet(nn.Module):
             self._film_cache[key] = out
         return out
 
+    # ------------------------------------------------------------------ training path
+    def _is_embedding_param(self, name):
+        return name.startswith("time_embed.") or ".emb_layers." in name
+
+    def _kernel_params(self):
+        """(name, parameter) of everything the backward kernels differentiate (all but the embedding MLP), state_dict order."""
+        return [(n, p) for n, p in self.named_parameters() if not self._is_embedding_param(n)]
+
+    def _kernel_param_slots(self):
+        """(offset, numel, shape) inside the flat gradient buffer of s3d_unet_backward, aligned with _kernel_params()."""
+        if getattr(self, "_slots", None) is None:
+            L, h = _lib.lib(), self._handle
+            index = {k: i for i, k in enumerate(self.state_dict().keys())}
+            self._slots = [(L.s3d_unet_grad_offset(h, index[n]), p.numel(), tuple(p.shape)) for n, p in self._kernel_params()]
+        return self._slots
+
+    def _film_rows_torch(self, timesteps):
+        """The conditioning rows [B, film_dim] through the torch-owned embedding MLP (differentiable): sinusoid -> time_embed ->
+        every block's emb_layers, concatenated in block order (nn.py:103-121, unet_triplane.py:232-238, 371-375)."""
+        fr = sinusoid_freqs(self.model_channels).to(timesteps.device)
+        ang = timesteps.float()[:, None] * fr[None]
+        e = th.cat([th.cos(ang), th.sin(ang)], dim=-1)
+        emb = self.time_embed[2](th.nn.functional.silu(self.time_embed[0](e)))
+        se = th.nn.functional.silu(emb)
+        blocks = [m for seq in list(self.input_blocks) + list(self.output_blocks) for m in seq if isinstance(m, _ResBlockParams)]
+        return th.cat([b.emb_layers[1](se) for b in blocks], dim=1)
+
     # ------------------------------------------------------------------ forward
     def forward(self, x, timesteps, H=None, W=None, D=None, y=None):
-        """[N, C, H+D, W+D] -> same shape (unet_triplane.py:465-510).  Inference only."""
+        """[N, C, H+D, W+D] -> same shape (unet_triplane.py:465-510).  With autograd enabled and parameters that require a gradient
+        the call is differentiable w.r.t. the parameters (training); otherwise it is the plain inference forward."""
         assert H is not None and W is not None and D is not None
-        if th.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            if x.requires_grad or self.training:
-                raise NotImplementedError(
-                    "sin3dm_b200 implements the forward (sampling) path only; wrap the call in torch.no_grad() "
-                    "(backward for TrainLoop is SURVEY §8(f) rank 2)")
+        train = th.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if th.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("sin3dm_b200 produces parameter gradients only (no gradient w.r.t. the UNet input)")
         h = self.handle()
         xin = x if y is None else th.cat([x, y], dim=1)
         xin = xin.to(th.float32).contiguous()
@@ -225,6 +286,10 @@ class _S3DUNet(nn.Module):
                              f"(H+D, W+D)=({H + D}, {W + D})")
         if timesteps.shape != (B,):
             raise ValueError("timesteps must have shape [N]")
+        if train:
+            film = self._film_rows_torch(timesteps.to(xin.device))
+            return _UNetFn.apply(self, xin, film, int(H), int(W), int(D), *[p for _, p in self._kernel_params()])
+        _lib.check(_lib.lib().s3d_unet_set_training(h, 0))
         t = timesteps.to(xin.device, th.float32).contiguous()
         out = th.empty(B, self.out_channels, Hc, Wc, device=xin.device, dtype=th.float32)
         with th.cuda.device(xin.device):
