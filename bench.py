@@ -517,6 +517,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and torch-eager baseline legs")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary cfg3 / cfg5 records")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload (cfg4)")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch steady-state times of one step to this file")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

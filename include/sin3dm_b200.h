@@ -226,6 +226,11 @@ int s3d_unet_graph_builds(const s3d_unet* u);
  * x (the forward's input) and the conditioning rows must still be alive.  No gradient w.r.t. x is produced (TrainLoop does not
  * need one).  Gradients are carried multiplied by a device-chosen power-of-two loss scale and un-scaled at the end. */
 int s3d_unet_set_training(s3d_unet* u, int on);
+/* Re-pack every kernel operand from checkpoint tensors that are already on the device: tensors_dev[i] = device pointer of tensor i
+ * (s3d_unet_tensor_info order, n = s3d_unet_num_tensors without the "__freqs" pseudo tensor), fp32, contiguous, reference layout.
+ * The device-side equivalent of s3d_unet_load_tensor x n + s3d_unet_finalize (same packed values), for the optimizer step of a
+ * training loop: no host round trip, no synchronisation.  Needs one host-side load + finalize before (buffer allocation). */
+int s3d_unet_refresh_dev(s3d_unet* u, const float* const* tensors_dev, int n, void* stream);
 int64_t s3d_unet_grad_numel(s3d_unet* u);
 int64_t s3d_unet_grad_offset(s3d_unet* u, int index);
 int s3d_unet_backward(s3d_unet* u, const float* grad_out_dev, float* grads_dev, float* dfilm_dev, void* stream);

@@ -97,6 +97,7 @@ _SIGNATURES = {
     "s3d_sample_loop": (C.c_int, [C.c_void_p, C.POINTER(LoopArgs), C.c_void_p]),
     "s3d_unet_graph_builds": (C.c_int, [C.c_void_p]),
     "s3d_unet_set_training": (C.c_int, [C.c_void_p, C.c_int]),
+    "s3d_unet_refresh_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "s3d_unet_grad_numel": (C.c_int64, [C.c_void_p]),
     "s3d_unet_grad_offset": (C.c_int64, [C.c_void_p, C.c_int]),
     "s3d_unet_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -496,6 +496,85 @@ static void finalize(s3d_unet* u) {
     u->finalized = true;
 }
 
+// Device-side refresh of every packed operand from checkpoint tensors that already live on the device (state_dict order): what a
+// training step calls after the optimizer has changed the weights.  Same values as finalize() produces from host copies; needs
+// the buffers finalize() allocated.  Enqueued on `s`; no host synchronisation.
+static void refresh_from_device(s3d_unet* u, const float* const* src, int n_src, cudaStream_t s) {
+    S3D_CHECK(u->finalized, "s3d_unet_refresh_dev needs one host-side load + s3d_unet_finalize first (it allocates the operand buffers)");
+    std::map<std::string, const float*> by_name;
+    int k = 0;
+    for (const auto& t : u->tensors) {
+        if (t.name == "__freqs") continue;
+        S3D_CHECK(k < n_src && src[k] != nullptr, "s3d_unet_refresh_dev: one device pointer per checkpoint tensor, in state_dict order");
+        by_name[t.name] = src[k++];
+    }
+    S3D_CHECK(k == n_src, "s3d_unet_refresh_dev: tensor count mismatch");
+    auto numel = [&](const std::string& n) { return static_cast<size_t>(u->tensors[u->index.at(n)].numel()); };
+    auto copy = [&](float* dst, const std::string& n) {
+        CUDA_TRY(cudaMemcpyAsync(dst, by_name.at(n), sizeof(float) * numel(n), cudaMemcpyDeviceToDevice, s));
+    };
+    auto grid_for = [](size_t n) { return dim3(static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 1184))); };
+    copy(u->te_w0, "time_embed.0.weight");
+    copy(u->te_b0, "time_embed.0.bias");
+    copy(u->te_w2, "time_embed.2.weight");
+    copy(u->te_b2, "time_embed.2.bias");
+    for (const auto& b : u->blocks) {
+        copy(u->film_w + static_cast<size_t>(b.film_off) * u->emb_dim, b.name + ".emb_layers.1.weight");
+        copy(u->film_b + b.film_off, b.name + ".emb_layers.1.bias");
+    }
+    auto copy_norm = [&](DevNorm& nm, const std::string& name) {
+        for (int p = 0; p < 3; ++p) {
+            copy(nm.gamma[p], name + ".norm_" + kPlane[p] + ".weight");
+            copy(nm.beta[p], name + ".norm_" + kPlane[p] + ".bias");
+        }
+    };
+    for (int p = 0; p < 3; ++p) {
+        copy(u->in_w[p], std::string("in_conv.0.conv_") + kPlane[p] + ".weight");
+        copy(u->in_b[p], std::string("in_conv.0.conv_") + kPlane[p] + ".bias");
+        copy(u->out_w[p], std::string("out.2.conv_") + kPlane[p] + ".weight");
+        copy(u->out_b[p], std::string("out.2.conv_") + kPlane[p] + ".bias");
+    }
+    copy_norm(u->out_norm, "out.0");
+    const bool ro = u->cfg.rollout;
+    auto refresh_conv = [&](DevConv3& d, const std::string& name, const std::string& skip_name) {
+        for (int p = 0; p < 3; ++p) {
+            copy(d.w_orig[p], name + ".conv_" + kPlane[p] + ".weight");
+            const float* sb = nullptr;
+            if (d.Cs) {
+                copy(d.wskip_orig[p], skip_name + ".conv_" + kPlane[p] + ".weight");
+                sb = by_name.at(skip_name + ".conv_" + kPlane[p] + ".bias");
+            }
+            launch_plain(k_vec_add, dim3((d.Cout + 255) / 256), dim3(256), 0, s, by_name.at(name + ".conv_" + kPlane[p] + ".bias"), sb, d.bias[p], d.Cout);
+            LAUNCH_CHECK("k_vec_add");
+            launch_plain(k_pack_conv, grid_for(static_cast<size_t>(d.Cout) * d.Ktot), dim3(256), 0, s, d.w_orig[p], d.wskip_orig[p], d.Cout, d.Cw, d.C,
+                         d.Cs, d.w_pack[p]);
+            LAUNCH_CHECK("k_pack_conv");
+            if (ro)
+                for (int g = 1; g <= 2; ++g) {
+                    launch_plain(k_pack_roll, grid_for(static_cast<size_t>(3) * d.C * 4 * d.Cout), dim3(256), 0, s, d.w_orig[p], d.Cout, d.C, g,
+                                 roll_row_varying(p, g) ? 1 : 0, d.wr[p][g - 1], d.wr16[p][g - 1]);
+                    LAUNCH_CHECK("k_pack_roll");
+                }
+            if (d.wd_pack[p]) {
+                launch_plain(k_pack_dgrad, grid_for(static_cast<size_t>(d.C) * 9 * d.Cout), dim3(256), 0, s, d.w_orig[p], d.Cout, d.Cw, d.C, d.wd_pack[p]);
+                LAUNCH_CHECK("k_pack_dgrad");
+            }
+            if (d.Cs && d.wsd_pack[p]) {
+                launch_plain(k_pack_dgrad_1x1, grid_for(static_cast<size_t>(d.Cs) * d.Cout), dim3(256), 0, s, d.wskip_orig[p], d.Cout, d.Cs, d.wsd_pack[p]);
+                LAUNCH_CHECK("k_pack_dgrad_1x1");
+            }
+        }
+    };
+    for (size_t i = 0; i < u->blocks.size(); ++i) {
+        const auto& b = u->blocks[i];
+        DevBlock& d = u->dblocks[i];
+        copy_norm(d.n1, b.name + ".in_layers.0");
+        copy_norm(d.n2, b.name + ".out_layers.0");
+        refresh_conv(d.c1, b.name + ".in_layers.2", "");
+        refresh_conv(d.c2, b.name + ".out_layers.2", b.name + ".skip_connection");
+    }
+}
+
 // ------------------------------------------------------------------------------------ launch plan
 // GroupNorm statistics attached to a tensor by its producer kernel.  The buffers exist from the start; the consumer
 // arms the box with its norm parameters (attach_norm) before the plan runs, and an un-armed box is skipped at launch.
@@ -1800,6 +1879,14 @@ int s3d_unet_set_training(s3d_unet* u, int on) {
             if (u->finalized) build_dgrad_packs(u);
         }
     }
+    API_END
+}
+
+int s3d_unet_refresh_dev(s3d_unet* u, const float* const* tensors_dev, int n, void* stream) {
+    API_BEGIN
+    S3D_CHECK(u && tensors_dev && n >= 1, "bad argument");
+    CUDA_TRY(cudaSetDevice(u->device));
+    refresh_from_device(u, tensors_dev, n, static_cast<cudaStream_t>(stream));
     API_END
 }
 

@@ -778,6 +778,58 @@ __global__ void __launch_bounds__(256) k_pack_dgrad_1x1(const float* __restrict_
     }
 }
 
+// Forward operands re-packed on the device (same values, bit for bit, as the host packers pack_conv / pack_roll in s3d.cu): a
+// training step changes every weight, and a host round trip per step would cost more than the step.
+//   w_pack[half][co][tap*C + c] (+ [9C + cs] from the 1x1 skip) = split(W[co][c][tap])
+__global__ void __launch_bounds__(256) k_pack_conv(const float* __restrict__ w, const float* __restrict__ wskip, int Cout, int Cw, int C, int Cs,
+                                                   __half* __restrict__ out) {
+    const int Ktot = 9 * C + Cs;
+    const long long n = static_cast<long long>(Cout) * Ktot;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i / Ktot), k = static_cast<int>(i - static_cast<long long>(co) * Ktot);
+        float v;
+        if (k < 9 * C) {
+            const int tap = k / C, c = k - tap * C;
+            v = w[(static_cast<size_t>(co) * Cw + c) * 9 + tap];
+        } else {
+            v = wskip[static_cast<size_t>(co) * Cs + (k - 9 * C)];
+        }
+        __half hi, lo;
+        split_f16(v, hi, lo);
+        out[i] = hi;
+        out[n + i] = lo;
+    }
+}
+//   wc[(along*C + c)][cls*Cout + co] = sum over the taps `across` class cls keeps of W[co][g*C + c][kh][kw]   (fp32, pack_roll)
+//   w16[half][cls*Cout + co][along*C + c] = split(wc)
+__global__ void __launch_bounds__(256) k_pack_roll(const float* __restrict__ w, int Cout, int C, int g, int row_varying, float* __restrict__ wc,
+                                                   __half* __restrict__ w16) {
+    const int K = 3 * C, N = 4 * Cout, Cw = 3 * C;
+    const long long n = static_cast<long long>(K) * N;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i / N), nn = static_cast<int>(i - static_cast<long long>(k) * N);
+        const int along = k / C, c = k - along * C, cls = nn / Cout, co = nn - cls * Cout;
+        float acc = 0.f;
+#pragma unroll
+        for (int across = 0; across < 3; ++across) {
+            const bool keep = cls == 0 || (cls == 1 && across >= 1) || (cls == 2 && across <= 1) || (cls == 3 && across == 1);
+            if (keep) {
+                const int kh = row_varying ? along : across, kw = row_varying ? across : along;
+                acc += w[((static_cast<size_t>(co) * Cw + g * C + c) * 3 + kh) * 3 + kw];
+            }
+        }
+        wc[i] = acc;
+        __half hi, lo;
+        split_f16(acc, hi, lo);
+        w16[static_cast<size_t>(nn) * K + k] = hi;
+        w16[(static_cast<size_t>(N) + nn) * K + k] = lo;
+    }
+}
+__global__ void k_vec_add(const float* a, const float* b, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+
 // final pass: every gradient was carried times the loss scale
 __global__ void __launch_bounds__(256) k_unscale(float* __restrict__ p, long long n, const unsigned int* amax) {
     const float inv = 1.f / loss_scale(amax);

@@ -79,8 +79,14 @@ class FusedAdamWEMA:
         a.beta1, a.beta2, a.eps, a.weight_decay, a.step = self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count
         with torch.cuda.device(self.flat.device):
             _lib.check(_lib.lib().s3d_adamw_ema_step(C.byref(a), _lib.current_stream_ptr()))
-        for p in self.params:                                   # the kernel wrote the storage behind torch's back: bump the version
-            p.add_(0)                                           # counters so that weight caches keyed on them repack (handle())
+        # the kernel wrote the parameter storage behind torch's back: bump the version counters so that weight caches keyed on
+        # them (handle()) re-pack
+        bump = getattr(torch.autograd.graph, "increment_version", None)
+        for p in self.params:
+            if bump is not None:
+                bump(p)
+            else:
+                p.add_(0)
 
     def state_dict(self):
         """step count, moments and EMA copies (the reference saves opt*.pt / ema_*.pt, train_util.py:258-281)."""

@@ -204,6 +204,15 @@ class _S3DUNet(nn.Module):
             if names != mine:
                 raise _lib.S3DError("state_dict layout mismatch between host mirror and C library")
         wkey = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._weights_key != wkey and self._weights_key is not None and not os.environ.get("S3D_HOST_REPACK"):
+            # the weights changed (optimizer step) and the operand buffers exist: re-pack on the device, no host round trip
+            sd = [v.detach() for v in self.state_dict().values()]
+            if all(v.is_cuda and v.dtype == th.float32 and v.is_contiguous() for v in sd):
+                ptrs = (C.c_void_p * len(sd))(*[v.data_ptr() for v in sd])
+                with th.cuda.device(dev):
+                    _lib.check(L.s3d_unet_refresh_dev(self._handle, ptrs, len(sd), _lib.current_stream_ptr()))
+                self._weights_key = wkey
+                self.__dict__.pop("_film_cache", None)
         if self._weights_key != wkey:
             with th.no_grad():
                 for k, v in self.state_dict().items():

@@ -122,3 +122,46 @@ def test_backward_is_repeatable_and_forward_unchanged():
     for k in grads[0]:
         a, b = grads[0][k].double(), grads[1][k].double()
         assert float((a - b).norm()) <= 1e-5 * max(float(a.norm()), 1e-12), k      # fp32 atomics: order may differ, values agree
+
+
+def test_device_refresh_equals_host_repack():
+    """After an in-place weight change the handle re-packs its operands on the device (s3d_unet_refresh_dev); the result must be
+    the forward of a fresh handle that packed the same weights on the host."""
+    case = GRAD_CASES["eps_odd"]
+    spec = ur.UNetSpec(**case["spec"])
+    sd = ur.synthetic_state_dict(spec, case["wseed"])
+    m = make_cuda_model(spec, sd)
+    H, W, D = case["HWD"]
+    x0, _, t = make_grad_inputs(case)
+    x, t = x0.cuda(), t.cuda()
+    with torch.no_grad():
+        m(x, t, H=H, W=W, D=D)                                   # first handle: host path
+        gen = torch.Generator().manual_seed(3)
+        for p in m.parameters():
+            p.add_(0.01 * torch.randn(p.shape, generator=gen).cuda())
+        got = m(x, t, H=H, W=W, D=D)                             # device refresh
+        fresh = make_cuda_model(spec, {k: v.detach().cpu() for k, v in m.state_dict().items()})
+        want = fresh(x, t, H=H, W=W, D=D)
+    assert torch.equal(got, want)
+
+
+def test_fused_optimizer_training_steps_reduce_the_loss():
+    """TrainLoop.run_step in miniature: a few AdamW steps on one fixed batch through the CUDA forward / backward / optimizer."""
+    from sin3dm_b200.optim import FusedAdamWEMA
+    case = GRAD_CASES["startx"]
+    spec = ur.UNetSpec(**case["spec"])
+    m = make_cuda_model(spec, ur.synthetic_state_dict(spec, case["wseed"])).train()
+    opt = FusedAdamWEMA(m.parameters(), lr=2e-3, weight_decay=0.0, ema_rates="0.99")
+    d = create_gaussian_diffusion(steps=1000, predict_xstart=True, timestep_respacing="")
+    H, W, D = case["HWD"]
+    x0, nz, t = make_grad_inputs(case)
+    x0, nz, t = x0.cuda(), nz.cuda(), t.cuda()
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss = d.training_losses(m, x0, t, model_kwargs=dict(H=H, W=W, D=D), noise=nz)["loss"].mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    print("training losses", [round(v, 4) for v in losses])
+    assert losses[-1] < 0.8 * losses[0]

@@ -1,0 +1,124 @@
+"""bench.py --workload cfg4: one diffusion-training iteration of the triplane UNet (BASELINE.json configs[3], the diffusion half of
+train.py: TrainLoop.run_step, reference src/diffusion/train_util.py:163-235) —
+
+    t ~ UniformSampler, x_t = q_sample(x_0, t, noise)            (k_q_sample)
+    out = UNet(x_t, t)                                            (training plan: forward kernels, activations kept)
+    loss = mean_b sum_planes mse(out, x_0)                        (torch reductions on the output, on the autograd tape)
+    loss.backward()                                               (s3d_unet_backward + the embedding MLP through torch)
+    AdamW + EMA                                                   (k_adamw_ema over the flat parameter buffer)
+    operand re-pack for the next forward                          (s3d_unet_refresh_dev, on the device)
+
+`value` = iterations/s with the latent batch resident; `e2e` = the same loop fed from pinned host memory (batch H2D + loss D2H per
+step, as TrainLoop's data iterator does).  roofline = the backward GEMMs (dgrad on tcgen05, wgrad) from per-op CUDA-event times."""
+import ctypes as C
+import json
+import os
+import sys
+
+
+def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
+    torch = bn.torch
+    from sin3dm_b200 import _lib
+    from sin3dm_b200.optim import FusedAdamWEMA
+    from sin3dm_b200.script_util import create_gaussian_diffusion
+    L = _lib.lib()
+    Cc, (H, W, D), B = wl["C"], wl["HWD"], args.batch or wl["B"]
+    model = bn.model(Cc).train()
+    opt = FusedAdamWEMA(model.parameters(), lr=5e-4, weight_decay=0.0, ema_rates="0.9999")
+    diff = create_gaussian_diffusion(predict_xstart=True, timestep_respacing="")
+    g = torch.Generator().manual_seed(bn.rank)
+    latent = (torch.rand(1, Cc, H + D, W + D, generator=g) * 2 - 1)
+    x_host = latent.expand(B, -1, -1, -1).contiguous().pin_memory()        # get_data_iterator repeats the single latent
+    x_dev = x_host.to(bn.dev)
+    kw = dict(H=H, W=W, D=D)
+
+    def step(x0):
+        t = torch.randint(0, diff.num_timesteps, (B,), device=bn.dev)
+        opt.zero_grad()
+        losses = diff.training_losses(model, x0, t, model_kwargs=kw)
+        loss = losses["loss"].mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(n, from_host):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        bn.barrier()
+        e0.record()
+        last = None
+        for _ in range(n):
+            x0 = x_host.to(bn.dev, non_blocking=True) if from_host else x_dev
+            loss = step(x0)
+            if from_host:
+                last = float(loss.detach())          # loss read back every step (TrainLoop logs it)
+        e1.record()
+        bn.barrier()
+        return bn.max_over_ranks(e0.elapsed_time(e1)), last
+
+    for _ in range(max(Wm, 3)):
+        step(x_dev)
+    (ms, per_rank), _ = timed(K, False)
+    (ms2, _), last_loss = timed(max(3, min(K, 10)), True)
+    n2 = max(3, min(K, 10))
+    value = bn.world * K / (ms / 1e3)
+    h = model._handle
+
+    # ---- per-op times: forward list (graph replay with event nodes) and backward list (eager launches with events)
+    rec = {}
+    if bn.rank == 0:
+        peaks = load_peaks()
+        nf, nb = L.s3d_unet_op_count(h), L.s3d_unet_bwd_op_count(h)
+        mf, mb = (C.c_float * nf)(), (C.c_float * nb)()
+        step(x_dev)
+        torch.cuda.synchronize()
+        _lib.check(L.s3d_unet_profile_bwd_ops(h, 5, mb, _lib.current_stream_ptr()))
+        _lib.check(L.s3d_unet_profile_ops(h, 5, mf, _lib.current_stream_ptr()))
+        rows, per_kernel = [], {}
+        for which, n, msv, info in (("fwd", nf, mf, L.s3d_unet_op_info), ("bwd", nb, mb, L.s3d_unet_bwd_op_info)):
+            for i in range(n):
+                nm, fl = C.c_char_p(), C.c_double()
+                _lib.check(info(h, i, C.byref(nm), C.byref(fl)))
+                k = f"{which}:{nm.value.decode()}"
+                rows.append(f"{k:34s} {msv[i] * 1e3:10.1f} us {fl.value / 1e9:10.2f} GFLOP")
+                e = per_kernel.setdefault(k, dict(launches=0, ms=0.0, dense_gflop=0.0))
+                e["launches"] += 1
+                e["ms"] += msv[i]
+                e["dense_gflop"] += fl.value / 1e9
+        if args.dump_ops:
+            with open(args.dump_ops, "w") as f:
+                f.write("\n".join(rows) + f"\nstep in the loop {ms / K * 1e3:.1f} us\n")
+        for e in per_kernel.values():
+            e["ms"] = round(e["ms"], 4)
+            e["dense_gflop"] = round(e["dense_gflop"], 2)
+        roof = {}
+        for key, label in (("bwd:k_conv_tc<dgrad>", "dgrad"), ("bwd:k_wgrad_tc", "wgrad"), ("bwd:k_wgrad_ffma", "wgrad_ffma"),
+                           ("fwd:k_conv_tc", "fprop")):
+            e = per_kernel.get(key)
+            if e and e["ms"] > 0:
+                ach = e["dense_gflop"] / e["ms"]        # GFLOP / ms = TFLOP/s
+                roof[label] = dict(kernel=key, launches=e["launches"], ms=e["ms"], achieved=ach, peak=peaks["tflops"], unit="TFLOP/s",
+                                   frac=ach / peaks["tflops"])
+        rec = dict(kernels=per_kernel, roofline_parts=roof)
+        main = roof.get("wgrad") or roof.get("wgrad_ffma") or roof.get("dgrad")
+        if main:
+            rec["roofline"] = dict(bound="tensor", kernel=main["kernel"], achieved=main["achieved"], peak=main["peak"], unit="TFLOP/s",
+                                   frac=main["frac"], traffic=None, peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
+                                   note="dense algorithmic FLOPs of the op (rollout channels counted for dgrad / fprop as the reference executes "
+                                        "them; own-channel FLOPs for wgrad) / CUDA-event time of its launches in one step")
+    if bn.rank == 0:
+        cfg = config_of(args.workload, dict(wl, B=B), bn.world)
+        fwd_gf = cfg["dense_gflop_per_step"]
+        line = dict(metric="triplane diffusion training iterations/sec (train.py diffusion stage, cfg4)", value=value, unit="iterations/s",
+                    n_gpus=bn.world, steps=K, warmup=Wm, ms_per_step=ms / K, per_rank_ms=[round(v, 3) for v in per_rank],
+                    higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="fp16 hi/lo split operands on tcgen05 (fprop, dgrad), fp32 accumulate / norms / reductions / AdamW",
+                    data="synthetic", config=cfg,
+                    e2e=dict(value=bn.world * n2 / (ms2 / 1e3), unit="iterations/s", h2d_bytes_per_step=x_host.numel() * 4, d2h_bytes_per_step=4,
+                             steps=n2, api="training_losses + loss.backward() + FusedAdamWEMA.step(), batch from pinned host memory, loss read back"),
+                    gpu_launches=K * (L.s3d_unet_op_count(h) + L.s3d_unet_bwd_op_count(h) + 3),
+                    detail=dict(samples_per_s=value * B, fwd_dense_gflop=fwd_gf, train_dense_tflops=3 * fwd_gf * value / bn.world / 1e3,
+                                workspace_mib=round(L.s3d_unet_workspace_bytes(h) / 2 ** 20, 1), last_loss=last_loss),
+                    cpu_baseline=None, **rec)
+        print(json.dumps(line), flush=True)
+    if bn.world > 1:
+        bn.dist.destroy_process_group()
