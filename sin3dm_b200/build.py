@@ -16,7 +16,7 @@ OBJ_DIR = os.path.join(ROOT, "build", "obj")
 HEADER = os.path.join(ROOT, "include", "sin3dm_b200.h")
 UNITS = {
     "s3d.cu": ["s3d.cu", "kernels.cuh", "conv_tc.cuh", "boundary.cuh", "common.cuh", "ptx.cuh", "host_util.cuh", "train_kernels.cuh",
-               "train_host.cuh"],
+               "train_host.cuh", "wgrad_tc.cuh"],
     "dec.cu": ["dec.cu", "dec_kernels.cuh", "common.cuh", "ptx.cuh", "host_util.cuh"],
 }
 

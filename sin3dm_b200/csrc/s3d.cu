@@ -20,6 +20,7 @@
 #include "host_util.cuh"
 #include "kernels.cuh"
 #include "train_kernels.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace s3d;
 
@@ -488,6 +489,7 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<2>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<4>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_gn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kRollSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kRollSmemBytes));
@@ -1501,6 +1503,8 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     if (const char* e = getenv("S3D_PDL")) g_pdl = atoi(e) != 0;
     if (const char* e = getenv("S3D_HALO_BO_KW")) u->halo_bo_kw = atoi(e) != 0;
     if (const char* e = getenv("S3D_FUSE_POOL")) u->fuse_pool = atoi(e) != 0;
+    u->bwd_wgrad_ffma = false;
+    if (const char* e = getenv("S3D_WGRAD")) u->bwd_wgrad_ffma = std::string(e) == "ffma";      // CUDA-core cross-check kernel
     build_structure(u.get());
     *out = u.release();
     API_END

@@ -257,6 +257,10 @@ struct BackwardBuilder {
         P->op_trace.pop_back();
     }
     void wgrad(const Act16& dy, const Act16& a, int level, int C, int Cout, int ntap, int Cw, const std::string& name, double flops) {
+        if (!u->bwd_wgrad_ffma && C % kBK == 0 && Cout % kBK == 0 && Cout <= 128) {
+            wgrad_tc(dy, a, level, C, Cout, ntap, Cw, name, flops);
+            return;
+        }
         WgradArgs A{};
         A.dy = TriCH{{dy.p.p[0], dy.p.p[1], dy.p.p[2]}};
         A.a = TriCH{{a.p.p[0], a.p.p[1], a.p.p[2]}};
@@ -274,6 +278,96 @@ struct BackwardBuilder {
             launch_plain(k_wgrad_ffma, dim3(A.chunks, ny, 3), dim3(32, 8), 0, s, A);
             LAUNCH_CHECK("k_wgrad_ffma");
         });
+    }
+    // tcgen05 version (wgrad_tc.cuh): MN-major operands straight from the NHWC pairs, split-K partials + fixed-order reduction
+    void wgrad_tc(const Act16& dy, const Act16& a, int level, int C, int Cout, int ntap, int Cw, const std::string& name, double flops) {
+        const TriDims d = pb.dims[level];
+        auto maps = std::make_shared<WgradTcMaps>();
+        memset(maps.get(), 0, sizeof(WgradTcMaps));
+        WgradTcArgs A{};
+        A.Cout = Cout;
+        WgReduceArgs R{};
+        const int n_acc = ntap == 9 ? 5 : 1;
+        if (ntap == 9) {
+            // tap pairs: (kh, kw 0|1) for kh = 0..2 (paired tap one pixel to the right), then kw = 2 of kh 0|1 (one row down) and
+            // kw = 2 of kh = 2 with an unused second half
+            const uint32_t off[5] = {0u, 16u * 128u, 32u * 128u, 2u * 128u, (32u + 2u) * 128u};
+            const uint32_t lbo[5] = {128u, 128u, 128u, kHaloW * 128u, kHaloW * 128u};
+            const int taps[5][2] = {{0, 1}, {3, 4}, {6, 7}, {2, 5}, {8, -1}};
+            for (int i = 0; i < 5; ++i) {
+                A.a_off[i] = off[i];
+                A.lbo[i] = lbo[i];
+                R.tap[i][0] = taps[i][0];
+                R.tap[i][1] = taps[i][1];
+            }
+        } else {
+            A.a_off[0] = (16u + 1u) * 128u;       // centre of the halo patch
+            A.lbo[0] = 128u;                      // second half unused
+            R.tap[0][0] = 0;
+            R.tap[0][1] = -1;
+        }
+        const int ngroups = (n_acc * Cout + 511) / 512;
+        const int per_group = (n_acc + ngroups - 1) / ngroups;
+        long long tiles[3];
+        for (int p = 0; p < 3; ++p) {
+            const uint64_t adims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(d.cols[p]), static_cast<uint64_t>(d.rows[p]),
+                                       static_cast<uint64_t>(B), 2};
+            const uint32_t abox[5] = {kBK, kHaloW, kHaloH, 1, 1};
+            make_tmap(&maps->a[p], a.p.p[p], 5, adims, abox);
+            const uint64_t ydims[5] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(d.cols[p]), static_cast<uint64_t>(d.rows[p]),
+                                       static_cast<uint64_t>(B), 2};
+            const uint32_t ybox[5] = {kBK, kTileW, kTileH, 1, 1};
+            make_tmap(&maps->y[p], dy.p.p[p], 5, ydims, ybox);
+            A.tiles_x[p] = (d.cols[p] + kTileW - 1) / kTileW;
+            A.tiles_per_sample[p] = A.tiles_x[p] * ((d.rows[p] + kTileH - 1) / kTileH);
+            tiles[p] = static_cast<long long>(A.tiles_per_sample[p]) * B;
+        }
+        // split-K: about two waves of CTAs with equal MMA work
+        const int cblks = C / kBK;
+        double work_total = 0.0;
+        for (int p = 0; p < 3; ++p) work_total += static_cast<double>(tiles[p]) * cblks * n_acc;
+        const double quantum = work_total / (2.0 * u->num_sms);
+        std::vector<WgUnit> units;
+        std::vector<WgReduceGroup> groups;
+        int max_nacc = 0;
+        for (int p = 0; p < 3; ++p)
+            for (int cb = 0; cb < cblks; ++cb)
+                for (int g = 0; g < ngroups; ++g) {
+                    const int acc0 = g * per_group, nacc = std::min(per_group, n_acc - acc0);
+                    if (nacc <= 0) continue;
+                    max_nacc = std::max(max_nacc, nacc);
+                    long long ns = static_cast<long long>(static_cast<double>(tiles[p]) * nacc / quantum + 0.5);
+                    ns = std::max<long long>(1, std::min<long long>(ns, tiles[p]));
+                    groups.push_back(WgReduceGroup{static_cast<int>(units.size()), static_cast<int>(ns), p, cb, acc0, nacc});
+                    for (long long s = 0; s < ns; ++s)
+                        units.push_back(WgUnit{p, cb, acc0, nacc, static_cast<int>(tiles[p] * s / ns), static_cast<int>(tiles[p] * (s + 1) / ns)});
+                }
+        WgUnit* units_dev = dev_upload(P->allocs, units);
+        WgReduceGroup* groups_dev = dev_upload(P->allocs, groups);
+        const size_t partial_floats = units.size() * kWgMaxAcc * kBM * static_cast<size_t>(Cout);
+        float* partial = static_cast<float*>(pb.barena.alloc(sizeof(float) * partial_floats, P->allocs));
+        A.units = units_dev;
+        A.partial = partial;
+        R.groups = groups_dev;
+        R.partial = partial;
+        R.Cout = Cout;
+        R.Cw = Cw;
+        R.ntap = ntap;
+        R.C = C;
+        grad3(name, "conv", "weight", R.dw);
+        const int n_units = static_cast<int>(units.size()), n_groups = static_cast<int>(groups.size());
+        const size_t smem = 1024 + static_cast<size_t>(kWgStages) * (kWgABytes + (Cout / kBK) * kWgYBytes) + 128;
+        S3D_CHECK(smem <= 227 * 1024, "k_wgrad_tc shared memory");
+        add("k_wgrad_tc", flops, [=](cudaStream_t s) {
+            launch_plain(k_wgrad_tc, dim3(n_units), dim3(kWgThreads), smem, s, *maps, A);
+            LAUNCH_CHECK("k_wgrad_tc");
+        });
+        const int gx = (max_nacc * kBM * Cout + 255) / 256;
+        add("k_wgrad_reduce", 0.0, [=](cudaStream_t s) {
+            launch_plain(k_wgrad_reduce, dim3(gx, n_groups), dim3(256), 0, s, R);
+            LAUNCH_CHECK("k_wgrad_reduce");
+        });
+        pb.barena.release(partial);
     }
 
     // ---- GroupNorm (+FiLM) + SiLU backward of one norm site
