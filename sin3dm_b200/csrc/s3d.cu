@@ -61,6 +61,7 @@ struct DevConv3 {        // one 3x3 TriplaneConv (+ optional fused 1x1 skip)
     // training: operands of the backward GEMMs, re-packed on the device from w_orig / wskip_orig (k_pack_dgrad)
     __half* wd_pack[3] = {};    // dgrad of the 3x3: [2][C][9*Cout], K = tap'*Cout + co, value W[co][c][2-kh'][2-kw']
     __half* wsd_pack[3] = {};   // dgrad of the 1x1 skip: [2][Cs][Cout]
+    float* wrv[3][2] = {};      // rollout adjoint: the broadcast channels' weights as [along*3 + across][Cout][C] (k_pack_rollv)
 };
 struct DevNorm {
     float* gamma[3] = {};
@@ -490,6 +491,7 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<4>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_gn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_roll_bwd_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<3>::kRollSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kRollSmemBytes));
@@ -561,6 +563,12 @@ static void refresh_from_device(s3d_unet* u, const float* const* src, int n_src,
                 launch_plain(k_pack_dgrad, grid_for(static_cast<size_t>(d.C) * 9 * d.Cout), dim3(256), 0, s, d.w_orig[p], d.Cout, d.Cw, d.C, d.wd_pack[p]);
                 LAUNCH_CHECK("k_pack_dgrad");
             }
+            for (int g = 1; g <= 2 && ro; ++g)
+                if (d.wrv[p][g - 1]) {
+                    launch_plain(k_pack_rollv, grid_for(static_cast<size_t>(9) * d.Cout * d.C), dim3(256), 0, s, d.w_orig[p], d.Cout, d.C, g,
+                                 roll_row_varying(p, g) ? 1 : 0, d.wrv[p][g - 1]);
+                    LAUNCH_CHECK("k_pack_rollv");
+                }
             if (d.Cs && d.wsd_pack[p]) {
                 launch_plain(k_pack_dgrad_1x1, grid_for(static_cast<size_t>(d.Cs) * d.Cout), dim3(256), 0, s, d.wskip_orig[p], d.Cout, d.Cs, d.wsd_pack[p]);
                 LAUNCH_CHECK("k_pack_dgrad_1x1");

@@ -16,6 +16,13 @@ static void build_dgrad_packs(s3d_unet* u) {
                 launch_plain(k_pack_dgrad, dim3(static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 1184))), dim3(256), 0, nullptr, cv->w_orig[p],
                              cv->Cout, cv->Cw, cv->C, cv->wd_pack[p]);
                 LAUNCH_CHECK("k_pack_dgrad");
+                for (int g = 1; g <= 2 && u->cfg.rollout; ++g) {
+                    const size_t nv = static_cast<size_t>(9) * cv->Cout * cv->C;
+                    if (!cv->wrv[p][g - 1]) cv->wrv[p][g - 1] = dev_alloc<float>(u->wallocs, nv);
+                    launch_plain(k_pack_rollv, dim3(static_cast<unsigned>(std::min<size_t>((nv + 255) / 256, 1184))), dim3(256), 0, nullptr,
+                                 cv->w_orig[p], cv->Cout, cv->C, g, roll_row_varying(p, g) ? 1 : 0, cv->wrv[p][g - 1]);
+                    LAUNCH_CHECK("k_pack_rollv");
+                }
                 if (cv->Cs) {
                     const size_t ns = static_cast<size_t>(cv->Cs) * cv->Cout;
                     if (!cv->wsd_pack[p]) cv->wsd_pack[p] = dev_alloc<__half>(u->wallocs, 2 * ns);
@@ -179,22 +186,31 @@ struct BackwardBuilder {
                     s.vec_scale = static_cast<float>(1.0 / 16777216.0 / static_cast<double>(avg_len));
                     s.inv_navg = static_cast<float>(1.0 / static_cast<double>(avg_len));
                     s.T = kind == 0 ? T.Trow.p[sp] : T.Tcol.p[sp];
-                    s.w = cv.w_orig[p];
+                    s.wv = cv.wrv[p][g];
                     s.dw = dw[p];
                     S3D_CHECK((kind == 0 ? d.rows[sp] : d.cols[sp]) == s.L, "rollout adjoint geometry");
                     Lmax = std::max(Lmax, s.L);
                 }
             const int Bv = B;
-            const size_t smem = sizeof(float) * 3 * 18 * cv.Cout;
-            add("k_roll_bwd_vec", 0.0, [=](cudaStream_t s) {
-                launch_plain(k_roll_bwd_vec, dim3((Lmax + 15) / 16, 6, Bv), dim3(256), smem, s, R);
+            S3D_CHECK(cv.C % 64 == 0 && cv.Cout % 64 == 0, "rollout adjoint tiling");
+            const size_t smem = sizeof(float) * (3 * (kRvPos + 2) * cv.Cout + 32 * 64);
+            S3D_CHECK(smem <= 200 * 1024, "k_roll_bwd_vec shared memory");
+            const int nct = cv.C / 64;
+            add("k_roll_bwd_vec", 2.0 * B * 6.0 * Lmax * cv.C * 9.0 * cv.Cout, [=](cudaStream_t s) {
+                launch_plain(k_roll_bwd_vec, dim3((Lmax + kRvPos - 1) / kRvPos, 6 * nct, Bv), dim3(256), smem, s, R);
                 LAUNCH_CHECK("k_roll_bwd_vec");
             });
-            const int nwt = (cv.Cout * cv.C + 255) / 256;
-            add("k_roll_bwd_w", 0.0, [=](cudaStream_t s) {
-                launch_plain(k_roll_bwd_w, dim3(nwt, 6), dim3(256), 0, s, R);
+            const int nsplit = std::min(B, 8);
+            const size_t pn = static_cast<size_t>(nsplit) * 18 * 3 * cv.Cout * cv.C;
+            float* partial = static_cast<float*>(pb.barena.alloc(sizeof(float) * pn, P->allocs));
+            const int ntile = (cv.Cout / 64) * nct;
+            add("k_roll_bwd_w", 2.0 * B * 6.0 * Lmax * cv.C * 9.0 * cv.Cout, [=](cudaStream_t s) {
+                launch_plain(k_roll_bwd_w, dim3(ntile, 18, nsplit), dim3(256), 0, s, R, partial, nsplit);
                 LAUNCH_CHECK("k_roll_bwd_w");
+                launch_plain(k_roll_bwd_w_reduce, dim3((3 * cv.Cout * cv.C + 255) / 256, 18), dim3(256), 0, s, R, partial, nsplit);
+                LAUNCH_CHECK("k_roll_bwd_w_reduce");
             });
+            pb.barena.release(partial);
         }
         // dgrad: the forward kernel on flipped / transposed weights; the rollout adjoint rides in its epilogue as Trow / Tcol
         DevConv3 dg{};

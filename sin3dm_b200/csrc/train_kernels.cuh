@@ -333,8 +333,8 @@ struct RollBwdSrc {
     float vec_scale;             // 2^-24 / averaged length: fixed-point sum -> mean
     float inv_navg;              // 1 / averaged length
     float* T;                    // dgrad addend of the source plane [B][4][L][C]
-    const float* w;              // W of plane p [Cout][3C][3][3]
-    float* dw;                   // gradient of the same tensor (+=)
+    const float* wv;             // the group's weights as [along*3 + across][Cout][C] (k_pack_rollv)
+    float* dw;                   // gradient of W of plane p [Cout][3C][3][3] (+=)
 };
 struct RollBwdArgs {
     RollBwdSrc s[6];
@@ -352,75 +352,146 @@ __device__ __forceinline__ float roll_edge(const RollBwdArgs& A, const RollBwdSr
     const int r = S.row_varying ? pos : line, c = S.row_varying ? line : pos;
     return __ldg(p + (static_cast<size_t>(r) * cols + c) * A.Cout + co);
 }
-// grid (ceil(L/16), 6, B), block 256: dvec for 16 positions of one source
-__global__ void __launch_bounds__(256) k_roll_bwd_vec(RollBwdArgs A) {
-    extern __shared__ float sm[];      // sy3[3][18][Cout]
-    const RollBwdSrc S = A.s[blockIdx.y];
-    const int b = blockIdx.z, p0 = blockIdx.x * 16, Cout = A.Cout, C = A.C;
-    if (p0 >= S.L) return;
-    const double* sy = A.sy + (static_cast<size_t>(b) * A.total_len + S.sy_off) * Cout;
-    for (int i = threadIdx.x; i < 18 * Cout; i += blockDim.x) {
-        const int j = i / Cout, co = i - j * Cout, pos = p0 + j - 1;
-        float full = 0.f, first = 0.f, last = 0.f;
-        if (pos >= 0 && pos < S.L) {
-            full = static_cast<float>(sy[static_cast<size_t>(pos) * Cout + co]);
-            first = roll_edge(A, S, b, pos, co, 0);
-            last = roll_edge(A, S, b, pos, co, 1);
-        }
-        sm[(0 * 18 + j) * Cout + co] = full - first;
-        sm[(1 * 18 + j) * Cout + co] = full;
-        sm[(2 * 18 + j) * Cout + co] = full - last;
-    }
-    __syncthreads();
-    const int Cw = 3 * C;
-    for (int i = threadIdx.x; i < 16 * C; i += blockDim.x) {
-        const int jl = i / C, c = i - jl * C, j = p0 + jl;
-        if (j >= S.L) continue;
-        float acc = 0.f;
-        for (int co = 0; co < Cout; ++co) {
-            const float* wp = S.w + (static_cast<size_t>(co) * Cw + S.g * C + c) * 9;
-#pragma unroll
-            for (int al = 0; al < 3; ++al)
-#pragma unroll
-                for (int ac = 0; ac < 3; ++ac) {
-                    const float wv = __ldg(wp + (S.row_varying ? al * 3 + ac : ac * 3 + al));
-                    acc = fmaf(sm[(ac * 18 + (jl + 1 - al + 1)) * Cout + co], wv, acc);      // position j - al + 1 -> slot jl + 2 - al
-                }
-        }
-        acc *= S.inv_navg;
-#pragma unroll
-        for (int cls = 0; cls < 4; ++cls) S.T[((static_cast<size_t>(b) * 4 + cls) * S.L + j) * C + c] = acc;
+// Sy_a[pos][co] for the three taps across, from the full axis sum and the first / last line of dY
+__device__ __forceinline__ void roll_sy3(const RollBwdArgs& A, const RollBwdSrc& S, int b, int pos, int co, float (&out)[3]) {
+    out[0] = out[1] = out[2] = 0.f;
+    if (pos >= 0 && pos < S.L) {
+        const float full = static_cast<float>(A.sy[(static_cast<size_t>(b) * A.total_len + S.sy_off + pos) * A.Cout + co]);
+        out[0] = full - roll_edge(A, S, b, pos, co, 0);
+        out[1] = full;
+        out[2] = full - roll_edge(A, S, b, pos, co, 1);
     }
 }
-// grid (ceil(Cout*C / 256), 6): dW of the broadcast channels, one thread per (co, c): 9 taps, loop over (b, pos)
-__global__ void __launch_bounds__(256) k_roll_bwd_w(RollBwdArgs A) {
-    const RollBwdSrc S = A.s[blockIdx.y];
-    const int Cout = A.Cout, C = A.C;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Cout * C) return;
-    const int co = i / C, c = i - co * C;
-    float acc[3][3] = {};      // [along][across]
-    for (int b = 0; b < A.B; ++b) {
-        const double* sy = A.sy + (static_cast<size_t>(b) * A.total_len + S.sy_off) * Cout;
-        const unsigned long long* fv = A.fsums + (static_cast<size_t>(b) * A.total_len + S.vec_off) * C;
-        for (int pos = 0; pos < S.L; ++pos) {
-            const float full = static_cast<float>(sy[static_cast<size_t>(pos) * Cout + co]);
-            const float s3[3] = {full - roll_edge(A, S, b, pos, co, 0), full, full - roll_edge(A, S, b, pos, co, 1)};
-#pragma unroll
-            for (int al = 0; al < 3; ++al) {
-                const int q = pos + al - 1;
-                if (q < 0 || q >= S.L) continue;
-                const float v = __ll2float_rn(static_cast<long long>(__ldg(fv + static_cast<size_t>(q) * C + c))) * S.vec_scale;
-#pragma unroll
-                for (int ac = 0; ac < 3; ++ac) acc[al][ac] = fmaf(s3[ac], v, acc[al][ac]);
+// dvec for 32 positions x 64 channels of one source and sample: a small tiled fp32 GEMM, K = (along, across, co).
+//   wrv: weights re-packed as [along*3 + across][Cout][C] (k_pack_rollv) so that weight tiles load coalesced
+// grid (ceil(Lmax/32), 6 * (C/64), B), block 256; dynamic smem: sy3[3][34][Cout] + wt[32][64]
+constexpr int kRvPos = 32;
+__global__ void __launch_bounds__(256) k_roll_bwd_vec(RollBwdArgs A) {
+    extern __shared__ float sm[];
+    const int nct = A.C / 64;
+    const RollBwdSrc S = A.s[blockIdx.y / nct];
+    const int c0 = (blockIdx.y % nct) * 64;
+    const int b = blockIdx.z, p0 = blockIdx.x * kRvPos, Cout = A.Cout, C = A.C;
+    if (p0 >= S.L) return;
+    float* sy3 = sm;                                   // [3][kRvPos + 2][Cout], slot j <-> position p0 + j - 1
+    float* wt = sm + 3 * (kRvPos + 2) * Cout;          // [32][64]
+    for (int i = threadIdx.x; i < (kRvPos + 2) * Cout; i += blockDim.x) {
+        const int j = i / Cout, co = i - j * Cout;
+        float v[3];
+        roll_sy3(A, S, b, p0 + j - 1, co, v);
+        sy3[(0 * (kRvPos + 2) + j) * Cout + co] = v[0];
+        sy3[(1 * (kRvPos + 2) + j) * Cout + co] = v[1];
+        sy3[(2 * (kRvPos + 2) + j) * Cout + co] = v[2];
+    }
+    const int cq = threadIdx.x & 15, pp = threadIdx.x >> 4;        // 4 channels x 2 positions per thread
+    float acc[2][4] = {};
+    for (int t = 0; t < 9; ++t) {
+        const int al = t / 3, ac = t - al * 3;
+        const float* s0 = sy3 + (ac * (kRvPos + 2) + (2 * pp + 2 - al)) * Cout;      // position j - al + 1 -> slot jl + 2 - al
+        const float* s1 = s0 + Cout;
+        for (int co0 = 0; co0 < Cout; co0 += 32) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
+                const int k = i >> 4, q = i & 15;
+                *reinterpret_cast<float4*>(wt + k * 64 + q * 4) =
+                    __ldg(reinterpret_cast<const float4*>(S.wv + (static_cast<size_t>(t) * Cout + co0 + k) * C + c0) + q);
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(wt + k * 64 + cq * 4);
+                const float a0 = s0[co0 + k], a1 = s1[co0 + k];
+                acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
+                acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
+                acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]);
+                acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
             }
         }
     }
-    float* dp = S.dw + (static_cast<size_t>(co) * 3 * C + S.g * C + c) * 9;
 #pragma unroll
-    for (int al = 0; al < 3; ++al)
+    for (int r = 0; r < 2; ++r) {
+        const int j = p0 + 2 * pp + r;
+        if (j < S.L) {
+            const float4 o = make_float4(acc[r][0] * S.inv_navg, acc[r][1] * S.inv_navg, acc[r][2] * S.inv_navg, acc[r][3] * S.inv_navg);
 #pragma unroll
-        for (int ac = 0; ac < 3; ++ac) dp[S.row_varying ? al * 3 + ac : ac * 3 + al] += acc[al][ac];
+            for (int cls = 0; cls < 4; ++cls)
+                *reinterpret_cast<float4*>(S.T + ((static_cast<size_t>(b) * 4 + cls) * S.L + j) * C + c0 + cq * 4) = o;
+        }
+    }
+}
+// dW of the broadcast channels: a 64 (co) x 64 (c) tile of one (source, along) for the three taps across, K = (b, pos) over a
+// slice of the batch; partial[split][source*3 + along][across][co][c] is reduced in a fixed order by k_roll_bwd_w_reduce.
+// grid ((Cout/64) * (C/64), 18, nsplit), block 256
+__global__ void __launch_bounds__(256) k_roll_bwd_w(RollBwdArgs A, float* __restrict__ partial, int nsplit) {
+    __shared__ __align__(16) float sy3[3][16][64];
+    __shared__ __align__(16) float vv[16][64];
+    const int Cout = A.Cout, C = A.C, nct = C / 64;
+    const int co0 = (blockIdx.x / nct) * 64, c0 = (blockIdx.x % nct) * 64;
+    const int src = blockIdx.y / 3, al = blockIdx.y - src * 3;
+    const RollBwdSrc S = A.s[src];
+    const int b0 = static_cast<int>(static_cast<long long>(A.B) * blockIdx.z / nsplit), b1 = static_cast<int>(static_cast<long long>(A.B) * (blockIdx.z + 1) / nsplit);
+    const int tc = threadIdx.x & 15, tco = threadIdx.x >> 4;
+    float acc[3][4][4] = {};
+    for (int b = b0; b < b1; ++b) {
+        const unsigned long long* fv = A.fsums + (static_cast<size_t>(b) * A.total_len + S.vec_off) * C;
+        for (int p0 = 0; p0 < S.L; p0 += 16) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+                const int k = i >> 6, x = i & 63;
+                float v[3];
+                roll_sy3(A, S, b, p0 + k, co0 + x, v);
+                sy3[0][k][x] = v[0];
+                sy3[1][k][x] = v[1];
+                sy3[2][k][x] = v[2];
+                const int q = p0 + k + al - 1;
+                vv[k][x] = (p0 + k < S.L && q >= 0 && q < S.L)
+                               ? __ll2float_rn(static_cast<long long>(__ldg(fv + static_cast<size_t>(q) * C + c0 + x))) * S.vec_scale : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const float4 v = *reinterpret_cast<const float4*>(&vv[k][tc * 4]);
+#pragma unroll
+                for (int ac = 0; ac < 3; ++ac) {
+                    const float4 y = *reinterpret_cast<const float4*>(&sy3[ac][k][tco * 4]);
+                    const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[ac][i][0] = fmaf(yy[i], v.x, acc[ac][i][0]); acc[ac][i][1] = fmaf(yy[i], v.y, acc[ac][i][1]);
+                        acc[ac][i][2] = fmaf(yy[i], v.z, acc[ac][i][2]); acc[ac][i][3] = fmaf(yy[i], v.w, acc[ac][i][3]);
+                    }
+                }
+            }
+        }
+    }
+    float* out = partial + (static_cast<size_t>(blockIdx.z) * 18 + blockIdx.y) * 3 * Cout * C;
+#pragma unroll
+    for (int ac = 0; ac < 3; ++ac)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(out + (static_cast<size_t>(ac) * Cout + co0 + tco * 4 + i) * C + c0 + tc * 4) =
+                make_float4(acc[ac][i][0], acc[ac][i][1], acc[ac][i][2], acc[ac][i][3]);
+}
+// grid (ceil(3*Cout*C / 256), 18), block 256
+__global__ void __launch_bounds__(256) k_roll_bwd_w_reduce(RollBwdArgs A, const float* __restrict__ partial, int nsplit) {
+    const int Cout = A.Cout, C = A.C;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * Cout * C) return;
+    const int src = blockIdx.y / 3, al = blockIdx.y - src * 3;
+    const RollBwdSrc S = A.s[src];
+    const int c = i % C, co = (i / C) % Cout, ac = i / (C * Cout);
+    float acc = 0.f;
+    for (int s = 0; s < nsplit; ++s) acc += partial[(static_cast<size_t>(s) * 18 + blockIdx.y) * 3 * Cout * C + i];
+    S.dw[(static_cast<size_t>(co) * 3 * C + S.g * C + c) * 9 + (S.row_varying ? al * 3 + ac : ac * 3 + al)] += acc;
+}
+// wv[(along*3 + across)][co][c] = W[co][g*C + c][kh][kw], (kh, kw) = (along, across) for a row-indexed vector, else (across, along)
+__global__ void __launch_bounds__(256) k_pack_rollv(const float* __restrict__ w, int Cout, int C, int g, int row_varying, float* __restrict__ out) {
+    const long long n = static_cast<long long>(9) * Cout * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C), co = static_cast<int>((i / C) % Cout), t = static_cast<int>(i / (static_cast<long long>(C) * Cout));
+        const int al = t / 3, ac = t - al * 3;
+        out[i] = w[(static_cast<size_t>(co) * 3 * C + g * C + c) * 9 + (row_varying ? al * 3 + ac : ac * 3 + al)];
+    }
 }
 
 // =====================================================================================

@@ -121,7 +121,7 @@ def test_backward_is_repeatable_and_forward_unchanged():
     assert float((outs[0] - ref).norm() / ref.norm()) < 1e-5
     for k in grads[0]:
         a, b = grads[0][k].double(), grads[1][k].double()
-        assert float((a - b).norm()) <= 1e-5 * max(float(a.norm()), 1e-12), k      # fp32 atomics: order may differ, values agree
+        assert float((a - b).norm()) <= 1e-4 * max(float(a.norm()), 1e-12), k      # fp32 / fp64 atomics: the order may differ, the values agree
 
 
 def test_device_refresh_equals_host_repack():
