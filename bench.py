@@ -489,6 +489,15 @@ def run_ours(args, wl):
             except Exception as e:       # baseline leg only: never take the product line down with it
                 lib["tf32_on" if tf32 else "fp32"] = f"failed: {type(e).__name__}: {e}"
         torch.backends.cudnn.allow_tf32 = True
+        try:        # the step after the path: decode_grid of a sampled latent, with its CPU oracle beside it
+            from tools.bench_decoder import run as run_decoder
+            dl = run_decoder(reso=256, iters=3, cpu_baseline=True, device=bn.local)
+            also["decoder_grid256"] = dict(metric=dl["metric"], value=dl["value"], unit=dl["unit"], ms_per_step=dl["ms_per_step"],
+                                           workload=dl["config"]["workload"], e2e=dl["e2e"],
+                                           roofline={k: dl["roofline"][k] for k in ("kernel", "achieved", "peak", "unit", "frac")},
+                                           cpu_baseline=dl.get("cpu_baseline"), parity_vs_oracle_rel_l2=dl.get("parity_vs_oracle_rel_l2"))
+        except Exception as e:
+            also["decoder_grid256"] = f"failed: {type(e).__name__}: {e}"
         sps, done, dt, thr, kind = cpu_steps_per_s(wl, 200, 3, budget_s=20.0)
         cpu = dict(value=sps, unit="steps/s", cores=thr, kind=kind, sample=cpu_sample_text(kind, done, wl, args.workload, 3, thr, dt))
     if bn.rank == 0:

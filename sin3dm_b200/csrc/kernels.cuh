@@ -854,6 +854,7 @@ __global__ void __launch_bounds__(256) k_sched_step(SchedArgs A) {
     }
 }
 
+// float4 path when a sample's element count is a multiple of 4 (every sample then starts 16-byte aligned), scalar otherwise
 __global__ void __launch_bounds__(256) k_q_sample(const float* __restrict__ x0, const float* __restrict__ noise,
                                                   float* __restrict__ out, const float* __restrict__ coef,
                                                   const int* __restrict__ t_idx, long long n) {
@@ -862,8 +863,19 @@ __global__ void __launch_bounds__(256) k_q_sample(const float* __restrict__ x0, 
     const int b = blockIdx.y, t = t_idx[b];
     const float a = coef[static_cast<size_t>(t) * 12 + 10], s = coef[static_cast<size_t>(t) * 12 + 11];
     const size_t base = static_cast<size_t>(b) * n;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x, i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if ((n & 3) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(x0 + base);
+        const float4* z4 = reinterpret_cast<const float4*>(noise + base);
+        float4* o4 = reinterpret_cast<float4*>(out + base);
+        for (long long i = i0; i < (n >> 2); i += stride) {
+            const float4 x = __ldg(x4 + i), z = __ldg(z4 + i);
+            o4[i] = make_float4(__fadd_rn(__fmul_rn(a, x.x), __fmul_rn(s, z.x)), __fadd_rn(__fmul_rn(a, x.y), __fmul_rn(s, z.y)),
+                                __fadd_rn(__fmul_rn(a, x.z), __fmul_rn(s, z.z)), __fadd_rn(__fmul_rn(a, x.w), __fmul_rn(s, z.w)));
+        }
+        return;
+    }
+    for (long long i = i0; i < n; i += stride)
         out[base + i] = __fadd_rn(__fmul_rn(a, x0[base + i]), __fmul_rn(s, noise[base + i]));
 }
 
@@ -887,6 +899,36 @@ struct VbArgs {
 __device__ __forceinline__ float vb_cdf(float v) {       // losses.py:44-49
     return 0.5f * (1.0f + tanhf(0.7978845608028654f * (v + 0.044715f * (v * v * v))));
 }
+__device__ __forceinline__ void vb_one(const VbArgs& A, const float (&cf)[4], int t, float lv1, float lv2, float e12, float einv2, float inv_stdv,
+                                       float xs, float xt, float mo, float nzv, bool has_noise, float& x0_out, double (&acc)[3]) {
+    float x0 = A.mean_type == 0 ? mo : __fsub_rn(__fmul_rn(cf[0], xt), __fmul_rn(cf[1], mo));
+    if (A.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    x0_out = x0;
+    const float true_mean = __fadd_rn(__fmul_rn(cf[2], xs), __fmul_rn(cf[3], xt));
+    const float mean = __fadd_rn(__fmul_rn(cf[2], x0), __fmul_rn(cf[3], xt));
+    float term;
+    if (t != 0) {
+        const float d = true_mean - mean;
+        term = 0.5f * (-1.0f + lv2 - lv1 + e12 + (d * d) * einv2);
+    } else {
+        const float c = xs - mean;
+        const float cdf_plus = vb_cdf(inv_stdv * (c + 1.0f / 255.0f)), cdf_min = vb_cdf(inv_stdv * (c - 1.0f / 255.0f));
+        float lp;
+        if (xs < -0.999f) lp = logf(fmaxf(cdf_plus, 1e-12f));
+        else if (xs > 0.999f) lp = logf(fmaxf(1.0f - cdf_min, 1e-12f));
+        else lp = logf(fmaxf(cdf_plus - cdf_min, 1e-12f));
+        term = -lp;
+    }
+    acc[0] += static_cast<double>(term);
+    const float dx = x0 - xs;
+    acc[1] += static_cast<double>(dx * dx);
+    if (has_noise) {
+        const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(cf[0], xt), x0), cf[1]);
+        const float de = eps - nzv;
+        acc[2] += static_cast<double>(de * de);
+    }
+}
+// Sums are fp64 from the first element on (fixed order above the thread level): 1e-7 parity with the reference's mean_flat.
 __global__ void __launch_bounds__(256) k_vb_terms(VbArgs A) {
     const int b = blockIdx.y, t = A.t_idx[b];
     float cf[4];
@@ -895,35 +937,31 @@ __global__ void __launch_bounds__(256) k_vb_terms(VbArgs A) {
     const float lv1 = __ldg(A.logvar + 2 * t), lv2 = __ldg(A.logvar + 2 * t + 1);
     const float e12 = expf(lv1 - lv2), einv2 = expf(-lv2), inv_stdv = expf(-(0.5f * lv2));
     const size_t base = static_cast<size_t>(b) * A.n;
+    const bool has_noise = A.noise != nullptr;
     double acc[3] = {0.0, 0.0, 0.0};
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < A.n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float xs = A.x_start[base + i], xt = A.x_t[base + i], mo = A.model_out[base + i];
-        float x0 = A.mean_type == 0 ? mo : __fsub_rn(__fmul_rn(cf[0], xt), __fmul_rn(cf[1], mo));
-        if (A.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-        if (A.x0_out) A.x0_out[base + i] = x0;
-        const float true_mean = __fadd_rn(__fmul_rn(cf[2], xs), __fmul_rn(cf[3], xt));
-        const float mean = __fadd_rn(__fmul_rn(cf[2], x0), __fmul_rn(cf[3], xt));
-        float term;
-        if (t != 0) {
-            const float d = true_mean - mean;
-            term = 0.5f * (-1.0f + lv2 - lv1 + e12 + (d * d) * einv2);
-        } else {
-            const float c = xs - mean;
-            const float cdf_plus = vb_cdf(inv_stdv * (c + 1.0f / 255.0f)), cdf_min = vb_cdf(inv_stdv * (c - 1.0f / 255.0f));
-            float lp;
-            if (xs < -0.999f) lp = logf(fmaxf(cdf_plus, 1e-12f));
-            else if (xs > 0.999f) lp = logf(fmaxf(1.0f - cdf_min, 1e-12f));
-            else lp = logf(fmaxf(cdf_plus - cdf_min, 1e-12f));
-            term = -lp;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x, i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if ((A.n & 3) == 0) {
+        const float4* xs4 = reinterpret_cast<const float4*>(A.x_start + base);
+        const float4* xt4 = reinterpret_cast<const float4*>(A.x_t + base);
+        const float4* mo4 = reinterpret_cast<const float4*>(A.model_out + base);
+        const float4* nz4 = has_noise ? reinterpret_cast<const float4*>(A.noise + base) : nullptr;
+        float4* o4 = A.x0_out ? reinterpret_cast<float4*>(A.x0_out + base) : nullptr;
+        for (long long i = i0; i < (A.n >> 2); i += stride) {
+            const float4 xs = __ldg(xs4 + i), xt = __ldg(xt4 + i), mo = __ldg(mo4 + i);
+            const float4 nz = has_noise ? __ldg(nz4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o;
+            vb_one(A, cf, t, lv1, lv2, e12, einv2, inv_stdv, xs.x, xt.x, mo.x, nz.x, has_noise, o.x, acc);
+            vb_one(A, cf, t, lv1, lv2, e12, einv2, inv_stdv, xs.y, xt.y, mo.y, nz.y, has_noise, o.y, acc);
+            vb_one(A, cf, t, lv1, lv2, e12, einv2, inv_stdv, xs.z, xt.z, mo.z, nz.z, has_noise, o.z, acc);
+            vb_one(A, cf, t, lv1, lv2, e12, einv2, inv_stdv, xs.w, xt.w, mo.w, nz.w, has_noise, o.w, acc);
+            if (o4) o4[i] = o;
         }
-        acc[0] += static_cast<double>(term);
-        const float dx = x0 - xs;
-        acc[1] += static_cast<double>(dx * dx);
-        if (A.noise) {
-            const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(cf[0], xt), x0), cf[1]);
-            const float de = eps - A.noise[base + i];
-            acc[2] += static_cast<double>(de * de);
+    } else {
+        for (long long i = i0; i < A.n; i += stride) {
+            float o;
+            vb_one(A, cf, t, lv1, lv2, e12, einv2, inv_stdv, A.x_start[base + i], A.x_t[base + i], A.model_out[base + i],
+                   has_noise ? A.noise[base + i] : 0.f, has_noise, o, acc);
+            if (A.x0_out) A.x0_out[base + i] = o;
         }
     }
     __shared__ double red[3][8];
@@ -969,13 +1007,44 @@ __global__ void __launch_bounds__(256) k_plane_mse(PlaneMseArgs A) {
     const size_t base = static_cast<size_t>(b) * A.n;
     const int Wc = A.W + A.D, hw = (A.H + A.D) * Wc;
     double acc[3] = {0.0, 0.0, 0.0};
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < A.n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int pix = static_cast<int>(i % hw), r = pix / Wc, c = pix - r * Wc;
-        const float d = A.target[base + i] - A.output[base + i];
-        const double d2 = static_cast<double>(d * d);
-        if (r < A.H) acc[c < A.W ? 0 : 1] += d2;
-        else if (c < A.W) acc[2] += d2;
+    float q[3] = {0.f, 0.f, 0.f};                            // partial sums of one quad (fp32), folded into fp64 per quad
+    auto add = [&](int r, int c, float tg, float ou) {       // the plane of composed pixel (r, c); the D x D corner belongs to none
+        const float d = tg - ou, d2 = d * d;
+        if (r < A.H) q[c < A.W ? 0 : 1] += d2;
+        else if (c < A.W) q[2] += d2;
+    };
+    auto fold = [&]() {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            acc[k] += static_cast<double>(q[k]);
+            q[k] = 0.f;
+        }
+    };
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x, i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if ((A.n & 3) == 0) {
+        const float4* t4 = reinterpret_cast<const float4*>(A.target + base);
+        const float4* o4 = reinterpret_cast<const float4*>(A.output + base);
+        for (long long i = i0; i < (A.n >> 2); i += stride) {
+            const float4 tg = __ldg(t4 + i), ou = __ldg(o4 + i);
+            const int pix = static_cast<int>((i << 2) % hw);      // one division per four elements; the quad may run over a row end
+            int r = pix / Wc, c = pix - r * Wc;
+            const float tv[4] = {tg.x, tg.y, tg.z, tg.w}, ov[4] = {ou.x, ou.y, ou.z, ou.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                add(r, c, tv[k], ov[k]);
+                if (++c == Wc) {
+                    c = 0;
+                    if (++r == A.H + A.D) r = 0;                  // next channel
+                }
+            }
+            fold();
+        }
+    } else {
+        for (long long i = i0; i < A.n; i += stride) {
+            const int pix = static_cast<int>(i % hw), r = pix / Wc, c = pix - r * Wc;
+            add(r, c, A.target[base + i], A.output[base + i]);
+            fold();
+        }
     }
     __shared__ double red[3][8];
 #pragma unroll

@@ -1653,13 +1653,14 @@ int s3d_q_sample(const float* x0_dev, const float* noise_dev, float* out_dev, co
                  int64_t n, void* stream) {
     API_BEGIN
     S3D_CHECK(x0_dev && noise_dev && out_dev && coef_dev && t_idx_dev && B >= 1 && n >= 1, "bad argument");
-    int gx = static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 8));
+    int gx = static_cast<int>(std::min<long long>((n / 4 + 255) / 256 + 1, 148LL * 8));
     launch(k_q_sample, dim3(dim3(gx, B)), dim3(256), 0, static_cast<cudaStream_t>(stream), x0_dev, noise_dev, out_dev, coef_dev, t_idx_dev, n);
     LAUNCH_CHECK("k_q_sample");
     API_END
 }
 
-static int vb_grid(int64_t n) { return static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 4)); }
+// one float4 per thread and iteration: enough CTAs to fill the machine at any batch size (the batch is the grid's y dimension)
+static int vb_grid(int64_t n) { return static_cast<int>(std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148LL * 8))); }
 int64_t s3d_vb_workspace_bytes(int B, int64_t n) { return static_cast<int64_t>(B) * vb_grid(n) * 3 * sizeof(double); }
 int s3d_vb_terms(const s3d_vb_args* a, void* stream) {
     API_BEGIN

@@ -324,7 +324,8 @@ class GaussianDiffusion:
 
     def _run_device_loop(self, kind, model, shape, noise, clip_denoised, model_kwargs, device, eta, y0, mask, is_mask_t0,
                          step_noise, seed, sample_base, use_graph=True):
-        mdev = next(model.parameters()).device
+        h = model.handle()
+        mdev = model._fast_params()[0].device
         dev = th.device(device) if device is not None else mdev
         if dev.type == "cuda" and dev.index is None:
             dev = th.device("cuda", th.cuda.current_device())
@@ -353,7 +354,11 @@ class GaussianDiffusion:
             img.copy_(noise.to(dev, th.float32))
         else:
             img.normal_()
-        film = model.film_table(self._model_timesteps(th.arange(T)).float(), cache=True)
+        ts = self.__dict__.get("_loop_ts")          # the network's timesteps of the whole chain + their cache key, per instance
+        if ts is None or ts[0] != T:
+            tsv = self._model_timesteps(th.arange(T)).float()
+            ts = self.__dict__["_loop_ts"] = (T, tsv, tsv.numpy().tobytes())
+        film = model.film_table(ts[1], cache=True, handle=h, cache_key=ts[2])
         coef = self.coef_table(dev, eta)
         a = _lib.LoopArgs()
         a.kind, a.mean_type, a.clip_denoised, a.is_mask_t0 = kind, self._mean_code(), int(bool(clip_denoised)), int(bool(is_mask_t0))
@@ -380,7 +385,6 @@ class GaussianDiffusion:
         a.seed = (self._fresh_seed() if seed is None else int(seed)) & (2 ** 64 - 1)
         a.sample_base = int(sample_base)
         a.use_graph = int(bool(use_graph))
-        h = model.handle()
         _lib.check(_lib.lib().s3d_unet_set_training(h, 0))
         with th.cuda.device(dev):
             _lib.check(_lib.lib().s3d_sample_loop(h, C.byref(a), _lib.current_stream_ptr()))

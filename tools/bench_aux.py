@@ -2,8 +2,8 @@
 """HBM-bound helper kernels against the measured copy bandwidth: fused AdamW+EMA, variational-bound terms, per-plane MSE, q_sample.
 
     python tools/bench_aux.py            # one JSON line per kernel: GB/s = algorithmic bytes / CUDA-event time, frac of MEASURED_PEAKS hbm
-Buffers are sized like the real use (7.1 M parameters; the cfg3 batch-8 latent [8, 12, 230, 266]) and every timed call is preceded
-by a write of a 256 MiB scratch buffer (L2 flush), so the numbers are HBM numbers."""
+AdamW: 7.1 M parameters, every timed call preceded by a write of a 256 MiB scratch buffer (L2 flush).  Latent passes: a batch-32 cfg3
+latent (94 MB per tensor, every call streams more than the L2 holds), called back to back through the C ABI."""
 import ctypes as C
 import json
 import os
@@ -51,27 +51,47 @@ def main():
     opt.grad.normal_()
     report("k_adamw_ema", timed(lambda: opt.step()), opt.n * 4 * 10, "7.1 M parameters, 1 EMA copy")
 
-    # ---- scheduler-side reductions on the cfg3 batch-8 latent
-    shape = (8, 12, 230, 266)
+    # ---- scheduler-side passes on a batch-32 cfg3 latent [32, 12, 230, 266] (94 MB per tensor: every call streams 2-5 tensors, i.e.
+    # more than the 126 MB L2 — no flush needed); the kernels are called through the C ABI back to back, so the time is device time
+    shape = (32, 12, 230, 266)
     H, W, D = 92, 128, 138
     g = torch.Generator(device="cuda").manual_seed(0)
     x0 = torch.rand(shape, device="cuda", generator=g) * 2 - 1
     nz = torch.randn(shape, device="cuda", generator=g)
     mo = torch.randn(shape, device="cuda", generator=g)
-    t = torch.randint(0, 1000, (8,), device="cuda")
+    out = torch.empty_like(x0)
+    t = torch.randint(1, 1000, (shape[0],), device="cuda").to(torch.int32)
     d = create_gaussian_diffusion(predict_xstart=True)
-    nb = x0.numel() * 4
-    xt = d.q_sample(x0, t, nz)
-    report("k_q_sample", timed(lambda: d.q_sample(x0, t, nz)), 3 * nb, "cfg3 latent, B=8: 2 reads + 1 write")
-    model = lambda xx, tt, **k: mo
-    report("k_vb_terms", timed(lambda: d._vb_device(model, x0, xt, t, True, None, noise=nz)), 5 * nb,
-           "cfg3 latent, B=8: x_start, x_t, model_out, noise read, pred_xstart written")
+    coef = d.coef_table(x0.device)
+    d._vb_device(lambda xx, tt, **k: mo[:1], x0[:1], x0[:1], t[:1], True, None)          # builds the log-variance table
+    logvar = d._coef_cache[("logvar", str(x0.device))]
+    nb, n = x0.numel() * 4, x0[0].numel()
     L = _lib.lib()
-    ws = torch.empty(L.s3d_vb_workspace_bytes(8, x0[0].numel()), dtype=torch.uint8, device="cuda")
-    mse = torch.empty(8, 3, device="cuda")
-    report("k_plane_mse", timed(lambda: _lib.check(L.s3d_plane_mse(C.c_void_p(x0.data_ptr()), C.c_void_p(mo.data_ptr()), 8, 12, H, W, D,
-                                                                   C.c_void_p(ws.data_ptr()), C.c_void_p(mse.data_ptr()),
-                                                                   _lib.current_stream_ptr()))), 2 * nb, "cfg3 latent, B=8: 2 reads")
+    st = _lib.current_stream_ptr()
+    P = lambda v: C.c_void_p(v.data_ptr())
+
+    def timed_dev(fn, iters=10):
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    report("k_q_sample", timed_dev(lambda: _lib.check(L.s3d_q_sample(P(x0), P(nz), P(out), P(coef), P(t), shape[0], n, st))), 3 * nb,
+           "cfg3 latent, B=32: 2 reads + 1 write")
+    ws = torch.empty(L.s3d_vb_workspace_bytes(shape[0], n), dtype=torch.uint8, device="cuda")
+    res = torch.empty(shape[0], 3, device="cuda")
+    a = _lib.VbArgs()
+    a.mean_type, a.clip_denoised, a.B, a.n_per_sample = _lib.START_X, 1, shape[0], n
+    a.x_start, a.x_t, a.model_out, a.noise, a.pred_xstart = x0.data_ptr(), nz.data_ptr(), mo.data_ptr(), nz.data_ptr(), out.data_ptr()
+    a.coef_dev, a.logvar_dev, a.t_idx_dev, a.workspace, a.out = coef.data_ptr(), logvar.data_ptr(), t.data_ptr(), ws.data_ptr(), res.data_ptr()
+    report("k_vb_terms", timed_dev(lambda: _lib.check(L.s3d_vb_terms(C.byref(a), st))), 5 * nb,
+           "cfg3 latent, B=32: x_start, x_t, model_out, noise read, pred_xstart written (+ k_vb_finalize)")
+    report("k_plane_mse", timed_dev(lambda: _lib.check(L.s3d_plane_mse(P(x0), P(mo), shape[0], 12, H, W, D, P(ws), P(res), st))), 2 * nb,
+           "cfg3 latent, B=32: 2 reads (+ k_plane_mse_finalize)")
 
 
 if __name__ == "__main__":
