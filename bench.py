@@ -44,6 +44,8 @@ METRIC = "triplane denoising steps/sec (DDPM-1000, DDIM-100) at 1/2/4/8 B200"
 DTYPE = {3: "fp16 hi/lo split operands (3 tcgen05 MMAs, fp32-grade), fp32 accumulate / norm / scheduler",
          2: "fp16 activations x fp16 hi/lo split weights (one N=128 tcgen05 MMA per tile step), fp32 accumulate / norm / scheduler",
          4: "fp16 hi/lo split activations x fp16 weights (2 tcgen05 MMAs), fp32 accumulate / norm / scheduler",
+         5: "fp16 activations x fp16 hi/lo split weights (one N=128 tcgen05 MMA per tile step; rollout terms with the full 3-term split), "
+            "fp32 accumulate / norm / scheduler",
          1: "fp16 operands (1 tcgen05 MMA), fp32 accumulate / norm / scheduler"}
 
 

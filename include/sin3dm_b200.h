@@ -43,7 +43,8 @@ typedef struct {
     int rollout;                   /* 1: TriplaneUNetModelSmall, 0: ...SmallRaw */
     int precision;                 /* conv operand terms (v = hi + lo/2048, fp16 halves): 3: Ah*Bh + Ah*Bl + Al*Bh (fp32-grade);
                                       2: Ah*(Bh + Bl) (exact weights, fp16 activations); 4: (Ah + Al)*Bh (exact activations, fp16
-                                      weights); 1: Ah*Bh.  DESIGN.md §3 has the measured full-chain error of each. */
+                                      weights); 1: Ah*Bh; 5: mode 2 for the conv tiles with mode 3 for the rollout 1-D GEMM tiles.  DESIGN.md §3 has the measured
+                                      full-chain error of each. */
     int conv_impl;                 /* 0: tcgen05 implicit GEMM; 1: CUDA-core debug kernel */
 } s3d_unet_config;
 

@@ -24,11 +24,19 @@
 namespace s3d {
 
 constexpr int kTileH = 16, kTileW = 8;     // conv M tile = 16 rows x 8 cols of one plane (m = h*8 + w)
-constexpr int kHaloH = kTileH + 2, kHaloW = 16;   // halo patch rows / (padded) cols: row pitch 16 px = 2048 B keeps every
-                                                   // 8-pixel row group on the same 128B-swizzle phase
+// Halo patch of one 64-channel block: 18 rows x kHaloW pixels, one 128-byte line per pixel.  The tensor core takes the swizzle phase
+// from the absolute shared-memory address and the distance between the 8-pixel row groups from the descriptor's SBO, so the row
+// pitch needs no power-of-two padding: 10 pixels (tile width + 2) instead of 16 shrinks the patch from 36 to 22.5 KiB, and the
+// shared memory that frees buys a weight ring deep enough to cover the L2 latency of the weight tiles.
+#ifndef S3D_HALO_W
+#define S3D_HALO_W 10
+#endif
+constexpr int kHaloH = kTileH + 2, kHaloW = S3D_HALO_W;
+static_assert(kHaloW >= kTileW + 2, "halo width");
 constexpr int kBM = 128, kBN = 64, kBK = 64;
 constexpr int kABytes = kBM * kBK * 2;             // 16 KiB: plain 128-row A tile (skip / rollout groups)
-constexpr int kAHaloBytes = kHaloH * kHaloW * kBK * 2;   // 36 KiB: halo patch of one 64-channel block
+constexpr int kAHaloBytes = kHaloH * kHaloW * kBK * 2;   // bytes one halo TMA box delivers
+constexpr int kAHaloPad = (kAHaloBytes + 1023) / 1024 * 1024;   // its footprint: the next operand starts 1024-byte aligned
 constexpr int kBBytes = kBN * kBK * 2;             //  8 KiB
 constexpr int kConvThreads = 352;                  // warps: 0 A-producer, 1 MMA, 2..9 epilogue, 10 B-producer
 constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;
@@ -92,19 +100,28 @@ struct FusedRoll {
 //   2: Ah*Bh + Ah*Bl                   one N=128 MMA (lo weight tile behind the hi tile): exact weights, fp16-rounded activations
 //   4: Ah*Bh + Al*Bh                   two MMAs: exact activations, fp16-rounded weights
 //   3: Ah*Bh + Ah*Bl + Al*Bh           fp32-grade (error ~2^-22)
+//   5: mode 2 for the conv tiles, mode 3 for the rollout 1-D GEMM tiles (their A operand is built in shared memory from the fp32
+//      axis means, so its lo half costs no memory traffic: it sits behind the hi patch inside the same A slot)
 template <int MODE>
 struct ConvTcCfg {
     static constexpr bool kAlo = MODE == 3 || MODE == 4;      // the lo halves of the activations are loaded and multiplied
-    static constexpr bool kBlo = MODE == 2 || MODE == 3;      // the lo halves of the weights
+    static constexpr bool kBlo = MODE == 2 || MODE == 3 || MODE == 5;      // the lo halves of the weights
     static constexpr bool kTwo = MODE != 1;                   // a second accumulator D2 (scaled by 1/2048 in the epilogue)
-    static constexpr int kASlotBytes = (kAlo ? 2 : 1) * kAHaloBytes;   // hi at +0, lo at +kAHaloBytes
+    static constexpr bool kRollAlo = kAlo || MODE == 5;       // roll tiles multiply the lo halves of the means
+    static constexpr int kRollLoOff = kAlo ? kAHaloPad : 18 * 1024;   // where a roll tile's lo patch sits inside its A slot
+    static constexpr int kASlotBytes = kAlo ? 2 * kAHaloPad : (MODE == 5 ? 36 * 1024 : kAHaloPad);   // hi at +0, lo at +kAHaloPad
     static constexpr int kBSlotBytes = (kBlo ? 2 : 1) * kBBytes;       // hi at +0, lo at +kBBytes
     static constexpr int kASlots = kAlo ? 2 : 3;
-    static constexpr int kBSlots = MODE == 3 ? 3 : (MODE == 4 ? 6 : (MODE == 2 ? 4 : 8));
+    static constexpr int kEpiBytes = kEpiWarps * 32 * 32 * 4 + 64;   // epilogue staging: [32 rows][32 cols] fp32 per epilogue warp
+    // weight ring: whatever shared memory is left (the barrier block holds 30 mbarriers at most)
+    static constexpr int kBBudget = (227 * 1024 - 1024 - 256 - kEpiBytes - kASlots * kASlotBytes) / kBSlotBytes;
+    static constexpr int kBCap = (30 - 5 - 2 * kASlots) / 2;
+    static constexpr int kBSlots = kBBudget < kBCap ? kBBudget : kBCap;
+    static_assert(kBSlots >= 3, "weight ring too shallow");
+    static_assert(kABytes + (kAlo ? kAHaloPad : 0) <= kASlotBytes && kAHaloPad >= kABytes, "a plain skip tile must fit the A slot");
     static constexpr int kRingBytes = kASlots * kASlotBytes + kBSlots * kBSlotBytes;
     static constexpr int kAccCols = kTwo ? 128 : 64;            // TMEM columns of one accumulator stage
     static constexpr int kTmemCols = 2 * kAccCols;              // double-buffered accumulators
-    static constexpr int kEpiBytes = kEpiWarps * 32 * 32 * 4 + 64;   // epilogue staging: [32 rows][32 cols] fp32 per epilogue warp
     static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
     static_assert(2 * kASlots + 2 * kBSlots + 5 <= 30, "barrier block");
@@ -158,6 +175,8 @@ __device__ __forceinline__ RollTile roll_tile_decode(const FusedRoll& F, int t) 
 
 constexpr int kRollTmMax = 96;           // most positions a roll tile produces (the MMA is M = 128 regardless: rows beyond tm are don't-care)
 constexpr int kRollRows = kRollTmMax + 2;   // most rows of a roll tile's A patch: positions p0-1 .. p0+tm
+static_assert((kRollRows + 32) * 128 <= 18 * 1024 && (kRollRows + 32) * 128 <= kAHaloPad,
+              "a roll tile's hi patch (the M = 128 MMA reads 2 + 128 rows) must end before its lo patch and inside an A slot");
 
 // Persistent implicit-GEMM convolution, one CTA per SM, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
 //
@@ -202,7 +221,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     if (threadIdx.x == 0) trace_mark(A.tr, 0);
     const int cblks = A.C / kBK;
     const int nskip = A.Cs / kBK;
-    constexpr uint32_t kALo = kAHaloBytes, kBLo = kBBytes;
+    constexpr uint32_t kALo = kAHaloPad;
     constexpr uint32_t kAStdTx = (kAlo ? 2 : 1) * kABytes, kAHaloTx = (kAlo ? 2 : 1) * kAHaloBytes;
 
     if (warp == 0 && lane == 0) {
@@ -362,7 +381,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         off = static_cast<uint32_t>(tap) * 128u;     // 1-D tap: rows tap .. tap+127 of the 130-row patch
                     }
                     const uint64_t a_hi = ptx::make_sw128_desc(a_base + off, sbo, 0);
-                    const uint64_t a_lo = ptx::make_sw128_desc(a_base + kALo + off, sbo, 0);
+                    const uint64_t a_lo = ptx::make_sw128_desc(a_base + (roll ? Cfg::kRollLoOff : kALo) + off, sbo, 0);
+                    const bool use_alo = kAlo || (Cfg::kRollAlo && roll);
                     const uint64_t b_hi = ptx::make_sw128_desc(b_base, 1024u, 0);
                     if (ptx::elect_one()) {
 #pragma unroll
@@ -372,7 +392,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                                 // [D1 | D2] (+)= Ah * [Bh | Bl]  (one N=128 MMA: the lo weight tile sits right behind the hi
                                 // tile in shared memory and D2 right behind D1 in TMEM), then D2 += Al * Bh
                                 ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc2, k == 0 ? acc : 1u);
-                                if (kAlo) ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, 1u);
+                                if (use_alo) ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, 1u);
                             } else {
                                 ptx::umma_f16(d1, a_hi + ko, b_hi + ko, idesc, k == 0 ? acc : 1u);
                                 if (kAlo) ptx::umma_f16(d2, a_lo + ko, b_hi + ko, idesc, k == 0 ? acc : 1u);     // D2 (+)= Al * Bh
@@ -423,7 +443,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                         ptx::mbar_wait(&emptyA[s], ((ga / Cfg::kASlots) & 1) ^ 1);
                         if (et == 0 && lt == 0 && cb == 0) trace_mark(A.tr, 16);
                         uint8_t* hi = smem_a + s * Cfg::kASlotBytes;
-                        uint8_t* lo = hi + kALo;
+                        uint8_t* lo = hi + Cfg::kRollLoOff;
 #pragma unroll
                         for (int hb = 0; hb < 1; ++hb) {
                             ulonglong2 raw[kBatch][4];
@@ -447,7 +467,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                                                     __ll2float_rn(static_cast<long long>(raw[i][e].y)) * scale, h[e], l[e]);
                                     const uint32_t off = static_cast<uint32_t>(j) * 128u + (static_cast<uint32_t>(k ^ (j & 7)) << 4);
                                     *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                                    if (kAlo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                                    if (Cfg::kRollAlo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
                                 }
                             }
                         }

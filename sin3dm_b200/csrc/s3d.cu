@@ -154,7 +154,7 @@ struct s3d_unet {
     bool bwd_wgrad_ffma = true;
 };
 
-static bool mode_has_blo(int precision) { return precision == 2 || precision == 3; }
+static bool mode_has_blo(int precision) { return precision == 2 || precision == 3 || precision == 5; }
 static int ch_of(const s3d_unet_config& c, int level) { return c.channel_mult[level] * c.model_channels; }
 
 static void add_tensor(s3d_unet* u, const std::string& name, std::vector<int64_t> shape) {
@@ -489,6 +489,7 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<1>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<2>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<4>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_conv_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTcCfg<5>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(k_gn_silu, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_roll_bwd_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1089,6 +1090,7 @@ struct PlanBuilder {
             if (mode == 3) launch(k_conv_tc<3>, dim3(grid), dim3(kConvThreads), ConvTcCfg<3>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
             else if (mode == 2) launch(k_conv_tc<2>, dim3(grid), dim3(kConvThreads), ConvTcCfg<2>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
             else if (mode == 4) launch(k_conv_tc<4>, dim3(grid), dim3(kConvThreads), ConvTcCfg<4>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
+            else if (mode == 5) launch(k_conv_tc<5>, dim3(grid), dim3(kConvThreads), ConvTcCfg<5>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
             else launch(k_conv_tc<1>, dim3(grid), dim3(kConvThreads), ConvTcCfg<1>::kSmemBytes, s, *maps, *rmaps, Al, F, total_tiles);
             LAUNCH_CHECK("k_conv_tc");
         }, A.tr);
@@ -1496,7 +1498,7 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     S3D_CHECK(cfg->model_channels > 0 && cfg->model_channels % 64 == 0, "model_channels must be a multiple of 64");
     S3D_CHECK(cfg->in_channels >= 1 && cfg->out_channels >= 1 && cfg->out_channels <= 64, "channel counts out of range");
     for (int l = 0; l < cfg->n_levels; ++l) S3D_CHECK(cfg->channel_mult[l] >= 1, "channel_mult must be >= 1");
-    S3D_CHECK(cfg->precision >= 1 && cfg->precision <= 4, "precision must be 1, 2, 3 or 4");
+    S3D_CHECK(cfg->precision >= 1 && cfg->precision <= 5, "precision must be 1 .. 5");
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     S3D_CHECK(device >= 0 && device < ndev, "no such CUDA device");

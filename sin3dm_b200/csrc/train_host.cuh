@@ -307,8 +307,9 @@ struct BackwardBuilder {
         if (ntap == 9) {
             // tap pairs: (kh, kw 0|1) for kh = 0..2 (paired tap one pixel to the right), then kw = 2 of kh 0|1 (one row down) and
             // kw = 2 of kh = 2 with an unused second half
-            const uint32_t off[5] = {0u, 16u * 128u, 32u * 128u, 2u * 128u, (32u + 2u) * 128u};
-            const uint32_t lbo[5] = {128u, 128u, 128u, kHaloW * 128u, kHaloW * 128u};
+            const uint32_t W = kWgHaloW;
+            const uint32_t off[5] = {0u, W * 128u, 2u * W * 128u, 2u * 128u, (2u * W + 2u) * 128u};
+            const uint32_t lbo[5] = {128u, 128u, 128u, W * 128u, W * 128u};
             const int taps[5][2] = {{0, 1}, {3, 4}, {6, 7}, {2, 5}, {8, -1}};
             for (int i = 0; i < 5; ++i) {
                 A.a_off[i] = off[i];
@@ -317,7 +318,7 @@ struct BackwardBuilder {
                 R.tap[i][1] = taps[i][1];
             }
         } else {
-            A.a_off[0] = (16u + 1u) * 128u;       // centre of the halo patch
+            A.a_off[0] = (kWgHaloW + 1u) * 128u;       // centre of the halo patch
             A.lbo[0] = 128u;                      // second half unused
             R.tap[0][0] = 0;
             R.tap[0][1] = -1;
@@ -328,7 +329,7 @@ struct BackwardBuilder {
         for (int p = 0; p < 3; ++p) {
             const uint64_t adims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(d.cols[p]), static_cast<uint64_t>(d.rows[p]),
                                        static_cast<uint64_t>(B), 2};
-            const uint32_t abox[5] = {kBK, kHaloW, kHaloH, 1, 1};
+            const uint32_t abox[5] = {kBK, kWgHaloW, kHaloH, 1, 1};
             make_tmap(&maps->a[p], a.p.p[p], 5, adims, abox);
             const uint64_t ydims[5] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(d.cols[p]), static_cast<uint64_t>(d.rows[p]),
                                        static_cast<uint64_t>(B), 2};

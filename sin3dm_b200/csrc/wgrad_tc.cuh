@@ -31,11 +31,14 @@ namespace s3d {
 constexpr int kWgThreads = 192;                 // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int kWgStages = 3;
 constexpr int kWgMaxAcc = 5;
-constexpr int kWgABytes = kAHaloBytes;          // 36 KiB halo patch (hi half)
+// The wgrad keeps its own halo patch with a 16-pixel row pitch (2048 B between image rows): with the forward's 10-pixel pitch the
+// MN-major reads came out wrong on B200 (measured: 4 % error in dW), while every K-major read of the forward is fine with it.
+constexpr int kWgHaloW = 16;
+constexpr int kWgABytes = kHaloH * kWgHaloW * kBK * 2;          // 36 KiB halo patch (hi half)
 constexpr int kWgYBytes = kBM * kBK * 2;        // 16 KiB: 128 pixels x 64 output channels
 
 struct WgradTcMaps {
-    CUtensorMap a[3];     // activations (C, cols, rows, B, 2) box {64, 16, 18}
+    CUtensorMap a[3];     // activations (C, cols, rows, B, 2) box {64, kWgHaloW, 18}
     CUtensorMap y[3];     // dY          (Cout, cols, rows, B, 2) box {64, 8, 16}
 };
 struct WgUnit {
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
                 for (int i = 0; i < kTileH / 2; ++i) {                    // K step: tile rows 2i, 2i + 1
                     const uint64_t yd = make_mn_sw128_desc(y_base + i * 2048u, kWgYBytes, 1024u);
                     for (int a = 0; a < U.nacc; ++a) {
-                        const uint64_t ad = make_mn_sw128_desc(a_base + A.a_off[U.acc0 + a] + i * (2u * kHaloW * 128u), A.lbo[U.acc0 + a], kHaloW * 128u);
+                        const uint64_t ad = make_mn_sw128_desc(a_base + A.a_off[U.acc0 + a] + i * (2u * kWgHaloW * 128u), A.lbo[U.acc0 + a], kWgHaloW * 128u);
                         ptx::umma_f16(tmem_base + a * A.Cout, ad, yd, idesc, (g > 0 || i > 0) ? 1u : 0u);
                     }
                 }

@@ -21,7 +21,7 @@ def main():
     out = {}
     for name in names:
         fx = np.load(os.path.join(ROOT, "tests", "golden", f"full_{name}.npz"))
-        for mode in (3, 2, 4, 1):
+        for mode in [int(v) for v in os.environ.get('SWEEP_MODES', '3,2,4,1').split(',')]:
             t0 = time.time()
             got = run_full_chain(name, mode)
             rel0, rel_rest = full_errors(got, fx, *FULL_CASES[name]["HWD"])
