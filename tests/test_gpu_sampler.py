@@ -95,5 +95,6 @@ def test_training_losses_forward(golden_dir):
     assert np.array_equal(d.q_sample(x0, t, nz).cpu().numpy(), g["q_sample"])
     with torch.no_grad():
         terms = d.training_losses(m, x0, t, model_kwargs=dict(H=H, W=W, D=D), noise=nz)
+    # the terms are means of (target - output)^2: they inherit twice the UNet output's relative error (~1e-6 with the 3-term split)
     for k in ("mse_xy", "mse_xz", "mse_yz", "loss"):
-        assert np.allclose(terms[k].cpu().numpy(), g[k], rtol=1e-3), k
+        assert np.allclose(terms[k].cpu().numpy(), g[k], rtol=2e-5), k
