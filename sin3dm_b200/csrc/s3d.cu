@@ -152,6 +152,8 @@ struct s3d_unet {
     std::vector<int64_t> grad_off;   // offset of tensor i inside the flat gradient buffer (multiples of 4 floats)
     int64_t grad_numel = 0;
     bool bwd_wgrad_ffma = true;
+    void* pack_jobs_dev = nullptr;       // job table of the last s3d_unet_refresh_dev (k_pack_jobs)
+    std::vector<char> pack_jobs_host;
 };
 
 static bool mode_has_blo(int precision) { return precision == 2 || precision == 3 || precision == 5; }
@@ -446,6 +448,7 @@ static void finalize(s3d_unet* u) {
     CUDA_TRY(cudaSetDevice(u->device));
     destroy_plan(u);
     free_all(u->wallocs);
+    u->pack_jobs_host.clear();           // the cached refresh table points into the buffers just freed
     const auto& c = u->cfg;
     u->te_w0 = dev_upload(u->wallocs, T_(u, "time_embed.0.weight").host);
     u->te_b0 = dev_upload(u->wallocs, T_(u, "time_embed.0.bias").host);
@@ -514,11 +517,17 @@ static void refresh_from_device(s3d_unet* u, const float* const* src, int n_src,
         by_name[t.name] = src[k++];
     }
     S3D_CHECK(k == n_src, "s3d_unet_refresh_dev: tensor count mismatch");
-    auto numel = [&](const std::string& n) { return static_cast<size_t>(u->tensors[u->index.at(n)].numel()); };
-    auto copy = [&](float* dst, const std::string& n) {
-        CUDA_TRY(cudaMemcpyAsync(dst, by_name.at(n), sizeof(float) * numel(n), cudaMemcpyDeviceToDevice, s));
+    auto numel = [&](const std::string& n) { return static_cast<long long>(u->tensors[u->index.at(n)].numel()); };
+    // everything goes into ONE job table (k_pack_jobs): ~140 copies + ~170 re-packs would otherwise be ~300 launches per step
+    std::vector<PackJob> jobs;
+    auto job = [&](int kind, const float* src, const float* src2, void* dst, void* dst2, long long n, int Cout = 0, int Cw = 0, int C = 0,
+                   int Cs = 0, int g = 0, int rowv = 0) {
+        PackJob J{};
+        J.kind = kind; J.src = src; J.src2 = src2; J.dst = dst; J.dst2 = dst2; J.n = n;
+        J.Cout = Cout; J.Cw = Cw; J.C = C; J.Cs = Cs; J.g = g; J.rowv = rowv;
+        jobs.push_back(J);
     };
-    auto grid_for = [](size_t n) { return dim3(static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 1184))); };
+    auto copy = [&](float* dst, const std::string& n) { job(0, by_name.at(n), nullptr, dst, nullptr, numel(n)); };
     copy(u->te_w0, "time_embed.0.weight");
     copy(u->te_b0, "time_embed.0.bias");
     copy(u->te_w2, "time_embed.2.weight");
@@ -543,37 +552,27 @@ static void refresh_from_device(s3d_unet* u, const float* const* src, int n_src,
     const bool ro = u->cfg.rollout;
     auto refresh_conv = [&](DevConv3& d, const std::string& name, const std::string& skip_name) {
         for (int p = 0; p < 3; ++p) {
-            copy(d.w_orig[p], name + ".conv_" + kPlane[p] + ".weight");
+            const float* w = by_name.at(name + ".conv_" + kPlane[p] + ".weight");
+            const float* ws = nullptr;
             const float* sb = nullptr;
+            copy(d.w_orig[p], name + ".conv_" + kPlane[p] + ".weight");
             if (d.Cs) {
+                ws = by_name.at(skip_name + ".conv_" + kPlane[p] + ".weight");
                 copy(d.wskip_orig[p], skip_name + ".conv_" + kPlane[p] + ".weight");
                 sb = by_name.at(skip_name + ".conv_" + kPlane[p] + ".bias");
             }
-            launch_plain(k_vec_add, dim3((d.Cout + 255) / 256), dim3(256), 0, s, by_name.at(name + ".conv_" + kPlane[p] + ".bias"), sb, d.bias[p], d.Cout);
-            LAUNCH_CHECK("k_vec_add");
-            launch_plain(k_pack_conv, grid_for(static_cast<size_t>(d.Cout) * d.Ktot), dim3(256), 0, s, d.w_orig[p], d.wskip_orig[p], d.Cout, d.Cw, d.C,
-                         d.Cs, d.w_pack[p]);
-            LAUNCH_CHECK("k_pack_conv");
+            job(1, by_name.at(name + ".conv_" + kPlane[p] + ".bias"), sb, d.bias[p], nullptr, d.Cout);
+            job(2, w, ws, d.w_pack[p], nullptr, static_cast<long long>(d.Cout) * d.Ktot, d.Cout, d.Cw, d.C, d.Cs);
             if (ro)
-                for (int g = 1; g <= 2; ++g) {
-                    launch_plain(k_pack_roll, grid_for(static_cast<size_t>(3) * d.C * 4 * d.Cout), dim3(256), 0, s, d.w_orig[p], d.Cout, d.C, g,
-                                 roll_row_varying(p, g) ? 1 : 0, d.wr[p][g - 1], d.wr16[p][g - 1]);
-                    LAUNCH_CHECK("k_pack_roll");
-                }
-            if (d.wd_pack[p]) {
-                launch_plain(k_pack_dgrad, grid_for(static_cast<size_t>(d.C) * 9 * d.Cout), dim3(256), 0, s, d.w_orig[p], d.Cout, d.Cw, d.C, d.wd_pack[p]);
-                LAUNCH_CHECK("k_pack_dgrad");
-            }
+                for (int g = 1; g <= 2; ++g)
+                    job(3, w, nullptr, d.wr[p][g - 1], d.wr16[p][g - 1], static_cast<long long>(3) * d.C * 4 * d.Cout, d.Cout, d.Cw, d.C, d.Cs, g,
+                        roll_row_varying(p, g) ? 1 : 0);
+            if (d.wd_pack[p]) job(4, w, nullptr, d.wd_pack[p], nullptr, static_cast<long long>(d.C) * 9 * d.Cout, d.Cout, d.Cw, d.C, d.Cs);
             for (int g = 1; g <= 2 && ro; ++g)
-                if (d.wrv[p][g - 1]) {
-                    launch_plain(k_pack_rollv, grid_for(static_cast<size_t>(9) * d.Cout * d.C), dim3(256), 0, s, d.w_orig[p], d.Cout, d.C, g,
-                                 roll_row_varying(p, g) ? 1 : 0, d.wrv[p][g - 1]);
-                    LAUNCH_CHECK("k_pack_rollv");
-                }
-            if (d.Cs && d.wsd_pack[p]) {
-                launch_plain(k_pack_dgrad_1x1, grid_for(static_cast<size_t>(d.Cs) * d.Cout), dim3(256), 0, s, d.wskip_orig[p], d.Cout, d.Cs, d.wsd_pack[p]);
-                LAUNCH_CHECK("k_pack_dgrad_1x1");
-            }
+                if (d.wrv[p][g - 1])
+                    job(6, w, nullptr, d.wrv[p][g - 1], nullptr, static_cast<long long>(9) * d.Cout * d.C, d.Cout, d.Cw, d.C, d.Cs, g,
+                        roll_row_varying(p, g) ? 1 : 0);
+            if (d.Cs && d.wsd_pack[p]) job(5, ws, nullptr, d.wsd_pack[p], nullptr, static_cast<long long>(d.Cs) * d.Cout, d.Cout, d.Cw, d.C, d.Cs);
         }
     };
     for (size_t i = 0; i < u->blocks.size(); ++i) {
@@ -584,6 +583,16 @@ static void refresh_from_device(s3d_unet* u, const float* const* src, int n_src,
         refresh_conv(d.c1, b.name + ".in_layers.2", "");
         refresh_conv(d.c2, b.name + ".out_layers.2", b.name + ".skip_connection");
     }
+    // the table only changes when the caller's pointers (or the set of training packs) do: upload it then, replay it otherwise
+    const size_t bytes = jobs.size() * sizeof(PackJob);
+    if (u->pack_jobs_host.size() != bytes || memcmp(u->pack_jobs_host.data(), jobs.data(), bytes) != 0) {
+        if (u->pack_jobs_dev) cudaFree(u->pack_jobs_dev);
+        CUDA_TRY(cudaMalloc(&u->pack_jobs_dev, bytes));
+        CUDA_TRY(cudaMemcpy(u->pack_jobs_dev, jobs.data(), bytes, cudaMemcpyHostToDevice));
+        u->pack_jobs_host.assign(reinterpret_cast<const char*>(jobs.data()), reinterpret_cast<const char*>(jobs.data()) + bytes);
+    }
+    launch_plain(k_pack_jobs, dim3(24, static_cast<unsigned>(jobs.size())), dim3(256), 0, s, static_cast<const PackJob*>(u->pack_jobs_dev));
+    LAUNCH_CHECK("k_pack_jobs");
 }
 
 // ------------------------------------------------------------------------------------ launch plan
@@ -1525,6 +1534,7 @@ int s3d_unet_destroy(s3d_unet* u) {
     cudaSetDevice(u->device);
     destroy_plan(u);
     free_all(u->wallocs);
+    if (u->pack_jobs_dev) cudaFree(u->pack_jobs_dev);
     delete u;
     return 0;
 }

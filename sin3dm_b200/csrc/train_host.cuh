@@ -90,7 +90,12 @@ struct BackwardBuilder {
     void release(const Act16& a) {
         for (int p = 0; p < 3; ++p) pb.barena.release(a.p.p[p]);
     }
-    int slots(int level) const { return std::max(1, std::min(2 * u->num_sms / 3, pb.max_px(level) / 32)); }
+    // CTAs per (plane, sample) of the element-wise backward kernels: one wave at batch 1, about eight CTAs per SM in all at large
+    // batch (their per-CTA reductions end in atomics on a few addresses: no more CTAs than fill the machine)
+    int slots(int level) const {
+        const int per_wave = std::min(2 * u->num_sms / 3, pb.max_px(level) / 32);
+        return std::max(1, std::min(per_wave, std::max(4, 8 * u->num_sms / (3 * B))));
+    }
 
     // ---- fp32 gradient of a conv output -> (hi, lo) pair + axis sums + per-channel totals
     struct Staged {
@@ -527,13 +532,15 @@ static void build_backward(s3d_unet* u, PlanBuilder& pb, const ActF& h_last, con
         A.dy = dy_head.p;
         bb.grad3("out.2", "conv", "weight", A.dw);
         bb.grad3("out.2", "conv", "bias", A.db);
-        A.nslots = bb.slots(0);
-        S3D_CHECK(c0 <= 128 && Cf <= kMaxCf, "head backward supports C0 <= 128 and <= 16 triplane channels");
-        const size_t smem = sizeof(float) * (2 * c0 + 2 * Cf * c0 + Cf + 8 * Cf);
+        for (int i = 0; i < 4; ++i) A.tile_start[i] = bnd.tile_start[i];
+        for (int i = 0; i < 3; ++i) A.tiles_fast[i] = bnd.tiles_fast[i];
+        S3D_CHECK((c0 == 64 || c0 == 128) && Cf <= kMaxCf, "head backward supports C0 = 64 | 128 and <= 16 triplane channels");
         bb.add("k_head_bwd", 4.0 * B * bb.px3(0) * c0 * Cf, [=](cudaStream_t s) {
             HeadBwdArgs Al = A;
             Al.g = P->grad_out;
-            launch_plain(k_head_bwd, dim3(Al.nslots, 3, B), dim3(256), smem, s, Al);
+            const dim3 grid(std::max(1, 4 * u->num_sms / (3 * B)), B, 3);
+            if (c0 == 64) launch_plain(k_head_bwd<16>, dim3(grid), dim3(256), 0, s, Al);
+            else launch_plain(k_head_bwd<32>, dim3(grid), dim3(256), 0, s, Al);
             LAUNCH_CHECK("k_head_bwd");
         });
     }
@@ -568,8 +575,23 @@ static void build_backward(s3d_unet* u, PlanBuilder& pb, const ActF& h_last, con
         const int Ct = A.Cu + A.Cs, bx = Ct / 4, ny = std::max(1, 256 / bx);
         size_t low_bytes[3];
         for (int p = 0; p < 3; ++p) low_bytes[p] = sizeof(float) * static_cast<size_t>(B) * pb.px(U.low.level, p) * U.low.C;
+        // plain x2 (even sizes, no resize step): the up half as a deterministic gather over the low-resolution pixels
+        bool plain_up = U.do_up;
+        for (int p = 0; p < 3; ++p)
+            plain_up = plain_up && 2 * A.dlow.rows[p] == A.dout.rows[p] && 2 * A.dlow.cols[p] == A.dout.cols[p];
+        if (plain_up) {
+            UpcatBwdArgs G = A;
+            G.nslots = bb.slots(U.low.level);
+            A.skip_only = 1;
+            const int gbx = A.Cu / 4, gny = std::max(1, 256 / gbx);
+            bb.add("k_up2_bwd_gather", 0.0, [=](cudaStream_t s) {
+                launch_plain(k_up2_bwd_gather, dim3(G.nslots, 3, B), dim3(gbx, gny), 0, s, G);
+                LAUNCH_CHECK("k_up2_bwd_gather");
+            });
+        }
         bb.add("k_upcat_bwd", 0.0, [=](cudaStream_t s) {
-            for (int p = 0; p < 3; ++p) CUDA_TRY(cudaMemsetAsync(A.dlow_g.p[p], 0, low_bytes[p], s));      // scatter target
+            if (!A.skip_only)
+                for (int p = 0; p < 3; ++p) CUDA_TRY(cudaMemsetAsync(A.dlow_g.p[p], 0, low_bytes[p], s));      // scatter target
             launch_plain(k_upcat_bwd, dim3(A.nslots, 3, B), dim3(bx, ny), 0, s, A);
             LAUNCH_CHECK("k_upcat_bwd");
         });
@@ -621,12 +643,14 @@ static void build_backward(s3d_unet* u, PlanBuilder& pb, const ActF& h_last, con
         A.B = B;
         bb.grad3("in_conv.0", "conv", "weight", A.dw);
         bb.grad3("in_conv.0", "conv", "bias", A.db);
-        A.nslots = bb.slots(0);
-        const size_t smem = sizeof(float) * (c0 * A.Cf + c0 + 8 * A.Cf);
+        for (int i = 0; i < 4; ++i) A.tile_start[i] = bnd.tile_start[i];
+        for (int i = 0; i < 3; ++i) A.tiles_fast[i] = bnd.tiles_fast[i];
         bb.add("k_inconv_wgrad", 2.0 * B * bb.px3(0) * c0 * A.Cf, [=](cudaStream_t s) {
             InconvBwdArgs Al = A;
             Al.x = P->x;
-            launch_plain(k_inconv_wgrad, dim3(Al.nslots, 3, B), dim3(256), smem, s, Al);
+            const dim3 grid(std::max(1, 4 * u->num_sms / (3 * B)), B, 3);
+            if (c0 == 64) launch_plain(k_inconv_wgrad<16>, dim3(grid), dim3(256), 0, s, Al);
+            else launch_plain(k_inconv_wgrad<32>, dim3(grid), dim3(256), 0, s, Al);
             LAUNCH_CHECK("k_inconv_wgrad");
         });
         bb.release(dpool);

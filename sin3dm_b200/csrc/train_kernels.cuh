@@ -570,7 +570,6 @@ __global__ void __launch_bounds__(256) k_wgrad_ffma(WgradArgs A) {
 //                 dw[co][c] += S * sum_px g y,  db[co] += S * sum_px g             (g = dL/dout in the composed layout)
 //   in_conv (:378): h0[px][co] = b[co] + sum_c w[co][c] x[c][px]
 //     k_inconv_wgrad: dw[co][c] += sum_px dh0[px][co] x[c][px],  db[co] += sum_px dh0[px][co]
-// grid (slots, 3, B), block 256; one warp per pixel at a time (lane = channel pair / quad)
 // =====================================================================================
 struct HeadBwdArgs {
     const float* g;            // composed [B][Cf][H+D][W+D]
@@ -578,82 +577,114 @@ struct HeadBwdArgs {
     TriCF h;                   // [B][rows][cols][C0]
     TriDims d;
     int C0, Cf, H, W, Dd, B;
+    int tile_start[4], tiles_fast[3];      // the boundary kernels' 4 x 32-pixel tiling of the three planes
     const unsigned long long* acc;
     TriCF gamma, beta;
     TriCF w_out;               // [Cf][C0]
     TriF dy;                   // out [B][rows][cols][C0]
     float* dw[3];              // [Cf][C0] (+=)
     float* db[3];              // [Cf] (+=)
-    int nslots;
 };
+// Same mapping as k_boundary: a CTA owns a 128-pixel tile (4 x 32 with the 32 along the axis that is contiguous in the composed
+// tensor), the composed gradient tile is staged through shared memory, a thread is (pixel, channel quad) with its 4 channels'
+// rows of w_out in registers; dw partials stay in registers over the tile's 8 passes and are reduced once per CTA.
+// A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... of ONE plane and reduces its dw / db partials once at the end (the
+// global atomics all land on the same Cf x C0 addresses: as few CTAs as fill the machine).  grid (gx, B, 3), block 256
+template <int NQ>
 __global__ void __launch_bounds__(256) k_head_bwd(HeadBwdArgs A) {
-    extern __shared__ float sm[];      // ca[C0] cb[C0] w[Cf][C0] dwacc[Cf][C0] dbacc[Cf] gbuf[8 warps][Cf]
+    constexpr int PPP = 256 / NQ, NPASS = kBndPx / PPP, C0 = NQ * 4;
+    __shared__ __align__(16) float gs[kMaxCf][kBndPx];      // S * dL/dout of the tile, [channel][pixel]
+    __shared__ __align__(16) float coefA[C0], coefB[C0];
+    __shared__ float dwacc[kMaxCf][C0];
+    __shared__ float dbacc[kMaxCf];
     __shared__ float mean[kGroups], rstd[kGroups];
-    const int plane = blockIdx.y, b = blockIdx.z, C0 = A.C0, Cf = A.Cf, cpg = C0 / kGroups;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rows = A.d.rows[plane], cols = A.d.cols[plane], npx = rows * cols;
-    float *ca = sm, *cb = sm + C0, *w = sm + 2 * C0, *dwacc = w + Cf * C0, *dbacc = dwacc + Cf * C0, *gbuf = dbacc + Cf;
+    const int tid = threadIdx.x, b = blockIdx.y, Cf = A.Cf, plane = blockIdx.z;
+    const int ntile = A.tile_start[plane + 1] - A.tile_start[plane];
+    if (static_cast<int>(blockIdx.x) >= ntile) return;
+    const int rows = A.d.rows[plane], cols = A.d.cols[plane], npx = rows * cols, cpg = C0 / kGroups;
+    const bool fast_rows = plane == 2;
+    const int Hc = A.H + A.Dd, Wc = A.W + A.Dd;
+    const long long hw = static_cast<long long>(Hc) * Wc;
+    const float S = loss_scale(A.amax);
+    for (int e = tid; e < kMaxCf * C0; e += 256) (&dwacc[0][0])[e] = 0.f;
+    if (tid < kMaxCf) dbacc[tid] = 0.f;
     gn_mean_rstd(A.acc, b, plane, static_cast<double>(npx) * cpg, tid, mean, rstd);
     __syncthreads();
     for (int c = tid; c < C0; c += 256) {
         const int g = c / cpg;
         const float ga = __ldg(A.gamma.p[plane] + c) * rstd[g];
-        ca[c] = ga;
-        cb[c] = __ldg(A.beta.p[plane] + c) - mean[g] * ga;
+        coefA[c] = ga;
+        coefB[c] = __ldg(A.beta.p[plane] + c) - mean[g] * ga;
     }
-    for (int i = tid; i < Cf * C0; i += 256) {
-        w[i] = __ldg(A.w_out.p[plane] + i);
-        dwacc[i] = 0.f;
-    }
-    for (int i = tid; i < Cf; i += 256) dbacc[i] = 0.f;
-    __syncthreads();
-    const float S = loss_scale(A.amax);
-    const int Hc = A.H + A.Dd, Wc = A.W + A.Dd;
-    const long long hw = static_cast<long long>(Hc) * Wc;
-    const int ppc = (npx + A.nslots - 1) / A.nslots;
-    const int p0 = blockIdx.x * ppc, p1 = min(npx, p0 + ppc);
-    const float* hp = A.h.p[plane] + static_cast<size_t>(b) * npx * C0;
-    float* dyp = A.dy.p[plane] + static_cast<size_t>(b) * npx * C0;
-    float* gw = gbuf + warp * Cf;
-    // lane owns channels lane, lane + 32, ... (at most 4: C0 <= 128): its dw partials for all Cf outputs stay in registers
-    float dwr[4][kMaxCf] = {};
-    float dbr = 0.f;
-    for (int px = p0 + warp; px < p1; px += 8) {
-        const int r = px / cols, c = px - r * cols;
-        const long long off = composed_offset(plane, r, c, A.H, A.W, Wc);
-        if (lane < Cf) gw[lane] = S * __ldg(A.g + (static_cast<size_t>(b) * Cf + lane) * hw + off);
-        __syncwarp();
+    const int ql = tid & (NQ - 1), pslot = tid / NQ;
+    float4 wq[kMaxCf];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int ch = lane + 32 * q;
-            if (ch < C0) {
-                const float y = silu_f(fmaf(__ldg(hp + static_cast<size_t>(px) * C0 + ch), ca[ch], cb[ch]));
-                float dy = 0.f;
+    for (int co = 0; co < kMaxCf; ++co)
+        wq[co] = co < Cf ? __ldg(reinterpret_cast<const float4*>(A.w_out.p[plane] + static_cast<size_t>(co) * C0 + ql * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const float4 ca = *reinterpret_cast<const float4*>(coefA + ql * 4), cb = *reinterpret_cast<const float4*>(coefB + ql * 4);
+    const float* hp = A.h.p[plane] + static_cast<size_t>(b) * npx * C0 + ql * 4;
+    float* dyp = A.dy.p[plane] + static_cast<size_t>(b) * npx * C0 + ql * 4;
+    float4 dwr[kMaxCf];
+#pragma unroll
+    for (int co = 0; co < kMaxCf; ++co) dwr[co] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dbr = 0.f;
+    for (int ip = blockIdx.x; ip < ntile; ip += gridDim.x) {
+        const int tf = ip % A.tiles_fast[plane], ts = ip / A.tiles_fast[plane];
+        const int r0 = fast_rows ? tf * kBndFast : ts * kBndSlow, c0 = fast_rows ? ts * kBndSlow : tf * kBndFast;
+        auto pix_r = [&](int i) { return r0 + (fast_rows ? (i & (kBndFast - 1)) : (i >> 5)); };
+        auto pix_c = [&](int i) { return c0 + (fast_rows ? (i >> 5) : (i & (kBndFast - 1))); };
+        __syncthreads();                                     // the previous tile's gs has been read
+        for (int e = tid; e < Cf * kBndPx; e += 256) {
+            const int co = e >> 7, i = e & (kBndPx - 1), r = pix_r(i), c = pix_c(i);
+            gs[co][i] = (r < rows && c < cols) ? S * __ldg(A.g + (static_cast<size_t>(b) * Cf + co) * hw + composed_offset(plane, r, c, A.H, A.W, Wc)) : 0.f;
+        }
+        __syncthreads();
+        // four pixels in flight per thread: the activation loads of a batch are issued before the first use
+        constexpr int NB = NPASS < 4 ? NPASS : 4;
+#pragma unroll
+        for (int p0 = 0; p0 < NPASS; p0 += NB) {
+            float4 hv[NB];
+            size_t off[NB];
+            bool ok[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                const int i = (p0 + k) * PPP + pslot, r = pix_r(i), c = pix_c(i);
+                ok[k] = r < rows && c < cols;
+                off[k] = ok[k] ? (static_cast<size_t>(r) * cols + c) * C0 : 0;
+                hv[k] = ok[k] ? __ldg(reinterpret_cast<const float4*>(hp + off[k])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                const int i = (p0 + k) * PPP + pslot;
+                float4 y;
+                y.x = silu_f(fmaf(hv[k].x, ca.x, cb.x)); y.y = silu_f(fmaf(hv[k].y, ca.y, cb.y));
+                y.z = silu_f(fmaf(hv[k].z, ca.z, cb.z)); y.w = silu_f(fmaf(hv[k].w, ca.w, cb.w));
+                float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int co = 0; co < kMaxCf; ++co)
                     if (co < Cf) {
-                        const float gv = gw[co];
-                        dy = fmaf(gv, w[co * C0 + ch], dy);
-                        dwr[q][co] = fmaf(gv, y, dwr[q][co]);
+                        const float gv = gs[co][i];          // zero for pixels outside the plane
+                        dy.x = fmaf(gv, wq[co].x, dy.x); dy.y = fmaf(gv, wq[co].y, dy.y); dy.z = fmaf(gv, wq[co].z, dy.z); dy.w = fmaf(gv, wq[co].w, dy.w);
+                        dwr[co].x = fmaf(gv, y.x, dwr[co].x); dwr[co].y = fmaf(gv, y.y, dwr[co].y);
+                        dwr[co].z = fmaf(gv, y.z, dwr[co].z); dwr[co].w = fmaf(gv, y.w, dwr[co].w);
                     }
-                dyp[static_cast<size_t>(px) * C0 + ch] = dy;
+                if (ok[k]) *reinterpret_cast<float4*>(dyp + off[k]) = dy;
             }
         }
-        if (lane < Cf) dbr += gw[lane];
-        __syncwarp();
+        if (tid < Cf)
+            for (int i = 0; i < kBndPx; ++i) dbr += gs[tid][i];
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int ch = lane + 32 * q;
-        if (ch < C0)
-#pragma unroll
-            for (int co = 0; co < kMaxCf; ++co)
-                if (co < Cf) atomicAdd(&dwacc[co * C0 + ch], dwr[q][co]);
-    }
-    if (lane < Cf) atomicAdd(&dbacc[lane], dbr);
+    for (int co = 0; co < kMaxCf; ++co)
+        if (co < Cf) {
+            atomicAdd(&dwacc[co][ql * 4 + 0], dwr[co].x); atomicAdd(&dwacc[co][ql * 4 + 1], dwr[co].y);
+            atomicAdd(&dwacc[co][ql * 4 + 2], dwr[co].z); atomicAdd(&dwacc[co][ql * 4 + 3], dwr[co].w);
+        }
+    if (tid < Cf) dbacc[tid] = dbr;
     __syncthreads();
-    for (int i = tid; i < Cf * C0; i += 256) atomicAdd(A.dw[plane] + i, dwacc[i]);
-    for (int i = tid; i < Cf; i += 256) atomicAdd(A.db[plane] + i, dbacc[i]);
+    for (int e = tid; e < Cf * C0; e += 256) atomicAdd(A.dw[plane] + e, dwacc[e / C0][e % C0]);
+    if (tid < Cf) atomicAdd(A.db[plane] + tid, dbacc[tid]);
 }
 
 struct InconvBwdArgs {
@@ -661,57 +692,68 @@ struct InconvBwdArgs {
     TriCF dh0;                 // [B][rows][cols][C0]
     TriDims d;
     int C0, Cf, H, W, Dd, B;
+    int tile_start[4], tiles_fast[3];
     float* dw[3];              // [C0][Cf] (+=)
     float* db[3];              // [C0] (+=)
-    int nslots;
 };
+// same tiling and tile walk (grid (gx, B, 3)); thread = (pixel, output-channel quad): dw[co][c] += dh0[px][co] x[c][px]
+template <int NQ>
 __global__ void __launch_bounds__(256) k_inconv_wgrad(InconvBwdArgs A) {
-    extern __shared__ float sm[];      // dwacc[C0][Cf] dbacc[C0] xbuf[8][Cf]
-    const int plane = blockIdx.y, b = blockIdx.z, C0 = A.C0, Cf = A.Cf;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int PPP = 256 / NQ, NPASS = kBndPx / PPP, C0 = NQ * 4;
+    __shared__ __align__(16) float xs[kMaxCf][kBndPx];
+    __shared__ float dwacc[C0][kMaxCf];
+    __shared__ float dbacc[C0];
+    const int tid = threadIdx.x, b = blockIdx.y, Cf = A.Cf, plane = blockIdx.z;
+    const int ntile = A.tile_start[plane + 1] - A.tile_start[plane];
+    if (static_cast<int>(blockIdx.x) >= ntile) return;
     const int rows = A.d.rows[plane], cols = A.d.cols[plane], npx = rows * cols;
-    float *dwacc = sm, *dbacc = sm + C0 * Cf, *xbuf = dbacc + C0;
-    for (int i = tid; i < C0 * Cf + C0; i += 256) sm[i] = 0.f;
-    __syncthreads();
+    const bool fast_rows = plane == 2;
     const int Hc = A.H + A.Dd, Wc = A.W + A.Dd;
     const long long hw = static_cast<long long>(Hc) * Wc;
-    const int ppc = (npx + A.nslots - 1) / A.nslots;
-    const int p0 = blockIdx.x * ppc, p1 = min(npx, p0 + ppc);
-    const float* dp = A.dh0.p[plane] + static_cast<size_t>(b) * npx * C0;
-    float* xw = xbuf + warp * Cf;
-    float dwr[4][kMaxCf] = {};     // lane owns output channels lane, lane + 32, ... (C0 <= 128)
-    float dbr[4] = {};
-    for (int px = p0 + warp; px < p1; px += 8) {
-        const int r = px / cols, c = px - r * cols;
-        const long long off = composed_offset(plane, r, c, A.H, A.W, Wc);
-        if (lane < Cf) xw[lane] = __ldg(A.x + (static_cast<size_t>(b) * Cf + lane) * hw + off);
-        __syncwarp();
+    for (int e = tid; e < C0 * kMaxCf; e += 256) (&dwacc[0][0])[e] = 0.f;
+    for (int e = tid; e < C0; e += 256) dbacc[e] = 0.f;
+    const int ql = tid & (NQ - 1), pslot = tid / NQ;
+    const float* dp = A.dh0.p[plane] + static_cast<size_t>(b) * npx * C0 + ql * 4;
+    float4 dwr[kMaxCf];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int co = lane + 32 * q;
-            if (co < C0) {
-                const float dv = __ldg(dp + static_cast<size_t>(px) * C0 + co);
+    for (int ch = 0; ch < kMaxCf; ++ch) dwr[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 dbr = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ip = blockIdx.x; ip < ntile; ip += gridDim.x) {
+        const int tf = ip % A.tiles_fast[plane], ts = ip / A.tiles_fast[plane];
+        const int r0 = fast_rows ? tf * kBndFast : ts * kBndSlow, c0 = fast_rows ? ts * kBndSlow : tf * kBndFast;
+        auto pix_r = [&](int i) { return r0 + (fast_rows ? (i & (kBndFast - 1)) : (i >> 5)); };
+        auto pix_c = [&](int i) { return c0 + (fast_rows ? (i >> 5) : (i & (kBndFast - 1))); };
+        __syncthreads();
+        for (int e = tid; e < kMaxCf * kBndPx; e += 256) {
+            const int ch = e >> 7, i = e & (kBndPx - 1), r = pix_r(i), c = pix_c(i);
+            xs[ch][i] = (ch < Cf && r < rows && c < cols) ? __ldg(A.x + (static_cast<size_t>(b) * Cf + ch) * hw + composed_offset(plane, r, c, A.H, A.W, Wc)) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int pass = 0; pass < NPASS; ++pass) {
+            const int i = pass * PPP + pslot, r = pix_r(i), c = pix_c(i);
+            if (r >= rows || c >= cols) continue;
+            const float4 dv = __ldg(reinterpret_cast<const float4*>(dp + (static_cast<size_t>(r) * cols + c) * C0));
+            dbr.x += dv.x; dbr.y += dv.y; dbr.z += dv.z; dbr.w += dv.w;
 #pragma unroll
-                for (int ch = 0; ch < kMaxCf; ++ch)
-                    if (ch < Cf) dwr[q][ch] = fmaf(dv, xw[ch], dwr[q][ch]);
-                dbr[q] += dv;
+            for (int ch = 0; ch < kMaxCf; ++ch) {
+                const float xv = xs[ch][i];
+                dwr[ch].x = fmaf(dv.x, xv, dwr[ch].x); dwr[ch].y = fmaf(dv.y, xv, dwr[ch].y);
+                dwr[ch].z = fmaf(dv.z, xv, dwr[ch].z); dwr[ch].w = fmaf(dv.w, xv, dwr[ch].w);
             }
         }
-        __syncwarp();
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int co = lane + 32 * q;
-        if (co < C0) {
-#pragma unroll
-            for (int ch = 0; ch < kMaxCf; ++ch)
-                if (ch < Cf) atomicAdd(&dwacc[co * Cf + ch], dwr[q][ch]);
-            atomicAdd(&dbacc[co], dbr[q]);
+    for (int ch = 0; ch < kMaxCf; ++ch)
+        if (ch < Cf) {
+            atomicAdd(&dwacc[ql * 4 + 0][ch], dwr[ch].x); atomicAdd(&dwacc[ql * 4 + 1][ch], dwr[ch].y);
+            atomicAdd(&dwacc[ql * 4 + 2][ch], dwr[ch].z); atomicAdd(&dwacc[ql * 4 + 3][ch], dwr[ch].w);
         }
-    }
+    atomicAdd(&dbacc[ql * 4 + 0], dbr.x); atomicAdd(&dbacc[ql * 4 + 1], dbr.y);
+    atomicAdd(&dbacc[ql * 4 + 2], dbr.z); atomicAdd(&dbacc[ql * 4 + 3], dbr.w);
     __syncthreads();
-    for (int i = tid; i < C0 * Cf; i += 256) atomicAdd(A.dw[plane] + i, dwacc[i]);
-    for (int i = tid; i < C0; i += 256) atomicAdd(A.db[plane] + i, dbacc[i]);
+    for (int e = tid; e < C0 * Cf; e += 256) atomicAdd(A.dw[plane] + e, dwacc[e / Cf][e % Cf]);
+    for (int e = tid; e < C0; e += 256) atomicAdd(A.db[plane] + e, dbacc[e]);
 }
 
 // =====================================================================================
@@ -725,6 +767,7 @@ struct UpcatBwdArgs {
     TriCF dcat;
     TriDims dout, dlow;
     int Cu, Cs, B, do_up;
+    int skip_only;             // 1: only the skip / pool-adjoint half (the up half is done by k_up2_bwd_gather)
     TriF dlow_g;               // [B][lrows][lcols][Cu] (+=, atomics)
     TriF dskip;                // [B][rows][cols][Cs]
     TriCF dpool;               // gradient of the pooled copy of the skip tensor [B][rows/2][cols/2][Cs], or nullptr
@@ -762,6 +805,7 @@ __global__ void __launch_bounds__(256) k_upcat_bwd(UpcatBwdArgs A) {
     };
     for (int px = p0 + ty; px < p1; px += NY) {
         const int r = px / ocols, c = px - r * ocols;
+        if (tx < u4 && A.skip_only) continue;
         const float4 v = __ldg(reinterpret_cast<const float4*>(gp + static_cast<size_t>(px) * Ct + tx * 4));
         if (tx < u4) {
             if (resize) {
@@ -788,6 +832,56 @@ __global__ void __launch_bounds__(256) k_upcat_bwd(UpcatBwdArgs A) {
             }
             *(reinterpret_cast<float4*>(A.dskip.p[plane] + (static_cast<size_t>(b) * npx + px) * A.Cs) + (tx - u4)) = o;
         }
+    }
+}
+
+// Gather form of the plain x2 bilinear adjoint (no resize step, i.e. even plane sizes): every LOW-resolution pixel sums the <= 4 x 4
+// high-resolution pixels whose bilinear footprint contains it, with the weights bilin_src() gives the forward (so the clamped edges
+// come out right by construction).  No atomics, deterministic.  dcat: [B][rows][cols][Ct] (first Cu channels), dlow: [B][lrows][lcols][Cu].
+// grid (slots, 3, B), block (Cu/4, NY)
+__global__ void __launch_bounds__(256) k_up2_bwd_gather(UpcatBwdArgs A) {
+    const int plane = blockIdx.y, b = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y;
+    const int orows = A.dout.rows[plane], ocols = A.dout.cols[plane], lrows = A.dlow.rows[plane], lcols = A.dlow.cols[plane];
+    const int Ct = A.Cu + A.Cs;
+    const int npx = lrows * lcols;
+    const int ppc = (npx + A.nslots - 1) / A.nslots;
+    const int p0 = blockIdx.x * ppc, p1 = min(npx, p0 + ppc);
+    const float* gp = A.dcat.p[plane] + static_cast<size_t>(b) * orows * ocols * Ct + tx * 4;
+    float* lp = A.dlow_g.p[plane] + static_cast<size_t>(b) * npx * A.Cu + tx * 4;
+    for (int px = p0 + ty; px < p1; px += NY) {
+        const int r = px / lcols, c = px - r * lcols;
+        float wr[4], wc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                 // candidate high-res rows 2r-1 .. 2r+2 / columns 2c-1 .. 2c+2
+            const int hr = 2 * r - 1 + k, hc = 2 * c - 1 + k;
+            int i0, i1;
+            float l1;
+            wr[k] = wc[k] = 0.f;
+            if (hr >= 0 && hr < orows) {
+                bilin_src(hr, lrows, 0.5f, i0, i1, l1);
+                wr[k] = (i0 == r ? 1.f - l1 : 0.f) + (i1 == r ? l1 : 0.f);
+            }
+            if (hc >= 0 && hc < ocols) {
+                bilin_src(hc, lcols, 0.5f, i0, i1, l1);
+                wc[k] = (i0 == c ? 1.f - l1 : 0.f) + (i1 == c ? l1 : 0.f);
+            }
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int kr = 0; kr < 4; ++kr) {
+            if (wr[kr] == 0.f) continue;
+            const int hr = 2 * r - 1 + kr;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                if (wc[kc] == 0.f) continue;
+                const int hc = 2 * c - 1 + kc;
+                const float w = wr[kr] * wc[kc];
+                const float4 v = __ldg(reinterpret_cast<const float4*>(gp + (static_cast<size_t>(hr) * ocols + hc) * Ct));
+                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            }
+        }
+        *reinterpret_cast<float4*>(lp + static_cast<size_t>(px) * A.Cu) = acc;
     }
 }
 
@@ -899,6 +993,81 @@ __global__ void __launch_bounds__(256) k_pack_roll(const float* __restrict__ w, 
 __global__ void k_vec_add(const float* a, const float* b, float* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+// One launch for a whole refresh: a table of jobs (plain copies, bias sums and the packers above), blockIdx.y = job.  Every job
+// reads the CALLER's tensors, so there is no ordering between the jobs of a launch.
+struct PackJob {
+    int kind;                  // 0 copy, 1 dst = src + src2, 2 pack_conv, 3 pack_roll, 4 pack_dgrad, 5 pack_dgrad_1x1, 6 pack_rollv
+    int Cout, Cw, C, Cs, g, rowv;
+    long long n;               // elements of the job's index space
+    const float* src;
+    const float* src2;
+    void* dst;
+    void* dst2;
+};
+__global__ void __launch_bounds__(256) k_pack_jobs(const PackJob* __restrict__ jobs) {
+    const PackJob J = jobs[blockIdx.y];
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < J.n; i += stride) {
+        if (J.kind == 0) {
+            static_cast<float*>(J.dst)[i] = J.src[i];
+        } else if (J.kind == 1) {
+            static_cast<float*>(J.dst)[i] = J.src[i] + (J.src2 ? J.src2[i] : 0.f);
+        } else if (J.kind == 2) {                      // k_pack_conv
+            const int Ktot = 9 * J.C + J.Cs;
+            const int co = static_cast<int>(i / Ktot), k = static_cast<int>(i - static_cast<long long>(co) * Ktot);
+            float v;
+            if (k < 9 * J.C) {
+                const int tap = k / J.C, c = k - tap * J.C;
+                v = J.src[(static_cast<size_t>(co) * J.Cw + c) * 9 + tap];
+            } else {
+                v = J.src2[static_cast<size_t>(co) * J.Cs + (k - 9 * J.C)];
+            }
+            __half hi, lo;
+            split_f16(v, hi, lo);
+            static_cast<__half*>(J.dst)[i] = hi;
+            static_cast<__half*>(J.dst)[J.n + i] = lo;
+        } else if (J.kind == 3) {                      // k_pack_roll
+            const int K = 3 * J.C, N = 4 * J.Cout, Cw = 3 * J.C;
+            const int k = static_cast<int>(i / N), nn = static_cast<int>(i - static_cast<long long>(k) * N);
+            const int along = k / J.C, c = k - along * J.C, cls = nn / J.Cout, co = nn - cls * J.Cout;
+            float acc = 0.f;
+#pragma unroll
+            for (int across = 0; across < 3; ++across) {
+                const bool keep = cls == 0 || (cls == 1 && across >= 1) || (cls == 2 && across <= 1) || (cls == 3 && across == 1);
+                if (keep) {
+                    const int kh = J.rowv ? along : across, kw = J.rowv ? across : along;
+                    acc += J.src[((static_cast<size_t>(co) * Cw + J.g * J.C + c) * 3 + kh) * 3 + kw];
+                }
+            }
+            static_cast<float*>(J.dst)[i] = acc;
+            __half hi, lo;
+            split_f16(acc, hi, lo);
+            __half* w16 = static_cast<__half*>(J.dst2);
+            w16[static_cast<size_t>(nn) * K + k] = hi;
+            w16[(static_cast<size_t>(N) + nn) * K + k] = lo;
+        } else if (J.kind == 4) {                      // k_pack_dgrad
+            const int K = 9 * J.Cout;
+            const int c = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(c) * K);
+            const int tap = k / J.Cout, co = k - tap * J.Cout;
+            const int kh = 2 - tap / 3, kw = 2 - tap % 3;
+            __half hi, lo;
+            split_f16(J.src[(static_cast<size_t>(co) * J.Cw + c) * 9 + kh * 3 + kw], hi, lo);
+            static_cast<__half*>(J.dst)[i] = hi;
+            static_cast<__half*>(J.dst)[J.n + i] = lo;
+        } else if (J.kind == 5) {                      // k_pack_dgrad_1x1
+            const int cs = static_cast<int>(i / J.Cout), co = static_cast<int>(i - static_cast<long long>(cs) * J.Cout);
+            __half hi, lo;
+            split_f16(J.src[static_cast<size_t>(co) * J.Cs + cs], hi, lo);
+            static_cast<__half*>(J.dst)[i] = hi;
+            static_cast<__half*>(J.dst)[J.n + i] = lo;
+        } else {                                       // k_pack_rollv
+            const int c = static_cast<int>(i % J.C), co = static_cast<int>((i / J.C) % J.Cout), t = static_cast<int>(i / (static_cast<long long>(J.C) * J.Cout));
+            const int al = t / 3, ac = t - al * 3;
+            static_cast<float*>(J.dst)[i] = J.src[(static_cast<size_t>(co) * 3 * J.C + J.g * J.C + c) * 9 + (J.rowv ? al * 3 + ac : ac * 3 + al)];
+        }
+    }
 }
 
 // final pass: every gradient was carried times the loss scale

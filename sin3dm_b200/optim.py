@@ -48,6 +48,7 @@ class FusedAdamWEMA:
                 view.copy_(p)
                 p.data = view                                   # the module now lives in the flat buffer
                 p.grad = self.grad[o:o + p.numel()].view_as(p)  # autograd accumulates straight into the flat gradient
+                p._s3d_flat = (self.grad, o)                    # lets the UNet's backward add its whole flat gradient in one pass
         self.ema = [self.flat.clone() for _ in self.ema_rates]  # copies of the initial parameters (train_util.py:93-96)
 
     def zero_grad(self):

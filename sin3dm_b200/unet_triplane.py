@@ -89,7 +89,18 @@ class _UNetFn(th.autograd.Function):
         with th.cuda.device(g.device):
             _lib.check(L.s3d_unet_backward(h, C.c_void_p(g.data_ptr()), C.c_void_p(flat.data_ptr()), C.c_void_p(dfilm.data_ptr()),
                                            _lib.current_stream_ptr()))
-        grads = [flat[o:o + n].view(shape) for o, n, shape in module._kernel_param_slots()]
+        slots = module._kernel_param_slots()
+        # Parameters that live in FusedAdamWEMA's flat buffers (same 4-float-aligned state_dict layout as the library's gradient
+        # buffer): ONE add into the flat gradient instead of 130 AccumulateGrad kernels (the embedding MLP's slots are zero here
+        # and are filled by torch afterwards).
+        params = [p for _, p in module._kernel_params()]
+        tag = getattr(params[0], "_s3d_flat", None)
+        if tag is not None and tag[0].numel() == flat.numel() and tag[0].device == flat.device and all(
+                getattr(p, "_s3d_flat", (None, -1))[0] is tag[0] and p._s3d_flat[1] == o and p.grad is not None
+                and p.grad.data_ptr() == tag[0].data_ptr() + 4 * o for p, (o, _, _) in zip(params, slots)):
+            tag[0].add_(flat)
+            return (None, None, dfilm, None, None, None, *([None] * len(params)))
+        grads = [flat[o:o + n].view(shape) for o, n, shape in slots]
         return (None, None, dfilm, None, None, None, *grads)
 
 

@@ -165,3 +165,27 @@ def test_fused_optimizer_training_steps_reduce_the_loss():
         losses.append(float(loss.detach()))
     print("training losses", [round(v, 4) for v in losses])
     assert losses[-1] < 0.8 * losses[0]
+
+
+def test_flat_gradient_path_equals_per_parameter_path():
+    """With FusedAdamWEMA the backward adds its flat gradient buffer into the optimizer's flat gradient in one pass; the result
+    must equal the per-parameter autograd accumulation (and accumulate over two backward calls like autograd does)."""
+    from sin3dm_b200.optim import FusedAdamWEMA
+    case = GRAD_CASES["startx"]
+    spec = ur.UNetSpec(**case["spec"])
+    sd = ur.synthetic_state_dict(spec, case["wseed"])
+    H, W, D = case["HWD"]
+    x0, _, t = make_grad_inputs(case)
+    x, t = x0.cuda(), t.cuda()
+    ref = make_cuda_model(spec, sd).train()
+    for _ in range(2):
+        ref(x, t, H=H, W=W, D=D).square().mean().backward()
+    want = {k: p.grad.clone() for k, p in ref.named_parameters()}
+    m = make_cuda_model(spec, sd).train()
+    opt = FusedAdamWEMA(m.parameters(), lr=1e-3)
+    opt.zero_grad()
+    for _ in range(2):
+        m(x, t, H=H, W=W, D=D).square().mean().backward()
+    for k, p in m.named_parameters():
+        a, b = p.grad.double(), want[k].double()
+        assert float((a - b).norm()) <= 1e-4 * max(float(b.norm()), 1e-12), k
