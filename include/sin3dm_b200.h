@@ -262,6 +262,8 @@ typedef struct {
     int ks;                        /* kernel size of the TriplaneGroupResnetBlock convs (5, networks.py:152-153) */
     int precision;                 /* 3: fp16 hi/lo split, 3 MMAs (fp32-grade, default); 1: single fp16 MMA */
     int mlp_impl;                  /* 0: tcgen05 fused MLP; 1: CUDA-core fp32 kernel (cross-check / other MLP shapes) */
+    int mlp_kind;                  /* 0: DecoderMLPSkipConcat heads (AutoEncoderGroupSkip, enc_net_type "skip", networks.py:134);
+                                      1: plain DecoderMLP heads (AutoEncoderGroupV3, enc_net_type "base", networks.py:21, blocks.py:46) */
 } s3d_decoder_config;
 
 int s3d_decoder_create(const s3d_decoder_config* cfg, int device, s3d_decoder** out);

@@ -84,6 +84,9 @@ DECODER_CASES = {
     # data_type == "sdf": geometry branch only
     "sdf_only": dict(spec=dict(use_tex=False, tex_feat_channels=0), wseed=53, HWD=(12, 16, 12), n=257,
                      aabb=[-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], seed=63, spill=1.3),
+    # enc_net_type == "base": AutoEncoderGroupV3 with the plain DecoderMLP heads (networks.py:21-131, blocks.py:46-62)
+    "base_v3": dict(spec=dict(mlp_kind="base"), wseed=55, HWD=(18, 12, 22), n=500, aabb=[-0.8, -0.6, -1.0, 0.8, 0.6, 1.0], seed=65,
+                    spill=1.1),
     # decode_grid (model.py:335-349) over sample_grid_points_aabb (utils3d.py:13-25)
     "grid": dict(spec=dict(), wseed=54, HWD=(16, 22, 12), grid=20, aabb=[-0.72, -1.0, -0.55, 0.72, 1.0, 0.55], seed=64),
 }

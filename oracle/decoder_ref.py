@@ -37,6 +37,7 @@ class DecoderSpec:
     use_tex: bool = True
     tex_channels: int = 3
     ks: int = 5
+    mlp_kind: str = "skip"      # "skip": AutoEncoderGroupSkip / DecoderMLPSkipConcat; "base": AutoEncoderGroupV3 / DecoderMLP (networks.py:21-131)
 
     @property
     def out_channels(self) -> int:
@@ -51,8 +52,11 @@ def _branches(spec: DecoderSpec):
 
 
 def mlp_layer_names(spec: DecoderSpec):
-    """(sequential name, index) of every Linear of DecoderMLPSkipConcat, in evaluation order (blocks.py:65-91)."""
+    """(sequential name, index) of every Linear of DecoderMLPSkipConcat, in evaluation order (blocks.py:65-91); for the plain
+    DecoderMLP (blocks.py:46-62) everything is one Sequential `layers` and the second list is empty."""
     nh = spec.mlp_hidden_layers
+    if spec.mlp_kind == "base":
+        return [("layers", 2 * i) for i in range(nh + 2)], []
     first = [("first_layers", 2 * i) for i in range(1 + nh // 2)]
     second = [("second_layers", 2 * i) for i in range(1 + max(nh // 2 - 1, 0) + 1)]
     return first, second
@@ -79,7 +83,8 @@ def param_shapes(spec: DecoderSpec):
         first, second = mlp_layer_names(spec)
         for j, (seq, i) in enumerate(first):
             cin = up if j == 0 else hid
-            out += [(q + f"{seq}.{i}.weight", (hid, cin)), (q + f"{seq}.{i}.bias", (hid,))]
+            cout = oc if (spec.mlp_kind == "base" and j == len(first) - 1) else hid
+            out += [(q + f"{seq}.{i}.weight", (cout, cin)), (q + f"{seq}.{i}.bias", (cout,))]
         for j, (seq, i) in enumerate(second):
             cin = up + hid if j == 0 else hid
             cout = oc if j == len(second) - 1 else hid
@@ -181,6 +186,12 @@ def mlp_skip_concat(sd, prefix: str, spec: DecoderSpec, x):
     """DecoderMLPSkipConcat.forward (blocks.py:84-91), posenc == 0."""
     first, second = mlp_layer_names(spec)
     h = x
+    if spec.mlp_kind == "base":             # DecoderMLP.forward (blocks.py:59-62): Linear + ReLU ..., last Linear bare
+        for j, (seq, i) in enumerate(first):
+            h = F.linear(h, sd[prefix + f"{seq}.{i}.weight"], sd[prefix + f"{seq}.{i}.bias"])
+            if j < len(first) - 1:
+                h = F.relu(h)
+        return h
     for seq, i in first:
         h = F.relu(F.linear(h, sd[prefix + f"{seq}.{i}.weight"], sd[prefix + f"{seq}.{i}.bias"]))
     h = torch.cat([x, h], dim=-1)

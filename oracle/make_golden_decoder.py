@@ -36,16 +36,17 @@ def ref_grid_fn():
 
 def main():
     sys.path.insert(0, REF)
-    from encoding.networks import AutoEncoderGroupSkip
+    from encoding.networks import AutoEncoderGroupSkip, AutoEncoderGroupV3
     grid_fn = ref_grid_fn()
     os.makedirs(OUT, exist_ok=True)
     for name, case in DECODER_CASES.items():
         spec = de.DecoderSpec(**case["spec"])
         sd = de.synthetic_state_dict(spec, case["wseed"])
+        cls = AutoEncoderGroupV3 if spec.mlp_kind == "base" else AutoEncoderGroupSkip
         with contextlib.redirect_stdout(io.StringIO()):
-            net = AutoEncoderGroupSkip(spec.geo_feat_channels, spec.tex_feat_channels, spec.feat_channel_up,
-                                       spec.mlp_hidden_channels, spec.mlp_hidden_layers, use_tex=spec.use_tex,
-                                       tex_channels=spec.tex_channels)
+            net = cls(spec.geo_feat_channels, spec.tex_feat_channels, spec.feat_channel_up,
+                      spec.mlp_hidden_channels, spec.mlp_hidden_layers, use_tex=spec.use_tex,
+                      tex_channels=spec.tex_channels)
         assert [k for k, _ in de.param_shapes(spec)] == list(net.state_dict().keys()), "state_dict key order differs"
         net.load_state_dict(sd)
         net.eval()

@@ -90,6 +90,12 @@ struct LinName {
 std::vector<LinName> mlp_layers(const s3d_decoder_config& c, const std::string& prefix, int n_out, int* n_first) {
     std::vector<LinName> v;
     const int nh = c.mlp_hidden_layers, up = c.feat_channel_up, hid = c.mlp_hidden_channels;
+    if (c.mlp_kind == 1) {
+        // DecoderMLP (blocks.py:46-62): one Sequential `layers`: Linear(up, hid), nh x Linear(hid, hid), Linear(hid, out); no concat
+        for (int j = 0; j < nh + 2; ++j) v.push_back({prefix + "layers." + std::to_string(2 * j), j == 0 ? up : hid, j == nh + 1 ? n_out : hid});
+        *n_first = -1;
+        return v;
+    }
     const int nf = 1 + nh / 2, ns = 1 + std::max(nh / 2 - 1, 0) + 1;
     for (int j = 0; j < nf; ++j) v.push_back({prefix + "first_layers." + std::to_string(2 * j), j == 0 ? up : hid, hid});
     for (int j = 0; j < ns; ++j)
@@ -379,6 +385,7 @@ void decode(s3d_decoder* d, const DecPoints& P, int clamp_tex, float* out, cudaS
         std::copy(B.b_last_h.begin(), B.b_last_h.end(), tc.b_last[b]);
         ta.n_out[b] = B.n_out;
     }
+    ta.skip = d->cfg.mlp_kind == 0 ? 1 : 0;
     ta.n_tiles = (P.n + kDecPts - 1) / kDecPts;
     const unsigned grid = static_cast<unsigned>(std::min<long long>(ta.n_tiles, d->n_sm));
     if (d->cfg.precision == 1) {

@@ -428,6 +428,7 @@ struct DecTcArgs {
     DecArgs D;
     float inv_scale[2][kDecLayers];       // 1 / (power-of-two weight scale)
     int n_out[2];
+    int skip;                             // 1: the fourth layer reads cat[X, H3] (DecoderMLPSkipConcat); 0: plain DecoderMLP
     long long n_tiles;
 };
 // Epilogue constants travel as a kernel parameter (18.5 KB of the 32 KB parameter space): every thread of a warp reads the same
@@ -489,7 +490,8 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     // K chunks of layer l: layer 0 reads X, layer 3 reads [X | ACT], the others ACT
-    auto n_chunks = [](int l) { return l == 0 ? 1 : (l == 3 ? 5 : 4); };
+    const bool skip = A.skip != 0;
+    auto n_chunks = [skip](int l) { return l == 0 ? 1 : ((l == 3 && skip) ? 5 : 4); };
 
     if (warp == 0) {
         // ===================== TMA producer: weight tiles, in the order the MMA warp consumes them =====================
@@ -524,8 +526,8 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                     const int nk = n_chunks(l);
                     for (int kc = 0; kc < nk; ++kc) {
                         // A chunk: X for the first chunk of layers 0 and 3, else ACT chunk
-                        const bool from_x = (l == 0) || (l == 3 && kc == 0);
-                        const int ac = l == 3 ? kc - 1 : kc;
+                        const bool from_x = (l == 0) || (skip && l == 3 && kc == 0);
+                        const int ac = (skip && l == 3) ? kc - 1 : kc;
                         if (l == 0) ptx::mbar_wait(x_ready, xit & 1);
                         else if (!from_x) ptx::mbar_wait(&chunk_ready[ac], (l - 1) & 1);     // 4 producing epilogues per branch
                         ptx::tc_fence_after();

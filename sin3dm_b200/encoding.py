@@ -76,8 +76,21 @@ def sample_grid_points_axes(aabb, resolution):
             for i in range(3)]
 
 
+def _mlp_params_plain(cin, cout, hidden, n_hidden):
+    """Parameters of the plain DecoderMLP (blocks.py:46-62): one Sequential `layers`, ReLUs at the odd indices."""
+    m = _Holder()
+    layers = [nn.Linear(cin, hidden), _Holder()]
+    for _ in range(n_hidden):
+        layers += [nn.Linear(hidden, hidden), _Holder()]
+    layers.append(nn.Linear(hidden, cout))
+    m.layers = nn.Sequential(*layers)
+    return m
+
+
 class AutoEncoderGroupSkip(nn.Module):
     """Decode side of the reference auto-encoder (networks.py:134-223) on the sm_100a kernels."""
+    _mlp_kind = 0                      # s3d_decoder_config.mlp_kind
+    _mlp_factory = staticmethod(_mlp_params)
 
     def __init__(self, geo_feat_channels, tex_feat_channels, feat_channel_up, mlp_hidden_channels, mlp_hidden_layers,
                  use_tex=True, tex_channels=3, posenc=0):
@@ -92,10 +105,10 @@ class AutoEncoderGroupSkip(nn.Module):
         if use_tex:
             self.tex_encoder = _conv_params(tex_feat_channels, tex_channels + 1, 4, dims=3)
         self.geo_convs = _group_resnet_params(geo_feat_channels, feat_channel_up, 5)
-        self.geo_decoder = _mlp_params(feat_channel_up, 1, mlp_hidden_channels, mlp_hidden_layers)
+        self.geo_decoder = self._mlp_factory(feat_channel_up, 1, mlp_hidden_channels, mlp_hidden_layers)
         if use_tex:
             self.tex_convs = _group_resnet_params(tex_feat_channels, feat_channel_up, 5)
-            self.tex_decoder = _mlp_params(feat_channel_up, tex_channels, mlp_hidden_channels, mlp_hidden_layers)
+            self.tex_decoder = self._mlp_factory(feat_channel_up, tex_channels, mlp_hidden_channels, mlp_hidden_layers)
         self.register_buffer("aabb", torch.tensor([-1, -1, -1, 1, 1, 1], dtype=torch.float32))
         # kernel options: fp16x3 split (fp32-grade) unless S3D_PRECISION=1; tcgen05 MLP unless S3D_MLP_IMPL=ffma
         self.s3d_precision = int(os.environ.get("S3D_PRECISION", "3"))
@@ -160,7 +173,7 @@ class AutoEncoderGroupSkip(nn.Module):
             self._drop_handle()
             cfg = _lib.DecoderConfig(self.geo_feat_dim, self.tex_feat_dim if self.use_tex else 0, self.feat_channel_up,
                                      self.mlp_hidden_channels, self.mlp_hidden_layers, int(bool(self.use_tex)),
-                                     self.tex_channels, 5, self.s3d_precision, self.s3d_mlp_impl)
+                                     self.tex_channels, 5, self.s3d_precision, self.s3d_mlp_impl, self._mlp_kind)
             h = C.c_void_p()
             _lib.check(L.s3d_decoder_create(C.byref(cfg), idx, C.byref(h)))
             self._handle, self._handle_key = h, hkey
@@ -245,6 +258,23 @@ class AutoEncoderGroupSkip(nn.Module):
             _lib.check(L.s3d_decoder_planes_read(h, p, C.c_void_p(buf.data_ptr()), buf.numel()))
             out.append(buf)
         return out
+
+
+class AutoEncoderGroupV3(AutoEncoderGroupSkip):
+    """``enc_net_type == "base"`` (reference networks.py:21-131): the same encoder and feature-plane blocks with plain DecoderMLP
+    heads (blocks.py:46-62) instead of the skip-concat ones; same kernels, the fourth layer just has no concat chunk."""
+    _mlp_kind = 1
+    _mlp_factory = staticmethod(_mlp_params_plain)
+
+
+def get_networks(cfg):
+    """networks.py:7-18 (``pbr`` = AutoEncoderGroupPBR is not built: DESIGN.md §6)."""
+    use_tex = cfg.data_type != "sdf"
+    tex_channels = 8 if cfg.data_type == "sdfpbr" else 3
+    cls = {"base": AutoEncoderGroupV3, "skip": AutoEncoderGroupSkip}.get(cfg.enc_net_type)
+    if cls is None:
+        raise ValueError("Unknown / unsupported net type: {}".format(cfg.enc_net_type))
+    return cls(cfg.fdim_geo, cfg.fdim_tex, cfg.fdim_up, cfg.hidden_dim, cfg.n_hidden_layers, use_tex=use_tex, tex_channels=tex_channels)
 
 
 class TriplaneDecoder:

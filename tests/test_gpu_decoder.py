@@ -7,7 +7,7 @@ import torch
 
 from oracle import decoder_ref as de
 from oracle.cases import DECODER_CASES, make_decoder_inputs
-from sin3dm_b200.encoding import AutoEncoderGroupSkip, TriplaneDecoder
+from sin3dm_b200.encoding import AutoEncoderGroupSkip, AutoEncoderGroupV3, TriplaneDecoder
 
 pytestmark = pytest.mark.gpu
 
@@ -16,7 +16,8 @@ TOL_SPLIT = 2e-5    # what the fp16 hi/lo split and the fp32 CUDA-core kernel ac
 
 
 def make_net(spec, sd, precision=3, impl="tc"):
-    net = AutoEncoderGroupSkip(spec.geo_feat_channels, spec.tex_feat_channels, spec.feat_channel_up,
+    cls = AutoEncoderGroupV3 if spec.mlp_kind == "base" else AutoEncoderGroupSkip
+    net = cls(spec.geo_feat_channels, spec.tex_feat_channels, spec.feat_channel_up,
                                spec.mlp_hidden_channels, spec.mlp_hidden_layers, use_tex=spec.use_tex,
                                tex_channels=spec.tex_channels)
     net.load_state_dict(sd)

@@ -100,13 +100,13 @@ def test_abi_exports_every_declared_symbol():
     declared = set(re.findall(r"\b(s3d_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib._SIGNATURES), declared ^ set(_lib._SIGNATURES)
     L = _lib.lib()            # raises if the .so is missing or a symbol cannot be bound
-    assert L.s3d_abi_version() == 2
+    assert L.s3d_abi_version() == 3
     for name in declared:
         assert hasattr(L, name)
     # struct sizes agree with the header layout (no compute call: there is no GPU here)
     import ctypes as C
     assert C.sizeof(_lib.UNetConfig) == 4 * (5 + 8 + 4)
-    assert C.sizeof(_lib.DecoderConfig) == 4 * 10
+    assert C.sizeof(_lib.DecoderConfig) == 4 * 11
 
 
 @pytest.mark.parametrize("use_tex", [True, False])
