@@ -34,6 +34,19 @@ def broadcast_parameters(module, src=0):
     return flat.numel()
 
 
+def all_reduce_gradients(flat_grad, average=True):
+    """Data-parallel training: ONE all-reduce of the flat gradient buffer per step (``FusedAdamWEMA.grad``, ~28 MB for the default
+    UNet: the backward writes every gradient into that one buffer, so there is nothing to bucket).  NCCL over NVLink / NVSwitch on
+    the GPU box, gloo in the CPU tests.  The reference trains on one device (src/utils/dist_util.py:19-42); this is the exchange
+    step its commented-out ``sync_params`` / DDP lineage (guided-diffusion) would have had."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return flat_grad
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    if average:
+        flat_grad.div_(dist.get_world_size())
+    return flat_grad
+
+
 def sample_sharded(sample_fn, n_samples, sample_shape, batch_size=None, gather=True, device=None):
     """Runs ``sample_fn(shape, sample_base)`` for this rank's block of the ``n_samples`` global samples.
 

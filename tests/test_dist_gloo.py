@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sin3dm_b200.dist import broadcast_parameters, sample_sharded, shard_range
+from sin3dm_b200.dist import all_reduce_gradients, broadcast_parameters, sample_sharded, shard_range
 
 
 def test_shard_range_partitions_exactly():
@@ -43,6 +43,10 @@ def _worker(rank, world, port, q):
 
         out = sample_sharded(fake, 5, (2, 3), batch_size=2, gather=True)
         ok = out.shape == (5, 2, 3) and all(float(out[i, 0, 0]) == i for i in range(5))
+        # data-parallel training: one all-reduce of the flat gradient buffer, averaged over the ranks
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        all_reduce_gradients(flat)
+        ok = ok and torch.allclose(flat, torch.arange(10, dtype=torch.float32) * (sum(range(1, world + 1)) / world))
         q.put((rank, n, same, ok))
     finally:
         dist.destroy_process_group()

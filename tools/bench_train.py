@@ -19,6 +19,7 @@ import sys
 def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
     torch = bn.torch
     from sin3dm_b200 import _lib
+    from sin3dm_b200.dist import all_reduce_gradients
     from sin3dm_b200.optim import FusedAdamWEMA
     from sin3dm_b200.script_util import create_gaussian_diffusion
     L = _lib.lib()
@@ -38,6 +39,8 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
         losses = diff.training_losses(model, x0, t, model_kwargs=kw)
         loss = losses["loss"].mean()
         loss.backward()
+        if bn.world > 1:
+            all_reduce_gradients(opt.grad)        # data parallel: one NCCL all-reduce of the flat gradient buffer per step
         opt.step()
         return loss
 
@@ -112,7 +115,8 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
                     n_gpus=bn.world, steps=K, warmup=Wm, ms_per_step=ms / K, per_rank_ms=[round(v, 3) for v in per_rank],
                     higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="fp16 hi/lo split operands on tcgen05 (fprop, dgrad), fp32 accumulate / norms / reductions / AdamW",
-                    data="synthetic", config=cfg,
+                    data="synthetic", config=dict(cfg, parallelism=f"data parallel x{bn.world}: per-GPU batch {B}, one NCCL all-reduce of the "
+                                                                   "flat 28 MB gradient buffer per step" if bn.world > 1 else "single GPU"),
                     e2e=dict(value=bn.world * n2 / (ms2 / 1e3), unit="iterations/s", h2d_bytes_per_step=x_host.numel() * 4, d2h_bytes_per_step=4,
                              steps=n2, api="training_losses + loss.backward() + FusedAdamWEMA.step(), batch from pinned host memory, loss read back"),
                     gpu_launches=K * (L.s3d_unet_op_count(h) + L.s3d_unet_bwd_op_count(h) + 3),
