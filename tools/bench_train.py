@@ -33,13 +33,13 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
     x_dev = x_host.to(bn.dev)
     kw = dict(H=H, W=W, D=D)
 
-    def step(x0):
+    def step(x0, exchange=True):
         t = torch.randint(0, diff.num_timesteps, (B,), device=bn.dev)
         opt.zero_grad()
         losses = diff.training_losses(model, x0, t, model_kwargs=kw)
         loss = losses["loss"].mean()
         loss.backward()
-        if bn.world > 1:
+        if bn.world > 1 and exchange:
             all_reduce_gradients(opt.grad)        # data parallel: one NCCL all-reduce of the flat gradient buffer per step
         opt.step()
         return loss
@@ -72,7 +72,7 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
         peaks = load_peaks()
         nf, nb = L.s3d_unet_op_count(h), L.s3d_unet_bwd_op_count(h)
         mf, mb = (C.c_float * nf)(), (C.c_float * nb)()
-        step(x_dev)
+        step(x_dev, exchange=False)            # rank 0 alone from here on: no collective
         torch.cuda.synchronize()
         _lib.check(L.s3d_unet_profile_bwd_ops(h, 5, mb, _lib.current_stream_ptr()))
         _lib.check(L.s3d_unet_profile_ops(h, 5, mf, _lib.current_stream_ptr()))
@@ -125,4 +125,5 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
                     cpu_baseline=None, **rec)
         print(json.dumps(line), flush=True)
     if bn.world > 1:
+        bn.barrier()
         bn.dist.destroy_process_group()
