@@ -301,10 +301,11 @@ class Bench:
         v = [float(a.item()) for a in allv]
         return max(v), v
 
-    def model(self, Cc):
+    def model(self, Cc, fresh=False):
         import sin3dm_b200 as s3
         from sin3dm_b200.synthetic import synthetic_state_dict_like
-        if Cc not in self.models:
+        key = ("fresh", Cc) if fresh else Cc        # fresh: a model of its own (the training leg moves its parameters around)
+        if key not in self.models:
             m = s3.TriplaneUNetModelSmall(Cc, 64, Cc, 1, 0, (1, 2), use_scale_shift_norm=True)
             if self.rank == 0:
                 m.load_state_dict(synthetic_state_dict_like(m, 1234))
@@ -313,8 +314,8 @@ class Bench:
                 # one broadcast of the flattened checkpoint over NVLink, no collective in the step loop
                 from sin3dm_b200.dist import broadcast_parameters
                 broadcast_parameters(m, src=0)
-            self.models[Cc] = m
-        return self.models[Cc]
+            self.models[key] = m
+        return self.models[key] if not fresh else self.models.pop(key)
 
     def sampling(self, name, wl, K, Wm, roofline=True):
         """device-timed value, e2e and (rank 0) the per-op roofline leg of one sampling workload"""
@@ -502,6 +503,16 @@ def run_ours(args, wl):
             also["decoder_grid256"] = f"failed: {type(e).__name__}: {e}"
         sps, done, dt, thr, kind = cpu_steps_per_s(wl, 200, 3, budget_s=20.0)
         cpu = dict(value=sps, unit="steps/s", cores=thr, kind=kind, sample=cpu_sample_text(kind, done, wl, args.workload, 3, thr, dt))
+    if not args.no_also:
+        # the training step (BASELINE configs[3], diffusion half): forward + backward + AdamW/EMA at B=32 per GPU, data parallel at N>1
+        try:
+            from tools.bench_train import run_train
+            tr = run_train(bn, args, WORKLOADS["cfg4"], 5, 3, METRIC, config_of, load_peaks, emit=False, profile=bn.world == 1)
+            if tr is not None:
+                also["cfg4_train_b32"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "per_rank_ms", "config", "e2e", "detail",
+                                                             "roofline", "roofline_parts") if k in tr}
+        except Exception as e:
+            also["cfg4_train_b32"] = f"failed: {type(e).__name__}: {e}"
     if bn.rank == 0:
         Cc, (H, W, D), B = wl["C"], wl["HWD"], wl["B"]
         cfg = config_of(args.workload, wl, bn.world)       # identical in both arms

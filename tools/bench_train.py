@@ -16,7 +16,8 @@ import os
 import sys
 
 
-def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
+def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks, emit=True, profile=True):
+    """emit=True: print the JSON line (bench.py --workload cfg4).  emit=False: return it (the default bench adds it to `also`)."""
     torch = bn.torch
     from sin3dm_b200 import _lib
     from sin3dm_b200.dist import all_reduce_gradients
@@ -24,7 +25,7 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
     from sin3dm_b200.script_util import create_gaussian_diffusion
     L = _lib.lib()
     Cc, (H, W, D), B = wl["C"], wl["HWD"], args.batch or wl["B"]
-    model = bn.model(Cc).train()
+    model = bn.model(Cc, fresh=True).train()       # its parameters move into the optimizer's flat buffer: never the sampling model
     opt = FusedAdamWEMA(model.parameters(), lr=5e-4, weight_decay=0.0, ema_rates="0.9999")
     diff = create_gaussian_diffusion(predict_xstart=True, timestep_respacing="")
     g = torch.Generator().manual_seed(bn.rank)
@@ -68,7 +69,7 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
 
     # ---- per-op times: forward list (graph replay with event nodes) and backward list (eager launches with events)
     rec = {}
-    if bn.rank == 0:
+    if bn.rank == 0 and profile:
         peaks = load_peaks()
         nf, nb = L.s3d_unet_op_count(h), L.s3d_unet_bwd_op_count(h)
         mf, mb = (C.c_float * nf)(), (C.c_float * nb)()
@@ -87,7 +88,7 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
                 e["launches"] += 1
                 e["ms"] += msv[i]
                 e["dense_gflop"] += fl.value / 1e9
-        if args.dump_ops:
+        if args.dump_ops and emit:
             with open(args.dump_ops, "w") as f:
                 f.write("\n".join(rows) + f"\nstep in the loop {ms / K * 1e3:.1f} us\n")
         for e in per_kernel.values():
@@ -108,8 +109,9 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
                                    frac=main["frac"], traffic=None, peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
                                    note="dense algorithmic FLOPs of the op (rollout channels counted for dgrad / fprop as the reference executes "
                                         "them; own-channel FLOPs for wgrad) / CUDA-event time of its launches in one step")
+    line = None
     if bn.rank == 0:
-        cfg = config_of(args.workload, dict(wl, B=B), bn.world)
+        cfg = config_of("cfg4", dict(wl, B=B), bn.world)
         fwd_gf = cfg["dense_gflop_per_step"]
         line = dict(metric="triplane diffusion training iterations/sec (train.py diffusion stage, cfg4)", value=value, unit="iterations/s",
                     n_gpus=bn.world, steps=K, warmup=Wm, ms_per_step=ms / K, per_rank_ms=[round(v, 3) for v in per_rank],
@@ -123,7 +125,12 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks):
                     detail=dict(samples_per_s=value * B, fwd_dense_gflop=fwd_gf, train_dense_tflops=3 * fwd_gf * value / bn.world / 1e3,
                                 workspace_mib=round(L.s3d_unet_workspace_bytes(h) / 2 ** 20, 1), last_loss=last_loss),
                     cpu_baseline=None, **rec)
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
+    del opt, model
+    torch.cuda.empty_cache()
     if bn.world > 1:
         bn.barrier()
-        bn.dist.destroy_process_group()
+        if emit:
+            bn.dist.destroy_process_group()
+    return line
