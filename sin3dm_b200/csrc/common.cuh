@@ -79,6 +79,7 @@ constexpr int kTraceSlots = 32;
 struct Trace {
     unsigned long long* buf;   // [max_ctas][2][kTraceSlots]; nullptr: tracing off
     int max_ctas;
+    int lt0;                   // k_conv_tc: the three local tiles lt0 .. lt0+2 of each CTA stamp their phases (S3D_TRACE_LT0)
 };
 __device__ __forceinline__ void trace_mark(const Trace& T, int slot) {
     if (T.buf) {

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
     // uniform registers (a role written under `if (lane == 0)` makes the compiler wrap every TMA / MMA issue in an
     // elect-and-broadcast loop: measured ~117 cycles per tcgen05.mma instead of the 32-64 the tensor core needs)
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    // trace slots: 0 entry, 1 set-up done, 3 first roll patch filled, 22 exit; per local tile lt < 3 at 4 + 6*lt:
+    // trace slots: 0 entry, 1 set-up done, 3 first roll patch filled, 22 exit; per local tile lt0 <= lt < lt0 + 3 (S3D_TRACE_LT0, default 0) at 4 + 6*(lt - lt0):
     // +0 first operands landed, +1 all MMAs issued, +2 epilogue addends of the first batch requested, +3 accumulator complete,
     // +4 epilogue done, +5 A loads issued
     if (threadIdx.x == 0) trace_mark(A.tr, 0);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 }
                 __syncwarp();
             }
-            if (ltp < 3 && lane == 0) trace_mark(A.tr, 4 + 6 * ltp + 5);
+            if (static_cast<unsigned>(ltp - A.tr.lt0) < 3u && lane == 0) trace_mark(A.tr, 4 + 6 * (ltp - A.tr.lt0) + 5);
         }
     } else if (warp == 2 + kEpiWarps) {
         // ===================== TMA producer: B (weight) tiles =====================
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     const int sb = gb % Cfg::kBSlots;
                     ptx::mbar_wait(&fullB[sb], (gb / Cfg::kBSlots) & 1);
                     ptx::tc_fence_after();
-                    if (acc == 0u && lt < 3 && lane == 0) trace_mark(A.tr, 4 + 6 * lt + 0);
+                    if (acc == 0u && static_cast<unsigned>(lt - A.tr.lt0) < 3u && lane == 0) trace_mark(A.tr, 4 + 6 * (lt - A.tr.lt0) + 0);
                     const uint32_t b_base = ptx::smem_u32(smem_b + sb * Cfg::kBSlotBytes);
                     uint32_t off = 0;
                     if (patch && !roll) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             }
             if (ptx::elect_one()) ptx::umma_commit(&tmem_full_bar[as]);     // this tile's accumulators are complete
             __syncwarp();
-            if (lt < 3 && lane == 0) trace_mark(A.tr, 4 + 6 * lt + 1);
+            if (static_cast<unsigned>(lt - A.tr.lt0) < 3u && lane == 0) trace_mark(A.tr, 4 + 6 * (lt - A.tr.lt0) + 1);
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                 const int cls = T.n0 / A.Cout, co0 = T.n0 - cls * A.Cout;
                 float* __restrict__ outp = F.R.T[T.src] + ((static_cast<size_t>(T.b) * 4 + cls) * L + T.p0 + quarter * 32) * A.Cout + co0;
                 ptx::mbar_wait(&tmem_full_bar[as], aph);
-                if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 3);
+                if (et == 0 && static_cast<unsigned>(lt - A.tr.lt0) < 3u) trace_mark(A.tr, 4 + 6 * (lt - A.tr.lt0) + 3);
                 __syncwarp();
                 ptx::tc_fence_after();
                 {
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(F.counters), "r"(1u) : "memory");
                     if (lt == 0) trace_mark(A.tr, 21);
                 }
-                if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 4);
+                if (et == 0 && static_cast<unsigned>(lt - A.tr.lt0) < 3u) trace_mark(A.tr, 4 + 6 * (lt - A.tr.lt0) + 4);
                 continue;
             }
             // ---------- conv tile ----------
@@ -624,9 +624,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
             Addends D;
             float4 add[8];
             fetch(half, D);
-            if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 2);
+            if (et == 0 && static_cast<unsigned>(lt - A.tr.lt0) < 3u) trace_mark(A.tr, 4 + 6 * (lt - A.tr.lt0) + 2);
             ptx::mbar_wait(&tmem_full_bar[as], aph);
-            if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 3);
+            if (et == 0 && static_cast<unsigned>(lt - A.tr.lt0) < 3u) trace_mark(A.tr, 4 + 6 * (lt - A.tr.lt0) + 3);
             __syncwarp();
             ptx::tc_fence_after();
             fold(D, add);
@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv_tc(const __grid_consta
                     }
                 if (A.pool_sink.acc) emit_stats(A.pool_sink, psum, psq);
             }
-            if (et == 0 && lt < 3) trace_mark(A.tr, 4 + 6 * lt + 4);
+            if (et == 0 && static_cast<unsigned>(lt - A.tr.lt0) < 3u) trace_mark(A.tr, 4 + 6 * (lt - A.tr.lt0) + 4);
         }
     }
     ptx::tc_fence_before();

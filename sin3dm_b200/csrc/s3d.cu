@@ -638,6 +638,7 @@ struct PlanBuilder {
         t.buf = dev_alloc<unsigned long long>(P->allocs, n);
         CUDA_TRY(cudaMemset(t.buf, 0, n * sizeof(unsigned long long)));
         t.max_ctas = kTraceCtas;
+        if (const char* e = getenv("S3D_TRACE_LT0")) t.lt0 = atoi(e);
         return t;
     }
     // dense FLOPs of one TriplaneConv 3x3 (+ its 1x1 skip) as the reference executes it: rollout channels counted

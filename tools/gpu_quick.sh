@@ -3,8 +3,8 @@
 tag=${1:-q}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu --maxfail=8 -q > gpurun_out/${tag}_pytest.log 2>&1; tail -4 gpurun_out/${tag}_pytest.log
-python bench.py --steps 200 --warmup 20 --no-cpu-baseline --dump-ops gpurun_out/${tag}_ops_cfg2.txt > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 300 gpurun_out/${tag}_bench.err
-python bench.py --workload cfg4 --steps 10 --warmup 3 --dump-ops gpurun_out/${tag}_train_ops.txt > gpurun_out/${tag}_train.json 2> gpurun_out/${tag}_train.err; tail -c 300 gpurun_out/${tag}_train.err
+timeout 300 python bench.py --steps 200 --warmup 20 --no-cpu-baseline --dump-ops gpurun_out/${tag}_ops_cfg2.txt > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 300 gpurun_out/${tag}_bench.err
+timeout 200 python bench.py --workload cfg4 --steps 10 --warmup 3 --dump-ops gpurun_out/${tag}_train_ops.txt > gpurun_out/${tag}_train.json 2> gpurun_out/${tag}_train.err; tail -c 300 gpurun_out/${tag}_train.err
 python - <<PY
 import json
 try:
