@@ -264,6 +264,10 @@ typedef struct {
     int mlp_impl;                  /* 0: tcgen05 fused MLP; 1: CUDA-core fp32 kernel (cross-check / other MLP shapes) */
     int mlp_kind;                  /* 0: DecoderMLPSkipConcat heads (AutoEncoderGroupSkip, enc_net_type "skip", networks.py:134);
                                       1: plain DecoderMLP heads (AutoEncoderGroupV3, enc_net_type "base", networks.py:21, blocks.py:46) */
+    int net_kind;                  /* 0: AutoEncoderGroupSkip / V3 layout (one ks x ks block per branch; heads geo(1), tex(tex_channels) + sigmoid);
+                                      1: AutoEncoderGroupPBR (enc_net_type "pbr", networks.py:227-331): geo block ks 5, two texture blocks
+                                         ks 3 (the second with input InstanceNorm + SiLU and an identity shortcut), heads geo(1), rgb(3),
+                                         mr(2), normal(3) on the shared texture planes, no sigmoid; tex_channels must be 8, `ks` is unused */
 } s3d_decoder_config;
 
 int s3d_decoder_create(const s3d_decoder_config* cfg, int device, s3d_decoder** out);

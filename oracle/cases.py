@@ -87,6 +87,9 @@ DECODER_CASES = {
     # enc_net_type == "base": AutoEncoderGroupV3 with the plain DecoderMLP heads (networks.py:21-131, blocks.py:46-62)
     "base_v3": dict(spec=dict(mlp_kind="base"), wseed=55, HWD=(18, 12, 22), n=500, aabb=[-0.8, -0.6, -1.0, 0.8, 0.6, 1.0], seed=65,
                     spill=1.1),
+    # enc_net_type == "pbr": AutoEncoderGroupPBR (networks.py:227-331), data_type "sdfpbr" -> 8 texture channels
+    "pbr": dict(spec=dict(net_kind="pbr", tex_channels=8), wseed=56, HWD=(14, 20, 17), n=400, aabb=[-0.9, -1.0, -0.7, 0.9, 1.0, 0.7], seed=66,
+                spill=1.1),
     # decode_grid (model.py:335-349) over sample_grid_points_aabb (utils3d.py:13-25)
     "grid": dict(spec=dict(), wseed=54, HWD=(16, 22, 12), grid=20, aabb=[-0.72, -1.0, -0.55, 0.72, 1.0, 0.55], seed=64),
 }
@@ -141,6 +144,8 @@ ENCODER_CASES = {
     "aligned": dict(spec=dict(), wseed=94, XYZ=(10, 14, 148), seed=98),
     # non-default channel counts (fdim_geo 3, fdim_tex 5, two colour channels): the generic direct-convolution kernel
     "custom": dict(spec=dict(geo_feat_channels=3, tex_feat_channels=5, tex_channels=2), wseed=99, XYZ=(14, 11, 150), seed=100),
+    # AutoEncoderGroupPBR.encode (networks.py:270-287): sdf + 8 material channels in
+    "pbr": dict(spec=dict(net_kind="pbr", tex_channels=8), wseed=101, XYZ=(18, 12, 26), seed=102),
 }
 
 

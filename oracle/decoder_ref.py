@@ -11,6 +11,9 @@ Functional fp32 restatement, over a flat ``state_dict`` with the reference's own
   * ``ShapeAutoEncoder.decode_batch / decode_grid``  reference src/encoding/model.py:319-349
   * ``sample_grid_points_aabb``               reference src/encoding/utils3d.py:13-25
   * ``AutoEncoderGroupSkip.encode``           reference src/encoding/networks.py:164-180
+  * ``AutoEncoderGroupPBR``                   reference src/encoding/networks.py:227-331 (``net_kind="pbr"``: geo block ks 5, two
+                                              texture blocks ks 3 — the second with input_norm / input_act — and the rgb / mr /
+                                              normal heads on the shared texture planes)
 
 Written against plain ``torch.nn.functional`` on CPU tensors.  No module objects, no autograd.
 """
@@ -38,6 +41,7 @@ class DecoderSpec:
     tex_channels: int = 3
     ks: int = 5
     mlp_kind: str = "skip"      # "skip": AutoEncoderGroupSkip / DecoderMLPSkipConcat; "base": AutoEncoderGroupV3 / DecoderMLP (networks.py:21-131)
+    net_kind: str = "skip"      # "pbr": AutoEncoderGroupPBR (networks.py:227-331; tex_channels 8, `ks` unused: 5 for geo, 3 for tex)
 
     @property
     def out_channels(self) -> int:
@@ -49,6 +53,22 @@ def _branches(spec: DecoderSpec):
     if spec.use_tex:
         b.append(("tex", spec.tex_feat_channels, spec.tex_channels))
     return b
+
+
+# AutoEncoderGroupPBR (networks.py:241-257): (block prefix, in channels (None = feat_channel_up), ks, input norm + act) per branch,
+# and (head prefix, branch, outputs) in output order
+def pbr_blocks(spec: DecoderSpec):
+    out = {"geo": [("geo_convs.", spec.geo_feat_channels, 5, False)]}
+    if spec.use_tex:
+        out["tex"] = [("tex_convs.0.", spec.tex_feat_channels, 3, False), ("tex_convs.1.", spec.feat_channel_up, 3, True)]
+    return out
+
+
+def pbr_heads(spec: DecoderSpec):
+    h = [("geo_decoder.", "geo", 1)]
+    if spec.use_tex:
+        h += [("rgb_decoder.", "tex", 3), ("mr_decoder.", "tex", 2), ("normal_decoder.", "tex", 3)]
+    return h
 
 
 def mlp_layer_names(spec: DecoderSpec):
@@ -71,6 +91,34 @@ def param_shapes(spec: DecoderSpec):
     if spec.use_tex:
         out += [("tex_encoder.weight", (spec.tex_feat_channels, spec.tex_channels + 1, 4, 4, 4)),
                 ("tex_encoder.bias", (spec.tex_feat_channels,))]
+    def mlp_shapes(q, oc):
+        o = []
+        first, second = mlp_layer_names(spec)
+        for j, (seq, i) in enumerate(first):
+            cin = up if j == 0 else hid
+            cout = oc if (spec.mlp_kind == "base" and j == len(first) - 1) else hid
+            o += [(q + f"{seq}.{i}.weight", (cout, cin)), (q + f"{seq}.{i}.bias", (cout,))]
+        for j, (seq, i) in enumerate(second):
+            cin = up + hid if j == 0 else hid
+            cout = oc if j == len(second) - 1 else hid
+            o += [(q + f"{seq}.{i}.weight", (cout, cin)), (q + f"{seq}.{i}.bias", (cout,))]
+        return o
+
+    if spec.net_kind == "pbr":
+        blocks, heads = pbr_blocks(spec), pbr_heads(spec)
+        for br in blocks:
+            for p, c, ks, in_norm in blocks[br]:
+                conv = p + ("in_layers.1" if in_norm else "in_layers.0")      # Sequential(SiLU, Conv2d) with input_act (blocks.py:199-204)
+                out += [(conv + ".weight", (3 * up, c, ks, ks)), (conv + ".bias", (3 * up,))]
+                for pl in PLANES:
+                    out += [(p + f"norm_{pl}.weight", (up,)), (p + f"norm_{pl}.bias", (up,))]
+                out += [(p + "out_layers.1.weight", (3 * up, up, ks, ks)), (p + "out_layers.1.bias", (3 * up,))]
+                if c != up:
+                    out += [(p + "shortcut.weight", (3 * up, c, 1, 1)), (p + "shortcut.bias", (3 * up,))]
+            for q, hb, oc in heads:
+                if hb == br:
+                    out += mlp_shapes(q, oc)
+        return out
     for name, c, oc in _branches(spec):
         p = f"{name}_convs."
         out += [(p + "in_layers.0.weight", (3 * up, c, spec.ks, spec.ks)), (p + "in_layers.0.bias", (3 * up,))]
@@ -146,12 +194,19 @@ def decompose_channelwise(h, sizes):
     return h[:, :C, :H, :W], h[:, C:2 * C, :H, :D], h[:, 2 * C:, :W, :D]
 
 
-def group_resnet_block(sd, prefix: str, maps, ks: int):
-    """TriplaneGroupResnetBlock.forward with input_norm=False, input_act=False (blocks.py:232-256):
-    grouped conv ks x ks -> per-plane InstanceNorm -> SiLU -> grouped conv ks x ks, + grouped 1x1 shortcut."""
-    x, sizes = compose_channelwise(maps)
+def group_resnet_block(sd, prefix: str, maps, ks: int, in_norm: bool = False):
+    """TriplaneGroupResnetBlock.forward (blocks.py:232-256): [input_norm + input_act: the block's own per-plane InstanceNorms
+    on the input, then SiLU ->] grouped conv ks x ks -> per-plane InstanceNorm -> SiLU -> grouped conv ks x ks, + grouped 1x1
+    shortcut (identity on the — normed — input when the channel counts agree)."""
     pad = (ks - 1) // 2
-    h = F.conv2d(x, sd[prefix + "in_layers.0.weight"], sd[prefix + "in_layers.0.bias"], padding=pad, groups=3)
+    if in_norm:
+        maps = [F.instance_norm(a, weight=sd[prefix + f"norm_{pl}.weight"], bias=sd[prefix + f"norm_{pl}.bias"], eps=IN_EPS)
+                for a, pl in zip(maps, PLANES)]
+        x, sizes = compose_channelwise(maps)
+        h = F.conv2d(silu(x), sd[prefix + "in_layers.1.weight"], sd[prefix + "in_layers.1.bias"], padding=pad, groups=3)
+    else:
+        x, sizes = compose_channelwise(maps)
+        h = F.conv2d(x, sd[prefix + "in_layers.0.weight"], sd[prefix + "in_layers.0.bias"], padding=pad, groups=3)
     hs = decompose_channelwise(h, sizes)
     hs = [F.instance_norm(a, weight=sd[prefix + f"norm_{pl}.weight"], bias=sd[prefix + f"norm_{pl}.bias"], eps=IN_EPS)
           for a, pl in zip(hs, PLANES)]
@@ -168,6 +223,14 @@ def feature_planes(sd, spec: DecoderSpec, feat_maps):
     """The up-convolved geo / tex planes decode() samples (networks.py:203-213).  They depend on the latent only, so a
     caller may compute them once per latent; the reference recomputes them for every chunk of points."""
     g = spec.geo_feat_channels
+    if spec.net_kind == "pbr":          # networks.py:307-316
+        out = {}
+        for br, blocks in pbr_blocks(spec).items():
+            maps = [fm[:, :g] if br == "geo" else fm[:, g:] for fm in feat_maps]
+            for p, _, ks, in_norm in blocks:
+                maps = group_resnet_block(sd, p, maps, ks, in_norm)
+            out[br] = maps
+        return out
     out = {"geo": group_resnet_block(sd, "geo_convs.", [fm[:, :g] for fm in feat_maps], spec.ks)}
     if spec.use_tex:
         out["tex"] = group_resnet_block(sd, "tex_convs.", [fm[:, g:] for fm in feat_maps], spec.ks)
@@ -210,6 +273,11 @@ def decode(sd, spec: DecoderSpec, pts, feat_maps, aabb=None, planes=None):
     if planes is None:
         planes = feature_planes(sd, spec, feat_maps)
     outs = []
+    if spec.net_kind == "pbr":          # networks.py:318-331: four heads, no sigmoid
+        feat = {}
+        for br in planes:
+            feat[br] = sum(sample_plane(planes[br][i], x[..., list(COORDS[i])]) for i in range(3))
+        return torch.cat([mlp_skip_concat(sd, q, spec, feat[hb]) for q, hb, _ in pbr_heads(spec)], dim=1)
     for name, _, _ in _branches(spec):
         h = 0
         for i in range(3):

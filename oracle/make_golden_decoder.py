@@ -1,6 +1,6 @@
 """Generate tests/golden/decoder_*.npz from the REAL reference decoder (authoring container only).
 
-    python -m oracle.make_golden_decoder        # needs /root/reference/src (read-only import)
+    python -m oracle.make_golden_decoder [case ...]     # needs /root/reference/src (read-only import); no names = every case
 
 ``encoding.networks.AutoEncoderGroupSkip`` is imported unmodified and fed ``oracle.decoder_ref.synthetic_state_dict``
 weights; ``decode_batch`` / ``decode_grid`` live in ``encoding/model.py``, which does not import here (tensorboardX,
@@ -36,13 +36,16 @@ def ref_grid_fn():
 
 def main():
     sys.path.insert(0, REF)
-    from encoding.networks import AutoEncoderGroupSkip, AutoEncoderGroupV3
+    from encoding.networks import AutoEncoderGroupPBR, AutoEncoderGroupSkip, AutoEncoderGroupV3
     grid_fn = ref_grid_fn()
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, case in DECODER_CASES.items():
+        if only and name not in only:
+            continue
         spec = de.DecoderSpec(**case["spec"])
         sd = de.synthetic_state_dict(spec, case["wseed"])
-        cls = AutoEncoderGroupV3 if spec.mlp_kind == "base" else AutoEncoderGroupSkip
+        cls = AutoEncoderGroupPBR if spec.net_kind == "pbr" else (AutoEncoderGroupV3 if spec.mlp_kind == "base" else AutoEncoderGroupSkip)
         with contextlib.redirect_stdout(io.StringIO()):
             net = cls(spec.geo_feat_channels, spec.tex_feat_channels, spec.feat_channel_up,
                       spec.mlp_hidden_channels, spec.mlp_hidden_layers, use_tex=spec.use_tex,
@@ -85,10 +88,12 @@ def main():
 
     # ---- encoder half (networks.py:164-180)
     for name, case in ENCODER_CASES.items():
+        if only and ("enc_" + name) not in only:
+            continue
         spec = de.DecoderSpec(**case["spec"])
         sd = de.synthetic_state_dict(spec, case["wseed"])
         with contextlib.redirect_stdout(io.StringIO()):
-            net = AutoEncoderGroupSkip(spec.geo_feat_channels, spec.tex_feat_channels, spec.feat_channel_up,
+            net = (AutoEncoderGroupPBR if spec.net_kind == "pbr" else AutoEncoderGroupSkip)(spec.geo_feat_channels, spec.tex_feat_channels, spec.feat_channel_up,
                                        spec.mlp_hidden_channels, spec.mlp_hidden_layers, use_tex=spec.use_tex,
                                        tex_channels=spec.tex_channels)
         net.load_state_dict(sd)

@@ -56,7 +56,7 @@ class DecoderConfig(C.Structure):
     _fields_ = [("geo_feat_channels", C.c_int), ("tex_feat_channels", C.c_int), ("feat_channel_up", C.c_int),
                 ("mlp_hidden_channels", C.c_int), ("mlp_hidden_layers", C.c_int), ("use_tex", C.c_int),
                 ("tex_channels", C.c_int), ("ks", C.c_int), ("precision", C.c_int), ("mlp_impl", C.c_int),
-                ("mlp_kind", C.c_int)]
+                ("mlp_kind", C.c_int), ("net_kind", C.c_int)]
 
 
 # every symbol include/sin3dm_b200.h declares: (restype, argtypes)

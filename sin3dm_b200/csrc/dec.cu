@@ -34,10 +34,23 @@ struct DTensor {
     }
 };
 
-struct Branch {
-    int c0 = 0, cin = 0, n_out = 0;
+// One TriplaneGroupResnetBlock (blocks.py:189-256) of a feature branch
+struct ConvBlk {
+    std::string prefix;                     // "geo_convs." / "tex_convs." / "tex_convs.0." ...
+    int cin = 0, ks = 0;
+    bool in_norm = false;                   // input_norm + input_act (PBR's second texture block): identity shortcut on the normed input
     float *w_in = nullptr, *b_in = nullptr, *w_out = nullptr, *b_out = nullptr, *ws = nullptr, *bs = nullptr;
     float *gamma = nullptr, *beta = nullptr;
+};
+// feature branch: geo (latent channels [0, geo)) or tex (latent channels [geo, geo + tex)); its planes are F[..][b * 64 ...]
+struct Branch {
+    int c0 = 0, cin = 0;
+    std::vector<ConvBlk> blocks;
+};
+// One decoder MLP (DecoderMLPSkipConcat / DecoderMLP) reading the planes of branch `feat`
+struct Head {
+    std::string prefix;                     // "geo_decoder." ...
+    int feat = 0, n_out = 1, out_col = 0, sigmoid = 0;
     DecMlpF32 mf{};                         // CUDA-core kernel: transposed fp32 weights
     uint16_t* w16[kDecLayers] = {};         // tensor-core kernel: [2][256][K] fp16 (hi, lo) of scale * W
     float inv_scale[kDecLayers] = {};
@@ -55,11 +68,14 @@ struct s3d_decoder {
     bool finalized = false, tc_ok = false;
     std::vector<void*> owned;
     Branch br[2];
+    std::vector<Head> heads;                // evaluation / output order
     int nb = 1, n_sm = 148;
+    int out_channels = 1;
     // feature planes of the current latent
     std::vector<void*> plane_owned;
     float* F[3] = {nullptr, nullptr, nullptr};
     float* h1[3] = {nullptr, nullptr, nullptr};
+    float* T1[3] = {nullptr, nullptr, nullptr};       // output of a branch's first block when a second one follows (PBR)
     double* partial = nullptr;
     float* coef = nullptr;
     int rows[3] = {0, 0, 0}, cols[3] = {0, 0, 0}, max_strips = 0;
@@ -104,9 +120,62 @@ std::vector<LinName> mlp_layers(const s3d_decoder_config& c, const std::string& 
     return v;
 }
 
-// state_dict() order of the reference module (networks.py:134-162)
+// Blocks and heads of the configured network:
+//   net_kind 0  AutoEncoderGroupSkip / V3 (networks.py:134-162, 21-60): one ks x ks block per branch, heads geo(1) and tex(tex_channels, sigmoid)
+//   net_kind 1  AutoEncoderGroupPBR (networks.py:227-262): geo block ks 5; tex blocks ks 3 (plain) + ks 3 (input norm + act);
+//               heads geo(1), rgb(3), mr(2), normal(3), no sigmoid
+void describe(s3d_decoder* d) {
+    const auto& c = d->cfg;
+    d->br[0] = Branch{};
+    d->br[1] = Branch{};
+    d->heads.clear();
+    d->br[0].c0 = 0;
+    d->br[0].cin = c.geo_feat_channels;
+    d->br[1].c0 = c.geo_feat_channels;
+    d->br[1].cin = c.tex_feat_channels;
+    auto blk = [](const std::string& p, int cin, int ks, bool in_norm) {
+        ConvBlk b;
+        b.prefix = p;
+        b.cin = cin;
+        b.ks = ks;
+        b.in_norm = in_norm;
+        return b;
+    };
+    auto head = [](const std::string& p, int feat, int n_out, int col, int sig) {
+        Head h;
+        h.prefix = p;
+        h.feat = feat;
+        h.n_out = n_out;
+        h.out_col = col;
+        h.sigmoid = sig;
+        return h;
+    };
+    if (c.net_kind == 1) {
+        d->br[0].blocks.push_back(blk("geo_convs.", c.geo_feat_channels, 5, false));
+        d->heads.push_back(head("geo_decoder.", 0, 1, 0, 0));
+        if (c.use_tex) {
+            d->br[1].blocks.push_back(blk("tex_convs.0.", c.tex_feat_channels, 3, false));
+            d->br[1].blocks.push_back(blk("tex_convs.1.", c.feat_channel_up, 3, true));
+            d->heads.push_back(head("rgb_decoder.", 1, 3, 1, 0));
+            d->heads.push_back(head("mr_decoder.", 1, 2, 4, 0));
+            d->heads.push_back(head("normal_decoder.", 1, 3, 6, 0));
+        }
+        d->out_channels = c.use_tex ? 9 : 1;
+    } else {
+        d->br[0].blocks.push_back(blk("geo_convs.", c.geo_feat_channels, c.ks, false));
+        d->heads.push_back(head("geo_decoder.", 0, 1, 0, 0));
+        if (c.use_tex) {
+            d->br[1].blocks.push_back(blk("tex_convs.", c.tex_feat_channels, c.ks, false));
+            d->heads.push_back(head("tex_decoder.", 1, c.tex_channels, 1, 1));
+        }
+        d->out_channels = 1 + (c.use_tex ? c.tex_channels : 0);
+    }
+}
+
+// state_dict() order of the reference module (networks.py:134-162 / 227-262): encoders, then per branch its blocks followed by its heads
 void build_structure(s3d_decoder* d) {
     const auto& c = d->cfg;
+    describe(d);
     add_tensor(d, "aabb", {6}, false);
     add_tensor(d, "geo_encoder.weight", {c.geo_feat_channels, 1, 4, 4, 4}, false);
     add_tensor(d, "geo_encoder.bias", {c.geo_feat_channels}, false);
@@ -116,23 +185,30 @@ void build_structure(s3d_decoder* d) {
     }
     const int up = c.feat_channel_up;
     for (int b = 0; b < d->nb; ++b) {
-        const std::string n = b == 0 ? "geo" : "tex";
-        const int cin = b == 0 ? c.geo_feat_channels : c.tex_feat_channels, n_out = b == 0 ? 1 : c.tex_channels;
-        const std::string p = n + "_convs.";
-        add_tensor(d, p + "in_layers.0.weight", {3 * up, cin, c.ks, c.ks});
-        add_tensor(d, p + "in_layers.0.bias", {3 * up});
-        for (int pl = 0; pl < 3; ++pl) {
-            add_tensor(d, p + "norm_" + kPlaneName[pl] + ".weight", {up});
-            add_tensor(d, p + "norm_" + kPlaneName[pl] + ".bias", {up});
+        for (const ConvBlk& K : d->br[b].blocks) {
+            const std::string& p = K.prefix;
+            // in_layers = Sequential(conv) without input activation, Sequential(SiLU, conv) with it (blocks.py:199-216)
+            const std::string in_conv = p + (K.in_norm ? "in_layers.1" : "in_layers.0");
+            add_tensor(d, in_conv + ".weight", {3 * up, K.cin, K.ks, K.ks});
+            add_tensor(d, in_conv + ".bias", {3 * up});
+            for (int pl = 0; pl < 3; ++pl) {
+                add_tensor(d, p + "norm_" + kPlaneName[pl] + ".weight", {up});
+                add_tensor(d, p + "norm_" + kPlaneName[pl] + ".bias", {up});
+            }
+            add_tensor(d, p + "out_layers.1.weight", {3 * up, up, K.ks, K.ks});
+            add_tensor(d, p + "out_layers.1.bias", {3 * up});
+            if (!K.in_norm) {
+                add_tensor(d, p + "shortcut.weight", {3 * up, K.cin, 1, 1});
+                add_tensor(d, p + "shortcut.bias", {3 * up});
+            }
         }
-        add_tensor(d, p + "out_layers.1.weight", {3 * up, up, c.ks, c.ks});
-        add_tensor(d, p + "out_layers.1.bias", {3 * up});
-        add_tensor(d, p + "shortcut.weight", {3 * up, cin, 1, 1});
-        add_tensor(d, p + "shortcut.bias", {3 * up});
-        int nf;
-        for (const auto& l : mlp_layers(c, n + "_decoder.", n_out, &nf)) {
-            add_tensor(d, l.key + ".weight", {l.cout, l.cin});
-            add_tensor(d, l.key + ".bias", {l.cout});
+        for (const Head& Hd : d->heads) {
+            if (Hd.feat != b) continue;
+            int nf;
+            for (const auto& l : mlp_layers(c, Hd.prefix, Hd.n_out, &nf)) {
+                add_tensor(d, l.key + ".weight", {l.cout, l.cin});
+                add_tensor(d, l.key + ".bias", {l.cout});
+            }
         }
     }
 }
@@ -190,32 +266,34 @@ void finalize(s3d_decoder* d) {
     for (void* p : d->owned) cudaFree(p);
     d->owned.clear();
     for (auto& p : d->enc_w) p = nullptr;
-    d->tc_ok = up == kDecUp && hid == kDecHid && c.mlp_hidden_layers == 4 && c.tex_channels <= 4;
+    d->tc_ok = up == kDecUp && hid == kDecHid && c.mlp_hidden_layers == 4;
+    for (const Head& Hd : d->heads) d->tc_ok = d->tc_ok && Hd.n_out <= 4;
     for (int b = 0; b < d->nb; ++b) {
-        Branch& B = d->br[b];
-        const std::string n = b == 0 ? "geo" : "tex";
-        B.cin = b == 0 ? c.geo_feat_channels : c.tex_feat_channels;
-        B.c0 = b == 0 ? 0 : c.geo_feat_channels;
-        B.n_out = b == 0 ? 1 : c.tex_channels;
-        const std::string p = n + "_convs.";
-        B.w_in = dev_upload(d->owned, pack_gconv(T_(d, p + "in_layers.0.weight").host, up, B.cin, c.ks));
-        B.b_in = dev_upload(d->owned, T_(d, p + "in_layers.0.bias").host);
-        B.w_out = dev_upload(d->owned, pack_gconv(T_(d, p + "out_layers.1.weight").host, up, up, c.ks));
-        B.b_out = dev_upload(d->owned, T_(d, p + "out_layers.1.bias").host);
-        B.ws = dev_upload(d->owned, pack_gconv(T_(d, p + "shortcut.weight").host, up, B.cin, 1));
-        B.bs = dev_upload(d->owned, T_(d, p + "shortcut.bias").host);
-        std::vector<float> g(3 * up), be(3 * up);
-        for (int pl = 0; pl < 3; ++pl) {
-            const auto& gw = T_(d, p + "norm_" + kPlaneName[pl] + ".weight").host;
-            const auto& gb = T_(d, p + "norm_" + kPlaneName[pl] + ".bias").host;
-            std::copy(gw.begin(), gw.end(), g.begin() + pl * up);
-            std::copy(gb.begin(), gb.end(), be.begin() + pl * up);
+        for (ConvBlk& K : d->br[b].blocks) {
+            const std::string& p = K.prefix;
+            const std::string in_conv = p + (K.in_norm ? "in_layers.1" : "in_layers.0");
+            K.w_in = dev_upload(d->owned, pack_gconv(T_(d, in_conv + ".weight").host, up, K.cin, K.ks));
+            K.b_in = dev_upload(d->owned, T_(d, in_conv + ".bias").host);
+            K.w_out = dev_upload(d->owned, pack_gconv(T_(d, p + "out_layers.1.weight").host, up, up, K.ks));
+            K.b_out = dev_upload(d->owned, T_(d, p + "out_layers.1.bias").host);
+            if (!K.in_norm) {
+                K.ws = dev_upload(d->owned, pack_gconv(T_(d, p + "shortcut.weight").host, up, K.cin, 1));
+                K.bs = dev_upload(d->owned, T_(d, p + "shortcut.bias").host);
+            }
+            std::vector<float> g(3 * up), be(3 * up);
+            for (int pl = 0; pl < 3; ++pl) {
+                const auto& gw = T_(d, p + "norm_" + kPlaneName[pl] + ".weight").host;
+                const auto& gb = T_(d, p + "norm_" + kPlaneName[pl] + ".bias").host;
+                std::copy(gw.begin(), gw.end(), g.begin() + pl * up);
+                std::copy(gb.begin(), gb.end(), be.begin() + pl * up);
+            }
+            K.gamma = dev_upload(d->owned, g);
+            K.beta = dev_upload(d->owned, be);
         }
-        B.gamma = dev_upload(d->owned, g);
-        B.beta = dev_upload(d->owned, be);
-
+    }
+    for (Head& B : d->heads) {
         int nf;
-        const auto layers = mlp_layers(c, n + "_decoder.", B.n_out, &nf);
+        const auto layers = mlp_layers(c, B.prefix, B.n_out, &nf);
         S3D_CHECK(layers.size() <= 8, "too many MLP layers");
         B.mf = DecMlpF32{};
         B.mf.n_first = nf;
@@ -240,17 +318,17 @@ void finalize(s3d_decoder* d) {
                 // power-of-two scale: the largest weight lands in [2048, 4096), so the (unscaled) lo halves of all but
                 // vanishing weights stay in fp16 normal range
                 const int e = mx > 0.f ? static_cast<int>(std::floor(std::log2(4096.0 / mx))) : 0;
-                const float s = std::ldexp(1.f, std::min(std::max(e, -20), 30));
+                const float sc = std::ldexp(1.f, std::min(std::max(e, -20), 30));
                 std::vector<uint16_t> w16(static_cast<size_t>(2) * kDecHid * K);
                 for (int nn = 0; nn < kDecHid; ++nn)
                     for (int k = 0; k < K; ++k) {
-                        const float v = std::min(std::max(w[static_cast<size_t>(nn) * K + k] * s, -65504.f), 65504.f);
+                        const float v = std::min(std::max(w[static_cast<size_t>(nn) * K + k] * sc, -65504.f), 65504.f);
                         const uint16_t hi = f2h_bits(v);
                         w16[static_cast<size_t>(nn) * K + k] = hi;
                         w16[(static_cast<size_t>(kDecHid) + nn) * K + k] = f2h_bits(v - h2f(hi));
                     }
                 B.w16[l] = dev_upload(d->owned, w16);
-                B.inv_scale[l] = 1.f / s;
+                B.inv_scale[l] = 1.f / sc;
                 B.bias_h[l] = T_(d, layers[l].key + ".bias").host;
                 S3D_CHECK(B.bias_h[l].size() == static_cast<size_t>(kDecHid), "hidden bias size");
                 const uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(kDecHid), 2};
@@ -271,6 +349,8 @@ void set_planes(s3d_decoder* d, const float* xy, const float* xz, const float* y
     S3D_CHECK(H > 0 && W > 0 && D > 0, "plane sizes must be positive");
     const int rows[3] = {H, H, W}, cols[3] = {W, D, D};
     const int CF = kDecUp * d->nb;
+    bool two_blocks = false;
+    for (int b = 0; b < d->nb; ++b) two_blocks = two_blocks || d->br[b].blocks.size() > 1;
     bool same = d->F[0] != nullptr;
     for (int p = 0; p < 3; ++p) same = same && rows[p] == d->rows[p] && cols[p] == d->cols[p];
     if (!same) {
@@ -283,6 +363,7 @@ void set_planes(s3d_decoder* d, const float* xy, const float* xz, const float* y
             const size_t n = static_cast<size_t>(rows[p]) * cols[p];
             d->F[p] = dev_alloc<float>(d->plane_owned, n * CF);
             d->h1[p] = dev_alloc<float>(d->plane_owned, n * kDecUp);
+            d->T1[p] = two_blocks ? dev_alloc<float>(d->plane_owned, n * kDecUp) : nullptr;
             mx = std::max(mx, static_cast<int>((n + kDecStripPix - 1) / kDecStripPix));
         }
         d->max_strips = mx;
@@ -290,53 +371,72 @@ void set_planes(s3d_decoder* d, const float* xy, const float* xz, const float* y
         d->coef = dev_alloc<float>(d->plane_owned, 3 * 64 * 2);
     }
     const float* x[3] = {xy, xz, yz};
-    const int ks = d->cfg.ks, hw = kDecTile + ks - 1, hstride = (hw * hw) | 1;
+    const int n0 = rows[0] * cols[0], n1 = rows[1] * cols[1], n2 = rows[2] * cols[2];
     d->last_launches = 0;
+    // InstanceNorm statistics of a [rows][cols][64] tensor -> per-channel (scale, shift) with the block's affine parameters
+    auto in_coef = [&](float* const t[3], const ConvBlk& K) {
+        launch_plain(k_dec_in_stats, dim3(d->max_strips, 3), dim3(256), 0, st, t[0], t[1], t[2], n0, n1, n2, d->partial, d->max_strips);
+        launch_plain(k_dec_in_finalize, dim3(3), dim3(64), 0, st, d->partial, d->max_strips, n0, n1, n2, K.gamma, K.beta, d->coef);
+        d->last_launches += 2;
+    };
     for (int b = 0; b < d->nb; ++b) {
         const Branch& B = d->br[b];
-        DecConvArgs a{};
-        int ts = 0;
-        for (int p = 0; p < 3; ++p) {
-            a.rows[p] = rows[p];
-            a.cols[p] = cols[p];
-            a.tiles_x[p] = (cols[p] + kDecTile - 1) / kDecTile;
-            a.tile_start[p] = ts;
-            ts += a.tiles_x[p] * ((rows[p] + kDecTile - 1) / kDecTile);
-            a.h1[p] = d->h1[p];
-            a.F[p] = d->F[p];
+        for (size_t bi = 0; bi < B.blocks.size(); ++bi) {
+            const ConvBlk& K = B.blocks[bi];
+            const bool last_block = bi + 1 == B.blocks.size();
+            const int ks = K.ks, hw = kDecTile + ks - 1, hstride = (hw * hw) | 1;
+            DecConvArgs a{};
+            int ts = 0;
+            for (int p = 0; p < 3; ++p) {
+                a.rows[p] = rows[p];
+                a.cols[p] = cols[p];
+                a.tiles_x[p] = (cols[p] + kDecTile - 1) / kDecTile;
+                a.tile_start[p] = ts;
+                ts += a.tiles_x[p] * ((rows[p] + kDecTile - 1) / kDecTile);
+                a.h1[p] = d->h1[p];
+                a.F[p] = last_block ? d->F[p] : d->T1[p];          // the block's output: the branch's slice of F, or the next block's input
+            }
+            a.tile_start[3] = ts;
+            a.CF = last_block ? CF : kDecUp;
+            a.foff = last_block ? b * kDecUp : 0;
+            a.ks = ks;
+            const size_t sm1 = static_cast<size_t>(kDecUp) * (hstride + 64) * sizeof(float);
+            DecConvArgs a0 = a;
+            a0.w = K.w_in;
+            a0.bias = K.b_in;
+            if (!K.in_norm) {
+                // conv ks x ks (c -> 64) on the raw latent + 1x1 shortcut
+                S3D_CHECK(bi == 0, "a block without input norm reads the latent");
+                for (int p = 0; p < 3; ++p) a0.x[p] = x[p];
+                a0.c0 = B.c0;
+                a0.cin = K.cin;
+                a0.ws = K.ws;
+                a0.bs = K.bs;
+                const size_t sm0 = static_cast<size_t>(K.cin) * (hstride + 64) * sizeof(float);
+                CUDA_TRY(cudaFuncSetAttribute(k_dec_conv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm0)));
+                launch_plain(k_dec_conv<0>, dim3(ts), dim3(256), sm0, st, a0);
+            } else {
+                // input InstanceNorm (the block's own norm_* modules, blocks.py:233-234) + SiLU + conv; identity shortcut on the normed input
+                S3D_CHECK(bi > 0 && K.cin == kDecUp, "a block with input norm follows another block");
+                in_coef(d->T1, K);
+                for (int p = 0; p < 3; ++p) a0.x[p] = d->T1[p];
+                a0.cin = kDecUp;
+                a0.coef = d->coef;
+                CUDA_TRY(cudaFuncSetAttribute(k_dec_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm1)));
+                launch_plain(k_dec_conv<2>, dim3(ts), dim3(256), sm1, st, a0);
+            }
+            // norm + SiLU + conv ks x ks (64 -> 64), added onto the shortcut
+            in_coef(d->h1, K);
+            DecConvArgs a1 = a;
+            for (int p = 0; p < 3; ++p) a1.x[p] = d->h1[p];
+            a1.cin = kDecUp;
+            a1.w = K.w_out;
+            a1.bias = K.b_out;
+            a1.coef = d->coef;
+            CUDA_TRY(cudaFuncSetAttribute(k_dec_conv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm1)));
+            launch_plain(k_dec_conv<1>, dim3(ts), dim3(256), sm1, st, a1);
+            d->last_launches += 2;
         }
-        a.tile_start[3] = ts;
-        a.CF = CF;
-        a.foff = b * kDecUp;
-        a.ks = ks;
-        // conv ks x ks (c -> 64) + 1x1 shortcut
-        DecConvArgs a0 = a;
-        for (int p = 0; p < 3; ++p) a0.x[p] = x[p];
-        a0.c0 = B.c0;
-        a0.cin = B.cin;
-        a0.w = B.w_in;
-        a0.bias = B.b_in;
-        a0.ws = B.ws;
-        a0.bs = B.bs;
-        const size_t sm0 = static_cast<size_t>(B.cin) * (hstride + 64) * sizeof(float);
-        CUDA_TRY(cudaFuncSetAttribute(k_dec_conv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm0)));
-        launch_plain(k_dec_conv<0>, dim3(ts), dim3(256), sm0, st, a0);
-        // InstanceNorm statistics of h1
-        const int n0 = rows[0] * cols[0], n1 = rows[1] * cols[1], n2 = rows[2] * cols[2];
-        launch_plain(k_dec_in_stats, dim3(d->max_strips, 3), dim3(256), 0, st, d->h1[0], d->h1[1], d->h1[2], n0, n1, n2, d->partial,
-               d->max_strips);
-        launch_plain(k_dec_in_finalize, dim3(3), dim3(64), 0, st, d->partial, d->max_strips, n0, n1, n2, B.gamma, B.beta, d->coef);
-        // norm + SiLU + conv ks x ks (64 -> 64), added onto the shortcut
-        DecConvArgs a1 = a;
-        for (int p = 0; p < 3; ++p) a1.x[p] = d->h1[p];
-        a1.cin = kDecUp;
-        a1.w = B.w_out;
-        a1.bias = B.b_out;
-        a1.coef = d->coef;
-        const size_t sm1 = static_cast<size_t>(kDecUp) * (hstride + 64) * sizeof(float);
-        CUDA_TRY(cudaFuncSetAttribute(k_dec_conv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm1)));
-        launch_plain(k_dec_conv<1>, dim3(ts), dim3(256), sm1, st, a1);
-        d->last_launches += 4;
     }
     d->planes_set = true;
 }
@@ -352,52 +452,64 @@ void decode(s3d_decoder* d, const DecPoints& P, int clamp_tex, float* out, cudaS
     }
     a.G.CF = kDecUp * d->nb;
     a.P = P;
-    a.nb = d->nb;
-    a.oc = 1 + (d->cfg.use_tex ? d->cfg.tex_channels : 0);
+    a.oc = d->out_channels;
     a.tex_channels = d->cfg.tex_channels;
     a.clamp_tex = clamp_tex;
     a.out = out;
-    if (d->cfg.mlp_impl == 1) {
-        const int hid = d->cfg.mlp_hidden_channels;
-        const size_t sm = (static_cast<size_t>(32) * kDecUp + static_cast<size_t>(64) * hid) * sizeof(float);
-        CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_ffma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
-        const long long blocks = (P.n + 31) / 32;
-        S3D_CHECK(blocks < (1LL << 31), "too many points for one launch");
-        launch_plain(k_dec_mlp_ffma, dim3(static_cast<unsigned>(blocks)), dim3(256), sm, st, a, d->br[0].mf, d->br[d->nb - 1].mf, hid);
-        d->last_launches = 1;
-        return;
-    }
-    S3D_CHECK(d->tc_ok, "the tensor-core decoder is specialised for feat_channel_up=64, hidden_dim=256, n_hidden_layers=4 "
-                        "(the reference defaults); use mlp_impl=1 for other shapes");
-    DecTcMaps maps{};
-    DecTcArgs ta{};
-    static thread_local DecTcConst tc;          // 18.5 KB: kept off the stack
-    std::memset(&tc, 0, sizeof(tc));
-    ta.D = a;
-    for (int b = 0; b < d->nb; ++b) {
-        const Branch& B = d->br[b];
-        for (int l = 0; l < kDecLayers; ++l) {
-            maps.w[b][l] = B.maps[l];
-            ta.inv_scale[b][l] = B.inv_scale[l];
-            std::copy(B.bias_h[l].begin(), B.bias_h[l].end(), tc.bias[b][l]);
+    if (d->cfg.mlp_impl == 0)
+        S3D_CHECK(d->tc_ok, "the tensor-core decoder is specialised for feat_channel_up=64, hidden_dim=256, n_hidden_layers=4 "
+                            "(the reference defaults); use mlp_impl=1 for other shapes");
+    d->last_launches = 0;
+    // the heads two at a time: (geo, tex) for AutoEncoderGroupSkip / V3, (geo, rgb) then (mr, normal) for AutoEncoderGroupPBR
+    for (size_t h0 = 0; h0 < d->heads.size(); h0 += 2) {
+        const int nh = static_cast<int>(std::min<size_t>(2, d->heads.size() - h0));
+        const Head* Hh[2] = {&d->heads[h0], &d->heads[h0 + nh - 1]};
+        a.nb = nh;
+        for (int b = 0; b < nh; ++b) {
+            a.feat_off[b] = Hh[b]->feat * kDecUp;
+            a.out_col[b] = Hh[b]->out_col;
+            a.sigmoid[b] = Hh[b]->sigmoid;
         }
-        std::copy(B.w_last_h.begin(), B.w_last_h.end(), &tc.w_last[b][0][0]);
-        std::copy(B.b_last_h.begin(), B.b_last_h.end(), tc.b_last[b]);
-        ta.n_out[b] = B.n_out;
+        if (d->cfg.mlp_impl == 1) {
+            const int hid = d->cfg.mlp_hidden_channels;
+            const size_t sm = (static_cast<size_t>(32) * kDecUp + static_cast<size_t>(64) * hid) * sizeof(float);
+            CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_ffma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
+            const long long blocks = (P.n + 31) / 32;
+            S3D_CHECK(blocks < (1LL << 31), "too many points for one launch");
+            launch_plain(k_dec_mlp_ffma, dim3(static_cast<unsigned>(blocks)), dim3(256), sm, st, a, Hh[0]->mf, Hh[1]->mf, hid);
+            ++d->last_launches;
+            continue;
+        }
+        DecTcMaps maps{};
+        DecTcArgs ta{};
+        static thread_local DecTcConst tc;          // 18.5 KB: kept off the stack
+        std::memset(&tc, 0, sizeof(tc));
+        ta.D = a;
+        for (int b = 0; b < nh; ++b) {
+            const Head& B = *Hh[b];
+            for (int l = 0; l < kDecLayers; ++l) {
+                maps.w[b][l] = B.maps[l];
+                ta.inv_scale[b][l] = B.inv_scale[l];
+                std::copy(B.bias_h[l].begin(), B.bias_h[l].end(), tc.bias[b][l]);
+            }
+            std::copy(B.w_last_h.begin(), B.w_last_h.end(), &tc.w_last[b][0][0]);
+            std::copy(B.b_last_h.begin(), B.b_last_h.end(), tc.b_last[b]);
+            ta.n_out[b] = B.n_out;
+        }
+        ta.skip = d->cfg.mlp_kind == 0 ? 1 : 0;
+        ta.n_tiles = (P.n + kDecPts - 1) / kDecPts;
+        const unsigned grid = static_cast<unsigned>(std::min<long long>(ta.n_tiles, d->n_sm));
+        if (d->cfg.precision == 1) {
+            using Cfg = DecTcCfg<1>;
+            CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+            launch_plain(k_dec_mlp_tc<1>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
+        } else {
+            using Cfg = DecTcCfg<3>;
+            CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+            launch_plain(k_dec_mlp_tc<3>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
+        }
+        ++d->last_launches;
     }
-    ta.skip = d->cfg.mlp_kind == 0 ? 1 : 0;
-    ta.n_tiles = (P.n + kDecPts - 1) / kDecPts;
-    const unsigned grid = static_cast<unsigned>(std::min<long long>(ta.n_tiles, d->n_sm));
-    if (d->cfg.precision == 1) {
-        using Cfg = DecTcCfg<1>;
-        CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        launch_plain(k_dec_mlp_tc<1>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
-    } else {
-        using Cfg = DecTcCfg<3>;
-        CUDA_TRY(cudaFuncSetAttribute(k_dec_mlp_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        launch_plain(k_dec_mlp_tc<3>, dim3(grid), dim3(kDecTcThreads), Cfg::kSmemBytes, st, maps, ta, tc);
-    }
-    d->last_launches = 1;
 }
 
 template <int GEO, int TEX, int CT>
@@ -522,6 +634,10 @@ int s3d_decoder_create(const s3d_decoder_config* cfg, int device, s3d_decoder** 
     S3D_CHECK(cfg->tex_channels >= 1 && cfg->tex_channels <= 8, "tex_channels out of range");
     S3D_CHECK(cfg->precision == 1 || cfg->precision == 3, "precision must be 1 or 3");
     S3D_CHECK(cfg->mlp_impl == 0 || cfg->mlp_impl == 1, "mlp_impl must be 0 or 1");
+    S3D_CHECK(cfg->mlp_kind == 0 || cfg->mlp_kind == 1, "mlp_kind must be 0 or 1");
+    S3D_CHECK(cfg->net_kind == 0 || cfg->net_kind == 1, "net_kind must be 0 or 1");
+    S3D_CHECK(cfg->net_kind == 0 || (cfg->mlp_kind == 0 && (!cfg->use_tex || cfg->tex_channels == 8)),
+              "AutoEncoderGroupPBR has skip-concat heads and 8 texture channels (rgb 3, metallic-roughness 2, normal 3)");
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     S3D_CHECK(device >= 0 && device < ndev, "no such CUDA device");

@@ -36,14 +36,14 @@ struct DecPlanes {
 // grid (tiles of the three planes), block 256 = one 16 x 16 pixel tile, thread = pixel, 64 accumulators.
 // ------------------------------------------------------------------------------------------------------------------
 struct DecConvArgs {
-    const float* x[3];       // MODE 0: latent plane [c_total][rows][cols]; MODE 1: h1 [rows][cols][64]
+    const float* x[3];       // MODE 0: latent plane [c_total][rows][cols]; MODE 1 / 2: [rows][cols][64]
     int c0, cin;             // MODE 0: first channel / channel count of this branch inside the latent
     const float* w;          // [3 planes][ks*ks][cin][64]
     const float* bias;       // [3][64]
     const float* ws;         // MODE 0: shortcut [3][cin][64]   (nullptr: identity shortcut, cin == 64)
     const float* bs;         // MODE 0: shortcut bias [3][64]
-    const float* coef;       // MODE 1: [3][64][2] = (gamma * rstd, beta - mean * gamma * rstd)
-    float* h1[3];            // MODE 0 output
+    const float* coef;       // MODE 1 / 2: [3][64][2] = (gamma * rstd, beta - mean * gamma * rstd) of the input
+    float* h1[3];            // MODE 0 / 2 output
     float* F[3];             // feature plane [rows][cols][CF]
     int CF, foff;            // channel stride / channel offset of this branch in F
     int rows[3], cols[3];
@@ -51,6 +51,10 @@ struct DecConvArgs {
     int ks;
 };
 
+// MODE 0: in_layers conv of a block without input norm / activation + its 1x1 shortcut (raw latent in).
+// MODE 1: InstanceNorm + SiLU + out_layers conv, added onto the shortcut already in F.
+// MODE 2: in_layers of a block WITH input norm and activation (blocks.py:199-204, 233-236; AutoEncoderGroupPBR's second texture
+//         block): h1 = conv(SiLU(norm(x))), and the identity shortcut norm(x) goes to F.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_dec_conv(const DecConvArgs A) {
     extern __shared__ float dsm[];
@@ -155,6 +159,20 @@ __global__ void __launch_bounds__(256) k_dec_conv(const DecConvArgs A) {
             for (int j = 0; j < 16; ++j) {
                 const float4 b = __ldg(s4 + j);
                 o[j] = make_float4(acc[4 * j] + b.x, acc[4 * j + 1] + b.y, acc[4 * j + 2] + b.z, acc[4 * j + 3] + b.w);
+            }
+        }
+    } else if (MODE == 2) {
+        if (valid) {
+            float4* o = reinterpret_cast<float4*>(A.h1[plane] + (static_cast<size_t>(r) * cols + c) * 64);
+            const float4* xi = reinterpret_cast<const float4*>(A.x[plane] + (static_cast<size_t>(r) * cols + c) * 64);
+            const float4* cf = reinterpret_cast<const float4*>(A.coef + plane * 64 * 2);      // (a, b) pairs: two channels per float4
+            float4* f = reinterpret_cast<float4*>(A.F[plane] + (static_cast<size_t>(r) * cols + c) * A.CF + A.foff);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 b = __ldg(b4 + j);
+                o[j] = make_float4(acc[4 * j] + b.x, acc[4 * j + 1] + b.y, acc[4 * j + 2] + b.z, acc[4 * j + 3] + b.w);
+                const float4 xv = __ldg(xi + j), c0 = __ldg(cf + 2 * j), c1 = __ldg(cf + 2 * j + 1);
+                f[j] = make_float4(fmaf(xv.x, c0.x, c0.y), fmaf(xv.y, c0.z, c0.w), fmaf(xv.z, c1.x, c1.y), fmaf(xv.w, c1.z, c1.w));
             }
         }
     } else if (valid) {
@@ -291,11 +309,14 @@ struct DecMlpF32 {
 struct DecArgs {
     DecPlanes G;
     DecPoints P;
-    int nb;                // branches: 1 (geo) or 2 (geo, tex)
-    int oc;                // output channels per point (1 + tex_channels)
+    int nb;                // MLP heads evaluated by this launch: 1 or 2
+    int oc;                // output channels per point (row stride of `out`)
     int tex_channels;
-    int clamp_tex;         // decode_batch's clamp of the colour channels (model.py:332)
+    int clamp_tex;         // decode_batch's clamp of every channel but the first (model.py:332)
     float* out;            // [n][oc]
+    // per head: first feature channel it reads in F (0 = geo planes, 64 = tex planes), first output column, sigmoid on the output
+    // (AutoEncoderGroupSkip / V3: {0, 64}, {0, 1}, {0, 1}; AutoEncoderGroupPBR runs (geo, rgb) then (mr, normal), no sigmoid)
+    int feat_off[2], out_col[2], sigmoid[2];
 };
 
 __global__ void __launch_bounds__(256) k_dec_mlp_ffma(const DecArgs A, const DecMlpF32 M0, const DecMlpF32 M1, int hid) {
@@ -325,7 +346,7 @@ __global__ void __launch_bounds__(256) k_dec_mlp_ffma(const DecArgs A, const Dec
                 for (int e = 0; e < 8; ++e) s[e] = 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float4* f = reinterpret_cast<const float4*>(A.G.F[p] + static_cast<size_t>(K.off[4 * p + k]) * A.G.CF + br * kDecUp + j * 8);
+                    const float4* f = reinterpret_cast<const float4*>(A.G.F[p] + static_cast<size_t>(K.off[4 * p + k]) * A.G.CF + A.feat_off[br] + j * 8);
                     const float4 a = __ldg(f), b = __ldg(f + 1);
                     const float w = K.w[4 * p + k];
                     s[0] = fmaf(a.x, w, s[0]); s[1] = fmaf(a.y, w, s[1]); s[2] = fmaf(a.z, w, s[2]); s[3] = fmaf(a.w, w, s[3]);
@@ -374,11 +395,9 @@ __global__ void __launch_bounds__(256) k_dec_mlp_ffma(const DecArgs A, const Dec
 #pragma unroll
                     for (int p = 0; p < 32; ++p) {
                         float v = acc[p] + bias;
-                        if (br == 1) {
-                            v = 1.f / (1.f + expf(-v));                       // networks.py:216  .sigmoid()
-                            if (A.clamp_tex) v = fminf(fmaxf(v, 0.f), 1.f);
-                        }
-                        if (g0 + p < A.P.n) A.out[(g0 + p) * A.oc + (br == 0 ? 0 : 1) + tid] = v;
+                        if (A.sigmoid[br]) v = 1.f / (1.f + expf(-v));      // networks.py:216  .sigmoid()
+                        if (A.clamp_tex && A.out_col[br] + tid > 0) v = fminf(fmaxf(v, 0.f), 1.f);
+                        if (g0 + p < A.P.n) A.out[(g0 + p) * A.oc + A.out_col[br] + tid] = v;
                     }
                 }
             }
@@ -585,7 +604,7 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                         float4 fa[12], fb[12];
 #pragma unroll
                         for (int c = 0; c < 12; ++c) {
-                            const float4* f = reinterpret_cast<const float4*>(A.D.G.F[c >> 2] + static_cast<size_t>(K.off[c]) * A.D.G.CF + br * kDecUp + j * 8);
+                            const float4* f = reinterpret_cast<const float4*>(A.D.G.F[c >> 2] + static_cast<size_t>(K.off[c]) * A.D.G.CF + A.D.feat_off[br] + j * 8);
                             fa[c] = __ldg(f);
                             fb[c] = __ldg(f + 1);
                         }
@@ -696,15 +715,14 @@ __global__ void __launch_bounds__(kDecTcThreads, 1) k_dec_mlp_tc(const __grid_co
                         }
                     }
                     if (last && half == 0 && g0 + m < A.D.P.n) {
-                        float* op = A.D.out + (g0 + m) * A.D.oc + (br == 0 ? 0 : 1);
+                        const int col0 = A.D.out_col[br];
+                        float* op = A.D.out + (g0 + m) * A.D.oc + col0;
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
                             if (o < n_out) {
                                 float v = o_acc[o] + C.b_last[br][o];
-                                if (br == 1) {
-                                    v = 1.f / (1.f + expf(-v));
-                                    if (A.D.clamp_tex) v = fminf(fmaxf(v, 0.f), 1.f);
-                                }
+                                if (A.D.sigmoid[br]) v = 1.f / (1.f + expf(-v));
+                                if (A.D.clamp_tex && col0 + o > 0) v = fminf(fmaxf(v, 0.f), 1.f);
                                 op[o] = v;
                             }
                         }

@@ -1495,7 +1495,7 @@ static void launch_sched(const SchedArgs& A, cudaStream_t s) {
 
 extern "C" {
 
-int s3d_abi_version(void) { return 3; }
+int s3d_abi_version(void) { return 4; }
 const char* s3d_last_error(void) { return g_err.c_str(); }
 
 int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {

@@ -52,6 +52,20 @@ def _group_resnet_params(cin, cout, ks):
     return m
 
 
+def _group_resnet_params_in(c, ks):
+    """Parameters of TriplaneGroupResnetBlock(c, c, ks, input_norm=True, input_act=True) (blocks.py:199-204): the conv sits at
+    in_layers.1 behind the SiLU, the shortcut is the identity."""
+    m = _Holder()
+    m.in_layers = nn.Sequential(_Holder(), _conv_params(3 * c, c, ks))
+    m.norm_xy, m.norm_xz, m.norm_yz = _affine_params(c), _affine_params(c), _affine_params(c)
+    out_conv = _conv_params(3 * c, c, ks)
+    with torch.no_grad():
+        out_conv.weight.zero_()
+        out_conv.bias.zero_()
+    m.out_layers = nn.Sequential(_Holder(), out_conv)
+    return m
+
+
 def _mlp_params(cin, cout, hidden, n_hidden):
     """Parameters of DecoderMLPSkipConcat (blocks.py:65-83); ReLUs sit at the odd indices."""
     m = _Holder()
@@ -90,6 +104,7 @@ def _mlp_params_plain(cin, cout, hidden, n_hidden):
 class AutoEncoderGroupSkip(nn.Module):
     """Decode side of the reference auto-encoder (networks.py:134-223) on the sm_100a kernels."""
     _mlp_kind = 0                      # s3d_decoder_config.mlp_kind
+    _net_kind = 0                      # s3d_decoder_config.net_kind
     _mlp_factory = staticmethod(_mlp_params)
 
     def __init__(self, geo_feat_channels, tex_feat_channels, feat_channel_up, mlp_hidden_channels, mlp_hidden_layers,
@@ -104,16 +119,20 @@ class AutoEncoderGroupSkip(nn.Module):
         self.geo_encoder = _conv_params(geo_feat_channels, 1, 4, dims=3)
         if use_tex:
             self.tex_encoder = _conv_params(tex_feat_channels, tex_channels + 1, 4, dims=3)
-        self.geo_convs = _group_resnet_params(geo_feat_channels, feat_channel_up, 5)
-        self.geo_decoder = self._mlp_factory(feat_channel_up, 1, mlp_hidden_channels, mlp_hidden_layers)
-        if use_tex:
-            self.tex_convs = _group_resnet_params(tex_feat_channels, feat_channel_up, 5)
-            self.tex_decoder = self._mlp_factory(feat_channel_up, tex_channels, mlp_hidden_channels, mlp_hidden_layers)
+        self._build_decode_side(geo_feat_channels, tex_feat_channels, feat_channel_up, mlp_hidden_channels, mlp_hidden_layers)
         self.register_buffer("aabb", torch.tensor([-1, -1, -1, 1, 1, 1], dtype=torch.float32))
         # kernel options: fp16x3 split (fp32-grade) unless S3D_PRECISION=1; tcgen05 MLP unless S3D_MLP_IMPL=ffma
         self.s3d_precision = int(os.environ.get("S3D_PRECISION", "3"))
         self.s3d_mlp_impl = 1 if os.environ.get("S3D_MLP_IMPL", "tc") == "ffma" else 0
         self._handle = self._handle_key = self._weights_key = self._planes_key = None
+
+    def _build_decode_side(self, geo, tex, up, hidden, n_hidden):
+        """Sub-modules in the reference's registration order (state_dict order)."""
+        self.geo_convs = _group_resnet_params(geo, up, 5)
+        self.geo_decoder = self._mlp_factory(up, 1, hidden, n_hidden)
+        if self.use_tex:
+            self.tex_convs = _group_resnet_params(tex, up, 5)
+            self.tex_decoder = self._mlp_factory(up, self.tex_channels, hidden, n_hidden)
 
     # ------------------------------------------------------------------ reference surface
     def geo_parameters(self):
@@ -173,7 +192,7 @@ class AutoEncoderGroupSkip(nn.Module):
             self._drop_handle()
             cfg = _lib.DecoderConfig(self.geo_feat_dim, self.tex_feat_dim if self.use_tex else 0, self.feat_channel_up,
                                      self.mlp_hidden_channels, self.mlp_hidden_layers, int(bool(self.use_tex)),
-                                     self.tex_channels, 5, self.s3d_precision, self.s3d_mlp_impl, self._mlp_kind)
+                                     self.tex_channels, 5, self.s3d_precision, self.s3d_mlp_impl, self._mlp_kind, self._net_kind)
             h = C.c_void_p()
             _lib.check(L.s3d_decoder_create(C.byref(cfg), idx, C.byref(h)))
             self._handle, self._handle_key = h, hkey
@@ -267,11 +286,38 @@ class AutoEncoderGroupV3(AutoEncoderGroupSkip):
     _mlp_factory = staticmethod(_mlp_params_plain)
 
 
+class AutoEncoderGroupPBR(AutoEncoderGroupSkip):
+    """``enc_net_type == "pbr"`` (reference networks.py:227-331, data_type "sdfpbr"): geometry block ks 5; two texture blocks ks 3,
+    the second with input InstanceNorm + SiLU and an identity shortcut; four skip-concat heads — sdf(1), rgb(3),
+    metallic-roughness(2), normal(3) — on the shared texture planes, no sigmoid.  decode -> [N, 9]."""
+    _net_kind = 1
+
+    def __init__(self, geo_feat_channels, tex_feat_channels, feat_channel_up, mlp_hidden_channels, mlp_hidden_layers,
+                 use_tex=True, tex_channels=3, posenc=0):
+        if use_tex and tex_channels != 8:
+            raise ValueError("AutoEncoderGroupPBR decodes rgb(3) + mr(2) + normal(3): tex_channels must be 8 (data_type 'sdfpbr')")
+        super().__init__(geo_feat_channels, tex_feat_channels, feat_channel_up, mlp_hidden_channels, mlp_hidden_layers,
+                         use_tex=use_tex, tex_channels=tex_channels, posenc=posenc)
+
+    def _build_decode_side(self, geo, tex, up, hidden, n_hidden):
+        self.geo_convs = _group_resnet_params(geo, up, 5)
+        self.geo_decoder = _mlp_params(up, 1, hidden, n_hidden)
+        if self.use_tex:
+            self.tex_convs = nn.Sequential(_group_resnet_params(tex, up, 3), _group_resnet_params_in(up, 3))
+            self.rgb_decoder = _mlp_params(up, 3, hidden, n_hidden)
+            self.mr_decoder = _mlp_params(up, 2, hidden, n_hidden)
+            self.normal_decoder = _mlp_params(up, 3, hidden, n_hidden)
+
+    def tex_parameters(self):
+        return list(self.tex_encoder.parameters()) + list(self.tex_convs.parameters()) + list(self.rgb_decoder.parameters()) + \
+            list(self.mr_decoder.parameters()) + list(self.normal_decoder.parameters())
+
+
 def get_networks(cfg):
-    """networks.py:7-18 (``pbr`` = AutoEncoderGroupPBR is not built: DESIGN.md §6)."""
+    """networks.py:7-18."""
     use_tex = cfg.data_type != "sdf"
     tex_channels = 8 if cfg.data_type == "sdfpbr" else 3
-    cls = {"base": AutoEncoderGroupV3, "skip": AutoEncoderGroupSkip}.get(cfg.enc_net_type)
+    cls = {"base": AutoEncoderGroupV3, "skip": AutoEncoderGroupSkip, "pbr": AutoEncoderGroupPBR}.get(cfg.enc_net_type)
     if cls is None:
         raise ValueError("Unknown / unsupported net type: {}".format(cfg.enc_net_type))
     return cls(cfg.fdim_geo, cfg.fdim_tex, cfg.fdim_up, cfg.hidden_dim, cfg.n_hidden_layers, use_tex=use_tex, tex_channels=tex_channels)

@@ -7,7 +7,7 @@ import torch
 
 from oracle import decoder_ref as de
 from oracle.cases import DECODER_CASES, make_decoder_inputs
-from sin3dm_b200.encoding import AutoEncoderGroupSkip, AutoEncoderGroupV3, TriplaneDecoder
+from sin3dm_b200.encoding import AutoEncoderGroupPBR, AutoEncoderGroupSkip, AutoEncoderGroupV3, TriplaneDecoder
 
 pytestmark = pytest.mark.gpu
 
@@ -16,7 +16,7 @@ TOL_SPLIT = 2e-5    # what the fp16 hi/lo split and the fp32 CUDA-core kernel ac
 
 
 def make_net(spec, sd, precision=3, impl="tc"):
-    cls = AutoEncoderGroupV3 if spec.mlp_kind == "base" else AutoEncoderGroupSkip
+    cls = AutoEncoderGroupPBR if spec.net_kind == "pbr" else (AutoEncoderGroupV3 if spec.mlp_kind == "base" else AutoEncoderGroupSkip)
     net = cls(spec.geo_feat_channels, spec.tex_feat_channels, spec.feat_channel_up,
                                spec.mlp_hidden_channels, spec.mlp_hidden_layers, use_tex=spec.use_tex,
                                tex_channels=spec.tex_channels)
@@ -119,7 +119,27 @@ def test_empty_and_single_point():
 
 
 # ------------------------------------------------------------------------------------------------ encoder half
-@pytest.mark.parametrize("name", ["default", "odd", "sdf_only", "aligned", "custom"])
+def test_pbr_unclamped_heads_match_oracle():
+    """AutoEncoderGroupPBR.decode (networks.py:296-331) without decode_batch's clamp: the rgb / mr / normal heads are raw
+    (no sigmoid), so the unclamped values are what pins them; both MLP kernels."""
+    case = DECODER_CASES["pbr"]
+    spec = de.DecoderSpec(**case["spec"])
+    sd = de.synthetic_state_dict(spec, case["wseed"])
+    maps, pts, aabb = make_decoder_inputs(case)
+    want = de.decode(sd, spec, pts, maps, aabb=aabb)
+    assert want.shape == (case["n"], 9) and float(want[:, 1:].abs().max()) > 1.0      # the clamp would have hidden these
+    for impl in ("ffma", "tc"):
+        net = make_net(spec, sd, 3, impl)
+        got = net.decode(pts.cuda(), [m.cuda() for m in maps], aabb=aabb)
+        rel, mx = errors(got, want)
+        print(f"pbr unclamped {impl}: rel_l2={rel:.2e} max={mx:.2e}")
+        assert rel < TOL_SPLIT and mx < TOL_SPLIT * 5, (impl, rel, mx)
+        for c0, c1 in ((0, 1), (1, 4), (4, 6), (6, 9)):                                # every head on its own columns
+            r, _ = errors(got[:, c0:c1], want[:, c0:c1])
+            assert r < TOL_SPLIT * 2, (impl, c0, r)
+
+
+@pytest.mark.parametrize("name", ["default", "odd", "sdf_only", "aligned", "custom", "pbr"])
 def test_encode_matches_reference_golden(golden_dir, name):
     """AutoEncoderGroupSkip.encode (networks.py:164-180) through s3d_decoder_encode vs the real reference's planes."""
     from oracle.cases import ENCODER_CASES, make_encoder_inputs

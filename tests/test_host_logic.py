@@ -100,13 +100,13 @@ def test_abi_exports_every_declared_symbol():
     declared = set(re.findall(r"\b(s3d_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib._SIGNATURES), declared ^ set(_lib._SIGNATURES)
     L = _lib.lib()            # raises if the .so is missing or a symbol cannot be bound
-    assert L.s3d_abi_version() == 3
+    assert L.s3d_abi_version() == 4
     for name in declared:
         assert hasattr(L, name)
     # struct sizes agree with the header layout (no compute call: there is no GPU here)
     import ctypes as C
     assert C.sizeof(_lib.UNetConfig) == 4 * (5 + 8 + 4)
-    assert C.sizeof(_lib.DecoderConfig) == 4 * 11
+    assert C.sizeof(_lib.DecoderConfig) == 4 * 12
 
 
 @pytest.mark.parametrize("use_tex", [True, False])
@@ -125,6 +125,26 @@ def test_decoder_state_dict_layout(use_tex):
         m.decode(torch.zeros(4, 3), [torch.zeros(1, spec.geo_feat_channels + spec.tex_feat_channels, 8, 8)] * 3)
     with pytest.raises(_lib.S3DError), torch.no_grad():        # encode runs on the GPU only, like decode
         m.encode(torch.zeros(1, 4 if use_tex else 1, 8, 8, 8))
+
+
+@pytest.mark.parametrize("use_tex", [True, False])
+def test_pbr_decoder_state_dict_layout(use_tex):
+    """AutoEncoderGroupPBR (networks.py:227-262): checkpoint keys and order (tex_convs.0 / tex_convs.1, rgb / mr / normal heads)."""
+    from oracle import decoder_ref as de
+    from sin3dm_b200.encoding import AutoEncoderGroupPBR, get_networks
+    spec = de.DecoderSpec(net_kind="pbr", use_tex=use_tex, tex_feat_channels=8 if use_tex else 0, tex_channels=8)
+    m = AutoEncoderGroupPBR(4, spec.tex_feat_channels, 64, 256, 4, use_tex=use_tex, tex_channels=8)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s in de.param_shapes(spec)]
+    m.load_state_dict(de.synthetic_state_dict(spec, 1))
+    assert m.out_channels == (9 if use_tex else 1)
+    if use_tex:
+        assert "tex_convs.1.in_layers.1.weight" in m.state_dict() and "tex_convs.1.shortcut.weight" not in m.state_dict()
+        with pytest.raises(ValueError):
+            AutoEncoderGroupPBR(4, 8, 64, 256, 4, use_tex=True, tex_channels=3)
+
+    class Cfg:
+        data_type, enc_net_type, fdim_geo, fdim_tex, fdim_up, hidden_dim, n_hidden_layers = "sdfpbr", "pbr", 4, 8, 64, 256, 4
+    assert isinstance(get_networks(Cfg), AutoEncoderGroupPBR)
 
 
 def test_grid_axes_match_oracle():

@@ -45,7 +45,7 @@ def test_hoisted_planes_equal_per_chunk_recompute():
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("name", ["default", "odd", "sdf_only", "aligned", "custom"])
+@pytest.mark.parametrize("name", ["default", "odd", "sdf_only", "aligned", "custom", "pbr"])
 def test_encoder_oracle_matches_reference(golden_dir, name):
     """oracle encode (networks.py:164-180 restated) against the planes the real reference produced."""
     from oracle.cases import ENCODER_CASES, make_encoder_inputs
