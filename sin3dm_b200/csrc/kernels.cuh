@@ -980,11 +980,18 @@ __global__ void __launch_bounds__(256) k_vb_terms(VbArgs A) {
     }
 }
 // grid B, block 32: lane k < 3 adds the gx block sums of term k in order
-__global__ void k_vb_finalize(VbArgs A, int gx) {
-    const int b = blockIdx.x, k = threadIdx.x;
-    if (k >= 3) return;
+// block sums of sample b, term k: lane l adds blocks l, l + 32, ... in order, then a fixed butterfly (same result on every run)
+__device__ __forceinline__ double partial_sum(const double* partial, int b, int gx, int k) {
     double s = 0.0;
-    for (int j = 0; j < gx; ++j) s += A.partial[(static_cast<size_t>(b) * gx + j) * 3 + k];
+    for (int j = threadIdx.x & 31; j < gx; j += 32) s += partial[(static_cast<size_t>(b) * gx + j) * 3 + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+__global__ void k_vb_finalize(VbArgs A, int gx) {       // grid B, block 96: warp k reduces term k
+    const int b = blockIdx.x, k = threadIdx.x >> 5;
+    const double s = partial_sum(A.partial, b, gx, k);
+    if ((threadIdx.x & 31) != 0) return;
     double m = s / static_cast<double>(A.n);
     if (k == 0) m /= 0.6931471805599453;        // nats -> bits (np.log(2.0))
     A.out[b * 3 + k] = static_cast<float>(m);
@@ -1021,20 +1028,37 @@ __global__ void __launch_bounds__(256) k_plane_mse(PlaneMseArgs A) {
         }
     };
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x, i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if ((A.n & 3) == 0) {
+    if ((A.n & 3) == 0 && A.n < (1LL << 31)) {
+        // Quads with 32-bit index arithmetic (the kernel is issue bound: the 64-bit modulo per quad used to dominate it).  A quad
+        // that stays inside one row and on one side of column W lies in ONE plane: four squared differences, one predicated add.
         const float4* t4 = reinterpret_cast<const float4*>(A.target + base);
         const float4* o4 = reinterpret_cast<const float4*>(A.output + base);
-        for (long long i = i0; i < (A.n >> 2); i += stride) {
+        const unsigned nq = static_cast<unsigned>(A.n >> 2), uhw = static_cast<unsigned>(hw), uWc = static_cast<unsigned>(Wc);
+        const unsigned ustride = static_cast<unsigned>(stride);
+        for (unsigned i = static_cast<unsigned>(i0); i < nq; i += ustride) {
             const float4 tg = __ldg(t4 + i), ou = __ldg(o4 + i);
-            const int pix = static_cast<int>((i << 2) % hw);      // one division per four elements; the quad may run over a row end
-            int r = pix / Wc, c = pix - r * Wc;
-            const float tv[4] = {tg.x, tg.y, tg.z, tg.w}, ov[4] = {ou.x, ou.y, ou.z, ou.w};
+            const unsigned pix = (i << 2) % uhw;
+            int r = static_cast<int>(pix / uWc), c = static_cast<int>(pix - static_cast<unsigned>(r) * uWc);
+            const float dx = tg.x - ou.x, dy = tg.y - ou.y, dz = tg.z - ou.z, dw = tg.w - ou.w;
+            if (c + 3 < Wc && (c + 3 < A.W || c >= A.W)) {
+                const float s4 = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                const bool top = r < A.H, left = c < A.W;
+                q[0] += (top && left) ? s4 : 0.f;
+                q[1] += (top && !left) ? s4 : 0.f;
+                q[2] += (!top && left) ? s4 : 0.f;
+            } else {
+                const float dv[4] = {dx, dy, dz, dw};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                add(r, c, tv[k], ov[k]);
-                if (++c == Wc) {
-                    c = 0;
-                    if (++r == A.H + A.D) r = 0;                  // next channel
+                for (int k = 0; k < 4; ++k) {
+                    const float d2 = dv[k] * dv[k];
+                    const bool top = r < A.H, left = c < A.W;
+                    q[0] += (top && left) ? d2 : 0.f;
+                    q[1] += (top && !left) ? d2 : 0.f;
+                    q[2] += (!top && left) ? d2 : 0.f;
+                    if (++c == Wc) {
+                        c = 0;
+                        if (++r == A.H + A.D) r = 0;                  // next channel
+                    }
                 }
             }
             fold();
@@ -1061,11 +1085,10 @@ __global__ void __launch_bounds__(256) k_plane_mse(PlaneMseArgs A) {
         A.partial[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
     }
 }
-__global__ void k_plane_mse_finalize(PlaneMseArgs A, int gx) {
-    const int b = blockIdx.x, k = threadIdx.x;
-    if (k >= 3) return;
-    double t = 0.0;
-    for (int j = 0; j < gx; ++j) t += A.partial[(static_cast<size_t>(b) * gx + j) * 3 + k];
+__global__ void k_plane_mse_finalize(PlaneMseArgs A, int gx) {       // grid B, block 96: warp k reduces plane k
+    const int b = blockIdx.x, k = threadIdx.x >> 5;
+    const double t = partial_sum(A.partial, b, gx, k);
+    if ((threadIdx.x & 31) != 0) return;
     const double cnt = static_cast<double>(A.C) * (k == 0 ? A.H * A.W : (k == 1 ? A.H * A.D : A.W * A.D));
     A.out[b * 3 + k] = static_cast<float>(t / cnt);
 }

@@ -1672,9 +1672,14 @@ int s3d_q_sample(const float* x0_dev, const float* noise_dev, float* out_dev, co
     API_END
 }
 
-// one float4 per thread and iteration: enough CTAs to fill the machine at any batch size (the batch is the grid's y dimension)
-static int vb_grid(int64_t n) { return static_cast<int>(std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148LL * 8))); }
-int64_t s3d_vb_workspace_bytes(int B, int64_t n) { return static_cast<int64_t>(B) * vb_grid(n) * 3 * sizeof(double); }
+// CTAs per sample (the batch is the grid's y dimension): about eight float4 per thread so that the block reduction is amortised, but
+// never fewer CTAs in total than four per SM
+static int vb_grid(int64_t n, int B) {
+    const long long quads = (n / 4 + 255) / 256;                          // one float4 per thread
+    const long long want = std::max<long long>((quads + 7) / 8, (148LL * 4 + B - 1) / std::max(B, 1));
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(want, quads)));
+}
+int64_t s3d_vb_workspace_bytes(int B, int64_t n) { return static_cast<int64_t>(B) * vb_grid(n, B) * 3 * sizeof(double); }
 int s3d_vb_terms(const s3d_vb_args* a, void* stream) {
     API_BEGIN
     S3D_CHECK(a && a->x_start && a->x_t && a->model_out && a->coef_dev && a->logvar_dev && a->t_idx_dev && a->workspace && a->out &&
@@ -1695,10 +1700,10 @@ int s3d_vb_terms(const s3d_vb_args* a, void* stream) {
     A.t_idx = a->t_idx_dev;
     A.partial = static_cast<double*>(a->workspace);
     A.out = a->out;
-    const int gx = vb_grid(A.n);
+    const int gx = vb_grid(A.n, A.B);
     launch_plain(k_vb_terms, dim3(gx, A.B), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
     LAUNCH_CHECK("k_vb_terms");
-    launch_plain(k_vb_finalize, dim3(A.B), dim3(32), 0, static_cast<cudaStream_t>(stream), A, gx);
+    launch_plain(k_vb_finalize, dim3(A.B), dim3(96), 0, static_cast<cudaStream_t>(stream), A, gx);
     LAUNCH_CHECK("k_vb_finalize");
     API_END
 }
@@ -1714,10 +1719,10 @@ int s3d_plane_mse(const float* target_dev, const float* output_dev, int B, int C
     A.n = static_cast<long long>(C) * (H + D) * (W + D);
     A.partial = static_cast<double*>(workspace);
     A.out = out_dev;
-    const int gx = vb_grid(A.n);
+    const int gx = vb_grid(A.n, B);
     launch_plain(k_plane_mse, dim3(gx, B), dim3(256), 0, static_cast<cudaStream_t>(stream), A);
     LAUNCH_CHECK("k_plane_mse");
-    launch_plain(k_plane_mse_finalize, dim3(B), dim3(32), 0, static_cast<cudaStream_t>(stream), A, gx);
+    launch_plain(k_plane_mse_finalize, dim3(B), dim3(96), 0, static_cast<cudaStream_t>(stream), A, gx);
     LAUNCH_CHECK("k_plane_mse_finalize");
     API_END
 }

@@ -59,6 +59,7 @@ def main():
     x0 = torch.rand(shape, device="cuda", generator=g) * 2 - 1
     nz = torch.randn(shape, device="cuda", generator=g)
     mo = torch.randn(shape, device="cuda", generator=g)
+    xt = torch.randn(shape, device="cuda", generator=g)          # x_t: its own buffer (every stream of k_vb_terms is distinct memory)
     out = torch.empty_like(x0)
     t = torch.randint(1, 1000, (shape[0],), device="cuda").to(torch.int32)
     d = create_gaussian_diffusion(predict_xstart=True)
@@ -86,7 +87,7 @@ def main():
     res = torch.empty(shape[0], 3, device="cuda")
     a = _lib.VbArgs()
     a.mean_type, a.clip_denoised, a.B, a.n_per_sample = _lib.START_X, 1, shape[0], n
-    a.x_start, a.x_t, a.model_out, a.noise, a.pred_xstart = x0.data_ptr(), nz.data_ptr(), mo.data_ptr(), nz.data_ptr(), out.data_ptr()
+    a.x_start, a.x_t, a.model_out, a.noise, a.pred_xstart = x0.data_ptr(), xt.data_ptr(), mo.data_ptr(), nz.data_ptr(), out.data_ptr()
     a.coef_dev, a.logvar_dev, a.t_idx_dev, a.workspace, a.out = coef.data_ptr(), logvar.data_ptr(), t.data_ptr(), ws.data_ptr(), res.data_ptr()
     report("k_vb_terms", timed_dev(lambda: _lib.check(L.s3d_vb_terms(C.byref(a), st))), 5 * nb,
            "cfg3 latent, B=32: x_start, x_t, model_out, noise read, pred_xstart written (+ k_vb_finalize)")
