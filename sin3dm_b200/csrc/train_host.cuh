@@ -205,7 +205,7 @@ struct BackwardBuilder {
                 launch_plain(k_roll_bwd_vec, dim3((Lmax + kRvPos - 1) / kRvPos, 6 * nct, Bv), dim3(256), smem, s, R);
                 LAUNCH_CHECK("k_roll_bwd_vec");
             });
-            const int nsplit = std::min(B, 8);
+            const int nsplit = std::min(B, 32);      // K = (sample, position) split by sample: 18 x nsplit CTAs, about four per SM at B = 32
             const size_t pn = static_cast<size_t>(nsplit) * 18 * 3 * cv.Cout * cv.C;
             float* partial = static_cast<float*>(pb.barena.alloc(sizeof(float) * pn, P->allocs));
             const int ntile = (cv.Cout / 64) * nct;
