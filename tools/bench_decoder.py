@@ -31,15 +31,17 @@ def mlp_flops_per_point(spec):
 
 
 def run(reso=256, iters=5, cpu_baseline=True, precision=3, device=0):
+    import types
     import torch
-    from oracle import decoder_ref as de            # synthetic weight recipe + the CPU baseline
     from sin3dm_b200.encoding import AutoEncoderGroupSkip, TriplaneDecoder, sample_grid_points_axes
+    from sin3dm_b200.synthetic import synthetic_state_dict_like
     import bench as B
 
     torch.cuda.set_device(device)
-    spec = de.DecoderSpec()
-    sd = de.synthetic_state_dict(spec, 1234)
+    spec = types.SimpleNamespace(feat_channel_up=64, mlp_hidden_channels=256, mlp_hidden_layers=4, tex_channels=3, use_tex=True)
     net = AutoEncoderGroupSkip(4, 8, 64, 256, 4, use_tex=True, tex_channels=3)
+    sd = synthetic_state_dict_like(net, 1234)       # the measured arm never imports oracle/ (only the cpu_baseline leg below does)
+    sd["aabb"] = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0])
     net.load_state_dict(sd)
     net.s3d_precision = precision
     net = net.cuda().eval()
@@ -115,6 +117,8 @@ def run(reso=256, iters=5, cpu_baseline=True, precision=3, device=0):
                            "kernel time; the hi/lo split executes 3x that on the tensor cores",
                       peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})"))
     if cpu_baseline:
+        from oracle import decoder_ref as de            # the checker / CPU baseline: the oracle on the same weights
+        spec = de.DecoderSpec()
         pts = de.grid_points(aabb, reso).view(-1, 3)
         sel = pts[: 4 * 2 ** 14]
         cm = [m.clone() for m in host_maps]
@@ -136,14 +140,14 @@ def run(reso=256, iters=5, cpu_baseline=True, precision=3, device=0):
 def run_encode(iters=10, cpu_baseline=True, device=0):
     """Encoder half (AutoEncoderGroupSkip.encode): the 184 x 256 x 184 sdf+rgb volume of the cfg2 latent -> three planes."""
     import torch
-    from oracle import decoder_ref as de
     from sin3dm_b200.encoding import AutoEncoderGroupSkip
+    from sin3dm_b200.synthetic import synthetic_state_dict_like
     import bench as B
 
     torch.cuda.set_device(device)
-    spec = de.DecoderSpec()
-    sd = de.synthetic_state_dict(spec, 1234)
     net = AutoEncoderGroupSkip(4, 8, 64, 256, 4, use_tex=True, tex_channels=3)
+    sd = synthetic_state_dict_like(net, 1234)
+    sd["aabb"] = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0])
     net.load_state_dict(sd)
     net = net.cuda().eval()
     X, Y, Z = 184, 256, 184
@@ -194,6 +198,8 @@ def run_encode(iters=10, cpu_baseline=True, device=0):
                               "(2304 per output voxel), which is what bounds it on the CUDA cores",
                               peak_source=f"MEASURED_PEAKS.json hbm_gbs ({peaks['src']})"))
     if cpu_baseline:
+        from oracle import decoder_ref as de            # the checker / CPU baseline
+        spec = de.DecoderSpec()
         torch.set_num_threads(min(os.cpu_count() or 1, 32))
         with torch.no_grad():
             t0 = time.perf_counter()
