@@ -144,6 +144,7 @@ struct s3d_unet {
     int num_sms = 148;
     bool fuse_roll = true;   // S3D_FUSE_ROLL=0 launches the rollout 1-D GEMM separately
     bool halo_bo_kw = false;
+    int roll_tm = kRollTmMax;   // S3D_ROLL_TM: most positions per roll tile (shorter tiles = a shorter roll chain in front of the conv tiles)
     bool fuse_pool = true;      // S3D_FUSE_POOL=0: stand-alone k_avgpool2 instead of pooling in the conv epilogue
     bool trace_on = false;   // s3d_unet_trace_enable
     int profile_mode = -1;   // last s3d_unet_profile_ops: 1 = graph replay with event nodes, 0 = eager launches
@@ -943,7 +944,8 @@ struct PlanBuilder {
             }
             A.tile_start[i] = total;
             {
-                const int nt = (L[i] + kRollTmMax - 1) / kRollTmMax;      // equal tiles of at most kRollTmMax positions
+                const int tmax = std::max(8, std::min(kRollTmMax, u->roll_tm));
+                const int nt = (L[i] + tmax - 1) / tmax;                  // equal tiles of at most `tmax` positions
                 A.tm[i] = (L[i] + nt - 1) / nt;
                 total += nt;
             }
@@ -1523,6 +1525,7 @@ int s3d_unet_create(const s3d_unet_config* cfg, int device, s3d_unet** out) {
     if (const char* e = getenv("S3D_PDL")) g_pdl = atoi(e) != 0;
     if (const char* e = getenv("S3D_HALO_BO_KW")) u->halo_bo_kw = atoi(e) != 0;
     if (const char* e = getenv("S3D_FUSE_POOL")) u->fuse_pool = atoi(e) != 0;
+    if (const char* e = getenv("S3D_ROLL_TM")) u->roll_tm = atoi(e);
     u->bwd_wgrad_ffma = false;
     if (const char* e = getenv("S3D_WGRAD")) u->bwd_wgrad_ffma = std::string(e) == "ffma";      // CUDA-core cross-check kernel
     build_structure(u.get());
