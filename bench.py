@@ -482,6 +482,18 @@ def run_ours(args, wl):
                                                                     "conv_share_of_event_timed_step")}
                 entry["kernels"] = r["kernels"]
             also[f"{nm}_{w2['sampler']}{w2['chain']}"] = entry
+    if not args.no_also:
+        # (before the host-side baseline legs, which leave the GPU idle for ~30 s; 40 warm-up steps = 0.9 s: building the training plan
+        # idles the GPU for seconds and the first ~10 iterations after it run 10-20 % slow)
+        # the training step (BASELINE configs[3], diffusion half): forward + backward + AdamW/EMA at B=32 per GPU, data parallel at N>1
+        try:
+            from tools.bench_train import run_train
+            tr = run_train(bn, args, WORKLOADS["cfg4"], 10, 40, METRIC, config_of, load_peaks, emit=False, profile=bn.world == 1)
+            if tr is not None:
+                also["cfg4_train_b32"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "per_rank_ms", "config", "e2e", "detail",
+                                                             "roofline", "roofline_parts") if k in tr}
+        except Exception as e:
+            also["cfg4_train_b32"] = f"failed: {type(e).__name__}: {e}"
     cpu = lib = None
     if bn.rank == 0 and bn.world == 1 and not args.no_cpu_baseline:
         lib = dict(what="reference arithmetic (oracle restatement) run by torch eager on the same GPU: cuDNN / cuBLAS / ATen library "
@@ -503,16 +515,6 @@ def run_ours(args, wl):
             also["decoder_grid256"] = f"failed: {type(e).__name__}: {e}"
         sps, done, dt, thr, kind = cpu_steps_per_s(wl, 200, 3, budget_s=20.0)
         cpu = dict(value=sps, unit="steps/s", cores=thr, kind=kind, sample=cpu_sample_text(kind, done, wl, args.workload, 3, thr, dt))
-    if not args.no_also:
-        # the training step (BASELINE configs[3], diffusion half): forward + backward + AdamW/EMA at B=32 per GPU, data parallel at N>1
-        try:
-            from tools.bench_train import run_train
-            tr = run_train(bn, args, WORKLOADS["cfg4"], 5, 3, METRIC, config_of, load_peaks, emit=False, profile=bn.world == 1)
-            if tr is not None:
-                also["cfg4_train_b32"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "per_rank_ms", "config", "e2e", "detail",
-                                                             "roofline", "roofline_parts") if k in tr}
-        except Exception as e:
-            also["cfg4_train_b32"] = f"failed: {type(e).__name__}: {e}"
     if bn.rank == 0:
         Cc, (H, W, D), B = wl["C"], wl["HWD"], wl["B"]
         cfg = config_of(args.workload, wl, bn.world)       # identical in both arms
