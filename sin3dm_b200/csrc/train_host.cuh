@@ -538,9 +538,15 @@ static void build_backward(s3d_unet* u, PlanBuilder& pb, const ActF& h_last, con
         bb.add("k_head_bwd", 4.0 * B * bb.px3(0) * c0 * Cf, [=](cudaStream_t s) {
             HeadBwdArgs Al = A;
             Al.g = P->grad_out;
-            const dim3 grid(std::max(1, 4 * u->num_sms / (3 * B)), B, 3);
-            if (c0 == 64) launch_plain(k_head_bwd<16>, dim3(grid), dim3(256), 0, s, Al);
-            else launch_plain(k_head_bwd<32>, dim3(grid), dim3(256), 0, s, Al);
+            // two launches (dy, then dw / db): each half fits two CTAs per SM, the combined kernel held 236 registers
+            const dim3 grid_dy(std::max(1, 8 * u->num_sms / (3 * B)), B, 3), grid_dw(std::max(1, 4 * u->num_sms / (3 * B)), B, 3);
+            if (c0 == 64) {
+                launch_plain(k_head_bwd<16, 0>, dim3(grid_dy), dim3(256), 0, s, Al);
+                launch_plain(k_head_bwd<16, 1>, dim3(grid_dw), dim3(256), 0, s, Al);
+            } else {
+                launch_plain(k_head_bwd<32, 0>, dim3(grid_dy), dim3(256), 0, s, Al);
+                launch_plain(k_head_bwd<32, 1>, dim3(grid_dw), dim3(256), 0, s, Al);
+            }
             LAUNCH_CHECK("k_head_bwd");
         });
     }

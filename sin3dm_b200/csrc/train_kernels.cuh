@@ -598,8 +598,10 @@ struct HeadBwdArgs {
 // rows of w_out in registers; dw partials stay in registers over the tile's 8 passes and are reduced once per CTA.
 // A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... of ONE plane and reduces its dw / db partials once at the end (the
 // global atomics all land on the same Cf x C0 addresses: as few CTAs as fill the machine).  grid (gx, B, 3), block 256
-template <int NQ>
-__global__ void __launch_bounds__(256) k_head_bwd(HeadBwdArgs A) {
+// PART 0: dy only (needs g and w_out: no activation read); PART 1: dw / db only (needs g and y = silu(GN(h))).  One kernel doing both
+// held 96 weight + accumulator registers per thread (236 in all, one CTA per SM); the two halves run two CTAs per SM each.
+template <int NQ, int PART>
+__global__ void __launch_bounds__(256, 2) k_head_bwd(HeadBwdArgs A) {
     constexpr int PPP = 256 / NQ, NPASS = kBndPx / PPP, C0 = NQ * 4;
     __shared__ __align__(16) float gs[kMaxCf][kBndPx];      // S * dL/dout of the tile, [channel][pixel]
     __shared__ __align__(16) float coefA[C0], coefB[C0];
@@ -614,29 +616,34 @@ __global__ void __launch_bounds__(256) k_head_bwd(HeadBwdArgs A) {
     const int Hc = A.H + A.Dd, Wc = A.W + A.Dd;
     const long long hw = static_cast<long long>(Hc) * Wc;
     const float S = loss_scale(A.amax);
-    for (int e = tid; e < kMaxCf * C0; e += 256) (&dwacc[0][0])[e] = 0.f;
-    if (tid < kMaxCf) dbacc[tid] = 0.f;
-    gn_mean_rstd(A.acc, b, plane, static_cast<double>(npx) * cpg, tid, mean, rstd);
-    __syncthreads();
-    for (int c = tid; c < C0; c += 256) {
-        const int g = c / cpg;
-        const float ga = __ldg(A.gamma.p[plane] + c) * rstd[g];
-        coefA[c] = ga;
-        coefB[c] = __ldg(A.beta.p[plane] + c) - mean[g] * ga;
-    }
     const int ql = tid & (NQ - 1), pslot = tid / NQ;
-    float4 wq[kMaxCf];
+    float4 wq[kMaxCf];                                       // PART 0: this lane's four columns of w_out
+    float4 dwr[kMaxCf];                                      // PART 1: this lane's dw partials
+    float dbr = 0.f;
+    float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), cb = ca;
+    if (PART == 1) {
+        for (int e = tid; e < kMaxCf * C0; e += 256) (&dwacc[0][0])[e] = 0.f;
+        if (tid < kMaxCf) dbacc[tid] = 0.f;
+        gn_mean_rstd(A.acc, b, plane, static_cast<double>(npx) * cpg, tid, mean, rstd);
+        __syncthreads();
+        for (int c = tid; c < C0; c += 256) {
+            const int g = c / cpg;
+            const float ga = __ldg(A.gamma.p[plane] + c) * rstd[g];
+            coefA[c] = ga;
+            coefB[c] = __ldg(A.beta.p[plane] + c) - mean[g] * ga;
+        }
+        __syncthreads();
+        ca = *reinterpret_cast<const float4*>(coefA + ql * 4);
+        cb = *reinterpret_cast<const float4*>(coefB + ql * 4);
 #pragma unroll
-    for (int co = 0; co < kMaxCf; ++co)
-        wq[co] = co < Cf ? __ldg(reinterpret_cast<const float4*>(A.w_out.p[plane] + static_cast<size_t>(co) * C0 + ql * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const float4 ca = *reinterpret_cast<const float4*>(coefA + ql * 4), cb = *reinterpret_cast<const float4*>(coefB + ql * 4);
+        for (int co = 0; co < kMaxCf; ++co) dwr[co] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+        for (int co = 0; co < kMaxCf; ++co)
+            wq[co] = co < Cf ? __ldg(reinterpret_cast<const float4*>(A.w_out.p[plane] + static_cast<size_t>(co) * C0 + ql * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const float* hp = A.h.p[plane] + static_cast<size_t>(b) * npx * C0 + ql * 4;
     float* dyp = A.dy.p[plane] + static_cast<size_t>(b) * npx * C0 + ql * 4;
-    float4 dwr[kMaxCf];
-#pragma unroll
-    for (int co = 0; co < kMaxCf; ++co) dwr[co] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float dbr = 0.f;
     for (int ip = blockIdx.x; ip < ntile; ip += gridDim.x) {
         const int tf = ip % A.tiles_fast[plane], ts = ip / A.tiles_fast[plane];
         const int r0 = fast_rows ? tf * kBndFast : ts * kBndSlow, c0 = fast_rows ? ts * kBndSlow : tf * kBndFast;
@@ -660,39 +667,49 @@ __global__ void __launch_bounds__(256) k_head_bwd(HeadBwdArgs A) {
                 const int i = (p0 + k) * PPP + pslot, r = pix_r(i), c = pix_c(i);
                 ok[k] = r < rows && c < cols;
                 off[k] = ok[k] ? (static_cast<size_t>(r) * cols + c) * C0 : 0;
-                hv[k] = ok[k] ? __ldg(reinterpret_cast<const float4*>(hp + off[k])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (PART == 1) hv[k] = ok[k] ? __ldg(reinterpret_cast<const float4*>(hp + off[k])) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int k = 0; k < NB; ++k) {
                 const int i = (p0 + k) * PPP + pslot;
-                float4 y;
-                y.x = silu_f(fmaf(hv[k].x, ca.x, cb.x)); y.y = silu_f(fmaf(hv[k].y, ca.y, cb.y));
-                y.z = silu_f(fmaf(hv[k].z, ca.z, cb.z)); y.w = silu_f(fmaf(hv[k].w, ca.w, cb.w));
-                float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (PART == 1) {
+                    float4 y;
+                    y.x = silu_f(fmaf(hv[k].x, ca.x, cb.x)); y.y = silu_f(fmaf(hv[k].y, ca.y, cb.y));
+                    y.z = silu_f(fmaf(hv[k].z, ca.z, cb.z)); y.w = silu_f(fmaf(hv[k].w, ca.w, cb.w));
 #pragma unroll
-                for (int co = 0; co < kMaxCf; ++co)
-                    if (co < Cf) {
-                        const float gv = gs[co][i];          // zero for pixels outside the plane
-                        dy.x = fmaf(gv, wq[co].x, dy.x); dy.y = fmaf(gv, wq[co].y, dy.y); dy.z = fmaf(gv, wq[co].z, dy.z); dy.w = fmaf(gv, wq[co].w, dy.w);
-                        dwr[co].x = fmaf(gv, y.x, dwr[co].x); dwr[co].y = fmaf(gv, y.y, dwr[co].y);
-                        dwr[co].z = fmaf(gv, y.z, dwr[co].z); dwr[co].w = fmaf(gv, y.w, dwr[co].w);
-                    }
-                if (ok[k]) *reinterpret_cast<float4*>(dyp + off[k]) = dy;
+                    for (int co = 0; co < kMaxCf; ++co)
+                        if (co < Cf) {
+                            const float gv = gs[co][i];          // zero for pixels outside the plane
+                            dwr[co].x = fmaf(gv, y.x, dwr[co].x); dwr[co].y = fmaf(gv, y.y, dwr[co].y);
+                            dwr[co].z = fmaf(gv, y.z, dwr[co].z); dwr[co].w = fmaf(gv, y.w, dwr[co].w);
+                        }
+                } else {
+                    float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int co = 0; co < kMaxCf; ++co)
+                        if (co < Cf) {
+                            const float gv = gs[co][i];
+                            dy.x = fmaf(gv, wq[co].x, dy.x); dy.y = fmaf(gv, wq[co].y, dy.y); dy.z = fmaf(gv, wq[co].z, dy.z); dy.w = fmaf(gv, wq[co].w, dy.w);
+                        }
+                    if (ok[k]) *reinterpret_cast<float4*>(dyp + off[k]) = dy;
+                }
             }
         }
-        if (tid < Cf)
+        if (PART == 1 && tid < Cf)
             for (int i = 0; i < kBndPx; ++i) dbr += gs[tid][i];
     }
+    if (PART == 1) {
 #pragma unroll
-    for (int co = 0; co < kMaxCf; ++co)
-        if (co < Cf) {
-            atomicAdd(&dwacc[co][ql * 4 + 0], dwr[co].x); atomicAdd(&dwacc[co][ql * 4 + 1], dwr[co].y);
-            atomicAdd(&dwacc[co][ql * 4 + 2], dwr[co].z); atomicAdd(&dwacc[co][ql * 4 + 3], dwr[co].w);
-        }
-    if (tid < Cf) dbacc[tid] = dbr;
-    __syncthreads();
-    for (int e = tid; e < Cf * C0; e += 256) atomicAdd(A.dw[plane] + e, dwacc[e / C0][e % C0]);
-    if (tid < Cf) atomicAdd(A.db[plane] + tid, dbacc[tid]);
+        for (int co = 0; co < kMaxCf; ++co)
+            if (co < Cf) {
+                atomicAdd(&dwacc[co][ql * 4 + 0], dwr[co].x); atomicAdd(&dwacc[co][ql * 4 + 1], dwr[co].y);
+                atomicAdd(&dwacc[co][ql * 4 + 2], dwr[co].z); atomicAdd(&dwacc[co][ql * 4 + 3], dwr[co].w);
+            }
+        if (tid < Cf) dbacc[tid] = dbr;
+        __syncthreads();
+        for (int e = tid; e < Cf * C0; e += 256) atomicAdd(A.dw[plane] + e, dwacc[e / C0][e % C0]);
+        if (tid < Cf) atomicAdd(A.db[plane] + tid, dbacc[tid]);
+    }
 }
 
 struct InconvBwdArgs {
