@@ -387,32 +387,45 @@ __global__ void __launch_bounds__(256) k_roll_bwd_vec(RollBwdArgs A) {
     }
     const int cq = threadIdx.x & 15, pp = threadIdx.x >> 4;        // 4 channels x 2 positions per thread
     float acc[2][4] = {};
-    for (int t = 0; t < 9; ++t) {
+    // weight chunks of 32 (co) x 64 (c), software pipelined: the next chunk is requested into registers before the current one is
+    // multiplied (two float4 per thread), so its L2 latency hides behind the FMAs
+    const int nco = Cout / 32, nchunk = 9 * nco;
+    float4 wn[2];
+    auto request = [&](int ch) {
+        const int t = ch / nco, co0 = (ch - t * nco) * 32;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = threadIdx.x + j * 256, k = i >> 4, q = i & 15;
+            wn[j] = __ldg(reinterpret_cast<const float4*>(S.wv + (static_cast<size_t>(t) * Cout + co0 + k) * C + c0) + q);
+        }
+    };
+    request(0);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const int t = ch / nco, co0 = (ch - t * nco) * 32;
         const int al = t / 3, ac = t - al * 3;
         const float* s0 = sy3 + (ac * (kRvPos + 2) + (2 * pp + 2 - al)) * Cout;      // position j - al + 1 -> slot jl + 2 - al
         const float* s1 = s0 + Cout;
-        for (int co0 = 0; co0 < Cout; co0 += 32) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
-                const int k = i >> 4, q = i & 15;
-                *reinterpret_cast<float4*>(wt + k * 64 + q * 4) =
-                    __ldg(reinterpret_cast<const float4*>(S.wv + (static_cast<size_t>(t) * Cout + co0 + k) * C + c0) + q);
-            }
-            __syncthreads();
-            // k in steps of four: the two positions' operands come as one 16-byte broadcast load each (the loop was bound by
-            // shared-memory instructions: 12 per 32 FMAs before, 6 now); same accumulation order as the scalar loop
-#pragma unroll 2
-            for (int k = 0; k < 32; k += 4) {
-                const float4 a0 = *reinterpret_cast<const float4*>(s0 + co0 + k), a1 = *reinterpret_cast<const float4*>(s1 + co0 + k);
-                const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
+        __syncthreads();                               // the previous chunk has been multiplied (first pass: sy3 is complete)
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const float4 w = *reinterpret_cast<const float4*>(wt + (k + kk) * 64 + cq * 4);
-                    acc[0][0] = fmaf(av0[kk], w.x, acc[0][0]); acc[0][1] = fmaf(av0[kk], w.y, acc[0][1]);
-                    acc[0][2] = fmaf(av0[kk], w.z, acc[0][2]); acc[0][3] = fmaf(av0[kk], w.w, acc[0][3]);
-                    acc[1][0] = fmaf(av1[kk], w.x, acc[1][0]); acc[1][1] = fmaf(av1[kk], w.y, acc[1][1]);
-                    acc[1][2] = fmaf(av1[kk], w.z, acc[1][2]); acc[1][3] = fmaf(av1[kk], w.w, acc[1][3]);
-                }
+        for (int j = 0; j < 2; ++j) {
+            const int i = threadIdx.x + j * 256, k = i >> 4, q = i & 15;
+            *reinterpret_cast<float4*>(wt + k * 64 + q * 4) = wn[j];
+        }
+        __syncthreads();
+        if (ch + 1 < nchunk) request(ch + 1);
+        // k in steps of four: the two positions' operands come as one 16-byte broadcast load each (the loop was bound by
+        // shared-memory instructions: 12 per 32 FMAs before, 6 now); same accumulation order as the scalar loop
+#pragma unroll 2
+        for (int k = 0; k < 32; k += 4) {
+            const float4 a0 = *reinterpret_cast<const float4*>(s0 + co0 + k), a1 = *reinterpret_cast<const float4*>(s1 + co0 + k);
+            const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 w = *reinterpret_cast<const float4*>(wt + (k + kk) * 64 + cq * 4);
+                acc[0][0] = fmaf(av0[kk], w.x, acc[0][0]); acc[0][1] = fmaf(av0[kk], w.y, acc[0][1]);
+                acc[0][2] = fmaf(av0[kk], w.z, acc[0][2]); acc[0][3] = fmaf(av0[kk], w.w, acc[0][3]);
+                acc[1][0] = fmaf(av1[kk], w.x, acc[1][0]); acc[1][1] = fmaf(av1[kk], w.y, acc[1][1]);
+                acc[1][2] = fmaf(av1[kk], w.z, acc[1][2]); acc[1][3] = fmaf(av1[kk], w.w, acc[1][3]);
             }
         }
     }
@@ -430,7 +443,7 @@ __global__ void __launch_bounds__(256) k_roll_bwd_vec(RollBwdArgs A) {
 // dW of the broadcast channels: a 64 (co) x 64 (c) tile of one (source, along) for the three taps across, K = (b, pos) over a
 // slice of the batch; partial[split][source*3 + along][across][co][c] is reduced in a fixed order by k_roll_bwd_w_reduce.
 // grid ((Cout/64) * (C/64), 18, nsplit), block 256
-__global__ void __launch_bounds__(256) k_roll_bwd_w(RollBwdArgs A, float* __restrict__ partial, int nsplit) {
+__global__ void __launch_bounds__(256, 2) k_roll_bwd_w(RollBwdArgs A, float* __restrict__ partial, int nsplit) {
     __shared__ __align__(16) float sy3[3][16][64];
     __shared__ __align__(16) float vv[16][64];
     const int Cout = A.Cout, C = A.C, nct = C / 64;
@@ -440,34 +453,57 @@ __global__ void __launch_bounds__(256) k_roll_bwd_w(RollBwdArgs A, float* __rest
     const int b0 = static_cast<int>(static_cast<long long>(A.B) * blockIdx.z / nsplit), b1 = static_cast<int>(static_cast<long long>(A.B) * (blockIdx.z + 1) / nsplit);
     const int tc = threadIdx.x & 15, tco = threadIdx.x >> 4;
     float acc[3][4][4] = {};
-    for (int b = b0; b < b1; ++b) {
+    // K chunks of 16 positions, software pipelined: the NEXT chunk's operands (axis sum of dY, its first / last line, the forward axis
+    // sum) are requested into registers before the current chunk is multiplied, so their L2 latency hides behind the FMAs
+    const int nper = (S.L + 15) / 16, nchunk = (b1 - b0) * nper;
+    double pfull[4];
+    float pe0[4], pe1[4];
+    unsigned long long pfv[4];
+    bool pok[4], pvok[4];
+    auto request = [&](int ch) {
+        const int b = b0 + ch / nper, p0 = (ch % nper) * 16;
         const unsigned long long* fv = A.fsums + (static_cast<size_t>(b) * A.total_len + S.vec_off) * C;
-        for (int p0 = 0; p0 < S.L; p0 += 16) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
-                const int k = i >> 6, x = i & 63;
-                float v[3];
-                roll_sy3(A, S, b, p0 + k, co0 + x, v);
-                sy3[0][k][x] = v[0];
-                sy3[1][k][x] = v[1];
-                sy3[2][k][x] = v[2];
-                const int q = p0 + k + al - 1;
-                vv[k][x] = (p0 + k < S.L && q >= 0 && q < S.L)
-                               ? __ll2float_rn(static_cast<long long>(__ldg(fv + static_cast<size_t>(q) * C + c0 + x))) * S.vec_scale : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = threadIdx.x + j * 256, k = i >> 6, x = i & 63, pos = p0 + k, q = pos + al - 1;
+            pok[j] = pos < S.L;
+            pvok[j] = pok[j] && q >= 0 && q < S.L;
+            pfull[j] = 0.0;
+            pe0[j] = pe1[j] = 0.f;
+            pfv[j] = 0ull;
+            if (pok[j]) {
+                pfull[j] = A.sy[(static_cast<size_t>(b) * A.total_len + S.sy_off + pos) * A.Cout + co0 + x];
+                pe0[j] = roll_edge(A, S, b, pos, co0 + x, 0);
+                pe1[j] = roll_edge(A, S, b, pos, co0 + x, 1);
             }
-            __syncthreads();
+            if (pvok[j]) pfv[j] = __ldg(fv + static_cast<size_t>(q) * C + c0 + x);
+        }
+    };
+    if (nchunk > 0) request(0);
+    for (int ch = 0; ch < nchunk; ++ch) {
+        __syncthreads();                                     // the previous chunk has been multiplied
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = threadIdx.x + j * 256, k = i >> 6, x = i & 63;
+            const float full = static_cast<float>(pfull[j]);       // same arithmetic as roll_sy3
+            sy3[0][k][x] = pok[j] ? full - pe0[j] : 0.f;
+            sy3[1][k][x] = pok[j] ? full : 0.f;
+            sy3[2][k][x] = pok[j] ? full - pe1[j] : 0.f;
+            vv[k][x] = pvok[j] ? __ll2float_rn(static_cast<long long>(pfv[j])) * S.vec_scale : 0.f;
+        }
+        __syncthreads();
+        if (ch + 1 < nchunk) request(ch + 1);
 #pragma unroll 4
-            for (int k = 0; k < 16; ++k) {
-                const float4 v = *reinterpret_cast<const float4*>(&vv[k][tc * 4]);
+        for (int k = 0; k < 16; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(&vv[k][tc * 4]);
 #pragma unroll
-                for (int ac = 0; ac < 3; ++ac) {
-                    const float4 y = *reinterpret_cast<const float4*>(&sy3[ac][k][tco * 4]);
-                    const float yy[4] = {y.x, y.y, y.z, y.w};
+            for (int ac = 0; ac < 3; ++ac) {
+                const float4 y = *reinterpret_cast<const float4*>(&sy3[ac][k][tco * 4]);
+                const float yy[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        acc[ac][i][0] = fmaf(yy[i], v.x, acc[ac][i][0]); acc[ac][i][1] = fmaf(yy[i], v.y, acc[ac][i][1]);
-                        acc[ac][i][2] = fmaf(yy[i], v.z, acc[ac][i][2]); acc[ac][i][3] = fmaf(yy[i], v.w, acc[ac][i][3]);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    acc[ac][i][0] = fmaf(yy[i], v.x, acc[ac][i][0]); acc[ac][i][1] = fmaf(yy[i], v.y, acc[ac][i][1]);
+                    acc[ac][i][2] = fmaf(yy[i], v.z, acc[ac][i][2]); acc[ac][i][3] = fmaf(yy[i], v.w, acc[ac][i][3]);
                 }
             }
         }
