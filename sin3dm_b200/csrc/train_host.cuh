@@ -128,7 +128,7 @@ struct BackwardBuilder {
         const int strips = (std::max({d.rows[0], d.rows[1], d.rows[2]}) + kGsRows - 1) / kGsRows;
         const int Bv = B;
         add("k_grad_stage", 0.0, [=](cudaStream_t s) {
-            launch_plain(k_grad_stage, dim3(strips, 3, Bv), dim3(bx, ny), sizeof(float) * ny * A.C, s, A);
+            launch_plain(k_grad_stage, dim3(strips, 3, Bv), dim3(bx, ny), sizeof(float) * ny * kGsRows * A.C, s, A);
             LAUNCH_CHECK("k_grad_stage");
         });
         return S;

@@ -109,7 +109,7 @@ __device__ __forceinline__ void gnb_prologue(const GnBwdArgs& A, int b, int plan
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_gn_bwd_a(GnBwdArgs A) {
+__global__ void __launch_bounds__(256, 4) k_gn_bwd_a(GnBwdArgs A) {
     extern __shared__ float sm[];      // ca[C] cb[C] xm[C] xr[C] red[NY][2][C]
     __shared__ float mean[kGroups], rstd[kGroups];
     const int plane = blockIdx.y, b = blockIdx.z, C = A.C;
@@ -123,10 +123,21 @@ __global__ void __launch_bounds__(256) k_gn_bwd_a(GnBwdArgs A) {
     const float4 a4 = *reinterpret_cast<const float4*>(ca + tx * 4), b4 = *reinterpret_cast<const float4*>(cb + tx * 4);
     const float4 m4 = *reinterpret_cast<const float4*>(xm + tx * 4), r4 = *reinterpret_cast<const float4*>(xr + tx * 4);
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-    for (int px = p0 + ty; px < p1; px += NY) {      // (unrolling this loop by four costs registers / occupancy: 1.43 -> 1.82 ms per step, measured)
-        const size_t e = static_cast<size_t>(px) * C + tx * 4;
-        const float4 x = gnb_load_x(A, plane, sample_off, lo_off, e);
-        const float4 dy = __ldg(reinterpret_cast<const float4*>(A.dy.p[plane] + sample_off + e));
+    // (unrolling this loop by four costs registers / occupancy: 1.43 -> 1.82 ms per step, measured; instead the NEXT pixel's two
+    // loads are requested before the current pixel is used: two pixels in flight per thread for eight more registers)
+    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f), dyn = xn;
+    if (p0 + ty < p1) {
+        const size_t e = static_cast<size_t>(p0 + ty) * C + tx * 4;
+        xn = gnb_load_x(A, plane, sample_off, lo_off, e);
+        dyn = __ldg(reinterpret_cast<const float4*>(A.dy.p[plane] + sample_off + e));
+    }
+    for (int px = p0 + ty; px < p1; px += NY) {
+        const float4 x = xn, dy = dyn;
+        if (px + NY < p1) {
+            const size_t e = static_cast<size_t>(px + NY) * C + tx * 4;
+            xn = gnb_load_x(A, plane, sample_off, lo_off, e);
+            dyn = __ldg(reinterpret_cast<const float4*>(A.dy.p[plane] + sample_off + e));
+        }
         const float d0 = dy.x * silu_grad(fmaf(x.x, a4.x, b4.x)), d1 = dy.y * silu_grad(fmaf(x.y, a4.y, b4.y));
         const float d2 = dy.z * silu_grad(fmaf(x.z, a4.z, b4.z)), d3 = dy.w * silu_grad(fmaf(x.w, a4.w, b4.w));
         s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(256) k_gn_bwd_a(GnBwdArgs A) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_gn_bwd_b(GnBwdArgs A) {
+__global__ void __launch_bounds__(256, 4) k_gn_bwd_b(GnBwdArgs A) {
     extern __shared__ float sm[];      // ca cb xm xr k1[C] k2[C] k3[C] gs[2*32]
     __shared__ float mean[kGroups], rstd[kGroups];
     const int plane = blockIdx.y, b = blockIdx.z, C = A.C, cpg = C / kGroups;
@@ -178,11 +189,20 @@ __global__ void __launch_bounds__(256) k_gn_bwd_b(GnBwdArgs A) {
     const float4 q2 = *reinterpret_cast<const float4*>(k2 + tx * 4), q3 = *reinterpret_cast<const float4*>(k3 + tx * 4);
     const float* addp = A.add.p[plane];
     float* out = A.dx.p[plane];
-#pragma unroll 4
+    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f), dyn = xn;
+    if (p0 + ty < p1) {
+        const size_t e = static_cast<size_t>(p0 + ty) * C + tx * 4;
+        xn = gnb_load_x(A, plane, sample_off, lo_off, e);
+        dyn = __ldg(reinterpret_cast<const float4*>(A.dy.p[plane] + sample_off + e));
+    }
     for (int px = p0 + ty; px < p1; px += NY) {
         const size_t e = static_cast<size_t>(px) * C + tx * 4;
-        const float4 x = gnb_load_x(A, plane, sample_off, lo_off, e);
-        const float4 dy = __ldg(reinterpret_cast<const float4*>(A.dy.p[plane] + sample_off + e));
+        const float4 x = xn, dy = dyn;
+        if (px + NY < p1) {                              // the next pixel's loads are in flight while this one is processed
+            const size_t en = static_cast<size_t>(px + NY) * C + tx * 4;
+            xn = gnb_load_x(A, plane, sample_off, lo_off, en);
+            dyn = __ldg(reinterpret_cast<const float4*>(A.dy.p[plane] + sample_off + en));
+        }
         float4 o;
         o.x = dy.x * silu_grad(fmaf(x.x, a4.x, b4.x)) * a4.x - x.x * q3.x - q2.x;
         o.y = dy.y * silu_grad(fmaf(x.y, a4.y, b4.y)) * a4.y - x.y * q3.y - q2.y;
@@ -259,7 +279,7 @@ struct StageArgs {
     double* bc_sum;       // [B][C] (+= over planes) or nullptr
 };
 __global__ void __launch_bounds__(256) k_grad_stage(StageArgs A) {
-    extern __shared__ float sm[];      // red[NY][C]
+    extern __shared__ float sm[];      // red[NY][kGsRows][C]
     const int plane = blockIdx.y, b = blockIdx.z, C = A.C;
     const int rows = A.d.rows[plane], cols = A.d.cols[plane];
     const int tx = threadIdx.x, ty = threadIdx.y, NY = blockDim.y, tid = ty * blockDim.x + tx, nthr = blockDim.x * NY;
@@ -273,37 +293,46 @@ __global__ void __launch_bounds__(256) k_grad_stage(StageArgs A) {
     double* sb = A.sums + static_cast<size_t>(b) * A.total_len * C;
     double* srow = sb + static_cast<size_t>(A.seg_off[plane * 2 + 0]) * C;
     double* scol = sb + static_cast<size_t>(A.seg_off[plane * 2 + 1]) * C;
-    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < nr; ++r) {
-        float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = ty; c < cols; c += NY) {
-            const size_t e = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(gp + e));
-            store_split4(ph + e, ph + lo_off + e, v);
-            racc.x += v.x; racc.y += v.y; racc.z += v.z; racc.w += v.w;
-        }
-        float* cell = sm + ty * C + tx * 4;
-        cell[0] = racc.x; cell[1] = racc.y; cell[2] = racc.z; cell[3] = racc.w;
-        __syncthreads();
-        for (int i = tid; i < C; i += nthr) {
-            double acc = 0.0;
-            for (int y = 0; y < NY; ++y) acc += static_cast<double>(sm[y * C + i]);
-            atomicAdd(srow + static_cast<size_t>(r0 + r) * C + i, acc);
-        }
-        __syncthreads();
-        tot.x += racc.x; tot.y += racc.y; tot.z += racc.z; tot.w += racc.w;
-    }
-    // column sums of this strip: one thread per (column, channel quad)
+    // One pass over the strip: a thread takes a column at a time with all of its (<= 8) rows' loads in flight, splits and stores
+    // them, and keeps the row sums in registers; the column sum falls out of the same values (the strip used to be read twice, one
+    // row at a time with a block-wide reduction per row).  Same summation orders as before: results are bit-identical.
+    float4 racc[kGsRows];
+#pragma unroll
+    for (int r = 0; r < kGsRows; ++r) racc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = ty; c < cols; c += NY) {
+        float4 v[kGsRows];
+#pragma unroll
+        for (int r = 0; r < kGsRows; ++r)
+            v[r] = r < nr ? __ldg(reinterpret_cast<const float4*>(gp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < nr; ++r) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(gp + (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4));
-            cacc.x += v.x; cacc.y += v.y; cacc.z += v.z; cacc.w += v.w;
-        }
+#pragma unroll
+        for (int r = 0; r < kGsRows; ++r)
+            if (r < nr) {
+                const size_t e = (static_cast<size_t>(r0 + r) * cols + c) * C + tx * 4;
+                store_split4(ph + e, ph + lo_off + e, v[r]);
+                racc[r].x += v[r].x; racc[r].y += v[r].y; racc[r].z += v[r].z; racc[r].w += v[r].w;
+                cacc.x += v[r].x; cacc.y += v[r].y; cacc.z += v[r].z; cacc.w += v[r].w;
+            }
         double* p = scol + static_cast<size_t>(c) * C + tx * 4;
         atomicAdd(p, static_cast<double>(cacc.x)); atomicAdd(p + 1, static_cast<double>(cacc.y));
         atomicAdd(p + 2, static_cast<double>(cacc.z)); atomicAdd(p + 3, static_cast<double>(cacc.w));
     }
+    // row sums: sm[ty][r][C], added over ty in a fixed order
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kGsRows; ++r) {
+        float* cellr = sm + (static_cast<size_t>(ty) * kGsRows + r) * C + tx * 4;
+        cellr[0] = racc[r].x; cellr[1] = racc[r].y; cellr[2] = racc[r].z; cellr[3] = racc[r].w;
+        if (r < nr) { tot.x += racc[r].x; tot.y += racc[r].y; tot.z += racc[r].z; tot.w += racc[r].w; }
+    }
+    __syncthreads();
+    for (int i = tid; i < nr * C; i += nthr) {
+        const int r = i / C, ch = i - r * C;
+        double acc = 0.0;
+        for (int y = 0; y < NY; ++y) acc += static_cast<double>(sm[(static_cast<size_t>(y) * kGsRows + r) * C + ch]);
+        atomicAdd(srow + static_cast<size_t>(r0 + r) * C + ch, acc);
+    }
+    __syncthreads();
     // per-channel total of the strip
     float* cell = sm + ty * C + tx * 4;
     cell[0] = tot.x; cell[1] = tot.y; cell[2] = tot.z; cell[3] = tot.w;
