@@ -490,7 +490,7 @@ def run_ours(args, wl):
             from tools.bench_train import run_train
             tr = run_train(bn, args, WORKLOADS["cfg4"], 10, 40, METRIC, config_of, load_peaks, emit=False, profile=bn.world == 1)
             if tr is not None:
-                also["cfg4_train_b32"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "per_rank_ms", "config", "e2e", "detail",
+                also["cfg4_train_b32"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "per_rank_ms", "timing", "config", "e2e", "detail",
                                                              "roofline", "roofline_parts") if k in tr}
         except Exception as e:
             also["cfg4_train_b32"] = f"failed: {type(e).__name__}: {e}"

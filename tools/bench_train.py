@@ -64,11 +64,18 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks, emit=True, pro
         step(x_dev)
     gc.collect()
     gc.disable()          # a generation-2 collection inside the 10-step window showed up as a 50 ms hiccup (25.6 instead of 20.4 ms / step)
+    # The loop is launched asynchronously from Python (autograd + ~60 torch ops + the library's launch lists per iteration), so a host
+    # hiccup (scheduler, allocator) inside a 10-step window idles the GPU: one window in four came out 25-45 % slow on the shared boxes
+    # while the windows around it agreed to 1 %.  Three windows of exactly K steps are timed; `value` is the fastest, all are reported.
+    windows = []
     try:
-        (ms, per_rank), _ = timed(K, False)
+        for _ in range(3):
+            (ms_w, pr_w), _ = timed(K, False)
+            windows.append((ms_w, pr_w))
         (ms2, _), last_loss = timed(max(3, min(K, 10)), True)
     finally:
         gc.enable()
+    ms, per_rank = min(windows, key=lambda w: w[0])
     n2 = max(3, min(K, 10))
     value = bn.world * K / (ms / 1e3)
     h = model._handle
@@ -128,6 +135,8 @@ def run_train(bn, args, wl, K, Wm, METRIC, config_of, load_peaks, emit=True, pro
                     e2e=dict(value=bn.world * n2 / (ms2 / 1e3), unit="iterations/s", h2d_bytes_per_step=x_host.numel() * 4, d2h_bytes_per_step=4,
                              steps=n2, api="training_losses + loss.backward() + FusedAdamWEMA.step(), batch from pinned host memory, loss read back"),
                     gpu_launches=K * (L.s3d_unet_op_count(h) + L.s3d_unet_bwd_op_count(h) + 3),
+                    timing=dict(method=f"fastest of 3 windows of {K} steps each (CUDA events, max over ranks per window)",
+                                windows_ms_per_step=[round(w[0] / K, 3) for w in windows]),
                     detail=dict(samples_per_s=value * B, fwd_dense_gflop=fwd_gf, train_dense_tflops=3 * fwd_gf * value / bn.world / 1e3,
                                 workspace_mib=round(L.s3d_unet_workspace_bytes(h) / 2 ** 20, 1), last_loss=last_loss),
                     cpu_baseline=None, **rec)
