@@ -450,7 +450,7 @@ struct BackwardBuilder {
                 Fl.film = Pp->film;
                 Fl.film_row = Pp->film_row;
             }
-            launch_plain(k_gn_bwd_fin, dim3(1), dim3(256), 0, s, Fl);
+            launch_plain(k_gn_bwd_fin, dim3(std::max(1, (Fl.B * Fl.C + 255) / 256)), dim3(256), 0, s, Fl);
             LAUNCH_CHECK("k_gn_bwd_fin");
         });
         return dx;

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256, 4) k_gn_bwd_b(GnBwdArgs A) {
 
 // Parameter / FiLM gradients of one norm site from the pass-A sums (still multiplied by the loss scale).
 //   dgamma[plane][c] = sum_b (1+sc) P2 ; dbeta = sum_b (1+sc) P1 ; dscale[b][c] += gamma P2 + beta P1 ; dshift[b][c] += P1 (over planes)
-// grid 1, block 256
+// grid ceil(B*C / 256), block 256 (grid-stride loops)
 struct GnFinArgs {
     const double* psum;      // [B][3][C][2]
     TriCF gamma, beta;
@@ -231,9 +231,11 @@ struct GnFinArgs {
 };
 __global__ void __launch_bounds__(256) k_gn_bwd_fin(GnFinArgs A) {
     const int C = A.C;
-    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;      // grid-stride: a few CTAs instead of one
+    for (int i = gtid; i < 3 * C; i += gstride) {
         const int plane = i / C, c = i - plane * C;
         double dg = 0.0, db = 0.0;
+#pragma unroll 8
         for (int b = 0; b < A.B; ++b) {
             const double* p = A.psum + ((static_cast<size_t>(b) * 3 + plane) * C + c) * 2;
             double sc = 1.0;
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(256) k_gn_bwd_fin(GnFinArgs A) {
         A.dbeta[plane][c] = static_cast<float>(db);
     }
     if (A.film && A.dfilm) {
-        for (int i = threadIdx.x; i < A.B * C; i += blockDim.x) {
+        for (int i = gtid; i < A.B * C; i += gstride) {
             const int b = i / C, c = i - b * C;
             double dsc = 0.0, dsh = 0.0;
             for (int plane = 0; plane < 3; ++plane) {
@@ -788,7 +790,7 @@ struct InconvBwdArgs {
 };
 // same tiling and tile walk (grid (gx, B, 3)); thread = (pixel, output-channel quad): dw[co][c] += dh0[px][co] x[c][px]
 template <int NQ>
-__global__ void __launch_bounds__(256) k_inconv_wgrad(InconvBwdArgs A) {
+__global__ void __launch_bounds__(256, 2) k_inconv_wgrad(InconvBwdArgs A) {
     constexpr int PPP = 256 / NQ, NPASS = kBndPx / PPP, C0 = NQ * 4;
     __shared__ __align__(16) float xs[kMaxCf][kBndPx];
     __shared__ float dwacc[C0][kMaxCf];
@@ -819,17 +821,27 @@ __global__ void __launch_bounds__(256) k_inconv_wgrad(InconvBwdArgs A) {
             xs[ch][i] = (ch < Cf && r < rows && c < cols) ? __ldg(A.x + (static_cast<size_t>(b) * Cf + ch) * hw + composed_offset(plane, r, c, A.H, A.W, Wc)) : 0.f;
         }
         __syncthreads();
-#pragma unroll 2
-        for (int pass = 0; pass < NPASS; ++pass) {
-            const int i = pass * PPP + pslot, r = pix_r(i), c = pix_c(i);
-            if (r >= rows || c >= cols) continue;
-            const float4 dv = __ldg(reinterpret_cast<const float4*>(dp + (static_cast<size_t>(r) * cols + c) * C0));
-            dbr.x += dv.x; dbr.y += dv.y; dbr.z += dv.z; dbr.w += dv.w;
+        // four pixels' gradient loads in flight per thread (a pixel outside the plane contributes zeros)
+        constexpr int NB = NPASS < 4 ? NPASS : 4;
 #pragma unroll
-            for (int ch = 0; ch < kMaxCf; ++ch) {
-                const float xv = xs[ch][i];
-                dwr[ch].x = fmaf(dv.x, xv, dwr[ch].x); dwr[ch].y = fmaf(dv.y, xv, dwr[ch].y);
-                dwr[ch].z = fmaf(dv.z, xv, dwr[ch].z); dwr[ch].w = fmaf(dv.w, xv, dwr[ch].w);
+        for (int p0 = 0; p0 < NPASS; p0 += NB) {
+            float4 dv[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                const int i = (p0 + k) * PPP + pslot, r = pix_r(i), c = pix_c(i);
+                dv[k] = (r < rows && c < cols) ? __ldg(reinterpret_cast<const float4*>(dp + (static_cast<size_t>(r) * cols + c) * C0))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                const int i = (p0 + k) * PPP + pslot;
+                dbr.x += dv[k].x; dbr.y += dv[k].y; dbr.z += dv[k].z; dbr.w += dv[k].w;
+#pragma unroll
+                for (int ch = 0; ch < kMaxCf; ++ch) {
+                    const float xv = xs[ch][i];
+                    dwr[ch].x = fmaf(dv[k].x, xv, dwr[ch].x); dwr[ch].y = fmaf(dv[k].y, xv, dwr[ch].y);
+                    dwr[ch].z = fmaf(dv[k].z, xv, dwr[ch].z); dwr[ch].w = fmaf(dv[k].w, xv, dwr[ch].w);
+                }
             }
         }
     }
