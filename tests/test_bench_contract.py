@@ -37,3 +37,27 @@ def test_reference_arm_other_ranks_exit_without_work():
     r = _run(dict(RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29599"), args=())
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_contract_line():
+    """The GPU arm through the same command line the driver uses (short: no secondary records, no CPU baseline legs)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "5", "--warmup", "3", "--no-also", "--no-cpu-baseline"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert "impl" not in line or line["impl"] != "reference"
+    assert line["unit"] == "steps/s" and line["n_gpus"] == 1 and line["steps"] == 5 and line["warmup"] == 3 and line["value"] > 100
+    assert line["scaling"] == "weak" and line["higher_is_better"] is True and line["data"] == "synthetic" and line["vs_baseline"] is None
+    assert line["config"]["workload"].startswith("cfg2") and "model" not in line["config"]
+    assert line["gpu_launches"] == 5 * line["launches_per_step"] and line["launches_per_step"] >= 10
+    e = line["e2e"]
+    assert e["value"] > 100 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != line["value"]
+    rf = line["roofline"]
+    assert rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s" and 0 < rf["frac"] < 1 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    clk = line["clocks"]
+    assert clk is None or {"sm_mhz", "sm_max_mhz", "reasons"} <= set(clk)
+    assert line["detail"]["graph_captures_in_timed_region"] == 0
